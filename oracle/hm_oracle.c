@@ -1,0 +1,329 @@
+/* TEST INFRASTRUCTURE — NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this.  The product library (libhmb200.so) never links, loads or calls it.
+ *
+ * Plain-C restatement of the HM-16.5 (xkfz007/video_codecs, hm-16.5rc1) integer-pel full search, quarter-pel
+ * refinement and block-distortion arithmetic.  Written from the behaviour of the reference, not from its text;
+ * every function cites the reference lines whose results it must reproduce (paths relative to
+ * hm-16.5rc1/source/Lib/).  PARITY IS PINNED: tests/test_oracle_vs_reference.py checks every function below
+ * against the unmodified reference compiled into oracle/_ref/libhmref.so, and tests/golden/ holds vectors
+ * generated from that reference (tests/golden/make_golden.py) for machines where /root/reference is absent.
+ *
+ * Types follow the default reference build (TLibCommon/TypeDef.h:219-230): Pel = int16, Distortion = uint32.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+typedef struct { int32_t pu_x, pu_y, w, h, lt_x, lt_y, rb_x, rb_y, pred_x, pred_y; uint32_t lambda_cost; int32_t reserved; } hmo_job;
+typedef struct { int32_t mv_x, mv_y; uint32_t sad; int32_t half_x, half_y, qter_x, qter_y; uint32_t frac_cost; } hmo_result;
+
+/* ---------------------------------------------------------------- MV rate ------------------------------------- */
+
+/* TLibCommon/TComRdCost.cpp:279-292  xGetExpGolombNumberOfBits: 1 + 2*floor(log2(v<=0 ? -2v+1 : 2v)) */
+uint32_t hmo_eg_bits(int32_t v)
+{
+  uint32_t t = (v <= 0) ? (((uint32_t)(-v)) << 1) + 1u : ((uint32_t)v << 1);
+  uint32_t len = 1;
+  while (t != 1u) { t >>= 1; len += 2; }
+  return len;
+}
+
+/* TLibCommon/TComRdCost.h:184-188  getBits(x, y) with m_mvPredictor, m_iCostScale */
+uint32_t hmo_mv_bits(int x, int y, int pred_x, int pred_y, int scale)
+{
+  return hmo_eg_bits((int32_t)(x * (1 << scale)) - pred_x) + hmo_eg_bits((int32_t)(y * (1 << scale)) - pred_y);
+}
+
+/* TLibCommon/TComRdCost.h:172-183  getCost: (m_uiCost * bits) >> 16, all in 32-bit unsigned (wraps) */
+uint32_t hmo_mv_cost(uint32_t lambda_cost, uint32_t bits)
+{
+  return (uint32_t)(lambda_cost * bits) >> 16;
+}
+
+/* ---------------------------------------------------------------- SAD / SSE / HAD ----------------------------- */
+
+static int is_sized_sad_width(int w)
+{
+  return w == 4 || w == 8 || w == 12 || w == 16 || w == 24 || w == 32 || w == 48 || w == 64;
+}
+
+/* TLibCommon/TComRdCost.cpp:489-953 (xGetSAD4..64, 12/24/48): rows 0, 2^s, 2*2^s, ...; (sum << s) >> (bd-8).
+ * TLibCommon/TComRdCost.cpp:461-487 (generic xGetSAD, other widths): every row, sub_shift ignored. */
+uint32_t hmo_sad(const int16_t* org, int so, const int16_t* cur, int sc, int w, int h, int bit_depth, int sub_shift)
+{
+  uint32_t sum = 0;
+  int step = is_sized_sad_width(w) ? (1 << sub_shift) : 1;
+  int shl  = is_sized_sad_width(w) ? sub_shift : 0;
+  for (int y = 0; y < h; y += step)
+    for (int x = 0; x < w; x++)
+      sum += (uint32_t)abs((int)org[y * so + x] - (int)cur[y * sc + x]);
+  sum <<= shl;
+  return sum >> (bit_depth - 8);
+}
+
+/* TLibCommon/TComRdCost.cpp:959-1304: per-sample ((d*d) >> 2(bd-8)) summed in uint32 */
+uint32_t hmo_sse(const int16_t* org, int so, const int16_t* cur, int sc, int w, int h, int bit_depth)
+{
+  uint32_t sum = 0, sh = (uint32_t)((bit_depth - 8) << 1);
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+    {
+      int32_t d = (int32_t)org[y * so + x] - (int32_t)cur[y * sc + x];
+      sum += (uint32_t)((d * d) >> sh);
+    }
+  return sum;
+}
+
+/* Un-normalised n x n Hadamard of the difference block, sum of absolute coefficients.  SURVEY.md App. A.10:
+ * the reference's butterfly order (TComRdCost.cpp:1332-1523) only permutes / sign-flips coefficients. */
+static uint32_t hadamard_abs_sum(const int16_t* org, int so, const int16_t* cur, int sc, int n)
+{
+  int32_t m[64];
+  for (int y = 0; y < n; y++)
+    for (int x = 0; x < n; x++)
+      m[y * n + x] = (int32_t)org[y * so + x] - (int32_t)cur[y * sc + x];
+  for (int len = 1; len < n; len <<= 1)                 /* rows */
+    for (int y = 0; y < n; y++)
+      for (int b = 0; b < n; b += 2 * len)
+        for (int k = 0; k < len; k++)
+        {
+          int32_t a0 = m[y * n + b + k], a1 = m[y * n + b + k + len];
+          m[y * n + b + k] = a0 + a1; m[y * n + b + k + len] = a0 - a1;
+        }
+  for (int len = 1; len < n; len <<= 1)                 /* columns */
+    for (int x = 0; x < n; x++)
+      for (int b = 0; b < n; b += 2 * len)
+        for (int k = 0; k < len; k++)
+        {
+          int32_t a0 = m[(b + k) * n + x], a1 = m[(b + k + len) * n + x];
+          m[(b + k) * n + x] = a0 + a1; m[(b + k + len) * n + x] = a0 - a1;
+        }
+  uint32_t s = 0;
+  for (int i = 0; i < n * n; i++) s += (uint32_t)abs(m[i]);
+  return s;
+}
+
+/* TLibCommon/TComRdCost.cpp:1526-1593 xGetHADs: 8x8 tiles iff both dims %8==0 ((s+2)>>2 per tile, :1520),
+ * else 4x4 tiles iff %4 ((s+1)>>1, :1423), else 2x2 (no rounding, :1310-1330); total >> (bd-8). */
+uint32_t hmo_had(const int16_t* org, int so, const int16_t* cur, int sc, int w, int h, int bit_depth)
+{
+  uint32_t sum = 0;
+  int n = (w % 8 == 0 && h % 8 == 0) ? 8 : (w % 4 == 0 && h % 4 == 0) ? 4 : 2;
+  for (int y = 0; y < h; y += n)
+    for (int x = 0; x < w; x += n)
+    {
+      uint32_t s = hadamard_abs_sum(org + y * so + x, so, cur + y * sc + x, sc, n);
+      sum += (n == 8) ? ((s + 2) >> 2) : (n == 4) ? ((s + 1) >> 1) : s;
+    }
+  return sum >> (bit_depth - 8);
+}
+
+/* kind: 0 SAD (integer ME), 1 SSE, 2 HAD, 3 SAD (sub-pel, DF_SADS*: same arithmetic as kind 0) */
+uint32_t hmo_dist(int kind, const int16_t* org, int so, const int16_t* cur, int sc, int w, int h, int bit_depth, int sub_shift)
+{
+  if (kind == 1) return hmo_sse(org, so, cur, sc, w, h, bit_depth);
+  if (kind == 2) return hmo_had(org, so, cur, sc, w, h, bit_depth);
+  return hmo_sad(org, so, cur, sc, w, h, bit_depth, sub_shift);
+}
+
+/* ---------------------------------------------------------------- search window -------------------------------- */
+
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* TLibCommon/TComDataCU.cpp:2788-2801 clipMv: quarter-pel MV clipped against the picture +- (8, maxCU+8) relative
+ * to the CU origin (cu_x, cu_y). */
+void hmo_clip_mv(int* mv_x, int* mv_y, int cu_x, int cu_y, int pic_w, int pic_h, int max_cu_w, int max_cu_h)
+{
+  int hmax = (pic_w + 8 - cu_x - 1) * 4, hmin = (-max_cu_w - 8 - cu_x + 1) * 4;
+  int vmax = (pic_h + 8 - cu_y - 1) * 4, vmin = (-max_cu_h - 8 - cu_y + 1) * 4;
+  *mv_x = clampi(*mv_x, hmin, hmax);
+  *mv_y = clampi(*mv_y, vmin, vmax);
+}
+
+static int asr2(int v) { return (v >= 0) ? (v >> 2) : -((-v + 3) >> 2); }   /* floor(v / 4): arithmetic shift of a Short */
+
+/* TLibEncoder/TEncSearch.cpp:3765-3781 xSetSearchRange: clip(pred) -+ (range << 2), clip both corners, >> 2 */
+void hmo_search_range(int pred_x, int pred_y, int range, int cu_x, int cu_y, int pic_w, int pic_h, int max_cu_w, int max_cu_h,
+                      int* lt_x, int* lt_y, int* rb_x, int* rb_y)
+{
+  int px = pred_x, py = pred_y;
+  hmo_clip_mv(&px, &py, cu_x, cu_y, pic_w, pic_h, max_cu_w, max_cu_h);
+  int lx = (int16_t)(px - (range << 2)), ly = (int16_t)(py - (range << 2));
+  int rx = (int16_t)(px + (range << 2)), ry = (int16_t)(py + (range << 2));
+  hmo_clip_mv(&lx, &ly, cu_x, cu_y, pic_w, pic_h, max_cu_w, max_cu_h);
+  hmo_clip_mv(&rx, &ry, cu_x, cu_y, pic_w, pic_h, max_cu_w, max_cu_h);
+  *lt_x = asr2(lx); *lt_y = asr2(ly); *rb_x = asr2(rx); *rb_y = asr2(ry);
+}
+
+/* ---------------------------------------------------------------- integer full search -------------------------- */
+
+/* TLibEncoder/TEncSearch.cpp:3786-3843 xPatternSearch.  ref_at_pu = reference sample co-located with the PU's
+ * top-left.  fen != 0 reproduces getUseFastEnc(): iSubShift = 1 when the PU has more than 8 rows (:3804-3810).
+ * Scan y-outer / x-inner, strict '<' (first wins); cost scale 2 (:3722); returned SAD excludes the MV cost (:3841). */
+void hmo_pattern_search(const int16_t* org, int so, int w, int h, int bit_depth,
+                        const int16_t* ref_at_pu, int sr, int lt_x, int lt_y, int rb_x, int rb_y,
+                        uint32_t lambda_cost, int pred_x, int pred_y, int fen,
+                        int* mv_x, int* mv_y, uint32_t* sad_out)
+{
+  uint32_t best = 0xFFFFFFFFu; int bx = 0, by = 0;
+  int sub = (fen && h > 8) ? 1 : 0;
+  for (int y = lt_y; y <= rb_y; y++)
+    for (int x = lt_x; x <= rb_x; x++)
+    {
+      uint32_t c = hmo_sad(org, so, ref_at_pu + y * sr + x, sr, w, h, bit_depth, sub)
+                 + hmo_mv_cost(lambda_cost, hmo_mv_bits(x, y, pred_x, pred_y, 2));
+      if (c < best) { best = c; bx = x; by = y; }
+    }
+  *mv_x = bx; *mv_y = by;
+  *sad_out = best - hmo_mv_cost(lambda_cost, hmo_mv_bits(bx, by, pred_x, pred_y, 2));
+}
+
+/* ---------------------------------------------------------------- interpolation -------------------------------- */
+
+/* TLibCommon/TComInterpolationFilter.cpp:57-63 m_lumaFilter */
+static const int k_luma_taps[4][8] = {
+  {  0, 0,   0, 64,  0,   0, 0,  0 },
+  { -1, 4, -10, 58, 17,  -5, 1,  0 },
+  { -1, 4, -11, 40, 40, -11, 4, -1 },
+  {  0, 1,  -5, 17, 58, -10, 4, -1 } };
+
+/* One sample of the separable luma interpolation at integer position p (pointer into a padded plane) and
+ * fractional phase (fx, fy) in quarter samples.  Horizontal pass first into the 14-bit intermediate domain, then
+ * vertical pass back to pixels, exactly as the reference chains filterHor(isLast=false) and
+ * filterVer(isFirst=false, isLast=true) for every plane it builds, including phase 0
+ * (TLibCommon/TComInterpolationFilter.cpp:94-154 filterCopy, :172-257 filter<>, headRoom = max(2, 14 - bd),
+ *  IF_INTERNAL_OFFS = 8192, TLibCommon/TComInterpolationFilter.h:47-51). */
+static int16_t interp_sample(const int16_t* p, int stride, int fx, int fy, int bit_depth)
+{
+  int head = 14 - bit_depth; if (head < 2) head = 2;
+  int16_t col[8];
+  int r0 = (fy == 0) ? 0 : -3, r1 = (fy == 0) ? 0 : 4;
+  for (int r = r0; r <= r1; r++)
+  {
+    const int16_t* q = p + r * stride;
+    int16_t v;
+    if (fx == 0)
+      v = (int16_t)((int16_t)(q[0] << head) - 8192);                       /* filterCopy, isFirst && !isLast */
+    else
+    {
+      int sum = 0;
+      for (int t = 0; t < 8; t++) sum += q[t - 3] * k_luma_taps[fx][t];
+      int shift = 6 - head;
+      v = (int16_t)((sum + (-8192 * (1 << shift))) >> shift);              /* filter<8,false,true,false> */
+    }
+    col[r + 3] = v;
+  }
+  int maxv = (1 << bit_depth) - 1;
+  int val;
+  if (fy == 0)
+    val = (int16_t)((col[3] + 8192 + (1 << (head - 1))) >> head);          /* filterCopy, !isFirst && isLast */
+  else
+  {
+    int sum = 0;
+    for (int t = 0; t < 8; t++) sum += col[t] * k_luma_taps[fy][t];
+    int shift = 6 + head;
+    val = (int16_t)((sum + (1 << (shift - 1)) + (8192 << 6)) >> shift);    /* filter<8,true,false,true> */
+  }
+  if (val < 0) val = 0;
+  if (val > maxv) val = maxv;
+  return (int16_t)val;
+}
+
+/* Interpolated W x H block at quarter-pel displacement (qx, qy) from `base` (integer-MV-compensated block origin). */
+static void interp_block(const int16_t* base, int stride, int qx, int qy, int w, int h, int bit_depth, int16_t* dst /* w*h */)
+{
+  int ix = asr2(qx), iy = asr2(qy), fx = qx & 3, fy = qy & 3;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+      dst[y * w + x] = interp_sample(base + (y + iy) * stride + x + ix, stride, fx, fy, bit_depth);
+}
+
+/* TLibEncoder/TEncSearch.cpp:51-75 candidate orders */
+static const int k_refine_h[9][2] = { {0,0},{0,-1},{0,1},{-1,0},{1,0},{-1,-1},{1,-1},{-1,1},{1,1} };
+static const int k_refine_q[9][2] = { {0,0},{0,-1},{0,1},{-1,-1},{1,-1},{-1,0},{1,0},{-1,1},{1,1} };
+
+/* TLibEncoder/TEncSearch.cpp:4240-4276 xPatternSearchFracDIF with :808-861 xPatternRefinement and the planes of
+ * :5338-5539 xExtDIFUpSamplingH/Q.  Each of the reference's pre-filtered planes, at the offset xPatternRefinement
+ * applies to it (:830-840), is the block interpolated at quarter-pel displacement 2*half (stage 1) or
+ * 2*half + qter (stage 2) from the integer MV; here each candidate block is interpolated directly.
+ * Cost: distortion + getCost at scale 1 (half, :3746) / scale 0 (quarter, :4267) of (candidate + accumulated MV);
+ * strict '<', first in table order wins.  Distortion is HAD when use_had (HadamardME && !lossless), else SAD. */
+void hmo_frac_search(const int16_t* org, int so, int w, int h, int bit_depth,
+                     const int16_t* ref_at_pu, int sr, int mv_x, int mv_y,
+                     uint32_t lambda_cost, int pred_x, int pred_y, int use_had,
+                     int* half_x, int* half_y, int* qter_x, int* qter_y, uint32_t* cost_out)
+{
+  const int16_t* base = ref_at_pu + mv_y * sr + mv_x;
+  int16_t* blk = (int16_t*)malloc(sizeof(int16_t) * (size_t)w * (size_t)h);
+  uint32_t best = 0xFFFFFFFFu; int bi = 0;
+  for (int i = 0; i < 9; i++)
+  {
+    int cx = k_refine_h[i][0], cy = k_refine_h[i][1];
+    interp_block(base, sr, 2 * cx, 2 * cy, w, h, bit_depth, blk);
+    uint32_t d = use_had ? hmo_had(org, so, blk, w, w, h, bit_depth) : hmo_sad(org, so, blk, w, w, h, bit_depth, 0);
+    d += hmo_mv_cost(lambda_cost, hmo_mv_bits(cx + 2 * mv_x, cy + 2 * mv_y, pred_x, pred_y, 1));
+    if (d < best) { best = d; bi = i; }
+  }
+  int hx = k_refine_h[bi][0], hy = k_refine_h[bi][1];
+  best = 0xFFFFFFFFu; bi = 0;
+  for (int i = 0; i < 9; i++)
+  {
+    int cx = k_refine_q[i][0], cy = k_refine_q[i][1];
+    interp_block(base, sr, 2 * hx + cx, 2 * hy + cy, w, h, bit_depth, blk);
+    uint32_t d = use_had ? hmo_had(org, so, blk, w, w, h, bit_depth) : hmo_sad(org, so, blk, w, w, h, bit_depth, 0);
+    d += hmo_mv_cost(lambda_cost, hmo_mv_bits(cx + 2 * (2 * mv_x + hx), cy + 2 * (2 * mv_y + hy), pred_x, pred_y, 0));
+    if (d < best) { best = d; bi = i; }
+  }
+  free(blk);
+  *half_x = hx; *half_y = hy; *qter_x = k_refine_q[bi][0]; *qter_y = k_refine_q[bi][1]; *cost_out = best;
+}
+
+/* ---------------------------------------------------------------- planes --------------------------------------- */
+
+/* TLibCommon/TComPicYuv.cpp:197-242 extendPicBorder: replicate edge samples into the margins.
+ * plane0 points at sample (0,0); the buffer holds margin_x / margin_y samples on every side. */
+void hmo_extend_border(int16_t* plane0, int stride, int w, int h, int margin_x, int margin_y)
+{
+  for (int y = 0; y < h; y++)
+  {
+    int16_t* row = plane0 + y * stride;
+    for (int x = 1; x <= margin_x; x++) { row[-x] = row[0]; row[w - 1 + x] = row[w - 1]; }
+  }
+  for (int y = 1; y <= margin_y; y++)
+  {
+    memcpy(plane0 - y * stride - margin_x, plane0 - margin_x, sizeof(int16_t) * (size_t)(w + 2 * margin_x));
+    memcpy(plane0 + (h - 1 + y) * stride - margin_x, plane0 + (h - 1) * stride - margin_x, sizeof(int16_t) * (size_t)(w + 2 * margin_x));
+  }
+}
+
+/* ---------------------------------------------------------------- job lists ------------------------------------ */
+
+/* Executes a job list the way TEncSearch::xMotionEstimation (TLibEncoder/TEncSearch.cpp:3663-3760) drives the two
+ * searches: integer search at cost scale 2, then quarter-pel refinement.  cur0 / ref0 point at luma sample (0,0) of
+ * the current (original) and padded reference planes.  Returns CPU seconds (clock()). */
+double hmo_run_jobs(const int16_t* cur0, int cur_stride, const int16_t* ref0, int ref_stride, int bit_depth,
+                    const hmo_job* jobs, int njobs, int fen, int use_had, int do_frac, hmo_result* out)
+{
+  clock_t t0 = clock();
+  for (int i = 0; i < njobs; i++)
+  {
+    const hmo_job* j = &jobs[i];
+    const int16_t* org = cur0 + j->pu_y * cur_stride + j->pu_x;
+    const int16_t* ref = ref0 + j->pu_y * ref_stride + j->pu_x;
+    hmo_result r; memset(&r, 0, sizeof(r));
+    int mx, my;
+    hmo_pattern_search(org, cur_stride, j->w, j->h, bit_depth, ref, ref_stride, j->lt_x, j->lt_y, j->rb_x, j->rb_y,
+                       j->lambda_cost, j->pred_x, j->pred_y, fen, &mx, &my, &r.sad);
+    r.mv_x = mx; r.mv_y = my;
+    if (do_frac)
+    {
+      int hx, hy, qx, qy;
+      hmo_frac_search(org, cur_stride, j->w, j->h, bit_depth, ref, ref_stride, mx, my, j->lambda_cost, j->pred_x, j->pred_y,
+                      use_had, &hx, &hy, &qx, &qy, &r.frac_cost);
+      r.half_x = hx; r.half_y = hy; r.qter_x = qx; r.qter_y = qy;
+    }
+    out[i] = r;
+  }
+  return (double)(clock() - t0) / CLOCKS_PER_SEC;
+}

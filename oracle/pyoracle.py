@@ -1,0 +1,195 @@
+"""TEST INFRASTRUCTURE — ctypes front-ends for the two checkers, with one API:
+
+  Oracle()     -> oracle/_build/libhmoracle.so   (C restatement, oracle/hm_oracle.c)
+  Reference()  -> oracle/_ref/libhmref.so        (unmodified HM-16.5 behind oracle/ref_harness.cpp)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
+All sample buffers are numpy int16 ("Pel", TLibCommon/TypeDef.h:219); jobs/results use JOB_DTYPE/RESULT_DTYPE,
+which match hmb200_pu_job / hmb200_pu_result in include/hmb200.h field for field.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build_oracle as _b
+
+JOB_DTYPE = np.dtype([("pu_x", "<i4"), ("pu_y", "<i4"), ("w", "<i4"), ("h", "<i4"),
+                      ("lt_x", "<i4"), ("lt_y", "<i4"), ("rb_x", "<i4"), ("rb_y", "<i4"),
+                      ("pred_x", "<i4"), ("pred_y", "<i4"), ("lambda_cost", "<u4"), ("reserved", "<i4")])
+RESULT_DTYPE = np.dtype([("mv_x", "<i4"), ("mv_y", "<i4"), ("sad", "<u4"),
+                         ("half_x", "<i4"), ("half_y", "<i4"), ("qter_x", "<i4"), ("qter_y", "<i4"),
+                         ("frac_cost", "<u4")])
+
+_p16 = C.POINTER(C.c_int16)
+_pi = C.POINTER(C.c_int)
+_pu = C.POINTER(C.c_uint32)
+
+
+def _ptr(a, off=0):
+    """Pointer to element `off` of a C-contiguous int16 array (off may address the interior of a padded plane)."""
+    assert a.dtype == np.int16 and a.flags["C_CONTIGUOUS"]
+    return C.cast(a.ctypes.data + 2 * int(off), _p16)
+
+
+class _Base:
+    """Shared Python surface.  `org`/`cur`/`ref` arguments are (array, element offset, stride) triples."""
+
+    def dist(self, kind, org, cur, w, h, bit_depth=8, sub_shift=0):
+        raise NotImplementedError
+
+    def sad(self, org, cur, w, h, bit_depth=8, sub_shift=0):
+        return self.dist(0, org, cur, w, h, bit_depth, sub_shift)
+
+    def sse(self, org, cur, w, h, bit_depth=8):
+        return self.dist(1, org, cur, w, h, bit_depth, 0)
+
+    def had(self, org, cur, w, h, bit_depth=8):
+        return self.dist(2, org, cur, w, h, bit_depth, 0)
+
+
+class Oracle(_Base):
+    def __init__(self, fen=1, hadme=1):
+        self.fen, self.hadme = int(fen), int(hadme)
+        L = self.lib = C.CDLL(_b.build_oracle())
+        L.hmo_eg_bits.restype = C.c_uint32
+        L.hmo_eg_bits.argtypes = [C.c_int32]
+        L.hmo_mv_bits.restype = C.c_uint32
+        L.hmo_mv_bits.argtypes = [C.c_int] * 5
+        L.hmo_mv_cost.restype = C.c_uint32
+        L.hmo_mv_cost.argtypes = [C.c_uint32, C.c_uint32]
+        L.hmo_dist.restype = C.c_uint32
+        L.hmo_dist.argtypes = [C.c_int, _p16, C.c_int, _p16, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.hmo_search_range.restype = None
+        L.hmo_search_range.argtypes = [C.c_int] * 9 + [_pi] * 4
+        L.hmo_pattern_search.restype = None
+        L.hmo_pattern_search.argtypes = [_p16, C.c_int, C.c_int, C.c_int, C.c_int, _p16, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                         _pi, _pi, _pu]
+        L.hmo_frac_search.restype = None
+        L.hmo_frac_search.argtypes = [_p16, C.c_int, C.c_int, C.c_int, C.c_int, _p16, C.c_int, C.c_int, C.c_int,
+                                      C.c_uint32, C.c_int, C.c_int, C.c_int, _pi, _pi, _pi, _pi, _pu]
+        L.hmo_extend_border.restype = None
+        L.hmo_extend_border.argtypes = [_p16, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.hmo_run_jobs.restype = C.c_double
+        L.hmo_run_jobs.argtypes = [_p16, C.c_int, _p16, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_void_p]
+
+    def eg_bits(self, v):
+        return self.lib.hmo_eg_bits(int(v))
+
+    def mv_bits(self, x, y, pred, scale):
+        return self.lib.hmo_mv_bits(int(x), int(y), int(pred[0]), int(pred[1]), int(scale))
+
+    def mv_cost(self, lambda_cost, x, y, pred, scale):
+        return self.lib.hmo_mv_cost(int(lambda_cost), self.mv_bits(x, y, pred, scale))
+
+    def dist(self, kind, org, cur, w, h, bit_depth=8, sub_shift=0):
+        (oa, oo, os_), (ca, co, cs) = org, cur
+        return self.lib.hmo_dist(kind, _ptr(oa, oo), os_, _ptr(ca, co), cs, w, h, bit_depth, sub_shift)
+
+    def search_range(self, pred, rng, cu_xy, pic_wh, max_cu=64):
+        o = [C.c_int() for _ in range(4)]
+        self.lib.hmo_search_range(pred[0], pred[1], rng, cu_xy[0], cu_xy[1], pic_wh[0], pic_wh[1], max_cu, max_cu,
+                                  *[C.byref(v) for v in o])
+        return tuple(v.value for v in o)
+
+    def pattern_search(self, org, w, h, ref, lt, rb, lambda_cost, pred, bit_depth=8):
+        (oa, oo, os_), (ra, ro, rs) = org, ref
+        mx, my, sad = C.c_int(), C.c_int(), C.c_uint32()
+        self.lib.hmo_pattern_search(_ptr(oa, oo), os_, w, h, bit_depth, _ptr(ra, ro), rs, lt[0], lt[1], rb[0], rb[1],
+                                    int(lambda_cost), pred[0], pred[1], self.fen, C.byref(mx), C.byref(my), C.byref(sad))
+        return (mx.value, my.value), sad.value
+
+    def pattern_search_frac(self, org, w, h, ref, mv_int, lambda_cost, pred, bit_depth=8, lossless=0):
+        (oa, oo, os_), (ra, ro, rs) = org, ref
+        v = [C.c_int() for _ in range(4)]
+        cost = C.c_uint32()
+        use_had = 1 if (self.hadme and not lossless) else 0
+        self.lib.hmo_frac_search(_ptr(oa, oo), os_, w, h, bit_depth, _ptr(ra, ro), rs, mv_int[0], mv_int[1],
+                                 int(lambda_cost), pred[0], pred[1], use_had, *[C.byref(x) for x in v], C.byref(cost))
+        return (v[0].value, v[1].value), (v[2].value, v[3].value), cost.value
+
+    def extend_border(self, plane, origin_off, stride, w, h, mx, my):
+        self.lib.hmo_extend_border(_ptr(plane, origin_off), stride, w, h, mx, my)
+
+    def run_jobs(self, cur, ref, jobs, bit_depth=8, do_frac=True):
+        """cur/ref: (array, offset of sample (0,0), stride).  Returns (results, cpu_seconds)."""
+        (ca, co, cs), (ra, ro, rs) = cur, ref
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        out = np.zeros(len(jobs), dtype=RESULT_DTYPE)
+        t = self.lib.hmo_run_jobs(_ptr(ca, co), cs, _ptr(ra, ro), rs, bit_depth, jobs.ctypes.data, len(jobs),
+                                  self.fen, self.hadme, int(bool(do_frac)), out.ctypes.data)
+        return out, t
+
+
+class Reference(_Base):
+    """The unmodified reference.  Raises FileNotFoundError when oracle/_ref/libhmref.so is absent."""
+
+    def __init__(self, fen=1, hadme=1):
+        so = _b.build_reference()
+        if so is None or not os.path.exists(so):
+            raise FileNotFoundError("oracle/_ref/libhmref.so not built (needs /root/reference)")
+        self.fen, self.hadme = int(fen), int(hadme)
+        L = self.lib = C.CDLL(so)
+        L.hmref_create.restype = C.c_void_p
+        L.hmref_create.argtypes = [C.c_int, C.c_int]
+        L.hmref_destroy.argtypes = [C.c_void_p]
+        L.hmref_dist.restype = C.c_uint32
+        L.hmref_dist.argtypes = [C.c_void_p, C.c_int, _p16, C.c_int, _p16, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.hmref_get_cost.restype = C.c_uint32
+        L.hmref_get_cost.argtypes = [C.c_void_p, C.c_uint32] + [C.c_int] * 5
+        L.hmref_get_bits.restype = C.c_uint32
+        L.hmref_get_bits.argtypes = [C.c_void_p] + [C.c_int] * 5
+        L.hmref_pattern_search.restype = None
+        L.hmref_pattern_search.argtypes = [C.c_void_p, _p16, C.c_int, C.c_int, C.c_int, C.c_int, _p16, C.c_int,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int,
+                                           _pi, _pi, _pu]
+        L.hmref_pattern_search_frac.restype = None
+        L.hmref_pattern_search_frac.argtypes = [C.c_void_p, C.c_int, _p16, C.c_int, C.c_int, C.c_int, C.c_int, _p16,
+                                                C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int,
+                                                _pi, _pi, _pi, _pi, _pu]
+        L.hmref_run_jobs.restype = C.c_double
+        L.hmref_run_jobs.argtypes = [C.c_void_p, _p16, C.c_int, _p16, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_void_p]
+        self.h = L.hmref_create(self.fen, self.hadme)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.hmref_destroy(self.h)
+            self.h = None
+
+    def mv_bits(self, x, y, pred, scale):
+        return self.lib.hmref_get_bits(self.h, pred[0], pred[1], scale, x, y)
+
+    def mv_cost(self, lambda_cost, x, y, pred, scale):
+        return self.lib.hmref_get_cost(self.h, int(lambda_cost), pred[0], pred[1], scale, x, y)
+
+    def dist(self, kind, org, cur, w, h, bit_depth=8, sub_shift=0):
+        (oa, oo, os_), (ca, co, cs) = org, cur
+        return self.lib.hmref_dist(self.h, kind, _ptr(oa, oo), os_, _ptr(ca, co), cs, w, h, bit_depth, sub_shift)
+
+    def pattern_search(self, org, w, h, ref, lt, rb, lambda_cost, pred, bit_depth=8):
+        (oa, oo, os_), (ra, ro, rs) = org, ref
+        mx, my, sad = C.c_int(), C.c_int(), C.c_uint32()
+        self.lib.hmref_pattern_search(self.h, _ptr(oa, oo), os_, w, h, bit_depth, _ptr(ra, ro), rs,
+                                      lt[0], lt[1], rb[0], rb[1], int(lambda_cost), pred[0], pred[1],
+                                      C.byref(mx), C.byref(my), C.byref(sad))
+        return (mx.value, my.value), sad.value
+
+    def pattern_search_frac(self, org, w, h, ref, mv_int, lambda_cost, pred, bit_depth=8, lossless=0):
+        (oa, oo, os_), (ra, ro, rs) = org, ref
+        v = [C.c_int() for _ in range(4)]
+        cost = C.c_uint32()
+        self.lib.hmref_pattern_search_frac(self.h, lossless, _ptr(oa, oo), os_, w, h, bit_depth, _ptr(ra, ro), rs,
+                                           mv_int[0], mv_int[1], int(lambda_cost), pred[0], pred[1],
+                                           *[C.byref(x) for x in v], C.byref(cost))
+        return (v[0].value, v[1].value), (v[2].value, v[3].value), cost.value
+
+    def run_jobs(self, cur, ref, jobs, bit_depth=8, do_frac=True):
+        (ca, co, cs), (ra, ro, rs) = cur, ref
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        out = np.zeros(len(jobs), dtype=RESULT_DTYPE)
+        t = self.lib.hmref_run_jobs(self.h, _ptr(ca, co), cs, _ptr(ra, ro), rs, bit_depth, jobs.ctypes.data, len(jobs),
+                                    int(bool(do_frac)), out.ctypes.data)
+        return out, t

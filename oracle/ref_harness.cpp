@@ -1,0 +1,174 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+//
+// C-ABI harness around the UNMODIFIED reference (xkfz007/video_codecs, hm-16.5rc1).  It is compiled by
+// oracle/Makefile.ref against objects built from the sources where they lie under /root/reference and
+// lands in oracle/_ref/libhmref.so.  Nothing of the reference is copied here: this file only *calls*
+//   TComRdCost::setDistParam / DistParam::DistFunc / getDistPart     (TLibCommon/TComRdCost.h:153-158,221)
+//   TEncSearch::xPatternSearch                                       (TLibEncoder/TEncSearch.cpp:3786)
+//   TEncSearch::xPatternSearchFracDIF                                (TLibEncoder/TEncSearch.cpp:4240)
+// through a subclass (both are `protected`, TLibEncoder/TEncSearch.h:413-430).
+//
+// Users: tests/ (pins oracle/hm_oracle.c and generates tests/golden/*), bench.py `--impl reference` and the
+// `cpu_baseline` leg.  The product library (libhmb200.so) never links or loads this.
+#include <cstdint>
+#include <cstring>
+#include <ctime>
+#include "TLibCommon/TComRom.h"
+#include "TLibCommon/TComRdCost.h"
+#include "TLibCommon/TComPattern.h"
+#include "TLibEncoder/TEncCfg.h"
+#include "TLibEncoder/TEncSearch.h"
+
+namespace {
+
+struct Harness : public TEncSearch
+{
+  TEncCfg    cfg;
+  TComRdCost rd;
+
+  Harness(int fen, int hadme)
+  {
+    cfg.setUseFastEnc(fen != 0);
+    cfg.setUseHADME(hadme != 0);
+    m_pcEncCfg = &cfg;
+    m_pcRdCost = &rd;
+    initTempBuff(CHROMA_420);              // allocates m_filteredBlock / m_filteredBlockTmp (TComPrediction.cpp:126)
+    m_cDistParam.bApplyWeight = false;     // what setWpScalingDistParam does when weighted prediction is off
+    BitDepths bd; bd.recon[0] = bd.recon[1] = 8;
+#if O0043_BEST_EFFORT_DECODING
+    bd.stream[0] = bd.stream[1] = 8;
+#endif
+    rd.setLambda(0.0, bd);                 // m_uiLambdaMotionSAD[0] = 0, so getMotionCost(true, add, false) sets m_uiCost = add
+  }
+  ~Harness() { m_pcEncCfg = NULL; }        // the base destructor dereferences m_pcEncCfg (TEncSearch.cpp:152-178)
+
+  void setCost(uint32_t uiCost, int predx, int predy, int scale)
+  {
+    rd.getMotionCost(true, (Int)uiCost, false);
+    TComMv p((Short)predx, (Short)predy);
+    rd.setPredictor(p);
+    rd.setCostScale(scale);
+  }
+
+  void search(Pel* org, int orgStride, int w, int h, int bitDepth, Pel* refAtPu, int refStride,
+              int ltx, int lty, int rbx, int rby, uint32_t uiCost, int predx, int predy,
+              int* mvx, int* mvy, uint32_t* sad)
+  {
+    TComPattern pat;
+    pat.initPattern(org, w, h, orgStride, bitDepth);
+    setCost(uiCost, predx, predy, 2);      // TEncSearch.cpp:3719-3722
+    TComMv lt((Short)ltx, (Short)lty), rb((Short)rbx, (Short)rby), mv;
+    Distortion d = 0;
+    xPatternSearch(&pat, refAtPu, refStride, &lt, &rb, mv, d);
+    *mvx = mv.getHor(); *mvy = mv.getVer(); *sad = d;
+  }
+
+  void frac(int lossless, Pel* org, int orgStride, int w, int h, int bitDepth, Pel* refAtPu, int refStride,
+            int mvx, int mvy, uint32_t uiCost, int predx, int predy,
+            int* hx, int* hy, int* qx, int* qy, uint32_t* cost)
+  {
+    TComPattern pat;
+    pat.initPattern(org, w, h, orgStride, bitDepth);
+    setCost(uiCost, predx, predy, 1);      // TEncSearch.cpp:3745-3746
+    TComMv mvInt((Short)mvx, (Short)mvy), half, qter;
+    Distortion d = 0;
+    xPatternSearchFracDIF(lossless != 0, &pat, refAtPu, refStride, &mvInt, half, qter, d);
+    *hx = half.getHor(); *hy = half.getVer(); *qx = qter.getHor(); *qy = qter.getVer(); *cost = d;
+  }
+};
+
+bool g_rom = false;
+
+} // namespace
+
+extern "C" {
+
+// Job / result records shared with oracle/hm_oracle.c, include/hmb200.h (same field order) so that one
+// numpy dtype serves the reference, the oracle and the CUDA path.
+struct hmref_job    { int32_t pu_x, pu_y, w, h, lt_x, lt_y, rb_x, rb_y, pred_x, pred_y; uint32_t lambda_cost; int32_t reserved; };
+struct hmref_result { int32_t mv_x, mv_y; uint32_t sad; int32_t half_x, half_y, qter_x, qter_y; uint32_t frac_cost; };
+
+void* hmref_create(int fen, int hadme)
+{
+  if (!g_rom) { initROM(); g_rom = true; }
+  return new Harness(fen, hadme);
+}
+void hmref_destroy(void* h) { delete static_cast<Harness*>(h); }
+
+// kind: 0 = SAD via the integer-ME setDistParam (TComRdCost.cpp:306) with iSubShift = sub_shift,
+//       1 = SSE via getDistPart(DF_SSE) (TComRdCost.cpp:429),
+//       2 = HAD via the sub-pel setDistParam with bHADME (TComRdCost.cpp:338),
+//       3 = SAD via the sub-pel setDistParam without HAD (DF_SADS*)
+uint32_t hmref_dist(void* hv, int kind, const int16_t* org, int org_stride, const int16_t* cur, int cur_stride,
+                    int w, int h, int bit_depth, int sub_shift)
+{
+  Harness* H = static_cast<Harness*>(hv);
+  Pel* o = const_cast<Pel*>(org); Pel* c = const_cast<Pel*>(cur);
+  if (kind == 1)
+    return H->rd.getDistPart(bit_depth, c, cur_stride, o, org_stride, w, h, COMPONENT_Y, DF_SSE);
+  TComPattern pat; pat.initPattern(o, w, h, org_stride, bit_depth);
+  DistParam dp; dp.bApplyWeight = false;
+  if (kind == 0)      H->rd.setDistParam(&pat, c, cur_stride, dp);
+  else                H->rd.setDistParam(&pat, c, cur_stride, 1, dp, kind == 2);
+  dp.iSubShift = sub_shift;
+  dp.bitDepth  = bit_depth;
+  dp.pCur      = c;
+  return dp.DistFunc(&dp);
+}
+
+uint32_t hmref_get_cost(void* hv, uint32_t ui_cost, int pred_x, int pred_y, int scale, int x, int y)
+{
+  Harness* H = static_cast<Harness*>(hv);
+  H->setCost(ui_cost, pred_x, pred_y, scale);
+  return H->rd.getCost(x, y);
+}
+uint32_t hmref_get_bits(void* hv, int pred_x, int pred_y, int scale, int x, int y)
+{
+  Harness* H = static_cast<Harness*>(hv);
+  H->setCost(0, pred_x, pred_y, scale);
+  return H->rd.getBits(x, y);
+}
+
+void hmref_pattern_search(void* hv, const int16_t* org, int org_stride, int w, int h, int bit_depth,
+                          const int16_t* ref_at_pu, int ref_stride, int lt_x, int lt_y, int rb_x, int rb_y,
+                          uint32_t ui_cost, int pred_x, int pred_y, int* mv_x, int* mv_y, uint32_t* sad)
+{
+  static_cast<Harness*>(hv)->search(const_cast<Pel*>(org), org_stride, w, h, bit_depth, const_cast<Pel*>(ref_at_pu),
+                                    ref_stride, lt_x, lt_y, rb_x, rb_y, ui_cost, pred_x, pred_y, mv_x, mv_y, sad);
+}
+
+void hmref_pattern_search_frac(void* hv, int lossless, const int16_t* org, int org_stride, int w, int h, int bit_depth,
+                               const int16_t* ref_at_pu, int ref_stride, int mv_x, int mv_y,
+                               uint32_t ui_cost, int pred_x, int pred_y,
+                               int* half_x, int* half_y, int* qter_x, int* qter_y, uint32_t* cost)
+{
+  static_cast<Harness*>(hv)->frac(lossless, const_cast<Pel*>(org), org_stride, w, h, bit_depth,
+                                  const_cast<Pel*>(ref_at_pu), ref_stride, mv_x, mv_y, ui_cost, pred_x, pred_y,
+                                  half_x, half_y, qter_x, qter_y, cost);
+}
+
+// Runs xPatternSearch (+ xPatternSearchFracDIF when do_frac) over a job list on padded Pel planes.
+// cur0 / ref0 point at luma sample (0,0) of the current (original) and reference planes.
+// Returns elapsed CPU seconds (clock()), used as the reference arm of bench.py.
+double hmref_run_jobs(void* hv, const int16_t* cur0, int cur_stride, const int16_t* ref0, int ref_stride,
+                      int bit_depth, const hmref_job* jobs, int njobs, int do_frac, hmref_result* out)
+{
+  Harness* H = static_cast<Harness*>(hv);
+  clock_t t0 = clock();
+  for (int i = 0; i < njobs; i++)
+  {
+    const hmref_job& j = jobs[i];
+    Pel* org = const_cast<Pel*>(cur0) + j.pu_y * cur_stride + j.pu_x;
+    Pel* ref = const_cast<Pel*>(ref0) + j.pu_y * ref_stride + j.pu_x;
+    hmref_result r; memset(&r, 0, sizeof(r));
+    H->search(org, cur_stride, j.w, j.h, bit_depth, ref, ref_stride, j.lt_x, j.lt_y, j.rb_x, j.rb_y,
+              j.lambda_cost, j.pred_x, j.pred_y, &r.mv_x, &r.mv_y, &r.sad);
+    if (do_frac)
+      H->frac(0, org, cur_stride, j.w, j.h, bit_depth, ref, ref_stride, r.mv_x, r.mv_y,
+              j.lambda_cost, j.pred_x, j.pred_y, &r.half_x, &r.half_y, &r.qter_x, &r.qter_y, &r.frac_cost);
+    out[i] = r;
+  }
+  return double(clock() - t0) / CLOCKS_PER_SEC;
+}
+
+} // extern "C"
