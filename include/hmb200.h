@@ -1,0 +1,200 @@
+/* hmb200.h — C-ABI of the B200-native HM-16.5 integer-pel motion search + block-distortion path.
+ *
+ * This is the drop-in boundary (plain pointers and sizes, no C++/torch types).  Every entry point names the
+ * reference interface it replaces; paths are relative to /root/reference/hm-16.5rc1/source/Lib/.
+ * The reference has no plugin API: the boundary is three C++ member functions plus the distortion function
+ * pointer table, so the entry points mirror those signatures with POD stand-ins for DistParam / TComPattern /
+ * TComMv.  INTEGRATION.md shows the forwarders a maintainer adds to TComRdCost.cpp / TEncSearch.cpp.
+ *
+ * There is NO CPU fallback: every compute entry returns HMB200_ERR_CUDA (and hmb200_last_error() explains) when
+ * no sm_100 device is usable.  Loading the library and querying symbols does not need a GPU.
+ */
+#ifndef HMB200_H
+#define HMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMB200_OK            0
+#define HMB200_ERR_CUDA     -1   /* CUDA runtime/driver failure or no device */
+#define HMB200_ERR_ARG      -2   /* bad argument (unsupported size, unknown plane, pointer outside planes ...) */
+#define HMB200_ERR_STATE    -3   /* hmb200_init not called */
+
+/* ---- flags of the search entries (TEncCfg getters the callee reads, TLibEncoder/TEncCfg.h:570,577) ---- */
+#define HMB200_FLAG_FEN      1   /* getUseFastEnc(): iSubShift = 1 for PUs with more than 8 rows (TEncSearch.cpp:3804-3810) */
+#define HMB200_FLAG_HADME    2   /* getUseHADME(): sub-pel refinement uses xGetHADs (TComRdCost.cpp:355-374)           */
+#define HMB200_FLAG_FRAC     4   /* also run the quarter-pel refinement (xPatternSearchFracDIF)                          */
+
+/* ---- distortion function families, the rows of m_afpDistortFunc (TLibCommon/TypeDef.h:334-378) ---- */
+#define HMB200_DF_SAD        0   /* DF_SAD*  : xGetSAD4..64/12/24/48 honouring iSubShift (TComRdCost.cpp:489-953) */
+#define HMB200_DF_SSE        1   /* DF_SSE*  : xGetSSE* (TComRdCost.cpp:959-1304)                                 */
+#define HMB200_DF_HADS       2   /* DF_HADS* : xGetHADs (TComRdCost.cpp:1526-1593)                                */
+#define HMB200_DF_SADS       3   /* DF_SADS* : same functions as DF_SAD (TComRdCost.cpp:248-254)                  */
+
+#define HMB200_PLANE_ORG     0
+#define HMB200_PLANE_REC     1
+
+/* TComMv (TLibCommon/TComMv.h:50-55): two Shorts; widened to int32 at the boundary. */
+typedef struct { int32_t x, y; } hmb200_mv;
+
+/* POD mirror of DistParam (TLibCommon/TComRdCost.h:67-101).  bApplyWeight must be 0 (weighted prediction is out of
+ * scope: WeightedPredP defaults to false, App/TAppEncoder/TAppEncCfg.cpp:897); iStep must be 1 (asserted by the
+ * reference, TComRdCost.cpp:1314,1338,1433). */
+typedef struct {
+  const int16_t* pOrg;       /* Pel* */
+  const int16_t* pCur;
+  int32_t iStrideOrg, iStrideCur;
+  int32_t iRows, iCols;
+  int32_t iStep;
+  int32_t func;              /* HMB200_DF_* — stands in for the DistFunc pointer */
+  int32_t bitDepth;
+  int32_t bApplyWeight;
+  int32_t iSubShift;
+} hmb200_dist_param;
+
+/* One distortion evaluation between two blocks of REGISTERED planes (device-resident; no host copies). */
+typedef struct {
+  int32_t org_plane, org_x, org_y;
+  int32_t cur_plane, cur_x, cur_y;
+  int32_t w, h;
+  int32_t sub_shift;
+  int32_t reserved;
+} hmb200_dist_desc;
+
+/* POD mirror of TComPattern's luma ROI (TLibCommon/TComPattern.h:54-99). */
+typedef struct {
+  const int16_t* roi;        /* getROIY()            */
+  int32_t width, height;     /* getROIYWidth/Height  */
+  int32_t stride;            /* getPatternLStride()  */
+  int32_t bit_depth;         /* getBitDepthY()       */
+} hmb200_pattern;
+
+/* The TComRdCost state xPatternSearch / xPatternRefinement read through getCost()
+ * (TLibCommon/TComRdCost.h:118-130,172-189): m_uiCost, m_mvPredictor.  The cost scale is fixed by the callee
+ * (2 integer, 1 half, 0 quarter: TEncSearch.cpp:3722,3746,4267). */
+typedef struct {
+  uint32_t  lambda_cost;     /* m_uiCost after getMotionCost(true, 0, ...) */
+  hmb200_mv pred;            /* m_mvPredictor, quarter-pel                 */
+} hmb200_cost_state;
+
+/* One PU search of the batched form.  pu_x/pu_y: luma position of the PU in the picture; the window corners are
+ * xSetSearchRange's outputs (integer pel, inclusive; TEncSearch.cpp:3765-3781).  48 bytes. */
+typedef struct {
+  int32_t pu_x, pu_y, w, h;
+  int32_t lt_x, lt_y, rb_x, rb_y;
+  int32_t pred_x, pred_y;    /* quarter-pel, unclipped AMVP predictor (TEncSearch.cpp:3721) */
+  uint32_t lambda_cost;
+  int32_t reserved;
+} hmb200_pu_job;
+
+/* 32 bytes.  mv/sad = xPatternSearch outputs (rcMv, ruiSAD without MV cost); half/qter/frac_cost =
+ * xPatternSearchFracDIF outputs (rcMvHalf, rcMvQter, ruiCost with MV bits). */
+typedef struct {
+  int32_t mv_x, mv_y;
+  uint32_t sad;
+  int32_t half_x, half_y, qter_x, qter_y;
+  uint32_t frac_cost;
+} hmb200_pu_result;
+
+/* ------------------------------------------------------------------ lifetime ---------------------------------- */
+
+/* Replaces nothing in the reference; called from TEncSearch::init (TEncSearch.cpp:201) where picture and CTU size
+ * are known.  Selects the device, creates streams and pinned staging.  Idempotent per device. */
+int  hmb200_init(int device);
+void hmb200_shutdown(void);
+const char* hmb200_last_error(void);
+/* Number of kernel launches issued by this library since init (bench.py's gpu_launches). */
+uint64_t hmb200_launch_count(void);
+
+/* ------------------------------------------------------------------ host-side window / job-list logic ---------- */
+
+/* TEncSearch::xSetSearchRange (TLibEncoder/TEncSearch.cpp:3765-3781) with TComDataCU::clipMv
+ * (TLibCommon/TComDataCU.cpp:2788-2801): pred is the quarter-pel predictor, (cu_x, cu_y) the luma origin of the CU
+ * that owns the PU.  Pure host arithmetic (no GPU needed). */
+void hmb200_set_search_range(hmb200_mv pred, int search_range, int cu_x, int cu_y, int pic_w, int pic_h,
+                             int max_cu_w, int max_cu_h, hmb200_mv* lt, hmb200_mv* rb);
+/* Canonical all-PU job list of a picture: every CU of depth 0..3 that lies inside the
+ * picture, partition modes 2Nx2N / 2NxN / Nx2N at every depth plus the four AMP modes at depths 0..2
+ * (TLibCommon/TComDataCU.cpp:1893-1931 getPartIndexAndSize), 593 PUs per 64x64 CTU, predictor `pred` for every PU,
+ * window from hmb200_set_search_range.  Writes at most `capacity` jobs; returns the total count (call with
+ * capacity 0 to size the buffer).  ctu_first/ctu_count select a raster range of CTUs (ctu_count < 0: to the end). */
+int  hmb200_build_canonical_jobs(int pic_w, int pic_h, int max_cu, int search_range, uint32_t lambda_cost, hmb200_mv pred,
+                                 int ctu_first, int ctu_count, hmb200_pu_job* jobs, int capacity);
+
+/* ------------------------------------------------------------------ planes ------------------------------------ */
+
+/* Uploads one luma plane once per frame.  host_origin points at sample (0,0) of a TComPicYuv luma buffer
+ * (Pel = int16, TLibCommon/TComPicYuv.cpp:81-143: stride = width + 2*margin_x); the margins must already be
+ * extended (TComPicYuv::extendPicBorder, :197-242) when they will be searched.  8-bit planes are narrowed to uint8
+ * on upload, deeper ones to uint16.  The host range [origin - margin, ...] is remembered so that the 1:1 search
+ * entries can translate a `Pel*` into (plane, x, y).  Returns a plane id >= 0 or an error code.
+ * Call sites: after TComSlice::setRefPicList (TLibCommon/TComSlice.cpp:351-377) for reconstructed pictures,
+ * TEncTop::encode (TLibEncoder/TEncTop.cpp:323-325) for originals. */
+int  hmb200_register_plane(const int16_t* host_origin, int stride, int width, int height,
+                           int margin_x, int margin_y, int bit_depth, int kind, int poc);
+/* Same, from 8-bit samples without margins (planar YUV luma as read by TVideoIOYuv); the margins are synthesised on
+ * the device exactly like extendPicBorder. */
+int  hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width, int height,
+                              int margin_x, int margin_y, int kind, int poc);
+/* Reads a registered plane back (including margins) as Pel samples; dst_stride >= width + 2*margin_x. */
+int  hmb200_read_plane(int plane_id, int16_t* dst_origin, int dst_stride);
+void hmb200_release_plane(int plane_id);
+
+/* ------------------------------------------------------------------ distortion table -------------------------- */
+
+/* Signature-compatible with FpDistFunc (TLibCommon/TComRdCost.h:60): Distortion (*)(DistParam*).  Host buffers are
+ * copied to the device per call (latency-bound; for parity and for the table hook of TComRdCost::init,
+ * TComRdCost.cpp:224-276).  Aborts the process on CUDA failure like the reference aborts on assert. */
+uint32_t hmb200_dist(const hmb200_dist_param* p);
+/* n evaluations of one family between registered planes, one launch. */
+int  hmb200_dist_batch(int func, int bit_depth, int n, const hmb200_dist_desc* descs, uint32_t* out);
+
+/* ------------------------------------------------------------------ searches, 1:1 ----------------------------- */
+
+/* TEncSearch::xPatternSearch(TComPattern*, Pel* piRefY, Int iRefStride, TComMv* LT, TComMv* RB, TComMv& rcMv,
+ * Distortion& ruiSAD)  (TLibEncoder/TEncSearch.h:413-419, .cpp:3786-3843).  ref_at_pu must point into a registered
+ * plane.  flags: HMB200_FLAG_FEN. */
+int  hmb200_pattern_search(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride,
+                           hmb200_mv lt, hmb200_mv rb, const hmb200_cost_state* cs, int flags,
+                           hmb200_mv* mv_out, uint32_t* sad_out);
+/* TEncSearch::xPatternSearchFracDIF(Bool bIsLosslessCoded, TComPattern*, Pel*, Int, TComMv* pcMvInt,
+ * TComMv& rcMvHalf, TComMv& rcMvQter, Distortion& ruiCost)  (TEncSearch.h:421-430, .cpp:4240-4276).
+ * flags: HMB200_FLAG_HADME. */
+int  hmb200_pattern_search_frac(int lossless, const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride,
+                                hmb200_mv mv_int, const hmb200_cost_state* cs, int flags,
+                                hmb200_mv* half_out, hmb200_mv* qter_out, uint32_t* cost_out);
+
+/* ------------------------------------------------------------------ searches, batched ------------------------- */
+
+/* Many PUs of one (current, reference) plane pair.  Jobs are grouped by CTU and search window on the host side; each
+ * group's window is staged once into shared memory with TMA.  flags: FEN | HADME | FRAC.
+ * Results are written in job order.  Blocking. */
+int  hmb200_me_jobs(int cur_plane, int ref_plane, const hmb200_pu_job* jobs, int njobs, int flags,
+                    hmb200_pu_result* results);
+/* One CTU row of a picture (the launch granularity the in-encoder frontend uses): jobs must all lie in CTU row
+ * `ctu_row` (pu_y / max_cu == ctu_row). */
+int  hmb200_me_ctu_row(int cur_plane, int ref_plane, int ctu_row, int max_cu, const hmb200_pu_job* jobs, int njobs,
+                       int flags, hmb200_pu_result* results);
+
+/* Device-resident variant used by benchmarks: jobs/results are DEVICE pointers, no host copies, asynchronous on
+ * the library's stream; hmb200_sync() waits.  prepared = handle from hmb200_prepare_jobs (host-side grouping and
+ * upload of the schedule are done once). */
+typedef struct hmb200_prepared hmb200_prepared;
+hmb200_prepared* hmb200_prepare_jobs(const hmb200_pu_job* jobs, int njobs, int flags, int bit_depth);
+void hmb200_free_prepared(hmb200_prepared* p);
+int  hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane);
+int  hmb200_fetch_results(hmb200_prepared* p, hmb200_pu_result* results);   /* D2H + sync */
+int  hmb200_sync(void);
+/* CUDA-event timing of the last hmb200_run_prepared: total and per-kernel milliseconds. */
+int  hmb200_last_timing(float* total_ms, float* search_ms, float* frac_ms);
+/* Algorithmic work of a prepared job list: candidate-SADs and byte abs-diffs as HM would execute them
+ * (SURVEY.md section 8d). */
+int  hmb200_prepared_work(const hmb200_prepared* p, uint64_t* cand_sads, uint64_t* abs_diffs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMB200_H */

@@ -1,0 +1,122 @@
+"""Generates tests/golden/hm_golden.npz from the UNMODIFIED reference (oracle/_ref/libhmref.so, built from
+/root/reference/hm-16.5rc1 by oracle/Makefile.ref).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The .npz holds the inputs (small planes, job lists) and the reference's outputs, so that the oracle and the CUDA
+path can be checked on machines where /root/reference does not exist.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.pyoracle import Reference, JOB_DTYPE  # noqa: E402
+from video_codecs_b200 import synth  # noqa: E402
+
+PU_SIZES = [(64, 64), (64, 32), (32, 64), (64, 16), (64, 48), (16, 64), (48, 64), (32, 32), (32, 16), (16, 32), (32, 8),
+            (32, 24), (8, 32), (24, 32), (16, 16), (16, 8), (8, 16), (16, 4), (16, 12), (4, 16), (12, 16), (8, 8), (8, 4),
+            (4, 8)]
+MARGIN = 80
+W, H = 256, 128
+
+
+def make_dist_cases(rng):
+    """(bit_depth, kind, sub_shift, w, h, org_off, cur_off) over two random planes per bit depth."""
+    cases = []
+    for bd in (8, 10):
+        for (w, h) in PU_SIZES:
+            for kind, ss in ((0, 0), (0, 1), (1, 0), (2, 0), (3, 0)):
+                for _ in range(2):
+                    oy, ox = rng.integers(0, 192 - h), rng.integers(0, 192 - w)
+                    cy, cx = rng.integers(0, 192 - h), rng.integers(0, 192 - w)
+                    cases.append((bd, kind, ss, w, h, oy * 192 + ox, cy * 192 + cx))
+    return np.array(cases, dtype=np.int32)
+
+
+def make_jobs(rng, n_per_size, search_range, lam_choices):
+    jobs = []
+    for (w, h) in PU_SIZES:
+        for k in range(n_per_size):
+            if k == 0:   # picture corner: exercises window clipping against the margins
+                px, py = (0, 0) if (w + h) % 16 == 0 else (W - w, H - h)
+            else:
+                px, py = int(rng.integers(0, (W - w) // 4 + 1)) * 4, int(rng.integers(0, (H - h) // 4 + 1)) * 4
+            pred = (int(rng.integers(-40, 41)), int(rng.integers(-40, 41))) if k % 2 else (0, 0)
+            jobs.append((px, py, w, h, pred, int(lam_choices[rng.integers(0, len(lam_choices))])))
+    return jobs
+
+
+def window(pred, rng_, cu_x, cu_y):
+    """xSetSearchRange restated for the generator (TEncSearch.cpp:3765-3781, TComDataCU.cpp:2788-2801); the CU is
+    taken to be the 64-aligned block containing the PU."""
+    def clip(x, y):
+        hmax, hmin = (W + 8 - cu_x - 1) * 4, (-64 - 8 - cu_x + 1) * 4
+        vmax, vmin = (H + 8 - cu_y - 1) * 4, (-64 - 8 - cu_y + 1) * 4
+        return min(hmax, max(hmin, x)), min(vmax, max(vmin, y))
+    px, py = clip(*pred)
+    lx, ly = clip(px - rng_ * 4, py - rng_ * 4)
+    rx, ry = clip(px + rng_ * 4, py + rng_ * 4)
+    return lx >> 2, ly >> 2, rx >> 2, ry >> 2
+
+
+def main():
+    rng = np.random.default_rng(20261018)
+    out = {}
+    # ---- distortion table ---------------------------------------------------------------------------------------
+    ref_fen = Reference(fen=1, hadme=1)
+    for bd in (8, 10):
+        hi = 1 << bd
+        a = rng.integers(0, hi, size=(192, 192)).astype(np.int16)
+        b = np.clip(a + rng.integers(-24, 25, size=a.shape), 0, hi - 1).astype(np.int16)
+        b[:96] = rng.integers(0, hi, size=(96, 192)).astype(np.int16)          # half correlated, half not
+        out[f"dist_org_{bd}"], out[f"dist_cur_{bd}"] = a, b
+    cases = make_dist_cases(rng)
+    vals = []
+    for (bd, kind, ss, w, h, oo, co) in cases:
+        vals.append(ref_fen.dist(int(kind), (out[f"dist_org_{bd}"], int(oo), 192), (out[f"dist_cur_{bd}"], int(co), 192),
+                                 int(w), int(h), int(bd), int(ss)))
+    out["dist_cases"], out["dist_expected"] = cases, np.array(vals, dtype=np.uint32)
+    # ---- MV rate ---------------------------------------------------------------------------------------------------
+    bits_cases = []
+    for _ in range(400):
+        bits_cases.append((int(rng.integers(-300, 301)), int(rng.integers(-300, 301)), int(rng.integers(-200, 201)),
+                           int(rng.integers(-200, 201)), int(rng.integers(0, 3)), int(rng.integers(0, 1 << 23))))
+    bits_cases.append((0, 0, 0, 0, 2, 4037017))
+    bits_cases.append((64, -64, -3, 5, 2, 0xFFFFFFFF))      # 32-bit wrap of m_uiCost * bits
+    bc = np.array(bits_cases, dtype=np.int64)
+    out["rate_cases"] = bc
+    out["rate_bits"] = np.array([ref_fen.mv_bits(int(x), int(y), (int(px), int(py)), int(s)) for (x, y, px, py, s, lam) in bc], dtype=np.uint32)
+    out["rate_cost"] = np.array([ref_fen.mv_cost(int(lam), int(x), int(y), (int(px), int(py)), int(s)) for (x, y, px, py, s, lam) in bc], dtype=np.uint32)
+    # ---- searches ------------------------------------------------------------------------------------------------
+    lam = [int(np.floor(65536.0 * np.sqrt(0.4624 * 2 ** ((qp - 12) / 3.0)))) for qp in (22, 32, 35, 40)]
+    for bd in (8, 10):
+        f0 = synth.luma_frame(W, H, 0, seed=77, bit_depth=bd)
+        f1 = synth.luma_frame(W, H, 1, seed=77, bit_depth=bd, vx=2.75, vy=-1.25)
+        out[f"frame0_{bd}"], out[f"frame1_{bd}"] = f0, f1
+        cur = synth.pad_plane(f1, MARGIN, MARGIN)
+        refp = synth.pad_plane(f0, MARGIN, MARGIN)
+        stride = cur.shape[1]
+        o0 = MARGIN * stride + MARGIN
+        for fen, hadme, sr, nps in ((1, 1, 64, 3), (0, 0, 12, 3), (1, 0, 20, 1), (0, 1, 9, 1)):
+            spec = make_jobs(rng, nps, sr, lam)
+            jobs = np.zeros(len(spec), dtype=JOB_DTYPE)
+            for i, (px, py, w, h, pred, lc) in enumerate(spec):
+                lt_x, lt_y, rb_x, rb_y = window(pred, sr, (px // 64) * 64, (py // 64) * 64)
+                jobs[i] = (px, py, w, h, lt_x, lt_y, rb_x, rb_y, pred[0], pred[1], lc, 0)
+            R = Reference(fen=fen, hadme=hadme)
+            res, _ = R.run_jobs((cur, o0, stride), (refp, o0, stride), jobs, bit_depth=bd, do_frac=True)
+            tag = f"search_bd{bd}_fen{fen}_had{hadme}"
+            out[tag + "_jobs"], out[tag + "_results"] = jobs, res
+            print(tag, len(jobs), "half!=0:", int(np.count_nonzero((res["half_x"] != 0) | (res["half_y"] != 0))),
+                  "qter!=0:", int(np.count_nonzero((res["qter_x"] != 0) | (res["qter_y"] != 0))))
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hm_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

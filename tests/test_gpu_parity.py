@@ -1,0 +1,247 @@
+"""GPU suite: the CUDA path, called through the C-ABI (include/hmb200.h), against the oracle on the same seeded
+inputs and against the golden vectors of the unmodified reference.  Integer work: the bar is bit-exact."""
+import numpy as np
+import pytest
+
+from common import PU_SIZES, MARGIN, load_golden, padded, results_equal
+from oracle.pyoracle import Oracle
+from video_codecs_b200 import (FLAG_FEN, FLAG_HADME, FLAG_FRAC, DF_SAD, DF_SSE, DF_HADS, DF_SADS, JOB_DTYPE, DIST_DESC_DTYPE,
+                               synth)
+
+pytestmark = pytest.mark.gpu
+
+
+def flags_of(fen, had, frac=True):
+    return (FLAG_FEN if fen else 0) | (FLAG_HADME if had else 0) | (FLAG_FRAC if frac else 0)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return load_golden()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# distortion table (BASELINE config 2)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_dist_single_call_golden(hm, gold):
+    cases, exp = gold["dist_cases"], gold["dist_expected"]
+    for (bd, kind, ss, w, h, oo, co), e in list(zip(cases, exp))[::3]:
+        got = hm.dist(int(kind), (gold[f"dist_org_{bd}"], int(oo), 192), (gold[f"dist_cur_{bd}"], int(co), 192),
+                      int(w), int(h), int(bd), int(ss))
+        assert got == int(e), (bd, kind, ss, w, h)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_dist_batch_every_pu_size(hm, oracle, bd):
+    rng = np.random.default_rng(40 + bd)
+    W, H = 320, 192
+    hi = 1 << bd
+    a = rng.integers(0, hi, size=(H, W)).astype(np.int16)
+    b = np.clip(a.astype(np.int32) + rng.integers(-20, 21, size=a.shape), 0, hi - 1).astype(np.int16)
+    pa, o0, stride = padded(a.astype(np.uint16))
+    pb, _, _ = padded(b.astype(np.uint16))
+    ida = hm.register_plane(pa, W, H, MARGIN, MARGIN, bd)
+    idb = hm.register_plane(pb, W, H, MARGIN, MARGIN, bd)
+    try:
+        for func in (DF_SAD, DF_SSE, DF_HADS, DF_SADS):
+            descs, expect = [], []
+            for (w, h) in PU_SIZES:
+                for rep in range(40):
+                    ox, oy = int(rng.integers(-8, W - w + 8)), int(rng.integers(-8, H - h + 8))
+                    cx, cy = int(rng.integers(-8, W - w + 8)), int(rng.integers(-8, H - h + 8))
+                    ss = int(rng.integers(0, 2)) if func in (DF_SAD, DF_SADS) else 0
+                    descs.append((ida, ox, oy, idb, cx, cy, w, h, ss, 0))
+                    expect.append(oracle.dist(func, (pa, o0 + oy * stride + ox, stride), (pb, o0 + cy * stride + cx, stride), w, h, bd, ss))
+            got = hm.dist_batch(func, bd, np.array(descs, dtype=DIST_DESC_DTYPE))
+            assert np.array_equal(got, np.array(expect, dtype=np.uint32)), func
+    finally:
+        hm.release_plane(ida)
+        hm.release_plane(idb)
+
+
+def test_dist_signed_pattern(hm, oracle):
+    rng = np.random.default_rng(6)
+    org = rng.integers(-255, 511, size=64 * 64).astype(np.int16)
+    cur = rng.integers(0, 256, size=64 * 64).astype(np.int16)
+    for (w, h) in ((8, 8), (64, 64), (12, 16), (4, 8)):
+        for func in (DF_SAD, DF_SSE, DF_HADS):
+            assert hm.dist(func, (org, 0, 64), (cur, 0, 64), w, h, 8, 0) == oracle.dist(func, (org, 0, 64), (cur, 0, 64), w, h, 8, 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# plane ingest
+# ---------------------------------------------------------------------------------------------------------------------
+def test_plane_round_trip_and_border_extension(hm, oracle):
+    f = synth.luma_frame(200, 72, 3, seed=2)
+    pid = hm.register_plane_u8(f, 80, 80)
+    try:
+        back = hm.read_plane(pid, 200, 72, 80, 80)
+        assert np.array_equal(back, synth.pad_plane(f, 80, 80))
+        manual = np.zeros((72 + 160, 200 + 160), dtype=np.int16)
+        manual[80:-80, 80:-80] = f
+        oracle.extend_border(manual, 80 * manual.shape[1] + 80, manual.shape[1], 200, 72, 80, 80)
+        assert np.array_equal(back, manual)
+    finally:
+        hm.release_plane(pid)
+    f10 = synth.luma_frame(64, 64, 0, seed=3, bit_depth=10)
+    p10 = synth.pad_plane(f10, 16, 24)
+    pid = hm.register_plane(p10, 64, 64, 16, 24, 10)
+    try:
+        assert np.array_equal(hm.read_plane(pid, 64, 64, 16, 24), p10)
+    finally:
+        hm.release_plane(pid)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# batched search against the reference's golden vectors and against the oracle
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bd", [8, 10])
+@pytest.mark.parametrize("fen,had", [(1, 1), (0, 0), (1, 0), (0, 1)])
+def test_me_jobs_golden(hm, gold, bd, fen, had):
+    tag = f"search_bd{bd}_fen{fen}_had{had}"
+    jobs, exp = gold[tag + "_jobs"], gold[tag + "_results"]
+    f0, f1 = gold[f"frame0_{bd}"], gold[f"frame1_{bd}"]
+    H, W = f0.shape
+    cur, _, _ = padded(f1)
+    ref, _, _ = padded(f0)
+    idc = hm.register_plane(cur, W, H, MARGIN, MARGIN, bd, kind=0)
+    idr = hm.register_plane(ref, W, H, MARGIN, MARGIN, bd, kind=1)
+    try:
+        got = hm.me_jobs(idc, idr, jobs, flags_of(fen, had))
+        assert results_equal(got, exp) == []
+    finally:
+        hm.release_plane(idc)
+        hm.release_plane(idr)
+
+
+@pytest.mark.parametrize("fen", [1, 0])
+def test_me_canonical_ctus_vs_oracle(hm, fen):
+    """Every PU of a few CTUs (interior, picture corner, last partial row) of a 416x240 pair, +-64, with refinement."""
+    W, H = 416, 240
+    f0 = synth.luma_frame(W, H, 0)
+    f1 = synth.luma_frame(W, H, 1)
+    cur, o0, stride = padded(f1)
+    ref, _, _ = padded(f0)
+    lam = int(np.floor(65536.0 * np.sqrt(0.4624 * 2 ** ((35 - 12) / 3.0))))
+    jobs = np.concatenate([hm.build_canonical_jobs(W, H, 64, lam, ctu_first=c, ctu_count=1) for c in (0, 9, 27)])
+    jobs = jobs[:: 3 if fen else 5]
+    idc = hm.register_plane_u8(f1, MARGIN, MARGIN, kind=0)
+    idr = hm.register_plane_u8(f0, MARGIN, MARGIN, kind=1)
+    try:
+        got = hm.me_jobs(idc, idr, jobs, flags_of(fen, 1))
+    finally:
+        hm.release_plane(idc)
+        hm.release_plane(idr)
+    exp, _ = Oracle(fen=fen, hadme=1).run_jobs((cur, o0, stride), (ref, o0, stride), jobs, 8, True)
+    assert results_equal(got, exp) == []
+    assert len(set(zip(got["mv_x"].tolist(), got["mv_y"].tolist()))) > 3      # the MV field is not trivial
+
+
+def test_me_random_predictors_and_windows(hm):
+    """Per-PU predictors and asymmetric, clipped, tiny and single-candidate windows."""
+    W, H = 256, 192
+    rng = np.random.default_rng(12)
+    f0 = synth.luma_frame(W, H, 0, seed=5)
+    f1 = synth.luma_frame(W, H, 2, seed=5)
+    cur, o0, stride = padded(f1)
+    ref, _, _ = padded(f0)
+    jobs = np.zeros(len(PU_SIZES) * 4, dtype=JOB_DTYPE)
+    for i, (w, h) in enumerate(PU_SIZES * 4):
+        px, py = int(rng.integers(0, (W - w) // 4 + 1)) * 4, int(rng.integers(0, (H - h) // 4 + 1)) * 4
+        pred = (int(rng.integers(-60, 61)), int(rng.integers(-60, 61)))
+        kind = i % 4
+        if kind == 0:      # HM-style window
+            sr = int(rng.choice([7, 16, 33]))
+            lt = (max((pred[0] >> 2) - sr, -(px + 64 + 7)), max((pred[1] >> 2) - sr, -(py + 64 + 7)))
+            rb = (min((pred[0] >> 2) + sr, W + 7 - px), min((pred[1] >> 2) + sr, H + 7 - py))
+        elif kind == 1:    # single candidate
+            lt = rb = (int(rng.integers(-5, 6)), int(rng.integers(-5, 6)))
+        elif kind == 2:    # one row / one column
+            lt = (-9, 3)
+            rb = (22, 3) if i % 8 == 2 else (-9, 30)
+        else:              # wide and flat / odd sizes
+            lt = (-int(rng.integers(1, 70)), -int(rng.integers(1, 6)))
+            rb = (int(rng.integers(1, 70)), int(rng.integers(1, 6)))
+        jobs[i] = (px, py, w, h, lt[0], lt[1], rb[0], rb[1], pred[0], pred[1], int(rng.integers(0, 9000000)), 0)
+    idc = hm.register_plane_u8(f1, MARGIN, MARGIN, kind=0)
+    idr = hm.register_plane_u8(f0, MARGIN, MARGIN, kind=1)
+    try:
+        for fen, had in ((1, 1), (0, 0)):
+            got = hm.me_jobs(idc, idr, jobs, flags_of(fen, had))
+            exp, _ = Oracle(fen=fen, hadme=had).run_jobs((cur, o0, stride), (ref, o0, stride), jobs, 8, True)
+            assert results_equal(got, exp) == [], (fen, had)
+    finally:
+        hm.release_plane(idc)
+        hm.release_plane(idr)
+
+
+def test_tie_break_flat_content(hm):
+    """All SADs tie: the winner is decided by the MV cost and then by raster order (strict '<', first wins)."""
+    W, H = 128, 128
+    flat = np.full((H, W), 77, dtype=np.uint8)
+    cur, o0, stride = padded(flat)
+    jobs = np.zeros(6, dtype=JOB_DTYPE)
+    jobs[0] = (32, 32, 8, 8, -64, -64, 64, 64, 0, 0, 0, 0)                # lambda 0: everything ties -> (-64,-64)
+    jobs[1] = (32, 32, 16, 16, -64, -64, 64, 64, 9, -6, 65536 * 4, 0)
+    jobs[2] = (0, 0, 64, 64, -64, -64, 64, 64, 2, 2, 65536 * 4, 0)
+    jobs[3] = (64, 64, 4, 8, -3, -3, 3, 3, 1, 1, 4037017, 0)
+    jobs[4] = (64, 64, 32, 32, -64, -64, 64, 64, -255, 255, 0xFFFFFFFF, 0)   # 32-bit wrap of m_uiCost * bits
+    jobs[5] = (64, 0, 64, 32, -64, -64, 64, 64, 0, 0, 1, 0)
+    idc = hm.register_plane_u8(flat, MARGIN, MARGIN)
+    try:
+        got = hm.me_jobs(idc, idc, jobs, flags_of(1, 1))
+    finally:
+        hm.release_plane(idc)
+    exp, _ = Oracle(fen=1, hadme=1).run_jobs((cur, o0, stride), (cur, o0, stride), jobs, 8, True)
+    assert results_equal(got, exp) == []
+    assert (got[0]["mv_x"], got[0]["mv_y"]) == (-64, -64)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 1:1 entries (the TEncSearch signatures)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bd", [8, 10])
+def test_pattern_search_and_frac_one_to_one(hm, bd):
+    W, H = 192, 128
+    f0 = synth.luma_frame(W, H, 0, seed=31, bit_depth=bd)
+    f1 = synth.luma_frame(W, H, 1, seed=31, bit_depth=bd)
+    ref, o0, stride = padded(f0)
+    O = Oracle(fen=1, hadme=1)
+    rng = np.random.default_rng(8)
+    idr = hm.register_plane(ref, W, H, MARGIN, MARGIN, bd)
+    try:
+        for (w, h) in PU_SIZES[::2]:
+            # CU-local original buffer with its own stride, as TEncCu hands it over (stride 64 >> depth)
+            px, py = int(rng.integers(0, (W - w) // 4 + 1)) * 4, int(rng.integers(0, (H - h) // 4 + 1)) * 4
+            org = np.ascontiguousarray(f1[py:py + h, px:px + w].astype(np.int16))
+            if w == 16:     # bi-pred style pattern: 2*org - pred may leave the pixel range
+                org = (2 * org - rng.integers(0, 1 << bd, size=org.shape)).astype(np.int16)
+            pred = (int(rng.integers(-20, 21)), int(rng.integers(-20, 21)))
+            lam = int(rng.integers(100000, 6000000))
+            roff = o0 + py * stride + px
+            lt, rb = (-12 + (pred[0] >> 2), -9 + (pred[1] >> 2)), (12 + (pred[0] >> 2), 9 + (pred[1] >> 2))
+            mv, sad = hm.pattern_search((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred, bd, FLAG_FEN)
+            assert (mv, sad) == O.pattern_search((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred, bd)
+            got = hm.pattern_search_frac((org, 0, w), w, h, (ref, roff, stride), mv, lam, pred, bd, FLAG_HADME)
+            assert got == O.pattern_search_frac((org, 0, w), w, h, (ref, roff, stride), mv, lam, pred, bd)
+    finally:
+        hm.release_plane(idr)
+
+
+def test_error_behaviour(hm):
+    from video_codecs_b200 import HMB200Error
+    with pytest.raises(HMB200Error):
+        hm.me_jobs(991, 992, np.zeros(1, dtype=JOB_DTYPE))
+    flat = np.zeros((64, 64), dtype=np.uint8)
+    pid = hm.register_plane_u8(flat, 80, 80)
+    try:
+        bad = np.zeros(1, dtype=JOB_DTYPE)
+        bad[0] = (0, 0, 5, 8, -1, -1, 1, 1, 0, 0, 0, 0)        # width 5 is not a PU size
+        with pytest.raises(HMB200Error):
+            hm.me_jobs(pid, pid, bad)
+        bad[0] = (0, 0, 8, 8, 2, 0, 1, 0, 0, 0, 0, 0)          # empty window
+        with pytest.raises(HMB200Error):
+            hm.me_jobs(pid, pid, bad)
+        assert len(hm.me_jobs(pid, pid, np.zeros(0, dtype=JOB_DTYPE))) == 0      # empty job list is fine
+    finally:
+        hm.release_plane(pid)

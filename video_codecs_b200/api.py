@@ -1,0 +1,240 @@
+"""ctypes mirror of include/hmb200.h.  Names follow the header one to one."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+FLAG_FEN, FLAG_HADME, FLAG_FRAC = 1, 2, 4
+DF_SAD, DF_SSE, DF_HADS, DF_SADS = 0, 1, 2, 3
+PLANE_ORG, PLANE_REC = 0, 1
+
+JOB_DTYPE = np.dtype([("pu_x", "<i4"), ("pu_y", "<i4"), ("w", "<i4"), ("h", "<i4"),
+                      ("lt_x", "<i4"), ("lt_y", "<i4"), ("rb_x", "<i4"), ("rb_y", "<i4"),
+                      ("pred_x", "<i4"), ("pred_y", "<i4"), ("lambda_cost", "<u4"), ("reserved", "<i4")])
+RESULT_DTYPE = np.dtype([("mv_x", "<i4"), ("mv_y", "<i4"), ("sad", "<u4"),
+                         ("half_x", "<i4"), ("half_y", "<i4"), ("qter_x", "<i4"), ("qter_y", "<i4"),
+                         ("frac_cost", "<u4")])
+DIST_DESC_DTYPE = np.dtype([("org_plane", "<i4"), ("org_x", "<i4"), ("org_y", "<i4"),
+                            ("cur_plane", "<i4"), ("cur_x", "<i4"), ("cur_y", "<i4"),
+                            ("w", "<i4"), ("h", "<i4"), ("sub_shift", "<i4"), ("reserved", "<i4")])
+assert JOB_DTYPE.itemsize == 48 and RESULT_DTYPE.itemsize == 32 and DIST_DESC_DTYPE.itemsize == 40
+
+
+class HMB200Error(RuntimeError):
+    pass
+
+
+class _Mv(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32)]
+
+
+class _DistParam(C.Structure):
+    _fields_ = [("pOrg", C.c_void_p), ("pCur", C.c_void_p), ("iStrideOrg", C.c_int32), ("iStrideCur", C.c_int32),
+                ("iRows", C.c_int32), ("iCols", C.c_int32), ("iStep", C.c_int32), ("func", C.c_int32),
+                ("bitDepth", C.c_int32), ("bApplyWeight", C.c_int32), ("iSubShift", C.c_int32)]
+
+
+class _Pattern(C.Structure):
+    _fields_ = [("roi", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("stride", C.c_int32),
+                ("bit_depth", C.c_int32)]
+
+
+class _CostState(C.Structure):
+    _fields_ = [("lambda_cost", C.c_uint32), ("pred", _Mv)]
+
+
+def lib_path():
+    return os.path.join(HERE, "libhmb200.so")
+
+
+def _load():
+    path = lib_path()
+    if not os.path.exists(path):
+        raise HMB200Error(f"{path} is missing: build it with `python -m video_codecs_b200.build` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, i32, u32 = C.c_void_p, C.c_int, C.c_uint32
+    sig = {
+        "hmb200_init": (i32, [i32]), "hmb200_shutdown": (None, []), "hmb200_last_error": (C.c_char_p, []),
+        "hmb200_launch_count": (C.c_uint64, []),
+        "hmb200_set_search_range": (None, [_Mv, i32, i32, i32, i32, i32, i32, i32, C.POINTER(_Mv), C.POINTER(_Mv)]),
+        "hmb200_build_canonical_jobs": (i32, [i32, i32, i32, i32, u32, _Mv, i32, i32, vp, i32]),
+        "hmb200_register_plane": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32]),
+        "hmb200_register_plane_u8": (i32, [vp, i32, i32, i32, i32, i32, i32, i32]),
+        "hmb200_read_plane": (i32, [i32, vp, i32]), "hmb200_release_plane": (None, [i32]),
+        "hmb200_dist": (u32, [C.POINTER(_DistParam)]),
+        "hmb200_dist_batch": (i32, [i32, i32, i32, vp, vp]),
+        "hmb200_pattern_search": (i32, [C.POINTER(_Pattern), vp, i32, _Mv, _Mv, C.POINTER(_CostState), i32,
+                                        C.POINTER(_Mv), C.POINTER(u32)]),
+        "hmb200_pattern_search_frac": (i32, [i32, C.POINTER(_Pattern), vp, i32, _Mv, C.POINTER(_CostState), i32,
+                                             C.POINTER(_Mv), C.POINTER(_Mv), C.POINTER(u32)]),
+        "hmb200_me_jobs": (i32, [i32, i32, vp, i32, i32, vp]),
+        "hmb200_me_ctu_row": (i32, [i32, i32, i32, i32, vp, i32, i32, vp]),
+        "hmb200_prepare_jobs": (vp, [vp, i32, i32, i32]), "hmb200_free_prepared": (None, [vp]),
+        "hmb200_run_prepared": (i32, [vp, i32, i32]), "hmb200_fetch_results": (i32, [vp, vp]),
+        "hmb200_sync": (i32, []),
+        "hmb200_last_timing": (i32, [C.POINTER(C.c_float)] * 3),
+        "hmb200_prepared_work": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)          # AttributeError here == the library does not export what the header declares
+        f.restype, f.argtypes = res, args
+    return L, sorted(sig)
+
+
+def _addr(a, off=0):
+    return a.ctypes.data + a.dtype.itemsize * int(off)
+
+
+class HMB200:
+    """One instance per process (the C library keeps process-global state, like the encoder it serves)."""
+
+    def __init__(self):
+        self.lib, self.exported = _load()
+
+    # -- lifetime --------------------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc < 0:
+            raise HMB200Error(f"hmb200 error {rc}: {self.lib.hmb200_last_error().decode()}")
+        return rc
+
+    def init(self, device=0):
+        self._check(self.lib.hmb200_init(int(device)))
+
+    def shutdown(self):
+        self.lib.hmb200_shutdown()
+
+    def launch_count(self):
+        return int(self.lib.hmb200_launch_count())
+
+    # -- host logic ------------------------------------------------------------------------------------------------
+    def set_search_range(self, pred, search_range, cu_xy, pic_wh, max_cu=64):
+        lt, rb = _Mv(), _Mv()
+        self.lib.hmb200_set_search_range(_Mv(*pred), search_range, cu_xy[0], cu_xy[1], pic_wh[0], pic_wh[1], max_cu, max_cu,
+                                         C.byref(lt), C.byref(rb))
+        return (lt.x, lt.y, rb.x, rb.y)
+
+    def build_canonical_jobs(self, pic_w, pic_h, search_range=64, lambda_cost=0, pred=(0, 0), max_cu=64,
+                             ctu_first=0, ctu_count=-1):
+        n = self._check(self.lib.hmb200_build_canonical_jobs(pic_w, pic_h, max_cu, search_range, int(lambda_cost), _Mv(*pred),
+                                                             ctu_first, ctu_count, None, 0))
+        jobs = np.zeros(n, dtype=JOB_DTYPE)
+        self._check(self.lib.hmb200_build_canonical_jobs(pic_w, pic_h, max_cu, search_range, int(lambda_cost), _Mv(*pred),
+                                                         ctu_first, ctu_count, jobs.ctypes.data, n))
+        return jobs
+
+    # -- planes ----------------------------------------------------------------------------------------------------
+    def register_plane(self, padded, width, height, margin_x, margin_y, bit_depth=8, kind=PLANE_REC, poc=0):
+        """padded: C-contiguous int16 array of shape (height + 2*margin_y, width + 2*margin_x) (a TComPicYuv luma
+        buffer).  The caller must keep it alive while 1:1 entries refer to it by pointer."""
+        assert padded.dtype == np.int16 and padded.flags["C_CONTIGUOUS"]
+        stride = padded.shape[1]
+        assert padded.shape[0] == height + 2 * margin_y and stride >= width + 2 * margin_x
+        origin = _addr(padded, margin_y * stride + margin_x)
+        return self._check(self.lib.hmb200_register_plane(origin, stride, width, height, margin_x, margin_y, bit_depth, kind, poc))
+
+    def register_plane_u8(self, samples, margin_x=80, margin_y=80, kind=PLANE_REC, poc=0):
+        assert samples.dtype == np.uint8 and samples.ndim == 2 and samples.strides[1] == 1
+        h, w = samples.shape
+        return self._check(self.lib.hmb200_register_plane_u8(samples.ctypes.data, samples.strides[0], w, h, margin_x, margin_y, kind, poc))
+
+    def read_plane(self, plane_id, width, height, margin_x, margin_y):
+        out = np.zeros((height + 2 * margin_y, width + 2 * margin_x), dtype=np.int16)
+        self._check(self.lib.hmb200_read_plane(plane_id, _addr(out, margin_y * out.shape[1] + margin_x), out.shape[1]))
+        return out
+
+    def release_plane(self, plane_id):
+        self.lib.hmb200_release_plane(int(plane_id))
+
+    # -- distortion table ------------------------------------------------------------------------------------------
+    def dist(self, func, org, cur, w, h, bit_depth=8, sub_shift=0):
+        """org/cur: (int16 array, element offset, stride) — the FpDistFunc-compatible single call."""
+        (oa, oo, os_), (ca, co, cs) = org, cur
+        p = _DistParam(_addr(oa, oo), _addr(ca, co), os_, cs, h, w, 1, func, bit_depth, 0, sub_shift)
+        return int(self.lib.hmb200_dist(C.byref(p)))
+
+    def dist_batch(self, func, bit_depth, descs):
+        descs = np.ascontiguousarray(descs, dtype=DIST_DESC_DTYPE)
+        out = np.zeros(len(descs), dtype=np.uint32)
+        self._check(self.lib.hmb200_dist_batch(func, bit_depth, len(descs), descs.ctypes.data, out.ctypes.data))
+        return out
+
+    # -- 1:1 searches ----------------------------------------------------------------------------------------------
+    def pattern_search(self, org, w, h, ref, lt, rb, lambda_cost, pred, bit_depth=8, flags=FLAG_FEN):
+        """org: (array, offset, stride) host pattern; ref: (registered padded array, offset of the co-located sample, stride)."""
+        (oa, oo, os_), (ra, ro, rs) = org, ref
+        key = _Pattern(_addr(oa, oo), w, h, os_, bit_depth)
+        cs = _CostState(int(lambda_cost), _Mv(*pred))
+        mv, sad = _Mv(), C.c_uint32()
+        self._check(self.lib.hmb200_pattern_search(C.byref(key), _addr(ra, ro), rs, _Mv(*lt), _Mv(*rb), C.byref(cs), flags,
+                                                   C.byref(mv), C.byref(sad)))
+        return (mv.x, mv.y), sad.value
+
+    def pattern_search_frac(self, org, w, h, ref, mv_int, lambda_cost, pred, bit_depth=8, flags=FLAG_HADME, lossless=0):
+        (oa, oo, os_), (ra, ro, rs) = org, ref
+        key = _Pattern(_addr(oa, oo), w, h, os_, bit_depth)
+        cs = _CostState(int(lambda_cost), _Mv(*pred))
+        half, qter, cost = _Mv(), _Mv(), C.c_uint32()
+        self._check(self.lib.hmb200_pattern_search_frac(lossless, C.byref(key), _addr(ra, ro), rs, _Mv(*mv_int), C.byref(cs), flags,
+                                                        C.byref(half), C.byref(qter), C.byref(cost)))
+        return (half.x, half.y), (qter.x, qter.y), cost.value
+
+    # -- batched searches ------------------------------------------------------------------------------------------
+    def me_jobs(self, cur_plane, ref_plane, jobs, flags=FLAG_FEN | FLAG_HADME | FLAG_FRAC):
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        out = np.zeros(len(jobs), dtype=RESULT_DTYPE)
+        self._check(self.lib.hmb200_me_jobs(cur_plane, ref_plane, jobs.ctypes.data, len(jobs), flags, out.ctypes.data))
+        return out
+
+    def me_ctu_row(self, cur_plane, ref_plane, ctu_row, jobs, flags=FLAG_FEN | FLAG_HADME | FLAG_FRAC, max_cu=64):
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        out = np.zeros(len(jobs), dtype=RESULT_DTYPE)
+        self._check(self.lib.hmb200_me_ctu_row(cur_plane, ref_plane, ctu_row, max_cu, jobs.ctypes.data, len(jobs), flags, out.ctypes.data))
+        return out
+
+    def prepare_jobs(self, jobs, flags=FLAG_FEN | FLAG_HADME | FLAG_FRAC, bit_depth=8):
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        h = self.lib.hmb200_prepare_jobs(jobs.ctypes.data, len(jobs), flags, bit_depth)
+        if not h:
+            raise HMB200Error(self.lib.hmb200_last_error().decode())
+        return Prepared(self, h, len(jobs))
+
+    def sync(self):
+        self._check(self.lib.hmb200_sync())
+
+
+class Prepared:
+    def __init__(self, owner, handle, n):
+        self.o, self.h, self.n = owner, handle, n
+
+    def run(self, cur_plane, ref_plane):
+        self.o._check(self.o.lib.hmb200_run_prepared(self.h, cur_plane, ref_plane))
+
+    def fetch(self, out=None):
+        if out is None:
+            out = np.zeros(self.n, dtype=RESULT_DTYPE)
+        self.o._check(self.o.lib.hmb200_fetch_results(self.h, out.ctypes.data))
+        return out
+
+    def timing(self):
+        t = [C.c_float() for _ in range(3)]
+        self.o._check(self.o.lib.hmb200_last_timing(*[C.byref(x) for x in t]))
+        return {"total_ms": t[0].value, "search_ms": t[1].value, "frac_ms": t[2].value}
+
+    def work(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self.o._check(self.o.lib.hmb200_prepared_work(self.h, C.byref(a), C.byref(b)))
+        return {"cand_sads": a.value, "abs_diffs": b.value}
+
+    def free(self):
+        if self.h:
+            self.o.lib.hmb200_free_prepared(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,0 +1,633 @@
+// C-ABI frontend of libhmb200.so (include/hmb200.h): plane registry, job scheduling, kernel launches.
+// One caller thread per process (the reference path is non-reentrant too: shared m_cDistParam / m_filteredBlock,
+// TLibEncoder/TEncSearch.h:113).  No CPU fallback anywhere: without a usable sm_100 device every compute entry
+// fails with HMB200_ERR_CUDA.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include "hmb200_device.cuh"
+#include "hmb200_generic.cuh"
+#include "hmb200_search8.cuh"
+
+using namespace hmb200;
+
+namespace {
+
+struct Plane {
+  bool used = false;
+  DevPlane d{};
+  const int16_t* host_lo = nullptr;   // first Pel of the registered host buffer (row -my, col -mx)
+  const int16_t* host_hi = nullptr;   // one past the last Pel
+  int host_stride = 0;
+  int kind = 0, poc = 0;
+  size_t bytes = 0;
+  Search8Maps maps{};                 // TMA descriptors (8-bit planes only)
+  bool has_maps = false;
+};
+
+struct State {
+  bool ready = false;
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  std::vector<Plane> planes;
+  void* pinned = nullptr; size_t pinned_bytes = 0;
+  void* dstage = nullptr; size_t dstage_bytes = 0;     // device staging for plane uploads / per-call blocks
+  Plane pattern;                                       // 64x64 int16 pattern buffer for the 1:1 entries
+  uint64_t launches = 0;
+  float last_total_ms = 0, last_search_ms = 0, last_frac_ms = 0;
+  EncodeTiledFn encode = nullptr;
+};
+
+State g;
+std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(HMB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
+  } while (0)
+#define NEED_READY() do { if (!g.ready) return fail(HMB200_ERR_STATE, "hmb200_init has not succeeded"); } while (0)
+
+int ensure_pinned(size_t bytes) {
+  if (bytes <= g.pinned_bytes) return HMB200_OK;
+  if (g.pinned) cudaFreeHost(g.pinned);
+  g.pinned = nullptr; g.pinned_bytes = 0;
+  CUDA_TRY(cudaMallocHost(&g.pinned, bytes));
+  g.pinned_bytes = bytes;
+  return HMB200_OK;
+}
+int ensure_dstage(size_t bytes) {
+  if (bytes <= g.dstage_bytes) return HMB200_OK;
+  if (g.dstage) cudaFree(g.dstage);
+  g.dstage = nullptr; g.dstage_bytes = 0;
+  CUDA_TRY(cudaMalloc(&g.dstage, bytes));
+  g.dstage_bytes = bytes;
+  return HMB200_OK;
+}
+
+int alloc_plane_slot() {
+  for (size_t i = 0; i < g.planes.size(); i++) if (!g.planes[i].used) return (int)i;
+  g.planes.emplace_back();
+  return (int)g.planes.size() - 1;
+}
+
+int make_plane(Plane& p, int width, int height, int mx, int my, int bit_depth) {
+  int bps = bit_depth > 8 ? 2 : 1;
+  int total_w = width + 2 * mx, total_h = height + 2 * my;
+  int pitch_bytes = ((total_w * bps + 127) / 128) * 128;
+  p.d.pitch = pitch_bytes / bps;
+  p.d.width = width; p.d.height = height; p.d.margin_x = mx; p.d.margin_y = my;
+  p.d.bytes_per_sample = bps; p.d.bit_depth = bit_depth;
+  p.bytes = (size_t)pitch_bytes * total_h;
+  CUDA_TRY(cudaMalloc(&p.d.base, p.bytes));
+  p.has_maps = false;
+  if (bps == 1) {
+    std::string why;
+    if (!search8_make_maps(g.encode, p.d, &p.maps, &why)) { cudaFree(p.d.base); p.d.base = nullptr; return fail(HMB200_ERR_CUDA, why); }
+    p.has_maps = true;
+  }
+  p.used = true;
+  return HMB200_OK;
+}
+
+Plane* get_plane(int id) {
+  if (id < 0 || id >= (int)g.planes.size() || !g.planes[id].used) return nullptr;
+  return &g.planes[id];
+}
+
+// which registered plane does a host Pel* fall into?  (1:1 entries hand us raw pointers into TComPicYuv buffers)
+Plane* find_plane_by_host(const int16_t* ptr, int* x, int* y) {
+  for (auto& p : g.planes) {
+    if (!p.used || !p.host_lo) continue;
+    if (ptr >= p.host_lo && ptr < p.host_hi) {
+      ptrdiff_t off = ptr - p.host_lo;
+      *y = (int)(off / p.host_stride) - p.d.margin_y;
+      *x = (int)(off % p.host_stride) - p.d.margin_x;
+      return &p;
+    }
+  }
+  return nullptr;
+}
+
+bool supported_pu(int w, int h) { return w >= 4 && h >= 4 && w <= 64 && h <= 64 && (w % 4) == 0 && (h % 2) == 0; }
+
+template <typename RefT, typename OrgT>
+void launch_generic(const SearchTask* d_tasks, hmb200_pu_result* d_res, int n, const DevPlane& cur, const DevPlane& ref,
+                    int flags, bool do_search, cudaEvent_t mid) {
+  if (do_search) {
+    k_search_generic<RefT, OrgT><<<n, 256, 0, g.stream>>>(d_tasks, d_res, cur, ref);
+    g.launches++;
+  }
+  if (mid) cudaEventRecord(mid, g.stream);
+  if (flags & HMB200_FLAG_FRAC) {
+    k_frac_generic<RefT, OrgT><<<n, FRAC_THREADS, FRAC_SMEM_BYTES, g.stream>>>(d_tasks, d_res, cur, ref,
+                                                                               (flags & HMB200_FLAG_HADME) ? 1 : 0);
+    g.launches++;
+  }
+}
+
+void dispatch_generic(const SearchTask* d_tasks, hmb200_pu_result* d_res, int n, const DevPlane& cur, const DevPlane& ref,
+                      int flags, bool do_search, cudaEvent_t mid) {
+  if (n <= 0) { if (mid) cudaEventRecord(mid, g.stream); return; }
+  bool r8 = ref.bytes_per_sample == 1, o8 = cur.bytes_per_sample == 1;
+  if (r8 && o8)        launch_generic<uint8_t, uint8_t>(d_tasks, d_res, n, cur, ref, flags, do_search, mid);
+  else if (r8 && !o8)  launch_generic<uint8_t, int16_t>(d_tasks, d_res, n, cur, ref, flags, do_search, mid);
+  else if (!r8 && o8)  launch_generic<int16_t, uint8_t>(d_tasks, d_res, n, cur, ref, flags, do_search, mid);
+  else                 launch_generic<int16_t, int16_t>(d_tasks, d_res, n, cur, ref, flags, do_search, mid);
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+struct hmb200_prepared {
+  int n = 0, flags = 0, bit_depth = 8;
+  std::vector<SearchTask> tasks;
+  SearchTask* d_tasks = nullptr;
+  hmb200_pu_result* d_results = nullptr;
+  uint64_t cand_sads = 0, abs_diffs = 0;
+  Search8Schedule sched;          // tiled 8-bit kernel schedule (empty when not applicable)
+};
+
+extern "C" {
+
+const char* hmb200_last_error(void) { return g_err.c_str(); }
+uint64_t hmb200_launch_count(void) { return g.launches; }
+
+int hmb200_init(int device) {
+  if (g.ready && g.device == device) return HMB200_OK;
+  if (g.ready) hmb200_shutdown();
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(HMB200_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)");
+  if (device < 0 || device >= count) return fail(HMB200_ERR_ARG, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(HMB200_ERR_CUDA, "libhmb200 is built for sm_100a only; found " + std::string(prop.name));
+  g.sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  for (auto& ev : g.ev) CUDA_TRY(cudaEventCreate(&ev));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn) return fail(HMB200_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  g.encode = reinterpret_cast<EncodeTiledFn>(fn);
+  int rc = search8_configure(&g_err);
+  if (rc != HMB200_OK) return rc;
+  g.device = device;
+  g.ready = true;
+  // pattern buffer for the 1:1 entries: 64x64 int16, no margins
+  g.pattern = Plane();
+  rc = make_plane(g.pattern, 64, 64, 0, 0, 16);
+  if (rc != HMB200_OK) { g.ready = false; return rc; }
+  g.launches = 0;
+  return HMB200_OK;
+}
+
+void hmb200_shutdown(void) {
+  if (!g.ready) return;
+  cudaStreamSynchronize(g.stream);
+  for (auto& p : g.planes) if (p.used && p.d.base) cudaFree(p.d.base);
+  g.planes.clear();
+  if (g.pattern.d.base) cudaFree(g.pattern.d.base);
+  g.pattern = Plane();
+  if (g.pinned) cudaFreeHost(g.pinned);
+  if (g.dstage) cudaFree(g.dstage);
+  g.pinned = nullptr; g.pinned_bytes = 0; g.dstage = nullptr; g.dstage_bytes = 0;
+  for (auto& ev : g.ev) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+  cudaStreamDestroy(g.stream); g.stream = nullptr;
+  g.ready = false; g.device = -1;
+}
+
+int hmb200_sync(void) { NEED_READY(); CUDA_TRY(cudaStreamSynchronize(g.stream)); return HMB200_OK; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// host-side window / job-list logic (no GPU)
+// ------------------------------------------------------------------------------------------------------------------
+static void clip_mv(int& x, int& y, int cu_x, int cu_y, int pic_w, int pic_h, int max_cu_w, int max_cu_h) {
+  // TLibCommon/TComDataCU.cpp:2788-2801
+  const int off = 8;
+  int hmax = (pic_w + off - cu_x - 1) * 4, hmin = (-max_cu_w - off - cu_x + 1) * 4;
+  int vmax = (pic_h + off - cu_y - 1) * 4, vmin = (-max_cu_h - off - cu_y + 1) * 4;
+  x = std::min(hmax, std::max(hmin, x));
+  y = std::min(vmax, std::max(vmin, y));
+}
+
+void hmb200_set_search_range(hmb200_mv pred, int search_range, int cu_x, int cu_y, int pic_w, int pic_h, int max_cu_w, int max_cu_h,
+                             hmb200_mv* lt, hmb200_mv* rb) {
+  int px = pred.x, py = pred.y;
+  clip_mv(px, py, cu_x, cu_y, pic_w, pic_h, max_cu_w, max_cu_h);
+  // TComMv components are Shorts: the sums wrap to 16 bits before the second clip (TLibCommon/TComMv.h:53-54)
+  int lx = (int16_t)(px - (search_range << 2)), ly = (int16_t)(py - (search_range << 2));
+  int rx = (int16_t)(px + (search_range << 2)), ry = (int16_t)(py + (search_range << 2));
+  clip_mv(lx, ly, cu_x, cu_y, pic_w, pic_h, max_cu_w, max_cu_h);
+  clip_mv(rx, ry, cu_x, cu_y, pic_w, pic_h, max_cu_w, max_cu_h);
+  lt->x = lx >> 2; lt->y = ly >> 2; rb->x = rx >> 2; rb->y = ry >> 2;      // arithmetic shifts of Shorts
+}
+
+int hmb200_build_canonical_jobs(int pic_w, int pic_h, int max_cu, int search_range, uint32_t lambda_cost, hmb200_mv pred,
+                                int ctu_first, int ctu_count, hmb200_pu_job* jobs, int capacity) {
+  if (pic_w <= 0 || pic_h <= 0 || max_cu < 8 || max_cu > 64 || (max_cu & (max_cu - 1))) return HMB200_ERR_ARG;
+  const int ctus_x = (pic_w + max_cu - 1) / max_cu, ctus_y = (pic_h + max_cu - 1) / max_cu;
+  const int n_ctus = ctus_x * ctus_y;
+  if (ctu_first < 0) ctu_first = 0;
+  int ctu_end = (ctu_count < 0) ? n_ctus : std::min(n_ctus, ctu_first + ctu_count);
+  int count = 0;
+  auto emit = [&](int cu_x, int cu_y, int px, int py, int w, int h) {
+    if (count < capacity && jobs) {
+      hmb200_pu_job j;
+      j.pu_x = px; j.pu_y = py; j.w = w; j.h = h;
+      hmb200_mv lt, rb;
+      hmb200_set_search_range(pred, search_range, cu_x, cu_y, pic_w, pic_h, max_cu, max_cu, &lt, &rb);
+      j.lt_x = lt.x; j.lt_y = lt.y; j.rb_x = rb.x; j.rb_y = rb.y;
+      j.pred_x = pred.x; j.pred_y = pred.y; j.lambda_cost = lambda_cost; j.reserved = 0;
+      jobs[count] = j;
+    }
+    count++;
+  };
+  for (int ctu = ctu_first; ctu < ctu_end; ctu++) {
+    const int ox = (ctu % ctus_x) * max_cu, oy = (ctu / ctus_x) * max_cu;
+    int depth = 0;
+    for (int s = max_cu; s >= 8; s >>= 1, depth++) {
+      for (int cy = oy; cy < oy + max_cu; cy += s)
+        for (int cx = ox; cx < ox + max_cu; cx += s) {
+          if (cx + s > pic_w || cy + s > pic_h) continue;          // the encoder only tests CUs inside the picture
+          const int q = s >> 2;
+          emit(cx, cy, cx, cy, s, s);                                              // SIZE_2Nx2N
+          emit(cx, cy, cx, cy, s, s / 2);  emit(cx, cy, cx, cy + s / 2, s, s / 2);  // SIZE_2NxN
+          emit(cx, cy, cx, cy, s / 2, s);  emit(cx, cy, cx + s / 2, cy, s / 2, s);  // SIZE_Nx2N
+          if (s > 8) {                                                              // AMP: not for the smallest CU
+            emit(cx, cy, cx, cy, s, q);      emit(cx, cy, cx, cy + q, s, s - q);    // SIZE_2NxnU
+            emit(cx, cy, cx, cy, s, s - q);  emit(cx, cy, cx, cy + s - q, s, q);    // SIZE_2NxnD
+            emit(cx, cy, cx, cy, q, s);      emit(cx, cy, cx + q, cy, s - q, s);    // SIZE_nLx2N
+            emit(cx, cy, cx, cy, s - q, s);  emit(cx, cy, cx + s - q, cy, q, s);    // SIZE_nRx2N
+          }
+        }
+    }
+  }
+  return count;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// planes
+// ------------------------------------------------------------------------------------------------------------------
+int hmb200_register_plane(const int16_t* host_origin, int stride, int width, int height, int margin_x, int margin_y,
+                          int bit_depth, int kind, int poc) {
+  NEED_READY();
+  if (!host_origin || width <= 0 || height <= 0 || margin_x < 0 || margin_y < 0 || stride < width + 2 * margin_x ||
+      bit_depth < 8 || bit_depth > 16)
+    return fail(HMB200_ERR_ARG, "hmb200_register_plane: bad geometry");
+  int id = alloc_plane_slot();
+  Plane& p = g.planes[id];
+  p = Plane();
+  int rc = make_plane(p, width, height, margin_x, margin_y, bit_depth);
+  if (rc != HMB200_OK) return rc;
+  int total_w = width + 2 * margin_x, total_h = height + 2 * margin_y;
+  const int16_t* src = host_origin - (ptrdiff_t)margin_y * stride - margin_x;
+  size_t bytes = (size_t)total_w * total_h * sizeof(int16_t);
+  if ((rc = ensure_pinned(bytes)) != HMB200_OK || (rc = ensure_dstage(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
+  int16_t* pin = reinterpret_cast<int16_t*>(g.pinned);
+  for (int y = 0; y < total_h; y++) memcpy(pin + (size_t)y * total_w, src + (size_t)y * stride, (size_t)total_w * sizeof(int16_t));
+  CUDA_TRY(cudaMemcpyAsync(g.dstage, pin, bytes, cudaMemcpyHostToDevice, g.stream));
+  dim3 grid((total_w + 255) / 256, total_h);
+  if (p.d.bytes_per_sample == 1)
+    k_narrow_plane<uint8_t><<<grid, 256, 0, g.stream>>>(reinterpret_cast<const int16_t*>(g.dstage), total_w,
+                                                        reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, total_w, total_h);
+  else
+    k_narrow_plane<uint16_t><<<grid, 256, 0, g.stream>>>(reinterpret_cast<const int16_t*>(g.dstage), total_w,
+                                                         reinterpret_cast<uint16_t*>(p.d.base), p.d.pitch, total_w, total_h);
+  g.launches++;
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  p.host_lo = src; p.host_hi = src + (size_t)(total_h - 1) * stride + total_w; p.host_stride = stride;
+  p.kind = kind; p.poc = poc;
+  return id;
+}
+
+int hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width, int height, int margin_x, int margin_y,
+                             int kind, int poc) {
+  NEED_READY();
+  if (!host_samples || width <= 0 || height <= 0 || stride < width || margin_x < 0 || margin_y < 0)
+    return fail(HMB200_ERR_ARG, "hmb200_register_plane_u8: bad geometry");
+  int id = alloc_plane_slot();
+  Plane& p = g.planes[id];
+  p = Plane();
+  int rc = make_plane(p, width, height, margin_x, margin_y, 8);
+  if (rc != HMB200_OK) return rc;
+  size_t bytes = (size_t)width * height;
+  if ((rc = ensure_pinned(bytes)) != HMB200_OK || (rc = ensure_dstage(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
+  uint8_t* pin = reinterpret_cast<uint8_t*>(g.pinned);
+  for (int y = 0; y < height; y++) memcpy(pin + (size_t)y * width, host_samples + (size_t)y * stride, (size_t)width);
+  CUDA_TRY(cudaMemcpyAsync(g.dstage, pin, bytes, cudaMemcpyHostToDevice, g.stream));
+  dim3 grid((width + 2 * margin_x + 255) / 256, height + 2 * margin_y);
+  k_pad_plane_u8<<<grid, 256, 0, g.stream>>>(reinterpret_cast<const uint8_t*>(g.dstage), width,
+                                             reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, width, height, margin_x, margin_y);
+  g.launches++;
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  p.kind = kind; p.poc = poc;
+  return id;
+}
+
+int hmb200_read_plane(int plane_id, int16_t* dst_origin, int dst_stride) {
+  NEED_READY();
+  Plane* p = get_plane(plane_id);
+  if (!p || !dst_origin) return fail(HMB200_ERR_ARG, "hmb200_read_plane: unknown plane");
+  int total_w = p->d.width + 2 * p->d.margin_x, total_h = p->d.height + 2 * p->d.margin_y;
+  if (dst_stride < total_w) return fail(HMB200_ERR_ARG, "hmb200_read_plane: dst_stride too small");
+  size_t bytes = (size_t)total_w * total_h * sizeof(int16_t);
+  int rc;
+  if ((rc = ensure_pinned(bytes)) != HMB200_OK || (rc = ensure_dstage(bytes)) != HMB200_OK) return rc;
+  dim3 grid((total_w + 255) / 256, total_h);
+  if (p->d.bytes_per_sample == 1)
+    k_widen_plane<uint8_t><<<grid, 256, 0, g.stream>>>(reinterpret_cast<const uint8_t*>(p->d.base), p->d.pitch,
+                                                       reinterpret_cast<int16_t*>(g.dstage), total_w, total_w, total_h);
+  else
+    k_widen_plane<uint16_t><<<grid, 256, 0, g.stream>>>(reinterpret_cast<const uint16_t*>(p->d.base), p->d.pitch,
+                                                        reinterpret_cast<int16_t*>(g.dstage), total_w, total_w, total_h);
+  g.launches++;
+  CUDA_TRY(cudaMemcpyAsync(g.pinned, g.dstage, bytes, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  const int16_t* pin = reinterpret_cast<const int16_t*>(g.pinned);
+  int16_t* dst = dst_origin - (ptrdiff_t)p->d.margin_y * dst_stride - p->d.margin_x;
+  for (int y = 0; y < total_h; y++) memcpy(dst + (size_t)y * dst_stride, pin + (size_t)y * total_w, (size_t)total_w * sizeof(int16_t));
+  return HMB200_OK;
+}
+
+void hmb200_release_plane(int plane_id) {
+  Plane* p = get_plane(plane_id);
+  if (!p) return;
+  cudaStreamSynchronize(g.stream);
+  if (p->d.base) cudaFree(p->d.base);
+  *p = Plane();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// distortion table
+// ------------------------------------------------------------------------------------------------------------------
+uint32_t hmb200_dist(const hmb200_dist_param* dp) {
+  auto die = [](const char* m) { fprintf(stderr, "hmb200_dist: %s (%s)\n", m, g_err.c_str()); abort(); };
+  if (!g.ready) die("library not initialised");
+  if (!dp || !dp->pOrg || !dp->pCur) die("null DistParam");
+  if (dp->bApplyWeight) die("weighted prediction is out of scope (bApplyWeight must be false)");
+  if (dp->iStep != 1) die("iStep must be 1");
+  int w = dp->iCols, h = dp->iRows;
+  if (w <= 0 || h <= 0 || w > 64 || h > 64) die("block size out of range");
+  size_t n = (size_t)w * h;
+  if (ensure_pinned(2 * n * sizeof(int16_t) + 64) != HMB200_OK || ensure_dstage(2 * n * sizeof(int16_t) + sizeof(DistTask) + 64) != HMB200_OK)
+    die("allocation failed");
+  int16_t* pin = reinterpret_cast<int16_t*>(g.pinned);
+  for (int y = 0; y < h; y++) {
+    memcpy(pin + (size_t)y * w, dp->pOrg + (ptrdiff_t)y * dp->iStrideOrg, (size_t)w * sizeof(int16_t));
+    memcpy(pin + n + (size_t)y * w, dp->pCur + (ptrdiff_t)y * dp->iStrideCur, (size_t)w * sizeof(int16_t));
+  }
+  int16_t* d = reinterpret_cast<int16_t*>(g.dstage);
+  size_t task_off = ((2 * n * sizeof(int16_t) + 15) / 16) * 16;
+  DistTask t{d, d + n, w, w, w, h, dp->iSubShift, 0};
+  memcpy(reinterpret_cast<char*>(g.pinned) + task_off, &t, sizeof(t));
+  uint32_t* d_out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(g.dstage) + task_off + sizeof(DistTask));
+  if (cudaMemcpyAsync(g.dstage, g.pinned, task_off + sizeof(DistTask), cudaMemcpyHostToDevice, g.stream) != cudaSuccess) die("H2D failed");
+  k_dist_generic<int16_t><<<1, 128, 0, g.stream>>>(reinterpret_cast<const DistTask*>(reinterpret_cast<char*>(g.dstage) + task_off),
+                                                   d_out, 1, dp->func, dp->bitDepth);
+  g.launches++;
+  uint32_t out = 0;
+  if (cudaMemcpyAsync(&out, d_out, sizeof(out), cudaMemcpyDeviceToHost, g.stream) != cudaSuccess ||
+      cudaStreamSynchronize(g.stream) != cudaSuccess) { g_err = cudaGetErrorString(cudaGetLastError()); die("kernel failed"); }
+  return out;
+}
+
+int hmb200_dist_batch(int func, int bit_depth, int n, const hmb200_dist_desc* descs, uint32_t* out) {
+  NEED_READY();
+  if (n <= 0) return HMB200_OK;
+  if (!descs || !out || func < 0 || func > 3) return fail(HMB200_ERR_ARG, "hmb200_dist_batch: bad arguments");
+  std::vector<DistTask> tasks((size_t)n);
+  int bps = 0;
+  for (int i = 0; i < n; i++) {
+    const hmb200_dist_desc& d = descs[i];
+    Plane* po = get_plane(d.org_plane); Plane* pc = get_plane(d.cur_plane);
+    if (!po || !pc) return fail(HMB200_ERR_ARG, "hmb200_dist_batch: unknown plane");
+    if (po->d.bytes_per_sample != pc->d.bytes_per_sample) return fail(HMB200_ERR_ARG, "hmb200_dist_batch: planes differ in sample size");
+    if (bps && bps != po->d.bytes_per_sample) return fail(HMB200_ERR_ARG, "hmb200_dist_batch: mixed sample sizes in one batch");
+    bps = po->d.bytes_per_sample;
+    if (d.w <= 0 || d.h <= 0 || d.w > 64 || d.h > 64) return fail(HMB200_ERR_ARG, "hmb200_dist_batch: block size out of range");
+    auto addr = [&](Plane* p, int x, int y) {
+      return reinterpret_cast<char*>(p->d.base) + ((size_t)(y + p->d.margin_y) * p->d.pitch + (x + p->d.margin_x)) * bps;
+    };
+    tasks[i] = DistTask{addr(po, d.org_x, d.org_y), addr(pc, d.cur_x, d.cur_y), po->d.pitch, pc->d.pitch, d.w, d.h, d.sub_shift, 0};
+  }
+  size_t tb = tasks.size() * sizeof(DistTask), ob = (size_t)n * sizeof(uint32_t);
+  int rc;
+  if ((rc = ensure_dstage(tb + ob)) != HMB200_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(g.dstage, tasks.data(), tb, cudaMemcpyHostToDevice, g.stream));
+  uint32_t* d_out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(g.dstage) + tb);
+  int blocks = (n + 3) / 4;
+  if (bps == 1) k_dist_generic<uint8_t><<<blocks, 128, 0, g.stream>>>(reinterpret_cast<const DistTask*>(g.dstage), d_out, n, func, bit_depth);
+  else          k_dist_generic<int16_t><<<blocks, 128, 0, g.stream>>>(reinterpret_cast<const DistTask*>(g.dstage), d_out, n, func, bit_depth);
+  g.launches++;
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  return HMB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// batched searches
+// ------------------------------------------------------------------------------------------------------------------
+hmb200_prepared* hmb200_prepare_jobs(const hmb200_pu_job* jobs, int njobs, int flags, int bit_depth) {
+  if (!g.ready) { fail(HMB200_ERR_STATE, "hmb200_init has not succeeded"); return nullptr; }
+  if (njobs < 0 || (njobs > 0 && !jobs)) { fail(HMB200_ERR_ARG, "hmb200_prepare_jobs: bad arguments"); return nullptr; }
+  auto* p = new hmb200_prepared();
+  p->n = njobs; p->flags = flags; p->bit_depth = bit_depth;
+  p->tasks.resize((size_t)njobs);
+  for (int i = 0; i < njobs; i++) {
+    const hmb200_pu_job& j = jobs[i];
+    if (!supported_pu(j.w, j.h) || j.rb_x < j.lt_x || j.rb_y < j.lt_y ||
+        (int64_t)(j.rb_x - j.lt_x + 1) * (j.rb_y - j.lt_y + 1) > (int64_t)1 << 24) {
+      fail(HMB200_ERR_ARG, "hmb200_prepare_jobs: unsupported PU size or empty/oversized window in job " + std::to_string(i));
+      delete p; return nullptr;
+    }
+    int ss = ((flags & HMB200_FLAG_FEN) && j.h > 8) ? 1 : 0;
+    p->tasks[i] = SearchTask{j.pu_x, j.pu_y, j.pu_x, j.pu_y, j.w, j.h, j.lt_x, j.lt_y, j.rb_x, j.rb_y, j.pred_x, j.pred_y, j.lambda_cost, ss};
+    uint64_t nc = (uint64_t)(j.rb_x - j.lt_x + 1) * (uint64_t)(j.rb_y - j.lt_y + 1);
+    p->cand_sads += nc;
+    p->abs_diffs += nc * (uint64_t)j.w * (uint64_t)(j.h >> ss);
+  }
+  if (njobs > 0) {
+    if (cudaMalloc(&p->d_tasks, (size_t)njobs * sizeof(SearchTask)) != cudaSuccess ||
+        cudaMalloc(&p->d_results, (size_t)njobs * sizeof(hmb200_pu_result)) != cudaSuccess ||
+        cudaMemcpyAsync(p->d_tasks, p->tasks.data(), (size_t)njobs * sizeof(SearchTask), cudaMemcpyHostToDevice, g.stream) != cudaSuccess ||
+        cudaMemsetAsync(p->d_results, 0, (size_t)njobs * sizeof(hmb200_pu_result), g.stream) != cudaSuccess ||
+        cudaStreamSynchronize(g.stream) != cudaSuccess) {
+      fail(HMB200_ERR_CUDA, std::string("hmb200_prepare_jobs: ") + cudaGetErrorString(cudaGetLastError()));
+      hmb200_free_prepared(p); return nullptr;
+    }
+    if (bit_depth == 8) {
+      std::string why;
+      if (!search8_build_schedule(p->tasks, g.sm_count, g.stream, &p->sched, &why)) {
+        fail(HMB200_ERR_CUDA, why); hmb200_free_prepared(p); return nullptr;
+      }
+    }
+  }
+  return p;
+}
+
+void hmb200_free_prepared(hmb200_prepared* p) {
+  if (!p) return;
+  if (g.ready) cudaStreamSynchronize(g.stream);
+  if (p->d_tasks) cudaFree(p->d_tasks);
+  if (p->d_results) cudaFree(p->d_results);
+  search8_free_schedule(&p->sched);
+  delete p;
+}
+
+int hmb200_prepared_work(const hmb200_prepared* p, uint64_t* cand_sads, uint64_t* abs_diffs) {
+  if (!p) return fail(HMB200_ERR_ARG, "null handle");
+  if (cand_sads) *cand_sads = p->cand_sads;
+  if (abs_diffs) *abs_diffs = p->abs_diffs;
+  return HMB200_OK;
+}
+
+int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
+  NEED_READY();
+  if (!p) return fail(HMB200_ERR_ARG, "null handle");
+  Plane* pc = get_plane(cur_plane); Plane* pr = get_plane(ref_plane);
+  if (!pc || !pr) return fail(HMB200_ERR_ARG, "hmb200_run_prepared: unknown plane");
+  if (pr->d.bit_depth != p->bit_depth) return fail(HMB200_ERR_ARG, "hmb200_run_prepared: bit depth differs from prepare_jobs");
+  if (p->n == 0) return HMB200_OK;
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  bool fast = pc->d.bytes_per_sample == 1 && pr->d.bytes_per_sample == 1 && pr->has_maps && p->sched.n_groups > 0;
+  if (fast) {
+    g.launches += search8_launch(p->sched, p->d_tasks, p->d_results, pc->d, pr->d, pr->maps, g.sm_count, g.stream);
+    // shapes the tiled kernel does not cover were scheduled into sched.d_leftover (task indices)
+    CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+    dispatch_generic(p->d_tasks, p->d_results, p->n, pc->d, pr->d, p->flags, /*do_search=*/false, nullptr);
+  } else {
+    dispatch_generic(p->d_tasks, p->d_results, p->n, pc->d, pr->d, p->flags, /*do_search=*/true, g.ev[1]);
+  }
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaGetLastError());
+  return HMB200_OK;
+}
+
+int hmb200_last_timing(float* total_ms, float* search_ms, float* frac_ms) {
+  NEED_READY();
+  CUDA_TRY(cudaEventSynchronize(g.ev[2]));
+  CUDA_TRY(cudaEventElapsedTime(&g.last_total_ms, g.ev[0], g.ev[2]));
+  CUDA_TRY(cudaEventElapsedTime(&g.last_search_ms, g.ev[0], g.ev[1]));
+  CUDA_TRY(cudaEventElapsedTime(&g.last_frac_ms, g.ev[1], g.ev[2]));
+  if (total_ms) *total_ms = g.last_total_ms;
+  if (search_ms) *search_ms = g.last_search_ms;
+  if (frac_ms) *frac_ms = g.last_frac_ms;
+  return HMB200_OK;
+}
+
+int hmb200_fetch_results(hmb200_prepared* p, hmb200_pu_result* results) {
+  NEED_READY();
+  if (!p || (p->n > 0 && !results)) return fail(HMB200_ERR_ARG, "hmb200_fetch_results: bad arguments");
+  if (p->n == 0) return HMB200_OK;
+  CUDA_TRY(cudaMemcpyAsync(results, p->d_results, (size_t)p->n * sizeof(hmb200_pu_result), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  return HMB200_OK;
+}
+
+int hmb200_me_jobs(int cur_plane, int ref_plane, const hmb200_pu_job* jobs, int njobs, int flags, hmb200_pu_result* results) {
+  NEED_READY();
+  Plane* pr = get_plane(ref_plane);
+  if (!pr) return fail(HMB200_ERR_ARG, "hmb200_me_jobs: unknown reference plane");
+  hmb200_prepared* p = hmb200_prepare_jobs(jobs, njobs, flags, pr->d.bit_depth);
+  if (!p) return g_err.empty() ? HMB200_ERR_ARG : (g_err.find("cuda") != std::string::npos ? HMB200_ERR_CUDA : HMB200_ERR_ARG);
+  int rc = hmb200_run_prepared(p, cur_plane, ref_plane);
+  if (rc == HMB200_OK) rc = hmb200_fetch_results(p, results);
+  hmb200_free_prepared(p);
+  return rc;
+}
+
+int hmb200_me_ctu_row(int cur_plane, int ref_plane, int ctu_row, int max_cu, const hmb200_pu_job* jobs, int njobs, int flags,
+                      hmb200_pu_result* results) {
+  NEED_READY();
+  if (max_cu <= 0) return fail(HMB200_ERR_ARG, "hmb200_me_ctu_row: max_cu must be positive");
+  for (int i = 0; i < njobs; i++)
+    if (jobs[i].pu_y / max_cu != ctu_row) return fail(HMB200_ERR_ARG, "hmb200_me_ctu_row: job outside the CTU row");
+  return hmb200_me_jobs(cur_plane, ref_plane, jobs, njobs, flags, results);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 1:1 entries (per call, synchronous): exact inside the real encoder where predictors arrive one PU at a time
+// ------------------------------------------------------------------------------------------------------------------
+static int upload_pattern(const hmb200_pattern* key) {
+  if (!key || !key->roi || !supported_pu(key->width, key->height)) return fail(HMB200_ERR_ARG, "unsupported pattern");
+  int rc = ensure_pinned(64 * 64 * sizeof(int16_t));
+  if (rc != HMB200_OK) return rc;
+  int16_t* pin = reinterpret_cast<int16_t*>(g.pinned);
+  for (int y = 0; y < key->height; y++)
+    memcpy(pin + (size_t)y * key->width, key->roi + (ptrdiff_t)y * key->stride, (size_t)key->width * sizeof(int16_t));
+  CUDA_TRY(cudaMemcpy2DAsync(g.pattern.d.base, (size_t)g.pattern.d.pitch * sizeof(int16_t), pin, (size_t)key->width * sizeof(int16_t),
+                             (size_t)key->width * sizeof(int16_t), key->height, cudaMemcpyHostToDevice, g.stream));
+  return HMB200_OK;
+}
+
+static int run_single(const hmb200_pattern* key, const int16_t* ref_at_pu, const SearchTask& proto, int flags, bool do_search,
+                      hmb200_pu_result* io) {
+  int rx, ry;
+  Plane* pr = find_plane_by_host(ref_at_pu, &rx, &ry);
+  if (!pr) return fail(HMB200_ERR_ARG, "reference pointer does not fall into a registered plane");
+  if (pr->d.bit_depth != key->bit_depth) return fail(HMB200_ERR_ARG, "pattern bit depth differs from the reference plane");
+  int rc = upload_pattern(key);
+  if (rc != HMB200_OK) return rc;
+  SearchTask t = proto;
+  t.org_x = 0; t.org_y = 0; t.ref_x = rx; t.ref_y = ry; t.w = key->width; t.h = key->height;
+  size_t need = sizeof(SearchTask) + sizeof(hmb200_pu_result) + 64;
+  if ((rc = ensure_dstage(need)) != HMB200_OK) return rc;
+  SearchTask* d_t = reinterpret_cast<SearchTask*>(g.dstage);
+  hmb200_pu_result* d_r = reinterpret_cast<hmb200_pu_result*>(reinterpret_cast<char*>(g.dstage) + 64);
+  CUDA_TRY(cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(d_r, io, sizeof(*io), cudaMemcpyHostToDevice, g.stream));
+  dispatch_generic(d_t, d_r, 1, g.pattern.d, pr->d, flags, do_search, nullptr);
+  CUDA_TRY(cudaMemcpyAsync(io, d_r, sizeof(*io), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  return HMB200_OK;
+}
+
+int hmb200_pattern_search(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride, hmb200_mv lt, hmb200_mv rb,
+                          const hmb200_cost_state* cs, int flags, hmb200_mv* mv_out, uint32_t* sad_out) {
+  NEED_READY();
+  (void)ref_stride;
+  if (!key || !cs || !mv_out || !sad_out || rb.x < lt.x || rb.y < lt.y) return fail(HMB200_ERR_ARG, "hmb200_pattern_search: bad arguments");
+  SearchTask t{};
+  t.lt_x = lt.x; t.lt_y = lt.y; t.rb_x = rb.x; t.rb_y = rb.y; t.pred_x = cs->pred.x; t.pred_y = cs->pred.y;
+  t.lambda_cost = cs->lambda_cost;
+  t.sub_shift = ((flags & HMB200_FLAG_FEN) && key->height > 8) ? 1 : 0;
+  hmb200_pu_result r{};
+  int rc = run_single(key, ref_at_pu, t, flags & ~HMB200_FLAG_FRAC, true, &r);
+  if (rc != HMB200_OK) return rc;
+  mv_out->x = r.mv_x; mv_out->y = r.mv_y; *sad_out = r.sad;
+  return HMB200_OK;
+}
+
+int hmb200_pattern_search_frac(int lossless, const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride, hmb200_mv mv_int,
+                               const hmb200_cost_state* cs, int flags, hmb200_mv* half_out, hmb200_mv* qter_out, uint32_t* cost_out) {
+  NEED_READY();
+  (void)ref_stride;
+  if (!key || !cs || !half_out || !qter_out || !cost_out) return fail(HMB200_ERR_ARG, "hmb200_pattern_search_frac: bad arguments");
+  SearchTask t{};
+  t.pred_x = cs->pred.x; t.pred_y = cs->pred.y; t.lambda_cost = cs->lambda_cost;
+  hmb200_pu_result r{};
+  r.mv_x = mv_int.x; r.mv_y = mv_int.y;
+  int f = HMB200_FLAG_FRAC | (((flags & HMB200_FLAG_HADME) && !lossless) ? HMB200_FLAG_HADME : 0);
+  int rc = run_single(key, ref_at_pu, t, f, false, &r);
+  if (rc != HMB200_OK) return rc;
+  half_out->x = r.half_x; half_out->y = r.half_y; qter_out->x = r.qter_x; qter_out->y = r.qter_y; *cost_out = r.frac_cost;
+  return HMB200_OK;
+}
+
+} // extern "C"
