@@ -9,7 +9,6 @@
 #include <vector>
 #include <algorithm>
 #include <cuda_runtime.h>
-#include <cuda.h>
 #include "hmb200_device.cuh"
 #include "hmb200_generic.cuh"
 #include "hmb200_search8.cuh"
@@ -26,9 +25,9 @@ struct Plane {
   int host_stride = 0;
   int kind = 0, poc = 0;
   size_t bytes = 0;
-  Search8Maps maps{};                 // TMA descriptors (8-bit planes only)
-  bool has_maps = false;
 };
+
+constexpr int N_SIDE = 4;
 
 struct State {
   bool ready = false;
@@ -36,13 +35,14 @@ struct State {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};     // side streams for concurrent variant kernels
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<Plane> planes;
   void* pinned = nullptr; size_t pinned_bytes = 0;
   void* dstage = nullptr; size_t dstage_bytes = 0;     // device staging for plane uploads / per-call blocks
   Plane pattern;                                       // 64x64 int16 pattern buffer for the 1:1 entries
   uint64_t launches = 0;
   float last_total_ms = 0, last_search_ms = 0, last_frac_ms = 0;
-  EncodeTiledFn encode = nullptr;
 };
 
 State g;
@@ -89,12 +89,6 @@ int make_plane(Plane& p, int width, int height, int mx, int my, int bit_depth) {
   p.d.bytes_per_sample = bps; p.d.bit_depth = bit_depth;
   p.bytes = (size_t)pitch_bytes * total_h;
   CUDA_TRY(cudaMalloc(&p.d.base, p.bytes));
-  p.has_maps = false;
-  if (bps == 1) {
-    std::string why;
-    if (!search8_make_maps(g.encode, p.d, &p.maps, &why)) { cudaFree(p.d.base); p.d.base = nullptr; return fail(HMB200_ERR_CUDA, why); }
-    p.has_maps = true;
-  }
   p.used = true;
   return HMB200_OK;
 }
@@ -122,10 +116,13 @@ bool supported_pu(int w, int h) { return w >= 4 && h >= 4 && w <= 64 && h <= 64 
 
 template <typename RefT, typename OrgT>
 void launch_generic(const SearchTask* d_tasks, hmb200_pu_result* d_res, int n, const DevPlane& cur, const DevPlane& ref,
-                    int flags, bool do_search, cudaEvent_t mid) {
+                    int flags, bool do_search, cudaEvent_t mid, const int* d_index = nullptr, int n_index = 0) {
   if (do_search) {
-    k_search_generic<RefT, OrgT><<<n, 256, 0, g.stream>>>(d_tasks, d_res, cur, ref);
-    g.launches++;
+    const int blocks = d_index ? n_index : n;
+    if (blocks > 0) {
+      k_search_generic<RefT, OrgT><<<blocks, 256, 0, g.stream>>>(d_tasks, d_res, cur, ref, d_index);
+      g.launches++;
+    }
   }
   if (mid) cudaEventRecord(mid, g.stream);
   if (flags & HMB200_FLAG_FRAC) {
@@ -177,11 +174,9 @@ int hmb200_init(int device) {
   g.sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   for (auto& ev : g.ev) CUDA_TRY(cudaEventCreate(&ev));
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-  if (qres != cudaDriverEntryPointSuccess || !fn) return fail(HMB200_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-  g.encode = reinterpret_cast<EncodeTiledFn>(fn);
+  for (auto& st : g.side) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
+  for (auto& ev : g.ev_join) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   int rc = search8_configure(&g_err);
   if (rc != HMB200_OK) return rc;
   g.device = device;
@@ -205,6 +200,9 @@ void hmb200_shutdown(void) {
   if (g.dstage) cudaFree(g.dstage);
   g.pinned = nullptr; g.pinned_bytes = 0; g.dstage = nullptr; g.dstage_bytes = 0;
   for (auto& ev : g.ev) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+  for (auto& st : g.side) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; }
+  if (g.ev_fork) { cudaEventDestroy(g.ev_fork); g.ev_fork = nullptr; }
+  for (auto& ev : g.ev_join) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
   cudaStreamDestroy(g.stream); g.stream = nullptr;
   g.ready = false; g.device = -1;
 }
@@ -503,10 +501,41 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
   if (pr->d.bit_depth != p->bit_depth) return fail(HMB200_ERR_ARG, "hmb200_run_prepared: bit depth differs from prepare_jobs");
   if (p->n == 0) return HMB200_OK;
   CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
-  bool fast = pc->d.bytes_per_sample == 1 && pr->d.bytes_per_sample == 1 && pr->has_maps && p->sched.n_groups > 0;
+  const Search8Schedule& sc = p->sched;
+  bool fast = pc->d.bytes_per_sample == 1 && pr->d.bytes_per_sample == 1 && sc.n_jobs > 0 &&
+              pc->d.margin_x % 16 == 0 && pr->d.margin_x % 16 == 0;
   if (fast) {
-    g.launches += search8_launch(p->sched, p->d_tasks, p->d_results, pc->d, pr->d, pr->maps, g.sm_count, g.stream);
-    // shapes the tiled kernel does not cover were scheduled into sched.d_leftover (task indices)
+    // every staged byte must lie inside the padded buffers (the reference would read outside its planes too)
+    auto inside = [](const DevPlane& d, int x0, int y0, int x1, int y1) {
+      return x0 + d.margin_x >= 0 && x1 + d.margin_x <= d.pitch && y0 + d.margin_y >= 0 && y1 + d.margin_y <= d.height + 2 * d.margin_y;
+    };
+    if (!inside(pr->d, sc.min_x, sc.min_y, sc.max_x, sc.max_y))
+      return fail(HMB200_ERR_ARG, "hmb200_run_prepared: a search window leaves the padded reference plane");
+    if (!inside(pc->d, sc.omin_x, sc.omin_y, sc.omax_x, sc.omax_y))
+      return fail(HMB200_ERR_ARG, "hmb200_run_prepared: a PU leaves the padded current plane");
+    CUDA_TRY(cudaMemsetAsync(sc.d_keys, 0xff, (size_t)sc.n_tasks * sizeof(unsigned long long), g.stream));
+    // one launch per tile variant present, spread over side streams so that their tails overlap
+    const S8Kernel* kern = search8_kernels();
+    CUDA_TRY(cudaEventRecord(g.ev_fork, g.stream));
+    int order[S8V_COUNT], used = 0;
+    for (int v = S8V_COUNT - 1; v >= 0; v--) if (sc.unit_count[v] > 0) order[used++] = v;     // wide tiles first
+    for (int k = 0; k < used; k++) {
+      const int v = order[k];
+      cudaStream_t st = (k == 0) ? g.stream : g.side[(k - 1) % N_SIDE];
+      if (k >= 1 && k <= N_SIDE) CUDA_TRY(cudaStreamWaitEvent(st, g.ev_fork, 0));
+      kern[v]<<<sc.unit_count[v], S8_THREADS, sc.smem_of[v], st>>>(sc.d_units + sc.unit_first[v], sc.d_jobs, sc.d_keys, pc->d, pr->d);
+      g.launches++;
+    }
+    for (int k = 0; k < N_SIDE && k + 1 < used; k++) {
+      CUDA_TRY(cudaEventRecord(g.ev_join[k], g.side[k]));
+      CUDA_TRY(cudaStreamWaitEvent(g.stream, g.ev_join[k], 0));
+    }
+    if (sc.n_leftover > 0) {    // shapes / windows the tiled kernel does not cover
+      k_search_generic<uint8_t, uint8_t><<<sc.n_leftover, 256, 0, g.stream>>>(p->d_tasks, p->d_results, pc->d, pr->d, sc.d_leftover);
+      g.launches++;
+    }
+    k_search8_finalize<<<(sc.n_tasks + 255) / 256, 256, 0, g.stream>>>(p->d_tasks, sc.d_keys, p->d_results, sc.n_tasks);
+    g.launches++;
     CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
     dispatch_generic(p->d_tasks, p->d_results, p->n, pc->d, pr->d, p->flags, /*do_search=*/false, nullptr);
   } else {

@@ -3,16 +3,9 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
-#include <cuda.h>
 #include "../../include/hmb200.h"
 
 namespace hmb200 {
-
-// cuTensorMapEncodeTiled, resolved at run time through cudaGetDriverEntryPoint so that the library loads (and its
-// symbols can be inspected) on machines without libcuda.
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // ---------------------------------------------------------------------------------------------------------------
 // records shared with the host frontend

@@ -28,10 +28,11 @@ struct DistTask {
 // ---------------------------------------------------------------------------------------------------------------
 template <typename RefT, typename OrgT>
 __global__ void __launch_bounds__(256) k_search_generic(const SearchTask* __restrict__ tasks, hmb200_pu_result* __restrict__ out,
-                                                        DevPlane cur_plane, DevPlane ref_plane) {
+                                                        DevPlane cur_plane, DevPlane ref_plane, const int* __restrict__ index) {
   __shared__ int16_t s_org[64 * 64];
   __shared__ unsigned long long s_best[8];
-  const SearchTask t = tasks[blockIdx.x];
+  const int ti = index ? index[blockIdx.x] : (int)blockIdx.x;     // optional indirection: a subset of the task list
+  const SearchTask t = tasks[ti];
   const OrgT* org = plane_at<OrgT>(cur_plane, t.org_x, t.org_y);
   const RefT* ref = plane_at<RefT>(ref_plane, t.ref_x, t.ref_y);
   const int org_stride = cur_plane.pitch, ref_stride = ref_plane.pitch, bit_depth = ref_plane.bit_depth;
@@ -70,10 +71,10 @@ __global__ void __launch_bounds__(256) k_search_generic(const SearchTask* __rest
     uint32_t idx = (uint32_t)(best & 0xffffffffu), cost = (uint32_t)(best >> 32);
     int cy = idx / nx, cx = idx - cy * nx;
     int x = t.lt_x + cx, y = t.lt_y + cy;
-    hmb200_pu_result r = out[blockIdx.x];
+    hmb200_pu_result r = out[ti];
     r.mv_x = x; r.mv_y = y;
     r.sad = cost - mv_cost(t.lambda_cost, mv_bits(x, y, t.pred_x, t.pred_y, 2));   // TEncSearch.cpp:3841
-    out[blockIdx.x] = r;
+    out[ti] = r;
   }
 }
 
