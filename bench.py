@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the HM-16.5 integer-pel full search + quarter-pel SATD refinement path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[2]): 1920x1080 8-bit (coded as 1920x1088, ConformanceWindowMode=1), lowdelay_P
+settings (FEN=1, HadamardME=1), full search +-64 over the canonical all-PU job list (593 PUs per CTU)
+followed by the quarter-pel SATD refinement of every PU.  One step = one (current, reference) frame pair per rank;
+ranks work on independent frame pairs (no collective on the data path, scaling = weak).
+
+Our arm prints `value` (planes resident in HBM, device time from CUDA events on the library's stream) and `e2e`
+(host planes in, host MV field out, through the C-ABI).  `--impl reference` times the unmodified reference
+(oracle/_ref/libhmref.so, HM-16.5 compiled from /root/reference in the build container) on all host cores on a bounded
+sample of the same job list.  Only that arm and the `cpu_baseline` leg execute anything under oracle/.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PIC_W, PIC_H, CODED_H = 1920, 1080, 1088
+SEARCH_RANGE = 64
+LAMBDA_COST = int(np.floor(65536.0 * np.sqrt(0.4624 * 2 ** ((35 - 12) / 3.0))))   # lowdelay-P slice at QP 35
+N_FRAMES = 5                      # distinct synthetic frames per rank -> 4 frame pairs, cycled
+WORKLOAD = "1080p_8bit_lowdelayP_fullsearch64_canonical593_fen1_hadme1_qpel"
+METRIC = "Mpixel/s, full-search +-64 ME with quarter-pel SATD refinement, 1080p"
+INT_PEAK_FILE = os.path.join(ROOT, "profiles", "r01_microbench_int.json")
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def int_simd_peak():
+    """Measured VABSDIFF4.U8.ACC issue peak of this pool's B200 (tools/microbench_int.cu, profiles/): abs-diffs / s."""
+    try:
+        d = json.load(open(INT_PEAK_FILE))
+        lane_ops = max(v for k, v in d.items() if k.startswith("alu_vabsdiff4_acc"))
+        return lane_ops * 1e9 * 4.0, "measured: profiles/r01_microbench_int.json (register-only VABSDIFF4.U8.ACC loop)"
+    except Exception:
+        return 148 * 64 * 4 * 1.965e9, "fallback: 64 lanes/clk/SM x 4 bytes x 148 SMs x 1.965 GHz"
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6500.0, "fallback (B200_PROFILING.md)"
+
+
+def make_frames(rank):
+    from video_codecs_b200 import synth
+    return [synth.luma_frame(PIC_W, CODED_H, t, seed=1234 + 97 * rank) for t in range(N_FRAMES)]
+
+
+def px_per_ctu():
+    n_ctus = ((PIC_W + 63) // 64) * ((CODED_H + 63) // 64)
+    return PIC_W * PIC_H / n_ctus, n_ctus
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (the only users of oracle/)
+# ---------------------------------------------------------------------------------------------------------------------
+def _cpu_checker():
+    from oracle.pyoracle import Oracle, Reference
+    try:
+        return Reference(fen=1, hadme=1), "reference"
+    except (FileNotFoundError, OSError):
+        return Oracle(fen=1, hadme=1), "port"
+
+
+_WORKER = {}
+
+
+def _cpu_worker(args):
+    """One host process: runs the CPU implementation over whole CTUs of one frame pair (inputs cached per process)."""
+    frames_seed, ctus = args
+    if frames_seed not in _WORKER:
+        from video_codecs_b200 import synth, HMB200
+        chk, _ = _cpu_checker()
+        _WORKER[frames_seed] = (chk, HMB200(),          # HMB200: host-side job-list builder only (no GPU call)
+                                synth.pad_plane(synth.luma_frame(PIC_W, CODED_H, 1, seed=frames_seed), 80, 80),
+                                synth.pad_plane(synth.luma_frame(PIC_W, CODED_H, 0, seed=frames_seed), 80, 80))
+    chk, hm, cur, ref = _WORKER[frames_seed]
+    stride = cur.shape[1]
+    o0 = 80 * stride + 80
+    t0 = time.perf_counter()
+    n = 0
+    for c in ctus:
+        jobs = hm.build_canonical_jobs(PIC_W, CODED_H, SEARCH_RANGE, LAMBDA_COST, ctu_first=c, ctu_count=1)
+        chk.run_jobs((cur, o0, stride), (ref, o0, stride), jobs, 8, True)
+        n += 1
+    return time.perf_counter() - t0, n
+
+
+def cpu_sample_single(n_ctus_sample):
+    """Single-thread CPU baseline on the first CTUs of the interior CTU row 8 (bounded sample)."""
+    chk, kind = _cpu_checker()
+    from video_codecs_b200 import synth, HMB200
+    hm = HMB200()
+    cur = synth.pad_plane(synth.luma_frame(PIC_W, CODED_H, 1, seed=1234), 80, 80)
+    ref = synth.pad_plane(synth.luma_frame(PIC_W, CODED_H, 0, seed=1234), 80, 80)
+    stride = cur.shape[1]
+    o0 = 80 * stride + 80
+    first = 8 * 30 + 3
+    jobs = hm.build_canonical_jobs(PIC_W, CODED_H, SEARCH_RANGE, LAMBDA_COST, ctu_first=first, ctu_count=n_ctus_sample)
+    t0 = time.perf_counter()
+    chk.run_jobs((cur, o0, stride), (ref, o0, stride), jobs, 8, True)
+    dt = time.perf_counter() - t0
+    ppc, _ = px_per_ctu()
+    return {"value": n_ctus_sample * ppc / dt / 1e6, "unit": "Mpixel/s", "cores": 1, "kind": kind,
+            "sample": f"{n_ctus_sample} interior CTUs ({len(jobs)} PU searches + refinements) of one 1080p frame pair, "
+                      f"{dt:.1f} s on one host core"}
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    ppc, n_ctus = px_per_ctu()
+    ctx = mp.get_context("spawn")
+    _, kind = _cpu_checker()
+    interior = [r * 30 + c for r in range(2, 15) for c in range(2, 28)]
+    with ctx.Pool(cores) as pool:
+        # calibration: one CTU per core
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(1234, [interior[i]]) for i in range(cores)])
+        t_ctu = time.perf_counter() - t0
+        budget = 150.0 / max(1, args.steps + args.warmup)
+        per_core = int(max(1, min(8, budget // max(t_ctu, 1e-3))))
+        def step(k):
+            base = (k * cores * per_core) % (len(interior) - cores * per_core)
+            work = [(1234, interior[base + i * per_core: base + (i + 1) * per_core]) for i in range(cores)]
+            t = time.perf_counter()
+            pool.map(_cpu_worker, work)
+            return time.perf_counter() - t
+        for k in range(args.warmup):
+            step(k)
+        t_total = 0.0
+        for k in range(args.steps):
+            t_total += step(args.warmup + k)
+    ctus_done = args.steps * cores * per_core
+    value = ctus_done * ppc / t_total / 1e6
+    sample = (f"{cores * per_core} CTUs per step ({per_core} per core, whole canonical job list of each CTU incl. "
+              f"quarter-pel refinement), {args.steps} steps, one process per host core")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "search_range": SEARCH_RANGE, "pus_per_ctu": 593, "sampled": True},
+            "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    from video_codecs_b200 import HMB200, FLAG_FEN, FLAG_HADME, FLAG_FRAC, RESULT_DTYPE
+    hm = HMB200()
+    hm.init(local)
+    flags = FLAG_FEN | FLAG_HADME | FLAG_FRAC
+    frames = make_frames(rank)
+    pairs = [(t + 1, t) for t in range(N_FRAMES - 1)]                       # (current, reference) = (t+1, t)
+    jobs = hm.build_canonical_jobs(PIC_W, CODED_H, SEARCH_RANGE, LAMBDA_COST)
+    prep = hm.prepare_jobs(jobs, flags, 8)
+    work = prep.work()
+    plane_ids = [hm.register_plane_u8(f, 80, 80, kind=0, poc=i) for i, f in enumerate(frames)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        hm.sync()
+
+    def device_step(k):
+        c, r = pairs[k % len(pairs)]
+        flush.zero_()                                   # L2 flush between timed iterations (not timed)
+        torch.cuda.synchronize()
+        prep.run(plane_ids[c], plane_ids[r])
+        hm.sync()
+        return prep.timing()
+
+    for k in range(args.warmup):
+        device_step(k)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = hm.launch_count()
+    t_wall0 = time.perf_counter()
+    tot = srch = frac = 0.0
+    for k in range(args.steps):
+        t = device_step(args.warmup + k)
+        tot += t["total_ms"]; srch += t["search_ms"]; frac += t["frac_ms"]
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall0)
+    launches = hm.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+
+    # ---- end to end through the C-ABI: host planes in, host MV field out, every step ------------------------------
+    out = np.zeros(len(jobs), dtype=RESULT_DTYPE)
+
+    def e2e_step(k):
+        c, r = pairs[k % len(pairs)]
+        idc = hm.register_plane_u8(frames[c], 80, 80, kind=0)       # pinned staging + H2D + border extension on device
+        idr = hm.register_plane_u8(frames[r], 80, 80, kind=1)
+        prep.run(idc, idr)
+        prep.fetch(out)                                             # D2H of the MV field / costs, synchronises
+        hm.release_plane(idc)
+        hm.release_plane(idr)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for k in range(2):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+
+    # ---- reduce over ranks: max time ------------------------------------------------------------------------------
+    vals = torch.tensor([tot, srch, frac, e2e_ms, wall_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    tot, srch, frac, e2e_ms, wall_ms = [float(v) for v in vals.cpu()]
+    clocks = sampler.summary()
+
+    if rank == 0:
+        K = max(1, args.steps)
+        ms_per_step = tot / K
+        mpix_step = PIC_W * PIC_H / 1e6
+        value = world * mpix_step / (ms_per_step / 1e3)
+        e2e_value = world * mpix_step / (e2e_ms / 1e3)
+        peak_abs, peak_src = int_simd_peak()
+        search_s = srch / K / 1e3
+        achieved = work["abs_diffs"] / search_s
+        hbm, hbm_src = hbm_peak()
+        plane_bytes = (PIC_W + 160) * (CODED_H + 160)
+        algo_bytes = 2 * plane_bytes + len(jobs) * (32 + 48)       # both planes once + job list + results
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "picture": f"{PIC_W}x{PIC_H} (coded {PIC_W}x{CODED_H})", "search_range": SEARCH_RANGE,
+                       "pus_per_frame": int(len(jobs)), "pus_per_ctu": 593, "frame_pairs_per_step_per_gpu": 1,
+                       "l2": "flushed between timed iterations (256 MiB write, untimed)", "mpixel_counts": "1920x1080 luma per step"},
+            "cand_sad_per_s": world * work["cand_sads"] / (ms_per_step / 1e3),
+            "search_ms": srch / K, "frac_ms": frac / K, "wall_ms_per_step_incl_flush": wall_ms / K,
+            "roofline": {"bound": "int_alu", "kernel": "k_search8<*> (VABSDIFF4.U8.ACC)", "achieved": achieved / 1e12,
+                         "peak": peak_abs / 1e12, "unit": "Tabsdiff/s", "frac": achieved / peak_abs, "traffic": None,
+                         "peak_source": peak_src,
+                         "algorithmic_absdiffs_per_launch": int(work["abs_diffs"]),
+                         "note": "algorithmic byte abs-diffs as HM executes them (W*H/2 per candidate under FEN for H>8); "
+                                 "per-rank search time incl. key memset + finalize"},
+            "roofline_hbm": {"bound": "hbm", "achieved": algo_bytes / (ms_per_step / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                             "frac": algo_bytes / (ms_per_step / 1e3) / 1e9 / hbm, "traffic": None, "peak_source": hbm_src},
+            "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(2 * PIC_W * CODED_H),
+                    "d2h_bytes_per_step": int(out.nbytes), "ms_per_step": e2e_ms, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_sample_single(args.cpu_ctus)
+        print(json.dumps(line), flush=True)
+    prep.free()
+    hm.shutdown()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-ctus", type=int, default=16, help="CTUs in the single-core cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
