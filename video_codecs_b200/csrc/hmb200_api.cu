@@ -12,6 +12,7 @@
 #include "hmb200_device.cuh"
 #include "hmb200_generic.cuh"
 #include "hmb200_search8.cuh"
+#include "hmb200_frac.cuh"
 
 using namespace hmb200;
 
@@ -152,6 +153,7 @@ struct hmb200_prepared {
   hmb200_pu_result* d_results = nullptr;
   uint64_t cand_sads = 0, abs_diffs = 0;
   Search8Schedule sched;          // tiled 8-bit kernel schedule (empty when not applicable)
+  FracSchedule frac;              // tile tables of the batched quarter-pel refinement
 };
 
 extern "C" {
@@ -467,11 +469,12 @@ hmb200_prepared* hmb200_prepare_jobs(const hmb200_pu_job* jobs, int njobs, int f
       fail(HMB200_ERR_CUDA, std::string("hmb200_prepare_jobs: ") + cudaGetErrorString(cudaGetLastError()));
       hmb200_free_prepared(p); return nullptr;
     }
-    if (bit_depth == 8) {
-      std::string why;
-      if (!search8_build_schedule(p->tasks, g.sm_count, g.stream, &p->sched, &why)) {
-        fail(HMB200_ERR_CUDA, why); hmb200_free_prepared(p); return nullptr;
-      }
+    std::string why;
+    if (bit_depth == 8 && !search8_build_schedule(p->tasks, g.sm_count, g.stream, &p->sched, &why)) {
+      fail(HMB200_ERR_CUDA, why); hmb200_free_prepared(p); return nullptr;
+    }
+    if ((flags & HMB200_FLAG_FRAC) && !frac_build_schedule(p->tasks, g.stream, &p->frac, &why)) {
+      fail(HMB200_ERR_CUDA, why); hmb200_free_prepared(p); return nullptr;
     }
   }
   return p;
@@ -483,6 +486,7 @@ void hmb200_free_prepared(hmb200_prepared* p) {
   if (p->d_tasks) cudaFree(p->d_tasks);
   if (p->d_results) cudaFree(p->d_results);
   search8_free_schedule(&p->sched);
+  frac_free_schedule(&p->frac);
   delete p;
 }
 
@@ -536,10 +540,20 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
     }
     k_search8_finalize<<<(sc.n_tasks + 255) / 256, 256, 0, g.stream>>>(p->d_tasks, sc.d_keys, p->d_results, sc.n_tasks);
     g.launches++;
-    CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
-    dispatch_generic(p->d_tasks, p->d_results, p->n, pc->d, pr->d, p->flags, /*do_search=*/false, nullptr);
   } else {
-    dispatch_generic(p->d_tasks, p->d_results, p->n, pc->d, pr->d, p->flags, /*do_search=*/true, g.ev[1]);
+    dispatch_generic(p->d_tasks, p->d_results, p->n, pc->d, pr->d, p->flags & ~HMB200_FLAG_FRAC, /*do_search=*/true, nullptr);
+  }
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  if (p->flags & HMB200_FLAG_FRAC) {
+    const bool had = (p->flags & HMB200_FLAG_HADME) != 0;
+    int nl;
+    if (pc->d.bytes_per_sample == 1 && pr->d.bytes_per_sample == 1)
+      nl = frac_launch<uint8_t, uint8_t>(p->frac, p->d_tasks, p->d_results, pc->d, pr->d, had, g.stream);
+    else if (pc->d.bytes_per_sample == 2 && pr->d.bytes_per_sample == 2)
+      nl = frac_launch<int16_t, int16_t>(p->frac, p->d_tasks, p->d_results, pc->d, pr->d, had, g.stream);
+    else { dispatch_generic(p->d_tasks, p->d_results, p->n, pc->d, pr->d, p->flags, /*do_search=*/false, nullptr); nl = 0; }
+    if (nl < 0) return fail(HMB200_ERR_CUDA, std::string("frac_launch: ") + cudaGetErrorString(cudaGetLastError()));
+    g.launches += (uint64_t)nl;
   }
   CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
   CUDA_TRY(cudaGetLastError());

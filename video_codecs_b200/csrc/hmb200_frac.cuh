@@ -1,0 +1,266 @@
+// Batched quarter-pel refinement: TEncSearch::xPatternSearchFracDIF (TLibEncoder/TEncSearch.cpp:4240-4276) for many PUs.
+//
+// The reference builds whole-PU half/quarter-pel planes (xExtDIFUpSamplingH/Q, :5338-5539) and then evaluates nine
+// candidates per stage with xGetHADs (TLibCommon/TComRdCost.cpp:1526-1593) or the SAD.  A candidate's distortion is a sum
+// over independent Hadamard tiles (8x8 when both PU dimensions are multiples of 8, else 4x4; per-tile rounding), so
+// here the unit of work is one (PU, candidate, tile): a thread interpolates exactly the samples its tile needs
+// (separable 8-tap, 14-bit intermediates, TComInterpolationFilter.cpp:172-257), transforms and adds the rounded tile
+// SATD to dist[PU][candidate] with one atomicAdd.  No shared memory, no block-level synchronisation, full occupancy for
+// 4x8 PUs and 64x64 PUs alike.  Two stages (half, quarter) with a per-PU argmin kernel after each (xPatternRefinement,
+// TEncSearch.cpp:808-861: candidate order of s_acMvRefineH/Q, strict '<', cost = dist + getCost at scale 1 / 0).
+// The centre candidate of the quarter stage is the half stage's winner: its distortion is reused, not recomputed.
+#pragma once
+#include <string>
+#include <vector>
+#include "hmb200_device.cuh"
+#include "hmb200_generic.cuh"
+
+namespace hmb200 {
+
+constexpr int FRAC_TILE_THREADS = 128;
+
+// tile table entry: PU index (24 bits) | tile column (4 bits) << 24 | tile row (4 bits) << 28
+__host__ __device__ __forceinline__ uint32_t frac_pack_tile(uint32_t pu, uint32_t tx, uint32_t ty) { return pu | (tx << 24) | (ty << 28); }
+
+__device__ __forceinline__ void frac_load_taps(int f, int (&t)[8]) {
+  // TComInterpolationFilter.cpp:57-63 (m_lumaFilter); f == 0 is the pass-through row {0,0,0,64,0,0,0,0}
+  t[0] = (f == 1 || f == 2) ? -1 : 0;
+  t[1] = (f == 0) ? 0 : (f == 3 ? 1 : 4);
+  t[2] = (f == 0) ? 0 : (f == 1 ? -10 : (f == 2 ? -11 : -5));
+  t[3] = (f == 0) ? 64 : (f == 1 ? 58 : (f == 2 ? 40 : 17));
+  t[4] = (f == 0) ? 0 : (f == 1 ? 17 : (f == 2 ? 40 : 58));
+  t[5] = (f == 0) ? 0 : (f == 1 ? -5 : (f == 2 ? -11 : -10));
+  t[6] = (f == 0) ? 0 : (f == 3 ? 4 : (f == 2 ? 4 : 1));
+  t[7] = (f == 2 || f == 3) ? -1 : 0;
+}
+
+// 11 consecutive samples of one row starting at p (any alignment)
+template <typename T>
+__device__ __forceinline__ void frac_load_row(const T* p, int (&px)[11]) {
+  if constexpr (sizeof(T) == 1) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8u;
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+    const uint32_t s0 = __funnelshift_r(w0, w1, sh), s1 = __funnelshift_r(w1, w2, sh), s2 = __funnelshift_r(w2, w3, sh);
+#pragma unroll
+    for (int i = 0; i < 4; i++) px[i] = (int)((s0 >> (8 * i)) & 0xffu);
+#pragma unroll
+    for (int i = 0; i < 4; i++) px[4 + i] = (int)((s1 >> (8 * i)) & 0xffu);
+#pragma unroll
+    for (int i = 0; i < 3; i++) px[8 + i] = (int)((s2 >> (8 * i)) & 0xffu);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 11; i++) px[i] = (int)__ldg(p + i);
+  }
+}
+
+// Interpolated-minus-original differences of one N x N tile at quarter-pel displacement (fx, fy) (fractions; the
+// integer parts are already folded into `ref`, which points at the tile's top-left reference sample).
+// HSKIP / VSKIP: warp-uniform knowledge that fx == 0 / fy == 0 (pass-through taps), which removes the multiplies.
+template <typename RefT, typename OrgT, int N, bool HSKIP, bool VSKIP>
+__device__ __forceinline__ void frac_tile_diff(const RefT* ref, int ref_pitch, const OrgT* org, int org_pitch, int fx, int fy,
+                                               int head, int maxv, int (&d)[N * N]) {
+  int th[8], tv[8];
+  frac_load_taps(fx, th);
+  frac_load_taps(fy, tv);
+  const int hshift = 6 - head, vshift = 6 + head;
+  const int hoff = 8192 << hshift, voff = (1 << (vshift - 1)) + (8192 << 6);
+  constexpr int R0 = VSKIP ? 3 : 0, R1 = VSKIP ? N + 3 : N + 7;          // rows of intermediates that are needed
+#pragma unroll
+  for (int cs = 0; cs < N; cs += 4) {                                    // four columns at a time: 8 x 4 live intermediates
+    int hh[N + 7][4];
+#pragma unroll
+    for (int r = R0; r < R1; r++) {
+      int px[11];
+      frac_load_row<RefT>(ref + (ptrdiff_t)(r - 3) * ref_pitch + (cs - 3), px);
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        int v;
+        if (HSKIP) v = (int16_t)(px[c + 3] << head) - 8192;             // filterCopy isFirst (TComInterpolationFilter.cpp:113-124)
+        else {
+          int sum = 0;
+#pragma unroll
+          for (int t = 0; t < 8; t++) sum += px[c + t] * th[t];
+          v = (int16_t)((sum - hoff) >> hshift);                         // filter<> isFirst: offset -8192 << shift (:196-251)
+        }
+        hh[r][c] = v;
+      }
+      if (r >= R1 - N) {                                                 // an output row is complete
+        const int y = r - (R1 - N);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          int val;
+          if (VSKIP) val = (int16_t)((hh[y + 3][c] + 8192 + (1 << (head - 1))) >> head);     // filterCopy isLast (:126-141)
+          else {
+            int sum = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) sum += hh[y + t][c] * tv[t];
+            val = (int16_t)((sum + voff) >> vshift);                     // filter<> isLast
+          }
+          val = min(max(val, 0), maxv);
+          d[y * N + cs + c] = (int)org[(ptrdiff_t)y * org_pitch + cs + c] - val;
+        }
+      }
+    }
+  }
+}
+
+// stage 0: half-pel candidates around the integer MV; stage 1: quarter-pel candidates 1..8 around the best half.
+// dist: [n_pu][9] accumulators (zeroed by the host; dist[.][0] of stage 1 is written by k_frac_argmin<0>).
+template <typename RefT, typename OrgT, int N, bool HAD>
+__global__ void __launch_bounds__(FRAC_TILE_THREADS)
+k_frac_tiles(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_result* __restrict__ results,
+             const uint32_t* __restrict__ tiles, int n_tiles, uint32_t* __restrict__ dist, DevPlane cur_plane, DevPlane ref_plane) {
+  const int nc = stage == 0 ? 9 : 8;
+  const long long t = (long long)blockIdx.x * FRAC_TILE_THREADS + threadIdx.x;
+  const int chunk = (int)(t / (32 * nc));
+  const int within = (int)(t - (long long)chunk * 32 * nc);
+  const int cand = within >> 5;                                          // warp-uniform
+  const int slot = chunk * 32 + (within & 31);
+  const bool active = slot < n_tiles;
+  int fx = 0, fy = 0;
+  uint32_t pu = 0;
+  const RefT* ref = nullptr;
+  const OrgT* org = nullptr;
+  int ci = 0;
+  if (active) {
+    const uint32_t tile = tiles[slot];
+    pu = tile & 0xffffffu;
+    const int tx = (tile >> 24) & 15, ty = tile >> 28;
+    const SearchTask tk = tasks[pu];
+    const hmb200_pu_result rs = results[pu];
+    int qx, qy;
+    if (stage == 0) { ci = cand; qx = 2 * k_refine_h[ci][0]; qy = 2 * k_refine_h[ci][1]; }
+    else            { ci = cand + 1; qx = 2 * rs.half_x + k_refine_q[ci][0]; qy = 2 * rs.half_y + k_refine_q[ci][1]; }
+    fx = qx & 3; fy = qy & 3;
+    ref = plane_at<RefT>(ref_plane, tk.ref_x + rs.mv_x + (qx >> 2) + tx * N, tk.ref_y + rs.mv_y + (qy >> 2) + ty * N);
+    org = plane_at<OrgT>(cur_plane, tk.org_x + tx * N, tk.org_y + ty * N);
+  }
+  const bool hskip = __all_sync(0xffffffffu, fx == 0), vskip = __all_sync(0xffffffffu, fy == 0);
+  if (!active) return;
+  const int bit_depth = ref_plane.bit_depth;
+  const int head = max(2, 14 - bit_depth), maxv = (1 << bit_depth) - 1;
+  int d[N * N];
+  if (hskip && vskip)  frac_tile_diff<RefT, OrgT, N, true, true>(ref, ref_plane.pitch, org, cur_plane.pitch, fx, fy, head, maxv, d);
+  else if (hskip)      frac_tile_diff<RefT, OrgT, N, true, false>(ref, ref_plane.pitch, org, cur_plane.pitch, fx, fy, head, maxv, d);
+  else if (vskip)      frac_tile_diff<RefT, OrgT, N, false, true>(ref, ref_plane.pitch, org, cur_plane.pitch, fx, fy, head, maxv, d);
+  else                 frac_tile_diff<RefT, OrgT, N, false, false>(ref, ref_plane.pitch, org, cur_plane.pitch, fx, fy, head, maxv, d);
+  uint32_t s;
+  if (HAD) {
+    if constexpr (N == 8) s = (had8x8_abs(d) + 2) >> 2;                  // TComRdCost.cpp:1520
+    else                  s = (had4x4_abs(d) + 1) >> 1;                  // TComRdCost.cpp:1423
+  } else {
+    s = 0;
+#pragma unroll
+    for (int i = 0; i < N * N; i++) s += (uint32_t)abs(d[i]);
+  }
+  atomicAdd(&dist[(size_t)pu * 9 + ci], s);
+}
+
+// xPatternRefinement's argmin (TEncSearch.cpp:808-861).  STAGE 0 writes rcMvHalf and seeds the quarter stage's
+// centre distortion; STAGE 1 writes rcMvQter and ruiCost.
+template <int STAGE>
+__global__ void k_frac_argmin(const SearchTask* __restrict__ tasks, hmb200_pu_result* __restrict__ results,
+                              const uint32_t* __restrict__ dist_in, uint32_t* __restrict__ dist_next, int n, int bit_depth) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const SearchTask t = tasks[i];
+  hmb200_pu_result r = results[i];
+  uint32_t best = 0xffffffffu;
+  int bi = 0;
+#pragma unroll
+  for (int c = 0; c < 9; c++) {
+    uint32_t bits;
+    if (STAGE == 0) bits = mv_bits(k_refine_h[c][0] + 2 * r.mv_x, k_refine_h[c][1] + 2 * r.mv_y, t.pred_x, t.pred_y, 1);      // :3746
+    else            bits = mv_bits(k_refine_q[c][0] + 4 * r.mv_x + 2 * r.half_x, k_refine_q[c][1] + 4 * r.mv_y + 2 * r.half_y,
+                                   t.pred_x, t.pred_y, 0);                                                                    // :4267
+    const uint32_t cost = (dist_in[(size_t)i * 9 + c] >> (bit_depth - 8)) + mv_cost(t.lambda_cost, bits);
+    if (cost < best) { best = cost; bi = c; }
+  }
+  if (STAGE == 0) {
+    r.half_x = k_refine_h[bi][0]; r.half_y = k_refine_h[bi][1];
+    dist_next[(size_t)i * 9] = dist_in[(size_t)i * 9 + bi];              // the quarter stage's candidate 0 is this block
+  } else {
+    r.qter_x = k_refine_q[bi][0]; r.qter_y = k_refine_q[bi][1];
+    r.frac_cost = best;
+  }
+  results[i] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct FracSchedule {
+  int n_pu = 0, n_tiles8 = 0, n_tiles4 = 0;
+  uint32_t* d_tiles8 = nullptr;
+  uint32_t* d_tiles4 = nullptr;
+  uint32_t* d_dist = nullptr;        // [2][n_pu][9]
+};
+
+inline void frac_free_schedule(FracSchedule* s) {
+  if (s->d_tiles8) cudaFree(s->d_tiles8);
+  if (s->d_tiles4) cudaFree(s->d_tiles4);
+  if (s->d_dist) cudaFree(s->d_dist);
+  *s = FracSchedule();
+}
+
+inline bool frac_build_schedule(const std::vector<SearchTask>& tasks, cudaStream_t stream, FracSchedule* out, std::string* err) {
+  const int n = (int)tasks.size();
+  if (n >= (1 << 24)) { if (err) *err = "frac_build_schedule: more than 2^24 PUs in one batch"; return false; }
+  std::vector<uint32_t> t8, t4;
+  for (int i = 0; i < n; i++) {
+    const SearchTask& t = tasks[i];
+    const int e = (t.w % 8 == 0 && t.h % 8 == 0) ? 8 : 4;               // xGetHADs tile choice (TComRdCost.cpp:1544-1572)
+    std::vector<uint32_t>& dst = (e == 8) ? t8 : t4;
+    for (int ty = 0; ty < t.h / e; ty++)
+      for (int tx = 0; tx < t.w / e; tx++) dst.push_back(frac_pack_tile((uint32_t)i, (uint32_t)tx, (uint32_t)ty));
+  }
+  out->n_pu = n; out->n_tiles8 = (int)t8.size(); out->n_tiles4 = (int)t4.size();
+  auto up = [&](uint32_t** d, const std::vector<uint32_t>& h) {
+    if (h.empty()) return true;
+    if (cudaMalloc((void**)d, h.size() * sizeof(uint32_t)) != cudaSuccess) return false;
+    return cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream) == cudaSuccess;
+  };
+  bool ok = up(&out->d_tiles8, t8) && up(&out->d_tiles4, t4) &&
+            (n == 0 || cudaMalloc((void**)&out->d_dist, (size_t)n * 18 * sizeof(uint32_t)) == cudaSuccess) &&
+            cudaStreamSynchronize(stream) == cudaSuccess;
+  if (!ok) {
+    if (err) *err = std::string("frac_build_schedule: ") + cudaGetErrorString(cudaGetLastError());
+    frac_free_schedule(out);
+  }
+  return ok;
+}
+
+// Enqueues the whole refinement on `stream`; returns the number of kernel launches, or -1 on a launch error.
+template <typename RefT, typename OrgT>
+inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200_pu_result* d_results, const DevPlane& cur,
+                       const DevPlane& ref, bool use_had, cudaStream_t stream) {
+  if (fs.n_pu == 0) return 0;
+  int launches = 0;
+  uint32_t* dist0 = fs.d_dist;
+  uint32_t* dist1 = fs.d_dist + (size_t)fs.n_pu * 9;
+  if (cudaMemsetAsync(fs.d_dist, 0, (size_t)fs.n_pu * 18 * sizeof(uint32_t), stream) != cudaSuccess) return -1;
+  for (int stage = 0; stage < 2; stage++) {
+    uint32_t* dist = stage == 0 ? dist0 : dist1;
+    const int nc = stage == 0 ? 9 : 8;
+    auto blocks = [&](int n_tiles) { return (int)((((long long)(n_tiles + 31) / 32) * 32 * nc + FRAC_TILE_THREADS - 1) / FRAC_TILE_THREADS); };
+    if (fs.n_tiles8 > 0) {
+      if (use_had) k_frac_tiles<RefT, OrgT, 8, true><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
+      else         k_frac_tiles<RefT, OrgT, 8, false><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
+      launches++;
+    }
+    if (fs.n_tiles4 > 0) {
+      if (use_had) k_frac_tiles<RefT, OrgT, 4, true><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
+      else         k_frac_tiles<RefT, OrgT, 4, false><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
+      launches++;
+    }
+    const int nb = (fs.n_pu + 255) / 256;
+    if (stage == 0) k_frac_argmin<0><<<nb, 256, 0, stream>>>(d_tasks, d_results, dist0, dist1, fs.n_pu, ref.bit_depth);
+    else            k_frac_argmin<1><<<nb, 256, 0, stream>>>(d_tasks, d_results, dist1, nullptr, fs.n_pu, ref.bit_depth);
+    launches++;
+  }
+  return cudaGetLastError() == cudaSuccess ? launches : -1;
+}
+
+}  // namespace hmb200
