@@ -555,12 +555,13 @@ inline bool search8_build_schedule(const std::vector<SearchTask>& tasks, int sm_
     total_cost += gi[gidx].cost;
     all_r = uni(all_r, g.rb); all_o = uni(all_o, g.ob);
   }
-  const long long target = std::max<long long>(total_cost / std::max(1, sm_count * 2 * 8), 20000);
+  // unit size per tile variant: every variant kernel gets ~12 units per resident CTA slot (2 per SM)
+  long long variant_cost[S8V_COUNT] = {0}, variant_target[S8V_COUNT];
+  for (size_t j = 0; j < jobs.size(); j++) variant_cost[jobs[j].variant] += job_item_cost[j] * jobs[j].n_items;
+  for (int v = 0; v < S8V_COUNT; v++) variant_target[v] = std::max<long long>(variant_cost[v] / std::max(1, sm_count * 2 * 12), 4000);
   for (size_t gidx = 0; gidx < groups.size(); gidx++) {
     const Group& g = groups[gidx];
     const GroupItems& G = gi[gidx];
-    const int n_units = (int)std::max<long long>(1, (G.cost + target - 1) / target);
-    const long long per = (G.cost + n_units - 1) / n_units;
     S8Unit u{};
     const int rx0 = fl(g.rb.x0), ox0 = fl(g.ob.x0);
     u.ref_bx = rx0; u.ref_by = g.rb.y0;
@@ -584,6 +585,7 @@ inline bool search8_build_schedule(const std::vector<SearchTask>& tasks, int sm_
     for (int jl = 0; jl < G.job_count; jl++) {
       const S8Job& j = jobs[G.job_first + jl];
       const long long c = job_item_cost[G.job_first + jl];
+      const long long per = variant_target[j.variant];
       if (acc > 0 && j.variant != jobs[G.job_first + jl - 1].variant) {
         emit(jl - 1, j.item_start);
         acc = 0; ufirst_item = j.item_start; ufirst_job = jl;
