@@ -1,0 +1,193 @@
+// Reference-side binding of libhmb200 for HM-16.5 (xkfz007/video_codecs, hm-16.5rc1): the forwarders that
+// integration/build_shim.py injects into TEncSearch::xPatternSearch, ::xPatternSearchFracDIF and
+// ::xMotionEstimation call the three functions below.  OUR code; it includes the reference's headers from where they
+// lie under /root/reference at build time and is compiled into integration/_build/ only (never copied into the repo).
+//
+// HMB200_SHIM=gpu (default)  every integer search and fractional refinement runs on the GPU through the C-ABI
+// HMB200_SHIM=verify         the GPU result is checked call by call against the reference body (abort on mismatch)
+// HMB200_SHIM=off            the reference bodies run (the stock encoder)
+// HMB200_SHIM_LOG=<file>     appends one record per call (PU, window, predictor, MV, SAD / half, quarter, cost)
+//
+// The private cost state of TComRdCost (m_uiCost, m_mvPredictor; TLibCommon/TComRdCost.h:118-130) is read with the
+// access-specifier trick below; a maintainer would add three public getters instead.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+// every standard header the reference pulls in, before the access-specifier trick (their include guards then keep
+// the trick away from libstdc++)
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <deque>
+#include <fstream>
+#include <functional>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <list>
+#include <numeric>
+#include <set>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+#include <math.h>
+#include <stdint.h>
+#include <time.h>
+
+#define private public
+#define protected public
+#include "TLibEncoder/TEncSearch.h"
+#include "TLibCommon/TComRdCost.h"
+#include "TLibCommon/TComPic.h"
+#include "TLibCommon/TComPicYuv.h"
+#undef private
+#undef protected
+
+#include "hmb200.h"
+
+namespace {
+
+enum Mode { OFF, GPU, VERIFY };
+struct Shim {
+  Mode mode = GPU;
+  bool ready = false;
+  bool in_reference = false;          // re-entrancy guard of verify mode
+  FILE* log = nullptr;
+  std::map<const Pel*, std::pair<int, int> > planes;   // buffer origin -> (plane id, POC)
+  unsigned long long n_search = 0, n_frac = 0, n_upload = 0;
+};
+Shim g_shim;
+
+void die(const char* what) {
+  fprintf(stderr, "hmb200 shim: %s: %s\n", what, hmb200_last_error());
+  abort();                            // like the reference: assert/exit, no CPU fallback
+}
+
+void at_exit() {
+  fprintf(stderr, "hmb200 shim: %llu integer searches, %llu fractional refinements, %llu plane uploads, %llu kernel launches\n",
+          g_shim.n_search, g_shim.n_frac, g_shim.n_upload, (unsigned long long)hmb200_launch_count());
+  if (g_shim.log) fclose(g_shim.log);
+}
+
+bool active() {
+  if (!g_shim.ready) {
+    const char* m = getenv("HMB200_SHIM");
+    g_shim.mode = (m && !strcmp(m, "off")) ? OFF : (m && !strcmp(m, "verify")) ? VERIFY : GPU;
+    if (const char* l = getenv("HMB200_SHIM_LOG")) g_shim.log = fopen(l, "w");
+    if (g_shim.mode != OFF) {
+      const char* d = getenv("HMB200_DEVICE");
+      if (hmb200_init(d ? atoi(d) : 0) != HMB200_OK) die("hmb200_init");
+      atexit(at_exit);
+    }
+    g_shim.ready = true;
+  }
+  return g_shim.mode != OFF && !g_shim.in_reference;
+}
+
+hmb200_cost_state cost_state(TComRdCost* rd) {
+  hmb200_cost_state cs;
+  cs.lambda_cost = rd->m_uiCost;
+  cs.pred.x = rd->m_mvPredictor.getHor();
+  cs.pred.y = rd->m_mvPredictor.getVer();
+  return cs;
+}
+
+hmb200_pattern pattern_of(TComPattern* key) {
+  hmb200_pattern p;
+  p.roi = key->getROIY();
+  p.width = key->getROIYWidth();
+  p.height = key->getROIYHeight();
+  p.stride = key->getPatternLStride();
+  p.bit_depth = key->getBitDepthY();
+  return p;
+}
+
+}  // namespace
+
+// Injected at the top of xMotionEstimation: makes sure the reconstructed reference picture is resident on the GPU.
+// Reconstructed planes are final and border-extended when a picture enters a reference list
+// (TLibCommon/TComSlice.cpp:351-377); a picture buffer is re-used for later pictures, hence the POC check.
+void hmb200_shim_ref_plane(TComPic* pic) {
+  if (!active()) return;
+  TComPicYuv* rec = pic->getPicYuvRec();
+  const Pel* origin = rec->getAddr(COMPONENT_Y);
+  const int poc = pic->getPOC();
+  std::map<const Pel*, std::pair<int, int> >::iterator it = g_shim.planes.find(origin);
+  if (it != g_shim.planes.end()) {
+    if (it->second.second == poc) return;
+    hmb200_release_plane(it->second.first);
+    g_shim.planes.erase(it);
+  }
+  const int mx = rec->getMarginX(COMPONENT_Y), my = rec->getMarginY(COMPONENT_Y);
+  const int id = hmb200_register_plane(origin, rec->getStride(COMPONENT_Y), rec->getWidth(COMPONENT_Y), rec->getHeight(COMPONENT_Y),
+                                       mx, my, pic->getPicSym()->getSPS().getBitDepth(CHANNEL_TYPE_LUMA), HMB200_PLANE_REC, poc);
+  if (id < 0) die("hmb200_register_plane");
+  g_shim.planes[origin] = std::make_pair(id, poc);
+  g_shim.n_upload++;
+}
+
+// TEncSearch::xPatternSearch (TLibEncoder/TEncSearch.cpp:3786-3843).  Returns true when the call was served.
+bool hmb200_shim_pattern_search(TEncSearch* self, TComPattern* key, Pel* piRefY, Int iRefStride, TComMv* lt, TComMv* rb,
+                                TComMv& rcMv, Distortion& ruiSAD) {
+  if (!active()) return false;
+  if (self->m_cDistParam.bApplyWeight) { fprintf(stderr, "hmb200 shim: weighted prediction is out of scope\n"); abort(); }
+  const hmb200_pattern p = pattern_of(key);
+  const hmb200_cost_state cs = cost_state(self->m_pcRdCost);
+  hmb200_mv l = {lt->getHor(), lt->getVer()}, r = {rb->getHor(), rb->getVer()}, mv;
+  uint32_t sad = 0;
+  const int flags = self->m_pcEncCfg->getUseFastEnc() ? HMB200_FLAG_FEN : 0;
+  if (hmb200_pattern_search(&p, piRefY, iRefStride, l, r, &cs, flags, &mv, &sad) != HMB200_OK) die("hmb200_pattern_search");
+  g_shim.n_search++;
+  if (g_shim.mode == VERIFY) {
+    TComMv ref_mv; Distortion ref_sad = 0;
+    g_shim.in_reference = true;
+    self->xPatternSearch(key, piRefY, iRefStride, lt, rb, ref_mv, ref_sad);
+    g_shim.in_reference = false;
+    if (ref_mv.getHor() != mv.x || ref_mv.getVer() != mv.y || ref_sad != sad) {
+      fprintf(stderr, "hmb200 shim: xPatternSearch mismatch %dx%d: gpu (%d,%d) %u, reference (%d,%d) %u\n", p.width, p.height,
+              mv.x, mv.y, sad, ref_mv.getHor(), ref_mv.getVer(), (unsigned)ref_sad);
+      abort();
+    }
+  }
+  if (g_shim.log)
+    fprintf(g_shim.log, "I %dx%d lt %d %d rb %d %d pred %d %d lam %u -> %d %d %u\n", p.width, p.height, l.x, l.y, r.x, r.y, cs.pred.x,
+            cs.pred.y, cs.lambda_cost, mv.x, mv.y, sad);
+  rcMv.set((Short)mv.x, (Short)mv.y);
+  ruiSAD = sad;
+  return true;
+}
+
+// TEncSearch::xPatternSearchFracDIF (TLibEncoder/TEncSearch.cpp:4240-4276).
+bool hmb200_shim_pattern_search_frac(TEncSearch* self, Bool lossless, TComPattern* key, Pel* piRefY, Int iRefStride, TComMv* mvInt,
+                                     TComMv& rcMvHalf, TComMv& rcMvQter, Distortion& ruiCost) {
+  if (!active()) return false;
+  const hmb200_pattern p = pattern_of(key);
+  const hmb200_cost_state cs = cost_state(self->m_pcRdCost);
+  hmb200_mv mi = {mvInt->getHor(), mvInt->getVer()}, half, qter;
+  uint32_t cost = 0;
+  const int flags = self->m_pcEncCfg->getUseHADME() ? HMB200_FLAG_HADME : 0;
+  if (hmb200_pattern_search_frac(lossless ? 1 : 0, &p, piRefY, iRefStride, mi, &cs, flags, &half, &qter, &cost) != HMB200_OK)
+    die("hmb200_pattern_search_frac");
+  g_shim.n_frac++;
+  if (g_shim.mode == VERIFY) {
+    TComMv rh, rq; Distortion rc = 0;
+    const Int scale = self->m_pcRdCost->m_iCostScale;
+    g_shim.in_reference = true;
+    self->xPatternSearchFracDIF(lossless, key, piRefY, iRefStride, mvInt, rh, rq, rc);
+    g_shim.in_reference = false;
+    self->m_pcRdCost->setCostScale(scale);
+    if (rh.getHor() != half.x || rh.getVer() != half.y || rq.getHor() != qter.x || rq.getVer() != qter.y || rc != cost) {
+      fprintf(stderr, "hmb200 shim: xPatternSearchFracDIF mismatch %dx%d: gpu h(%d,%d) q(%d,%d) %u, reference h(%d,%d) q(%d,%d) %u\n",
+              p.width, p.height, half.x, half.y, qter.x, qter.y, cost, rh.getHor(), rh.getVer(), rq.getHor(), rq.getVer(), (unsigned)rc);
+      abort();
+    }
+  }
+  if (g_shim.log)
+    fprintf(g_shim.log, "F %dx%d int %d %d -> %d %d %d %d %u\n", p.width, p.height, mi.x, mi.y, half.x, half.y, qter.x, qter.y, cost);
+  rcMvHalf.set((Short)half.x, (Short)half.y);
+  rcMvQter.set((Short)qter.x, (Short)qter.y);
+  ruiCost = cost;
+  return true;
+}

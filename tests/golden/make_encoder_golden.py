@@ -1,0 +1,56 @@
+"""Generates tests/golden/encoder_md5.json from the UNMODIFIED reference encoder (oracle/_ref/TAppEncoderStatic, built
+from /root/reference/hm-16.5rc1 by oracle/Makefile.ref).  Run in the build container only:
+
+    python tests/golden/make_encoder_golden.py
+
+BASELINE.json configs[0]: encoder_lowdelay_P_main.cfg, synthetic 416x240 8-bit, FastSearch=0 SearchRange=64.  The
+clip is video_codecs_b200.synth (seeded); the JSON records the bitstream md5 and the per-picture MD5 lines so that the
+GPU-routed encoder (integration/) can be checked on machines without /root/reference."""
+import hashlib
+import json
+import os
+import re
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from video_codecs_b200 import synth  # noqa: E402
+
+W, H = 416, 240
+CFG = "/root/reference/hm-16.5rc1/cfg/encoder_lowdelay_P_main.cfg"
+ENC = os.path.join(ROOT, "oracle", "_ref", "TAppEncoderStatic")
+
+
+def encoder_args(cfg, yuv, frames, out_bin):
+    return ["-c", cfg, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", str(frames), "--FastSearch=0",
+            "--SearchRange=64", "--SEIDecodedPictureHash=1", "-b", out_bin, "-o", ""]
+
+
+def write_clip(path, frames):
+    synth.write_yuv420(path, [synth.luma_frame(W, H, t, seed=77) for t in range(frames)], 8)
+
+
+def parse_md5_lines(stdout):
+    return re.findall(r"POC\s+(\d+).*?\[MD5:([0-9a-f,]+)\]", stdout)
+
+
+def main():
+    out = {}
+    for frames in (3, 8):
+        yuv, binf = f"/tmp/hmgold_{frames}.yuv", f"/tmp/hmgold_{frames}.bin"
+        write_clip(yuv, frames)
+        t0 = time.time()
+        p = subprocess.run([ENC] + encoder_args(CFG, yuv, frames, binf), capture_output=True, text=True, check=True)
+        dt = time.time() - t0
+        out[str(frames)] = {"bitstream_md5": hashlib.md5(open(binf, "rb").read()).hexdigest(),
+                            "bitstream_bytes": os.path.getsize(binf),
+                            "picture_md5": parse_md5_lines(p.stdout), "cpu_seconds": round(dt, 1),
+                            "yuv_md5": hashlib.md5(open(yuv, "rb").read()).hexdigest()}
+        print(frames, out[str(frames)]["bitstream_md5"], dt, flush=True)
+    json.dump(out, open(os.path.join(ROOT, "tests", "golden", "encoder_md5.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

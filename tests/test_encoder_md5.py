@@ -1,0 +1,46 @@
+"""BASELINE.json configs[0]: HM-16.5 TAppEncoder, encoder_lowdelay_P_main.cfg, synthetic 416x240 8-bit,
+FastSearch=0 SearchRange=64 — with every xPatternSearch / xPatternSearchFracDIF call routed through libhmb200
+(integration/hm_shim.cpp), the bitstream md5 and every decoded-picture MD5 must equal the stock reference encoder's
+(tests/golden/encoder_md5.json, produced by tests/golden/make_encoder_golden.py from the unmodified reference)."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_encoder_golden as meg  # noqa: E402  (clip generator + command line only; no arithmetic of the path)
+
+GOLD = os.path.join(ROOT, "tests", "golden", "encoder_md5.json")
+BIN = os.path.join(ROOT, "integration", "_build", "TAppEncoderB200")
+CFG = os.path.join(ROOT, "integration", "_build", "encoder_lowdelay_P_main.cfg")
+
+
+def _need_binary():
+    if not (os.path.exists(BIN) and os.path.exists(CFG)):
+        pytest.skip("integration/_build/TAppEncoderB200 not built (python integration/build_shim.py in the build container)")
+
+
+def test_golden_file_is_consistent():
+    gold = json.load(open(GOLD))
+    for frames, g in gold.items():
+        assert len(g["picture_md5"]) == int(frames) and len(g["bitstream_md5"]) == 32
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("frames,mode", [(3, "verify"), (8, "gpu")])
+def test_encoder_bitstream_md5_matches_reference(tmp_path, frames, mode):
+    _need_binary()
+    gold = json.load(open(GOLD))[str(frames)]
+    yuv, binf = str(tmp_path / "clip.yuv"), str(tmp_path / "out.bin")
+    meg.write_clip(yuv, frames)
+    assert hashlib.md5(open(yuv, "rb").read()).hexdigest() == gold["yuv_md5"], "synthetic clip differs from the golden run's"
+    env = dict(os.environ, HMB200_SHIM=mode)
+    p = subprocess.run([BIN] + meg.encoder_args(CFG, yuv, frames, binf), capture_output=True, text=True, env=env, timeout=1500)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "integer searches" in p.stderr and " 0 integer searches" not in p.stderr, "the GPU path was not exercised"
+    assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
+    assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]
