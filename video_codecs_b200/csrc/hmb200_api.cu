@@ -12,6 +12,7 @@
 #include "hmb200_device.cuh"
 #include "hmb200_generic.cuh"
 #include "hmb200_search8.cuh"
+#include "hmb200_search8_cu.cuh"
 #include "hmb200_frac.cuh"
 
 using namespace hmb200;
@@ -153,6 +154,7 @@ struct hmb200_prepared {
   hmb200_pu_result* d_results = nullptr;
   uint64_t cand_sads = 0, abs_diffs = 0;
   Search8Schedule sched;          // tiled 8-bit kernel schedule (empty when not applicable)
+  CuSchedule cu;                  // CU-fused bundles (PUs of one CU sharing window and predictor)
   FracSchedule frac;              // tile tables of the batched quarter-pel refinement
 };
 
@@ -181,6 +183,7 @@ int hmb200_init(int device) {
   for (auto& ev : g.ev_join) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   int rc = search8_configure(&g_err);
   if (rc != HMB200_OK) return rc;
+  if ((rc = cu_configure(&g_err)) != HMB200_OK) return rc;
   g.device = device;
   g.ready = true;
   // pattern buffer for the 1:1 entries: 64x64 int16, no margins
@@ -470,8 +473,14 @@ hmb200_prepared* hmb200_prepare_jobs(const hmb200_pu_job* jobs, int njobs, int f
       hmb200_free_prepared(p); return nullptr;
     }
     std::string why;
-    if (bit_depth == 8 && !search8_build_schedule(p->tasks, g.sm_count, g.stream, &p->sched, &why)) {
-      fail(HMB200_ERR_CUDA, why); hmb200_free_prepared(p); return nullptr;
+    if (bit_depth == 8) {
+      std::vector<char> bundled;
+      std::vector<CuBundleHost> hb;
+      if (!getenv("HMB200_NO_CU_FUSION")) cu_extract_bundles(p->tasks, bundled, hb);
+      if (!search8_build_schedule(p->tasks, bundled, g.sm_count, g.stream, &p->sched, &why) ||
+          !cu_build_schedule(p->tasks, hb, g.sm_count, g.stream, &p->cu, &why)) {
+        fail(HMB200_ERR_CUDA, why); hmb200_free_prepared(p); return nullptr;
+      }
     }
     if ((flags & HMB200_FLAG_FRAC) && !frac_build_schedule(p->tasks, g.stream, &p->frac, &why)) {
       fail(HMB200_ERR_CUDA, why); hmb200_free_prepared(p); return nullptr;
@@ -486,6 +495,7 @@ void hmb200_free_prepared(hmb200_prepared* p) {
   if (p->d_tasks) cudaFree(p->d_tasks);
   if (p->d_results) cudaFree(p->d_results);
   search8_free_schedule(&p->sched);
+  cu_free_schedule(&p->cu);
   frac_free_schedule(&p->frac);
   delete p;
 }
@@ -506,28 +516,36 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
   if (p->n == 0) return HMB200_OK;
   CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
   const Search8Schedule& sc = p->sched;
-  bool fast = pc->d.bytes_per_sample == 1 && pr->d.bytes_per_sample == 1 && sc.n_jobs > 0 &&
-              pc->d.margin_x % 16 == 0 && pr->d.margin_x % 16 == 0;
+  const CuSchedule& cu = p->cu;
+  bool fast = pc->d.bytes_per_sample == 1 && pr->d.bytes_per_sample == 1 && (sc.n_jobs > 0 || cu.n_bundles > 0) &&
+              pc->d.margin_x % 16 == 0 && pr->d.margin_x % 16 == 0 && sc.d_keys != nullptr;
   if (fast) {
     // every staged byte must lie inside the padded buffers (the reference would read outside its planes too)
     auto inside = [](const DevPlane& d, int x0, int y0, int x1, int y1) {
       return x0 + d.margin_x >= 0 && x1 + d.margin_x <= d.pitch && y0 + d.margin_y >= 0 && y1 + d.margin_y <= d.height + 2 * d.margin_y;
     };
-    if (!inside(pr->d, sc.min_x, sc.min_y, sc.max_x, sc.max_y))
+    if ((sc.n_jobs > 0 && !inside(pr->d, sc.min_x, sc.min_y, sc.max_x, sc.max_y)) ||
+        (cu.n_bundles > 0 && !inside(pr->d, cu.rbox.x0, cu.rbox.y0, cu.rbox.x1, cu.rbox.y1)))
       return fail(HMB200_ERR_ARG, "hmb200_run_prepared: a search window leaves the padded reference plane");
-    if (!inside(pc->d, sc.omin_x, sc.omin_y, sc.omax_x, sc.omax_y))
+    if ((sc.n_jobs > 0 && !inside(pc->d, sc.omin_x, sc.omin_y, sc.omax_x, sc.omax_y)) ||
+        (cu.n_bundles > 0 && !inside(pc->d, cu.obox.x0, cu.obox.y0, cu.obox.x1, cu.obox.y1)))
       return fail(HMB200_ERR_ARG, "hmb200_run_prepared: a PU leaves the padded current plane");
     CUDA_TRY(cudaMemsetAsync(sc.d_keys, 0xff, (size_t)sc.n_tasks * sizeof(unsigned long long), g.stream));
     // one launch per tile variant present, spread over side streams so that their tails overlap
     const S8Kernel* kern = search8_kernels();
+    const S8CuKernel* cukern = search8_cu_kernels();
     CUDA_TRY(cudaEventRecord(g.ev_fork, g.stream));
-    int order[S8V_COUNT], used = 0;
+    int order[S8V_COUNT + CUV_COUNT], used = 0;       // >= 0: per-PU variant, < 0: CU-fused variant ~v
+    for (int v = CUV_COUNT - 1; v >= 0; v--) if (cu.unit_count[v] > 0) order[used++] = ~v;    // big CUs first
     for (int v = S8V_COUNT - 1; v >= 0; v--) if (sc.unit_count[v] > 0) order[used++] = v;     // wide tiles first
     for (int k = 0; k < used; k++) {
       const int v = order[k];
       cudaStream_t st = (k == 0) ? g.stream : g.side[(k - 1) % N_SIDE];
       if (k >= 1 && k <= N_SIDE) CUDA_TRY(cudaStreamWaitEvent(st, g.ev_fork, 0));
-      kern[v]<<<sc.unit_count[v], S8_THREADS, sc.smem_of[v], st>>>(sc.d_units + sc.unit_first[v], sc.d_jobs, sc.d_keys, pc->d, pr->d);
+      if (v >= 0)
+        kern[v]<<<sc.unit_count[v], S8_THREADS, sc.smem_of[v], st>>>(sc.d_units + sc.unit_first[v], sc.d_jobs, sc.d_keys, pc->d, pr->d);
+      else
+        cukern[~v]<<<cu.unit_count[~v], S8_THREADS, cu.smem_of[~v], st>>>(cu.d_units + cu.unit_first[~v], cu.d_bundles, sc.d_keys, pc->d, pr->d);
       g.launches++;
     }
     for (int k = 0; k < N_SIDE && k + 1 < used; k++) {

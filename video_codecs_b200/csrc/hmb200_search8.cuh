@@ -455,25 +455,33 @@ inline void search8_free_schedule(Search8Schedule* s) {
 
 inline int s8_floor16(int v) { return v & ~15; }
 inline int s8_ceil16(int v) { return (v + 15) & ~15; }
+struct S8Box { int x0, y0, x1, y1; };
+inline S8Box s8_union(const S8Box& a, const S8Box& b) { return S8Box{std::min(a.x0, b.x0), std::min(a.y0, b.y0), std::max(a.x1, b.x1), std::max(a.y1, b.y1)}; }
+inline int s8_fl(int x) { return s8_floor16(x + 4096) - 4096; }      // 16-aligned in picture coordinates
+inline int s8_ce(int x) { return s8_ceil16(x + 4096) - 4096; }
+// dynamic shared memory of a group: window rows (+ slack) then the original tile, 128-byte aligned
+inline int s8_smem_need(const S8Box& rb, const S8Box& ob, int* org_off) {
+  const int rp = s8_ce(rb.x1) - s8_fl(rb.x0), rr = rb.y1 - rb.y0 + S8_SLACK_ROWS;
+  const int op = s8_ce(ob.x1) - s8_fl(ob.x0), orr = ob.y1 - ob.y0;
+  const int ro = ((rp * rr + 16) + 127) & ~127;
+  if (org_off) *org_off = ro;
+  return ro + op * orr + 16;
+}
 
 // Window origins are multiples of 16 in picture coordinates: 16-byte aligned in the buffer when margin_x % 16 == 0.
-inline bool search8_build_schedule(const std::vector<SearchTask>& tasks, int sm_count, cudaStream_t stream,
+// skip[i] != 0: task i is searched elsewhere (CU-fused kernel) and gets neither a job nor a leftover entry.
+inline bool search8_build_schedule(const std::vector<SearchTask>& tasks, const std::vector<char>& skip, int sm_count, cudaStream_t stream,
                                    Search8Schedule* out, std::string* err) {
-  struct Box { int x0, y0, x1, y1; };
-  auto uni = [](const Box& a, const Box& b) { return Box{std::min(a.x0, b.x0), std::min(a.y0, b.y0), std::max(a.x1, b.x1), std::max(a.y1, b.y1)}; };
-  auto fl = [&](int x) { return s8_floor16(x + 4096) - 4096; };
-  auto ce = [&](int x) { return s8_ceil16(x + 4096) - 4096; };
-  auto smem_need = [&](const Box& rb, const Box& ob, int* org_off) {
-    const int rp = ce(rb.x1) - fl(rb.x0), rr = rb.y1 - rb.y0 + S8_SLACK_ROWS;
-    const int op = ce(ob.x1) - fl(ob.x0), orr = ob.y1 - ob.y0;
-    const int ro = ((rp * rr + 16) + 127) & ~127;
-    if (org_off) *org_off = ro;
-    return ro + op * orr + 16;
-  };
+  typedef S8Box Box;
+  auto uni = [](const Box& a, const Box& b) { return s8_union(a, b); };
+  auto fl = [](int x) { return s8_fl(x); };
+  auto ce = [](int x) { return s8_ce(x); };
+  auto smem_need = [](const Box& rb, const Box& ob, int* org_off) { return s8_smem_need(rb, ob, org_off); };
   const int n = (int)tasks.size();
   std::vector<int> elig, left;
   std::vector<Box> rbox(n), obox(n);
   for (int i = 0; i < n; i++) {
+    if (!skip.empty() && skip[i]) continue;
     const SearchTask& t = tasks[i];
     const int nx = t.rb_x - t.lt_x + 1, ny = t.rb_y - t.lt_y + 1;
     rbox[i] = Box{t.ref_x + t.lt_x, t.ref_y + t.lt_y, t.ref_x + t.rb_x + t.w, t.ref_y + t.rb_y + t.h};

@@ -1,0 +1,551 @@
+// CU-fused integer full search for 8-bit planes: all partitions of one CU in one pass over its samples.
+//
+// Inside HM every PU of a CU is searched separately (TEncCu::xCheckRDCostInter -> predInterSearch -> xPatternSearch,
+// TLibEncoder/TEncCu.cpp:459-626, TEncSearch.cpp:2912-3063), so a sample of the CU is visited once per partition mode:
+// 2Nx2N, 2NxN, Nx2N and the four AMP modes (TLibCommon/TComDataCU.cpp:1893-1931) = 7 times (3 for 8x8 CUs).  When
+// those PUs share the search window and the MV predictor (xSetSearchRange clips by CU, TEncSearch.cpp:3765-3781; the
+// canonical job list gives every PU of a CU the same predictor) their SADs at one displacement are sums of the same
+// partial SADs.  This kernel computes, per candidate, a 4x4 grid of partial SADs over the CU (granule S/4 — every PU
+// boundary of every partition mode lies on that grid) and derives all 13 PU SADs from row / column sums:
+//
+//   FEN (iSubShift, TEncSearch.cpp:3804-3810, TComRdCost.cpp:564-595): PUs with more than 8 rows visit only even
+//   rows and shift the sum left by one; PUs with <= 8 rows visit every row.  Even rows accumulate into the grid E,
+//   odd rows into per-strip sums O that only the <= 8-row PUs add (16x8, 16x4 in a 16x16 CU; 32x8 in a 32x32 CU).
+//
+// Every PU keeps its own running argmin key, so results are bit-identical to thirteen separate searches; what changes
+// is the number of executed abs-diffs (1 pass over the CU instead of 3.5-4.25), not the arithmetic.
+// Tile: a quad of lanes owns 16 candidate columns (lane s: columns s, s+4, s+8, s+12, one funnel shift per word) of
+// KY candidate rows.  Windows whose width is not a multiple of 16 get a last block that overlaps its neighbour.
+#pragma once
+#include <map>
+#include "hmb200_search8.cuh"
+
+namespace hmb200 {
+
+constexpr int CU_SLOTS = 13;
+
+struct S8Bundle {             // 128 bytes
+  int32_t org_off, win_off;   // byte offsets of the CU's top-left sample / of candidate (lt_x, lt_y) in the staged tiles
+  int32_t nx, ny;
+  int32_t lt_x, lt_y, pred_x, pred_y;
+  uint32_t lambda;
+  int32_t n_blk;              // ceil(nx / 16)
+  int32_t item_start, n_items;
+  int32_t out_idx[CU_SLOTS];  // task index per partition slot (-1: that PU is not in the job list)
+  int32_t n_rowgroups;        // ceil(ny / KY)
+  int32_t pad[6];
+};
+
+// partition slots: 0 2Nx2N | 1,2 2NxN top,bottom | 3,4 Nx2N left,right | 5,6 2NxnU | 7,8 2NxnD | 9,10 nLx2N | 11,12 nRx2N
+__host__ __device__ constexpr int cu_slot_h(int S, int slot) {
+  return (slot == 1 || slot == 2) ? S / 2 : (slot == 5 || slot == 8) ? S / 4 : (slot == 6 || slot == 7) ? 3 * S / 4 : S;
+}
+__host__ __device__ constexpr int cu_slot_w(int S, int slot) {
+  return (slot == 3 || slot == 4) ? S / 2 : (slot == 9 || slot == 12) ? S / 4 : (slot == 10 || slot == 11) ? 3 * S / 4 : S;
+}
+__host__ __device__ constexpr int cu_slot_x(int S, int slot) { return slot == 4 ? S / 2 : slot == 10 ? S / 4 : slot == 12 ? 3 * S / 4 : 0; }
+__host__ __device__ constexpr int cu_slot_y(int S, int slot) { return slot == 2 ? S / 2 : slot == 6 ? S / 4 : slot == 8 ? 3 * S / 4 : 0; }
+__host__ __device__ constexpr int cu_ky(int S) { return S == 8 ? 4 : 1; }
+
+template <int S, bool FEN> struct CuTraits {
+  static constexpr int WW = S / 4;                 // 32-bit words per CU row
+  static constexpr int N = (S == 8) ? 2 : 4;       // grid is N x N cells
+  static constexpr int G = S / N;                  // rows per strip
+  static constexpr int WC = WW / N;                // words per cell column
+  static constexpr int KY = cu_ky(S);
+  static constexpr bool PARITY = FEN && S >= 16;   // even / odd rows are told apart
+  static constexpr bool ODD_ALL = PARITY && S == 16;   // odd rows needed in every strip
+  static constexpr bool ODD_EDGE = PARITY && S == 32;  // odd rows needed in strips 0 and 3 only
+};
+
+// broadcast load of one original row (WW words) from shared memory; the CU is S-byte aligned in the tile
+template <int WW>
+__device__ __forceinline__ void cu_load_org(const uint8_t* p, uint32_t (&o)[WW]) {
+  if constexpr (WW >= 4) {
+#pragma unroll
+    for (int i = 0; i < WW / 4; i++) {
+      const uint4 v = reinterpret_cast<const uint4*>(p)[i];
+      o[4 * i] = v.x; o[4 * i + 1] = v.y; o[4 * i + 2] = v.z; o[4 * i + 3] = v.w;
+    }
+  } else {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    o[0] = v.x; o[1] = v.y;
+  }
+}
+
+// one reference row against one original row: the words of cell column c feed acc[c][k] (k = candidate column)
+template <int WW, int NC>
+__device__ __forceinline__ void cu_row(const uint8_t* rp8, const uint32_t (&o)[WW], uint32_t sh, uint32_t (&acc)[NC][4]) {
+  const uint32_t* rp = reinterpret_cast<const uint32_t*>(rp8);
+  uint32_t lo = rp[0];
+#pragma unroll
+  for (int j = 0; j < WW + 3; j++) {
+    const uint32_t hi = rp[j + 1];
+    const uint32_t sw = __funnelshift_r(lo, hi, sh);
+    lo = hi;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int i = j - k;
+      if (i >= 0 && i < WW) acc[i / (WW / NC)][k] = sad4_acc(sw, o[i], acc[i / (WW / NC)][k]);
+    }
+  }
+}
+
+// same, every word into one accumulator per candidate column (odd-row strips)
+template <int WW>
+__device__ __forceinline__ void cu_row1(const uint8_t* rp8, const uint32_t (&o)[WW], uint32_t sh, uint32_t (&acc)[4]) {
+  const uint32_t* rp = reinterpret_cast<const uint32_t*>(rp8);
+  uint32_t lo = rp[0];
+#pragma unroll
+  for (int j = 0; j < WW + 3; j++) {
+    const uint32_t hi = rp[j + 1];
+    const uint32_t sw = __funnelshift_r(lo, hi, sh);
+    lo = hi;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int i = j - k;
+      if (i >= 0 && i < WW) acc[k] = sad4_acc(sw, o[i], acc[k]);
+    }
+  }
+}
+
+__device__ __forceinline__ void cu_min(unsigned long long& best, uint32_t cost, uint32_t idx) {
+  const unsigned long long key = make_key(cost, idx);
+  best = key < best ? key : best;
+}
+
+// S >= 16: grid E[4][4][k], odd-row strips O[4][k]; derives the 13 PU costs of candidate column k and updates the argmins
+template <int S, bool FEN>
+__device__ __forceinline__ void cu_epilogue16(const uint32_t (&E)[4][4][4], const uint32_t (&O)[4][4], int k, uint32_t cmv, uint32_t idx,
+                                              unsigned long long (&best)[CU_SLOTS]) {
+  uint32_t er[4], ec[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) er[r] = E[r][0][k] + E[r][1][k] + E[r][2][k] + E[r][3][k];
+#pragma unroll
+  for (int c = 0; c < 4; c++) ec[c] = E[0][c][k] + E[1][c][k] + E[2][c][k] + E[3][c][k];
+  // a PU with <= 8 rows under FEN visits every row: add the odd rows of its strips; all others shift by iSubShift
+  constexpr bool f1 = FEN && cu_slot_h(S, 1) <= 8;      // 2NxN halves (S == 16)
+  constexpr bool f5 = FEN && cu_slot_h(S, 5) <= 8;      // AMP quarter strips (S == 16, 32)
+  constexpr int sh_full = FEN ? 1 : 0;                  // iSubShift of the PUs taller than 8 rows
+  const uint32_t top = er[0] + er[1], bot = er[2] + er[3];
+  cu_min(best[0], ((top + bot) << sh_full) + cmv, idx);
+  cu_min(best[1], (f1 ? top + O[0][k] + O[1][k] : top << sh_full) + cmv, idx);
+  cu_min(best[2], (f1 ? bot + O[2][k] + O[3][k] : bot << sh_full) + cmv, idx);
+  cu_min(best[3], ((ec[0] + ec[1]) << sh_full) + cmv, idx);
+  cu_min(best[4], ((ec[2] + ec[3]) << sh_full) + cmv, idx);
+  cu_min(best[5], (f5 ? er[0] + O[0][k] : er[0] << sh_full) + cmv, idx);
+  cu_min(best[6], ((er[1] + bot) << sh_full) + cmv, idx);
+  cu_min(best[7], ((top + er[2]) << sh_full) + cmv, idx);
+  cu_min(best[8], (f5 ? er[3] + O[3][k] : er[3] << sh_full) + cmv, idx);
+  cu_min(best[9], (ec[0] << sh_full) + cmv, idx);
+  cu_min(best[10], ((ec[1] + ec[2] + ec[3]) << sh_full) + cmv, idx);
+  cu_min(best[11], ((ec[0] + ec[1] + ec[2]) << sh_full) + cmv, idx);
+  cu_min(best[12], (ec[3] << sh_full) + cmv, idx);
+}
+
+template <int S, bool FEN>
+__global__ void __launch_bounds__(S8_THREADS, 2)
+k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bundles, unsigned long long* __restrict__ keys,
+             DevPlane cur_plane, DevPlane ref_plane) {
+  typedef CuTraits<S, FEN> T;
+  constexpr int NSLOT = (S == 8) ? 5 : CU_SLOTS;
+  extern __shared__ __align__(128) uint8_t s8_smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_next;
+  __shared__ S8Bundle s_bd[S8_WARPS];
+
+  const S8Unit un = units[blockIdx.x];
+  uint8_t* s_ref = s8_smem;
+  uint8_t* s_org = s8_smem + un.org_smem_off;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) { mbar_init(&s_bar, 1); s_next = un.item_first; }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) mbar_expect_tx(&s_bar, (uint32_t)(un.ref_pitch * un.ref_rows + un.org_pitch * un.org_rows));
+    __syncwarp();
+    const uint8_t* gref = reinterpret_cast<const uint8_t*>(ref_plane.base) +
+                          (size_t)(un.ref_by + ref_plane.margin_y) * ref_plane.pitch + (un.ref_bx + ref_plane.margin_x);
+    for (int r = lane; r < un.ref_rows; r += 32)
+      bulk_g2s(s_ref + r * un.ref_pitch, gref + (size_t)r * ref_plane.pitch, (uint32_t)un.ref_pitch, &s_bar);
+    const uint8_t* gorg = reinterpret_cast<const uint8_t*>(cur_plane.base) +
+                          (size_t)(un.org_by + cur_plane.margin_y) * cur_plane.pitch + (un.org_bx + cur_plane.margin_x);
+    for (int r = lane; r < un.org_rows; r += 32)
+      bulk_g2s(s_org + r * un.org_pitch, gorg + (size_t)r * cur_plane.pitch, (uint32_t)un.org_pitch, &s_bar);
+  }
+  mbar_wait(&s_bar, 0);
+
+  int bslot = un.job_first;
+  S8Bundle& bd = s_bd[warp];
+  auto load_bundle = [&]() {
+    __syncwarp();
+    reinterpret_cast<int32_t*>(&bd)[lane] = reinterpret_cast<const int32_t*>(&bundles[bslot])[lane];   // 32 ints
+    __syncwarp();
+  };
+  load_bundle();
+  unsigned long long best[CU_SLOTS];
+#pragma unroll
+  for (int s = 0; s < CU_SLOTS; s++) best[s] = ~0ull;
+  auto flush = [&]() {
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) {
+      unsigned long long b = best[s];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
+        b = other < b ? other : b;
+      }
+      if (lane == 0 && b != ~0ull && bd.out_idx[s] >= 0) atomicMin(&keys[bd.out_idx[s]], b);
+      best[s] = ~0ull;
+    }
+  };
+
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(&s_next, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= un.item_last) break;
+    if (item >= bd.item_start + bd.n_items) {
+      flush();
+      do { bslot++; } while (item >= bundles[bslot].item_start + bundles[bslot].n_items);
+      load_bundle();
+    }
+    const int q = (item - bd.item_start) * 8 + (lane >> 2);
+    if (q < bd.n_blk * bd.n_rowgroups) {
+    const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
+    const int cyi0 = g * T::KY;
+    const int cxi0 = min(blk * 16, bd.nx - 16) + (lane & 3);          // the last block overlaps its neighbour
+    const int off = bd.win_off + cyi0 * un.ref_pitch + cxi0;
+    const uint8_t* refp = s_ref + (off & ~3);
+    const uint32_t sh = (uint32_t)(off & 3) * 8u;
+    const uint8_t* orgp = s_org + bd.org_off;
+    uint32_t px[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) px[k] = bd.lambda * eg_bits(((bd.lt_x + cxi0 + 4 * k) << 2) - bd.pred_x);
+
+    if constexpr (S == 8) {
+      // four candidate rows per tile, whole CU (8 rows x 2 words) in registers, quadrant sums Q[row half][column half]
+      uint32_t o[8][2];
+#pragma unroll
+      for (int r = 0; r < 8; r++) cu_load_org<2>(orgp + r * un.org_pitch, o[r]);
+      uint32_t Q[T::KY][2][2][4];
+#pragma unroll
+      for (int a = 0; a < T::KY; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+          for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) Q[a][b][c][k] = 0;
+#pragma unroll
+      for (int r = 0; r < 8 + T::KY - 1; r++) {
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(refp + r * un.ref_pitch);
+        uint32_t lo = rp[0];
+#pragma unroll
+        for (int j = 0; j < 2 + 3; j++) {
+          const uint32_t hi = rp[j + 1];
+          const uint32_t sw = __funnelshift_r(lo, hi, sh);
+          lo = hi;
+#pragma unroll
+          for (int jy = 0; jy < T::KY; jy++) {
+            if (r - jy >= 0 && r - jy < 8) {
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const int i = j - k;
+                if (i >= 0 && i < 2) Q[jy][(r - jy) >> 2][i][k] = sad4_acc(sw, o[r - jy][i], Q[jy][(r - jy) >> 2][i][k]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int jy = 0; jy < T::KY; jy++) {
+        const int cyi = cyi0 + jy;
+        if (cyi < bd.ny) {
+          const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + cyi) << 2) - bd.pred_y);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint32_t cmv = (px[k] + py) >> 16;
+            const uint32_t idx = (uint32_t)(cyi * bd.nx + cxi0 + 4 * k);
+            const uint32_t t = Q[jy][0][0][k] + Q[jy][0][1][k], b = Q[jy][1][0][k] + Q[jy][1][1][k];
+            const uint32_t l = Q[jy][0][0][k] + Q[jy][1][0][k], r = Q[jy][0][1][k] + Q[jy][1][1][k];
+            cu_min(best[0], t + b + cmv, idx);       // 8x8  (no PU of an 8x8 CU has more than 8 rows: iSubShift = 0)
+            cu_min(best[1], t + cmv, idx);           // 8x4 top
+            cu_min(best[2], b + cmv, idx);           // 8x4 bottom
+            cu_min(best[3], l + cmv, idx);           // 4x8 left
+            cu_min(best[4], r + cmv, idx);           // 4x8 right
+          }
+        }
+      }
+    } else {
+      uint32_t E[4][4][4], O[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          O[a][k] = 0;
+#pragma unroll
+          for (int c = 0; c < 4; c++) E[a][c][k] = 0;
+        }
+#pragma unroll
+      for (int r = 0; r < 4; r++) {                                      // strips: static, so the grid row index is too
+        const bool odd_here = T::ODD_ALL || (T::ODD_EDGE && (r == 0 || r == 3));
+        if constexpr (T::PARITY) {
+#pragma unroll 2
+          for (int rr = 0; rr < T::G; rr += 2) {
+            const int row = r * T::G + rr;
+            uint32_t o[T::WW];
+            cu_load_org<T::WW>(orgp + row * un.org_pitch, o);
+            cu_row<T::WW, 4>(refp + row * un.ref_pitch, o, sh, E[r]);
+            if (odd_here) {
+              uint32_t o1[T::WW];
+              cu_load_org<T::WW>(orgp + (row + 1) * un.org_pitch, o1);
+              cu_row1<T::WW>(refp + (row + 1) * un.ref_pitch, o1, sh, O[r]);
+            }
+          }
+        } else {
+#pragma unroll 2
+          for (int rr = 0; rr < T::G; rr++) {
+            const int row = r * T::G + rr;
+            uint32_t o[T::WW];
+            cu_load_org<T::WW>(orgp + row * un.org_pitch, o);
+            cu_row<T::WW, 4>(refp + row * un.ref_pitch, o, sh, E[r]);
+          }
+        }
+      }
+      if (cyi0 < bd.ny) {
+        const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + cyi0) << 2) - bd.pred_y);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          cu_epilogue16<S, FEN>(E, O, k, (px[k] + py) >> 16, (uint32_t)(cyi0 * bd.nx + cxi0 + 4 * k), best);
+      }
+    }
+    }   // q in range
+  }
+  flush();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+enum : int { CUV_8 = 0, CUV_16_F0, CUV_16_F1, CUV_32_F0, CUV_32_F1, CUV_64_F0, CUV_64_F1, CUV_COUNT };
+typedef void (*S8CuKernel)(const S8Unit*, const S8Bundle*, unsigned long long*, DevPlane, DevPlane);
+inline const S8CuKernel* search8_cu_kernels() {
+  static const S8CuKernel table[CUV_COUNT] = { k_search8_cu<8, false>, k_search8_cu<16, false>, k_search8_cu<16, true>,
+                                               k_search8_cu<32, false>, k_search8_cu<32, true>, k_search8_cu<64, false>,
+                                               k_search8_cu<64, true> };
+  return table;
+}
+inline int cu_variant(int S, bool fen) { return S == 8 ? CUV_8 : S == 16 ? (fen ? CUV_16_F1 : CUV_16_F0) : S == 32 ? (fen ? CUV_32_F1 : CUV_32_F0) : (fen ? CUV_64_F1 : CUV_64_F0); }
+
+struct CuSchedule {
+  int n_units = 0, n_bundles = 0;
+  S8Unit* d_units = nullptr;
+  S8Bundle* d_bundles = nullptr;
+  int unit_first[CUV_COUNT] = {0}, unit_count[CUV_COUNT] = {0}, smem_of[CUV_COUNT] = {0};
+  S8Box rbox{0, 0, 0, 0}, obox{0, 0, 0, 0};
+};
+
+inline void cu_free_schedule(CuSchedule* s) {
+  if (s->d_units) cudaFree(s->d_units);
+  if (s->d_bundles) cudaFree(s->d_bundles);
+  *s = CuSchedule();
+}
+
+inline int cu_configure(std::string* err) {
+  const S8CuKernel* k = search8_cu_kernels();
+  for (int v = 0; v < CUV_COUNT; v++) {
+    cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k[v]), cudaFuncAttributeMaxDynamicSharedMemorySize, S8_SMEM_MAX);
+    if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(k_search8_cu): ") + cudaGetErrorString(e); return HMB200_ERR_CUDA; }
+  }
+  return HMB200_OK;
+}
+
+// Finds CU bundles among `elig` (indices into tasks): PUs that are partitions of the same aligned S x S CU and share
+// window, predictor and lambda.  taken[i] = 1 for every bundled task (the per-PU schedule skips those).
+struct CuBundleHost { int S; bool fen; int cu_x, cu_y; int slot_task[CU_SLOTS]; int first_task; };
+inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, std::vector<char>& taken, std::vector<CuBundleHost>& out) {
+  struct Key {
+    int v[11];
+    bool operator<(const Key& o) const { for (int i = 0; i < 11; i++) if (v[i] != o.v[i]) return v[i] < o.v[i]; return false; }
+  };
+  std::map<Key, CuBundleHost> found;
+  for (int i = 0; i < (int)tasks.size(); i++) {
+    const SearchTask& t = tasks[i];
+    const int S = std::max(t.w, t.h);
+    if (!(S == 8 || S == 16 || S == 32 || S == 64) || t.ref_x != t.org_x || t.ref_y != t.org_y || t.org_x < 0 || t.org_y < 0) continue;
+    if (t.rb_x - t.lt_x + 1 < 16 || t.rb_y < t.lt_y) continue;
+    const int cx = t.org_x - t.org_x % S, cy = t.org_y - t.org_y % S;
+    if (s8_smem_need(S8Box{cx + t.lt_x, cy + t.lt_y, cx + t.rb_x + S, cy + t.rb_y + S}, S8Box{cx, cy, cx + S, cy + S}, nullptr) > S8_SMEM_MAX) continue;
+    int slot = -1;
+    for (int s = 0; s < (S == 8 ? 5 : CU_SLOTS); s++)
+      if (cu_slot_x(S, s) == t.org_x - cx && cu_slot_y(S, s) == t.org_y - cy && cu_slot_w(S, s) == t.w && cu_slot_h(S, s) == t.h) { slot = s; break; }
+    if (slot < 0) continue;
+    Key k = {{cx, cy, S, t.lt_x, t.lt_y, t.rb_x, t.rb_y, t.pred_x, t.pred_y, (int)t.lambda_cost, 0}};
+    auto it = found.find(k);
+    if (it == found.end()) {
+      CuBundleHost b; b.S = S; b.fen = false; b.cu_x = cx; b.cu_y = cy; b.first_task = i;
+      for (int s = 0; s < CU_SLOTS; s++) b.slot_task[s] = -1;
+      it = found.insert(std::make_pair(k, b)).first;
+    }
+    if (it->second.slot_task[slot] >= 0) continue;            // the same PU twice: the second one stays a plain job
+    it->second.slot_task[slot] = i;
+  }
+  taken.assign(tasks.size(), 0);
+  for (auto& kv : found) {
+    CuBundleHost& b = kv.second;
+    int n = 0, fen_seen = -1; bool consistent = true;
+    for (int s = 0; s < CU_SLOTS; s++) {
+      if (b.slot_task[s] < 0) continue;
+      n++;
+      const SearchTask& t = tasks[b.slot_task[s]];
+      if (t.h > 8) { if (fen_seen < 0) fen_seen = t.sub_shift; else if (fen_seen != t.sub_shift) consistent = false; }
+      else if (t.sub_shift != 0) consistent = false;
+    }
+    if (n < 2 || !consistent) continue;
+    b.fen = fen_seen == 1;
+    for (int s = 0; s < CU_SLOTS; s++) if (b.slot_task[s] >= 0) taken[b.slot_task[s]] = 1;
+    out.push_back(b);
+  }
+  std::sort(out.begin(), out.end(), [](const CuBundleHost& a, const CuBundleHost& b) { return a.first_task < b.first_task; });
+}
+
+inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::vector<CuBundleHost>& hb, int sm_count,
+                              cudaStream_t stream, CuSchedule* out, std::string* err) {
+  if (hb.empty()) return true;
+  struct Ent { int b; S8Box rb, ob; };
+  std::vector<Ent> ents(hb.size());
+  for (size_t i = 0; i < hb.size(); i++) {
+    const CuBundleHost& b = hb[i];
+    int any = -1;
+    for (int s = 0; s < CU_SLOTS; s++) if (b.slot_task[s] >= 0) { any = b.slot_task[s]; break; }
+    const SearchTask& t = tasks[any];
+    ents[i].b = (int)i;
+    ents[i].ob = S8Box{b.cu_x, b.cu_y, b.cu_x + b.S, b.cu_y + b.S};
+    ents[i].rb = S8Box{b.cu_x + t.lt_x, b.cu_y + t.lt_y, b.cu_x + t.rb_x + b.S, b.cu_y + t.rb_y + b.S};
+  }
+  std::stable_sort(ents.begin(), ents.end(), [&](const Ent& a, const Ent& b) {
+    const int ka = a.ob.y0 >> 6, kb = b.ob.y0 >> 6;
+    if (ka != kb) return ka < kb;
+    return (a.ob.x0 >> 6) < (b.ob.x0 >> 6);
+  });
+  struct Group { int first, count; S8Box rb, ob; };
+  std::vector<Group> groups;
+  for (size_t p = 0; p < ents.size(); p++) {
+    if (!groups.empty()) {
+      Group& g = groups.back();
+      const S8Box nr = s8_union(g.rb, ents[p].rb), no = s8_union(g.ob, ents[p].ob);
+      if (g.count < 4096 && no.x1 - no.x0 <= 128 && no.y1 - no.y0 <= 128 && s8_smem_need(nr, no, nullptr) <= S8_SMEM_SHARED2) {
+        g.rb = nr; g.ob = no; g.count++;
+        continue;
+      }
+    }
+    if (s8_smem_need(ents[p].rb, ents[p].ob, nullptr) > S8_SMEM_MAX) { if (err) *err = "cu_build_schedule: window too large"; return false; }
+    groups.push_back(Group{(int)p, 1, ents[p].rb, ents[p].ob});
+  }
+  auto item_cost = [](int S, bool fen) -> long long {
+    const int rows = (fen && S >= 16) ? (S == 16 ? 16 : S == 32 ? 24 : 32) : S;
+    return (long long)cu_ky(S) * (rows * (S / 4) + 40);
+  };
+  std::vector<S8Bundle> bundles; bundles.reserve(hb.size());
+  std::vector<int> bvar; bvar.reserve(hb.size());
+  std::vector<std::pair<int, int> > group_range(groups.size());
+  long long variant_cost[CUV_COUNT] = {0};
+  S8Box all_r{1 << 30, 1 << 30, -(1 << 30), -(1 << 30)}, all_o = all_r;
+  for (size_t gi = 0; gi < groups.size(); gi++) {
+    Group& g = groups[gi];
+    std::vector<int> ids;
+    for (int k = 0; k < g.count; k++) ids.push_back(ents[g.first + k].b);
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return cu_variant(hb[a].S, hb[a].fen) > cu_variant(hb[b].S, hb[b].fen); });
+    const int rx0 = s8_fl(g.rb.x0), ox0 = s8_fl(g.ob.x0);
+    const int rpitch = s8_ce(g.rb.x1) - rx0, opitch = s8_ce(g.ob.x1) - ox0;
+    group_range[gi] = std::make_pair((int)bundles.size(), g.count);
+    int item = 0;
+    for (int id : ids) {
+      const CuBundleHost& b = hb[id];
+      int any = -1;
+      for (int s = 0; s < CU_SLOTS; s++) if (b.slot_task[s] >= 0) { any = b.slot_task[s]; break; }
+      const SearchTask& t = tasks[any];
+      S8Bundle d{};
+      d.org_off = (b.cu_y - g.ob.y0) * opitch + (b.cu_x - ox0);
+      d.win_off = (b.cu_y + t.lt_y - g.rb.y0) * rpitch + (b.cu_x + t.lt_x - rx0);
+      d.nx = t.rb_x - t.lt_x + 1; d.ny = t.rb_y - t.lt_y + 1;
+      d.lt_x = t.lt_x; d.lt_y = t.lt_y; d.pred_x = t.pred_x; d.pred_y = t.pred_y; d.lambda = t.lambda_cost;
+      d.n_blk = (d.nx + 15) / 16;
+      d.n_rowgroups = (d.ny + cu_ky(b.S) - 1) / cu_ky(b.S);
+      d.n_items = (d.n_blk * d.n_rowgroups + 7) / 8;
+      d.item_start = item; item += d.n_items;
+      for (int s = 0; s < CU_SLOTS; s++) d.out_idx[s] = b.slot_task[s];
+      const int v = cu_variant(b.S, b.fen);
+      variant_cost[v] += item_cost(b.S, b.fen) * d.n_items;
+      bundles.push_back(d); bvar.push_back(v);
+    }
+    all_r = s8_union(all_r, g.rb); all_o = s8_union(all_o, g.ob);
+  }
+  long long target[CUV_COUNT];
+  for (int v = 0; v < CUV_COUNT; v++) target[v] = std::max<long long>(variant_cost[v] / std::max(1, sm_count * 2 * 12), 4000);
+  std::vector<S8Unit> units;
+  for (size_t gi = 0; gi < groups.size(); gi++) {
+    const Group& g = groups[gi];
+    S8Unit u{};
+    const int rx0 = s8_fl(g.rb.x0), ox0 = s8_fl(g.ob.x0);
+    u.ref_bx = rx0; u.ref_by = g.rb.y0; u.ref_pitch = s8_ce(g.rb.x1) - rx0; u.ref_rows = g.rb.y1 - g.rb.y0;
+    u.org_bx = ox0; u.org_by = g.ob.y0; u.org_pitch = s8_ce(g.ob.x1) - ox0; u.org_rows = g.ob.y1 - g.ob.y0;
+    int org_off = 0;
+    u.smem_need = s8_smem_need(g.rb, g.ob, &org_off);
+    u.org_smem_off = org_off;
+    const int bfirst = group_range[gi].first, bcount = group_range[gi].second;
+    long long acc = 0;
+    int ufirst_item = 0, ufirst_b = 0;
+    auto emit = [&](int last_local, int item_last) {
+      u.job_first = bfirst + ufirst_b; u.item_first = ufirst_item; u.item_last = item_last; u.job_count = last_local - ufirst_b + 1;
+      u.variant = bvar[u.job_first];
+      units.push_back(u);
+    };
+    for (int bl = 0; bl < bcount; bl++) {
+      const S8Bundle& b = bundles[bfirst + bl];
+      const int v = bvar[bfirst + bl];
+      // cost of one item of this variant
+      long long per_item = 1;
+      switch (v) {
+        case CUV_8: per_item = item_cost(8, false); break;
+        case CUV_16_F0: per_item = item_cost(16, false); break;
+        case CUV_16_F1: per_item = item_cost(16, true); break;
+        case CUV_32_F0: per_item = item_cost(32, false); break;
+        case CUV_32_F1: per_item = item_cost(32, true); break;
+        case CUV_64_F0: per_item = item_cost(64, false); break;
+        default: per_item = item_cost(64, true); break;
+      }
+      if (acc > 0 && v != bvar[bfirst + bl - 1]) { emit(bl - 1, b.item_start); acc = 0; ufirst_item = b.item_start; ufirst_b = bl; }
+      int done = 0;
+      while (done < b.n_items) {
+        const long long room = target[v] - acc;
+        const int take = (int)std::min<long long>(b.n_items - done, std::max<long long>(1, (room + per_item - 1) / per_item));
+        acc += take * per_item; done += take;
+        if (acc >= target[v]) {
+          emit(bl, b.item_start + done);
+          acc = 0; ufirst_item = b.item_start + done; ufirst_b = (done == b.n_items) ? bl + 1 : bl;
+        }
+      }
+    }
+    if (acc > 0) { const S8Bundle& last = bundles[bfirst + bcount - 1]; emit(bcount - 1, last.item_start + last.n_items); }
+  }
+  std::stable_sort(units.begin(), units.end(), [](const S8Unit& a, const S8Unit& b) { return a.variant < b.variant; });
+  for (size_t i = 0; i < units.size(); i++) {
+    const int v = units[i].variant;
+    if (out->unit_count[v]++ == 0) out->unit_first[v] = (int)i;
+    out->smem_of[v] = std::max(out->smem_of[v], units[i].smem_need);
+  }
+  out->n_units = (int)units.size(); out->n_bundles = (int)bundles.size();
+  out->rbox = S8Box{s8_fl(all_r.x0), all_r.y0, s8_ce(all_r.x1), all_r.y1};
+  out->obox = S8Box{s8_fl(all_o.x0), all_o.y0, s8_ce(all_o.x1), all_o.y1};
+  bool ok = cudaMalloc((void**)&out->d_units, units.size() * sizeof(S8Unit)) == cudaSuccess &&
+            cudaMalloc((void**)&out->d_bundles, bundles.size() * sizeof(S8Bundle)) == cudaSuccess &&
+            cudaMemcpyAsync(out->d_units, units.data(), units.size() * sizeof(S8Unit), cudaMemcpyHostToDevice, stream) == cudaSuccess &&
+            cudaMemcpyAsync(out->d_bundles, bundles.data(), bundles.size() * sizeof(S8Bundle), cudaMemcpyHostToDevice, stream) == cudaSuccess &&
+            cudaStreamSynchronize(stream) == cudaSuccess;
+  if (!ok) { if (err) *err = std::string("cu_build_schedule: ") + cudaGetErrorString(cudaGetLastError()); cu_free_schedule(out); }
+  return ok;
+}
+
+}  // namespace hmb200
