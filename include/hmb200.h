@@ -124,6 +124,14 @@ void hmb200_set_search_range(hmb200_mv pred, int search_range, int cu_x, int cu_
 int  hmb200_build_canonical_jobs(int pic_w, int pic_h, int max_cu, int search_range, uint32_t lambda_cost, hmb200_mv pred,
                                  int ctu_first, int ctu_count, hmb200_pu_job* jobs, int capacity);
 
+/* Same for a rectangle of CTUs [ctu_x0, ctu_x1) x [ctu_y0, ctu_y1) (CTU units): one tile column / CTU row of a picture.
+ * Jobs come out in CTU raster order inside the rectangle. */
+int  hmb200_build_canonical_jobs_rect(int pic_w, int pic_h, int max_cu, int search_range, uint32_t lambda_cost, hmb200_mv pred,
+                                      int ctu_x0, int ctu_x1, int ctu_y0, int ctu_y1, hmb200_pu_job* jobs, int capacity);
+/* CTU column range of tile column `column` of `n_columns` uniformly spaced tile columns
+ * (TileUniformSpacing, TLibCommon/TComPicSym.cpp:217-229): the multi-GPU tile-column shard of a picture. */
+int  hmb200_tile_column_range(int pic_w, int max_cu, int n_columns, int column, int* ctu_x0, int* ctu_x1);
+
 /* ------------------------------------------------------------------ planes ------------------------------------ */
 
 /* Uploads one luma plane once per frame.  host_origin points at sample (0,0) of a TComPicYuv luma buffer

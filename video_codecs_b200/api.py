@@ -61,6 +61,8 @@ def _load():
         "hmb200_launch_count": (C.c_uint64, []),
         "hmb200_set_search_range": (None, [_Mv, i32, i32, i32, i32, i32, i32, i32, C.POINTER(_Mv), C.POINTER(_Mv)]),
         "hmb200_build_canonical_jobs": (i32, [i32, i32, i32, i32, u32, _Mv, i32, i32, vp, i32]),
+        "hmb200_build_canonical_jobs_rect": (i32, [i32, i32, i32, i32, u32, _Mv, i32, i32, i32, i32, vp, i32]),
+        "hmb200_tile_column_range": (i32, [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]),
         "hmb200_register_plane": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32]),
         "hmb200_register_plane_u8": (i32, [vp, i32, i32, i32, i32, i32, i32, i32]),
         "hmb200_read_plane": (i32, [i32, vp, i32]), "hmb200_release_plane": (None, [i32]),
@@ -123,6 +125,19 @@ class HMB200:
         jobs = np.zeros(n, dtype=JOB_DTYPE)
         self._check(self.lib.hmb200_build_canonical_jobs(pic_w, pic_h, max_cu, search_range, int(lambda_cost), _Mv(*pred),
                                                          ctu_first, ctu_count, jobs.ctypes.data, n))
+        return jobs
+
+    def tile_column_range(self, pic_w, n_columns, column, max_cu=64):
+        a, b = C.c_int(), C.c_int()
+        self._check(self.lib.hmb200_tile_column_range(pic_w, max_cu, n_columns, column, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def build_canonical_jobs_rect(self, pic_w, pic_h, ctu_x, ctu_y, search_range=64, lambda_cost=0, pred=(0, 0), max_cu=64):
+        """ctu_x / ctu_y: (first, end) CTU ranges."""
+        args = (pic_w, pic_h, max_cu, search_range, int(lambda_cost), _Mv(*pred), ctu_x[0], ctu_x[1], ctu_y[0], ctu_y[1])
+        n = self._check(self.lib.hmb200_build_canonical_jobs_rect(*args, None, 0))
+        jobs = np.zeros(n, dtype=JOB_DTYPE)
+        self._check(self.lib.hmb200_build_canonical_jobs_rect(*args, jobs.ctypes.data, n))
         return jobs
 
     # -- planes ----------------------------------------------------------------------------------------------------

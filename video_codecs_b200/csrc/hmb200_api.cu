@@ -238,13 +238,10 @@ void hmb200_set_search_range(hmb200_mv pred, int search_range, int cu_x, int cu_
   lt->x = lx >> 2; lt->y = ly >> 2; rb->x = rx >> 2; rb->y = ry >> 2;      // arithmetic shifts of Shorts
 }
 
-int hmb200_build_canonical_jobs(int pic_w, int pic_h, int max_cu, int search_range, uint32_t lambda_cost, hmb200_mv pred,
-                                int ctu_first, int ctu_count, hmb200_pu_job* jobs, int capacity) {
-  if (pic_w <= 0 || pic_h <= 0 || max_cu < 8 || max_cu > 64 || (max_cu & (max_cu - 1))) return HMB200_ERR_ARG;
-  const int ctus_x = (pic_w + max_cu - 1) / max_cu, ctus_y = (pic_h + max_cu - 1) / max_cu;
-  const int n_ctus = ctus_x * ctus_y;
-  if (ctu_first < 0) ctu_first = 0;
-  int ctu_end = (ctu_count < 0) ? n_ctus : std::min(n_ctus, ctu_first + ctu_count);
+static int canonical_jobs_of_ctus(int pic_w, int pic_h, int max_cu, int search_range, uint32_t lambda_cost, hmb200_mv pred,
+                                  int cx0, int cx1, int cy0, int cy1, int raster_first, int raster_end,
+                                  hmb200_pu_job* jobs, int capacity) {
+  const int ctus_x = (pic_w + max_cu - 1) / max_cu;
   int count = 0;
   auto emit = [&](int cu_x, int cu_y, int px, int py, int w, int h) {
     if (count < capacity && jobs) {
@@ -258,27 +255,56 @@ int hmb200_build_canonical_jobs(int pic_w, int pic_h, int max_cu, int search_ran
     }
     count++;
   };
-  for (int ctu = ctu_first; ctu < ctu_end; ctu++) {
-    const int ox = (ctu % ctus_x) * max_cu, oy = (ctu / ctus_x) * max_cu;
-    int depth = 0;
-    for (int s = max_cu; s >= 8; s >>= 1, depth++) {
-      for (int cy = oy; cy < oy + max_cu; cy += s)
-        for (int cx = ox; cx < ox + max_cu; cx += s) {
-          if (cx + s > pic_w || cy + s > pic_h) continue;          // the encoder only tests CUs inside the picture
-          const int q = s >> 2;
-          emit(cx, cy, cx, cy, s, s);                                              // SIZE_2Nx2N
-          emit(cx, cy, cx, cy, s, s / 2);  emit(cx, cy, cx, cy + s / 2, s, s / 2);  // SIZE_2NxN
-          emit(cx, cy, cx, cy, s / 2, s);  emit(cx, cy, cx + s / 2, cy, s / 2, s);  // SIZE_Nx2N
-          if (s > 8) {                                                              // AMP: not for the smallest CU
-            emit(cx, cy, cx, cy, s, q);      emit(cx, cy, cx, cy + q, s, s - q);    // SIZE_2NxnU
-            emit(cx, cy, cx, cy, s, s - q);  emit(cx, cy, cx, cy + s - q, s, q);    // SIZE_2NxnD
-            emit(cx, cy, cx, cy, q, s);      emit(cx, cy, cx + q, cy, s - q, s);    // SIZE_nLx2N
-            emit(cx, cy, cx, cy, s - q, s);  emit(cx, cy, cx + s - q, cy, q, s);    // SIZE_nRx2N
+  for (int cty = cy0; cty < cy1; cty++)
+    for (int ctx = cx0; ctx < cx1; ctx++) {
+      const int ctu = cty * ctus_x + ctx;
+      if (ctu < raster_first || ctu >= raster_end) continue;
+      const int ox = ctx * max_cu, oy = cty * max_cu;
+      for (int s = max_cu; s >= 8; s >>= 1) {
+        for (int cy = oy; cy < oy + max_cu; cy += s)
+          for (int cx = ox; cx < ox + max_cu; cx += s) {
+            if (cx + s > pic_w || cy + s > pic_h) continue;          // the encoder only tests CUs inside the picture
+            const int q = s >> 2;
+            emit(cx, cy, cx, cy, s, s);                                              // SIZE_2Nx2N
+            emit(cx, cy, cx, cy, s, s / 2);  emit(cx, cy, cx, cy + s / 2, s, s / 2);  // SIZE_2NxN
+            emit(cx, cy, cx, cy, s / 2, s);  emit(cx, cy, cx + s / 2, cy, s / 2, s);  // SIZE_Nx2N
+            if (s > 8) {                                                              // AMP: not for the smallest CU
+              emit(cx, cy, cx, cy, s, q);      emit(cx, cy, cx, cy + q, s, s - q);    // SIZE_2NxnU
+              emit(cx, cy, cx, cy, s, s - q);  emit(cx, cy, cx, cy + s - q, s, q);    // SIZE_2NxnD
+              emit(cx, cy, cx, cy, q, s);      emit(cx, cy, cx + q, cy, s - q, s);    // SIZE_nLx2N
+              emit(cx, cy, cx, cy, s - q, s);  emit(cx, cy, cx + s - q, cy, q, s);    // SIZE_nRx2N
+            }
           }
-        }
+      }
     }
-  }
   return count;
+}
+
+int hmb200_build_canonical_jobs(int pic_w, int pic_h, int max_cu, int search_range, uint32_t lambda_cost, hmb200_mv pred,
+                                int ctu_first, int ctu_count, hmb200_pu_job* jobs, int capacity) {
+  if (pic_w <= 0 || pic_h <= 0 || max_cu < 8 || max_cu > 64 || (max_cu & (max_cu - 1))) return HMB200_ERR_ARG;
+  const int ctus_x = (pic_w + max_cu - 1) / max_cu, ctus_y = (pic_h + max_cu - 1) / max_cu;
+  const int n_ctus = ctus_x * ctus_y;
+  if (ctu_first < 0) ctu_first = 0;
+  const int ctu_end = (ctu_count < 0) ? n_ctus : std::min(n_ctus, ctu_first + ctu_count);
+  return canonical_jobs_of_ctus(pic_w, pic_h, max_cu, search_range, lambda_cost, pred, 0, ctus_x, 0, ctus_y, ctu_first, ctu_end, jobs, capacity);
+}
+
+int hmb200_tile_column_range(int pic_w, int max_cu, int n_columns, int column, int* ctu_x0, int* ctu_x1) {
+  if (pic_w <= 0 || max_cu <= 0 || n_columns <= 0 || column < 0 || column >= n_columns || !ctu_x0 || !ctu_x1) return HMB200_ERR_ARG;
+  const int ctus_x = (pic_w + max_cu - 1) / max_cu;
+  if (n_columns > ctus_x) return HMB200_ERR_ARG;
+  *ctu_x0 = (column * ctus_x) / n_columns;               // TLibCommon/TComPicSym.cpp:217-229 (uniform tile spacing)
+  *ctu_x1 = ((column + 1) * ctus_x) / n_columns;
+  return HMB200_OK;
+}
+
+int hmb200_build_canonical_jobs_rect(int pic_w, int pic_h, int max_cu, int search_range, uint32_t lambda_cost, hmb200_mv pred,
+                                     int ctu_x0, int ctu_x1, int ctu_y0, int ctu_y1, hmb200_pu_job* jobs, int capacity) {
+  if (pic_w <= 0 || pic_h <= 0 || max_cu < 8 || max_cu > 64 || (max_cu & (max_cu - 1))) return HMB200_ERR_ARG;
+  const int ctus_x = (pic_w + max_cu - 1) / max_cu, ctus_y = (pic_h + max_cu - 1) / max_cu;
+  if (ctu_x0 < 0 || ctu_y0 < 0 || ctu_x1 > ctus_x || ctu_y1 > ctus_y || ctu_x0 > ctu_x1 || ctu_y0 > ctu_y1) return HMB200_ERR_ARG;
+  return canonical_jobs_of_ctus(pic_w, pic_h, max_cu, search_range, lambda_cost, pred, ctu_x0, ctu_x1, ctu_y0, ctu_y1, 0, ctus_x * ctus_y, jobs, capacity);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
