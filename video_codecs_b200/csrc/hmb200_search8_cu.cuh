@@ -109,15 +109,19 @@ __device__ __forceinline__ void cu_row1(const uint8_t* rp8, const uint32_t (&o)[
   }
 }
 
-__device__ __forceinline__ void cu_min(unsigned long long& best, uint32_t cost, uint32_t idx) {
-  const unsigned long long key = make_key(cost, idx);
-  best = key < best ? key : best;
+// Per-lane running argmin as ONE 32-bit key: (cost << CU_LOCAL_BITS) | local index.  cost < 2^21 for 8-bit content
+// (SAD <= 64*32*255*2, MV cost < 2^16); the local index numbers this lane's candidates of the current CU in the order
+// it visits them (= raster order inside the lane), so an unsigned min is "strict '<', first wins" (TEncSearch.cpp:
+// 3813-3835).  Items are dealt to warps round-robin, which makes the local index decodable at flush time.
+constexpr int CU_LOCAL_BITS = 11;
+__device__ __forceinline__ void cu_min(uint32_t& best, uint32_t val_scaled, uint32_t base) {
+  best = min(best, val_scaled + base);
 }
 
 // S >= 16: grid E[4][4][k], odd-row strips O[4][k]; derives the 13 PU costs of candidate column k and updates the argmins
 template <int S, bool FEN>
-__device__ __forceinline__ void cu_epilogue16(const uint32_t (&E)[4][4][4], const uint32_t (&O)[4][4], int k, uint32_t cmv, uint32_t idx,
-                                              unsigned long long (&best)[CU_SLOTS]) {
+__device__ __forceinline__ void cu_epilogue16(const uint32_t (&E)[4][4][4], const uint32_t (&O)[4][4], int k, uint32_t base,
+                                              uint32_t (&best)[CU_SLOTS]) {
   uint32_t er[4], ec[4];
 #pragma unroll
   for (int r = 0; r < 4; r++) er[r] = E[r][0][k] + E[r][1][k] + E[r][2][k] + E[r][3][k];
@@ -126,21 +130,22 @@ __device__ __forceinline__ void cu_epilogue16(const uint32_t (&E)[4][4][4], cons
   // a PU with <= 8 rows under FEN visits every row: add the odd rows of its strips; all others shift by iSubShift
   constexpr bool f1 = FEN && cu_slot_h(S, 1) <= 8;      // 2NxN halves (S == 16)
   constexpr bool f5 = FEN && cu_slot_h(S, 5) <= 8;      // AMP quarter strips (S == 16, 32)
-  constexpr int sh_full = FEN ? 1 : 0;                  // iSubShift of the PUs taller than 8 rows
+  constexpr uint32_t M1 = 1u << CU_LOCAL_BITS;          // key scale of a full-row PU
+  constexpr uint32_t MS = M1 << (FEN ? 1 : 0);          // ... of a PU with iSubShift = FEN
   const uint32_t top = er[0] + er[1], bot = er[2] + er[3];
-  cu_min(best[0], ((top + bot) << sh_full) + cmv, idx);
-  cu_min(best[1], (f1 ? top + O[0][k] + O[1][k] : top << sh_full) + cmv, idx);
-  cu_min(best[2], (f1 ? bot + O[2][k] + O[3][k] : bot << sh_full) + cmv, idx);
-  cu_min(best[3], ((ec[0] + ec[1]) << sh_full) + cmv, idx);
-  cu_min(best[4], ((ec[2] + ec[3]) << sh_full) + cmv, idx);
-  cu_min(best[5], (f5 ? er[0] + O[0][k] : er[0] << sh_full) + cmv, idx);
-  cu_min(best[6], ((er[1] + bot) << sh_full) + cmv, idx);
-  cu_min(best[7], ((top + er[2]) << sh_full) + cmv, idx);
-  cu_min(best[8], (f5 ? er[3] + O[3][k] : er[3] << sh_full) + cmv, idx);
-  cu_min(best[9], (ec[0] << sh_full) + cmv, idx);
-  cu_min(best[10], ((ec[1] + ec[2] + ec[3]) << sh_full) + cmv, idx);
-  cu_min(best[11], ((ec[0] + ec[1] + ec[2]) << sh_full) + cmv, idx);
-  cu_min(best[12], (ec[3] << sh_full) + cmv, idx);
+  cu_min(best[0], (top + bot) * MS, base);
+  cu_min(best[1], f1 ? (top + O[0][k] + O[1][k]) * M1 : top * MS, base);
+  cu_min(best[2], f1 ? (bot + O[2][k] + O[3][k]) * M1 : bot * MS, base);
+  cu_min(best[3], (ec[0] + ec[1]) * MS, base);
+  cu_min(best[4], (ec[2] + ec[3]) * MS, base);
+  cu_min(best[5], f5 ? (er[0] + O[0][k]) * M1 : er[0] * MS, base);
+  cu_min(best[6], (er[1] + bot) * MS, base);
+  cu_min(best[7], (top + er[2]) * MS, base);
+  cu_min(best[8], f5 ? (er[3] + O[3][k]) * M1 : er[3] * MS, base);
+  cu_min(best[9], ec[0] * MS, base);
+  cu_min(best[10], (ec[1] + ec[2] + ec[3]) * MS, base);
+  cu_min(best[11], (ec[0] + ec[1] + ec[2]) * MS, base);
+  cu_min(best[12], ec[3] * MS, base);
 }
 
 template <int S, bool FEN>
@@ -159,7 +164,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   uint8_t* s_org = s8_smem + un.org_smem_off;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  if (threadIdx.x == 0) { mbar_init(&s_bar, 1); s_next = un.item_first; }
+  if (threadIdx.x == 0) { mbar_init(&s_bar, 1); s_next = 0; }
   __syncthreads();
   if (warp == 0) {
     if (lane == 0) mbar_expect_tx(&s_bar, (uint32_t)(un.ref_pitch * un.ref_rows + un.org_pitch * un.org_rows));
@@ -183,33 +188,43 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
     __syncwarp();
   };
   load_bundle();
-  unsigned long long best[CU_SLOTS];
+  constexpr int LK = (S == 8) ? 4 : 2;                // bits of the within-tile candidate index
+  uint32_t best[CU_SLOTS];
 #pragma unroll
-  for (int s = 0; s < CU_SLOTS; s++) best[s] = ~0ull;
+  for (int s = 0; s < CU_SLOTS; s++) best[s] = 0xffffffffu;
+  int first_item = un.item_first + warp;              // this warp's first item of the current CU (decodes local indices)
   auto flush = [&]() {
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) {
-      unsigned long long b = best[s];
+      unsigned long long b = ~0ull;
+      if (best[s] != 0xffffffffu) {
+        const uint32_t local = best[s] & ((1u << CU_LOCAL_BITS) - 1u);
+        const int it = first_item + (int)(local >> LK) * S8_WARPS;
+        const int q = (it - bd.item_start) * 8 + (lane >> 2);
+        const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
+        const int w = (int)(local & ((1u << LK) - 1u));
+        const int cyi = g * T::KY + (w >> 2), cxi = min(blk * 16, bd.nx - 16) + (lane & 3) + 4 * (w & 3);
+        b = make_key(best[s] >> CU_LOCAL_BITS, (uint32_t)(cyi * bd.nx + cxi));
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
         b = other < b ? other : b;
       }
       if (lane == 0 && b != ~0ull && bd.out_idx[s] >= 0) atomicMin(&keys[bd.out_idx[s]], b);
-      best[s] = ~0ull;
+      best[s] = 0xffffffffu;
     }
   };
+  (void)s_next;
 
-  for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(&s_next, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= un.item_last) break;
+  for (int item = un.item_first + warp; item < un.item_last; item += S8_WARPS) {
     if (item >= bd.item_start + bd.n_items) {
       flush();
       do { bslot++; } while (item >= bundles[bslot].item_start + bundles[bslot].n_items);
       load_bundle();
+      first_item = item;
     }
+    const uint32_t tile_local = (uint32_t)((item - first_item) / S8_WARPS) << LK;
     const int q = (item - bd.item_start) * 8 + (lane >> 2);
     if (q < bd.n_blk * bd.n_rowgroups) {
     const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
@@ -265,15 +280,15 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
           const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + cyi) << 2) - bd.pred_y);
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            const uint32_t cmv = (px[k] + py) >> 16;
-            const uint32_t idx = (uint32_t)(cyi * bd.nx + cxi0 + 4 * k);
+            constexpr uint32_t M1 = 1u << CU_LOCAL_BITS;
+            const uint32_t base = (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)(jy * 4 + k);
             const uint32_t t = Q[jy][0][0][k] + Q[jy][0][1][k], b = Q[jy][1][0][k] + Q[jy][1][1][k];
             const uint32_t l = Q[jy][0][0][k] + Q[jy][1][0][k], r = Q[jy][0][1][k] + Q[jy][1][1][k];
-            cu_min(best[0], t + b + cmv, idx);       // 8x8  (no PU of an 8x8 CU has more than 8 rows: iSubShift = 0)
-            cu_min(best[1], t + cmv, idx);           // 8x4 top
-            cu_min(best[2], b + cmv, idx);           // 8x4 bottom
-            cu_min(best[3], l + cmv, idx);           // 4x8 left
-            cu_min(best[4], r + cmv, idx);           // 4x8 right
+            cu_min(best[0], (t + b) * M1, base);     // 8x8  (no PU of an 8x8 CU has more than 8 rows: iSubShift = 0)
+            cu_min(best[1], t * M1, base);           // 8x4 top
+            cu_min(best[2], b * M1, base);           // 8x4 bottom
+            cu_min(best[3], l * M1, base);           // 4x8 left
+            cu_min(best[4], r * M1, base);           // 4x8 right
           }
         }
       }
@@ -317,7 +332,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
         const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + cyi0) << 2) - bd.pred_y);
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          cu_epilogue16<S, FEN>(E, O, k, (px[k] + py) >> 16, (uint32_t)(cyi0 * bd.nx + cxi0 + 4 * k), best);
+          cu_epilogue16<S, FEN>(E, O, k, (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)k, best);
       }
     }
     }   // q in range
@@ -375,6 +390,11 @@ inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, std::vector
     const int S = std::max(t.w, t.h);
     if (!(S == 8 || S == 16 || S == 32 || S == 64) || t.ref_x != t.org_x || t.ref_y != t.org_y || t.org_x < 0 || t.org_y < 0) continue;
     if (t.rb_x - t.lt_x + 1 < 16 || t.rb_y < t.lt_y) continue;
+    {   // the per-lane local candidate index must fit CU_LOCAL_BITS (see cu_min)
+      const int n_blk = (t.rb_x - t.lt_x + 1 + 15) / 16, nrg = (t.rb_y - t.lt_y + cu_ky(S)) / cu_ky(S);
+      const int n_items = (n_blk * nrg + 7) / 8;
+      if (n_items / S8_WARPS + 2 >= (1 << (CU_LOCAL_BITS - (S == 8 ? 4 : 2)))) continue;
+    }
     const int cx = t.org_x - t.org_x % S, cy = t.org_y - t.org_y % S;
     if (s8_smem_need(S8Box{cx + t.lt_x, cy + t.lt_y, cx + t.rb_x + S, cy + t.rb_y + S}, S8Box{cx, cy, cx + S, cy + S}, nullptr) > S8_SMEM_MAX) continue;
     int slot = -1;
