@@ -43,6 +43,7 @@ struct State {
   void* pinned = nullptr; size_t pinned_bytes = 0;
   void* dstage = nullptr; size_t dstage_bytes = 0;     // device staging for plane uploads / per-call blocks
   Plane pattern;                                       // 64x64 int16 pattern buffer for the 1:1 entries
+  std::vector<std::pair<size_t, void*> > pool;         // released plane buffers, recycled by size (no malloc/free per frame)
   uint64_t launches = 0;
   float last_total_ms = 0, last_search_ms = 0, last_frac_ms = 0;
 };
@@ -90,7 +91,10 @@ int make_plane(Plane& p, int width, int height, int mx, int my, int bit_depth) {
   p.d.width = width; p.d.height = height; p.d.margin_x = mx; p.d.margin_y = my;
   p.d.bytes_per_sample = bps; p.d.bit_depth = bit_depth;
   p.bytes = (size_t)pitch_bytes * total_h;
-  CUDA_TRY(cudaMalloc(&p.d.base, p.bytes));
+  p.d.base = nullptr;
+  for (size_t i = 0; i < g.pool.size(); i++)
+    if (g.pool[i].first == p.bytes) { p.d.base = g.pool[i].second; g.pool.erase(g.pool.begin() + i); break; }
+  if (!p.d.base) CUDA_TRY(cudaMalloc(&p.d.base, p.bytes));
   p.used = true;
   return HMB200_OK;
 }
@@ -199,6 +203,8 @@ void hmb200_shutdown(void) {
   cudaStreamSynchronize(g.stream);
   for (auto& p : g.planes) if (p.used && p.d.base) cudaFree(p.d.base);
   g.planes.clear();
+  for (auto& b : g.pool) cudaFree(b.second);
+  g.pool.clear();
   if (g.pattern.d.base) cudaFree(g.pattern.d.base);
   g.pattern = Plane();
   if (g.pinned) cudaFreeHost(g.pinned);
@@ -395,7 +401,10 @@ void hmb200_release_plane(int plane_id) {
   Plane* p = get_plane(plane_id);
   if (!p) return;
   cudaStreamSynchronize(g.stream);
-  if (p->d.base) cudaFree(p->d.base);
+  if (p->d.base) {
+    if (g.pool.size() < 16) g.pool.push_back(std::make_pair(p->bytes, p->d.base));
+    else cudaFree(p->d.base);
+  }
   *p = Plane();
 }
 
@@ -620,9 +629,13 @@ int hmb200_fetch_results(hmb200_prepared* p, hmb200_pu_result* results) {
   NEED_READY();
   if (!p || (p->n > 0 && !results)) return fail(HMB200_ERR_ARG, "hmb200_fetch_results: bad arguments");
   if (p->n == 0) return HMB200_OK;
-  CUDA_TRY(cudaMemcpyAsync(results, p->d_results, (size_t)p->n * sizeof(hmb200_pu_result), cudaMemcpyDeviceToHost, g.stream));
+  const size_t bytes = (size_t)p->n * sizeof(hmb200_pu_result);
+  int rc = ensure_pinned(bytes);
+  if (rc != HMB200_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(g.pinned, p->d_results, bytes, cudaMemcpyDeviceToHost, g.stream));    // pinned staging: full PCIe rate
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());
+  memcpy(results, g.pinned, bytes);
   return HMB200_OK;
 }
 

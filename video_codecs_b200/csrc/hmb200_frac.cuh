@@ -106,6 +106,78 @@ __device__ __forceinline__ void frac_tile_diff(const RefT* ref, int ref_pitch, c
   }
 }
 
+// ---- 8-bit planes: dot-product form ---------------------------------------------------------------------------------
+// taps of one fraction as two packed signed-byte words (IDP.4A.U8.S8 operands)
+__device__ __forceinline__ void frac_packed_taps(int f, int& lo, int& hi) {
+  // {0,0,0,64 | 0,0,0,0}  {-1,4,-10,58 | 17,-5,1,0}  {-1,4,-11,40 | 40,-11,4,-1}  {0,1,-5,17 | 58,-10,4,-1}
+  lo = (f == 0) ? 0x40000000 : (f == 1) ? 0x3AF604FF : (f == 2) ? 0x28F504FF : 0x11FB0100;
+  hi = (f == 0) ? 0x00000000 : (f == 1) ? 0x0001FB11 : (f == 2) ? (int)0xFF04F528 : (int)0xFF04F63A;
+}
+
+// unsigned samples x signed taps (SASS IDP.4A.U8.S8)
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// Same result as frac_tile_diff for 8-bit samples, one code path for every fraction (the pass-through taps
+// {0,0,0,64,0,0,0,0} give exactly filterCopy's values: 64*s >> 0 - 8192 and (64*(c + 8192) + 2^(5+head)) >> (6+head)).
+// Horizontal pass: each output is two IDP.4A on byte-shifted words of the row; vertical pass: 8 IMAD.  Column strips of
+// four share one rolled loop body, which keeps the kernel at ~20 KB of code (the fully specialised version thrashed
+// the instruction cache: ncu 'no_instruction' was the top stall).
+template <int N>
+__device__ __forceinline__ void frac_tile_diff_u8(const uint8_t* ref, int ref_pitch, const uint8_t* org, int org_pitch, int fx, int fy,
+                                                  int (&d)[N * N]) {
+  constexpr int head = 6, vshift = 12;                                   // bit depth 8: headroom 14 - 8
+  constexpr int voff = (1 << (vshift - 1)) + (8192 << 6);
+  int t0, t1, tv[8];
+  frac_packed_taps(fx, t0, t1);
+  frac_load_taps(fy, tv);
+  int dA[N][4], dB[N][4];
+#pragma unroll 1
+  for (int cs = 0; cs < N; cs += 4) {
+    int hh[N + 7][4];
+#pragma unroll
+    for (int r = 0; r < N + 7; r++) {
+      // 11 samples starting at column cs-3 of row r-3, as three words s0..s2 aligned to the first sample
+      const uintptr_t a = reinterpret_cast<uintptr_t>(ref + (ptrdiff_t)(r - 3) * ref_pitch + (cs - 3));
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+      const uint32_t sh = (uint32_t)(a & 3) * 8u;
+      const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+      const uint32_t s0 = __funnelshift_r(w0, w1, sh), s1 = __funnelshift_r(w1, w2, sh), s2 = __funnelshift_r(w2, w3, sh);
+      // W[k] = samples k..k+3
+      const uint32_t W0 = s0, W1 = __funnelshift_r(s0, s1, 8), W2 = __funnelshift_r(s0, s1, 16), W3 = __funnelshift_r(s0, s1, 24);
+      const uint32_t W4 = s1, W5 = __funnelshift_r(s1, s2, 8), W6 = __funnelshift_r(s1, s2, 16), W7 = __funnelshift_r(s1, s2, 24);
+      hh[r][0] = dp4a_us(W4, t1, dp4a_us(W0, t0, -8192));                  // filter<> isFirst at bit depth 8: shift 0, offset -8192
+      hh[r][1] = dp4a_us(W5, t1, dp4a_us(W1, t0, -8192));
+      hh[r][2] = dp4a_us(W6, t1, dp4a_us(W2, t0, -8192));
+      hh[r][3] = dp4a_us(W7, t1, dp4a_us(W3, t0, -8192));
+      if (r >= 7) {
+        const int y = r - 7;
+        const uint8_t* op = org + (ptrdiff_t)y * org_pitch + cs;
+        const uint32_t ow = ((reinterpret_cast<uintptr_t>(op) & 3) == 0)
+                                ? __ldg(reinterpret_cast<const uint32_t*>(op))
+                                : ((uint32_t)op[0] | ((uint32_t)op[1] << 8) | ((uint32_t)op[2] << 16) | ((uint32_t)op[3] << 24));
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          int sum = voff;
+#pragma unroll
+          for (int t = 0; t < 8; t++) sum += hh[y + t][c] * tv[t];
+          const int val = min(max(sum >> vshift, 0), 255);               // filter<> isLast + clip
+          const int dv = (int)((ow >> (8 * c)) & 0xffu) - val;
+          if (cs == 0) dA[y][c] = dv; else dB[y][c] = dv;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int y = 0; y < N; y++)
+#pragma unroll
+    for (int c = 0; c < N; c++) d[y * N + c] = (c < 4) ? dA[y][c] : dB[y][c & 3];
+  (void)head;
+}
+
 // stage 0: half-pel candidates around the integer MV; stage 1: quarter-pel candidates 1..8 around the best half.
 // dist: [n_pu][9] accumulators (zeroed by the host; dist[.][0] of stage 1 is written by k_frac_argmin<0>).
 template <typename RefT, typename OrgT, int N, bool HAD>
@@ -142,6 +214,10 @@ k_frac_tiles(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_re
   const int bit_depth = ref_plane.bit_depth;
   const int head = max(2, 14 - bit_depth), maxv = (1 << bit_depth) - 1;
   int d[N * N];
+  if constexpr (sizeof(RefT) == 1 && sizeof(OrgT) == 1) {
+    (void)hskip; (void)vskip;
+    frac_tile_diff_u8<N>(reinterpret_cast<const uint8_t*>(ref), ref_plane.pitch, reinterpret_cast<const uint8_t*>(org), cur_plane.pitch, fx, fy, d);
+  } else
   if (hskip && vskip)  frac_tile_diff<RefT, OrgT, N, true, true>(ref, ref_plane.pitch, org, cur_plane.pitch, fx, fy, head, maxv, d);
   else if (hskip)      frac_tile_diff<RefT, OrgT, N, true, false>(ref, ref_plane.pitch, org, cur_plane.pitch, fx, fy, head, maxv, d);
   else if (vskip)      frac_tile_diff<RefT, OrgT, N, false, true>(ref, ref_plane.pitch, org, cur_plane.pitch, fx, fy, head, maxv, d);
