@@ -308,7 +308,13 @@ def run_ours(args):
         peak_abs, peak_src = int_simd_peak()
         search_s = srch / K / 1e3
         achieved = work["abs_diffs"] / search_s
+        executed = work["abs_diffs_executed"] / search_s
         hbm, hbm_src = hbm_peak()
+        # refinement: integer multiply-add model per PU pixel: 17 SATD candidates x (separable 8-tap
+        # interpolation 16 MAC + Hadamard ~8 add/sub/abs) ~ 400 integer ops per pixel of every PU
+        pu_pixels = float(np.sum(jobs["w"].astype(np.int64) * jobs["h"].astype(np.int64)))
+        frac_ops = 400.0 * pu_pixels
+        imad_peak = 17.7e12
         plane_bytes = (PIC_W + 160) * (CODED_H + 160)
         algo_bytes = 2 * plane_bytes + len(jobs) * (32 + 48)       # both planes once + job list + results
         line = {
@@ -324,8 +330,16 @@ def run_ours(args):
                          "peak": peak_abs / 1e12, "unit": "Tabsdiff/s", "frac": achieved / peak_abs, "traffic": None,
                          "peak_source": peak_src,
                          "algorithmic_absdiffs_per_launch": int(work["abs_diffs"]),
-                         "note": "algorithmic byte abs-diffs as HM executes them (W*H/2 per candidate under FEN for H>8); "
-                                 "per-rank search time incl. key memset + finalize"},
+                         "executed": executed / 1e12, "executed_frac": executed / peak_abs,
+                         "executed_absdiffs_per_launch": int(work["abs_diffs_executed"]), "pus_cu_fused": int(work["pus_fused"]),
+                         "note": "achieved = algorithmic byte abs-diffs as HM executes them (W*H/2 per candidate under FEN for "
+                                 "H>8) per second; executed = abs-diffs the kernels really issue (CU-fused kernels compute each "
+                                 "CU sample once for all 13 partitions, so achieved/peak may exceed 1; executed_frac is the pipe "
+                                 "utilisation); per-rank search time incl. key memset + finalize"},
+            "roofline_refine": {"bound": "int_alu", "kernel": "k_frac_tiles<u8,u8,8|4,HAD>", "achieved": frac_ops / (frac / K / 1e3) / 1e12,
+                                "peak": imad_peak / 1e12, "unit": "Tintop/s", "frac": frac_ops / (frac / K / 1e3) / imad_peak,
+                                "traffic": None, "peak_source": "measured IMAD issue rate, profiles/r01_microbench_int.json",
+                                "note": "400 integer ops per PU pixel (model, DESIGN.md 3.2)"},
             "roofline_hbm": {"bound": "hbm", "achieved": algo_bytes / (ms_per_step / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
                              "frac": algo_bytes / (ms_per_step / 1e3) / 1e9 / hbm, "traffic": None, "peak_source": hbm_src},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(2 * PIC_W * CODED_H),

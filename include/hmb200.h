@@ -202,6 +202,11 @@ int  hmb200_last_timing(float* total_ms, float* search_ms, float* frac_ms);
  * (SURVEY.md section 8d). */
 int  hmb200_prepared_work(const hmb200_prepared* p, uint64_t* cand_sads, uint64_t* abs_diffs);
 
+/* Byte abs-diffs the tiled kernels actually execute for a prepared list, and how many PUs run CU-fused (partial SADs
+ * of a CU shared by all its partitions): executed < algorithmic when fusion applies.  Reported next to the roofline
+ * so that algorithmic throughput and pipe utilisation are not conflated. */
+int  hmb200_prepared_executed_work(const hmb200_prepared* p, uint64_t* abs_diffs_executed, uint64_t* pus_fused);
+
 #ifdef __cplusplus
 }
 #endif

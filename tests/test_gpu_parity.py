@@ -245,3 +245,84 @@ def test_error_behaviour(hm):
         assert len(hm.me_jobs(pid, pid, np.zeros(0, dtype=JOB_DTYPE))) == 0      # empty job list is fine
     finally:
         hm.release_plane(pid)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE.json configs[2] / [4] geometry; the oracle only samples)
+# ---------------------------------------------------------------------------------------------------------------------
+def _run_full(hm, cur, ref, jobs, flags):
+    idc = hm.register_plane_u8(cur, MARGIN, MARGIN, kind=0)
+    idr = hm.register_plane_u8(ref, MARGIN, MARGIN, kind=1)
+    try:
+        prep = hm.prepare_jobs(jobs, flags, 8)
+        prep.run(idc, idr)
+        out = prep.fetch()
+        work = prep.work()
+        prep.free()
+        return out, work
+    finally:
+        hm.release_plane(idc)
+        hm.release_plane(idr)
+
+
+def test_1080p_fused_path_equals_per_pu_path_and_oracle_samples(hm, monkeypatch):
+    """The CU-fused kernels (one pass per CU for all 13 partitions) and the per-PU kernels must give the same MV field,
+    SADs and refinement for the whole 1080p canonical list; 400 sampled PUs are also checked against the oracle."""
+    W, H = 1920, 1088
+    f0, f1 = synth.luma_frame(W, H, 0, seed=21), synth.luma_frame(W, H, 1, seed=21)
+    lam = int(np.floor(65536.0 * np.sqrt(0.4624 * 2 ** ((35 - 12) / 3.0))))
+    jobs = hm.build_canonical_jobs(W, H, 64, lam)
+    assert len(jobs) == 302430
+    fused, work = _run_full(hm, f1, f0, jobs, flags_of(1, 1))
+    assert work["pus_fused"] == len(jobs) and work["abs_diffs_executed"] < work["abs_diffs"]
+    monkeypatch.setenv("HMB200_NO_CU_FUSION", "1")
+    plain, work2 = _run_full(hm, f1, f0, jobs, flags_of(1, 1))
+    monkeypatch.delenv("HMB200_NO_CU_FUSION")
+    assert work2["pus_fused"] == 0 and work2["abs_diffs_executed"] == work2["abs_diffs"] == work["abs_diffs"]
+    assert results_equal(fused, plain) == []
+    # every MV lies in its window
+    assert np.all((fused["mv_x"] >= jobs["lt_x"]) & (fused["mv_x"] <= jobs["rb_x"]) &
+                  (fused["mv_y"] >= jobs["lt_y"]) & (fused["mv_y"] <= jobs["rb_y"]))
+    rng = np.random.default_rng(3)
+    pick = np.sort(rng.choice(len(jobs), 400, replace=False))
+    cur, o0, stride = padded(f1)
+    ref, _, _ = padded(f0)
+    exp, _ = Oracle(fen=1, hadme=1).run_jobs((cur, o0, stride), (ref, o0, stride), jobs[pick], 8, True)
+    assert results_equal(fused[pick], exp) == []
+
+
+def test_2160p_translation_property(hm):
+    """cur(x, y) = ref(x + 7, y - 5): every PU whose displaced block stays inside the picture must find MV (7, -5) with
+    SAD 0 and keep it through the refinement (half = quarter = 0); 3840x2160, the largest geometry of BASELINE.json."""
+    W, H, dx, dy = 3840, 2160, 7, -5
+    big = synth.luma_frame(W + 32, H + 32, 0, seed=5, n_rect=0)
+    ref = np.ascontiguousarray(big[16:16 + H, 16:16 + W])
+    cur = np.ascontiguousarray(big[16 + dy:16 + dy + H, 16 + dx:16 + dx + W])
+    jobs = hm.build_canonical_jobs(W, H, 64, 40000)
+    res, work = _run_full(hm, cur, ref, jobs, flags_of(1, 1))
+    inside = (jobs["pu_x"] + dx >= 0) & (jobs["pu_y"] + dy >= 0) & (jobs["pu_x"] + jobs["w"] + dx <= W) & \
+             (jobs["pu_y"] + jobs["h"] + dy <= H)
+    assert inside.sum() > 0.97 * len(jobs)
+    r = res[inside]
+    assert np.all(r["mv_x"] == dx) and np.all(r["mv_y"] == dy) and np.all(r["sad"] == 0)
+    assert np.all(r["half_x"] == 0) and np.all(r["half_y"] == 0) and np.all(r["qter_x"] == 0) and np.all(r["qter_y"] == 0)
+    assert work["cand_sads"] > 1.9e10
+
+
+def test_search_range_128_vs_oracle(hm):
+    """+-128 windows (66049 candidates, BASELINE.json configs[3]'s range): window splitting across shared-memory groups."""
+    W, H = 320, 256
+    f0, f1 = synth.luma_frame(W, H, 0, seed=13), synth.luma_frame(W, H, 2, seed=13)
+    jobs = hm.build_canonical_jobs(W, H, 128, 123456, pred=(6, -3), ctu_first=6, ctu_count=1)[::9]
+    jobs = np.concatenate([jobs, hm.build_canonical_jobs(W, H, 128, 123456, ctu_first=0, ctu_count=1)[:13]])
+    cur, o0, stride = padded(f1, 144)
+    ref, _, _ = padded(f0, 144)
+    idc = hm.register_plane_u8(f1, 144, 144, kind=0)
+    idr = hm.register_plane_u8(f0, 144, 144, kind=1)
+    try:
+        got = hm.me_jobs(idc, idr, jobs, flags_of(1, 1))
+    finally:
+        hm.release_plane(idc)
+        hm.release_plane(idr)
+    exp, _ = Oracle(fen=1, hadme=1).run_jobs((cur, o0, stride), (ref, o0, stride), jobs, 8, True)
+    assert results_equal(got, exp) == []

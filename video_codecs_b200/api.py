@@ -79,6 +79,7 @@ def _load():
         "hmb200_sync": (i32, []),
         "hmb200_last_timing": (i32, [C.POINTER(C.c_float)] * 3),
         "hmb200_prepared_work": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "hmb200_prepared_executed_work": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)          # AttributeError here == the library does not export what the header declares
@@ -241,7 +242,9 @@ class Prepared:
     def work(self):
         a, b = C.c_uint64(), C.c_uint64()
         self.o._check(self.o.lib.hmb200_prepared_work(self.h, C.byref(a), C.byref(b)))
-        return {"cand_sads": a.value, "abs_diffs": b.value}
+        c, d = C.c_uint64(), C.c_uint64()
+        self.o._check(self.o.lib.hmb200_prepared_executed_work(self.h, C.byref(c), C.byref(d)))
+        return {"cand_sads": a.value, "abs_diffs": b.value, "abs_diffs_executed": c.value, "pus_fused": d.value}
 
     def free(self):
         if self.h:

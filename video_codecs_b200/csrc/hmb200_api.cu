@@ -542,6 +542,14 @@ int hmb200_prepared_work(const hmb200_prepared* p, uint64_t* cand_sads, uint64_t
   return HMB200_OK;
 }
 
+int hmb200_prepared_executed_work(const hmb200_prepared* p, uint64_t* abs_diffs_executed, uint64_t* pus_fused) {
+  if (!p) return fail(HMB200_ERR_ARG, "null handle");
+  // leftover (generic-kernel) PUs execute exactly their algorithmic work; they are not counted here separately
+  if (abs_diffs_executed) *abs_diffs_executed = p->sched.executed_abs_diffs + p->cu.executed_abs_diffs;
+  if (pus_fused) *pus_fused = p->cu.fused_tasks;
+  return HMB200_OK;
+}
+
 int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
   NEED_READY();
   if (!p) return fail(HMB200_ERR_ARG, "null handle");

@@ -355,6 +355,8 @@ inline int cu_variant(int S, bool fen) { return S == 8 ? CUV_8 : S == 16 ? (fen 
 
 struct CuSchedule {
   int n_units = 0, n_bundles = 0;
+  unsigned long long executed_abs_diffs = 0;     // byte abs-diffs the fused kernels execute (incl. overlapped last blocks)
+  unsigned long long fused_tasks = 0;
   S8Unit* d_units = nullptr;
   S8Bundle* d_bundles = nullptr;
   int unit_first[CUV_COUNT] = {0}, unit_count[CUV_COUNT] = {0}, smem_of[CUV_COUNT] = {0};
@@ -498,6 +500,11 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
       for (int s = 0; s < CU_SLOTS; s++) d.out_idx[s] = b.slot_task[s];
       const int v = cu_variant(b.S, b.fen);
       variant_cost[v] += item_cost(b.S, b.fen) * d.n_items;
+      {
+        const int rows = (b.fen && b.S >= 16) ? (b.S == 16 ? 16 : b.S == 32 ? 24 : 32) : b.S;      // rows visited per candidate
+        out->executed_abs_diffs += (unsigned long long)d.n_blk * 16ull * (unsigned long long)(d.n_rowgroups * cu_ky(b.S)) * rows * b.S;
+        for (int s2 = 0; s2 < CU_SLOTS; s2++) if (b.slot_task[s2] >= 0) out->fused_tasks++;
+      }
       bundles.push_back(d); bvar.push_back(v);
     }
     all_r = s8_union(all_r, g.rb); all_o = s8_union(all_o, g.ob);
