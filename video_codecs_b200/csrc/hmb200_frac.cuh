@@ -181,7 +181,7 @@ __device__ __forceinline__ void frac_tile_diff_u8(const uint8_t* ref, int ref_pi
 // stage 0: half-pel candidates around the integer MV; stage 1: quarter-pel candidates 1..8 around the best half.
 // dist: [n_pu][9] accumulators (zeroed by the host; dist[.][0] of stage 1 is written by k_frac_argmin<0>).
 template <typename RefT, typename OrgT, int N, bool HAD>
-__global__ void __launch_bounds__(FRAC_TILE_THREADS)
+__global__ void __launch_bounds__(FRAC_TILE_THREADS, N == 8 ? 4 : 8)
 k_frac_tiles(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_result* __restrict__ results,
              const uint32_t* __restrict__ tiles, int n_tiles, uint32_t* __restrict__ dist, DevPlane cur_plane, DevPlane ref_plane) {
   const int nc = stage == 0 ? 9 : 8;
