@@ -36,7 +36,30 @@ def parse_md5_lines(stdout):
     return re.findall(r"POC\s+(\d+).*?\[MD5:([0-9a-f,]+)\]", stdout)
 
 
+def golden_1080p():
+    """BASELINE.json configs[2] geometry, short prefix: 1920x1080 (coded 1088 rows, ConformanceWindowMode=1), 2 frames
+    (one I, one P with a single reference): ~6 minutes of CPU for the stock encoder."""
+    W2, H2, frames = 1920, 1080, 2
+    yuv, binf = "/tmp/hmgold_1080.yuv", "/tmp/hmgold_1080.bin"
+    synth.write_yuv420(yuv, [synth.luma_frame(W2, H2, t, seed=77) for t in range(frames)], 8)
+    args = args_1080p(CFG, yuv, frames, binf)
+    t0 = time.time()
+    p = subprocess.run([ENC] + args, capture_output=True, text=True, check=True)
+    out = {"bitstream_md5": hashlib.md5(open(binf, "rb").read()).hexdigest(), "bitstream_bytes": os.path.getsize(binf),
+           "picture_md5": parse_md5_lines(p.stdout), "cpu_seconds": round(time.time() - t0, 1),
+           "yuv_md5": hashlib.md5(open(yuv, "rb").read()).hexdigest()}
+    json.dump(out, open(os.path.join(ROOT, "tests", "golden", "encoder_md5_1080p.json"), "w"), indent=1)
+    print(out)
+
+
+def args_1080p(cfg, yuv, frames, out_bin):
+    return ["-c", cfg, "-i", yuv, "-wdt", "1920", "-hgt", "1080", "-fr", "30", "-f", str(frames), "--FastSearch=0",
+            "--SearchRange=64", "--SEIDecodedPictureHash=1", "--ConformanceWindowMode=1", "-b", out_bin, "-o", ""]
+
+
 def main():
+    if "--1080p" in sys.argv:
+        return golden_1080p()
     out = {}
     for frames in (3, 8):
         yuv, binf = f"/tmp/hmgold_{frames}.yuv", f"/tmp/hmgold_{frames}.bin"

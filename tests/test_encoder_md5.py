@@ -44,3 +44,19 @@ def test_encoder_bitstream_md5_matches_reference(tmp_path, frames, mode):
     assert "integer searches" in p.stderr and " 0 integer searches" not in p.stderr, "the GPU path was not exercised"
     assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
     assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]
+
+
+@pytest.mark.gpu
+def test_encoder_bitstream_md5_1080p_prefix(tmp_path):
+    """Same check at BASELINE.json configs[2]'s geometry: 1920x1080 (ConformanceWindowMode=1 -> 1088 coded rows), I + P."""
+    _need_binary()
+    from video_codecs_b200 import synth
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "encoder_md5_1080p.json")))
+    yuv, binf = str(tmp_path / "clip.yuv"), str(tmp_path / "out.bin")
+    synth.write_yuv420(yuv, [synth.luma_frame(1920, 1080, t, seed=77) for t in range(2)], 8)
+    assert hashlib.md5(open(yuv, "rb").read()).hexdigest() == gold["yuv_md5"]
+    p = subprocess.run([BIN] + meg.args_1080p(CFG, yuv, 2, binf), capture_output=True, text=True,
+                       env=dict(os.environ, HMB200_SHIM="gpu"), timeout=3000)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
+    assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]
