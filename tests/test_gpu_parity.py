@@ -326,3 +326,35 @@ def test_search_range_128_vs_oracle(hm):
         hm.release_plane(idr)
     exp, _ = Oracle(fen=1, hadme=1).run_jobs((cur, o0, stride), (ref, o0, stride), jobs, 8, True)
     assert results_equal(got, exp) == []
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 10-bit content: CU-fused 16-bit kernels (packed 16x2 arithmetic, distortion precision shift)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fen,sr", [(1, 64), (0, 64), (1, 128)])
+def test_me_canonical_ctus_10bit_vs_oracle(hm, fen, sr):
+    """Whole CTUs of a 10-bit pair (interior, corner, last partial row); +-128 exercises row-split windows."""
+    W, H = (416, 240) if sr == 64 else (320, 256)
+    f0 = synth.luma_frame(W, H, 0, seed=41, bit_depth=10)
+    f1 = synth.luma_frame(W, H, 1, seed=41, bit_depth=10)
+    margin = 80 if sr == 64 else 144
+    cur, o0, stride = padded(f1, margin)
+    ref, _, _ = padded(f0, margin)
+    lam = int(np.floor(65536.0 * np.sqrt(0.4624 * 2 ** ((35 - 12) / 3.0))))
+    ctus = (0, 9, 27) if sr == 64 else (6,)
+    jobs = np.concatenate([hm.build_canonical_jobs(W, H, sr, lam, pred=(3, -2), ctu_first=c, ctu_count=1) for c in ctus])
+    jobs = jobs[::4] if sr == 64 else jobs[::2]
+    idc = hm.register_plane(cur, W, H, margin, margin, 10, kind=0)
+    idr = hm.register_plane(ref, W, H, margin, margin, 10, kind=1)
+    try:
+        prep = hm.prepare_jobs(jobs, flags_of(fen, 1), 10)
+        prep.run(idc, idr)
+        got = prep.fetch()
+        work = prep.work()
+        prep.free()
+    finally:
+        hm.release_plane(idc)
+        hm.release_plane(idr)
+    assert work["pus_fused"] > 0.3 * len(jobs)          # the fused 16-bit kernels did run
+    exp, _ = Oracle(fen=fen, hadme=1).run_jobs((cur, o0, stride), (ref, o0, stride), jobs, 10, True)
+    assert results_equal(got, exp) == []

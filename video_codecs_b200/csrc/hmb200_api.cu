@@ -13,6 +13,7 @@
 #include "hmb200_generic.cuh"
 #include "hmb200_search8.cuh"
 #include "hmb200_search8_cu.cuh"
+#include "hmb200_search16_cu.cuh"
 #include "hmb200_frac.cuh"
 
 using namespace hmb200;
@@ -188,6 +189,7 @@ int hmb200_init(int device) {
   int rc = search8_configure(&g_err);
   if (rc != HMB200_OK) return rc;
   if ((rc = cu_configure(&g_err)) != HMB200_OK) return rc;
+  if ((rc = cu16_configure(&g_err)) != HMB200_OK) return rc;
   g.device = device;
   g.ready = true;
   // pattern buffer for the 1:1 entries: 64x64 int16, no margins
@@ -508,12 +510,14 @@ hmb200_prepared* hmb200_prepare_jobs(const hmb200_pu_job* jobs, int njobs, int f
       hmb200_free_prepared(p); return nullptr;
     }
     std::string why;
-    if (bit_depth == 8) {
+    if (bit_depth >= 8 && bit_depth <= 14) {
+      // 8-bit: per-PU tiles + CU-fused bundles; 9..14-bit: CU-fused bundles (packed 16x2 arithmetic), the rest generic
+      const int bps = bit_depth > 8 ? 2 : 1;
       std::vector<char> bundled;
       std::vector<CuBundleHost> hb;
-      if (!getenv("HMB200_NO_CU_FUSION")) cu_extract_bundles(p->tasks, bundled, hb);
-      if (!search8_build_schedule(p->tasks, bundled, g.sm_count, g.stream, &p->sched, &why) ||
-          !cu_build_schedule(p->tasks, hb, g.sm_count, g.stream, &p->cu, &why)) {
+      if (!getenv("HMB200_NO_CU_FUSION")) cu_extract_bundles(p->tasks, bps, bundled, hb);
+      if (!search8_build_schedule(p->tasks, bundled, g.sm_count, g.stream, &p->sched, &why, /*tiled=*/bps == 1) ||
+          !cu_build_schedule(p->tasks, hb, bps, bit_depth, g.sm_count, g.stream, &p->cu, &why)) {
         fail(HMB200_ERR_CUDA, why); hmb200_free_prepared(p); return nullptr;
       }
     }
@@ -560,8 +564,9 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
   CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
   const Search8Schedule& sc = p->sched;
   const CuSchedule& cu = p->cu;
-  bool fast = pc->d.bytes_per_sample == 1 && pr->d.bytes_per_sample == 1 && (sc.n_jobs > 0 || cu.n_bundles > 0) &&
-              pc->d.margin_x % 16 == 0 && pr->d.margin_x % 16 == 0 && sc.d_keys != nullptr;
+  const int bps = pr->d.bytes_per_sample;
+  bool fast = pc->d.bytes_per_sample == bps && ((bps == 1 && (sc.n_jobs > 0 || cu.n_bundles > 0)) || (bps == 2 && cu.n_bundles > 0)) &&
+              cu.bps == bps && pc->d.margin_x % 16 == 0 && pr->d.margin_x % 16 == 0 && sc.d_keys != nullptr;
   if (fast) {
     // every staged byte must lie inside the padded buffers (the reference would read outside its planes too)
     auto inside = [](const DevPlane& d, int x0, int y0, int x1, int y1) {
@@ -576,7 +581,7 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
     CUDA_TRY(cudaMemsetAsync(sc.d_keys, 0xff, (size_t)sc.n_tasks * sizeof(unsigned long long), g.stream));
     // one launch per tile variant present, spread over side streams so that their tails overlap
     const S8Kernel* kern = search8_kernels();
-    const S8CuKernel* cukern = search8_cu_kernels();
+    const S8CuKernel* cukern = bps == 1 ? search8_cu_kernels() : search16_cu_kernels();
     CUDA_TRY(cudaEventRecord(g.ev_fork, g.stream));
     int order[S8V_COUNT + CUV_COUNT], used = 0;       // >= 0: per-PU variant, < 0: CU-fused variant ~v
     for (int v = CUV_COUNT - 1; v >= 0; v--) if (cu.unit_count[v] > 0) order[used++] = ~v;    // big CUs first
@@ -595,8 +600,9 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
       CUDA_TRY(cudaEventRecord(g.ev_join[k], g.side[k]));
       CUDA_TRY(cudaStreamWaitEvent(g.stream, g.ev_join[k], 0));
     }
-    if (sc.n_leftover > 0) {    // shapes / windows the tiled kernel does not cover
-      k_search_generic<uint8_t, uint8_t><<<sc.n_leftover, 256, 0, g.stream>>>(p->d_tasks, p->d_results, pc->d, pr->d, sc.d_leftover);
+    if (sc.n_leftover > 0) {    // shapes / windows the tiled kernels do not cover
+      if (bps == 1) k_search_generic<uint8_t, uint8_t><<<sc.n_leftover, 256, 0, g.stream>>>(p->d_tasks, p->d_results, pc->d, pr->d, sc.d_leftover);
+      else          k_search_generic<int16_t, int16_t><<<sc.n_leftover, 256, 0, g.stream>>>(p->d_tasks, p->d_results, pc->d, pr->d, sc.d_leftover);
       g.launches++;
     }
     k_search8_finalize<<<(sc.n_tasks + 255) / 256, 256, 0, g.stream>>>(p->d_tasks, sc.d_keys, p->d_results, sc.n_tasks);

@@ -1,0 +1,298 @@
+// CU-fused integer full search for 16-bit planes (bit depths 9..14): the hmb200_search8_cu.cuh scheme with packed
+// 16x2 arithmetic.  There is no 16-bit SIMD SAD instruction on sm_100a; per 32-bit word (two samples) and candidate:
+//     t = o + (-r)                VIADD.16x2          (o - r)
+//     m = max(r + (-o), t)        VIADDMNMX.S16x2     (|r - o| per half-word)
+//     acc += m.lo + m.hi          IDP.2A.LO.S16.S8    (32-bit accumulator, taps 1,1)
+// with the half-word negations of the original words (once per row) and of the byte-shifted reference words (once per
+// word, shared by the lane's four candidates) hoisted.  ~1.6 instructions per sample against 0.25 for 8-bit content.
+// Distortion precision: (sum << iSubShift) >> (bitDepth - 8)  (TComRdCost.cpp:505-517, DISTORTION_PRECISION_ADJUSTMENT).
+// Lane layout: a PAIR of lanes owns 8 candidate columns (lane parity = sample alignment inside the word, four candidates
+// two samples apart per lane), 16 pairs per warp-item.
+#pragma once
+#include "hmb200_search8_cu.cuh"
+
+namespace hmb200 {
+
+__host__ __device__ constexpr int cu16_ky(int S) { return S == 8 ? 2 : 1; }
+
+__device__ __forceinline__ uint32_t absdiff16x2_acc(uint32_t r, uint32_t nr, uint32_t o, uint32_t no, uint32_t acc) {
+  const uint32_t t = __vadd2(o, nr);
+  const uint32_t m = __viaddmax_s16x2(r, no, t);
+  return (uint32_t)__dp2a_lo((int)m, 0x0101, (int)acc);
+}
+
+// one reference row against WW original words (a chunk of the CU row); words of cell column c feed acc[c][k]
+template <int WW, int NC>
+__device__ __forceinline__ void cu16_row(const uint8_t* rp8, const uint32_t (&o)[WW], const uint32_t (&no)[WW], uint32_t sh,
+                                         uint32_t (*acc)[4]) {
+  const uint32_t* rp = reinterpret_cast<const uint32_t*>(rp8);
+  uint32_t lo = rp[0];
+#pragma unroll
+  for (int j = 0; j < WW + 3; j++) {
+    const uint32_t hi = rp[j + 1];
+    const uint32_t sw = __funnelshift_r(lo, hi, sh);
+    lo = hi;
+    const uint32_t nsw = __vneg2(sw);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int i = j - k;
+      if (i >= 0 && i < WW) acc[i / (WW / NC)][k] = absdiff16x2_acc(sw, nsw, o[i], no[i], acc[i / (WW / NC)][k]);
+    }
+  }
+}
+
+template <int WW>
+__device__ __forceinline__ void cu16_load_org(const uint8_t* p, uint32_t (&o)[WW], uint32_t (&no)[WW]) {
+#pragma unroll
+  for (int i = 0; i < WW / 4; i++) {
+    const uint4 v = reinterpret_cast<const uint4*>(p)[i];
+    o[4 * i] = v.x; o[4 * i + 1] = v.y; o[4 * i + 2] = v.z; o[4 * i + 3] = v.w;
+  }
+#pragma unroll
+  for (int i = 0; i < WW; i++) no[i] = __vneg2(o[i]);
+}
+
+// key of one PU: ((sum << ss) >> shr) scaled into the cost field
+__device__ __forceinline__ void cu16_min(uint32_t& best, uint32_t sum, int ss, int shr, uint32_t base) {
+  best = min(best, (((sum << ss) >> shr) << CU_LOCAL_BITS) + base);
+}
+
+template <int S, bool FEN>
+__device__ __forceinline__ void cu16_epilogue(const uint32_t (&E)[4][4][4], const uint32_t (&O)[4][4], int k, int shr, uint32_t base,
+                                              uint32_t (&best)[CU_SLOTS]) {
+  uint32_t er[4], ec[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) er[r] = E[r][0][k] + E[r][1][k] + E[r][2][k] + E[r][3][k];
+#pragma unroll
+  for (int c = 0; c < 4; c++) ec[c] = E[0][c][k] + E[1][c][k] + E[2][c][k] + E[3][c][k];
+  constexpr bool f1 = FEN && cu_slot_h(S, 1) <= 8;
+  constexpr bool f5 = FEN && cu_slot_h(S, 5) <= 8;
+  constexpr int ss = FEN ? 1 : 0;
+  const uint32_t top = er[0] + er[1], bot = er[2] + er[3];
+  cu16_min(best[0], top + bot, ss, shr, base);
+  if (f1) { cu16_min(best[1], top + O[0][k] + O[1][k], 0, shr, base); cu16_min(best[2], bot + O[2][k] + O[3][k], 0, shr, base); }
+  else    { cu16_min(best[1], top, ss, shr, base);                    cu16_min(best[2], bot, ss, shr, base); }
+  cu16_min(best[3], ec[0] + ec[1], ss, shr, base);
+  cu16_min(best[4], ec[2] + ec[3], ss, shr, base);
+  if (f5) { cu16_min(best[5], er[0] + O[0][k], 0, shr, base); cu16_min(best[8], er[3] + O[3][k], 0, shr, base); }
+  else    { cu16_min(best[5], er[0], ss, shr, base);          cu16_min(best[8], er[3], ss, shr, base); }
+  cu16_min(best[6], er[1] + bot, ss, shr, base);
+  cu16_min(best[7], top + er[2], ss, shr, base);
+  cu16_min(best[9], ec[0], ss, shr, base);
+  cu16_min(best[10], ec[1] + ec[2] + ec[3], ss, shr, base);
+  cu16_min(best[11], ec[0] + ec[1] + ec[2], ss, shr, base);
+  cu16_min(best[12], ec[3], ss, shr, base);
+}
+
+template <int S, bool FEN>
+__global__ void __launch_bounds__(S8_THREADS, 2)
+k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bundles, unsigned long long* __restrict__ keys,
+              DevPlane cur_plane, DevPlane ref_plane) {
+  constexpr int NSLOT = (S == 8) ? 5 : CU_SLOTS;
+  constexpr int KY = cu16_ky(S);
+  constexpr int WW = S / 2;                            // 32-bit words per CU row
+  constexpr int G = S / 4;                             // rows per strip (S >= 16)
+  constexpr int CH = WW > 16 ? 16 : WW;                // words per row chunk (keeps the original row in <= 32 registers)
+  constexpr bool PARITY = FEN && S >= 16, ODD_ALL = PARITY && S == 16, ODD_EDGE = PARITY && S == 32;
+  extern __shared__ __align__(128) uint8_t s8_smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ S8Bundle s_bd[S8_WARPS];
+
+  const S8Unit un = units[blockIdx.x];
+  uint8_t* s_ref = s8_smem;
+  uint8_t* s_org = s8_smem + un.org_smem_off;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) mbar_expect_tx(&s_bar, (uint32_t)(un.ref_pitch * un.ref_rows + un.org_pitch * un.org_rows));
+    __syncwarp();
+    const uint8_t* gref = reinterpret_cast<const uint8_t*>(ref_plane.base) +
+                          ((size_t)(un.ref_by + ref_plane.margin_y) * ref_plane.pitch + (un.ref_bx + ref_plane.margin_x)) * 2;
+    for (int r = lane; r < un.ref_rows; r += 32)
+      bulk_g2s(s_ref + r * un.ref_pitch, gref + (size_t)r * ref_plane.pitch * 2, (uint32_t)un.ref_pitch, &s_bar);
+    const uint8_t* gorg = reinterpret_cast<const uint8_t*>(cur_plane.base) +
+                          ((size_t)(un.org_by + cur_plane.margin_y) * cur_plane.pitch + (un.org_bx + cur_plane.margin_x)) * 2;
+    for (int r = lane; r < un.org_rows; r += 32)
+      bulk_g2s(s_org + r * un.org_pitch, gorg + (size_t)r * cur_plane.pitch * 2, (uint32_t)un.org_pitch, &s_bar);
+  }
+  mbar_wait(&s_bar, 0);
+
+  int bslot = un.job_first;
+  S8Bundle& bd = s_bd[warp];
+  auto load_bundle = [&]() {
+    __syncwarp();
+    reinterpret_cast<int32_t*>(&bd)[lane] = reinterpret_cast<const int32_t*>(&bundles[bslot])[lane];
+    __syncwarp();
+  };
+  load_bundle();
+  constexpr int LK = (S == 8) ? 4 : 2;
+  uint32_t best[CU_SLOTS];
+#pragma unroll
+  for (int s = 0; s < CU_SLOTS; s++) best[s] = 0xffffffffu;
+  int first_item = un.item_first + warp;
+  auto flush = [&]() {
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) {
+      unsigned long long b = ~0ull;
+      if (best[s] != 0xffffffffu) {
+        const uint32_t local = best[s] & ((1u << CU_LOCAL_BITS) - 1u);
+        const int it = first_item + (int)(local >> LK) * S8_WARPS;
+        const int q = (it - bd.item_start) * 16 + (lane >> 1);
+        const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
+        const int w = (int)(local & ((1u << LK) - 1u));
+        const int cyi = bd.cy_first + g * KY + (w >> 2), cxi = min(blk * 8, bd.nx - 8) + (lane & 1) + 2 * (w & 3);
+        b = make_key(best[s] >> CU_LOCAL_BITS, (uint32_t)(cyi * bd.nx + cxi));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
+        b = other < b ? other : b;
+      }
+      if (lane == 0 && b != ~0ull && bd.out_idx[s] >= 0) atomicMin(&keys[bd.out_idx[s]], b);
+      best[s] = 0xffffffffu;
+    }
+  };
+
+  for (int item = un.item_first + warp; item < un.item_last; item += S8_WARPS) {
+    if (item >= bd.item_start + bd.n_items) {
+      flush();
+      do { bslot++; } while (item >= bundles[bslot].item_start + bundles[bslot].n_items);
+      load_bundle();
+      first_item = item;
+    }
+    const uint32_t tile_local = (uint32_t)((item - first_item) / S8_WARPS) << LK;
+    const int q = (item - bd.item_start) * 16 + (lane >> 1);
+    if (q < bd.n_blk * bd.n_rowgroups) {
+      const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
+      const int cyl0 = g * KY;                                            // candidate row inside this (row-split) bundle
+      const int cxi0 = min(blk * 8, bd.nx - 8) + (lane & 1);              // the last block overlaps its neighbour
+      const int off = bd.win_off + cyl0 * un.ref_pitch + cxi0 * 2;        // bytes
+      const uint8_t* refp = s_ref + (off & ~3);
+      const uint32_t sh = (uint32_t)(off & 3) * 8u;
+      const uint8_t* orgp = s_org + bd.org_off;
+      const int shr = bd.shr;
+      uint32_t px[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) px[k] = bd.lambda * eg_bits(((bd.lt_x + cxi0 + 2 * k) << 2) - bd.pred_x);
+
+      if constexpr (S == 8) {
+        uint32_t o[8][4], no[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; r++) cu16_load_org<4>(orgp + r * un.org_pitch, o[r], no[r]);
+        uint32_t Q[KY][2][2][4];
+#pragma unroll
+        for (int a = 0; a < KY; a++)
+#pragma unroll
+          for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+              for (int k = 0; k < 4; k++) Q[a][b][c][k] = 0;
+#pragma unroll
+        for (int r = 0; r < 8 + KY - 1; r++) {
+          const uint32_t* rp = reinterpret_cast<const uint32_t*>(refp + r * un.ref_pitch);
+          uint32_t lo = rp[0];
+#pragma unroll
+          for (int j = 0; j < 4 + 3; j++) {
+            const uint32_t hi = rp[j + 1];
+            const uint32_t sw = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+            const uint32_t nsw = __vneg2(sw);
+#pragma unroll
+            for (int jy = 0; jy < KY; jy++) {
+              if (r - jy >= 0 && r - jy < 8) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  const int i = j - k;
+                  if (i >= 0 && i < 4)
+                    Q[jy][(r - jy) >> 2][i >> 1][k] = absdiff16x2_acc(sw, nsw, o[r - jy][i], no[r - jy][i], Q[jy][(r - jy) >> 2][i >> 1][k]);
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int jy = 0; jy < KY; jy++) {
+          const int cyi = bd.cy_first + cyl0 + jy;
+          if (cyl0 + jy < bd.ny) {
+            const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + cyi) << 2) - bd.pred_y);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const uint32_t base = (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)(jy * 4 + k);
+              const uint32_t t = Q[jy][0][0][k] + Q[jy][0][1][k], b = Q[jy][1][0][k] + Q[jy][1][1][k];
+              const uint32_t l = Q[jy][0][0][k] + Q[jy][1][0][k], r = Q[jy][0][1][k] + Q[jy][1][1][k];
+              cu16_min(best[0], t + b, 0, shr, base);
+              cu16_min(best[1], t, 0, shr, base);
+              cu16_min(best[2], b, 0, shr, base);
+              cu16_min(best[3], l, 0, shr, base);
+              cu16_min(best[4], r, 0, shr, base);
+            }
+          }
+        }
+      } else {
+        uint32_t E[4][4][4], O[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            O[a][k] = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) E[a][c][k] = 0;
+          }
+        constexpr int NCH = WW / CH;                // chunks per row
+        constexpr int CPC = 4 / NCH;                // cell columns per chunk
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const bool odd_here = ODD_ALL || (ODD_EDGE && (r == 0 || r == 3));
+          constexpr int RSTEP = PARITY ? 2 : 1;
+#pragma unroll 1
+          for (int rr = 0; rr < G; rr += RSTEP) {
+            const int row = r * G + rr;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
+              uint32_t o[CH], no[CH];
+              cu16_load_org<CH>(orgp + row * un.org_pitch + ch * CH * 4, o, no);
+              cu16_row<CH, CPC>(refp + row * un.ref_pitch + ch * CH * 4, o, no, sh, &E[r][ch * CPC]);
+            }
+            if (PARITY && odd_here) {
+#pragma unroll
+              for (int ch = 0; ch < NCH; ch++) {
+                uint32_t o[CH], no[CH];
+                cu16_load_org<CH>(orgp + (row + 1) * un.org_pitch + ch * CH * 4, o, no);
+                cu16_row<CH, 1>(refp + (row + 1) * un.ref_pitch + ch * CH * 4, o, no, sh, &O[r]);
+              }
+            }
+          }
+        }
+        if (cyl0 < bd.ny) {
+          const int cyi = bd.cy_first + cyl0;
+          const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + cyi) << 2) - bd.pred_y);
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            cu16_epilogue<S, FEN>(E, O, k, shr, (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)k, best);
+        }
+      }
+    }
+  }
+  flush();
+}
+
+typedef void (*S16CuKernel)(const S8Unit*, const S8Bundle*, unsigned long long*, DevPlane, DevPlane);
+inline const S16CuKernel* search16_cu_kernels() {
+  static const S16CuKernel table[CUV_COUNT] = { k_search16_cu<8, false>, k_search16_cu<16, false>, k_search16_cu<16, true>,
+                                                k_search16_cu<32, false>, k_search16_cu<32, true>, k_search16_cu<64, false>,
+                                                k_search16_cu<64, true> };
+  return table;
+}
+inline int cu16_configure(std::string* err) {
+  const S16CuKernel* k = search16_cu_kernels();
+  for (int v = 0; v < CUV_COUNT; v++) {
+    cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k[v]), cudaFuncAttributeMaxDynamicSharedMemorySize, S8_SMEM_MAX);
+    if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(k_search16_cu): ") + cudaGetErrorString(e); return HMB200_ERR_CUDA; }
+  }
+  return HMB200_OK;
+}
+
+}  // namespace hmb200

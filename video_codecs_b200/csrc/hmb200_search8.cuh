@@ -461,9 +461,9 @@ inline S8Box s8_union(const S8Box& a, const S8Box& b) { return S8Box{std::min(a.
 inline int s8_fl(int x) { return s8_floor16(x + 4096) - 4096; }      // 16-aligned in picture coordinates
 inline int s8_ce(int x) { return s8_ceil16(x + 4096) - 4096; }
 // dynamic shared memory of a group: window rows (+ slack) then the original tile, 128-byte aligned
-inline int s8_smem_need(const S8Box& rb, const S8Box& ob, int* org_off) {
-  const int rp = s8_ce(rb.x1) - s8_fl(rb.x0), rr = rb.y1 - rb.y0 + S8_SLACK_ROWS;
-  const int op = s8_ce(ob.x1) - s8_fl(ob.x0), orr = ob.y1 - ob.y0;
+inline int s8_smem_need(const S8Box& rb, const S8Box& ob, int* org_off, int bps = 1) {
+  const int rp = (s8_ce(rb.x1) - s8_fl(rb.x0)) * bps, rr = rb.y1 - rb.y0 + S8_SLACK_ROWS;
+  const int op = (s8_ce(ob.x1) - s8_fl(ob.x0)) * bps, orr = ob.y1 - ob.y0;
   const int ro = ((rp * rr + 16) + 127) & ~127;
   if (org_off) *org_off = ro;
   return ro + op * orr + 16;
@@ -471,8 +471,9 @@ inline int s8_smem_need(const S8Box& rb, const S8Box& ob, int* org_off) {
 
 // Window origins are multiples of 16 in picture coordinates: 16-byte aligned in the buffer when margin_x % 16 == 0.
 // skip[i] != 0: task i is searched elsewhere (CU-fused kernel) and gets neither a job nor a leftover entry.
+// tiled == false: no per-PU tiles at all (16-bit planes): every task that is not skipped becomes a leftover.
 inline bool search8_build_schedule(const std::vector<SearchTask>& tasks, const std::vector<char>& skip, int sm_count, cudaStream_t stream,
-                                   Search8Schedule* out, std::string* err) {
+                                   Search8Schedule* out, std::string* err, bool tiled = true) {
   typedef S8Box Box;
   auto uni = [](const Box& a, const Box& b) { return s8_union(a, b); };
   auto fl = [](int x) { return s8_fl(x); };
@@ -489,7 +490,7 @@ inline bool search8_build_schedule(const std::vector<SearchTask>& tasks, const s
     obox[i] = Box{t.org_x, t.org_y, t.org_x + t.w, t.org_y + t.h};
     const bool shape_ok = (t.w % 4 == 0) && t.w >= 4 && t.w <= 64 && t.h >= 1 && t.h <= 64 && (t.sub_shift == 0 || t.h % 2 == 0) &&
                           (t.w == 4 || t.w == 8 || t.w == 12 || t.w == 16 || t.w == 24 || t.w == 32 || t.w == 48 || t.w == 64);
-    if (shape_ok && nx >= 1 && ny >= 1 && smem_need(rbox[i], obox[i], nullptr) <= S8_SMEM_MAX) elig.push_back(i);
+    if (tiled && shape_ok && nx >= 1 && ny >= 1 && smem_need(rbox[i], obox[i], nullptr) <= S8_SMEM_MAX) elig.push_back(i);
     else left.push_back(i);
   }
   // group: stable sort by CTU, then greedy extension while the staged regions still let two CTAs share an SM

@@ -33,7 +33,9 @@ struct S8Bundle {             // 128 bytes
   int32_t item_start, n_items;
   int32_t out_idx[CU_SLOTS];  // task index per partition slot (-1: that PU is not in the job list)
   int32_t n_rowgroups;        // ceil(ny / KY)
-  int32_t pad[6];
+  int32_t cy_first;           // first candidate row of this bundle in the PU's window (tall windows are split by rows)
+  int32_t shr;                // bitDepth - 8 (distortion precision adjustment); 0 for 8-bit planes
+  int32_t pad[4];
 };
 
 // partition slots: 0 2Nx2N | 1,2 2NxN top,bottom | 3,4 Nx2N left,right | 5,6 2NxnU | 7,8 2NxnD | 9,10 nLx2N | 11,12 nRx2N
@@ -203,7 +205,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
         const int q = (it - bd.item_start) * 8 + (lane >> 2);
         const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
         const int w = (int)(local & ((1u << LK) - 1u));
-        const int cyi = g * T::KY + (w >> 2), cxi = min(blk * 16, bd.nx - 16) + (lane & 3) + 4 * (w & 3);
+        const int cyi = bd.cy_first + g * T::KY + (w >> 2), cxi = min(blk * 16, bd.nx - 16) + (lane & 3) + 4 * (w & 3);
         b = make_key(best[s] >> CU_LOCAL_BITS, (uint32_t)(cyi * bd.nx + cxi));
       }
 #pragma unroll
@@ -275,8 +277,8 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
       }
 #pragma unroll
       for (int jy = 0; jy < T::KY; jy++) {
-        const int cyi = cyi0 + jy;
-        if (cyi < bd.ny) {
+        const int cyi = bd.cy_first + cyi0 + jy;
+        if (cyi0 + jy < bd.ny) {
           const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + cyi) << 2) - bd.pred_y);
 #pragma unroll
           for (int k = 0; k < 4; k++) {
@@ -329,7 +331,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
         }
       }
       if (cyi0 < bd.ny) {
-        const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + cyi0) << 2) - bd.pred_y);
+        const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + bd.cy_first + cyi0) << 2) - bd.pred_y);
 #pragma unroll
         for (int k = 0; k < 4; k++)
           cu_epilogue16<S, FEN>(E, O, k, (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)k, best);
@@ -357,6 +359,7 @@ struct CuSchedule {
   int n_units = 0, n_bundles = 0;
   unsigned long long executed_abs_diffs = 0;     // byte abs-diffs the fused kernels execute (incl. overlapped last blocks)
   unsigned long long fused_tasks = 0;
+  int bps = 1;                                   // bytes per sample of the planes this schedule was built for
   S8Unit* d_units = nullptr;
   S8Bundle* d_bundles = nullptr;
   int unit_first[CUV_COUNT] = {0}, unit_count[CUV_COUNT] = {0}, smem_of[CUV_COUNT] = {0};
@@ -378,32 +381,45 @@ inline int cu_configure(std::string* err) {
   return HMB200_OK;
 }
 
-// Finds CU bundles among `elig` (indices into tasks): PUs that are partitions of the same aligned S x S CU and share
-// window, predictor and lambda.  taken[i] = 1 for every bundled task (the per-PU schedule skips those).
+// geometry of the lane layout per sample size: 8-bit: quads of lanes own 16 columns, 8 quads per warp-item;
+// 16-bit: pairs of lanes own 8 columns, 16 pairs per warp-item (hmb200_search16_cu.cuh)
+struct CuGeom {
+  int bps, blkw, groups;
+  int ky(int S) const { return bps == 1 ? cu_ky(S) : (S == 8 ? 2 : 1); }
+  int lk(int S) const { return S == 8 ? 4 : 2; }
+};
+inline CuGeom cu_geom(int bps) { return bps == 1 ? CuGeom{1, 16, 8} : CuGeom{2, 8, 16}; }
+
+// Finds CU bundles: PUs that are partitions of the same aligned S x S CU and share window, predictor and lambda.
+// taken[i] = 1 for every bundled task (the per-PU schedule skips those).
 struct CuBundleHost { int S; bool fen; int cu_x, cu_y; int slot_task[CU_SLOTS]; int first_task; };
-inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, std::vector<char>& taken, std::vector<CuBundleHost>& out) {
+inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, int bps, std::vector<char>& taken, std::vector<CuBundleHost>& out) {
+  const CuGeom G = cu_geom(bps);
   struct Key {
-    int v[11];
-    bool operator<(const Key& o) const { for (int i = 0; i < 11; i++) if (v[i] != o.v[i]) return v[i] < o.v[i]; return false; }
+    int v[10];
+    bool operator<(const Key& o) const { for (int i = 0; i < 10; i++) if (v[i] != o.v[i]) return v[i] < o.v[i]; return false; }
   };
   std::map<Key, CuBundleHost> found;
   for (int i = 0; i < (int)tasks.size(); i++) {
     const SearchTask& t = tasks[i];
     const int S = std::max(t.w, t.h);
     if (!(S == 8 || S == 16 || S == 32 || S == 64) || t.ref_x != t.org_x || t.ref_y != t.org_y || t.org_x < 0 || t.org_y < 0) continue;
-    if (t.rb_x - t.lt_x + 1 < 16 || t.rb_y < t.lt_y) continue;
-    {   // the per-lane local candidate index must fit CU_LOCAL_BITS (see cu_min)
-      const int n_blk = (t.rb_x - t.lt_x + 1 + 15) / 16, nrg = (t.rb_y - t.lt_y + cu_ky(S)) / cu_ky(S);
-      const int n_items = (n_blk * nrg + 7) / 8;
-      if (n_items / S8_WARPS + 2 >= (1 << (CU_LOCAL_BITS - (S == 8 ? 4 : 2)))) continue;
-    }
+    const int nx = t.rb_x - t.lt_x + 1, ny = t.rb_y - t.lt_y + 1;
+    if (nx < G.blkw || ny < 1) continue;
     const int cx = t.org_x - t.org_x % S, cy = t.org_y - t.org_y % S;
-    if (s8_smem_need(S8Box{cx + t.lt_x, cy + t.lt_y, cx + t.rb_x + S, cy + t.rb_y + S}, S8Box{cx, cy, cx + S, cy + S}, nullptr) > S8_SMEM_MAX) continue;
+    // even a one-row-group slice of the window must fit in shared memory, and the per-lane local candidate index of
+    // a slice that fills it must fit CU_LOCAL_BITS (see cu_min)
+    if (s8_smem_need(S8Box{cx + t.lt_x, cy + t.lt_y, cx + t.rb_x + S, cy + t.lt_y + G.ky(S) - 1 + S}, S8Box{cx, cy, cx + S, cy + S}, nullptr, bps) > S8_SMEM_MAX) continue;
+    {
+      const int n_blk = (nx + G.blkw - 1) / G.blkw, nrg = (ny + G.ky(S) - 1) / G.ky(S);
+      const int n_items = (n_blk * nrg + G.groups - 1) / G.groups;
+      if (n_items / S8_WARPS + 2 >= (1 << (CU_LOCAL_BITS - G.lk(S)))) continue;
+    }
     int slot = -1;
     for (int s = 0; s < (S == 8 ? 5 : CU_SLOTS); s++)
       if (cu_slot_x(S, s) == t.org_x - cx && cu_slot_y(S, s) == t.org_y - cy && cu_slot_w(S, s) == t.w && cu_slot_h(S, s) == t.h) { slot = s; break; }
     if (slot < 0) continue;
-    Key k = {{cx, cy, S, t.lt_x, t.lt_y, t.rb_x, t.rb_y, t.pred_x, t.pred_y, (int)t.lambda_cost, 0}};
+    Key k = {{cx, cy, S, t.lt_x, t.lt_y, t.rb_x, t.rb_y, t.pred_x, t.pred_y, (int)t.lambda_cost}};
     auto it = found.find(k);
     if (it == found.end()) {
       CuBundleHost b; b.S = S; b.fen = false; b.cu_x = cx; b.cu_y = cy; b.first_task = i;
@@ -432,19 +448,33 @@ inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, std::vector
   std::sort(out.begin(), out.end(), [](const CuBundleHost& a, const CuBundleHost& b) { return a.first_task < b.first_task; });
 }
 
-inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::vector<CuBundleHost>& hb, int sm_count,
-                              cudaStream_t stream, CuSchedule* out, std::string* err) {
+inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::vector<CuBundleHost>& hb, int bps, int bit_depth,
+                              int sm_count, cudaStream_t stream, CuSchedule* out, std::string* err) {
   if (hb.empty()) return true;
-  struct Ent { int b; S8Box rb, ob; };
-  std::vector<Ent> ents(hb.size());
+  const CuGeom GM = cu_geom(bps);
+  out->bps = bps;
+  // entity = a bundle, or a horizontal slice of its window when the whole window does not let two CTAs share an SM
+  struct Ent { int b, cy_first, ny; S8Box rb, ob; };
+  std::vector<Ent> ents;
+  auto any_task = [&](const CuBundleHost& b) -> const SearchTask& {
+    for (int s = 0; s < CU_SLOTS; s++) if (b.slot_task[s] >= 0) return tasks[b.slot_task[s]];
+    return tasks[0];
+  };
   for (size_t i = 0; i < hb.size(); i++) {
     const CuBundleHost& b = hb[i];
-    int any = -1;
-    for (int s = 0; s < CU_SLOTS; s++) if (b.slot_task[s] >= 0) { any = b.slot_task[s]; break; }
-    const SearchTask& t = tasks[any];
-    ents[i].b = (int)i;
-    ents[i].ob = S8Box{b.cu_x, b.cu_y, b.cu_x + b.S, b.cu_y + b.S};
-    ents[i].rb = S8Box{b.cu_x + t.lt_x, b.cu_y + t.lt_y, b.cu_x + t.rb_x + b.S, b.cu_y + t.rb_y + b.S};
+    const SearchTask& t = any_task(b);
+    const int ny = t.rb_y - t.lt_y + 1, ky = GM.ky(b.S);
+    const S8Box ob{b.cu_x, b.cu_y, b.cu_x + b.S, b.cu_y + b.S};
+    auto rbox_of = [&](int r0, int n) { return S8Box{b.cu_x + t.lt_x, b.cu_y + t.lt_y + r0, b.cu_x + t.rb_x + b.S, b.cu_y + t.lt_y + r0 + n - 1 + b.S}; };
+    int parts = 1, rows = ny;
+    while (s8_smem_need(rbox_of(0, rows), ob, nullptr, bps) > S8_SMEM_SHARED2 && rows > ky) {
+      parts++;
+      rows = (((ny + parts - 1) / parts + ky - 1) / ky) * ky;
+    }
+    for (int r0 = 0; r0 < ny; r0 += rows) {
+      const int n = std::min(rows, ny - r0);
+      ents.push_back(Ent{(int)i, r0, n, rbox_of(r0, n), ob});
+    }
   }
   std::stable_sort(ents.begin(), ents.end(), [&](const Ent& a, const Ent& b) {
     const int ka = a.ob.y0 >> 6, kb = b.ob.y0 >> 6;
@@ -457,69 +487,70 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     if (!groups.empty()) {
       Group& g = groups.back();
       const S8Box nr = s8_union(g.rb, ents[p].rb), no = s8_union(g.ob, ents[p].ob);
-      if (g.count < 4096 && no.x1 - no.x0 <= 128 && no.y1 - no.y0 <= 128 && s8_smem_need(nr, no, nullptr) <= S8_SMEM_SHARED2) {
+      if (g.count < 4096 && no.x1 - no.x0 <= 128 && no.y1 - no.y0 <= 128 && s8_smem_need(nr, no, nullptr, bps) <= S8_SMEM_SHARED2) {
         g.rb = nr; g.ob = no; g.count++;
         continue;
       }
     }
-    if (s8_smem_need(ents[p].rb, ents[p].ob, nullptr) > S8_SMEM_MAX) { if (err) *err = "cu_build_schedule: window too large"; return false; }
+    if (s8_smem_need(ents[p].rb, ents[p].ob, nullptr, bps) > S8_SMEM_MAX) { if (err) *err = "cu_build_schedule: window too large"; return false; }
     groups.push_back(Group{(int)p, 1, ents[p].rb, ents[p].ob});
   }
-  auto item_cost = [](int S, bool fen) -> long long {
-    const int rows = (fen && S >= 16) ? (S == 16 ? 16 : S == 32 ? 24 : 32) : S;
-    return (long long)cu_ky(S) * (rows * (S / 4) + 40);
+  auto rows_visited = [](int S, bool fen) { return (fen && S >= 16) ? (S == 16 ? 16 : S == 32 ? 24 : 32) : S; };
+  auto item_cost = [&](int S, bool fen) -> long long {
+    return (long long)GM.ky(S) * (rows_visited(S, fen) * (S / 4) * (bps == 1 ? 1 : 6) + 40);
   };
-  std::vector<S8Bundle> bundles; bundles.reserve(hb.size());
-  std::vector<int> bvar; bvar.reserve(hb.size());
+  std::vector<S8Bundle> bundles; bundles.reserve(ents.size());
+  std::vector<int> bvar; bvar.reserve(ents.size());
   std::vector<std::pair<int, int> > group_range(groups.size());
   long long variant_cost[CUV_COUNT] = {0};
   S8Box all_r{1 << 30, 1 << 30, -(1 << 30), -(1 << 30)}, all_o = all_r;
   for (size_t gi = 0; gi < groups.size(); gi++) {
     Group& g = groups[gi];
     std::vector<int> ids;
-    for (int k = 0; k < g.count; k++) ids.push_back(ents[g.first + k].b);
-    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return cu_variant(hb[a].S, hb[a].fen) > cu_variant(hb[b].S, hb[b].fen); });
+    for (int k = 0; k < g.count; k++) ids.push_back(g.first + k);
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) {
+      return cu_variant(hb[ents[a].b].S, hb[ents[a].b].fen) > cu_variant(hb[ents[b].b].S, hb[ents[b].b].fen);
+    });
     const int rx0 = s8_fl(g.rb.x0), ox0 = s8_fl(g.ob.x0);
-    const int rpitch = s8_ce(g.rb.x1) - rx0, opitch = s8_ce(g.ob.x1) - ox0;
+    const int rpitch = (s8_ce(g.rb.x1) - rx0) * bps, opitch = (s8_ce(g.ob.x1) - ox0) * bps;      // bytes
     group_range[gi] = std::make_pair((int)bundles.size(), g.count);
     int item = 0;
     for (int id : ids) {
-      const CuBundleHost& b = hb[id];
-      int any = -1;
-      for (int s = 0; s < CU_SLOTS; s++) if (b.slot_task[s] >= 0) { any = b.slot_task[s]; break; }
-      const SearchTask& t = tasks[any];
+      const Ent& e = ents[id];
+      const CuBundleHost& b = hb[e.b];
+      const SearchTask& t = any_task(b);
       S8Bundle d{};
-      d.org_off = (b.cu_y - g.ob.y0) * opitch + (b.cu_x - ox0);
-      d.win_off = (b.cu_y + t.lt_y - g.rb.y0) * rpitch + (b.cu_x + t.lt_x - rx0);
-      d.nx = t.rb_x - t.lt_x + 1; d.ny = t.rb_y - t.lt_y + 1;
+      d.org_off = (b.cu_y - g.ob.y0) * opitch + (b.cu_x - ox0) * bps;
+      d.win_off = (b.cu_y + t.lt_y + e.cy_first - g.rb.y0) * rpitch + (b.cu_x + t.lt_x - rx0) * bps;
+      d.nx = t.rb_x - t.lt_x + 1; d.ny = e.ny; d.cy_first = e.cy_first; d.shr = bit_depth - 8;
       d.lt_x = t.lt_x; d.lt_y = t.lt_y; d.pred_x = t.pred_x; d.pred_y = t.pred_y; d.lambda = t.lambda_cost;
-      d.n_blk = (d.nx + 15) / 16;
-      d.n_rowgroups = (d.ny + cu_ky(b.S) - 1) / cu_ky(b.S);
-      d.n_items = (d.n_blk * d.n_rowgroups + 7) / 8;
+      d.n_blk = (d.nx + GM.blkw - 1) / GM.blkw;
+      d.n_rowgroups = (d.ny + GM.ky(b.S) - 1) / GM.ky(b.S);
+      d.n_items = (d.n_blk * d.n_rowgroups + GM.groups - 1) / GM.groups;
       d.item_start = item; item += d.n_items;
       for (int s = 0; s < CU_SLOTS; s++) d.out_idx[s] = b.slot_task[s];
       const int v = cu_variant(b.S, b.fen);
       variant_cost[v] += item_cost(b.S, b.fen) * d.n_items;
-      {
-        const int rows = (b.fen && b.S >= 16) ? (b.S == 16 ? 16 : b.S == 32 ? 24 : 32) : b.S;      // rows visited per candidate
-        out->executed_abs_diffs += (unsigned long long)d.n_blk * 16ull * (unsigned long long)(d.n_rowgroups * cu_ky(b.S)) * rows * b.S;
-        for (int s2 = 0; s2 < CU_SLOTS; s2++) if (b.slot_task[s2] >= 0) out->fused_tasks++;
-      }
+      out->executed_abs_diffs += (unsigned long long)d.n_blk * GM.blkw * (unsigned long long)(d.n_rowgroups * GM.ky(b.S)) *
+                                 rows_visited(b.S, b.fen) * b.S;
+      if (e.cy_first == 0) for (int s2 = 0; s2 < CU_SLOTS; s2++) if (b.slot_task[s2] >= 0) out->fused_tasks++;
       bundles.push_back(d); bvar.push_back(v);
     }
     all_r = s8_union(all_r, g.rb); all_o = s8_union(all_o, g.ob);
   }
   long long target[CUV_COUNT];
   for (int v = 0; v < CUV_COUNT; v++) target[v] = std::max<long long>(variant_cost[v] / std::max(1, sm_count * 2 * 12), 4000);
+  const int S_of_variant[CUV_COUNT] = {8, 16, 16, 32, 32, 64, 64};
+  const bool F_of_variant[CUV_COUNT] = {false, false, true, false, true, false, true};
   std::vector<S8Unit> units;
   for (size_t gi = 0; gi < groups.size(); gi++) {
     const Group& g = groups[gi];
     S8Unit u{};
     const int rx0 = s8_fl(g.rb.x0), ox0 = s8_fl(g.ob.x0);
-    u.ref_bx = rx0; u.ref_by = g.rb.y0; u.ref_pitch = s8_ce(g.rb.x1) - rx0; u.ref_rows = g.rb.y1 - g.rb.y0;
-    u.org_bx = ox0; u.org_by = g.ob.y0; u.org_pitch = s8_ce(g.ob.x1) - ox0; u.org_rows = g.ob.y1 - g.ob.y0;
+    u.ref_bx = rx0; u.ref_by = g.rb.y0; u.ref_pitch = (s8_ce(g.rb.x1) - rx0) * bps; u.ref_rows = g.rb.y1 - g.rb.y0;
+    u.org_bx = ox0; u.org_by = g.ob.y0; u.org_pitch = (s8_ce(g.ob.x1) - ox0) * bps; u.org_rows = g.ob.y1 - g.ob.y0;
     int org_off = 0;
-    u.smem_need = s8_smem_need(g.rb, g.ob, &org_off);
+    u.smem_need = s8_smem_need(g.rb, g.ob, &org_off, bps);
     u.org_smem_off = org_off;
     const int bfirst = group_range[gi].first, bcount = group_range[gi].second;
     long long acc = 0;
@@ -532,17 +563,7 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     for (int bl = 0; bl < bcount; bl++) {
       const S8Bundle& b = bundles[bfirst + bl];
       const int v = bvar[bfirst + bl];
-      // cost of one item of this variant
-      long long per_item = 1;
-      switch (v) {
-        case CUV_8: per_item = item_cost(8, false); break;
-        case CUV_16_F0: per_item = item_cost(16, false); break;
-        case CUV_16_F1: per_item = item_cost(16, true); break;
-        case CUV_32_F0: per_item = item_cost(32, false); break;
-        case CUV_32_F1: per_item = item_cost(32, true); break;
-        case CUV_64_F0: per_item = item_cost(64, false); break;
-        default: per_item = item_cost(64, true); break;
-      }
+      const long long per_item = item_cost(S_of_variant[v], F_of_variant[v]);
       if (acc > 0 && v != bvar[bfirst + bl - 1]) { emit(bl - 1, b.item_start); acc = 0; ufirst_item = b.item_start; ufirst_b = bl; }
       int done = 0;
       while (done < b.n_items) {
