@@ -27,6 +27,19 @@ sys.path.insert(0, ROOT)
 
 PIC_W, PIC_H, CODED_H = 1920, 1080, 1088
 SEARCH_RANGE = 64
+BIT_DEPTH = 8
+# --workload selects one of BASELINE.json's GPU configurations; the default (and the one the driver runs) is configs[2]
+WORKLOADS = {
+    "1080p": dict(w=1920, h=1080, coded_h=1088, sr=64, bd=8,
+                  name="1080p_8bit_lowdelayP_fullsearch64_canonical593_fen1_hadme1_qpel",
+                  metric="Mpixel/s, full-search +-64 ME with quarter-pel SATD refinement, 1080p"),
+    "2160p8": dict(w=3840, h=2160, coded_h=2160, sr=64, bd=8,
+                   name="2160p_8bit_lookahead_fullsearch64_canonical593_fen1_hadme1_qpel",
+                   metric="Mpixel/s, full-search +-64 ME with quarter-pel SATD refinement, 2160p"),
+    "2160p10": dict(w=3840, h=2160, coded_h=2160, sr=128, bd=10,
+                    name="2160p_10bit_main10_fullsearch128_canonical593_fen1_hadme1_qpel",
+                    metric="Mpixel/s, full-search +-128 ME with quarter-pel SATD refinement, 2160p 10-bit"),
+}
 LAMBDA_COST = int(np.floor(65536.0 * np.sqrt(0.4624 * 2 ** ((35 - 12) / 3.0))))   # lowdelay-P slice at QP 35
 N_FRAMES = 5                      # distinct synthetic frames per rank -> 4 frame pairs, cycled
 WORKLOAD = "1080p_8bit_lowdelayP_fullsearch64_canonical593_fen1_hadme1_qpel"
@@ -106,7 +119,14 @@ def hbm_peak():
 
 def make_frames(rank):
     from video_codecs_b200 import synth
-    return [synth.luma_frame(PIC_W, CODED_H, t, seed=1234 + 97 * rank) for t in range(N_FRAMES)]
+    return [synth.luma_frame(PIC_W, CODED_H, t, seed=1234 + 97 * rank, bit_depth=BIT_DEPTH) for t in range(N_FRAMES)]
+
+
+def select_workload(name):
+    global PIC_W, PIC_H, CODED_H, SEARCH_RANGE, BIT_DEPTH, WORKLOAD, METRIC
+    w = WORKLOADS[name]
+    PIC_W, PIC_H, CODED_H, SEARCH_RANGE, BIT_DEPTH = w["w"], w["h"], w["coded_h"], w["sr"], w["bd"]
+    WORKLOAD, METRIC = w["name"], w["metric"]
 
 
 def px_per_ctu():
@@ -236,9 +256,17 @@ def run_ours(args):
     frames = make_frames(rank)
     pairs = [(t + 1, t) for t in range(N_FRAMES - 1)]                       # (current, reference) = (t+1, t)
     jobs = hm.build_canonical_jobs(PIC_W, CODED_H, SEARCH_RANGE, LAMBDA_COST)
-    prep = hm.prepare_jobs(jobs, flags, 8)
+    prep = hm.prepare_jobs(jobs, flags, BIT_DEPTH)
     work = prep.work()
-    plane_ids = [hm.register_plane_u8(f, 80, 80, kind=0, poc=i) for i, f in enumerate(frames)]
+    margin = 80 if SEARCH_RANGE <= 64 else 144
+    from video_codecs_b200 import synth as _synth
+
+    def register(f, kind, poc=0):
+        if BIT_DEPTH == 8:
+            return hm.register_plane_u8(f, margin, margin, kind=kind, poc=poc)
+        return hm.register_plane(_synth.pad_plane(f, margin, margin), f.shape[1], f.shape[0], margin, margin, BIT_DEPTH, kind=kind, poc=poc)
+
+    plane_ids = [register(f, 0, i) for i, f in enumerate(frames)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
 
     def barrier():
@@ -277,8 +305,8 @@ def run_ours(args):
 
     def e2e_step(k):
         c, r = pairs[k % len(pairs)]
-        idc = hm.register_plane_u8(frames[c], 80, 80, kind=0)       # pinned staging + H2D + border extension on device
-        idr = hm.register_plane_u8(frames[r], 80, 80, kind=1)
+        idc = register(frames[c], 0)                                # pinned staging + H2D + border extension on device
+        idr = register(frames[r], 1)
         prep.run(idc, idr)
         prep.fetch(out)                                             # D2H of the MV field / costs, synchronises
         hm.release_plane(idc)
@@ -317,15 +345,15 @@ def run_ours(args):
         pu_pixels = float(np.sum(jobs["w"].astype(np.int64) * jobs["h"].astype(np.int64)))
         frac_ops = 400.0 * pu_pixels
         imad_peak = 17.7e12
-        plane_bytes = (PIC_W + 160) * (CODED_H + 160)
+        plane_bytes = (PIC_W + 2 * margin) * (CODED_H + 2 * margin) * (1 if BIT_DEPTH == 8 else 2)
         algo_bytes = 2 * plane_bytes + len(jobs) * (32 + 48)       # both planes once + job list + results
         line = {
             "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
+            "dtype": "u8" if BIT_DEPTH == 8 else "u16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "picture": f"{PIC_W}x{PIC_H} (coded {PIC_W}x{CODED_H})", "search_range": SEARCH_RANGE,
                        "pus_per_frame": int(len(jobs)), "pus_per_ctu": 593, "frame_pairs_per_step_per_gpu": 1,
-                       "l2": "flushed between timed iterations (256 MiB write, untimed)", "mpixel_counts": "1920x1080 luma per step"},
+                       "l2": "flushed between timed iterations (256 MiB write, untimed)", "mpixel_counts": f"{PIC_W}x{PIC_H} luma per step"},
             "cand_sad_per_s": world * work["cand_sads"] / (ms_per_step / 1e3),
             "search_ms": srch / K, "frac_ms": frac / K, "wall_ms_per_step_incl_flush": wall_ms / K,
             "roofline": {"bound": "int_alu", "kernel": "k_search8<*> (VABSDIFF4.U8.ACC)", "achieved": achieved / 1e12,
@@ -344,12 +372,13 @@ def run_ours(args):
                                 "note": "400 integer ops per PU pixel (model, DESIGN.md 3.2)"},
             "roofline_hbm": {"bound": "hbm", "achieved": algo_bytes / (ms_per_step / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
                              "frac": algo_bytes / (ms_per_step / 1e3) / 1e9 / hbm, "traffic": None, "peak_source": hbm_src},
-            "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(2 * PIC_W * CODED_H),
+            "e2e": {"value": e2e_value, "unit": "Mpixel/s",
+                    "h2d_bytes_per_step": int(2 * PIC_W * CODED_H) if BIT_DEPTH == 8 else int(2 * plane_bytes * 2),
                     "d2h_bytes_per_step": int(out.nbytes), "ms_per_step": e2e_ms, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "1080p":
             line["cpu_baseline"] = cpu_sample_single(args.cpu_ctus)
         print(json.dumps(line), flush=True)
     prep.free()
@@ -368,7 +397,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-ctus", type=int, default=16, help="CTUs in the single-core cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)
