@@ -110,6 +110,22 @@ def int_simd_peak():
         return 148 * 64 * 4 * 1.965e9, "fallback: 64 lanes/clk/SM x 4 bytes x 148 SMs x 1.965 GHz"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant search kernel, from the committed ncu
+    --set full capture of this round (profiles/r01_ncu_full_l.csv); None when the file is absent."""
+    import csv
+    try:
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01_ncu_full_l.csv"))))
+        hdr, units = rows[0], rows[1]
+        ki, ti = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
+        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        best = max((r for r in rows[2:] if "k_search8_cu" in r[ki]), key=lambda r: float(r[ti]))
+        return int(float(best[ri]) * scale.get(units[ri], 1.0) + float(best[wi]) * scale.get(units[wi], 1.0)), best[ki].split("(")[0]
+    except Exception:
+        return None, None
+
+
 def hbm_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
@@ -340,6 +356,7 @@ def run_ours(args):
         achieved = work["abs_diffs"] / search_s
         executed = work["abs_diffs_executed"] / search_s
         hbm, hbm_src = hbm_peak()
+        traffic, traffic_kernel = ncu_traffic() if args.workload == "1080p" else (None, None)
         # refinement: integer multiply-add model per PU pixel: 17 SATD candidates x (separable 8-tap
         # interpolation 16 MAC + Hadamard ~8 add/sub/abs) ~ 400 integer ops per pixel of every PU
         pu_pixels = float(np.sum(jobs["w"].astype(np.int64) * jobs["h"].astype(np.int64)))
@@ -357,7 +374,8 @@ def run_ours(args):
             "cand_sad_per_s": world * work["cand_sads"] / (ms_per_step / 1e3),
             "search_ms": srch / K, "frac_ms": frac / K, "wall_ms_per_step_incl_flush": wall_ms / K,
             "roofline": {"bound": "int_alu", "kernel": "k_search8<*> (VABSDIFF4.U8.ACC)", "achieved": achieved / 1e12,
-                         "peak": peak_abs / 1e12, "unit": "Tabsdiff/s", "frac": achieved / peak_abs, "traffic": None,
+                         "peak": peak_abs / 1e12, "unit": "Tabsdiff/s", "frac": achieved / peak_abs, "traffic": traffic,
+                         "traffic_kernel": traffic_kernel,
                          "peak_source": peak_src,
                          "algorithmic_absdiffs_per_launch": int(work["abs_diffs"]),
                          "executed": executed / 1e12, "executed_frac": executed / peak_abs,

@@ -8,7 +8,7 @@ What it does, without copying any reference source into the repository:
   2. compiles that copy and integration/hm_shim.cpp (our binding code) against the reference headers;
   3. links them with the UNMODIFIED reference objects already built by oracle/Makefile.ref (oracle/_ref/obj, minus the
      stock TEncSearch.o) and video_codecs_b200/libhmb200.so into integration/_build/TAppEncoderB200.
-The stock cfg file is copied next to the binary so that the test can run where /root/reference does not exist.
+The encoder settings are written next to the binary (bare key/value lines) for machines without /root/reference.
 """
 import os
 import shutil
@@ -78,8 +78,20 @@ def build(force=False):
         objs += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(".o") and f != "TEncSearch.o"]
     subprocess.check_call(["g++", "-o", BIN, os.path.join(OUT, "TEncSearch_shim.o"), os.path.join(OUT, "hm_shim.o")] + objs +
                           ["-L" + os.path.dirname(lib), "-lhmb200", "-Wl,-rpath,$ORIGIN/../../video_codecs_b200"])
-    shutil.copy(os.path.join(REF, "cfg", "encoder_lowdelay_P_main.cfg"), os.path.join(OUT, "encoder_lowdelay_P_main.cfg"))
+    write_settings(os.path.join(OUT, "lowdelay_P_settings.cfg"))
     return BIN
+
+
+def write_settings(path):
+    """The encoder settings of BASELINE.json configs[0] (the values of the stock lowdelay-P main configuration), reduced
+    to bare `Key : value` lines so that the test can run where /root/reference does not exist."""
+    keep = []
+    for line in open(os.path.join(REF, "cfg", "encoder_lowdelay_P_main.cfg")):
+        line = line.split("#", 1)[0].strip()
+        if ":" in line:
+            k, v = line.split(":", 1)
+            keep.append(f"{k.strip()} : {' '.join(v.split())}")
+    open(path, "w").write("\n".join(sorted(keep, key=lambda l: (not l.startswith("Frame"), l))) + "\n")
 
 
 if __name__ == "__main__":

@@ -16,7 +16,7 @@ import make_encoder_golden as meg  # noqa: E402  (clip generator + command line 
 
 GOLD = os.path.join(ROOT, "tests", "golden", "encoder_md5.json")
 BIN = os.path.join(ROOT, "integration", "_build", "TAppEncoderB200")
-CFG = os.path.join(ROOT, "integration", "_build", "encoder_lowdelay_P_main.cfg")
+CFG = os.path.join(ROOT, "integration", "_build", "lowdelay_P_settings.cfg")
 
 
 def _need_binary():
