@@ -147,6 +147,14 @@ int  hmb200_register_plane(const int16_t* host_origin, int stride, int width, in
  * the device exactly like extendPicBorder. */
 int  hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width, int height,
                               int margin_x, int margin_y, int kind, int poc);
+/* Direct ingest of one frame's luma from a planar YUV file image: TVideoIOYuv::read for COMPONENT_Y
+ * (TLibVideoIO/TVideoIOYuv.cpp:680-741 -> readPlane :247-377 -> scalePlane :70-99) fused with extendPicBorder.
+ * file_luma: width x height samples, bytes or (file_is16) 16-bit little endian; pad_x / pad_y: conformance padding
+ * (aiPad, replicates the last column / row; e.g. 1080 -> 1088 rows); samples are scaled by
+ * 2^(internal_bit_depth - file_bit_depth) (negative: round, shift, clip).  The registered plane has the coded size
+ * (width + pad_x) x (height + pad_y).  No host-side Pel conversion, one H2D copy of the file bytes. */
+int  hmb200_register_plane_yuv(const void* file_luma, int file_is16, int width, int height, int pad_x, int pad_y,
+                               int file_bit_depth, int internal_bit_depth, int margin_x, int margin_y, int kind, int poc);
 /* Reads a registered plane back (including margins) as Pel samples; dst_stride >= width + 2*margin_x. */
 int  hmb200_read_plane(int plane_id, int16_t* dst_origin, int dst_stride);
 void hmb200_release_plane(int plane_id);

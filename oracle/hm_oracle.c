@@ -297,6 +297,40 @@ void hmo_extend_border(int16_t* plane0, int stride, int w, int h, int margin_x, 
   }
 }
 
+/* TLibVideoIO/TVideoIOYuv.cpp:247-377 (readPlane, luma component) followed by :70-99 (scalePlane) as driven by
+ * TVideoIOYuv::read (:680-741): `file` holds width x height luma samples of one frame of a planar file (bytes, or
+ * 16-bit little endian when is16); dst receives (width + pad_x) x (height + pad_y) Pels: right / lower padding
+ * replicate the last column / row, then every sample is scaled by 2^shift (shift = internal - file bit depth;
+ * negative: round, shift, clip to [0, 2^internal - 1]). */
+void hmo_read_luma(const uint8_t* file, int is16, int width, int height, int pad_x, int pad_y, int shift,
+                   int internal_bit_depth, int16_t* dst, int dst_stride)
+{
+  const int fw = width + pad_x, fh = height + pad_y;
+  for (int y = 0; y < height; y++)
+  {
+    int16_t* row = dst + y * dst_stride;
+    const uint8_t* src = file + (size_t)y * width * (is16 ? 2 : 1);
+    for (int x = 0; x < width; x++)
+      row[x] = is16 ? (int16_t)((uint16_t)src[2 * x] | ((uint16_t)src[2 * x + 1] << 8)) : (int16_t)src[x];
+    for (int x = width; x < fw; x++) row[x] = row[width - 1];
+  }
+  for (int y = height; y < fh; y++) memcpy(dst + y * dst_stride, dst + (y - 1) * dst_stride, sizeof(int16_t) * (size_t)fw);
+  if (shift > 0)
+  {
+    for (int y = 0; y < fh; y++) for (int x = 0; x < fw; x++) dst[y * dst_stride + x] = (int16_t)(dst[y * dst_stride + x] << shift);
+  }
+  else if (shift < 0)
+  {
+    const int s = -shift, rounding = 1 << (s - 1), maxval = (1 << internal_bit_depth) - 1;
+    for (int y = 0; y < fh; y++)
+      for (int x = 0; x < fw; x++)
+      {
+        int v = (int16_t)((int16_t)(dst[y * dst_stride + x] + rounding) >> s);      /* Pel arithmetic, like the reference */
+        dst[y * dst_stride + x] = (int16_t)(v < 0 ? 0 : (v > maxval ? maxval : v));
+      }
+  }
+}
+
 /* ---------------------------------------------------------------- job lists ------------------------------------ */
 
 /* Executes a job list the way TEncSearch::xMotionEstimation (TLibEncoder/TEncSearch.cpp:3663-3760) drives the two

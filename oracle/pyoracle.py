@@ -113,6 +113,16 @@ class Oracle(_Base):
     def extend_border(self, plane, origin_off, stride, w, h, mx, my):
         self.lib.hmo_extend_border(_ptr(plane, origin_off), stride, w, h, mx, my)
 
+    def read_luma(self, file_bytes, width, height, pad_x=0, pad_y=0, file_bit_depth=8, internal_bit_depth=8):
+        """Luma plane (coded size, no margins) as TVideoIOYuv::read delivers it from a planar file image."""
+        buf = np.frombuffer(file_bytes, dtype=np.uint8)
+        out = np.zeros((height + pad_y, width + pad_x), dtype=np.int16)
+        self.lib.hmo_read_luma.restype = None
+        self.lib.hmo_read_luma.argtypes = [C.c_void_p] + [C.c_int] * 7 + [_p16, C.c_int]
+        self.lib.hmo_read_luma(buf.ctypes.data, 1 if file_bit_depth > 8 else 0, width, height, pad_x, pad_y,
+                               internal_bit_depth - file_bit_depth, internal_bit_depth, _ptr(out), out.shape[1])
+        return out
+
     def run_jobs(self, cur, ref, jobs, bit_depth=8, do_frac=True):
         """cur/ref: (array, offset of sample (0,0), stride).  Returns (results, cpu_seconds)."""
         (ca, co, cs), (ra, ro, rs) = cur, ref
@@ -185,6 +195,16 @@ class Reference(_Base):
                                            mv_int[0], mv_int[1], int(lambda_cost), pred[0], pred[1],
                                            *[C.byref(x) for x in v], C.byref(cost))
         return (v[0].value, v[1].value), (v[2].value, v[3].value), cost.value
+
+    def read_luma(self, path, width, height, pad_x=0, pad_y=0, file_bit_depth=8, internal_bit_depth=8):
+        """The reference's own reader (TVideoIOYuv) on a planar 4:0:0 file."""
+        out = np.zeros((height + pad_y, width + pad_x), dtype=np.int16)
+        self.lib.hmref_read_luma.restype = C.c_int
+        self.lib.hmref_read_luma.argtypes = [C.c_char_p] + [C.c_int] * 6 + [_p16, C.c_int]
+        rc = self.lib.hmref_read_luma(path.encode(), width, height, pad_x, pad_y, file_bit_depth, internal_bit_depth, _ptr(out), out.shape[1])
+        if rc != 0:
+            raise IOError(f"reference reader failed on {path}")
+        return out
 
     def run_jobs(self, cur, ref, jobs, bit_depth=8, do_frac=True):
         (ca, co, cs), (ra, ro, rs) = cur, ref

@@ -18,6 +18,8 @@
 #include "TLibCommon/TComPattern.h"
 #include "TLibEncoder/TEncCfg.h"
 #include "TLibEncoder/TEncSearch.h"
+#include "TLibVideoIO/TVideoIOYuv.h"
+#include "TLibCommon/TComPicYuv.h"
 
 namespace {
 
@@ -169,6 +171,28 @@ double hmref_run_jobs(void* hv, const int16_t* cur0, int cur_stride, const int16
     out[i] = r;
   }
   return double(clock() - t0) / CLOCKS_PER_SEC;
+}
+
+// TVideoIOYuv::open + read (TLibVideoIO/TVideoIOYuv.cpp:118-245, 680-741) on a planar 4:0:0 file: returns the luma
+// plane the encoder would see (conformance padding pad_x / pad_y, bit-depth scaling), without margins.
+int hmref_read_luma(const char* path, int width, int height, int pad_x, int pad_y, int file_bit_depth, int internal_bit_depth,
+                    int16_t* dst, int dst_stride)
+{
+  if (!g_rom) { initROM(); g_rom = true; }
+  TVideoIOYuv io;
+  Int fileBD[MAX_NUM_CHANNEL_TYPE], msbBD[MAX_NUM_CHANNEL_TYPE], intBD[MAX_NUM_CHANNEL_TYPE];
+  for (int c = 0; c < MAX_NUM_CHANNEL_TYPE; c++) { fileBD[c] = file_bit_depth; msbBD[c] = file_bit_depth; intBD[c] = internal_bit_depth; }
+  io.open(const_cast<char*>(path), false, fileBD, msbBD, intBD);
+  TComPicYuv pic;
+  pic.create(width + pad_x, height + pad_y, CHROMA_400, 64, 64, 4, true);
+  Int pad[2] = { pad_x, pad_y };
+  const bool ok = io.read(&pic, &pic, IPCOLOURSPACE_UNCHANGED, pad, CHROMA_400, false);
+  if (ok)
+    for (int y = 0; y < height + pad_y; y++)
+      memcpy(dst + y * dst_stride, pic.getAddr(COMPONENT_Y) + y * pic.getStride(COMPONENT_Y), sizeof(int16_t) * (size_t)(width + pad_x));
+  pic.destroy();
+  io.close();
+  return ok ? 0 : -1;
 }
 
 } // extern "C"

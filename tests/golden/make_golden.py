@@ -118,5 +118,28 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def make_ingest_golden():
+    """tests/golden/yuv_ingest_golden.npz: file images and the luma planes the reference's TVideoIOYuv reads from them."""
+    import tempfile
+    ref = Reference(fen=1, hadme=1)
+    cases = [(64, 40, 0, 0, 8, 8), (52, 36, 4, 4, 8, 8), (64, 24, 0, 8, 8, 10), (40, 24, 8, 0, 10, 10), (48, 32, 0, 0, 10, 8),
+             (32, 16, 8, 8, 12, 10), (24, 16, 0, 0, 16, 12)]
+    rng = np.random.default_rng(2024)
+    out = {"cases": np.array(cases, dtype=np.int32)}
+    with tempfile.TemporaryDirectory() as d:
+        for i, (w, h, px, py, fbd, ibd) in enumerate(cases):
+            data = (rng.integers(0, 256, size=w * h, dtype=np.uint8).tobytes() if fbd == 8
+                    else rng.integers(0, 1 << fbd, size=w * h).astype("<u2").tobytes())
+            path = os.path.join(d, f"c{i}.yuv")
+            open(path, "wb").write(data)
+            out[f"file_{i}"] = np.frombuffer(data, dtype=np.uint8)
+            out[f"plane_{i}"] = ref.read_luma(path, w, h, px, py, fbd, ibd)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "yuv_ingest_golden.npz"), **out)
+    print("wrote yuv_ingest_golden.npz")
+
+
 if __name__ == "__main__":
+    if "--ingest" in sys.argv:
+        make_ingest_golden()
+        sys.exit(0)
     main()

@@ -65,6 +65,7 @@ def _load():
         "hmb200_tile_column_range": (i32, [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]),
         "hmb200_register_plane": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32]),
         "hmb200_register_plane_u8": (i32, [vp, i32, i32, i32, i32, i32, i32, i32]),
+        "hmb200_register_plane_yuv": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32]),
         "hmb200_read_plane": (i32, [i32, vp, i32]), "hmb200_release_plane": (None, [i32]),
         "hmb200_dist": (u32, [C.POINTER(_DistParam)]),
         "hmb200_dist_batch": (i32, [i32, i32, i32, vp, vp]),
@@ -155,6 +156,16 @@ class HMB200:
         assert samples.dtype == np.uint8 and samples.ndim == 2 and samples.strides[1] == 1
         h, w = samples.shape
         return self._check(self.lib.hmb200_register_plane_u8(samples.ctypes.data, samples.strides[0], w, h, margin_x, margin_y, kind, poc))
+
+    def register_plane_yuv(self, file_luma, width, height, pad_x=0, pad_y=0, file_bit_depth=8, internal_bit_depth=8,
+                           margin_x=80, margin_y=80, kind=PLANE_ORG, poc=0):
+        """file_luma: bytes-like / uint8 array holding width*height luma samples of a planar file (16-bit LE when
+        file_bit_depth > 8)."""
+        buf = np.frombuffer(file_luma, dtype=np.uint8) if not isinstance(file_luma, np.ndarray) else np.ascontiguousarray(file_luma).view(np.uint8)
+        is16 = 1 if file_bit_depth > 8 else 0
+        assert buf.size >= width * height * (2 if is16 else 1)
+        return self._check(self.lib.hmb200_register_plane_yuv(buf.ctypes.data, is16, width, height, pad_x, pad_y, file_bit_depth,
+                                                              internal_bit_depth, margin_x, margin_y, kind, poc))
 
     def read_plane(self, plane_id, width, height, margin_x, margin_y):
         out = np.zeros((height + 2 * margin_y, width + 2 * margin_x), dtype=np.int16)

@@ -374,6 +374,37 @@ int hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width,
   return id;
 }
 
+int hmb200_register_plane_yuv(const void* file_luma, int file_is16, int width, int height, int pad_x, int pad_y,
+                              int file_bit_depth, int internal_bit_depth, int margin_x, int margin_y, int kind, int poc) {
+  NEED_READY();
+  if (!file_luma || width <= 0 || height <= 0 || pad_x < 0 || pad_y < 0 || margin_x < 0 || margin_y < 0 || file_bit_depth < 8 ||
+      file_bit_depth > 16 || internal_bit_depth < 8 || internal_bit_depth > 14 || (!file_is16 && file_bit_depth > 8))
+    return fail(HMB200_ERR_ARG, "hmb200_register_plane_yuv: bad geometry or bit depths");
+  int id = alloc_plane_slot();
+  Plane& p = g.planes[id];
+  p = Plane();
+  const int cw = width + pad_x, ch = height + pad_y;
+  int rc = make_plane(p, cw, ch, margin_x, margin_y, internal_bit_depth);
+  if (rc != HMB200_OK) return rc;
+  const size_t bytes = (size_t)width * height * (file_is16 ? 2 : 1);
+  if ((rc = ensure_pinned(bytes)) != HMB200_OK || (rc = ensure_dstage(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
+  memcpy(g.pinned, file_luma, bytes);
+  CUDA_TRY(cudaMemcpyAsync(g.dstage, g.pinned, bytes, cudaMemcpyHostToDevice, g.stream));
+  const int shift = internal_bit_depth - file_bit_depth, maxval = (1 << internal_bit_depth) - 1;
+  dim3 grid((cw + 2 * margin_x + 255) / 256, ch + 2 * margin_y);
+  if (p.d.bytes_per_sample == 1)
+    k_ingest_luma<uint8_t><<<grid, 256, 0, g.stream>>>(reinterpret_cast<const uint8_t*>(g.dstage), file_is16, width, height, pad_x, pad_y,
+                                                       shift, maxval, reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, margin_x, margin_y);
+  else
+    k_ingest_luma<uint16_t><<<grid, 256, 0, g.stream>>>(reinterpret_cast<const uint8_t*>(g.dstage), file_is16, width, height, pad_x, pad_y,
+                                                        shift, maxval, reinterpret_cast<uint16_t*>(p.d.base), p.d.pitch, margin_x, margin_y);
+  g.launches++;
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  p.kind = kind; p.poc = poc;
+  return id;
+}
+
 int hmb200_read_plane(int plane_id, int16_t* dst_origin, int dst_stride) {
   NEED_READY();
   Plane* p = get_plane(plane_id);

@@ -302,4 +302,22 @@ __global__ void k_pad_plane_u8(const uint8_t* __restrict__ src, int src_stride, 
   }
 }
 
+// Planar-file luma ingest: TVideoIOYuv::read for the luma component (TLibVideoIO/TVideoIOYuv.cpp:247-377 readPlane,
+// :70-99 scalePlane) fused with TComPicYuv::extendPicBorder (TLibCommon/TComPicYuv.cpp:197-242).  src: width x height
+// file samples (bytes, or 16-bit little endian); the coded picture is (width + pad_x) x (height + pad_y) with the last
+// column / row replicated; every sample is scaled by 2^shift; margins replicate the coded picture's edges.
+template <typename T>
+__global__ void k_ingest_luma(const uint8_t* __restrict__ src, int is16, int width, int height, int pad_x, int pad_y, int shift,
+                              int maxval, T* __restrict__ dst, int dst_pitch, int mx, int my) {
+  const int cw = width + pad_x, chh = height + pad_y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= cw + 2 * mx || y >= chh + 2 * my) return;
+  const int sx = min(min(max(x - mx, 0), cw - 1), width - 1), sy = min(min(max(y - my, 0), chh - 1), height - 1);
+  const size_t o = (size_t)sy * width + sx;
+  int v = is16 ? (int)(int16_t)((uint16_t)src[2 * o] | ((uint16_t)src[2 * o + 1] << 8)) : (int)src[o];
+  if (shift > 0) v = (int)(int16_t)(v << shift);
+  else if (shift < 0) { v = (int)(int16_t)((int16_t)(v + (1 << (-shift - 1))) >> (-shift)); v = min(max(v, 0), maxval); }
+  dst[(size_t)y * dst_pitch + x] = (T)v;
+}
+
 } // namespace hmb200
