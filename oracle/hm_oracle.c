@@ -179,6 +179,140 @@ void hmo_pattern_search(const int16_t* org, int so, int w, int h, int bit_depth,
   *sad_out = best - hmo_mv_cost(lambda_cost, hmo_mv_bits(bx, by, pred_x, pred_y, 2));
 }
 
+/* ---------------------------------------------------------------- TZ fast search ------------------------------- */
+
+/* TLibEncoder/TEncSearch.cpp:3881-4083 xTZSearch (FastSearch = 1) with its helpers xTZSearchHelp (:332-436, the
+ * non-selective branch: SAD with FEN sub-sampling + getCost, strict '<'), xTZ8PointDiamondSearch (:626-800) and
+ * xTZ2PointSearch (:438-567), under TZ_SEARCH_CONFIGURATION (:297-313): raster step 5, zero vector tested, diamond first
+ * search over distances 1, 2, 4 .. <= search range without early stop (FastMEAssumingSmootherMV off), raster search
+ * when the best distance exceeds 5, star refinement until the best distance is 0.
+ *
+ * Restated as "evaluate an ordered list of points, keep the first minimum": every stage of the reference issues
+ * xTZSearchHelp calls whose positions depend only on the stage's start point, so the sequential strict-'<' updates
+ * equal taking the first minimal cost in call order.  uiBestRound is only read by the two stop criteria that are off. */
+typedef struct { uint32_t cost; int x, y, dist, nr; } tz_state;
+typedef struct { int x, y, nr, dist; } tz_point;
+
+typedef struct {
+  const int16_t* org; int so; const int16_t* ref; int sr; int w, h, bit_depth, sub;
+  uint32_t lambda_cost; int pred_x, pred_y;
+} tz_ctx;
+
+static void tz_try(const tz_ctx* c, tz_state* st, int x, int y, int nr, int dist)
+{
+  uint32_t cost = hmo_sad(c->org, c->so, c->ref + y * c->sr + x, c->sr, c->w, c->h, c->bit_depth, c->sub)
+                + hmo_mv_cost(c->lambda_cost, hmo_mv_bits(x, y, c->pred_x, c->pred_y, 2));
+  if (cost < st->cost) { st->cost = cost; st->x = x; st->y = y; st->dist = dist; st->nr = nr; }
+}
+
+/* the points one diamond call visits, in call order; L/T/R/B = search range (inclusive).  Returns the count. */
+static int tz_diamond(int sx, int sy, int d, int L, int T, int R, int B, tz_point* out)
+{
+  int n = 0;
+  const int top = sy - d, bot = sy + d, left = sx - d, right = sx + d;
+#define TZ_ADD(cond, px, py, pnr, pd) do { if (cond) { out[n].x = (px); out[n].y = (py); out[n].nr = (pnr); out[n].dist = (pd); n++; } } while (0)
+  if (d == 1)
+  {
+    TZ_ADD(top >= T, sx, top, 2, d); TZ_ADD(left >= L, left, sy, 4, d); TZ_ADD(right <= R, right, sy, 5, d); TZ_ADD(bot <= B, sx, bot, 7, d);
+  }
+  else if (d <= 8)
+  {
+    const int h = d >> 1, t2 = sy - h, b2 = sy + h, l2 = sx - h, r2 = sx + h;
+    /* inside the range every condition below holds, which is the reference's unconditional branch (same order) */
+    TZ_ADD(top >= T, sx, top, 2, d);
+    TZ_ADD(t2 >= T && l2 >= L, l2, t2, 1, h);
+    TZ_ADD(t2 >= T && r2 <= R, r2, t2, 3, h);
+    TZ_ADD(left >= L, left, sy, 4, d);
+    TZ_ADD(right <= R, right, sy, 5, d);
+    TZ_ADD(b2 <= B && l2 >= L, l2, b2, 6, h);
+    TZ_ADD(b2 <= B && r2 <= R, r2, b2, 8, h);
+    TZ_ADD(bot <= B, sx, bot, 7, d);
+  }
+  else
+  {
+    TZ_ADD(top >= T, sx, top, 0, d); TZ_ADD(left >= L, left, sy, 0, d); TZ_ADD(right <= R, right, sy, 0, d); TZ_ADD(bot <= B, sx, bot, 0, d);
+    for (int i = 1; i < 4; i++)
+    {
+      const int q = (d >> 2) * i, yt = top + q, yb = bot - q, xl = sx - q, xr = sx + q;
+      TZ_ADD(yt >= T && xl >= L, xl, yt, 0, d); TZ_ADD(yt >= T && xr <= R, xr, yt, 0, d);
+      TZ_ADD(yb <= B && xl >= L, xl, yb, 0, d); TZ_ADD(yb <= B && xr <= R, xr, yb, 0, d);
+    }
+  }
+#undef TZ_ADD
+  return n;
+}
+
+/* xTZ2PointSearch: the two untested neighbours of the best point, selected by the diamond position it came from */
+static void tz_two_point(const tz_ctx* c, tz_state* st, int L, int T, int R, int B)
+{
+  const int x = st->x, y = st->y;
+  switch (st->nr)
+  {
+    case 1: if (x - 1 >= L) tz_try(c, st, x - 1, y, 0, 2);     if (y - 1 >= T) tz_try(c, st, x, y - 1, 0, 2); break;
+    case 2: if (y - 1 >= T) { if (x - 1 >= L) tz_try(c, st, x - 1, y - 1, 0, 2); if (x + 1 <= R) tz_try(c, st, x + 1, y - 1, 0, 2); } break;
+    case 3: if (y - 1 >= T) tz_try(c, st, x, y - 1, 0, 2);     if (x + 1 <= R) tz_try(c, st, x + 1, y, 0, 2); break;
+    case 4: if (x - 1 >= L) { if (y + 1 <= B) tz_try(c, st, x - 1, y + 1, 0, 2); if (y - 1 >= T) tz_try(c, st, x - 1, y - 1, 0, 2); } break;
+    case 5: if (x + 1 <= R) { if (y - 1 >= T) tz_try(c, st, x + 1, y - 1, 0, 2); if (y + 1 <= B) tz_try(c, st, x + 1, y + 1, 0, 2); } break;
+    case 6: if (x - 1 >= L) tz_try(c, st, x - 1, y, 0, 2);     if (y + 1 <= B) tz_try(c, st, x, y + 1, 0, 2); break;
+    case 7: if (y + 1 <= B) { if (x - 1 >= L) tz_try(c, st, x - 1, y + 1, 0, 2); if (x + 1 <= R) tz_try(c, st, x + 1, y + 1, 0, 2); } break;
+    case 8: if (x + 1 <= R) tz_try(c, st, x + 1, y, 0, 2);     if (y + 1 <= B) tz_try(c, st, x, y + 1, 0, 2); break;
+    default: break;   /* the reference asserts; the callers below never get here with nr == 0 */
+  }
+}
+
+/* (pred_x, pred_y): the AMVP predictor in quarter pel (rcMv on entry and m_mvPredictor); (lt, rb): the window of
+ * xSetSearchRange(pred); the CU geometry feeds clipMv (TLibCommon/TComDataCU.cpp:2788-2801); has_imv: pIntegerMv2Nx2NPred. */
+void hmo_tz_search(const int16_t* org, int so, int w, int h, int bit_depth, const int16_t* ref_at_pu, int sr,
+                   int lt_x, int lt_y, int rb_x, int rb_y, uint32_t lambda_cost, int pred_x, int pred_y, int fen,
+                   int cu_x, int cu_y, int pic_w, int pic_h, int max_cu, int search_range,
+                   int has_imv, int imv_x, int imv_y, int* mv_x, int* mv_y, uint32_t* sad_out)
+{
+  tz_ctx c = { org, so, ref_at_pu, sr, w, h, bit_depth, (fen && h > 8) ? 1 : 0, lambda_cost, pred_x, pred_y };
+  tz_state st = { 0xFFFFFFFFu, 0, 0, 0, 0 };
+  tz_point pts[16];
+  int rl = lt_x, rt = lt_y, rr = rb_x, rb = rb_y;             /* range of the raster search (reset below) */
+
+  int sx = pred_x, sy = pred_y;
+  hmo_clip_mv(&sx, &sy, cu_x, cu_y, pic_w, pic_h, max_cu, max_cu);
+  tz_try(&c, &st, asr2(sx), asr2(sy), 0, 0);                  /* :3908 predictor, clipped, integer pel */
+  tz_try(&c, &st, 0, 0, 0, 0);                                /* :3924 zero vector */
+  if (has_imv)
+  {
+    int ix = (int16_t)(imv_x << 2), iy = (int16_t)(imv_y << 2);
+    hmo_clip_mv(&ix, &iy, cu_x, cu_y, pic_w, pic_h, max_cu, max_cu);
+    tz_try(&c, &st, asr2(ix), asr2(iy), 0, 0);
+    /* :3935-3946 only the raster search sees the re-centred range; the diamonds keep the caller's range */
+    hmo_search_range((int16_t)(st.x << 2), (int16_t)(st.y << 2), search_range, cu_x, cu_y, pic_w, pic_h, max_cu, max_cu, &rl, &rt, &rr, &rb);
+  }
+
+  const int start_x = st.x, start_y = st.y;
+  for (int d = 1; d <= search_range; d *= 2)                  /* first search: every diamond around the same start */
+  {
+    int n = tz_diamond(start_x, start_y, d, lt_x, lt_y, rb_x, rb_y, pts);
+    for (int i = 0; i < n; i++) tz_try(&c, &st, pts[i].x, pts[i].y, pts[i].nr, pts[i].dist);
+  }
+  if (st.dist == 1) { st.dist = 0; tz_two_point(&c, &st, lt_x, lt_y, rb_x, rb_y); }
+  if (st.dist > 5)                                            /* raster search, step iRaster = 5 */
+  {
+    st.dist = 5;
+    for (int y = rt; y <= rb; y += 5)
+      for (int x = rl; x <= rr; x += 5) tz_try(&c, &st, x, y, 0, 5);
+  }
+  while (st.dist > 0)                                         /* star refinement */
+  {
+    const int bx = st.x, by = st.y;
+    st.dist = 0; st.nr = 0;
+    for (int d = 1; d < search_range + 1; d *= 2)
+    {
+      int n = tz_diamond(bx, by, d, lt_x, lt_y, rb_x, rb_y, pts);
+      for (int i = 0; i < n; i++) tz_try(&c, &st, pts[i].x, pts[i].y, pts[i].nr, pts[i].dist);
+    }
+    if (st.dist == 1) { st.dist = 0; if (st.nr != 0) tz_two_point(&c, &st, lt_x, lt_y, rb_x, rb_y); }
+  }
+  *mv_x = st.x; *mv_y = st.y;
+  *sad_out = st.cost - hmo_mv_cost(lambda_cost, hmo_mv_bits(st.x, st.y, pred_x, pred_y, 2));
+}
+
 /* ---------------------------------------------------------------- interpolation -------------------------------- */
 
 /* TLibCommon/TComInterpolationFilter.cpp:57-63 m_lumaFilter */

@@ -13,6 +13,34 @@
 #include <cstdint>
 #include <cstring>
 #include <ctime>
+// Standard headers first, then the access-specifier trick: the harness has to place a bare TComDataCU at a CU position
+// (m_uiCUPelX/Y, m_pcSlice are private, TLibCommon/TComDataCU.h:73-82) to drive xTZSearch, which calls pcCU->clipMv.
+// Layout is unaffected (GCC lays members out in declaration order regardless of access).
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <deque>
+#include <fstream>
+#include <functional>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <list>
+#include <map>
+#include <numeric>
+#include <set>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+#include <math.h>
+#include <stdint.h>
+#include <time.h>
+#define private public
+#define protected public
+#include "TLibCommon/TComDataCU.h"
+#undef private
+#undef protected
 #include "TLibCommon/TComRom.h"
 #include "TLibCommon/TComRdCost.h"
 #include "TLibCommon/TComPattern.h"
@@ -76,6 +104,33 @@ struct Harness : public TEncSearch
     Distortion d = 0;
     xPatternSearchFracDIF(lossless != 0, &pat, refAtPu, refStride, &mvInt, half, qter, d);
     *hx = half.getHor(); *hy = half.getVer(); *qx = qter.getHor(); *qy = qter.getVer(); *cost = d;
+  }
+
+  // TEncSearch::xTZSearch (TEncSearch.cpp:3881) as xMotionEstimation / xPatternSearchFast reach it with FastSearch = 1.
+  // The CU only has to answer clipMv(): picture size and max CU size through its slice's SPS, and its own position.
+  TComSPS    sps;
+  TComSlice  slice;
+  TComDataCU cu;
+  void tz(Pel* org, int orgStride, int w, int h, int bitDepth, Pel* refAtPu, int refStride,
+          int ltx, int lty, int rbx, int rby, uint32_t uiCost, int predx, int predy,
+          int cux, int cuy, int picw, int pich, int maxcu, int searchRange, int hasImv, int imvx, int imvy,
+          int* mvx, int* mvy, uint32_t* sad)
+  {
+    sps.setPicWidthInLumaSamples(picw); sps.setPicHeightInLumaSamples(pich);
+    sps.setMaxCUWidth(maxcu); sps.setMaxCUHeight(maxcu);
+    slice.setSPS(&sps);
+    cu.m_pcSlice = &slice; cu.m_uiCUPelX = cux; cu.m_uiCUPelY = cuy;
+    cfg.setFastSearch(1);
+    cfg.setFastMEAssumingSmootherMVEnabled(false);
+    m_iFastSearch = 1;
+    m_iSearchRange = searchRange;
+    TComPattern pat;
+    pat.initPattern(org, w, h, orgStride, bitDepth);
+    setCost(uiCost, predx, predy, 2);
+    TComMv lt((Short)ltx, (Short)lty), rb((Short)rbx, (Short)rby), mv((Short)predx, (Short)predy), imv((Short)imvx, (Short)imvy);
+    Distortion d = 0;
+    xTZSearch(&cu, &pat, refAtPu, refStride, &lt, &rb, mv, d, hasImv ? &imv : NULL);
+    *mvx = mv.getHor(); *mvy = mv.getVer(); *sad = d;
   }
 };
 
@@ -171,6 +226,16 @@ double hmref_run_jobs(void* hv, const int16_t* cur0, int cur_stride, const int16
     out[i] = r;
   }
   return double(clock() - t0) / CLOCKS_PER_SEC;
+}
+
+void hmref_tz_search(void* hv, const int16_t* org, int org_stride, int w, int h, int bit_depth,
+                     const int16_t* ref_at_pu, int ref_stride, int lt_x, int lt_y, int rb_x, int rb_y,
+                     uint32_t ui_cost, int pred_x, int pred_y, int cu_x, int cu_y, int pic_w, int pic_h, int max_cu,
+                     int search_range, int has_imv, int imv_x, int imv_y, int* mv_x, int* mv_y, uint32_t* sad)
+{
+  static_cast<Harness*>(hv)->tz(const_cast<Pel*>(org), org_stride, w, h, bit_depth, const_cast<Pel*>(ref_at_pu), ref_stride,
+                                lt_x, lt_y, rb_x, rb_y, ui_cost, pred_x, pred_y, cu_x, cu_y, pic_w, pic_h, max_cu, search_range,
+                                has_imv, imv_x, imv_y, mv_x, mv_y, sad);
 }
 
 // TVideoIOYuv::open + read (TLibVideoIO/TVideoIOYuv.cpp:118-245, 680-741) on a planar 4:0:0 file: returns the luma

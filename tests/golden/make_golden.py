@@ -138,7 +138,34 @@ def make_ingest_golden():
     print("wrote yuv_ingest_golden.npz")
 
 
+def make_tz_golden():
+    """tests/golden/tz_golden.npz: xTZSearch results of the unmodified reference (FEN = 1) for the cases of
+    tests/test_tz_search.py::make_cases, with the windows of xSetSearchRange."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_tz_search as T
+    from common import padded
+    from oracle.pyoracle import Oracle
+    ref_impl, O = Reference(fen=1, hadme=1), Oracle(fen=1, hadme=1)
+    f0, f1 = synth.luma_frame(T.W, T.H, 0, seed=17), synth.luma_frame(T.W, T.H, 3, seed=17)
+    cur, o0, stride = padded(f1)
+    ref, _, _ = padded(f0)
+    cases, exp = [], []
+    for (px, py, w, h, cu_x, cu_y, pred, lam, sr, imv) in T.make_cases(np.random.default_rng(7), 300):
+        lt_rb = O.search_range(pred, sr, (cu_x, cu_y), (T.W, T.H))
+        off = o0 + py * stride + px
+        mv, sad = ref_impl.tz_search((cur, off, stride), w, h, (ref, off, stride), lt_rb[:2], lt_rb[2:], lam, pred, (cu_x, cu_y), (T.W, T.H), sr, imv)
+        cases.append((px, py, w, h, cu_x, cu_y, pred[0], pred[1], lam, sr, 0 if imv is None else 1, 0 if imv is None else imv[0],
+                      0 if imv is None else imv[1]) + tuple(lt_rb))
+        exp.append((mv[0], mv[1], sad))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "tz_golden.npz"), frame0=f0, frame1=f1,
+                        cases=np.array(cases, dtype=np.int64), expected=np.array(exp, dtype=np.int64))
+    print("wrote tz_golden.npz", len(cases))
+
+
 if __name__ == "__main__":
+    if "--tz" in sys.argv:
+        make_tz_golden()
+        sys.exit(0)
     if "--ingest" in sys.argv:
         make_ingest_golden()
         sys.exit(0)
