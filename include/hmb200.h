@@ -27,6 +27,7 @@ extern "C" {
 #define HMB200_FLAG_FEN      1   /* getUseFastEnc(): iSubShift = 1 for PUs with more than 8 rows (TEncSearch.cpp:3804-3810) */
 #define HMB200_FLAG_HADME    2   /* getUseHADME(): sub-pel refinement uses xGetHADs (TComRdCost.cpp:355-374)           */
 #define HMB200_FLAG_FRAC     4   /* also run the quarter-pel refinement (xPatternSearchFracDIF)                          */
+#define HMB200_FLAG_TZ       8   /* integer search = xTZSearch (FastSearch = 1) instead of the full search                */
 
 /* ---- distortion function families, the rows of m_afpDistortFunc (TLibCommon/TypeDef.h:334-378) ---- */
 #define HMB200_DF_SAD        0   /* DF_SAD*  : xGetSAD4..64/12/24/48 honouring iSubShift (TComRdCost.cpp:489-953) */
@@ -209,6 +210,27 @@ int  hmb200_last_timing(float* total_ms, float* search_ms, float* frac_ms);
 /* Algorithmic work of a prepared job list: candidate-SADs and byte abs-diffs as HM would execute them
  * (SURVEY.md section 8d). */
 int  hmb200_prepared_work(const hmb200_prepared* p, uint64_t* cand_sads, uint64_t* abs_diffs);
+
+/* ------------------------------------------------------------------ TZ fast search, batched ------------------- */
+
+/* What xTZSearch reads besides the PU job: the CU that owns the PU (pcCU->clipMv of the predictor and of the re-centred
+ * raster range, TLibCommon/TComDataCU.cpp:2788-2801) and pIntegerMv2Nx2NPred (integer pel; TEncSearch.cpp:3926-3946). */
+typedef struct {
+  int32_t cu_x, cu_y;
+  int32_t has_imv, imv_x, imv_y;
+  int32_t reserved[3];
+} hmb200_tz_extra;
+
+/* cu_x / cu_y of canonical-list PUs (the aligned S x S CU with S = max(w, h)); has_imv = 0. */
+void hmb200_canonical_tz_extra(const hmb200_pu_job* jobs, int njobs, hmb200_tz_extra* extra);
+/* Turns a list prepared with HMB200_FLAG_TZ into a TZ search: TEncSearch::xTZSearch (TLibEncoder/TEncSearch.cpp:
+ * 3881-4083) under TZ_SEARCH_CONFIGURATION (:297-313) with FastMEAssumingSmootherMV off; jobs[i].pred is the AMVP
+ * predictor the search starts from (rcMv on entry), jobs[i].lt/rb the window of xSetSearchRange(pred),
+ * search_range = m_iSearchRange.  hmb200_run_prepared then runs it (followed by the refinement with FLAG_FRAC). */
+int  hmb200_prepared_set_tz(hmb200_prepared* p, const hmb200_tz_extra* extra, int pic_w, int pic_h, int max_cu, int search_range);
+/* prepare + set_tz + run + fetch in one blocking call. */
+int  hmb200_tz_jobs(int cur_plane, int ref_plane, const hmb200_pu_job* jobs, const hmb200_tz_extra* extra, int njobs,
+                    int pic_w, int pic_h, int max_cu, int search_range, int flags, hmb200_pu_result* results);
 
 /* Byte abs-diffs the tiled kernels actually execute for a prepared list, and how many PUs run CU-fused (partial SADs
  * of a CU shared by all its partitions): executed < algorithmic when fusion applies.  Reported next to the roofline

@@ -6,7 +6,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-FLAG_FEN, FLAG_HADME, FLAG_FRAC = 1, 2, 4
+FLAG_FEN, FLAG_HADME, FLAG_FRAC, FLAG_TZ = 1, 2, 4, 8
 DF_SAD, DF_SSE, DF_HADS, DF_SADS = 0, 1, 2, 3
 PLANE_ORG, PLANE_REC = 0, 1
 
@@ -19,6 +19,9 @@ RESULT_DTYPE = np.dtype([("mv_x", "<i4"), ("mv_y", "<i4"), ("sad", "<u4"),
 DIST_DESC_DTYPE = np.dtype([("org_plane", "<i4"), ("org_x", "<i4"), ("org_y", "<i4"),
                             ("cur_plane", "<i4"), ("cur_x", "<i4"), ("cur_y", "<i4"),
                             ("w", "<i4"), ("h", "<i4"), ("sub_shift", "<i4"), ("reserved", "<i4")])
+TZ_EXTRA_DTYPE = np.dtype([("cu_x", "<i4"), ("cu_y", "<i4"), ("has_imv", "<i4"), ("imv_x", "<i4"), ("imv_y", "<i4"),
+                           ("reserved", "<i4", (3,))])
+assert TZ_EXTRA_DTYPE.itemsize == 32
 assert JOB_DTYPE.itemsize == 48 and RESULT_DTYPE.itemsize == 32 and DIST_DESC_DTYPE.itemsize == 40
 
 
@@ -80,6 +83,9 @@ def _load():
         "hmb200_sync": (i32, []),
         "hmb200_last_timing": (i32, [C.POINTER(C.c_float)] * 3),
         "hmb200_prepared_work": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "hmb200_canonical_tz_extra": (None, [vp, i32, vp]),
+        "hmb200_prepared_set_tz": (i32, [vp, vp, i32, i32, i32, i32]),
+        "hmb200_tz_jobs": (i32, [i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
         "hmb200_prepared_executed_work": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     }
     for name, (res, args) in sig.items():
@@ -221,6 +227,21 @@ class HMB200:
         self._check(self.lib.hmb200_me_ctu_row(cur_plane, ref_plane, ctu_row, max_cu, jobs.ctypes.data, len(jobs), flags, out.ctypes.data))
         return out
 
+    def canonical_tz_extra(self, jobs):
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        extra = np.zeros(len(jobs), dtype=TZ_EXTRA_DTYPE)
+        self.lib.hmb200_canonical_tz_extra(jobs.ctypes.data, len(jobs), extra.ctypes.data)
+        return extra
+
+    def tz_jobs(self, cur_plane, ref_plane, jobs, extra, pic_wh, search_range=64, flags=FLAG_FEN | FLAG_HADME | FLAG_FRAC, max_cu=64):
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        extra = np.ascontiguousarray(extra, dtype=TZ_EXTRA_DTYPE)
+        assert len(extra) == len(jobs)
+        out = np.zeros(len(jobs), dtype=RESULT_DTYPE)
+        self._check(self.lib.hmb200_tz_jobs(cur_plane, ref_plane, jobs.ctypes.data, extra.ctypes.data, len(jobs), pic_wh[0], pic_wh[1],
+                                            max_cu, search_range, flags, out.ctypes.data))
+        return out
+
     def prepare_jobs(self, jobs, flags=FLAG_FEN | FLAG_HADME | FLAG_FRAC, bit_depth=8):
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         h = self.lib.hmb200_prepare_jobs(jobs.ctypes.data, len(jobs), flags, bit_depth)
@@ -235,6 +256,11 @@ class HMB200:
 class Prepared:
     def __init__(self, owner, handle, n):
         self.o, self.h, self.n = owner, handle, n
+
+    def set_tz(self, extra, pic_wh, search_range=64, max_cu=64):
+        extra = np.ascontiguousarray(extra, dtype=TZ_EXTRA_DTYPE)
+        assert len(extra) == self.n
+        self.o._check(self.o.lib.hmb200_prepared_set_tz(self.h, extra.ctypes.data, pic_wh[0], pic_wh[1], max_cu, search_range))
 
     def run(self, cur_plane, ref_plane):
         self.o._check(self.o.lib.hmb200_run_prepared(self.h, cur_plane, ref_plane))

@@ -15,6 +15,7 @@
 #include "hmb200_search8_cu.cuh"
 #include "hmb200_search16_cu.cuh"
 #include "hmb200_frac.cuh"
+#include "hmb200_tz.cuh"
 
 using namespace hmb200;
 
@@ -161,6 +162,8 @@ struct hmb200_prepared {
   Search8Schedule sched;          // tiled 8-bit kernel schedule (empty when not applicable)
   CuSchedule cu;                  // CU-fused bundles (PUs of one CU sharing window and predictor)
   FracSchedule frac;              // tile tables of the batched quarter-pel refinement
+  hmb200_tz_extra* d_tz = nullptr;    // HMB200_FLAG_TZ: per-PU CU geometry / 2Nx2N integer MV
+  TzParams tz{0, 0, 0, 0};
 };
 
 extern "C" {
@@ -541,7 +544,7 @@ hmb200_prepared* hmb200_prepare_jobs(const hmb200_pu_job* jobs, int njobs, int f
       hmb200_free_prepared(p); return nullptr;
     }
     std::string why;
-    if (bit_depth >= 8 && bit_depth <= 14) {
+    if (!(flags & HMB200_FLAG_TZ) && bit_depth >= 8 && bit_depth <= 14) {
       // 8-bit: per-PU tiles + CU-fused bundles; 9..14-bit: CU-fused bundles (packed 16x2 arithmetic), the rest generic
       const int bps = bit_depth > 8 ? 2 : 1;
       std::vector<char> bundled;
@@ -567,6 +570,7 @@ void hmb200_free_prepared(hmb200_prepared* p) {
   search8_free_schedule(&p->sched);
   cu_free_schedule(&p->cu);
   frac_free_schedule(&p->frac);
+  if (p->d_tz) cudaFree(p->d_tz);
   delete p;
 }
 
@@ -575,6 +579,44 @@ int hmb200_prepared_work(const hmb200_prepared* p, uint64_t* cand_sads, uint64_t
   if (cand_sads) *cand_sads = p->cand_sads;
   if (abs_diffs) *abs_diffs = p->abs_diffs;
   return HMB200_OK;
+}
+
+void hmb200_canonical_tz_extra(const hmb200_pu_job* jobs, int njobs, hmb200_tz_extra* extra) {
+  for (int i = 0; i < njobs; i++) {
+    const int s = std::max(jobs[i].w, jobs[i].h);
+    hmb200_tz_extra e{};
+    e.cu_x = jobs[i].pu_x - jobs[i].pu_x % s;
+    e.cu_y = jobs[i].pu_y - jobs[i].pu_y % s;
+    extra[i] = e;
+  }
+}
+
+int hmb200_prepared_set_tz(hmb200_prepared* p, const hmb200_tz_extra* extra, int pic_w, int pic_h, int max_cu, int search_range) {
+  NEED_READY();
+  if (!p || !(p->flags & HMB200_FLAG_TZ)) return fail(HMB200_ERR_ARG, "hmb200_prepared_set_tz: the list was not prepared with HMB200_FLAG_TZ");
+  if ((p->n > 0 && !extra) || pic_w <= 0 || pic_h <= 0 || max_cu <= 0 || search_range < 1 || search_range > 4096)
+    return fail(HMB200_ERR_ARG, "hmb200_prepared_set_tz: bad arguments");
+  if (p->n > 0) {
+    if (!p->d_tz) CUDA_TRY(cudaMalloc((void**)&p->d_tz, (size_t)p->n * sizeof(hmb200_tz_extra)));
+    CUDA_TRY(cudaMemcpyAsync(p->d_tz, extra, (size_t)p->n * sizeof(hmb200_tz_extra), cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+  }
+  p->tz = TzParams{pic_w, pic_h, max_cu, search_range};
+  return HMB200_OK;
+}
+
+int hmb200_tz_jobs(int cur_plane, int ref_plane, const hmb200_pu_job* jobs, const hmb200_tz_extra* extra, int njobs,
+                   int pic_w, int pic_h, int max_cu, int search_range, int flags, hmb200_pu_result* results) {
+  NEED_READY();
+  Plane* pr = get_plane(ref_plane);
+  if (!pr) return fail(HMB200_ERR_ARG, "hmb200_tz_jobs: unknown reference plane");
+  hmb200_prepared* p = hmb200_prepare_jobs(jobs, njobs, flags | HMB200_FLAG_TZ, pr->d.bit_depth);
+  if (!p) return HMB200_ERR_ARG;
+  int rc = hmb200_prepared_set_tz(p, extra, pic_w, pic_h, max_cu, search_range);
+  if (rc == HMB200_OK) rc = hmb200_run_prepared(p, cur_plane, ref_plane);
+  if (rc == HMB200_OK) rc = hmb200_fetch_results(p, results);
+  hmb200_free_prepared(p);
+  return rc;
 }
 
 int hmb200_prepared_executed_work(const hmb200_prepared* p, uint64_t* abs_diffs_executed, uint64_t* pus_fused) {
@@ -596,7 +638,15 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
   const Search8Schedule& sc = p->sched;
   const CuSchedule& cu = p->cu;
   const int bps = pr->d.bytes_per_sample;
-  bool fast = pc->d.bytes_per_sample == bps && ((bps == 1 && (sc.n_jobs > 0 || cu.n_bundles > 0)) || (bps == 2 && cu.n_bundles > 0)) &&
+  if (p->flags & HMB200_FLAG_TZ) {
+    if (!p->d_tz) return fail(HMB200_ERR_STATE, "hmb200_run_prepared: HMB200_FLAG_TZ list without hmb200_prepared_set_tz");
+    if (pc->d.bytes_per_sample != bps) return fail(HMB200_ERR_ARG, "hmb200_run_prepared: TZ search needs planes of one sample size");
+    const int blocks = (p->n + TZ_WARPS - 1) / TZ_WARPS;
+    if (bps == 1) k_tz_search<uint8_t><<<blocks, TZ_WARPS * 32, 0, g.stream>>>(p->d_tasks, p->d_tz, p->d_results, p->n, pc->d, pr->d, p->tz);
+    else          k_tz_search<uint16_t><<<blocks, TZ_WARPS * 32, 0, g.stream>>>(p->d_tasks, p->d_tz, p->d_results, p->n, pc->d, pr->d, p->tz);
+    g.launches++;
+  }
+  bool fast = !(p->flags & HMB200_FLAG_TZ) && pc->d.bytes_per_sample == bps && ((bps == 1 && (sc.n_jobs > 0 || cu.n_bundles > 0)) || (bps == 2 && cu.n_bundles > 0)) &&
               cu.bps == bps && pc->d.margin_x % 16 == 0 && pr->d.margin_x % 16 == 0 && sc.d_keys != nullptr;
   if (fast) {
     // every staged byte must lie inside the padded buffers (the reference would read outside its planes too)
@@ -638,7 +688,7 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
     }
     k_search8_finalize<<<(sc.n_tasks + 255) / 256, 256, 0, g.stream>>>(p->d_tasks, sc.d_keys, p->d_results, sc.n_tasks);
     g.launches++;
-  } else {
+  } else if (!(p->flags & HMB200_FLAG_TZ)) {
     dispatch_generic(p->d_tasks, p->d_results, p->n, pc->d, pr->d, p->flags & ~HMB200_FLAG_FRAC, /*do_search=*/true, nullptr);
   }
   CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
