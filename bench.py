@@ -265,14 +265,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
 
-    from video_codecs_b200 import HMB200, FLAG_FEN, FLAG_HADME, FLAG_FRAC, RESULT_DTYPE
+    from video_codecs_b200 import HMB200, FLAG_FEN, FLAG_HADME, FLAG_FRAC, FLAG_TZ, RESULT_DTYPE
     hm = HMB200()
     hm.init(local)
-    flags = FLAG_FEN | FLAG_HADME | FLAG_FRAC
+    flags = FLAG_FEN | FLAG_HADME | FLAG_FRAC | (FLAG_TZ if args.search == "tz" else 0)
     frames = make_frames(rank)
     pairs = [(t + 1, t) for t in range(N_FRAMES - 1)]                       # (current, reference) = (t+1, t)
     jobs = hm.build_canonical_jobs(PIC_W, CODED_H, SEARCH_RANGE, LAMBDA_COST)
     prep = hm.prepare_jobs(jobs, flags, BIT_DEPTH)
+    if args.search == "tz":
+        prep.set_tz(hm.canonical_tz_extra(jobs), (PIC_W, CODED_H), SEARCH_RANGE)
     work = prep.work()
     margin = 80 if SEARCH_RANGE <= 64 else 144
     from video_codecs_b200 import synth as _synth
@@ -368,7 +370,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8" if BIT_DEPTH == 8 else "u16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "picture": f"{PIC_W}x{PIC_H} (coded {PIC_W}x{CODED_H})", "search_range": SEARCH_RANGE,
+            "config": {"workload": WORKLOAD if args.search == "full" else WORKLOAD.replace("fullsearch", "tzsearch"), "picture": f"{PIC_W}x{PIC_H} (coded {PIC_W}x{CODED_H})", "search_range": SEARCH_RANGE,
                        "pus_per_frame": int(len(jobs)), "pus_per_ctu": 593, "frame_pairs_per_step_per_gpu": 1,
                        "l2": "flushed between timed iterations (256 MiB write, untimed)", "mpixel_counts": f"{PIC_W}x{PIC_H} luma per step"},
             "cand_sad_per_s": world * work["cand_sads"] / (ms_per_step / 1e3),
@@ -416,6 +418,7 @@ def main():
     ap.add_argument("--cpu-ctus", type=int, default=16, help="CTUs in the single-core cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--search", default="full", choices=["full", "tz"], help="tz: xTZSearch (FastSearch=1) instead of the full search")
     args = ap.parse_args()
     select_workload(args.workload)
     if args.impl == "reference":
