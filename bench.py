@@ -265,10 +265,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
 
-    from video_codecs_b200 import HMB200, FLAG_FEN, FLAG_HADME, FLAG_FRAC, FLAG_TZ, RESULT_DTYPE
+    from video_codecs_b200 import HMB200, FLAG_FEN, FLAG_HADME, FLAG_FRAC, FLAG_TZ, FLAG_TZ_STOP, RESULT_DTYPE
     hm = HMB200()
     hm.init(local)
-    flags = FLAG_FEN | FLAG_HADME | FLAG_FRAC | (FLAG_TZ if args.search == "tz" else 0)
+    flags = FLAG_FEN | FLAG_HADME | FLAG_FRAC | ((FLAG_TZ | FLAG_TZ_STOP) if args.search == "tz" else 0)
     frames = make_frames(rank)
     pairs = [(t + 1, t) for t in range(N_FRAMES - 1)]                       # (current, reference) = (t+1, t)
     jobs = hm.build_canonical_jobs(PIC_W, CODED_H, SEARCH_RANGE, LAMBDA_COST)

@@ -28,6 +28,7 @@ extern "C" {
 #define HMB200_FLAG_HADME    2   /* getUseHADME(): sub-pel refinement uses xGetHADs (TComRdCost.cpp:355-374)           */
 #define HMB200_FLAG_FRAC     4   /* also run the quarter-pel refinement (xPatternSearchFracDIF)                          */
 #define HMB200_FLAG_TZ       8   /* integer search = xTZSearch (FastSearch = 1) instead of the full search                */
+#define HMB200_FLAG_TZ_STOP 16   /* getFastMEAssumingSmootherMVEnabled(): first search stops after 3 idle diamonds (TEncSearch.cpp:304,3962) */
 
 /* ---- distortion function families, the rows of m_afpDistortFunc (TLibCommon/TypeDef.h:334-378) ---- */
 #define HMB200_DF_SAD        0   /* DF_SAD*  : xGetSAD4..64/12/24/48 honouring iSubShift (TComRdCost.cpp:489-953) */
@@ -177,6 +178,14 @@ int  hmb200_dist_batch(int func, int bit_depth, int n, const hmb200_dist_desc* d
 int  hmb200_pattern_search(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride,
                            hmb200_mv lt, hmb200_mv rb, const hmb200_cost_state* cs, int flags,
                            hmb200_mv* mv_out, uint32_t* sad_out);
+/* TEncSearch::xPatternSearchFast -> xTZSearch (TLibEncoder/TEncSearch.cpp:3847-3875, 3881-4083) for m_iFastSearch == 1,
+ * one call = one reference call.  cs->pred is both the MV-cost predictor and the start vector (rcMv on entry);
+ * extra: owning CU position and pIntegerMv2Nx2NPred; pic_w/pic_h/max_cu: what clipMv reads from the SPS;
+ * search_range: m_iSearchRange.  flags: HMB200_FLAG_FEN | HMB200_FLAG_TZ_STOP.  (hmb200_tz_extra is declared further down.) */
+struct hmb200_tz_extra_s;
+int  hmb200_pattern_search_tz(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride, hmb200_mv lt, hmb200_mv rb,
+                              const hmb200_cost_state* cs, int flags, const struct hmb200_tz_extra_s* extra, int pic_w, int pic_h,
+                              int max_cu, int search_range, hmb200_mv* mv_out, uint32_t* sad_out);
 /* TEncSearch::xPatternSearchFracDIF(Bool bIsLosslessCoded, TComPattern*, Pel*, Int, TComMv* pcMvInt,
  * TComMv& rcMvHalf, TComMv& rcMvQter, Distortion& ruiCost)  (TEncSearch.h:421-430, .cpp:4240-4276).
  * flags: HMB200_FLAG_HADME. */
@@ -215,7 +224,7 @@ int  hmb200_prepared_work(const hmb200_prepared* p, uint64_t* cand_sads, uint64_
 
 /* What xTZSearch reads besides the PU job: the CU that owns the PU (pcCU->clipMv of the predictor and of the re-centred
  * raster range, TLibCommon/TComDataCU.cpp:2788-2801) and pIntegerMv2Nx2NPred (integer pel; TEncSearch.cpp:3926-3946). */
-typedef struct {
+typedef struct hmb200_tz_extra_s {
   int32_t cu_x, cu_y;
   int32_t has_imv, imv_x, imv_y;
   int32_t reserved[3];
@@ -224,7 +233,7 @@ typedef struct {
 /* cu_x / cu_y of canonical-list PUs (the aligned S x S CU with S = max(w, h)); has_imv = 0. */
 void hmb200_canonical_tz_extra(const hmb200_pu_job* jobs, int njobs, hmb200_tz_extra* extra);
 /* Turns a list prepared with HMB200_FLAG_TZ into a TZ search: TEncSearch::xTZSearch (TLibEncoder/TEncSearch.cpp:
- * 3881-4083) under TZ_SEARCH_CONFIGURATION (:297-313) with FastMEAssumingSmootherMV off; jobs[i].pred is the AMVP
+ * 3881-4083) under TZ_SEARCH_CONFIGURATION (:297-313) (HMB200_FLAG_TZ_STOP = FastMEAssumingSmootherMVEnabled); jobs[i].pred is the AMVP
  * predictor the search starts from (rcMv on entry), jobs[i].lt/rb the window of xSetSearchRange(pred),
  * search_range = m_iSearchRange.  hmb200_run_prepared then runs it (followed by the refinement with FLAG_FRAC). */
 int  hmb200_prepared_set_tz(hmb200_prepared* p, const hmb200_tz_extra* extra, int pic_w, int pic_h, int max_cu, int search_range);

@@ -27,10 +27,13 @@ DECLS = '''
 class TComPic;
 void hmb200_shim_ref_plane(TComPic* pic);
 bool hmb200_shim_pattern_search(TEncSearch* self, TComPattern* key, Pel* piRefY, Int iRefStride, TComMv* lt, TComMv* rb, TComMv& rcMv, Distortion& ruiSAD);
+class TComDataCU;
+bool hmb200_shim_pattern_search_fast(TEncSearch* self, TComDataCU* pcCU, TComPattern* key, Pel* piRefY, Int iRefStride, TComMv* lt, TComMv* rb, TComMv& rcMv, Distortion& ruiSAD, const TComMv* pIntegerMv2Nx2NPred);
 bool hmb200_shim_pattern_search_frac(TEncSearch* self, Bool lossless, TComPattern* key, Pel* piRefY, Int iRefStride, TComMv* mvInt, TComMv& rcMvHalf, TComMv& rcMvQter, Distortion& ruiCost);
 '''
 FWD_SEARCH = "  if (hmb200_shim_pattern_search(this, pcPatternKey, piRefY, iRefStride, pcMvSrchRngLT, pcMvSrchRngRB, rcMv, ruiSAD)) return;\n"
 FWD_FRAC = "  if (hmb200_shim_pattern_search_frac(this, bIsLosslessCoded, pcPatternKey, piRefY, iRefStride, pcMvInt, rcMvHalf, rcMvQter, ruiCost)) return;\n"
+FWD_FAST = "  if (hmb200_shim_pattern_search_fast(this, pcCU, pcPatternKey, piRefY, iRefStride, pcMvSrchRngLT, pcMvSrchRngRB, rcMv, ruiSAD, pIntegerMv2Nx2NPred)) return;\n"
 FWD_PLANE = "  hmb200_shim_ref_plane(pcCU->getSlice()->getRefPic( eRefPicList, iRefIdxPred ));\n"
 
 
@@ -49,6 +52,7 @@ def patched_source():
     src = src.replace(marker, marker + DECLS)
     src = inject_after_open_brace(src, "Void TEncSearch::xPatternSearch( TComPattern* pcPatternKey,", FWD_SEARCH)
     src = inject_after_open_brace(src, "Void TEncSearch::xPatternSearchFracDIF(", FWD_FRAC)
+    src = inject_after_open_brace(src, "Void TEncSearch::xPatternSearchFast( TComDataCU*   pcCU,", FWD_FAST)
     src = inject_after_open_brace(src, "Void TEncSearch::xMotionEstimation( TComDataCU* pcCU,", FWD_PLANE)
     return src
 

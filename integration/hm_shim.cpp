@@ -42,6 +42,7 @@
 #include "TLibCommon/TComRdCost.h"
 #include "TLibCommon/TComPic.h"
 #include "TLibCommon/TComPicYuv.h"
+#include "TLibCommon/TComDataCU.h"
 #undef private
 #undef protected
 
@@ -154,6 +155,48 @@ bool hmb200_shim_pattern_search(TEncSearch* self, TComPattern* key, Pel* piRefY,
   if (g_shim.log)
     fprintf(g_shim.log, "I %dx%d lt %d %d rb %d %d pred %d %d lam %u -> %d %d %u\n", p.width, p.height, l.x, l.y, r.x, r.y, cs.pred.x,
             cs.pred.y, cs.lambda_cost, mv.x, mv.y, sad);
+  rcMv.set((Short)mv.x, (Short)mv.y);
+  ruiSAD = sad;
+  return true;
+}
+
+// TEncSearch::xPatternSearchFast -> xTZSearch (TLibEncoder/TEncSearch.cpp:3847-3875, 3881-4083), FastSearch = 1 only;
+// any other fast-search mode keeps the reference body.
+bool hmb200_shim_pattern_search_fast(TEncSearch* self, TComDataCU* pcCU, TComPattern* key, Pel* piRefY, Int iRefStride, TComMv* lt,
+                                     TComMv* rb, TComMv& rcMv, Distortion& ruiSAD, const TComMv* pIntegerMv2Nx2NPred) {
+  if (!active()) return false;
+  if (self->m_iFastSearch != 1) return false;
+  if (self->m_cDistParam.bApplyWeight) { fprintf(stderr, "hmb200 shim: weighted prediction is out of scope\n"); abort(); }
+  const hmb200_pattern p = pattern_of(key);
+  const hmb200_cost_state cs = cost_state(self->m_pcRdCost);
+  if (cs.pred.x != rcMv.getHor() || cs.pred.y != rcMv.getVer()) return false;      // start vector != cost predictor: not the xMotionEstimation call
+  hmb200_tz_extra ex;
+  memset(&ex, 0, sizeof(ex));
+  ex.cu_x = (int)pcCU->getCUPelX(); ex.cu_y = (int)pcCU->getCUPelY();
+  if (pIntegerMv2Nx2NPred) { ex.has_imv = 1; ex.imv_x = pIntegerMv2Nx2NPred->getHor(); ex.imv_y = pIntegerMv2Nx2NPred->getVer(); }
+  const TComSPS& sps = *pcCU->getSlice()->getSPS();
+  hmb200_mv l = {lt->getHor(), lt->getVer()}, r = {rb->getHor(), rb->getVer()}, mv;
+  uint32_t sad = 0;
+  const int flags = (self->m_pcEncCfg->getUseFastEnc() ? HMB200_FLAG_FEN : 0) |
+                    (self->m_pcEncCfg->getFastMEAssumingSmootherMVEnabled() ? HMB200_FLAG_TZ_STOP : 0);
+  if (hmb200_pattern_search_tz(&p, piRefY, iRefStride, l, r, &cs, flags, &ex, (int)sps.getPicWidthInLumaSamples(),
+                               (int)sps.getPicHeightInLumaSamples(), (int)sps.getMaxCUWidth(), self->m_iSearchRange, &mv, &sad) != HMB200_OK)
+    die("hmb200_pattern_search_tz");
+  g_shim.n_search++;
+  if (g_shim.mode == VERIFY) {
+    TComMv ref_mv = rcMv; Distortion ref_sad = 0;
+    g_shim.in_reference = true;
+    self->xPatternSearchFast(pcCU, key, piRefY, iRefStride, lt, rb, ref_mv, ref_sad, pIntegerMv2Nx2NPred);
+    g_shim.in_reference = false;
+    if (ref_mv.getHor() != mv.x || ref_mv.getVer() != mv.y || ref_sad != sad) {
+      fprintf(stderr, "hmb200 shim: xTZSearch mismatch %dx%d: gpu (%d,%d) %u, reference (%d,%d) %u\n", p.width, p.height, mv.x, mv.y, sad,
+              ref_mv.getHor(), ref_mv.getVer(), (unsigned)ref_sad);
+      abort();
+    }
+  }
+  if (g_shim.log)
+    fprintf(g_shim.log, "T %dx%d lt %d %d rb %d %d pred %d %d lam %u -> %d %d %u\n", p.width, p.height, l.x, l.y, r.x, r.y, cs.pred.x, cs.pred.y,
+            cs.lambda_cost, mv.x, mv.y, sad);
   rcMv.set((Short)mv.x, (Short)mv.y);
   ruiSAD = sad;
   return true;

@@ -189,7 +189,9 @@ void hmo_pattern_search(const int16_t* org, int so, int w, int h, int bit_depth,
  *
  * Restated as "evaluate an ordered list of points, keep the first minimum": every stage of the reference issues
  * xTZSearchHelp calls whose positions depend only on the stage's start point, so the sequential strict-'<' updates
- * equal taking the first minimal cost in call order.  uiBestRound is only read by the two stop criteria that are off. */
+ * equal taking the first minimal cost in call order.  uiBestRound (diamond calls since the last improvement) is only
+ * read by the first search's stop criterion, bFirstSearchStop = FastMEAssumingSmootherMVEnabled (on by default in
+ * TAppEncCfg.cpp:808): the first search ends after uiFirstSearchRounds = 3 diamonds in a row without improvement. */
 typedef struct { uint32_t cost; int x, y, dist, nr; } tz_state;
 typedef struct { int x, y, nr, dist; } tz_point;
 
@@ -198,11 +200,12 @@ typedef struct {
   uint32_t lambda_cost; int pred_x, pred_y;
 } tz_ctx;
 
-static void tz_try(const tz_ctx* c, tz_state* st, int x, int y, int nr, int dist)
+static int tz_try(const tz_ctx* c, tz_state* st, int x, int y, int nr, int dist)
 {
   uint32_t cost = hmo_sad(c->org, c->so, c->ref + y * c->sr + x, c->sr, c->w, c->h, c->bit_depth, c->sub)
                 + hmo_mv_cost(c->lambda_cost, hmo_mv_bits(x, y, c->pred_x, c->pred_y, 2));
-  if (cost < st->cost) { st->cost = cost; st->x = x; st->y = y; st->dist = dist; st->nr = nr; }
+  if (cost < st->cost) { st->cost = cost; st->x = x; st->y = y; st->dist = dist; st->nr = nr; return 1; }
+  return 0;
 }
 
 /* the points one diamond call visits, in call order; L/T/R/B = search range (inclusive).  Returns the count. */
@@ -264,7 +267,7 @@ static void tz_two_point(const tz_ctx* c, tz_state* st, int L, int T, int R, int
  * xSetSearchRange(pred); the CU geometry feeds clipMv (TLibCommon/TComDataCU.cpp:2788-2801); has_imv: pIntegerMv2Nx2NPred. */
 void hmo_tz_search(const int16_t* org, int so, int w, int h, int bit_depth, const int16_t* ref_at_pu, int sr,
                    int lt_x, int lt_y, int rb_x, int rb_y, uint32_t lambda_cost, int pred_x, int pred_y, int fen,
-                   int cu_x, int cu_y, int pic_w, int pic_h, int max_cu, int search_range,
+                   int cu_x, int cu_y, int pic_w, int pic_h, int max_cu, int search_range, int first_search_stop,
                    int has_imv, int imv_x, int imv_y, int* mv_x, int* mv_y, uint32_t* sad_out)
 {
   tz_ctx c = { org, so, ref_at_pu, sr, w, h, bit_depth, (fen && h > 8) ? 1 : 0, lambda_cost, pred_x, pred_y };
@@ -286,10 +289,13 @@ void hmo_tz_search(const int16_t* org, int so, int w, int h, int bit_depth, cons
   }
 
   const int start_x = st.x, start_y = st.y;
+  int rounds = 0;                                             /* uiBestRound: 0 after the start candidates (:3908 always improves) */
   for (int d = 1; d <= search_range; d *= 2)                  /* first search: every diamond around the same start */
   {
     int n = tz_diamond(start_x, start_y, d, lt_x, lt_y, rb_x, rb_y, pts);
-    for (int i = 0; i < n; i++) tz_try(&c, &st, pts[i].x, pts[i].y, pts[i].nr, pts[i].dist);
+    rounds++;
+    for (int i = 0; i < n; i++) if (tz_try(&c, &st, pts[i].x, pts[i].y, pts[i].nr, pts[i].dist)) rounds = 0;
+    if (first_search_stop && rounds >= 3) break;              /* :3962 bFirstSearchStop, uiFirstSearchRounds = 3 */
   }
   if (st.dist == 1) { st.dist = 0; tz_two_point(&c, &st, lt_x, lt_y, rb_x, rb_y); }
   if (st.dist > 5)                                            /* raster search, step iRaster = 5 */

@@ -113,15 +113,17 @@ class Oracle(_Base):
     def extend_border(self, plane, origin_off, stride, w, h, mx, my):
         self.lib.hmo_extend_border(_ptr(plane, origin_off), stride, w, h, mx, my)
 
-    def tz_search(self, org, w, h, ref, lt, rb, lambda_cost, pred, cu_xy, pic_wh, search_range=64, imv=None, bit_depth=8, max_cu=64):
-        """xTZSearch (FastSearch=1).  imv: pIntegerMv2Nx2NPred (integer pel) or None."""
+    def tz_search(self, org, w, h, ref, lt, rb, lambda_cost, pred, cu_xy, pic_wh, search_range=64, imv=None, bit_depth=8, max_cu=64,
+                  first_search_stop=1):
+        """xTZSearch (FastSearch=1).  imv: pIntegerMv2Nx2NPred (integer pel) or None; first_search_stop:
+        FastMEAssumingSmootherMVEnabled (the encoder's default is on)."""
         (oa, oo, os_), (ra, ro, rs) = org, ref
         mx, my, sad = C.c_int(), C.c_int(), C.c_uint32()
         f = self.lib.hmo_tz_search
         f.restype = None
-        f.argtypes = [_p16, C.c_int, C.c_int, C.c_int, C.c_int, _p16, C.c_int] + [C.c_int] * 4 + [C.c_uint32] + [C.c_int] * 12 + [_pi, _pi, _pu]
+        f.argtypes = [_p16, C.c_int, C.c_int, C.c_int, C.c_int, _p16, C.c_int] + [C.c_int] * 4 + [C.c_uint32] + [C.c_int] * 13 + [_pi, _pi, _pu]
         f(_ptr(oa, oo), os_, w, h, bit_depth, _ptr(ra, ro), rs, lt[0], lt[1], rb[0], rb[1], int(lambda_cost), pred[0], pred[1],
-          self.fen, cu_xy[0], cu_xy[1], pic_wh[0], pic_wh[1], max_cu, search_range,
+          self.fen, cu_xy[0], cu_xy[1], pic_wh[0], pic_wh[1], max_cu, search_range, int(first_search_stop),
           0 if imv is None else 1, 0 if imv is None else imv[0], 0 if imv is None else imv[1], C.byref(mx), C.byref(my), C.byref(sad))
         return (mx.value, my.value), sad.value
 
@@ -208,14 +210,15 @@ class Reference(_Base):
                                            *[C.byref(x) for x in v], C.byref(cost))
         return (v[0].value, v[1].value), (v[2].value, v[3].value), cost.value
 
-    def tz_search(self, org, w, h, ref, lt, rb, lambda_cost, pred, cu_xy, pic_wh, search_range=64, imv=None, bit_depth=8, max_cu=64):
+    def tz_search(self, org, w, h, ref, lt, rb, lambda_cost, pred, cu_xy, pic_wh, search_range=64, imv=None, bit_depth=8, max_cu=64,
+                  first_search_stop=1):
         (oa, oo, os_), (ra, ro, rs) = org, ref
         mx, my, sad = C.c_int(), C.c_int(), C.c_uint32()
         f = self.lib.hmref_tz_search
         f.restype = None
-        f.argtypes = [C.c_void_p, _p16, C.c_int, C.c_int, C.c_int, C.c_int, _p16, C.c_int] + [C.c_int] * 4 + [C.c_uint32] + [C.c_int] * 11 + [_pi, _pi, _pu]
+        f.argtypes = [C.c_void_p, _p16, C.c_int, C.c_int, C.c_int, C.c_int, _p16, C.c_int] + [C.c_int] * 4 + [C.c_uint32] + [C.c_int] * 12 + [_pi, _pi, _pu]
         f(self.h, _ptr(oa, oo), os_, w, h, bit_depth, _ptr(ra, ro), rs, lt[0], lt[1], rb[0], rb[1], int(lambda_cost), pred[0], pred[1],
-          cu_xy[0], cu_xy[1], pic_wh[0], pic_wh[1], max_cu, search_range,
+          cu_xy[0], cu_xy[1], pic_wh[0], pic_wh[1], max_cu, search_range, int(first_search_stop),
           0 if imv is None else 1, 0 if imv is None else imv[0], 0 if imv is None else imv[1], C.byref(mx), C.byref(my), C.byref(sad))
         return (mx.value, my.value), sad.value
 

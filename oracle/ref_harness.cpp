@@ -113,7 +113,7 @@ struct Harness : public TEncSearch
   TComDataCU cu;
   void tz(Pel* org, int orgStride, int w, int h, int bitDepth, Pel* refAtPu, int refStride,
           int ltx, int lty, int rbx, int rby, uint32_t uiCost, int predx, int predy,
-          int cux, int cuy, int picw, int pich, int maxcu, int searchRange, int hasImv, int imvx, int imvy,
+          int cux, int cuy, int picw, int pich, int maxcu, int searchRange, int firstSearchStop, int hasImv, int imvx, int imvy,
           int* mvx, int* mvy, uint32_t* sad)
   {
     sps.setPicWidthInLumaSamples(picw); sps.setPicHeightInLumaSamples(pich);
@@ -121,7 +121,7 @@ struct Harness : public TEncSearch
     slice.setSPS(&sps);
     cu.m_pcSlice = &slice; cu.m_uiCUPelX = cux; cu.m_uiCUPelY = cuy;
     cfg.setFastSearch(1);
-    cfg.setFastMEAssumingSmootherMVEnabled(false);
+    cfg.setFastMEAssumingSmootherMVEnabled(firstSearchStop != 0);
     m_iFastSearch = 1;
     m_iSearchRange = searchRange;
     TComPattern pat;
@@ -231,11 +231,11 @@ double hmref_run_jobs(void* hv, const int16_t* cur0, int cur_stride, const int16
 void hmref_tz_search(void* hv, const int16_t* org, int org_stride, int w, int h, int bit_depth,
                      const int16_t* ref_at_pu, int ref_stride, int lt_x, int lt_y, int rb_x, int rb_y,
                      uint32_t ui_cost, int pred_x, int pred_y, int cu_x, int cu_y, int pic_w, int pic_h, int max_cu,
-                     int search_range, int has_imv, int imv_x, int imv_y, int* mv_x, int* mv_y, uint32_t* sad)
+                     int search_range, int first_search_stop, int has_imv, int imv_x, int imv_y, int* mv_x, int* mv_y, uint32_t* sad)
 {
   static_cast<Harness*>(hv)->tz(const_cast<Pel*>(org), org_stride, w, h, bit_depth, const_cast<Pel*>(ref_at_pu), ref_stride,
                                 lt_x, lt_y, rb_x, rb_y, ui_cost, pred_x, pred_y, cu_x, cu_y, pic_w, pic_h, max_cu, search_range,
-                                has_imv, imv_x, imv_y, mv_x, mv_y, sad);
+                                first_search_stop, has_imv, imv_x, imv_y, mv_x, mv_y, sad);
 }
 
 // TVideoIOYuv::open + read (TLibVideoIO/TVideoIOYuv.cpp:118-245, 680-741) on a planar 4:0:0 file: returns the luma

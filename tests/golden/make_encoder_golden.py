@@ -57,9 +57,32 @@ def args_1080p(cfg, yuv, frames, out_bin):
             "--SearchRange=64", "--SEIDecodedPictureHash=1", "--ConformanceWindowMode=1", "-b", out_bin, "-o", ""]
 
 
+def golden_tz():
+    """The cfg's own FastSearch = 1 (TZ search): 416x240 x 8 frames and 1920x1080 x 3 frames of the stock encoder."""
+    out = {}
+    for tag, (w, h, frames, extra) in {"416x240": (W, H, 8, []), "1080p": (1920, 1080, 3, ["--ConformanceWindowMode=1"])}.items():
+        yuv, binf = f"/tmp/hmgold_tz_{tag}.yuv", f"/tmp/hmgold_tz_{tag}.bin"
+        synth.write_yuv420(yuv, [synth.luma_frame(w, h, t, seed=77) for t in range(frames)], 8)
+        args = args_tz(CFG, yuv, w, h, frames, binf) + extra
+        t0 = time.time()
+        p = subprocess.run([ENC] + args, capture_output=True, text=True, check=True)
+        out[tag] = {"bitstream_md5": hashlib.md5(open(binf, "rb").read()).hexdigest(), "bitstream_bytes": os.path.getsize(binf),
+                    "picture_md5": parse_md5_lines(p.stdout), "cpu_seconds": round(time.time() - t0, 1), "frames": frames,
+                    "yuv_md5": hashlib.md5(open(yuv, "rb").read()).hexdigest(), "extra_args": extra}
+        print(tag, out[tag]["bitstream_md5"], out[tag]["cpu_seconds"], flush=True)
+    json.dump(out, open(os.path.join(ROOT, "tests", "golden", "encoder_md5_tz.json"), "w"), indent=1)
+
+
+def args_tz(cfg, yuv, w, h, frames, out_bin):
+    return ["-c", cfg, "-i", yuv, "-wdt", str(w), "-hgt", str(h), "-fr", "30", "-f", str(frames), "--FastSearch=1",
+            "--SearchRange=64", "--SEIDecodedPictureHash=1", "-b", out_bin, "-o", ""]
+
+
 def main():
     if "--1080p" in sys.argv:
         return golden_1080p()
+    if "--tz" in sys.argv:
+        return golden_tz()
     out = {}
     for frames in (3, 8):
         yuv, binf = f"/tmp/hmgold_{frames}.yuv", f"/tmp/hmgold_{frames}.bin"

@@ -149,16 +149,21 @@ def make_tz_golden():
     f0, f1 = synth.luma_frame(T.W, T.H, 0, seed=17), synth.luma_frame(T.W, T.H, 3, seed=17)
     cur, o0, stride = padded(f1)
     ref, _, _ = padded(f0)
-    cases, exp = [], []
+    cases, exp, exp0 = [], [], []
     for (px, py, w, h, cu_x, cu_y, pred, lam, sr, imv) in T.make_cases(np.random.default_rng(7), 300):
         lt_rb = O.search_range(pred, sr, (cu_x, cu_y), (T.W, T.H))
         off = o0 + py * stride + px
-        mv, sad = ref_impl.tz_search((cur, off, stride), w, h, (ref, off, stride), lt_rb[:2], lt_rb[2:], lam, pred, (cu_x, cu_y), (T.W, T.H), sr, imv)
+        mv, sad = ref_impl.tz_search((cur, off, stride), w, h, (ref, off, stride), lt_rb[:2], lt_rb[2:], lam, pred, (cu_x, cu_y), (T.W, T.H), sr, imv,
+                                     first_search_stop=1)
+        mv0, sad0 = ref_impl.tz_search((cur, off, stride), w, h, (ref, off, stride), lt_rb[:2], lt_rb[2:], lam, pred, (cu_x, cu_y), (T.W, T.H), sr,
+                                       imv, first_search_stop=0)
+        exp0.append((mv0[0], mv0[1], sad0))
         cases.append((px, py, w, h, cu_x, cu_y, pred[0], pred[1], lam, sr, 0 if imv is None else 1, 0 if imv is None else imv[0],
                       0 if imv is None else imv[1]) + tuple(lt_rb))
         exp.append((mv[0], mv[1], sad))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "tz_golden.npz"), frame0=f0, frame1=f1,
-                        cases=np.array(cases, dtype=np.int64), expected=np.array(exp, dtype=np.int64))
+                        cases=np.array(cases, dtype=np.int64), expected_stop1=np.array(exp, dtype=np.int64),
+                        expected_stop0=np.array(exp0, dtype=np.int64))
     print("wrote tz_golden.npz", len(cases))
 
 

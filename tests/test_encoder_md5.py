@@ -60,3 +60,23 @@ def test_encoder_bitstream_md5_1080p_prefix(tmp_path):
     assert p.returncode == 0, p.stderr[-2000:]
     assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
     assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,mode", [("416x240", "verify"), ("1080p", "gpu")])
+def test_encoder_bitstream_md5_tz_search(tmp_path, tag, mode):
+    """The configuration file's own FastSearch = 1: every xPatternSearchFast (xTZSearch), bi-pred xPatternSearch and
+    xPatternSearchFracDIF call goes through libhmb200; the bitstream must equal the stock encoder's."""
+    _need_binary()
+    from video_codecs_b200 import synth
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "encoder_md5_tz.json")))[tag]
+    w, h = (416, 240) if tag == "416x240" else (1920, 1080)
+    yuv, binf = str(tmp_path / "clip.yuv"), str(tmp_path / "out.bin")
+    synth.write_yuv420(yuv, [synth.luma_frame(w, h, t, seed=77) for t in range(gold["frames"])], 8)
+    assert hashlib.md5(open(yuv, "rb").read()).hexdigest() == gold["yuv_md5"]
+    p = subprocess.run([BIN] + meg.args_tz(CFG, yuv, w, h, gold["frames"], binf) + gold["extra_args"], capture_output=True, text=True,
+                       env=dict(os.environ, HMB200_SHIM=mode), timeout=3000)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "integer searches" in p.stderr and " 0 integer searches" not in p.stderr
+    assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
+    assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]

@@ -6,7 +6,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-FLAG_FEN, FLAG_HADME, FLAG_FRAC, FLAG_TZ = 1, 2, 4, 8
+FLAG_FEN, FLAG_HADME, FLAG_FRAC, FLAG_TZ, FLAG_TZ_STOP = 1, 2, 4, 8, 16
 DF_SAD, DF_SSE, DF_HADS, DF_SADS = 0, 1, 2, 3
 PLANE_ORG, PLANE_REC = 0, 1
 
@@ -74,6 +74,8 @@ def _load():
         "hmb200_dist_batch": (i32, [i32, i32, i32, vp, vp]),
         "hmb200_pattern_search": (i32, [C.POINTER(_Pattern), vp, i32, _Mv, _Mv, C.POINTER(_CostState), i32,
                                         C.POINTER(_Mv), C.POINTER(u32)]),
+        "hmb200_pattern_search_tz": (i32, [C.POINTER(_Pattern), vp, i32, _Mv, _Mv, C.POINTER(_CostState), i32, vp, i32, i32, i32, i32,
+                                           C.POINTER(_Mv), C.POINTER(u32)]),
         "hmb200_pattern_search_frac": (i32, [i32, C.POINTER(_Pattern), vp, i32, _Mv, C.POINTER(_CostState), i32,
                                              C.POINTER(_Mv), C.POINTER(_Mv), C.POINTER(u32)]),
         "hmb200_me_jobs": (i32, [i32, i32, vp, i32, i32, vp]),
@@ -203,6 +205,19 @@ class HMB200:
         mv, sad = _Mv(), C.c_uint32()
         self._check(self.lib.hmb200_pattern_search(C.byref(key), _addr(ra, ro), rs, _Mv(*lt), _Mv(*rb), C.byref(cs), flags,
                                                    C.byref(mv), C.byref(sad)))
+        return (mv.x, mv.y), sad.value
+
+    def pattern_search_tz(self, org, w, h, ref, lt, rb, lambda_cost, pred, cu_xy, pic_wh, search_range=64, imv=None, bit_depth=8,
+                          flags=FLAG_FEN, max_cu=64):
+        (oa, oo, os_), (ra, ro, rs) = org, ref
+        key = _Pattern(_addr(oa, oo), w, h, os_, bit_depth)
+        cs = _CostState(int(lambda_cost), _Mv(*pred))
+        extra = np.zeros(1, dtype=TZ_EXTRA_DTYPE)
+        extra[0] = (cu_xy[0], cu_xy[1], 0 if imv is None else 1, 0 if imv is None else imv[0], 0 if imv is None else imv[1], (0, 0, 0))
+        mv, sad = _Mv(), C.c_uint32()
+        self._check(self.lib.hmb200_pattern_search_tz(C.byref(key), _addr(ra, ro), rs, _Mv(*lt), _Mv(*rb), C.byref(cs), flags,
+                                                      extra.ctypes.data, pic_wh[0], pic_wh[1], max_cu, search_range,
+                                                      C.byref(mv), C.byref(sad)))
         return (mv.x, mv.y), sad.value
 
     def pattern_search_frac(self, org, w, h, ref, mv_int, lambda_cost, pred, bit_depth=8, flags=FLAG_HADME, lossless=0):

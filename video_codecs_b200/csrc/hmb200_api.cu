@@ -163,7 +163,7 @@ struct hmb200_prepared {
   CuSchedule cu;                  // CU-fused bundles (PUs of one CU sharing window and predictor)
   FracSchedule frac;              // tile tables of the batched quarter-pel refinement
   hmb200_tz_extra* d_tz = nullptr;    // HMB200_FLAG_TZ: per-PU CU geometry / 2Nx2N integer MV
-  TzParams tz{0, 0, 0, 0};
+  TzParams tz{0, 0, 0, 0, 0};
 };
 
 extern "C" {
@@ -601,7 +601,7 @@ int hmb200_prepared_set_tz(hmb200_prepared* p, const hmb200_tz_extra* extra, int
     CUDA_TRY(cudaMemcpyAsync(p->d_tz, extra, (size_t)p->n * sizeof(hmb200_tz_extra), cudaMemcpyHostToDevice, g.stream));
     CUDA_TRY(cudaStreamSynchronize(g.stream));
   }
-  p->tz = TzParams{pic_w, pic_h, max_cu, search_range};
+  p->tz = TzParams{pic_w, pic_h, max_cu, search_range, (p->flags & HMB200_FLAG_TZ_STOP) ? 1 : 0};
   return HMB200_OK;
 }
 
@@ -642,8 +642,8 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
     if (!p->d_tz) return fail(HMB200_ERR_STATE, "hmb200_run_prepared: HMB200_FLAG_TZ list without hmb200_prepared_set_tz");
     if (pc->d.bytes_per_sample != bps) return fail(HMB200_ERR_ARG, "hmb200_run_prepared: TZ search needs planes of one sample size");
     const int blocks = (p->n + TZ_WARPS - 1) / TZ_WARPS;
-    if (bps == 1) k_tz_search<uint8_t><<<blocks, TZ_WARPS * 32, 0, g.stream>>>(p->d_tasks, p->d_tz, p->d_results, p->n, pc->d, pr->d, p->tz);
-    else          k_tz_search<uint16_t><<<blocks, TZ_WARPS * 32, 0, g.stream>>>(p->d_tasks, p->d_tz, p->d_results, p->n, pc->d, pr->d, p->tz);
+    if (bps == 1) k_tz_search<uint8_t, uint8_t><<<blocks, TZ_WARPS * 32, 0, g.stream>>>(p->d_tasks, p->d_tz, p->d_results, p->n, pc->d, pr->d, p->tz);
+    else          k_tz_search<int16_t, int16_t><<<blocks, TZ_WARPS * 32, 0, g.stream>>>(p->d_tasks, p->d_tz, p->d_results, p->n, pc->d, pr->d, p->tz);
     g.launches++;
   }
   bool fast = !(p->flags & HMB200_FLAG_TZ) && pc->d.bytes_per_sample == bps && ((bps == 1 && (sc.n_jobs > 0 || cu.n_bundles > 0)) || (bps == 2 && cu.n_bundles > 0)) &&
@@ -805,6 +805,41 @@ int hmb200_pattern_search(const hmb200_pattern* key, const int16_t* ref_at_pu, i
   hmb200_pu_result r{};
   int rc = run_single(key, ref_at_pu, t, flags & ~HMB200_FLAG_FRAC, true, &r);
   if (rc != HMB200_OK) return rc;
+  mv_out->x = r.mv_x; mv_out->y = r.mv_y; *sad_out = r.sad;
+  return HMB200_OK;
+}
+
+int hmb200_pattern_search_tz(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride, hmb200_mv lt, hmb200_mv rb,
+                             const hmb200_cost_state* cs, int flags, const hmb200_tz_extra* extra, int pic_w, int pic_h, int max_cu,
+                             int search_range, hmb200_mv* mv_out, uint32_t* sad_out) {
+  NEED_READY();
+  (void)ref_stride;
+  if (!key || !cs || !extra || !mv_out || !sad_out || rb.x < lt.x || rb.y < lt.y || search_range < 1)
+    return fail(HMB200_ERR_ARG, "hmb200_pattern_search_tz: bad arguments");
+  int rx, ry;
+  Plane* pr = find_plane_by_host(ref_at_pu, &rx, &ry);
+  if (!pr) return fail(HMB200_ERR_ARG, "reference pointer does not fall into a registered plane");
+  if (pr->d.bit_depth != key->bit_depth) return fail(HMB200_ERR_ARG, "pattern bit depth differs from the reference plane");
+  int rc = upload_pattern(key);
+  if (rc != HMB200_OK) return rc;
+  SearchTask t{};
+  t.org_x = 0; t.org_y = 0; t.ref_x = rx; t.ref_y = ry; t.w = key->width; t.h = key->height;
+  t.lt_x = lt.x; t.lt_y = lt.y; t.rb_x = rb.x; t.rb_y = rb.y; t.pred_x = cs->pred.x; t.pred_y = cs->pred.y;
+  t.lambda_cost = cs->lambda_cost;
+  t.sub_shift = ((flags & HMB200_FLAG_FEN) && key->height > 8) ? 1 : 0;
+  // one staging record: [SearchTask | tz_extra | result]
+  struct Rec { SearchTask t; hmb200_tz_extra e; hmb200_pu_result r; } rec{t, *extra, hmb200_pu_result{}};
+  if ((rc = ensure_dstage(sizeof(Rec) + 64)) != HMB200_OK) return rc;
+  Rec* d = reinterpret_cast<Rec*>(g.dstage);
+  CUDA_TRY(cudaMemcpyAsync(d, &rec, sizeof(rec), cudaMemcpyHostToDevice, g.stream));
+  const TzParams P{pic_w, pic_h, max_cu, search_range, (flags & HMB200_FLAG_TZ_STOP) ? 1 : 0};
+  if (pr->d.bytes_per_sample == 1) k_tz_search<uint8_t, int16_t><<<1, TZ_WARPS * 32, 0, g.stream>>>(&d->t, &d->e, &d->r, 1, g.pattern.d, pr->d, P);
+  else                             k_tz_search<int16_t, int16_t><<<1, TZ_WARPS * 32, 0, g.stream>>>(&d->t, &d->e, &d->r, 1, g.pattern.d, pr->d, P);
+  g.launches++;
+  hmb200_pu_result r{};
+  CUDA_TRY(cudaMemcpyAsync(&r, &d->r, sizeof(r), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
   mv_out->x = r.mv_x; mv_out->y = r.mv_y; *sad_out = r.sad;
   return HMB200_OK;
 }

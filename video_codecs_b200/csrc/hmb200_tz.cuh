@@ -8,8 +8,9 @@
 // from the padded plane through L1/L2 — a PU touches a few hundred scattered candidates, not a window worth staging),
 // then an ordered warp minimum (cost << 32 | position in call order) reproduces the sequential result.
 // A point is tested only against the window edges it moved towards — the rule behind every range check of the
-// reference's diamond and two-point code.  uiBestRound is only read by the two stop criteria the configuration
-// turns off (FastMEAssumingSmootherMV = 0, bStarRefinementStop = 0); the frontend rejects the other setting.
+// reference's diamond and two-point code.  uiBestRound (diamond calls since the last improvement) only feeds the first
+// search's stop criterion (bFirstSearchStop = FastMEAssumingSmootherMVEnabled, on by default): with it, the first three
+// diamonds (the earliest possible stop) are one batch with per-diamond minima, later diamonds go one at a time.
 #pragma once
 #include "hmb200_device.cuh"
 #include "hmb200_generic.cuh"
@@ -18,7 +19,7 @@ namespace hmb200 {
 
 constexpr int TZ_WARPS = 4;
 
-struct TzParams { int32_t pic_w, pic_h, max_cu, search_range; };
+struct TzParams { int32_t pic_w, pic_h, max_cu, search_range, first_stop; };
 
 // TComDataCU::clipMv (TLibCommon/TComDataCU.cpp:2788-2801), quarter-pel
 __device__ __forceinline__ void tz_clip_mv(int& x, int& y, int cu_x, int cu_y, const TzParams& P) {
@@ -77,11 +78,11 @@ __device__ __forceinline__ int tz_diamond_count(int search_range) {
 }
 
 // xGetSADnn with iSubShift (TComRdCost.cpp:489-953) at integer displacement (x, y) + getCost (TComRdCost.h:172-189)
-template <typename T>
+template <typename T, typename OrgT>
 __device__ __forceinline__ uint32_t tz_cost(const uint8_t* s_org, const T* ref0, int ref_pitch, const SearchTask& t, int bit_depth, int x, int y) {
   const int step = 1 << t.sub_shift, rows = t.h >> t.sub_shift;
   uint32_t sum = 0;
-  if constexpr (sizeof(T) == 1) {
+  if constexpr (sizeof(T) == 1 && sizeof(OrgT) == 1) {
     const int ww = t.w >> 2;
     for (int r = 0; r < rows; r++) {
       const uint32_t* ow = reinterpret_cast<const uint32_t*>(s_org + (r * step) * t.w);
@@ -96,7 +97,7 @@ __device__ __forceinline__ uint32_t tz_cost(const uint8_t* s_org, const T* ref0,
       }
     }
   } else {
-    const int16_t* so = reinterpret_cast<const int16_t*>(s_org);
+    const OrgT* so = reinterpret_cast<const OrgT*>(s_org);      // 16-bit planes, or a signed Pel pattern (1:1 entry)
     for (int r = 0; r < rows; r++) {
       const T* rr = ref0 + (ptrdiff_t)(y + r * step) * ref_pitch + x;
       for (int c = 0; c < t.w; c++) sum += (uint32_t)abs((int)so[(r * step) * t.w + c] - (int)rr[c]);
@@ -108,27 +109,29 @@ __device__ __forceinline__ uint32_t tz_cost(const uint8_t* s_org, const T* ref0,
 
 struct TzState { uint32_t cost; int x, y, dist, nr; };
 
-// lanes hold one candidate each (order = lane order); folds the warp's first minimum into the state (strict '<')
-__device__ __forceinline__ void tz_fold(TzState& st, bool valid, uint32_t cost, const TzPoint& p, int lane) {
+// lanes hold one candidate each (order = lane order); folds the warp's first minimum into the state (strict '<');
+// returns whether the state improved (warp-uniform)
+__device__ __forceinline__ bool tz_fold(TzState& st, bool valid, uint32_t cost, const TzPoint& p, int lane) {
   unsigned long long key = valid ? make_key(cost, (uint32_t)lane) : ~0ull;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
     key = other < key ? other : key;
   }
-  if (key == ~0ull) return;
+  if (key == ~0ull) return false;
   const uint32_t c = (uint32_t)(key >> 32);
   const int src = (int)(key & 31u);
   const int bx = __shfl_sync(0xffffffffu, p.x, src), by = __shfl_sync(0xffffffffu, p.y, src);
   const int bn = __shfl_sync(0xffffffffu, p.nr, src), bd = __shfl_sync(0xffffffffu, p.dist, src);
-  if (c < st.cost) { st.cost = c; st.x = bx; st.y = by; st.nr = bn; st.dist = bd; }
+  if (c < st.cost) { st.cost = c; st.x = bx; st.y = by; st.nr = bn; st.dist = bd; return true; }
+  return false;
 }
 
-template <typename T>
+template <typename T, typename OrgT>
 __global__ void __launch_bounds__(TZ_WARPS * 32)
 k_tz_search(const SearchTask* __restrict__ tasks, const hmb200_tz_extra* __restrict__ extra, hmb200_pu_result* __restrict__ out, int n,
             DevPlane cur_plane, DevPlane ref_plane, TzParams P) {
-  __shared__ __align__(16) uint8_t s_org_all[TZ_WARPS][64 * 64 * sizeof(T)];
+  __shared__ __align__(16) uint8_t s_org_all[TZ_WARPS][64 * 64 * sizeof(OrgT)];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pu = blockIdx.x * TZ_WARPS + warp;
   if (pu >= n) return;
@@ -136,8 +139,8 @@ k_tz_search(const SearchTask* __restrict__ tasks, const hmb200_tz_extra* __restr
   const hmb200_tz_extra ex = extra[pu];
   uint8_t* s_org = s_org_all[warp];
   {   // the PU's original block, row-major with stride w
-    const T* org = plane_at<T>(cur_plane, t.org_x, t.org_y);
-    T* so = reinterpret_cast<T*>(s_org);
+    const OrgT* org = plane_at<OrgT>(cur_plane, t.org_x, t.org_y);
+    OrgT* so = reinterpret_cast<OrgT*>(s_org);
     for (int i = lane; i < t.w * t.h; i += 32) { const int r = i / t.w, c = i - r * t.w; so[i] = org[(size_t)r * cur_plane.pitch + c]; }
   }
   __syncwarp();
@@ -157,7 +160,7 @@ k_tz_search(const SearchTask* __restrict__ tasks, const hmb200_tz_extra* __restr
     if (lane == 0) { p.x = sx >> 2; p.y = sy >> 2; p.valid = true; }
     if (lane == 1) { p.valid = true; }
     if (lane == 2 && ex.has_imv) { p.x = ix >> 2; p.y = iy >> 2; p.valid = true; }
-    const uint32_t c = p.valid ? tz_cost<T>(s_org, ref0, pitch, t, bd, p.x, p.y) : 0u;
+    const uint32_t c = p.valid ? tz_cost<T, OrgT>(s_org, ref0, pitch, t, bd, p.x, p.y) : 0u;
     tz_fold(st, p.valid, c, p, lane);
     if (ex.has_imv) {    // only the raster stage sees the range re-centred on the best start (:3935-3946)
       int cx = (int)(int16_t)(st.x << 2), cy = (int)(int16_t)(st.y << 2);
@@ -173,7 +176,7 @@ k_tz_search(const SearchTask* __restrict__ tasks, const hmb200_tz_extra* __restr
   auto diamonds = [&](int sx, int sy) {
     for (int base = 0; base < n_diamond; base += 32) {
       const TzPoint p = tz_diamond_point(base + lane, sx, sy, P.search_range, L, Tp, R, B);
-      const uint32_t c = p.valid ? tz_cost<T>(s_org, ref0, pitch, t, bd, p.x, p.y) : 0u;
+      const uint32_t c = p.valid ? tz_cost<T, OrgT>(s_org, ref0, pitch, t, bd, p.x, p.y) : 0u;
       tz_fold(st, p.valid, c, p, lane);
     }
   };
@@ -188,12 +191,40 @@ k_tz_search(const SearchTask* __restrict__ tasks, const hmb200_tz_extra* __restr
       p.y = st.y + (lane == 0 ? oy0[n8] : oy1[n8]);
       p.valid = tz_in_range(p.x, p.y, st.x, st.y, L, Tp, R, B);
     }
-    const uint32_t c = p.valid ? tz_cost<T>(s_org, ref0, pitch, t, bd, p.x, p.y) : 0u;
+    const uint32_t c = p.valid ? tz_cost<T, OrgT>(s_org, ref0, pitch, t, bd, p.x, p.y) : 0u;
     tz_fold(st, p.valid, c, p, lane);
   };
 
   // ---- first search, two-point completion, raster, star refinement (:3948-4078) ------------------------------------
-  diamonds(st.x, st.y);
+  if (!P.first_stop) diamonds(st.x, st.y);
+  else {
+    // :3949-3966 with bFirstSearchStop: stop after uiFirstSearchRounds = 3 diamonds in a row without improvement
+    const int sx = st.x, sy = st.y;
+    int rounds = 0;
+    {
+      const TzPoint p = tz_diamond_point(lane, sx, sy, P.search_range, L, Tp, R, B);      // d = 1, 2, 4: 4 + 8 + 8 points
+      const bool in_a = lane < 20 && p.valid;
+      const uint32_t c = in_a ? tz_cost<T, OrgT>(s_org, ref0, pitch, t, bd, p.x, p.y) : 0u;
+      const int k = lane < 4 ? 0 : (lane < 12 ? 1 : 2);
+#pragma unroll
+      for (int kk = 0; kk < 3; kk++) {
+        if ((1 << kk) <= P.search_range) {
+          const bool improved = tz_fold(st, in_a && k == kk, c, p, lane);
+          rounds = improved ? 0 : rounds + 1;
+        }
+      }
+    }
+    int base = 20;
+    for (int d = 8; d <= P.search_range && rounds < 3; d <<= 1) {
+      const int nd = d <= 8 ? 8 : 16;
+      TzPoint p{0, 0, 0, 0, false};
+      if (lane < nd) p = tz_diamond_point(base + lane, sx, sy, P.search_range, L, Tp, R, B);
+      const uint32_t c = p.valid ? tz_cost<T, OrgT>(s_org, ref0, pitch, t, bd, p.x, p.y) : 0u;
+      const bool improved = tz_fold(st, p.valid, c, p, lane);
+      rounds = improved ? 0 : rounds + 1;
+      base += nd;
+    }
+  }
   if (st.dist == 1) { st.dist = 0; two_point(); }
   if (st.dist > 5) {
     st.dist = 5;
@@ -202,7 +233,7 @@ k_tz_search(const SearchTask* __restrict__ tasks, const hmb200_tz_extra* __restr
       const int i = base + lane;
       TzPoint p{0, 0, 0, 5, i < nxr * nyr};
       if (p.valid) { const int iy = i / nxr; p.x = rl + 5 * (i - iy * nxr); p.y = rt + 5 * iy; }
-      const uint32_t c = p.valid ? tz_cost<T>(s_org, ref0, pitch, t, bd, p.x, p.y) : 0u;
+      const uint32_t c = p.valid ? tz_cost<T, OrgT>(s_org, ref0, pitch, t, bd, p.x, p.y) : 0u;
       tz_fold(st, p.valid, c, p, lane);
     }
   }
