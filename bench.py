@@ -270,6 +270,13 @@ def run_ours(args):
     hm.init(local)
     flags = FLAG_FEN | FLAG_HADME | FLAG_FRAC | ((FLAG_TZ | FLAG_TZ_STOP) if args.search == "tz" else 0)
     frames = make_frames(rank)
+    if BIT_DEPTH == 8:                                   # e2e inputs live in page-locked host memory (hmb200_host_alloc)
+        pinned_frames = []
+        for f in frames:
+            a = hm.host_array(f.size, np.uint8).reshape(f.shape)
+            a[...] = f
+            pinned_frames.append(a)
+        frames = pinned_frames
     pairs = [(t + 1, t) for t in range(N_FRAMES - 1)]                       # (current, reference) = (t+1, t)
     jobs = hm.build_canonical_jobs(PIC_W, CODED_H, SEARCH_RANGE, LAMBDA_COST)
     prep = hm.prepare_jobs(jobs, flags, BIT_DEPTH)
@@ -319,7 +326,7 @@ def run_ours(args):
     sampler.join()
 
     # ---- end to end through the C-ABI: host planes in, host MV field out, every step ------------------------------
-    out = np.zeros(len(jobs), dtype=RESULT_DTYPE)
+    out = hm.host_array(len(jobs), RESULT_DTYPE)                  # page-locked result array (hmb200_host_alloc)
 
     def e2e_step(k):
         c, r = pairs[k % len(pairs)]

@@ -12,6 +12,7 @@
 #ifndef HMB200_H
 #define HMB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -108,6 +109,10 @@ typedef struct {
 int  hmb200_init(int device);
 void hmb200_shutdown(void);
 const char* hmb200_last_error(void);
+/* Page-locked host memory for result arrays (hmb200_fetch_results copies straight into it, without the staging copy it
+ * needs for pageable memory) and for planes handed to hmb200_register_plane*. */
+void* hmb200_host_alloc(size_t bytes);
+void  hmb200_host_free(void* p);
 /* Number of kernel launches issued by this library since init (bench.py's gpu_launches). */
 uint64_t hmb200_launch_count(void);
 

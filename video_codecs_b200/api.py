@@ -62,6 +62,7 @@ def _load():
     sig = {
         "hmb200_init": (i32, [i32]), "hmb200_shutdown": (None, []), "hmb200_last_error": (C.c_char_p, []),
         "hmb200_launch_count": (C.c_uint64, []),
+        "hmb200_host_alloc": (vp, [C.c_size_t]), "hmb200_host_free": (None, [vp]),
         "hmb200_set_search_range": (None, [_Mv, i32, i32, i32, i32, i32, i32, i32, C.POINTER(_Mv), C.POINTER(_Mv)]),
         "hmb200_build_canonical_jobs": (i32, [i32, i32, i32, i32, u32, _Mv, i32, i32, vp, i32]),
         "hmb200_build_canonical_jobs_rect": (i32, [i32, i32, i32, i32, u32, _Mv, i32, i32, i32, i32, vp, i32]),
@@ -117,6 +118,24 @@ class HMB200:
 
     def shutdown(self):
         self.lib.hmb200_shutdown()
+
+    def host_array(self, n, dtype):
+        """numpy array of n records in page-locked memory (hmb200_host_alloc); keep the returned array alive, free with host_free."""
+        dtype = np.dtype(dtype)
+        ptr = self.lib.hmb200_host_alloc(max(1, n) * dtype.itemsize)
+        if not ptr:
+            raise HMB200Error(self.lib.hmb200_last_error().decode())
+        buf = (C.c_uint8 * (max(1, n) * dtype.itemsize)).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=n)
+        arr.flags.writeable = True
+        self._host_ptrs = getattr(self, "_host_ptrs", {})
+        self._host_ptrs[arr.ctypes.data] = ptr
+        return arr
+
+    def host_free(self, arr):
+        ptr = getattr(self, "_host_ptrs", {}).pop(arr.ctypes.data, None)
+        if ptr:
+            self.lib.hmb200_host_free(ptr)
 
     def launch_count(self):
         return int(self.lib.hmb200_launch_count())

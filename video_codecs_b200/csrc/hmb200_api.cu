@@ -223,6 +223,14 @@ void hmb200_shutdown(void) {
   g.ready = false; g.device = -1;
 }
 
+void* hmb200_host_alloc(size_t bytes) {
+  if (!g.ready) { fail(HMB200_ERR_STATE, "hmb200_init has not succeeded"); return nullptr; }
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) { fail(HMB200_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(cudaGetLastError())); return nullptr; }
+  return p;
+}
+void hmb200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int hmb200_sync(void) { NEED_READY(); CUDA_TRY(cudaStreamSynchronize(g.stream)); return HMB200_OK; }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -364,10 +372,18 @@ int hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width,
   int rc = make_plane(p, width, height, margin_x, margin_y, 8);
   if (rc != HMB200_OK) return rc;
   size_t bytes = (size_t)width * height;
-  if ((rc = ensure_pinned(bytes)) != HMB200_OK || (rc = ensure_dstage(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
-  uint8_t* pin = reinterpret_cast<uint8_t*>(g.pinned);
-  for (int y = 0; y < height; y++) memcpy(pin + (size_t)y * width, host_samples + (size_t)y * stride, (size_t)width);
-  CUDA_TRY(cudaMemcpyAsync(g.dstage, pin, bytes, cudaMemcpyHostToDevice, g.stream));
+  if ((rc = ensure_dstage(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
+  cudaPointerAttributes attr;
+  const bool user_pinned = stride == width && cudaPointerGetAttributes(&attr, host_samples) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const uint8_t* src = host_samples;                      // page-locked, tightly packed frames go to the device without a staging copy
+  if (!user_pinned) {
+    if ((rc = ensure_pinned(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
+    uint8_t* pin = reinterpret_cast<uint8_t*>(g.pinned);
+    for (int y = 0; y < height; y++) memcpy(pin + (size_t)y * width, host_samples + (size_t)y * stride, (size_t)width);
+    src = pin;
+  }
+  CUDA_TRY(cudaMemcpyAsync(g.dstage, src, bytes, cudaMemcpyHostToDevice, g.stream));
   dim3 grid((width + 2 * margin_x + 255) / 256, height + 2 * margin_y);
   k_pad_plane_u8<<<grid, 256, 0, g.stream>>>(reinterpret_cast<const uint8_t*>(g.dstage), width,
                                              reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, width, height, margin_x, margin_y);
@@ -725,6 +741,15 @@ int hmb200_fetch_results(hmb200_prepared* p, hmb200_pu_result* results) {
   if (!p || (p->n > 0 && !results)) return fail(HMB200_ERR_ARG, "hmb200_fetch_results: bad arguments");
   if (p->n == 0) return HMB200_OK;
   const size_t bytes = (size_t)p->n * sizeof(hmb200_pu_result);
+  cudaPointerAttributes attr;
+  const bool user_pinned = cudaPointerGetAttributes(&attr, results) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();                                                                              // clear the "not registered" status
+  if (user_pinned) {                                                                               // hmb200_host_alloc'ed: straight D2H
+    CUDA_TRY(cudaMemcpyAsync(results, p->d_results, bytes, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    CUDA_TRY(cudaGetLastError());
+    return HMB200_OK;
+  }
   int rc = ensure_pinned(bytes);
   if (rc != HMB200_OK) return rc;
   CUDA_TRY(cudaMemcpyAsync(g.pinned, p->d_results, bytes, cudaMemcpyDeviceToHost, g.stream));    // pinned staging: full PCIe rate
