@@ -175,6 +175,17 @@ uint32_t hmb200_dist(const hmb200_dist_param* p);
 /* n evaluations of one family between registered planes, one launch. */
 int  hmb200_dist_batch(int func, int bit_depth, int n, const hmb200_dist_desc* descs, uint32_t* out);
 
+/* One motion-compensated prediction: the PU and its quarter-pel MV as handed to xPredInterBlk (the caller clips it,
+ * TComDataCU::clipMv).  24 bytes. */
+typedef struct { int32_t pu_x, pu_y, w, h, mv_x, mv_y; } hmb200_mc_desc;
+/* Distortion between each original PU (cur_plane) and its uni-directional motion-compensated prediction from ref_plane:
+ * TComPrediction::xPredInterBlk(COMPONENT_Y, ..., bi = false) (TLibCommon/TComPrediction.cpp:668-706) followed by the
+ * distortion function — func = HMB200_DF_SAD: what TEncSearch::xGetTemplateCost takes through getDistPart(DF_SAD)
+ * (AMVP candidate selection, TLibEncoder/TEncSearch.cpp:3619-3658); func = HMB200_DF_HADS: what
+ * TEncSearch::xGetInterPredictionError takes (merge candidate cost, :2809-2830).  One launch set for the whole batch;
+ * the MV-index bit cost and calcRdCost stay on the host. */
+int  hmb200_mc_dist_batch(int cur_plane, int ref_plane, int func, int n, const hmb200_mc_desc* descs, uint32_t* out);
+
 /* ------------------------------------------------------------------ searches, 1:1 ----------------------------- */
 
 /* TEncSearch::xPatternSearch(TComPattern*, Pel* piRefY, Int iRefStride, TComMv* LT, TComMv* RB, TComMv& rcMv,

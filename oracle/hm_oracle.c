@@ -471,6 +471,64 @@ void hmo_read_luma(const uint8_t* file, int is16, int width, int height, int pad
   }
 }
 
+/* ---------------------------------------------------------------- motion compensation + distortion ------------- */
+
+/* TLibCommon/TComPrediction.cpp:668-706 xPredInterBlk for COMPONENT_Y with bi == false: the prediction block at
+ * quarter-pel MV (mv_x, mv_y).  Three branches: yFrac == 0 -> one horizontal pass straight to pixels (filterHor with
+ * isLast = true: shift 6, offset 32, clip; xFrac == 0 is a copy, TComInterpolationFilter.cpp:94-154); xFrac == 0 -> one
+ * vertical pass; else horizontal into the 14-bit domain (rows -3..+4) then vertical (:172-257).  ref_at_pu points at the
+ * reference sample co-located with the PU's top-left. */
+static int16_t mc_clip(int v, int maxv) { return (int16_t)(v < 0 ? 0 : (v > maxv ? maxv : v)); }
+
+void hmo_mc_block(const int16_t* ref_at_pu, int sr, int w, int h, int mv_x, int mv_y, int bit_depth, int16_t* dst, int sd)
+{
+  const int16_t* ref = ref_at_pu + asr2(mv_x) + asr2(mv_y) * sr;
+  const int fx = mv_x & 3, fy = mv_y & 3, maxv = (1 << bit_depth) - 1;
+  int head = 14 - bit_depth; if (head < 2) head = 2;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+    {
+      const int16_t* p = ref + y * sr + x;
+      if (fy == 0)
+      {
+        if (fx == 0) { dst[y * sd + x] = p[0]; continue; }
+        int sum = 0;
+        for (int t = 0; t < 8; t++) sum += k_luma_taps[fx][t] * p[t - 3];
+        dst[y * sd + x] = mc_clip((int16_t)((sum + 32) >> 6), maxv);
+      }
+      else if (fx == 0)
+      {
+        int sum = 0;
+        for (int t = 0; t < 8; t++) sum += k_luma_taps[fy][t] * p[(t - 3) * sr];
+        dst[y * sd + x] = mc_clip((int16_t)((sum + 32) >> 6), maxv);
+      }
+      else
+      {
+        const int sh1 = 6 - head, sh2 = 6 + head;
+        int col[8];
+        for (int r = 0; r < 8; r++)
+        {
+          int sum = 0;
+          for (int t = 0; t < 8; t++) sum += k_luma_taps[fx][t] * p[(r - 3) * sr + t - 3];
+          col[r] = (int16_t)((sum - (8192 << sh1)) >> sh1);
+        }
+        int sum = 0;
+        for (int t = 0; t < 8; t++) sum += k_luma_taps[fy][t] * col[t];
+        dst[y * sd + x] = mc_clip((int16_t)((sum + (1 << (sh2 - 1)) + (8192 << 6)) >> sh2), maxv);
+      }
+    }
+}
+
+/* Distortion of that prediction against the original: kind 0 = SAD as xGetTemplateCost computes it through
+ * getDistPart(DF_SAD) (TLibEncoder/TEncSearch.cpp:3619-3658), kind 2 = HADs as xGetInterPredictionError does
+ * (:2809-2830, setDistParam with bHadamard). */
+uint32_t hmo_mc_dist(int kind, const int16_t* org, int so, const int16_t* ref_at_pu, int sr, int w, int h, int mv_x, int mv_y, int bit_depth)
+{
+  int16_t pred[64 * 64];
+  hmo_mc_block(ref_at_pu, sr, w, h, mv_x, mv_y, bit_depth, pred, 64);
+  return hmo_dist(kind, org, so, pred, 64, w, h, bit_depth, 0);
+}
+
 /* ---------------------------------------------------------------- job lists ------------------------------------ */
 
 /* Executes a job list the way TEncSearch::xMotionEstimation (TLibEncoder/TEncSearch.cpp:3663-3760) drives the two

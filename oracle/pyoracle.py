@@ -113,6 +113,15 @@ class Oracle(_Base):
     def extend_border(self, plane, origin_off, stride, w, h, mx, my):
         self.lib.hmo_extend_border(_ptr(plane, origin_off), stride, w, h, mx, my)
 
+    def mc_dist(self, kind, org, w, h, ref, mv, bit_depth=8):
+        """Distortion (0 = SAD, 2 = HADs) between the original PU and its motion-compensated prediction at quarter-pel mv.
+        org / ref: (array, offset of the PU's top-left / of the co-located reference sample, stride)."""
+        (oa, oo, os_), (ra, ro, rs) = org, ref
+        f = self.lib.hmo_mc_dist
+        f.restype = C.c_uint32
+        f.argtypes = [C.c_int, _p16, C.c_int, _p16, C.c_int] + [C.c_int] * 5
+        return f(kind, _ptr(oa, oo), os_, _ptr(ra, ro), rs, w, h, mv[0], mv[1], bit_depth)
+
     def tz_search(self, org, w, h, ref, lt, rb, lambda_cost, pred, cu_xy, pic_wh, search_range=64, imv=None, bit_depth=8, max_cu=64,
                   first_search_stop=1):
         """xTZSearch (FastSearch=1).  imv: pIntegerMv2Nx2NPred (integer pel) or None; first_search_stop:
@@ -209,6 +218,14 @@ class Reference(_Base):
                                            mv_int[0], mv_int[1], int(lambda_cost), pred[0], pred[1],
                                            *[C.byref(x) for x in v], C.byref(cost))
         return (v[0].value, v[1].value), (v[2].value, v[3].value), cost.value
+
+    def mc_dist(self, kind, org, w, h, ref_plane0, pic_wh, margin, pu_xy, mv, bit_depth=8):
+        """The reference's own xPredInterBlk + distortion.  ref_plane0: (padded array, offset of sample (0,0), stride)."""
+        (oa, oo, os_), (ra, ro, rs) = org, ref_plane0
+        f = self.lib.hmref_mc_dist
+        f.restype = C.c_uint32
+        f.argtypes = [C.c_void_p, C.c_int, _p16, C.c_int, C.c_int, C.c_int, C.c_int, _p16, C.c_int] + [C.c_int] * 7
+        return f(self.h, kind, _ptr(oa, oo), os_, w, h, bit_depth, _ptr(ra, ro), rs, pic_wh[0], pic_wh[1], margin, pu_xy[0], pu_xy[1], mv[0], mv[1])
 
     def tz_search(self, org, w, h, ref, lt, rb, lambda_cost, pred, cu_xy, pic_wh, search_range=64, imv=None, bit_depth=8, max_cu=64,
                   first_search_stop=1):

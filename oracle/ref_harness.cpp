@@ -39,6 +39,7 @@
 #define private public
 #define protected public
 #include "TLibCommon/TComDataCU.h"
+#include "TLibCommon/TComPic.h"
 #undef private
 #undef protected
 #include "TLibCommon/TComRom.h"
@@ -104,6 +105,46 @@ struct Harness : public TEncSearch
     Distortion d = 0;
     xPatternSearchFracDIF(lossless != 0, &pat, refAtPu, refStride, &mvInt, half, qter, d);
     *hx = half.getHor(); *hy = half.getVer(); *qx = qter.getHor(); *qy = qter.getVer(); *cost = d;
+  }
+
+  // TComPrediction::xPredInterBlk (TComPrediction.cpp:668) for COMPONENT_Y, bi = false, on a reference picture we fill
+  // from the caller's padded plane; then the distortion the way xGetTemplateCost (getDistPart DF_SAD) or
+  // xGetInterPredictionError (setDistParam + bHadamard) take it.  The CU sits at the picture origin; the PU position is
+  // folded into the motion vector (xPredInterBlk only adds (mv >> 2) to the block address).
+  uint32_t mcDist(int kind, Pel* org, int orgStride, int w, int h, int bitDepth, const Pel* ref0, int refStride, int picW, int picH,
+                  int margin, int pux, int puy, int mvx, int mvy)
+  {
+    TComPicYuv refPic;
+    refPic.create(picW, picH, CHROMA_400, 64, 64, 4, true);               // margins 64 + 16 = 80 (TComPicYuv.cpp:93-94)
+    const int m = refPic.getMarginX(COMPONENT_Y);
+    for (int y = -m; y < picH + m; y++)
+      for (int x = -m; x < picW + m; x++)
+      {
+        const int sy = y < -margin ? -margin : (y >= picH + margin ? picH + margin - 1 : y);
+        const int sx = x < -margin ? -margin : (x >= picW + margin ? picW + margin - 1 : x);
+        refPic.getAddr(COMPONENT_Y)[y * refPic.getStride(COMPONENT_Y) + x] = ref0[sy * refStride + sx];
+      }
+    TComPic pic;
+    pic.m_apcPicYuv[TComPic::PIC_YUV_REC] = &refPic;
+    cu.m_pcPic = &pic; cu.m_ctuRsAddr = 0; cu.m_absZIdxInCtu = 0;
+    TComYuv dst;
+    dst.create(64, 64, CHROMA_400);
+    TComMv mv((Short)(mvx + 4 * pux), (Short)(mvy + 4 * puy));
+    xPredInterBlk(COMPONENT_Y, &cu, &refPic, 0, &mv, w, h, &dst, false, bitDepth);
+    uint32_t d;
+    if (kind == 0)
+      d = rd.getDistPart(bitDepth, dst.getAddr(COMPONENT_Y, 0), dst.getStride(COMPONENT_Y), org, orgStride, w, h, COMPONENT_Y, DF_SAD);
+    else
+    {
+      DistParam dp; dp.bApplyWeight = false;
+      rd.setDistParam(dp, bitDepth, org, orgStride, dst.getAddr(COMPONENT_Y, 0), dst.getStride(COMPONENT_Y), w, h, true);
+      d = dp.DistFunc(&dp);
+    }
+    dst.destroy();
+    pic.m_apcPicYuv[TComPic::PIC_YUV_REC] = NULL;
+    cu.m_pcPic = NULL;
+    refPic.destroy();
+    return d;
   }
 
   // TEncSearch::xTZSearch (TEncSearch.cpp:3881) as xMotionEstimation / xPatternSearchFast reach it with FastSearch = 1.
@@ -226,6 +267,13 @@ double hmref_run_jobs(void* hv, const int16_t* cur0, int cur_stride, const int16
     out[i] = r;
   }
   return double(clock() - t0) / CLOCKS_PER_SEC;
+}
+
+uint32_t hmref_mc_dist(void* hv, int kind, const int16_t* org, int org_stride, int w, int h, int bit_depth, const int16_t* ref0,
+                       int ref_stride, int pic_w, int pic_h, int margin, int pu_x, int pu_y, int mv_x, int mv_y)
+{
+  return static_cast<Harness*>(hv)->mcDist(kind, const_cast<Pel*>(org), org_stride, w, h, bit_depth, ref0, ref_stride, pic_w, pic_h,
+                                           margin, pu_x, pu_y, mv_x, mv_y);
 }
 
 void hmref_tz_search(void* hv, const int16_t* org, int org_stride, int w, int h, int bit_depth,

@@ -167,7 +167,27 @@ def make_tz_golden():
     print("wrote tz_golden.npz", len(cases))
 
 
+def make_mc_golden():
+    """tests/golden/mc_golden.npz: xPredInterBlk + SAD / HADs of the unmodified reference for tests/test_mc_dist.py::cases."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_mc_dist as T
+    ref_impl = Reference(fen=1, hadme=1)
+    out = {}
+    for bd in (8, 10):
+        f0, f1, cur, ref, o0, stride = T.frames(bd)
+        cs = T.cases(np.random.default_rng(11 + bd), 240)
+        out[f"frame0_{bd}"] = f0
+        out[f"cases_{bd}"] = np.array([(px, py, w, h, mv[0], mv[1], kind) for (px, py, w, h, mv, kind) in cs], dtype=np.int64)
+        out[f"expected_{bd}"] = np.array([ref_impl.mc_dist(kind, (cur, o0 + py * stride + px, stride), w, h, (ref, o0, stride), (T.W, T.H),
+                                                           T.MARGIN, (px, py), mv, bd) for (px, py, w, h, mv, kind) in cs], dtype=np.int64)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "mc_golden.npz"), **out)
+    print("wrote mc_golden.npz")
+
+
 if __name__ == "__main__":
+    if "--mc" in sys.argv:
+        make_mc_golden()
+        sys.exit(0)
     if "--tz" in sys.argv:
         make_tz_golden()
         sys.exit(0)

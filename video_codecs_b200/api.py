@@ -19,6 +19,7 @@ RESULT_DTYPE = np.dtype([("mv_x", "<i4"), ("mv_y", "<i4"), ("sad", "<u4"),
 DIST_DESC_DTYPE = np.dtype([("org_plane", "<i4"), ("org_x", "<i4"), ("org_y", "<i4"),
                             ("cur_plane", "<i4"), ("cur_x", "<i4"), ("cur_y", "<i4"),
                             ("w", "<i4"), ("h", "<i4"), ("sub_shift", "<i4"), ("reserved", "<i4")])
+MC_DESC_DTYPE = np.dtype([("pu_x", "<i4"), ("pu_y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("mv_x", "<i4"), ("mv_y", "<i4")])
 TZ_EXTRA_DTYPE = np.dtype([("cu_x", "<i4"), ("cu_y", "<i4"), ("has_imv", "<i4"), ("imv_x", "<i4"), ("imv_y", "<i4"),
                            ("reserved", "<i4", (3,))])
 assert TZ_EXTRA_DTYPE.itemsize == 32
@@ -73,6 +74,7 @@ def _load():
         "hmb200_read_plane": (i32, [i32, vp, i32]), "hmb200_release_plane": (None, [i32]),
         "hmb200_dist": (u32, [C.POINTER(_DistParam)]),
         "hmb200_dist_batch": (i32, [i32, i32, i32, vp, vp]),
+        "hmb200_mc_dist_batch": (i32, [i32, i32, i32, i32, vp, vp]),
         "hmb200_pattern_search": (i32, [C.POINTER(_Pattern), vp, i32, _Mv, _Mv, C.POINTER(_CostState), i32,
                                         C.POINTER(_Mv), C.POINTER(u32)]),
         "hmb200_pattern_search_tz": (i32, [C.POINTER(_Pattern), vp, i32, _Mv, _Mv, C.POINTER(_CostState), i32, vp, i32, i32, i32, i32,
@@ -213,6 +215,12 @@ class HMB200:
         descs = np.ascontiguousarray(descs, dtype=DIST_DESC_DTYPE)
         out = np.zeros(len(descs), dtype=np.uint32)
         self._check(self.lib.hmb200_dist_batch(func, bit_depth, len(descs), descs.ctypes.data, out.ctypes.data))
+        return out
+
+    def mc_dist_batch(self, cur_plane, ref_plane, func, descs):
+        descs = np.ascontiguousarray(descs, dtype=MC_DESC_DTYPE)
+        out = np.zeros(len(descs), dtype=np.uint32)
+        self._check(self.lib.hmb200_mc_dist_batch(cur_plane, ref_plane, func, len(descs), descs.ctypes.data, out.ctypes.data))
         return out
 
     # -- 1:1 searches ----------------------------------------------------------------------------------------------

@@ -528,6 +528,47 @@ int hmb200_dist_batch(int func, int bit_depth, int n, const hmb200_dist_desc* de
   return HMB200_OK;
 }
 
+int hmb200_mc_dist_batch(int cur_plane, int ref_plane, int func, int n, const hmb200_mc_desc* descs, uint32_t* out) {
+  NEED_READY();
+  if (n <= 0) return HMB200_OK;
+  Plane* pc = get_plane(cur_plane); Plane* pr = get_plane(ref_plane);
+  if (!pc || !pr) return fail(HMB200_ERR_ARG, "hmb200_mc_dist_batch: unknown plane");
+  if (!descs || !out || (func != HMB200_DF_SAD && func != HMB200_DF_SADS && func != HMB200_DF_HADS))
+    return fail(HMB200_ERR_ARG, "hmb200_mc_dist_batch: bad arguments (func must be SAD or HADS)");
+  if (pc->d.bytes_per_sample != pr->d.bytes_per_sample) return fail(HMB200_ERR_ARG, "hmb200_mc_dist_batch: planes differ in sample size");
+  std::vector<SearchTask> tasks((size_t)n);
+  std::vector<hmb200_pu_result> mv((size_t)n);
+  for (int i = 0; i < n; i++) {
+    const hmb200_mc_desc& d = descs[i];
+    if (!supported_pu(d.w, d.h)) return fail(HMB200_ERR_ARG, "hmb200_mc_dist_batch: unsupported PU size in descriptor " + std::to_string(i));
+    tasks[i] = SearchTask{d.pu_x, d.pu_y, d.pu_x, d.pu_y, d.w, d.h, 0, 0, 0, 0, 0, 0, 0u, 0};
+    mv[i] = hmb200_pu_result{0, 0, 0u, 0, 0, d.mv_x, d.mv_y, 0u};          // k_frac_tiles stage 2 reads the MV from qter_x / qter_y
+  }
+  FracSchedule fs;
+  std::string why;
+  if (!frac_build_schedule(tasks, g.stream, &fs, &why)) return fail(HMB200_ERR_CUDA, why);
+  const size_t tb = (size_t)n * sizeof(SearchTask), rb = (size_t)n * sizeof(hmb200_pu_result), ob = (size_t)n * sizeof(uint32_t);
+  int rc = ensure_dstage(tb + rb + ob + 256);
+  if (rc != HMB200_OK) { frac_free_schedule(&fs); return rc; }
+  char* base = reinterpret_cast<char*>(g.dstage);
+  SearchTask* d_tasks = reinterpret_cast<SearchTask*>(base);
+  hmb200_pu_result* d_mv = reinterpret_cast<hmb200_pu_result*>(base + ((tb + 63) & ~(size_t)63));
+  uint32_t* d_out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d_mv) + ((rb + 63) & ~(size_t)63));
+  cudaError_t e = cudaMemcpyAsync(d_tasks, tasks.data(), tb, cudaMemcpyHostToDevice, g.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_mv, mv.data(), rb, cudaMemcpyHostToDevice, g.stream);
+  int nl = -1;
+  if (e == cudaSuccess) {
+    const bool had = func == HMB200_DF_HADS;
+    nl = pr->d.bytes_per_sample == 1 ? mc_launch<uint8_t, uint8_t>(fs, d_tasks, d_mv, d_out, pc->d, pr->d, had, g.stream)
+                                     : mc_launch<int16_t, int16_t>(fs, d_tasks, d_mv, d_out, pc->d, pr->d, had, g.stream);
+  }
+  if (nl >= 0) { g.launches += (uint64_t)nl; e = cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, g.stream); }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  frac_free_schedule(&fs);
+  if (nl < 0 || e != cudaSuccess) return fail(HMB200_ERR_CUDA, std::string("hmb200_mc_dist_batch: ") + cudaGetErrorString(cudaGetLastError()));
+  return HMB200_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // batched searches
 // ------------------------------------------------------------------------------------------------------------------

@@ -184,7 +184,7 @@ template <typename RefT, typename OrgT, int N, bool HAD>
 __global__ void __launch_bounds__(FRAC_TILE_THREADS, N == 8 ? 4 : 8)
 k_frac_tiles(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_result* __restrict__ results,
              const uint32_t* __restrict__ tiles, int n_tiles, uint32_t* __restrict__ dist, DevPlane cur_plane, DevPlane ref_plane) {
-  const int nc = stage == 0 ? 9 : 8;
+  const int nc = stage == 0 ? 9 : (stage == 1 ? 8 : 1);     // stage 2: one explicit quarter-pel MV per PU (motion compensation)
   const long long t = (long long)blockIdx.x * FRAC_TILE_THREADS + threadIdx.x;
   const int chunk = (int)(t / (32 * nc));
   const int within = (int)(t - (long long)chunk * 32 * nc);
@@ -203,8 +203,9 @@ k_frac_tiles(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_re
     const SearchTask tk = tasks[pu];
     const hmb200_pu_result rs = results[pu];
     int qx, qy;
-    if (stage == 0) { ci = cand; qx = 2 * k_refine_h[ci][0]; qy = 2 * k_refine_h[ci][1]; }
-    else            { ci = cand + 1; qx = 2 * rs.half_x + k_refine_q[ci][0]; qy = 2 * rs.half_y + k_refine_q[ci][1]; }
+    if (stage == 0)      { ci = cand; qx = 2 * k_refine_h[ci][0]; qy = 2 * k_refine_h[ci][1]; }
+    else if (stage == 1) { ci = cand + 1; qx = 2 * rs.half_x + k_refine_q[ci][0]; qy = 2 * rs.half_y + k_refine_q[ci][1]; }
+    else                 { ci = 0; qx = rs.qter_x; qy = rs.qter_y; }      // xPredInterBlk: the whole MV in quarter pel, mv_x/y = 0
     fx = qx & 3; fy = qy & 3;
     ref = plane_at<RefT>(ref_plane, tk.ref_x + rs.mv_x + (qx >> 2) + tx * N, tk.ref_y + rs.mv_y + (qy >> 2) + ty * N);
     org = plane_at<OrgT>(cur_plane, tk.org_x + tx * N, tk.org_y + ty * N);
@@ -262,6 +263,12 @@ __global__ void k_frac_argmin(const SearchTask* __restrict__ tasks, hmb200_pu_re
     r.frac_cost = best;
   }
   results[i] = r;
+}
+
+// dist[pu][0] >> (bitDepth - 8): the distortion of one motion-compensated prediction per PU (stage 2 of k_frac_tiles)
+__global__ void k_mc_collect(const uint32_t* __restrict__ dist, uint32_t* __restrict__ out, int n, int bit_depth) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = dist[(size_t)i * 9] >> (bit_depth - 8);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -336,6 +343,29 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
     else            k_frac_argmin<1><<<nb, 256, 0, stream>>>(d_tasks, d_results, dist1, nullptr, fs.n_pu, ref.bit_depth);
     launches++;
   }
+  return cudaGetLastError() == cudaSuccess ? launches : -1;
+}
+
+// Motion-compensated distortion of n PUs: tiles of one candidate each (k_frac_tiles stage 2), then k_mc_collect.
+template <typename RefT, typename OrgT>
+inline int mc_launch(const FracSchedule& fs, const SearchTask* d_tasks, const hmb200_pu_result* d_mv, uint32_t* d_out, const DevPlane& cur,
+                     const DevPlane& ref, bool use_had, cudaStream_t stream) {
+  if (fs.n_pu == 0) return 0;
+  int launches = 0;
+  if (cudaMemsetAsync(fs.d_dist, 0, (size_t)fs.n_pu * 9 * sizeof(uint32_t), stream) != cudaSuccess) return -1;
+  auto blocks = [&](int n_tiles) { return (int)((((long long)(n_tiles + 31) / 32) * 32 + FRAC_TILE_THREADS - 1) / FRAC_TILE_THREADS); };
+  if (fs.n_tiles8 > 0) {
+    if (use_had) k_frac_tiles<RefT, OrgT, 8, true><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(2, d_tasks, d_mv, fs.d_tiles8, fs.n_tiles8, fs.d_dist, cur, ref);
+    else         k_frac_tiles<RefT, OrgT, 8, false><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(2, d_tasks, d_mv, fs.d_tiles8, fs.n_tiles8, fs.d_dist, cur, ref);
+    launches++;
+  }
+  if (fs.n_tiles4 > 0) {
+    if (use_had) k_frac_tiles<RefT, OrgT, 4, true><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(2, d_tasks, d_mv, fs.d_tiles4, fs.n_tiles4, fs.d_dist, cur, ref);
+    else         k_frac_tiles<RefT, OrgT, 4, false><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(2, d_tasks, d_mv, fs.d_tiles4, fs.n_tiles4, fs.d_dist, cur, ref);
+    launches++;
+  }
+  k_mc_collect<<<(fs.n_pu + 255) / 256, 256, 0, stream>>>(fs.d_dist, d_out, fs.n_pu, ref.bit_depth);
+  launches++;
   return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
 
