@@ -289,19 +289,19 @@ k_search8(const S8Unit* __restrict__ units, const S8Job* __restrict__ jobs, unsi
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   if (threadIdx.x == 0) { mbar_init(&s_bar, 1); s_next = un.item_first; }
-  __syncthreads();
-  if (warp == 0) {
-    // stage the window and the original tile: one bulk-async copy per row, all completing on one mbarrier
-    if (lane == 0) mbar_expect_tx(&s_bar, (uint32_t)(un.ref_pitch * un.ref_rows + un.org_pitch * un.org_rows));
-    __syncwarp();
+  __syncthreads();                                      // the initialised barrier is visible before its first use
+  if (threadIdx.x == 0) mbar_expect_tx(&s_bar, (uint32_t)(un.ref_pitch * un.ref_rows + un.org_pitch * un.org_rows));
+  __syncthreads();                                      // ... and armed before any copy can complete on it
+  {
+    // stage the window and the original tile: one bulk-async copy per row, issued by all threads, one mbarrier
     const uint8_t* gref = reinterpret_cast<const uint8_t*>(ref_plane.base) +
                           (size_t)(un.ref_by + ref_plane.margin_y) * ref_plane.pitch + (un.ref_bx + ref_plane.margin_x);
-    for (int r = lane; r < un.ref_rows; r += 32)
+    for (int r = threadIdx.x; r < un.ref_rows; r += S8_THREADS)
       bulk_g2s(s_ref + r * un.ref_pitch, gref + (size_t)r * ref_plane.pitch, (uint32_t)un.ref_pitch, &s_bar);
     const uint8_t* gorg = reinterpret_cast<const uint8_t*>(cur_plane.base) +
                           (size_t)(un.org_by + cur_plane.margin_y) * cur_plane.pitch + (un.org_bx + cur_plane.margin_x);
-    for (int r = lane; r < un.org_rows; r += 32)
-      bulk_g2s(s_org + r * un.org_pitch, gorg + (size_t)r * cur_plane.pitch, (uint32_t)un.org_pitch, &s_bar);
+    for (int r = (int)threadIdx.x - 128; r < un.org_rows; r += S8_THREADS)
+      if (r >= 0) bulk_g2s(s_org + r * un.org_pitch, gorg + (size_t)r * cur_plane.pitch, (uint32_t)un.org_pitch, &s_bar);
   }
   mbar_wait(&s_bar, 0);
 

@@ -158,7 +158,6 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   constexpr int NSLOT = (S == 8) ? 5 : CU_SLOTS;
   extern __shared__ __align__(128) uint8_t s8_smem[];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_next;
   __shared__ S8Bundle s_bd[S8_WARPS];
 
   const S8Unit un = units[blockIdx.x];
@@ -166,19 +165,21 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   uint8_t* s_org = s8_smem + un.org_smem_off;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  if (threadIdx.x == 0) { mbar_init(&s_bar, 1); s_next = 0; }
-  __syncthreads();
-  if (warp == 0) {
-    if (lane == 0) mbar_expect_tx(&s_bar, (uint32_t)(un.ref_pitch * un.ref_rows + un.org_pitch * un.org_rows));
-    __syncwarp();
+  // every thread issues the bulk copies of its rows (one warp alone serialises ~250 UBLKCP issues: ncu showed a
+  // fifth of the stall samples on the mbarrier spin); thread 0 arms the transaction count first
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __syncthreads();                                      // the initialised barrier is visible before its first use
+  if (threadIdx.x == 0) mbar_expect_tx(&s_bar, (uint32_t)(un.ref_pitch * un.ref_rows + un.org_pitch * un.org_rows));
+  __syncthreads();                                      // ... and armed before any copy can complete on it
+  {
     const uint8_t* gref = reinterpret_cast<const uint8_t*>(ref_plane.base) +
                           (size_t)(un.ref_by + ref_plane.margin_y) * ref_plane.pitch + (un.ref_bx + ref_plane.margin_x);
-    for (int r = lane; r < un.ref_rows; r += 32)
+    for (int r = threadIdx.x; r < un.ref_rows; r += S8_THREADS)
       bulk_g2s(s_ref + r * un.ref_pitch, gref + (size_t)r * ref_plane.pitch, (uint32_t)un.ref_pitch, &s_bar);
     const uint8_t* gorg = reinterpret_cast<const uint8_t*>(cur_plane.base) +
                           (size_t)(un.org_by + cur_plane.margin_y) * cur_plane.pitch + (un.org_bx + cur_plane.margin_x);
-    for (int r = lane; r < un.org_rows; r += 32)
-      bulk_g2s(s_org + r * un.org_pitch, gorg + (size_t)r * cur_plane.pitch, (uint32_t)un.org_pitch, &s_bar);
+    for (int r = (int)threadIdx.x - 128; r < un.org_rows; r += S8_THREADS)
+      if (r >= 0) bulk_g2s(s_org + r * un.org_pitch, gorg + (size_t)r * cur_plane.pitch, (uint32_t)un.org_pitch, &s_bar);
   }
   mbar_wait(&s_bar, 0);
 
@@ -217,7 +218,6 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
       best[s] = 0xffffffffu;
     }
   };
-  (void)s_next;
 
   for (int item = un.item_first + warp; item < un.item_last; item += S8_WARPS) {
     if (item >= bd.item_start + bd.n_items) {
