@@ -112,7 +112,7 @@ def int_simd_peak():
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant search kernel, from the committed ncu
-    --set full capture of this round (profiles/r01_ncu_full_l.csv); None when the file is absent."""
+    --set full capture of this round (profiles/r01_ncu_full_final.csv); None when the file is absent."""
     import csv
     try:
         rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01_ncu_full_l.csv"))))
