@@ -269,7 +269,7 @@ def run_ours(args):
     hm = HMB200()
     hm.init(local)
     flags = FLAG_FEN | FLAG_HADME | FLAG_FRAC | ((FLAG_TZ | FLAG_TZ_STOP) if args.search == "tz" else 0)
-    frames = make_frames(rank)
+    frames = make_frames(0 if (args.shard == "tiles" and world > 1) else rank)   # tile columns: every rank sees the same pictures
     if BIT_DEPTH == 8:                                   # e2e inputs live in page-locked host memory (hmb200_host_alloc)
         pinned_frames = []
         for f in frames:
@@ -278,7 +278,13 @@ def run_ours(args):
             pinned_frames.append(a)
         frames = pinned_frames
     pairs = [(t + 1, t) for t in range(N_FRAMES - 1)]                       # (current, reference) = (t+1, t)
-    jobs = hm.build_canonical_jobs(PIC_W, CODED_H, SEARCH_RANGE, LAMBDA_COST)
+    if args.shard == "tiles" and world > 1:
+        # tile-column sharding of ONE picture (BASELINE.json configs[3]): every rank holds both planes and searches the
+        # jobs of its uniformly spaced tile column; strong scaling, still no collective on the data path
+        from video_codecs_b200 import shard as _shard
+        jobs = _shard.tile_column_jobs(hm, PIC_W, CODED_H, world, rank, SEARCH_RANGE, LAMBDA_COST)
+    else:
+        jobs = hm.build_canonical_jobs(PIC_W, CODED_H, SEARCH_RANGE, LAMBDA_COST)
     prep = hm.prepare_jobs(jobs, flags, BIT_DEPTH)
     if args.search == "tz":
         prep.set_tz(hm.canonical_tz_extra(jobs), (PIC_W, CODED_H), SEARCH_RANGE)
@@ -358,8 +364,10 @@ def run_ours(args):
         K = max(1, args.steps)
         ms_per_step = tot / K
         mpix_step = PIC_W * PIC_H / 1e6
-        value = world * mpix_step / (ms_per_step / 1e3)
-        e2e_value = world * mpix_step / (e2e_ms / 1e3)
+        tiles = args.shard == "tiles" and world > 1
+        units = 1 if tiles else world                       # tile columns: all ranks together process ONE picture per step
+        value = units * mpix_step / (ms_per_step / 1e3)
+        e2e_value = units * mpix_step / (e2e_ms / 1e3)
         peak_abs, peak_src = int_simd_peak()
         search_s = srch / K / 1e3
         achieved = work["abs_diffs"] / search_s
@@ -375,12 +383,13 @@ def run_ours(args):
         algo_bytes = 2 * plane_bytes + len(jobs) * (32 + 48)       # both planes once + job list + results
         line = {
             "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
             "dtype": "u8" if BIT_DEPTH == 8 else "u16", "data": "synthetic",
             "config": {"workload": WORKLOAD if args.search == "full" else WORKLOAD.replace("fullsearch", "tzsearch"), "picture": f"{PIC_W}x{PIC_H} (coded {PIC_W}x{CODED_H})", "search_range": SEARCH_RANGE,
                        "pus_per_frame": int(len(jobs)), "pus_per_ctu": 593, "frame_pairs_per_step_per_gpu": 1,
                        "l2": "flushed between timed iterations (256 MiB write, untimed)", "mpixel_counts": f"{PIC_W}x{PIC_H} luma per step"},
             "cand_sad_per_s": world * work["cand_sads"] / (ms_per_step / 1e3),
+            "sharding": "tile columns of one picture" if tiles else "independent frame pairs",
             "search_ms": srch / K, "frac_ms": frac / K, "wall_ms_per_step_incl_flush": wall_ms / K,
             "roofline": {"bound": "int_alu", "kernel": "k_search8<*> (VABSDIFF4.U8.ACC)", "achieved": achieved / 1e12,
                          "peak": peak_abs / 1e12, "unit": "Tabsdiff/s", "frac": achieved / peak_abs, "traffic": traffic,
@@ -425,6 +434,8 @@ def main():
     ap.add_argument("--cpu-ctus", type=int, default=16, help="CTUs in the single-core cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--shard", default="frames", choices=["frames", "tiles"],
+                    help="N > 1: independent frame pairs per rank (weak scaling, default) or tile columns of one picture (strong)")
     ap.add_argument("--search", default="full", choices=["full", "tz"], help="tz: xTZSearch (FastSearch=1) instead of the full search")
     args = ap.parse_args()
     select_workload(args.workload)
