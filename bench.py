@@ -115,7 +115,7 @@ def ncu_traffic():
     --set full capture of this round (profiles/r01_ncu_full_final.csv); None when the file is absent."""
     import csv
     try:
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01_ncu_full_l.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01_ncu_full_final.csv"))))
         hdr, units = rows[0], rows[1]
         ki, ti = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
         ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
