@@ -846,13 +846,25 @@ static int run_single(const hmb200_pattern* key, const int16_t* ref_at_pu, const
   if (rc != HMB200_OK) return rc;
   SearchTask t = proto;
   t.org_x = 0; t.org_y = 0; t.ref_x = rx; t.ref_y = ry; t.w = key->width; t.h = key->height;
-  size_t need = sizeof(SearchTask) + sizeof(hmb200_pu_result) + 64;
+  size_t need = sizeof(SearchTask) + sizeof(hmb200_pu_result) + 128;
   if ((rc = ensure_dstage(need)) != HMB200_OK) return rc;
   SearchTask* d_t = reinterpret_cast<SearchTask*>(g.dstage);
   hmb200_pu_result* d_r = reinterpret_cast<hmb200_pu_result*>(reinterpret_cast<char*>(g.dstage) + 64);
+  unsigned long long* d_key = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(g.dstage) + 64 + sizeof(hmb200_pu_result));
   CUDA_TRY(cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, g.stream));
   CUDA_TRY(cudaMemcpyAsync(d_r, io, sizeof(*io), cudaMemcpyHostToDevice, g.stream));
-  dispatch_generic(d_t, d_r, 1, g.pattern.d, pr->d, flags, do_search, nullptr);
+  if (do_search) {
+    // one PU: spread its candidates over the whole GPU (one CTA per ~256 candidates), fold with atomicMin, decode
+    const long long total = (long long)(t.rb_x - t.lt_x + 1) * (t.rb_y - t.lt_y + 1);
+    const int splits = (int)std::max<long long>(1, std::min<long long>(4 * g.sm_count, (total + 255) / 256));
+    CUDA_TRY(cudaMemsetAsync(d_key, 0xff, sizeof(unsigned long long), g.stream));
+    const dim3 grid(1, splits);
+    if (pr->d.bytes_per_sample == 1) k_search_split<uint8_t, int16_t><<<grid, 256, 0, g.stream>>>(d_t, d_key, g.pattern.d, pr->d);
+    else                             k_search_split<int16_t, int16_t><<<grid, 256, 0, g.stream>>>(d_t, d_key, g.pattern.d, pr->d);
+    k_search8_finalize<<<1, 32, 0, g.stream>>>(d_t, d_key, d_r, 1);
+    g.launches += 2;
+  }
+  dispatch_generic(d_t, d_r, 1, g.pattern.d, pr->d, flags, /*do_search=*/false, nullptr);
   CUDA_TRY(cudaMemcpyAsync(io, d_r, sizeof(*io), cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaGetLastError());

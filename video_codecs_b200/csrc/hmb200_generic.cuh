@@ -78,6 +78,53 @@ __global__ void __launch_bounds__(256) k_search_generic(const SearchTask* __rest
   }
 }
 
+// Same search with the candidates of one PU split over gridDim.y CTAs (the 1:1 entries: one PU per call, the whole
+// GPU is idle otherwise).  Each CTA folds its slice into keys[task] with atomicMin; k_search8_finalize decodes the key.
+template <typename RefT, typename OrgT>
+__global__ void __launch_bounds__(256) k_search_split(const SearchTask* __restrict__ tasks, unsigned long long* __restrict__ keys,
+                                                      DevPlane cur_plane, DevPlane ref_plane) {
+  __shared__ int16_t s_org[64 * 64];
+  __shared__ unsigned long long s_best[8];
+  const SearchTask t = tasks[blockIdx.x];
+  const OrgT* org = plane_at<OrgT>(cur_plane, t.org_x, t.org_y);
+  const RefT* ref = plane_at<RefT>(ref_plane, t.ref_x, t.ref_y);
+  const int org_stride = cur_plane.pitch, ref_stride = ref_plane.pitch, bit_depth = ref_plane.bit_depth;
+  const int step = 1 << t.sub_shift, rows = t.h >> t.sub_shift;
+  for (int i = threadIdx.x; i < rows * t.w; i += blockDim.x) {
+    int r = i / t.w, c = i - r * t.w;
+    s_org[r * t.w + c] = (int16_t)org[(size_t)(r * step) * org_stride + c];
+  }
+  __syncthreads();
+  const int nx = t.rb_x - t.lt_x + 1, ny = t.rb_y - t.lt_y + 1, total = nx * ny;
+  const int chunk = (total + gridDim.y - 1) / gridDim.y;
+  const int first = blockIdx.y * chunk, last = min(total, first + chunk);
+  unsigned long long best = ~0ull;
+  for (int idx = first + threadIdx.x; idx < last; idx += blockDim.x) {
+    int cy = idx / nx, cx = idx - cy * nx;
+    int x = t.lt_x + cx, y = t.lt_y + cy;
+    const RefT* p = ref + (ptrdiff_t)y * ref_stride + x;
+    uint32_t sum = 0;
+    for (int r = 0; r < rows; r++) {
+      const RefT* q = p + (ptrdiff_t)(r * step) * ref_stride;
+      for (int c = 0; c < t.w; c++) sum += (uint32_t)abs((int)s_org[r * t.w + c] - (int)q[c]);
+    }
+    sum = (sum << t.sub_shift) >> (bit_depth - 8);
+    const unsigned long long key = make_key(sum + mv_cost(t.lambda_cost, mv_bits(x, y, t.pred_x, t.pred_y, 2)), (uint32_t)idx);
+    best = key < best ? key : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other < best ? other : best;
+  }
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) best = s_best[w] < best ? s_best[w] : best;
+    if (best != ~0ull) atomicMin(&keys[blockIdx.x], best);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // quarter-pel refinement, one CTA per PU.
 // TLibEncoder/TEncSearch.cpp:4240-4276 (xPatternSearchFracDIF), :808-861 (xPatternRefinement),
