@@ -53,7 +53,8 @@ struct State {
 State g;
 std::string g_err;
 
-int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int g_err_code = HMB200_OK;
+int fail(int code, const std::string& msg) { g_err = msg; g_err_code = code; return code; }
 #define CUDA_TRY(expr)                                                                                   \
   do {                                                                                                   \
     cudaError_t e__ = (expr);                                                                            \
@@ -668,7 +669,7 @@ int hmb200_tz_jobs(int cur_plane, int ref_plane, const hmb200_pu_job* jobs, cons
   Plane* pr = get_plane(ref_plane);
   if (!pr) return fail(HMB200_ERR_ARG, "hmb200_tz_jobs: unknown reference plane");
   hmb200_prepared* p = hmb200_prepare_jobs(jobs, njobs, flags | HMB200_FLAG_TZ, pr->d.bit_depth);
-  if (!p) return HMB200_ERR_ARG;
+  if (!p) return g_err_code != HMB200_OK ? g_err_code : HMB200_ERR_ARG;
   int rc = hmb200_prepared_set_tz(p, extra, pic_w, pic_h, max_cu, search_range);
   if (rc == HMB200_OK) rc = hmb200_run_prepared(p, cur_plane, ref_plane);
   if (rc == HMB200_OK) rc = hmb200_fetch_results(p, results);
@@ -805,7 +806,7 @@ int hmb200_me_jobs(int cur_plane, int ref_plane, const hmb200_pu_job* jobs, int 
   Plane* pr = get_plane(ref_plane);
   if (!pr) return fail(HMB200_ERR_ARG, "hmb200_me_jobs: unknown reference plane");
   hmb200_prepared* p = hmb200_prepare_jobs(jobs, njobs, flags, pr->d.bit_depth);
-  if (!p) return g_err.empty() ? HMB200_ERR_ARG : (g_err.find("cuda") != std::string::npos ? HMB200_ERR_CUDA : HMB200_ERR_ARG);
+  if (!p) return g_err_code != HMB200_OK ? g_err_code : HMB200_ERR_ARG;
   int rc = hmb200_run_prepared(p, cur_plane, ref_plane);
   if (rc == HMB200_OK) rc = hmb200_fetch_results(p, results);
   hmb200_free_prepared(p);
