@@ -17,6 +17,7 @@
 // Tile: a quad of lanes owns 16 candidate columns (lane s: columns s, s+4, s+8, s+12, one funnel shift per word) of
 // KY candidate rows.  Windows whose width is not a multiple of 16 get a last block that overlaps its neighbour.
 #pragma once
+#include <cstdlib>
 #include <map>
 #include "hmb200_search8.cuh"
 
@@ -539,7 +540,9 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     all_r = s8_union(all_r, g.rb); all_o = s8_union(all_o, g.ob);
   }
   long long target[CUV_COUNT];
-  for (int v = 0; v < CUV_COUNT; v++) target[v] = std::max<long long>(variant_cost[v] / std::max(1, sm_count * 2 * 12), 4000);
+  int per_slot = 6;                                    // units per resident CTA slot and variant (measured optimum 5-6; knob: HMB200_UNITS_PER_SLOT)
+  if (const char* e = getenv("HMB200_UNITS_PER_SLOT")) per_slot = std::max(1, atoi(e));
+  for (int v = 0; v < CUV_COUNT; v++) target[v] = std::max<long long>(variant_cost[v] / std::max(1, sm_count * 2 * per_slot), 4000);
   const int S_of_variant[CUV_COUNT] = {8, 16, 16, 32, 32, 64, 64};
   const bool F_of_variant[CUV_COUNT] = {false, false, true, false, true, false, true};
   std::vector<S8Unit> units;
