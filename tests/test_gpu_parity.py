@@ -358,3 +358,25 @@ def test_me_canonical_ctus_10bit_vs_oracle(hm, fen, sr):
     assert work["pus_fused"] > 0.3 * len(jobs)          # the fused 16-bit kernels did run
     exp, _ = Oracle(fen=fen, hadme=1).run_jobs((cur, o0, stride), (ref, o0, stride), jobs, 10, True)
     assert results_equal(got, exp) == []
+
+
+def test_me_ctu_row_entry(hm):
+    """hmb200_me_ctu_row: the per-CTU-row launch granularity of the in-encoder frontend; rows must agree with one
+    whole-picture call, and a job outside the row is rejected."""
+    from video_codecs_b200 import HMB200Error
+    W, H = 256, 192
+    f0, f1 = synth.luma_frame(W, H, 0, seed=61), synth.luma_frame(W, H, 1, seed=61)
+    jobs = hm.build_canonical_jobs(W, H, 64, 300000)
+    idc = hm.register_plane_u8(f1, MARGIN, MARGIN, kind=0)
+    idr = hm.register_plane_u8(f0, MARGIN, MARGIN, kind=1)
+    try:
+        whole = hm.me_jobs(idc, idr, jobs, flags_of(1, 1))
+        for row in range(3):
+            sel = jobs["pu_y"] // 64 == row
+            got = hm.me_ctu_row(idc, idr, row, jobs[sel], flags_of(1, 1))
+            assert np.array_equal(got, whole[sel])
+        with pytest.raises(HMB200Error):
+            hm.me_ctu_row(idc, idr, 0, jobs[jobs["pu_y"] // 64 == 1][:4], flags_of(1, 1))
+    finally:
+        hm.release_plane(idc)
+        hm.release_plane(idr)
