@@ -118,6 +118,10 @@ uint64_t hmb200_launch_count(void);
 
 /* ------------------------------------------------------------------ host-side window / job-list logic ---------- */
 
+/* m_uiCost of a slice: TComRdCost::setLambda (TLibCommon/TComRdCost.cpp:195-220) turns the slice's motion lambda into the
+ * fixed-point multiplier floor(65536 * sqrt(lambda)) (m_uiLambdaMotionSAD[0]) that getMotionCost(true, 0, ...) installs
+ * and getCost() multiplies the MV bits with; it is the lambda_cost of hmb200_cost_state / hmb200_pu_job. */
+uint32_t hmb200_motion_lambda_cost(double lambda);
 /* TEncSearch::xSetSearchRange (TLibEncoder/TEncSearch.cpp:3765-3781) with TComDataCU::clipMv
  * (TLibCommon/TComDataCU.cpp:2788-2801): pred is the quarter-pel predictor, (cu_x, cu_y) the luma origin of the CU
  * that owns the PU.  Pure host arithmetic (no GPU needed). */

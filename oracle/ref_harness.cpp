@@ -40,6 +40,7 @@
 #define protected public
 #include "TLibCommon/TComDataCU.h"
 #include "TLibCommon/TComPic.h"
+#include "TLibCommon/TComRdCost.h"
 #undef private
 #undef protected
 #include "TLibCommon/TComRom.h"
@@ -267,6 +268,19 @@ double hmref_run_jobs(void* hv, const int16_t* cur0, int cur_stride, const int16
     out[i] = r;
   }
   return double(clock() - t0) / CLOCKS_PER_SEC;
+}
+
+// TComRdCost::setLambda + getMotionCost(true, 0, false): the m_uiCost the searches multiply MV bits with
+uint32_t hmref_motion_lambda_cost(double lambda, int bit_depth)
+{
+  TComRdCost rd;
+  BitDepths bd; bd.recon[0] = bd.recon[1] = bit_depth;
+#if O0043_BEST_EFFORT_DECODING
+  bd.stream[0] = bd.stream[1] = bit_depth;
+#endif
+  rd.setLambda(lambda, bd);
+  rd.getMotionCost(true, 0, false);
+  return rd.m_uiCost;
 }
 
 uint32_t hmref_mc_dist(void* hv, int kind, const int16_t* org, int org_stride, int w, int h, int bit_depth, const int16_t* ref0,

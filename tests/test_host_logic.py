@@ -88,3 +88,15 @@ def test_window_clipping_at_borders(lib, oracle):
         assert j["lt_x"] <= j["rb_x"] and j["lt_y"] <= j["rb_y"]
         assert j["pu_x"] + j["lt_x"] >= -(size + 8) and j["pu_x"] + j["w"] - 1 + j["rb_x"] <= 416 + 8 + size
         assert j["pu_y"] + j["lt_y"] >= -(size + 8) and j["pu_y"] + j["h"] - 1 + j["rb_y"] <= 240 + 8 + size
+
+
+def test_motion_lambda_cost_matches_reference(lib, reference):
+    """TComRdCost::setLambda -> m_uiCost, for the lambdas HM derives from QP 0..51 at depth 0 and deeper (x4)."""
+    import ctypes as C
+    f = reference.lib.hmref_motion_lambda_cost
+    f.restype, f.argtypes = C.c_uint32, [C.c_double, C.c_int]
+    for qp in range(0, 52):
+        for scale in (0.4624, 0.578, 0.57, 1.0):
+            lam = scale * 2 ** ((qp - 12) / 3.0)
+            assert lib.motion_lambda_cost(lam) == f(lam, 8)
+    assert lib.motion_lambda_cost(0.4624 * 2 ** ((35 - 12) / 3.0)) == 635239

@@ -64,6 +64,7 @@ def _load():
         "hmb200_init": (i32, [i32]), "hmb200_shutdown": (None, []), "hmb200_last_error": (C.c_char_p, []),
         "hmb200_launch_count": (C.c_uint64, []),
         "hmb200_host_alloc": (vp, [C.c_size_t]), "hmb200_host_free": (None, [vp]),
+        "hmb200_motion_lambda_cost": (u32, [C.c_double]),
         "hmb200_set_search_range": (None, [_Mv, i32, i32, i32, i32, i32, i32, i32, C.POINTER(_Mv), C.POINTER(_Mv)]),
         "hmb200_build_canonical_jobs": (i32, [i32, i32, i32, i32, u32, _Mv, i32, i32, vp, i32]),
         "hmb200_build_canonical_jobs_rect": (i32, [i32, i32, i32, i32, u32, _Mv, i32, i32, i32, i32, vp, i32]),
@@ -143,6 +144,9 @@ class HMB200:
         return int(self.lib.hmb200_launch_count())
 
     # -- host logic ------------------------------------------------------------------------------------------------
+    def motion_lambda_cost(self, lam):
+        return int(self.lib.hmb200_motion_lambda_cost(float(lam)))
+
     def set_search_range(self, pred, search_range, cu_xy, pic_wh, max_cu=64):
         lt, rb = _Mv(), _Mv()
         self.lib.hmb200_set_search_range(_Mv(*pred), search_range, cu_xy[0], cu_xy[1], pic_wh[0], pic_wh[1], max_cu, max_cu,

@@ -2,6 +2,7 @@
 // One caller thread per process (the reference path is non-reentrant too: shared m_cDistParam / m_filteredBlock,
 // TLibEncoder/TEncSearch.h:113).  No CPU fallback anywhere: without a usable sm_100 device every compute entry
 // fails with HMB200_ERR_CUDA.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -244,6 +245,11 @@ static void clip_mv(int& x, int& y, int cu_x, int cu_y, int pic_w, int pic_h, in
   int vmax = (pic_h + off - cu_y - 1) * 4, vmin = (-max_cu_h - off - cu_y + 1) * 4;
   x = std::min(hmax, std::max(hmin, x));
   y = std::min(vmax, std::max(vmin, y));
+}
+
+uint32_t hmb200_motion_lambda_cost(double lambda) {
+  // TLibCommon/TComRdCost.cpp:195-220 setLambda: m_uiLambdaMotionSAD[0]; getMotionCost(true, 0, false) copies it to m_uiCost
+  return (uint32_t)std::floor(65536.0 * std::sqrt(lambda));
 }
 
 void hmb200_set_search_range(hmb200_mv pred, int search_range, int cu_x, int cu_y, int pic_w, int pic_h, int max_cu_w, int max_cu_h,
