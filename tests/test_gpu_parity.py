@@ -328,6 +328,32 @@ def test_search_range_128_vs_oracle(hm):
     assert results_equal(got, exp) == []
 
 
+@pytest.mark.parametrize("fen", [1, 0])
+def test_fused_windows_at_every_alignment(hm, fen):
+    """CU-fused kernels stage 16-column candidate blocks aligned in shared memory and mask the columns of the first and
+    last block that lie outside the window: a shared predictor per run moves the window's left edge through all 16
+    residues (and narrow windows of 1..40 columns through every block count); every PU of a CTU against the oracle."""
+    W, H = 192, 128
+    f0, f1 = synth.luma_frame(W, H, 0, seed=5), synth.luma_frame(W, H, 1, seed=5)
+    cur, o0, stride = padded(f1)
+    ref, _, _ = padded(f0)
+    idc = hm.register_plane_u8(f1, MARGIN, MARGIN, kind=0)
+    idr = hm.register_plane_u8(f0, MARGIN, MARGIN, kind=1)
+    rng = np.random.default_rng(11)
+    try:
+        for r in range(16):
+            pred = (4 * r + int(rng.integers(0, 4)), -4 * (r % 5) + int(rng.integers(0, 4)))
+            sr = int(rng.integers(1, 21))
+            jobs = hm.build_canonical_jobs(W, H, sr, 30000 + 977 * r, pred=pred, ctu_first=1 + (r % 2) * 3, ctu_count=1)
+            jobs = jobs[:: 2 if r % 3 else 1]
+            got = hm.me_jobs(idc, idr, jobs, flags_of(fen, 1, frac=False))
+            exp, _ = Oracle(fen=fen, hadme=1).run_jobs((cur, o0, stride), (ref, o0, stride), jobs, 8, False)
+            assert results_equal(got, exp, ("mv_x", "mv_y", "sad")) == [], (r, pred, sr)
+    finally:
+        hm.release_plane(idc)
+        hm.release_plane(idr)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # 10-bit content: CU-fused 16-bit kernels (packed 16x2 arithmetic, distortion precision shift)
 # ---------------------------------------------------------------------------------------------------------------------

@@ -738,7 +738,7 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
       if (v >= 0)
         kern[v]<<<sc.unit_count[v], S8_THREADS, sc.smem_of[v], st>>>(sc.d_units + sc.unit_first[v], sc.d_jobs, sc.d_keys, pc->d, pr->d);
       else
-        cukern[~v]<<<cu.unit_count[~v], S8_THREADS, cu.smem_of[~v], st>>>(cu.d_units + cu.unit_first[~v], cu.d_bundles, sc.d_keys, pc->d, pr->d);
+        cukern[~v]<<<cu.unit_count[~v], bps == 1 ? CU8_THREADS : S8_THREADS, cu.smem_of[~v], st>>>(cu.d_units + cu.unit_first[~v], cu.d_bundles, sc.d_keys, pc->d, pr->d);
       g.launches++;
     }
     for (int k = 0; k < N_SIDE && k + 1 < used; k++) {

@@ -60,7 +60,7 @@ struct S8Unit {             // 64 bytes
   int32_t org_smem_off;     // byte offset of the original tile in dynamic smem
   int32_t variant;          // tile variant of every PU of this unit
   int32_t smem_need;        // dynamic shared memory of this unit
-  int32_t pad;
+  int32_t copy_stride;      // CU-fused 8-bit kernels: bytes between the four byte-shifted copies of the window
 };
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -24,19 +24,26 @@
 namespace hmb200 {
 
 constexpr int CU_SLOTS = 13;
+// 8-bit CU-fused kernels: ONE CTA of 16 warps per SM, because the window is staged four times (byte phases 0..3, see
+// cu_load_ref): 4 x 37 KB for a CTU at +-64.  The 16-bit kernels keep two CTAs of 8 warps.
+constexpr int CU8_THREADS = 512;
+constexpr int CU8_WARPS = CU8_THREADS / 32;
 
 struct S8Bundle {             // 128 bytes
   int32_t org_off, win_off;   // byte offsets of the CU's top-left sample / of candidate (lt_x, lt_y) in the staged tiles
   int32_t nx, ny;
   int32_t lt_x, lt_y, pred_x, pred_y;
   uint32_t lambda;
-  int32_t n_blk;              // ceil(nx / 16)
+  int32_t n_blk;              // 16-column blocks per candidate row: ceil((xal + nx) / 16) for 8-bit planes, ceil(nx / 8) for 16-bit
   int32_t item_start, n_items;
   int32_t out_idx[CU_SLOTS];  // task index per partition slot (-1: that PU is not in the job list)
   int32_t n_rowgroups;        // ceil(ny / KY)
   int32_t cy_first;           // first candidate row of this bundle in the PU's window (tall windows are split by rows)
   int32_t shr;                // bitDepth - 8 (distortion precision adjustment); 0 for 8-bit planes
-  int32_t pad[4];
+  int32_t xal;                // 8-bit planes: bytes between the 16-byte boundary below candidate column 0 and that column (blocks are
+                              // aligned in shared memory; columns of the first / last block outside the window are masked)
+  int32_t step_g, step_blk;   // (quads per item step) / n_blk and % n_blk: how far a quad moves per item step
+  int32_t pad[1];
 };
 
 // partition slots: 0 2Nx2N | 1,2 2NxN top,bottom | 3,4 Nx2N left,right | 5,6 2NxnU | 7,8 2NxnD | 9,10 nLx2N | 11,12 nRx2N
@@ -76,38 +83,57 @@ __device__ __forceinline__ void cu_load_org(const uint8_t* p, uint32_t (&o)[WW])
   }
 }
 
+// The staged window exists four times in shared memory: copy s holds the rows shifted left by s bytes (built once per
+// CTA after the bulk copies land).  A lane whose candidates start s bytes past a 16-byte boundary reads copy s with
+// aligned LDS.128 and gets its reference words ready to use: no per-word funnel shift in the inner loop (the ALU pipe
+// that executes VABSDIFF4 also executes SHF, and it was the bound).  WW + 3 words serve the lane's four candidates.
+template <int WW>
+__device__ __forceinline__ void cu_load_ref(const uint8_t* p, uint32_t (&w)[WW + 3]) {
+  constexpr int NW = WW + 3;
+#pragma unroll
+  for (int i = 0; i < NW / 4; i++) {
+    const uint4 v = reinterpret_cast<const uint4*>(p)[i];
+    w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+  }
+  if constexpr (NW % 4 == 3) {                           // WW = 4, 8, 16: 7, 11, 19 words -> the last LDS.128 carries one spare word
+    const uint4 v = reinterpret_cast<const uint4*>(p)[NW / 4];
+    w[NW - 3] = v.x; w[NW - 2] = v.y; w[NW - 1] = v.z;
+  } else if constexpr (NW % 4 == 1) {                    // WW = 2: five words
+    w[NW - 1] = *reinterpret_cast<const uint32_t*>(p + 16 * (NW / 4));
+  }
+}
+
+// row address: one IMAD on the FMA pipe (a chain of pointer increments would sit on the ALU pipe next to VABSDIFF4)
+__device__ __forceinline__ const uint8_t* cu_row_ptr(const uint8_t* base, int row, int pitch) {
+  return base + __mul24(row, pitch);
+}
+
 // one reference row against one original row: the words of cell column c feed acc[c][k] (k = candidate column)
 template <int WW, int NC>
-__device__ __forceinline__ void cu_row(const uint8_t* rp8, const uint32_t (&o)[WW], uint32_t sh, uint32_t (&acc)[NC][4]) {
-  const uint32_t* rp = reinterpret_cast<const uint32_t*>(rp8);
-  uint32_t lo = rp[0];
+__device__ __forceinline__ void cu_row(const uint8_t* rp8, const uint32_t (&o)[WW], uint32_t (&acc)[NC][4]) {
+  uint32_t w[WW + 3];
+  cu_load_ref<WW>(rp8, w);
 #pragma unroll
   for (int j = 0; j < WW + 3; j++) {
-    const uint32_t hi = rp[j + 1];
-    const uint32_t sw = __funnelshift_r(lo, hi, sh);
-    lo = hi;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int i = j - k;
-      if (i >= 0 && i < WW) acc[i / (WW / NC)][k] = sad4_acc(sw, o[i], acc[i / (WW / NC)][k]);
+      if (i >= 0 && i < WW) acc[i / (WW / NC)][k] = sad4_acc(w[j], o[i], acc[i / (WW / NC)][k]);
     }
   }
 }
 
 // same, every word into one accumulator per candidate column (odd-row strips)
 template <int WW>
-__device__ __forceinline__ void cu_row1(const uint8_t* rp8, const uint32_t (&o)[WW], uint32_t sh, uint32_t (&acc)[4]) {
-  const uint32_t* rp = reinterpret_cast<const uint32_t*>(rp8);
-  uint32_t lo = rp[0];
+__device__ __forceinline__ void cu_row1(const uint8_t* rp8, const uint32_t (&o)[WW], uint32_t (&acc)[4]) {
+  uint32_t w[WW + 3];
+  cu_load_ref<WW>(rp8, w);
 #pragma unroll
   for (int j = 0; j < WW + 3; j++) {
-    const uint32_t hi = rp[j + 1];
-    const uint32_t sw = __funnelshift_r(lo, hi, sh);
-    lo = hi;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int i = j - k;
-      if (i >= 0 && i < WW) acc[k] = sad4_acc(sw, o[i], acc[k]);
+      if (i >= 0 && i < WW) acc[k] = sad4_acc(w[j], o[i], acc[k]);
     }
   }
 }
@@ -117,49 +143,76 @@ __device__ __forceinline__ void cu_row1(const uint8_t* rp8, const uint32_t (&o)[
 // it visits them (= raster order inside the lane), so an unsigned min is "strict '<', first wins" (TEncSearch.cpp:
 // 3813-3835).  Items are dealt to warps round-robin, which makes the local index decodable at flush time.
 constexpr int CU_LOCAL_BITS = 11;
-__device__ __forceinline__ void cu_min(uint32_t& best, uint32_t val_scaled, uint32_t base) {
-  best = min(best, val_scaled + base);
-}
+// Block columns outside the window (blocks are aligned in shared memory, not in the window) must never win.  For CUs up
+// to 32x32 their keys start at CU_KEY_MASKED = 2^32 - 1 - maxSAD * 2^11: key = sad * 2^11 + base cannot wrap, and no
+// real key (cost < 32*32*255 + 2^16) reaches it.  64x64 CUs have no such gap in 32 bits and skip the update instead.
+__host__ __device__ constexpr uint32_t cu_key_masked(int S) { return 0xffffffffu - ((uint32_t)(S * S * 255) << CU_LOCAL_BITS); }
 
-// S >= 16: grid E[4][4][k], odd-row strips O[4][k]; derives the 13 PU costs of candidate column k and updates the argmins
+// keys of candidate columns ka, kb -> running minima (VIMNMX3 when both columns are given)
+__device__ __forceinline__ void cu_min2(uint32_t& best, uint32_t a, uint32_t b) { best = min(min(best, a), b); }
+
+// S >= 16: per candidate column k, P[r][c] = partial SAD of cell column c over the strips 0..r (prefix sums come for
+// free: VABSDIFF4 takes its addend from the strip above), OP[r] = odd rows of the strips 0..r (FEN only; for S = 32
+// only strips 0 and 3 have odd rows that any PU needs, OP[3] = strip 0 + strip 3).  Derives the 13 PU keys of the
+// columns KA and KB (KB < 0: one column) and updates the argmins.  key(x, M) = x * M + base: one IMAD per PU; a PU
+// that is the complement of another inside the CU takes key(total) - x * M (still one IMAD, no sum of its own).
 template <int S, bool FEN>
-__device__ __forceinline__ void cu_epilogue16(const uint32_t (&E)[4][4][4], const uint32_t (&O)[4][4], int k, uint32_t base,
-                                              uint32_t (&best)[CU_SLOTS]) {
-  uint32_t er[4], ec[4];
-#pragma unroll
-  for (int r = 0; r < 4; r++) er[r] = E[r][0][k] + E[r][1][k] + E[r][2][k] + E[r][3][k];
-#pragma unroll
-  for (int c = 0; c < 4; c++) ec[c] = E[0][c][k] + E[1][c][k] + E[2][c][k] + E[3][c][k];
-  // a PU with <= 8 rows under FEN visits every row: add the odd rows of its strips; all others shift by iSubShift
-  constexpr bool f1 = FEN && cu_slot_h(S, 1) <= 8;      // 2NxN halves (S == 16)
-  constexpr bool f5 = FEN && cu_slot_h(S, 5) <= 8;      // AMP quarter strips (S == 16, 32)
-  constexpr uint32_t M1 = 1u << CU_LOCAL_BITS;          // key scale of a full-row PU
-  constexpr uint32_t MS = M1 << (FEN ? 1 : 0);          // ... of a PU with iSubShift = FEN
-  const uint32_t top = er[0] + er[1], bot = er[2] + er[3];
-  cu_min(best[0], (top + bot) * MS, base);
-  cu_min(best[1], f1 ? (top + O[0][k] + O[1][k]) * M1 : top * MS, base);
-  cu_min(best[2], f1 ? (bot + O[2][k] + O[3][k]) * M1 : bot * MS, base);
-  cu_min(best[3], (ec[0] + ec[1]) * MS, base);
-  cu_min(best[4], (ec[2] + ec[3]) * MS, base);
-  cu_min(best[5], f5 ? (er[0] + O[0][k]) * M1 : er[0] * MS, base);
-  cu_min(best[6], (er[1] + bot) * MS, base);
-  cu_min(best[7], (top + er[2]) * MS, base);
-  cu_min(best[8], f5 ? (er[3] + O[3][k]) * M1 : er[3] * MS, base);
-  cu_min(best[9], ec[0] * MS, base);
-  cu_min(best[10], (ec[1] + ec[2] + ec[3]) * MS, base);
-  cu_min(best[11], (ec[0] + ec[1] + ec[2]) * MS, base);
-  cu_min(best[12], ec[3] * MS, base);
-}
+struct CuKeys {
+  uint32_t v[CU_SLOTS];
+  __device__ __forceinline__ CuKeys(const uint32_t (&P)[4][4][4], const uint32_t (&OP)[4][4], int k, uint32_t base) {
+    // a PU with <= 8 rows under FEN visits every row: add the odd rows of its strips; all others shift by iSubShift
+    constexpr bool f1 = FEN && cu_slot_h(S, 1) <= 8;      // 2NxN halves (S == 16)
+    constexpr bool f5 = FEN && cu_slot_h(S, 5) <= 8;      // AMP quarter strips (S == 16, 32)
+    constexpr uint32_t M1 = 1u << CU_LOCAL_BITS;          // key scale of a full-row PU
+    constexpr uint32_t MS = M1 << (FEN ? 1 : 0);          // ... of a PU with iSubShift = FEN
+    const uint32_t r0 = P[0][0][k] + P[0][1][k] + P[0][2][k] + P[0][3][k];      // strip 0
+    const uint32_t r2 = P[2][0][k] + P[2][1][k] + P[2][2][k] + P[2][3][k];      // strips 0..2
+    const uint32_t tot = P[3][0][k] + P[3][1][k] + P[3][2][k] + P[3][3][k];
+    const uint32_t c0 = P[3][0][k], c3 = P[3][3][k], left = c0 + P[3][1][k];
+    const uint32_t k0 = tot * MS + base;
+    v[0] = k0;
+    if constexpr (f1) {          // S == 16 under FEN: 16x8 halves visit every row
+      const uint32_t a = P[1][0][k] + P[1][1][k] + P[1][2][k] + P[1][3][k] + OP[1][k];
+      const uint32_t kb = (tot + OP[3][k]) * M1 + base;
+      v[1] = a * M1 + base;
+      v[2] = kb - a * M1;
+      v[5] = (r0 + OP[0][k]) * M1 + base;
+      v[8] = kb - (r2 + OP[2][k]) * M1;
+    } else {
+      const uint32_t r1 = P[1][0][k] + P[1][1][k] + P[1][2][k] + P[1][3][k];    // strips 0..1
+      v[1] = r1 * MS + base;
+      v[2] = k0 - r1 * MS;
+      if constexpr (f5) {        // S == 32 under FEN: 32x8 strips visit every row
+        const uint32_t kb = (tot + OP[3][k]) * M1 + base;
+        v[5] = (r0 + OP[0][k]) * M1 + base;
+        v[8] = kb - (r2 + OP[0][k]) * M1;
+      } else {
+        v[5] = r0 * MS + base;
+        v[8] = k0 - r2 * MS;
+      }
+    }
+    v[3] = left * MS + base;
+    v[4] = k0 - left * MS;
+    v[6] = k0 - r0 * MS;
+    v[7] = r2 * MS + base;
+    v[9] = c0 * MS + base;
+    v[10] = k0 - c0 * MS;
+    v[11] = k0 - c3 * MS;
+    v[12] = c3 * MS + base;
+  }
+};
 
 template <int S, bool FEN>
-__global__ void __launch_bounds__(S8_THREADS, 2)
+__global__ void __launch_bounds__(CU8_THREADS, 1)
 k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bundles, unsigned long long* __restrict__ keys,
              DevPlane cur_plane, DevPlane ref_plane) {
   typedef CuTraits<S, FEN> T;
   constexpr int NSLOT = (S == 8) ? 5 : CU_SLOTS;
+  constexpr bool MASK_BY_KEY = S <= 32;                 // see cu_key_masked
+  constexpr uint32_t KEY_NONE = MASK_BY_KEY ? cu_key_masked(S) : 0xffffffffu;   // best >= KEY_NONE: no candidate yet
   extern __shared__ __align__(128) uint8_t s8_smem[];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ S8Bundle s_bd[S8_WARPS];
+  __shared__ S8Bundle s_bd[CU8_WARPS];
 
   const S8Unit un = units[blockIdx.x];
   uint8_t* s_ref = s8_smem;
@@ -175,14 +228,31 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   {
     const uint8_t* gref = reinterpret_cast<const uint8_t*>(ref_plane.base) +
                           (size_t)(un.ref_by + ref_plane.margin_y) * ref_plane.pitch + (un.ref_bx + ref_plane.margin_x);
-    for (int r = threadIdx.x; r < un.ref_rows; r += S8_THREADS)
+    for (int r = threadIdx.x; r < un.ref_rows; r += CU8_THREADS)
       bulk_g2s(s_ref + r * un.ref_pitch, gref + (size_t)r * ref_plane.pitch, (uint32_t)un.ref_pitch, &s_bar);
     const uint8_t* gorg = reinterpret_cast<const uint8_t*>(cur_plane.base) +
                           (size_t)(un.org_by + cur_plane.margin_y) * cur_plane.pitch + (un.org_bx + cur_plane.margin_x);
-    for (int r = (int)threadIdx.x - 128; r < un.org_rows; r += S8_THREADS)
+    for (int r = (int)threadIdx.x - 256; r < un.org_rows; r += CU8_THREADS)
       if (r >= 0) bulk_g2s(s_org + r * un.org_pitch, gorg + (size_t)r * cur_plane.pitch, (uint32_t)un.org_pitch, &s_bar);
   }
   mbar_wait(&s_bar, 0);
+  {
+    // copies 1..3: the window shifted left by 1..3 bytes (the word past the last row belongs to the slack rows)
+    const int nvec = (un.ref_pitch * un.ref_rows) >> 4;
+    const int cs = un.copy_stride;
+    for (int i = threadIdx.x; i < nvec; i += CU8_THREADS) {
+      const uint4 a = reinterpret_cast<const uint4*>(s_ref)[i];
+      const uint32_t e = reinterpret_cast<const uint32_t*>(s_ref)[4 * i + 4];
+#pragma unroll
+      for (int c = 1; c < 4; c++) {
+        uint4 o;
+        o.x = __funnelshift_r(a.x, a.y, 8 * c); o.y = __funnelshift_r(a.y, a.z, 8 * c);
+        o.z = __funnelshift_r(a.z, a.w, 8 * c); o.w = __funnelshift_r(a.w, e, 8 * c);
+        reinterpret_cast<uint4*>(s_ref + c * cs)[i] = o;
+      }
+    }
+  }
+  __syncthreads();
 
   int bslot = un.job_first;
   S8Bundle& bd = s_bd[warp];
@@ -193,6 +263,8 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   };
   load_bundle();
   constexpr int LK = (S == 8) ? 4 : 2;                // bits of the within-tile candidate index
+  const int quad = lane >> 2, sub = lane & 3;
+  const uint8_t* s_copy = s_ref + sub * un.copy_stride;   // this lane's byte phase
   uint32_t best[CU_SLOTS];
 #pragma unroll
   for (int s = 0; s < CU_SLOTS; s++) best[s] = 0xffffffffu;
@@ -201,13 +273,13 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) {
       unsigned long long b = ~0ull;
-      if (best[s] != 0xffffffffu) {
+      if (best[s] < KEY_NONE) {
         const uint32_t local = best[s] & ((1u << CU_LOCAL_BITS) - 1u);
-        const int it = first_item + (int)(local >> LK) * S8_WARPS;
-        const int q = (it - bd.item_start) * 8 + (lane >> 2);
+        const int it = first_item + (int)(local >> LK) * CU8_WARPS;
+        const int q = (it - bd.item_start) * 8 + quad;
         const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
         const int w = (int)(local & ((1u << LK) - 1u));
-        const int cyi = bd.cy_first + g * T::KY + (w >> 2), cxi = min(blk * 16, bd.nx - 16) + (lane & 3) + 4 * (w & 3);
+        const int cyi = bd.cy_first + g * T::KY + (w >> 2), cxi = blk * 16 + sub + 4 * (w & 3) - bd.xal;
         b = make_key(best[s] >> CU_LOCAL_BITS, (uint32_t)(cyi * bd.nx + cxi));
       }
 #pragma unroll
@@ -219,60 +291,68 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
       best[s] = 0xffffffffu;
     }
   };
+  // (row group, block) of this lane's quad in the current item; an item step is 16 warps x 8 quads = 128 quads further
+  int g = 0, blk = 0;
+  auto locate = [&](int item) {
+    const int q = (item - bd.item_start) * 8 + quad;
+    g = q / bd.n_blk; blk = q - g * bd.n_blk;
+  };
+  locate(un.item_first + warp);
 
-  for (int item = un.item_first + warp; item < un.item_last; item += S8_WARPS) {
+  for (int item = un.item_first + warp; item < un.item_last; item += CU8_WARPS) {
     if (item >= bd.item_start + bd.n_items) {
       flush();
       do { bslot++; } while (item >= bundles[bslot].item_start + bundles[bslot].n_items);
       load_bundle();
       first_item = item;
+      locate(item);
     }
-    const uint32_t tile_local = (uint32_t)((item - first_item) / S8_WARPS) << LK;
-    const int q = (item - bd.item_start) * 8 + (lane >> 2);
-    if (q < bd.n_blk * bd.n_rowgroups) {
-    const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
+    const uint32_t tile_local = (uint32_t)((item - first_item) / CU8_WARPS) << LK;
+    if (g < bd.n_rowgroups) {
     const int cyi0 = g * T::KY;
-    const int cxi0 = min(blk * 16, bd.nx - 16) + (lane & 3);          // the last block overlaps its neighbour
-    const int off = bd.win_off + cyi0 * un.ref_pitch + cxi0;
-    const uint8_t* refp = s_ref + (off & ~3);
-    const uint32_t sh = (uint32_t)(off & 3) * 8u;
+    const int cx0 = blk * 16 + sub - bd.xal;                            // window column of candidate k = 0 (may be < 0)
+    const uint8_t* refp = s_copy + bd.win_off - bd.xal + cyi0 * un.ref_pitch + blk * 16;     // 16-byte aligned
     const uint8_t* orgp = s_org + bd.org_off;
+    const int rpitch = un.ref_pitch, opitch = un.org_pitch;
     uint32_t px[4];
+    bool valid[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) px[k] = bd.lambda * eg_bits(((bd.lt_x + cxi0 + 4 * k) << 2) - bd.pred_x);
+    for (int k = 0; k < 4; k++) {
+      px[k] = bd.lambda * eg_bits(((bd.lt_x + cx0 + 4 * k) << 2) - bd.pred_x);
+      valid[k] = (unsigned)(cx0 + 4 * k) < (unsigned)bd.nx;             // block columns outside the window take no part
+    }
 
     if constexpr (S == 8) {
-      // four candidate rows per tile, whole CU (8 rows x 2 words) in registers, quadrant sums Q[row half][column half]
+      // four candidate rows per tile, whole CU (8 rows x 2 words) in registers; per candidate: Q[0][c] = rows 0..3 of
+      // column half c, Q[1][c] = rows 0..7 (the lower half continues the upper half's accumulators)
       uint32_t o[8][2];
 #pragma unroll
-      for (int r = 0; r < 8; r++) cu_load_org<2>(orgp + r * un.org_pitch, o[r]);
+      for (int r = 0; r < 8; r++) cu_load_org<2>(cu_row_ptr(orgp, r, opitch), o[r]);
       uint32_t Q[T::KY][2][2][4];
 #pragma unroll
       for (int a = 0; a < T::KY; a++)
 #pragma unroll
-        for (int b = 0; b < 2; b++)
+        for (int c = 0; c < 2; c++)
 #pragma unroll
-          for (int c = 0; c < 2; c++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) Q[a][b][c][k] = 0;
+          for (int k = 0; k < 4; k++) Q[a][0][c][k] = 0;
 #pragma unroll
       for (int r = 0; r < 8 + T::KY - 1; r++) {
-        const uint32_t* rp = reinterpret_cast<const uint32_t*>(refp + r * un.ref_pitch);
-        uint32_t lo = rp[0];
+        uint32_t w[5];
+        cu_load_ref<2>(cu_row_ptr(refp, r, rpitch), w);
 #pragma unroll
-        for (int j = 0; j < 2 + 3; j++) {
-          const uint32_t hi = rp[j + 1];
-          const uint32_t sw = __funnelshift_r(lo, hi, sh);
-          lo = hi;
+        for (int jy = 0; jy < T::KY; jy++) {
+          const int orow = r - jy;
+          if (orow >= 0 && orow < 8) {
 #pragma unroll
-          for (int jy = 0; jy < T::KY; jy++) {
-            if (r - jy >= 0 && r - jy < 8) {
+            for (int j = 0; j < 5; j++)
 #pragma unroll
               for (int k = 0; k < 4; k++) {
                 const int i = j - k;
-                if (i >= 0 && i < 2) Q[jy][(r - jy) >> 2][i][k] = sad4_acc(sw, o[r - jy][i], Q[jy][(r - jy) >> 2][i][k]);
+                if (i >= 0 && i < 2) {
+                  const uint32_t addend = (orow == 4) ? Q[jy][0][i][k] : Q[jy][orow >> 2][i][k];
+                  Q[jy][orow >> 2][i][k] = sad4_acc(w[j], o[orow][i], addend);
+                }
               }
-            }
           }
         }
       }
@@ -281,44 +361,47 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
         const int cyi = bd.cy_first + cyi0 + jy;
         if (cyi0 + jy < bd.ny) {
           const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + cyi) << 2) - bd.pred_y);
+          constexpr uint32_t M1 = 1u << CU_LOCAL_BITS;
+          uint32_t key[4][5];
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            constexpr uint32_t M1 = 1u << CU_LOCAL_BITS;
-            const uint32_t base = (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)(jy * 4 + k);
-            const uint32_t t = Q[jy][0][0][k] + Q[jy][0][1][k], b = Q[jy][1][0][k] + Q[jy][1][1][k];
-            const uint32_t l = Q[jy][0][0][k] + Q[jy][1][0][k], r = Q[jy][0][1][k] + Q[jy][1][1][k];
-            cu_min(best[0], (t + b) * M1, base);     // 8x8  (no PU of an 8x8 CU has more than 8 rows: iSubShift = 0)
-            cu_min(best[1], t * M1, base);           // 8x4 top
-            cu_min(best[2], b * M1, base);           // 8x4 bottom
-            cu_min(best[3], l * M1, base);           // 4x8 left
-            cu_min(best[4], r * M1, base);           // 4x8 right
+            uint32_t base = (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)(jy * 4 + k);
+            base = valid[k] ? base : KEY_NONE;
+            const uint32_t t = Q[jy][0][0][k] + Q[jy][0][1][k], l = Q[jy][1][0][k];
+            const uint32_t k0 = (l + Q[jy][1][1][k]) * M1 + base;
+            key[k][0] = k0;                       // 8x8  (no PU of an 8x8 CU has more than 8 rows: iSubShift = 0)
+            key[k][1] = t * M1 + base;            // 8x4 top
+            key[k][2] = k0 - t * M1;              // 8x4 bottom = whole - top
+            key[k][3] = l * M1 + base;            // 4x8 left
+            key[k][4] = k0 - l * M1;              // 4x8 right = whole - left
           }
+#pragma unroll
+          for (int s = 0; s < 5; s++) { cu_min2(best[s], key[0][s], key[1][s]); cu_min2(best[s], key[2][s], key[3][s]); }
         }
       }
     } else {
-      uint32_t E[4][4][4], O[4][4];
-#pragma unroll
-      for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          O[a][k] = 0;
-#pragma unroll
-          for (int c = 0; c < 4; c++) E[a][c][k] = 0;
-        }
+      uint32_t P[4][4][4], OP[4][4];
 #pragma unroll
       for (int r = 0; r < 4; r++) {                                      // strips: static, so the grid row index is too
         const bool odd_here = T::ODD_ALL || (T::ODD_EDGE && (r == 0 || r == 3));
+        constexpr int OPREV[4] = {0, 0, 1, T::ODD_ALL ? 2 : 0};          // the strip whose odd-row sums strip r continues
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+          for (int c = 0; c < 4; c++) P[r][c][k] = r ? P[r - 1][c][k] : 0u;
+          OP[r][k] = r ? OP[OPREV[r]][k] : 0u;
+        }
         if constexpr (T::PARITY) {
 #pragma unroll 2
           for (int rr = 0; rr < T::G; rr += 2) {
             const int row = r * T::G + rr;
             uint32_t o[T::WW];
-            cu_load_org<T::WW>(orgp + row * un.org_pitch, o);
-            cu_row<T::WW, 4>(refp + row * un.ref_pitch, o, sh, E[r]);
+            cu_load_org<T::WW>(cu_row_ptr(orgp, row, opitch), o);
+            cu_row<T::WW, 4>(cu_row_ptr(refp, row, rpitch), o, P[r]);
             if (odd_here) {
               uint32_t o1[T::WW];
-              cu_load_org<T::WW>(orgp + (row + 1) * un.org_pitch, o1);
-              cu_row1<T::WW>(refp + (row + 1) * un.ref_pitch, o1, sh, O[r]);
+              cu_load_org<T::WW>(cu_row_ptr(orgp, row + 1, opitch), o1);
+              cu_row1<T::WW>(cu_row_ptr(refp, row + 1, rpitch), o1, OP[r]);
             }
           }
         } else {
@@ -326,19 +409,37 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
           for (int rr = 0; rr < T::G; rr++) {
             const int row = r * T::G + rr;
             uint32_t o[T::WW];
-            cu_load_org<T::WW>(orgp + row * un.org_pitch, o);
-            cu_row<T::WW, 4>(refp + row * un.ref_pitch, o, sh, E[r]);
+            cu_load_org<T::WW>(cu_row_ptr(orgp, row, opitch), o);
+            cu_row<T::WW, 4>(cu_row_ptr(refp, row, rpitch), o, P[r]);
           }
         }
       }
       if (cyi0 < bd.ny) {
         const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + bd.cy_first + cyi0) << 2) - bd.pred_y);
+        uint32_t base[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          cu_epilogue16<S, FEN>(E, O, k, (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)k, best);
+        for (int k = 0; k < 4; k++) base[k] = (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)k;
+        if constexpr (MASK_BY_KEY) {
+#pragma unroll
+          for (int kk = 0; kk < 4; kk += 2) {
+            const CuKeys<S, FEN> a(P, OP, kk, valid[kk] ? base[kk] : KEY_NONE), b(P, OP, kk + 1, valid[kk + 1] ? base[kk + 1] : KEY_NONE);
+#pragma unroll
+            for (int s = 0; s < CU_SLOTS; s++) cu_min2(best[s], a.v[s], b.v[s]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (valid[k]) {
+              const CuKeys<S, FEN> a(P, OP, k, base[k]);
+#pragma unroll
+              for (int s = 0; s < CU_SLOTS; s++) best[s] = min(best[s], a.v[s]);
+            }
+        }
       }
     }
-    }   // q in range
+    }   // row group in range
+    blk += bd.step_blk; g += bd.step_g;                                  // 128 quads further
+    if (blk >= bd.n_blk) { blk -= bd.n_blk; g++; }
   }
   flush();
 }
@@ -385,11 +486,26 @@ inline int cu_configure(std::string* err) {
 // geometry of the lane layout per sample size: 8-bit: quads of lanes own 16 columns, 8 quads per warp-item;
 // 16-bit: pairs of lanes own 8 columns, 16 pairs per warp-item (hmb200_search16_cu.cuh)
 struct CuGeom {
-  int bps, blkw, groups;
+  int bps, blkw, groups, warps, smem_group;     // smem_group: dynamic shared memory a group may use
   int ky(int S) const { return bps == 1 ? cu_ky(S) : (S == 8 ? 2 : 1); }
   int lk(int S) const { return S == 8 ? 4 : 2; }
 };
-inline CuGeom cu_geom(int bps) { return bps == 1 ? CuGeom{1, 16, 8} : CuGeom{2, 8, 16}; }
+inline CuGeom cu_geom(int bps) { return bps == 1 ? CuGeom{1, 16, 8, CU8_WARPS, S8_SMEM_MAX} : CuGeom{2, 8, 16, S8_WARPS, S8_SMEM_SHARED2}; }
+
+// Dynamic shared memory of a CU-fused group.  8-bit planes: four byte-shifted copies of the window (see cu_load_ref),
+// copy_stride = 32 mod 128 so that the four lanes of a quad (one copy each) and the next quad (16 bytes further) hit
+// disjoint banks; a few slack rows behind the window for masked candidates; then the original tile.
+constexpr int CU8_SLACK_ROWS = 4;
+inline int cu_smem_need(const S8Box& rb, const S8Box& ob, int* org_off, int* copy_stride, int bps) {
+  if (bps != 1) { if (copy_stride) *copy_stride = 0; return s8_smem_need(rb, ob, org_off, bps); }
+  const int rp = s8_ce(rb.x1) - s8_fl(rb.x0), rr = rb.y1 - rb.y0 + CU8_SLACK_ROWS;
+  const int op = s8_ce(ob.x1) - s8_fl(ob.x0), orr = ob.y1 - ob.y0;
+  const int cs = ((rp * rr + 16 + 127) & ~127) + 32;
+  const int ro = (4 * cs + 127) & ~127;
+  if (copy_stride) *copy_stride = cs;
+  if (org_off) *org_off = ro;
+  return ro + op * orr + 16;
+}
 
 // Finds CU bundles: PUs that are partitions of the same aligned S x S CU and share window, predictor and lambda.
 // taken[i] = 1 for every bundled task (the per-PU schedule skips those).
@@ -406,15 +522,15 @@ inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, int bps, st
     const int S = std::max(t.w, t.h);
     if (!(S == 8 || S == 16 || S == 32 || S == 64) || t.ref_x != t.org_x || t.ref_y != t.org_y || t.org_x < 0 || t.org_y < 0) continue;
     const int nx = t.rb_x - t.lt_x + 1, ny = t.rb_y - t.lt_y + 1;
-    if (nx < G.blkw || ny < 1) continue;
+    if (nx < (bps == 1 ? 1 : G.blkw) || ny < 1) continue;    // 8-bit blocks are masked per column; 16-bit blocks overlap
     const int cx = t.org_x - t.org_x % S, cy = t.org_y - t.org_y % S;
     // even a one-row-group slice of the window must fit in shared memory, and the per-lane local candidate index of
     // a slice that fills it must fit CU_LOCAL_BITS (see cu_min)
-    if (s8_smem_need(S8Box{cx + t.lt_x, cy + t.lt_y, cx + t.rb_x + S, cy + t.lt_y + G.ky(S) - 1 + S}, S8Box{cx, cy, cx + S, cy + S}, nullptr, bps) > S8_SMEM_MAX) continue;
+    if (cu_smem_need(S8Box{cx + t.lt_x, cy + t.lt_y, cx + t.rb_x + S, cy + t.lt_y + G.ky(S) - 1 + S}, S8Box{cx, cy, cx + S, cy + S}, nullptr, nullptr, bps) > S8_SMEM_MAX) continue;
     {
-      const int n_blk = (nx + G.blkw - 1) / G.blkw, nrg = (ny + G.ky(S) - 1) / G.ky(S);
+      const int n_blk = (nx + (bps == 1 ? 15 : 0) + G.blkw - 1) / G.blkw, nrg = (ny + G.ky(S) - 1) / G.ky(S);   // worst alignment
       const int n_items = (n_blk * nrg + G.groups - 1) / G.groups;
-      if (n_items / S8_WARPS + 2 >= (1 << (CU_LOCAL_BITS - G.lk(S)))) continue;
+      if (n_items / G.warps + 2 >= (1 << (CU_LOCAL_BITS - G.lk(S)))) continue;
     }
     int slot = -1;
     for (int s = 0; s < (S == 8 ? 5 : CU_SLOTS); s++)
@@ -468,7 +584,7 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     const S8Box ob{b.cu_x, b.cu_y, b.cu_x + b.S, b.cu_y + b.S};
     auto rbox_of = [&](int r0, int n) { return S8Box{b.cu_x + t.lt_x, b.cu_y + t.lt_y + r0, b.cu_x + t.rb_x + b.S, b.cu_y + t.lt_y + r0 + n - 1 + b.S}; };
     int parts = 1, rows = ny;
-    while (s8_smem_need(rbox_of(0, rows), ob, nullptr, bps) > S8_SMEM_SHARED2 && rows > ky) {
+    while (cu_smem_need(rbox_of(0, rows), ob, nullptr, nullptr, bps) > GM.smem_group && rows > ky) {
       parts++;
       rows = (((ny + parts - 1) / parts + ky - 1) / ky) * ky;
     }
@@ -488,12 +604,12 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     if (!groups.empty()) {
       Group& g = groups.back();
       const S8Box nr = s8_union(g.rb, ents[p].rb), no = s8_union(g.ob, ents[p].ob);
-      if (g.count < 4096 && no.x1 - no.x0 <= 128 && no.y1 - no.y0 <= 128 && s8_smem_need(nr, no, nullptr, bps) <= S8_SMEM_SHARED2) {
+      if (g.count < 4096 && no.x1 - no.x0 <= 128 && no.y1 - no.y0 <= 128 && cu_smem_need(nr, no, nullptr, nullptr, bps) <= GM.smem_group) {
         g.rb = nr; g.ob = no; g.count++;
         continue;
       }
     }
-    if (s8_smem_need(ents[p].rb, ents[p].ob, nullptr, bps) > S8_SMEM_MAX) { if (err) *err = "cu_build_schedule: window too large"; return false; }
+    if (cu_smem_need(ents[p].rb, ents[p].ob, nullptr, nullptr, bps) > S8_SMEM_MAX) { if (err) *err = "cu_build_schedule: window too large"; return false; }
     groups.push_back(Group{(int)p, 1, ents[p].rb, ents[p].ob});
   }
   auto rows_visited = [](int S, bool fen) { return (fen && S >= 16) ? (S == 16 ? 16 : S == 32 ? 24 : 32) : S; };
@@ -525,7 +641,9 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
       d.win_off = (b.cu_y + t.lt_y + e.cy_first - g.rb.y0) * rpitch + (b.cu_x + t.lt_x - rx0) * bps;
       d.nx = t.rb_x - t.lt_x + 1; d.ny = e.ny; d.cy_first = e.cy_first; d.shr = bit_depth - 8;
       d.lt_x = t.lt_x; d.lt_y = t.lt_y; d.pred_x = t.pred_x; d.pred_y = t.pred_y; d.lambda = t.lambda_cost;
-      d.n_blk = (d.nx + GM.blkw - 1) / GM.blkw;
+      d.xal = (bps == 1) ? (d.win_off & 15) : 0;           // window pitch and origin are multiples of 16 bytes
+      d.n_blk = (d.xal + d.nx + GM.blkw - 1) / GM.blkw;
+      d.step_g = (GM.groups * GM.warps) / d.n_blk; d.step_blk = (GM.groups * GM.warps) % d.n_blk;
       d.n_rowgroups = (d.ny + GM.ky(b.S) - 1) / GM.ky(b.S);
       d.n_items = (d.n_blk * d.n_rowgroups + GM.groups - 1) / GM.groups;
       d.item_start = item; item += d.n_items;
@@ -540,9 +658,9 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     all_r = s8_union(all_r, g.rb); all_o = s8_union(all_o, g.ob);
   }
   long long target[CUV_COUNT];
-  int per_slot = 6;                                    // units per resident CTA slot and variant (measured optimum 5-6; knob: HMB200_UNITS_PER_SLOT)
+  int per_slot = bps == 1 ? 3 : 6;                     // units per resident CTA slot and variant (knob: HMB200_UNITS_PER_SLOT); 8-bit: one CTA per SM
   if (const char* e = getenv("HMB200_UNITS_PER_SLOT")) per_slot = std::max(1, atoi(e));
-  for (int v = 0; v < CUV_COUNT; v++) target[v] = std::max<long long>(variant_cost[v] / std::max(1, sm_count * 2 * per_slot), 4000);
+  for (int v = 0; v < CUV_COUNT; v++) target[v] = std::max<long long>(variant_cost[v] / std::max(1, sm_count * (bps == 1 ? 1 : 2) * per_slot), 4000);
   const int S_of_variant[CUV_COUNT] = {8, 16, 16, 32, 32, 64, 64};
   const bool F_of_variant[CUV_COUNT] = {false, false, true, false, true, false, true};
   std::vector<S8Unit> units;
@@ -552,9 +670,9 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     const int rx0 = s8_fl(g.rb.x0), ox0 = s8_fl(g.ob.x0);
     u.ref_bx = rx0; u.ref_by = g.rb.y0; u.ref_pitch = (s8_ce(g.rb.x1) - rx0) * bps; u.ref_rows = g.rb.y1 - g.rb.y0;
     u.org_bx = ox0; u.org_by = g.ob.y0; u.org_pitch = (s8_ce(g.ob.x1) - ox0) * bps; u.org_rows = g.ob.y1 - g.ob.y0;
-    int org_off = 0;
-    u.smem_need = s8_smem_need(g.rb, g.ob, &org_off, bps);
-    u.org_smem_off = org_off;
+    int org_off = 0, copy_stride = 0;
+    u.smem_need = cu_smem_need(g.rb, g.ob, &org_off, &copy_stride, bps);
+    u.org_smem_off = org_off; u.copy_stride = copy_stride;
     const int bfirst = group_range[gi].first, bcount = group_range[gi].second;
     long long acc = 0;
     int ufirst_item = 0, ufirst_b = 0;
