@@ -328,6 +328,25 @@ def test_search_range_128_vs_oracle(hm):
     assert results_equal(got, exp) == []
 
 
+@pytest.mark.parametrize("lam,pred", [(0, (0, 0)), (65536 * 4, (9, -6)), (1, (-30, 21))])
+def test_fused_tie_break_flat_content(hm, lam, pred):
+    """Flat content through the CU-fused kernels (every PU of two CTUs): all SADs tie, so the MV cost and then the raster
+    order decide for each of the 13 partitions of every CU; a lane sees several tiles of one candidate-row group."""
+    W, H = 128, 128
+    flat = np.full((H, W), 131, dtype=np.uint8)
+    cur, o0, stride = padded(flat)
+    jobs = np.concatenate([hm.build_canonical_jobs(W, H, 64, lam, pred=pred, ctu_first=c, ctu_count=1) for c in (0, 3)])
+    idc = hm.register_plane_u8(flat, MARGIN, MARGIN)
+    try:
+        got = hm.me_jobs(idc, idc, jobs, flags_of(1, 1, frac=False))
+    finally:
+        hm.release_plane(idc)
+    exp, _ = Oracle(fen=1, hadme=1).run_jobs((cur, o0, stride), (cur, o0, stride), jobs, 8, False)
+    assert results_equal(got, exp, ("mv_x", "mv_y", "sad")) == []
+    if lam == 0:
+        assert np.array_equal(got["mv_x"], jobs["lt_x"]) and np.array_equal(got["mv_y"], jobs["lt_y"])
+
+
 @pytest.mark.parametrize("fen", [1, 0])
 def test_fused_windows_at_every_alignment(hm, fen):
     """CU-fused kernels stage 16-column candidate blocks aligned in shared memory and mask the columns of the first and

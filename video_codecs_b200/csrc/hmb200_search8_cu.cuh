@@ -43,7 +43,7 @@ struct S8Bundle {             // 128 bytes
   int32_t xal;                // 8-bit planes: bytes between the 16-byte boundary below candidate column 0 and that column (blocks are
                               // aligned in shared memory; columns of the first / last block outside the window are masked)
   int32_t step_g, step_blk;   // (quads per item step) / n_blk and % n_blk: how far a quad moves per item step
-  int32_t pad[1];
+  int32_t rank_bits;          // 8x8 CUs (four candidate rows per tile): bits that number a lane's tiles inside one row group
 };
 
 // partition slots: 0 2Nx2N | 1,2 2NxN top,bottom | 3,4 Nx2N left,right | 5,6 2NxnU | 7,8 2NxnD | 9,10 nLx2N | 11,12 nRx2N
@@ -141,7 +141,7 @@ __device__ __forceinline__ void cu_row1(const uint8_t* rp8, const uint32_t (&o)[
 // Per-lane running argmin as ONE 32-bit key: (cost << CU_LOCAL_BITS) | local index.  cost < 2^21 for 8-bit content
 // (SAD <= 64*32*255*2, MV cost < 2^16); the local index numbers this lane's candidates of the current CU in the order
 // it visits them (= raster order inside the lane), so an unsigned min is "strict '<', first wins" (TEncSearch.cpp:
-// 3813-3835).  Items are dealt to warps round-robin, which makes the local index decodable at flush time.
+// 3813-3835).  Every warp takes a run of consecutive items; the tile loop says how the local index is formed.
 constexpr int CU_LOCAL_BITS = 11;
 // Block columns outside the window (blocks are aligned in shared memory, not in the window) must never win.  For CUs up
 // to 32x32 their keys start at CU_KEY_MASKED = 2^32 - 1 - maxSAD * 2^11: key = sad * 2^11 + base cannot wrap, and no
@@ -261,53 +261,73 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
     reinterpret_cast<int32_t*>(&bd)[lane] = reinterpret_cast<const int32_t*>(&bundles[bslot])[lane];   // 32 ints
     __syncwarp();
   };
-  load_bundle();
   constexpr int LK = (S == 8) ? 4 : 2;                // bits of the within-tile candidate index
+  constexpr int TILE_LIMIT = 1 << (CU_LOCAL_BITS - LK);   // tiles a lane may see between two flushes
   const int quad = lane >> 2, sub = lane & 3;
   const uint8_t* s_copy = s_ref + sub * un.copy_stride;   // this lane's byte phase
   uint32_t best[CU_SLOTS];
 #pragma unroll
   for (int s = 0; s < CU_SLOTS; s++) best[s] = 0xffffffffu;
-  int first_item = un.item_first + warp;              // this warp's first item of the current CU (decodes local indices)
+  // every warp takes a contiguous run of the unit's items (round-robin dealing made every warp visit, and flush, every CU)
+  const int per_warp = (un.item_last - un.item_first + CU8_WARPS - 1) / CU8_WARPS;
+  const int w_first = un.item_first + warp * per_warp, w_last = min(w_first + per_warp, un.item_last);
+  int first_item = w_first;                           // first item since the last flush (decodes local indices)
+  int g = 0, blk = 0, g0 = 0;                         // row group / block of the lane's quad; g0: row group at the last flush (8x8 CUs)
   auto flush = [&]() {
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) {
-      unsigned long long b = ~0ull;
-      if (best[s] < KEY_NONE) {
+      // lanes number their candidates locally: reduce the cost first, then the raster index among the lanes that hold it
+      const bool have = best[s] < KEY_NONE;
+      const uint32_t cost = have ? (best[s] >> CU_LOCAL_BITS) : 0xffffffffu;
+      const uint32_t cmin = __reduce_min_sync(0xffffffffu, cost);
+      uint32_t idx = 0xffffffffu;
+      if (have && cost == cmin) {
         const uint32_t local = best[s] & ((1u << CU_LOCAL_BITS) - 1u);
-        const int it = first_item + (int)(local >> LK) * CU8_WARPS;
-        const int q = (it - bd.item_start) * 8 + quad;
-        const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
-        const int w = (int)(local & ((1u << LK) - 1u));
-        const int cyi = bd.cy_first + g * T::KY + (w >> 2), cxi = blk * 16 + sub + 4 * (w & 3) - bd.xal;
-        b = make_key(best[s] >> CU_LOCAL_BITS, (uint32_t)(cyi * bd.nx + cxi));
+        int cyi, cxi;
+        if constexpr (S == 8) {      // (candidate row since g0, tile rank inside the row group, column): see the tile loop
+          const int rb = bd.rank_bits, rowrel = (int)(local >> (2 + rb)), rank = (int)(local >> 2) & ((1 << rb) - 1);
+          const int gg = g0 + (rowrel >> 2), bb = ((quad - gg * bd.n_blk) & 7) + 8 * rank;
+          cyi = bd.cy_first + gg * T::KY + (rowrel & 3); cxi = bb * 16 + sub + 4 * (int)(local & 3u) - bd.xal;
+        } else {                     // tile number since the last flush, column
+          const int q = (first_item + (int)(local >> LK) - bd.item_start) * 8 + quad;
+          const int gg = q / bd.n_blk, bb = q - gg * bd.n_blk;
+          cyi = bd.cy_first + gg; cxi = bb * 16 + sub + 4 * (int)(local & 3u) - bd.xal;
+        }
+        idx = (uint32_t)(cyi * bd.nx + cxi);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
-        b = other < b ? other : b;
-      }
-      if (lane == 0 && b != ~0ull && bd.out_idx[s] >= 0) atomicMin(&keys[bd.out_idx[s]], b);
+      const uint32_t imin = __reduce_min_sync(0xffffffffu, idx);
+      if (lane == 0 && cmin != 0xffffffffu && bd.out_idx[s] >= 0) atomicMin(&keys[bd.out_idx[s]], make_key(cmin, imin));
       best[s] = 0xffffffffu;
     }
   };
-  // (row group, block) of this lane's quad in the current item; an item step is 16 warps x 8 quads = 128 quads further
-  int g = 0, blk = 0;
+  // (row group, block) of this lane's quad in the current item; the next item is 8 quads further
   auto locate = [&](int item) {
     const int q = (item - bd.item_start) * 8 + quad;
-    g = q / bd.n_blk; blk = q - g * bd.n_blk;
+    g = q / bd.n_blk; blk = q - g * bd.n_blk; g0 = g;
   };
-  locate(un.item_first + warp);
+  if (w_first < w_last) {
+    while (w_first >= bundles[bslot].item_start + bundles[bslot].n_items) bslot++;
+    load_bundle();
+    locate(w_first);
+  }
 
-  for (int item = un.item_first + warp; item < un.item_last; item += CU8_WARPS) {
+  for (int item = w_first; item < w_last; item++) {
     if (item >= bd.item_start + bd.n_items) {
       flush();
       do { bslot++; } while (item >= bundles[bslot].item_start + bundles[bslot].n_items);
       load_bundle();
       first_item = item;
       locate(item);
+    } else if (S == 8 ? __any_sync(0xffffffffu, (g - g0) >= (1 << (CU_LOCAL_BITS - 4 - bd.rank_bits))) : (item - first_item >= TILE_LIMIT)) {
+      flush();                                        // the local index would run out of bits
+      first_item = item; g0 = g;
     }
-    const uint32_t tile_local = (uint32_t)((item - first_item) / CU8_WARPS) << LK;
+    // Local index of a candidate inside the key: must grow in raster order along the candidates ONE LANE sees between
+    // two flushes.  S >= 16 (one candidate row per tile): the lane's tiles come in raster order, so the tile number does.
+    // S == 8 (four rows per tile): the lane may see two tiles of one row group (8 blocks apart), so the index is
+    // (candidate row since g0, rank of the tile inside its row group = blk / 8, column).
+    const uint32_t tile_local = (S == 8) ? ((uint32_t)((g - g0) * 4) << (2 + bd.rank_bits)) | ((uint32_t)(blk >> 3) << 2)
+                                         : (uint32_t)(item - first_item) << LK;
     if (g < bd.n_rowgroups) {
     const int cyi0 = g * T::KY;
     const int cx0 = blk * 16 + sub - bd.xal;                            // window column of candidate k = 0 (may be < 0)
@@ -365,7 +385,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
           uint32_t key[4][5];
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            uint32_t base = (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)(jy * 4 + k);
+            uint32_t base = ((((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)k) + ((uint32_t)jy << (2 + bd.rank_bits));
             base = valid[k] ? base : KEY_NONE;
             const uint32_t t = Q[jy][0][0][k] + Q[jy][0][1][k], l = Q[jy][1][0][k];
             const uint32_t k0 = (l + Q[jy][1][1][k]) * M1 + base;
@@ -438,10 +458,10 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
       }
     }
     }   // row group in range
-    blk += bd.step_blk; g += bd.step_g;                                  // 128 quads further
+    blk += bd.step_blk; g += bd.step_g;                                  // 8 quads further
     if (blk >= bd.n_blk) { blk -= bd.n_blk; g++; }
   }
-  flush();
+  if (w_first < w_last) flush();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -530,7 +550,7 @@ inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, int bps, st
     {
       const int n_blk = (nx + (bps == 1 ? 15 : 0) + G.blkw - 1) / G.blkw, nrg = (ny + G.ky(S) - 1) / G.ky(S);   // worst alignment
       const int n_items = (n_blk * nrg + G.groups - 1) / G.groups;
-      if (n_items / G.warps + 2 >= (1 << (CU_LOCAL_BITS - G.lk(S)))) continue;
+      if (bps != 1 && n_items / G.warps + 2 >= (1 << (CU_LOCAL_BITS - G.lk(S)))) continue;   // 8-bit kernels flush when the index runs out
     }
     int slot = -1;
     for (int s = 0; s < (S == 8 ? 5 : CU_SLOTS); s++)
@@ -643,7 +663,9 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
       d.lt_x = t.lt_x; d.lt_y = t.lt_y; d.pred_x = t.pred_x; d.pred_y = t.pred_y; d.lambda = t.lambda_cost;
       d.xal = (bps == 1) ? (d.win_off & 15) : 0;           // window pitch and origin are multiples of 16 bytes
       d.n_blk = (d.xal + d.nx + GM.blkw - 1) / GM.blkw;
-      d.step_g = (GM.groups * GM.warps) / d.n_blk; d.step_blk = (GM.groups * GM.warps) % d.n_blk;
+      d.step_g = GM.groups / d.n_blk; d.step_blk = GM.groups % d.n_blk;      // 8-bit kernels: consecutive items per warp
+      d.rank_bits = 0;
+      while ((8 << d.rank_bits) < d.n_blk) d.rank_bits++;
       d.n_rowgroups = (d.ny + GM.ky(b.S) - 1) / GM.ky(b.S);
       d.n_items = (d.n_blk * d.n_rowgroups + GM.groups - 1) / GM.groups;
       d.item_start = item; item += d.n_items;
