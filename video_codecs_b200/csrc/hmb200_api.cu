@@ -729,7 +729,8 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
     const S8CuKernel* cukern = bps == 1 ? search8_cu_kernels() : search16_cu_kernels();
     CUDA_TRY(cudaEventRecord(g.ev_fork, g.stream));
     int order[S8V_COUNT + CUV_COUNT], used = 0;       // >= 0: per-PU variant, < 0: CU-fused variant ~v
-    for (int v = CUV_COUNT - 1; v >= 0; v--) if (cu.unit_count[v] > 0) order[used++] = ~v;    // big CUs first
+    if (bps == 1) { for (int v = 0; v < CUV_COUNT; v++) if (cu.unit_count[v] > 0) order[used++] = ~v; }       // longest CTAs first: 8x8 CUs
+    else for (int v = CUV_COUNT - 1; v >= 0; v--) if (cu.unit_count[v] > 0) order[used++] = ~v;
     for (int v = S8V_COUNT - 1; v >= 0; v--) if (sc.unit_count[v] > 0) order[used++] = v;     // wide tiles first
     for (int k = 0; k < used; k++) {
       const int v = order[k];

@@ -306,7 +306,13 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
     g = q / bd.n_blk; blk = q - g * bd.n_blk; g0 = g;
   };
   if (w_first < w_last) {
-    while (w_first >= bundles[bslot].item_start + bundles[bslot].n_items) bslot++;
+    // the CU that holds this warp's first item: 32 descriptors per probe instead of a walk of dependent loads
+    for (;; bslot += 32) {
+      const int j = bslot + lane;
+      const bool past = j >= un.job_first + un.job_count || w_first < bundles[j].item_start + bundles[j].n_items;
+      const unsigned m = __ballot_sync(0xffffffffu, past);
+      if (m) { bslot += __ffs(m) - 1; break; }
+    }
     load_bundle();
     locate(w_first);
   }
