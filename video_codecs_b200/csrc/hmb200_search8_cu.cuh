@@ -68,17 +68,41 @@ template <int S, bool FEN> struct CuTraits {
   static constexpr bool ODD_EDGE = PARITY && S == 32;  // odd rows needed in strips 0 and 3 only
 };
 
+// Shared-memory access by 32-bit shared address.  Row addresses are base + row * pitch with the row an immediate: written
+// as mad.lo so that they run on the FMA pipe (IMAD) - the ALU pipe is the one VABSDIFF4 needs, and pointer increments or
+// LEA would sit on it.  The loads are plain ld.shared (no volatile: the tiles are read-only after the staging barrier).
+__device__ __forceinline__ uint32_t cu_row_addr(uint32_t base, int row, uint32_t pitch) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(pitch), "r"(row), "r"(base));
+  return r;
+}
+__device__ __forceinline__ uint4 cu_lds128(uint32_t a) {
+  uint4 v;
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 cu_lds64(uint32_t a) {
+  uint2 v;
+  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t cu_lds32(uint32_t a) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
 // broadcast load of one original row (WW words) from shared memory; the CU is S-byte aligned in the tile
 template <int WW>
-__device__ __forceinline__ void cu_load_org(const uint8_t* p, uint32_t (&o)[WW]) {
+__device__ __forceinline__ void cu_load_org(uint32_t p, uint32_t (&o)[WW]) {
   if constexpr (WW >= 4) {
 #pragma unroll
     for (int i = 0; i < WW / 4; i++) {
-      const uint4 v = reinterpret_cast<const uint4*>(p)[i];
+      const uint4 v = cu_lds128(p + 16 * i);
       o[4 * i] = v.x; o[4 * i + 1] = v.y; o[4 * i + 2] = v.z; o[4 * i + 3] = v.w;
     }
   } else {
-    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const uint2 v = cu_lds64(p);
     o[0] = v.x; o[1] = v.y;
   }
 }
@@ -88,29 +112,24 @@ __device__ __forceinline__ void cu_load_org(const uint8_t* p, uint32_t (&o)[WW])
 // aligned LDS.128 and gets its reference words ready to use: no per-word funnel shift in the inner loop (the ALU pipe
 // that executes VABSDIFF4 also executes SHF, and it was the bound).  WW + 3 words serve the lane's four candidates.
 template <int WW>
-__device__ __forceinline__ void cu_load_ref(const uint8_t* p, uint32_t (&w)[WW + 3]) {
+__device__ __forceinline__ void cu_load_ref(uint32_t p, uint32_t (&w)[WW + 3]) {
   constexpr int NW = WW + 3;
 #pragma unroll
   for (int i = 0; i < NW / 4; i++) {
-    const uint4 v = reinterpret_cast<const uint4*>(p)[i];
+    const uint4 v = cu_lds128(p + 16 * i);
     w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
   }
   if constexpr (NW % 4 == 3) {                           // WW = 4, 8, 16: 7, 11, 19 words -> the last LDS.128 carries one spare word
-    const uint4 v = reinterpret_cast<const uint4*>(p)[NW / 4];
+    const uint4 v = cu_lds128(p + 16 * (NW / 4));
     w[NW - 3] = v.x; w[NW - 2] = v.y; w[NW - 1] = v.z;
   } else if constexpr (NW % 4 == 1) {                    // WW = 2: five words
-    w[NW - 1] = *reinterpret_cast<const uint32_t*>(p + 16 * (NW / 4));
+    w[NW - 1] = cu_lds32(p + 16 * (NW / 4));
   }
-}
-
-// row address: one IMAD on the FMA pipe (a chain of pointer increments would sit on the ALU pipe next to VABSDIFF4)
-__device__ __forceinline__ const uint8_t* cu_row_ptr(const uint8_t* base, int row, int pitch) {
-  return base + __mul24(row, pitch);
 }
 
 // one reference row against one original row: the words of cell column c feed acc[c][k] (k = candidate column)
 template <int WW, int NC>
-__device__ __forceinline__ void cu_row(const uint8_t* rp8, const uint32_t (&o)[WW], uint32_t (&acc)[NC][4]) {
+__device__ __forceinline__ void cu_row(uint32_t rp8, const uint32_t (&o)[WW], uint32_t (&acc)[NC][4]) {
   uint32_t w[WW + 3];
   cu_load_ref<WW>(rp8, w);
 #pragma unroll
@@ -125,7 +144,7 @@ __device__ __forceinline__ void cu_row(const uint8_t* rp8, const uint32_t (&o)[W
 
 // same, every word into one accumulator per candidate column (odd-row strips)
 template <int WW>
-__device__ __forceinline__ void cu_row1(const uint8_t* rp8, const uint32_t (&o)[WW], uint32_t (&acc)[4]) {
+__device__ __forceinline__ void cu_row1(uint32_t rp8, const uint32_t (&o)[WW], uint32_t (&acc)[4]) {
   uint32_t w[WW + 3];
   cu_load_ref<WW>(rp8, w);
 #pragma unroll
@@ -156,36 +175,44 @@ __device__ __forceinline__ void cu_min2(uint32_t& best, uint32_t a, uint32_t b) 
 // only strips 0 and 3 have odd rows that any PU needs, OP[3] = strip 0 + strip 3).  Derives the 13 PU keys of the
 // columns KA and KB (KB < 0: one column) and updates the argmins.  key(x, M) = x * M + base: one IMAD per PU; a PU
 // that is the complement of another inside the CU takes key(total) - x * M (still one IMAD, no sum of its own).
+#ifndef CU_ADD_ON_FMA
+#define CU_ADD_ON_FMA 0
+#endif
 template <int S, bool FEN>
 struct CuKeys {
   uint32_t v[CU_SLOTS];
-  __device__ __forceinline__ CuKeys(const uint32_t (&P)[4][4][4], const uint32_t (&OP)[4][4], int k, uint32_t base) {
+  // a + b as a * one + b with a run-time 1: IMAD on the FMA pipe instead of IADD3 on the ALU pipe
+  static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b, uint32_t one) { return CU_ADD_ON_FMA ? a * one + b : a + b; }
+  static __device__ __forceinline__ uint32_t add4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t one) {
+    return CU_ADD_ON_FMA ? add(add(a, b, one), add(c, d, one), one) : a + b + c + d;
+  }
+  __device__ __forceinline__ CuKeys(const uint32_t (&P)[4][4][4], const uint32_t (&OP)[4][4], int k, uint32_t base, uint32_t one) {
     // a PU with <= 8 rows under FEN visits every row: add the odd rows of its strips; all others shift by iSubShift
     constexpr bool f1 = FEN && cu_slot_h(S, 1) <= 8;      // 2NxN halves (S == 16)
     constexpr bool f5 = FEN && cu_slot_h(S, 5) <= 8;      // AMP quarter strips (S == 16, 32)
     constexpr uint32_t M1 = 1u << CU_LOCAL_BITS;          // key scale of a full-row PU
     constexpr uint32_t MS = M1 << (FEN ? 1 : 0);          // ... of a PU with iSubShift = FEN
-    const uint32_t r0 = P[0][0][k] + P[0][1][k] + P[0][2][k] + P[0][3][k];      // strip 0
-    const uint32_t r2 = P[2][0][k] + P[2][1][k] + P[2][2][k] + P[2][3][k];      // strips 0..2
-    const uint32_t tot = P[3][0][k] + P[3][1][k] + P[3][2][k] + P[3][3][k];
-    const uint32_t c0 = P[3][0][k], c3 = P[3][3][k], left = c0 + P[3][1][k];
+    const uint32_t r0 = add4(P[0][0][k], P[0][1][k], P[0][2][k], P[0][3][k], one);      // strip 0
+    const uint32_t r2 = add4(P[2][0][k], P[2][1][k], P[2][2][k], P[2][3][k], one);      // strips 0..2
+    const uint32_t c0 = P[3][0][k], c3 = P[3][3][k], left = add(c0, P[3][1][k], one);
+    const uint32_t tot = add(left, add(P[3][2][k], c3, one), one);
     const uint32_t k0 = tot * MS + base;
     v[0] = k0;
     if constexpr (f1) {          // S == 16 under FEN: 16x8 halves visit every row
-      const uint32_t a = P[1][0][k] + P[1][1][k] + P[1][2][k] + P[1][3][k] + OP[1][k];
-      const uint32_t kb = (tot + OP[3][k]) * M1 + base;
+      const uint32_t a = add(add4(P[1][0][k], P[1][1][k], P[1][2][k], P[1][3][k], one), OP[1][k], one);
+      const uint32_t kb = OP[3][k] * M1 + (tot * M1 + base);
       v[1] = a * M1 + base;
       v[2] = kb - a * M1;
-      v[5] = (r0 + OP[0][k]) * M1 + base;
-      v[8] = kb - (r2 + OP[2][k]) * M1;
+      v[5] = OP[0][k] * M1 + (r0 * M1 + base);
+      v[8] = (kb - r2 * M1) - OP[2][k] * M1;
     } else {
-      const uint32_t r1 = P[1][0][k] + P[1][1][k] + P[1][2][k] + P[1][3][k];    // strips 0..1
+      const uint32_t r1 = add4(P[1][0][k], P[1][1][k], P[1][2][k], P[1][3][k], one);    // strips 0..1
       v[1] = r1 * MS + base;
       v[2] = k0 - r1 * MS;
       if constexpr (f5) {        // S == 32 under FEN: 32x8 strips visit every row
-        const uint32_t kb = (tot + OP[3][k]) * M1 + base;
-        v[5] = (r0 + OP[0][k]) * M1 + base;
-        v[8] = kb - (r2 + OP[0][k]) * M1;
+        const uint32_t kb = OP[3][k] * M1 + (tot * M1 + base);
+        v[5] = OP[0][k] * M1 + (r0 * M1 + base);
+        v[8] = (kb - r2 * M1) - OP[0][k] * M1;
       } else {
         v[5] = r0 * MS + base;
         v[8] = k0 - r2 * MS;
@@ -264,7 +291,8 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   constexpr int LK = (S == 8) ? 4 : 2;                // bits of the within-tile candidate index
   constexpr int TILE_LIMIT = 1 << (CU_LOCAL_BITS - LK);   // tiles a lane may see between two flushes
   const int quad = lane >> 2, sub = lane & 3;
-  const uint8_t* s_copy = s_ref + sub * un.copy_stride;   // this lane's byte phase
+  const uint32_t s_copy = smem_u32(s_ref) + (uint32_t)(sub * un.copy_stride);   // this lane's byte phase (shared address)
+  const uint32_t one = blockDim.x >> 9;               // 1, but not to the compiler: see CuKeys::add
   uint32_t best[CU_SLOTS];
 #pragma unroll
   for (int s = 0; s < CU_SLOTS; s++) best[s] = 0xffffffffu;
@@ -332,20 +360,28 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
     // two flushes.  S >= 16 (one candidate row per tile): the lane's tiles come in raster order, so the tile number does.
     // S == 8 (four rows per tile): the lane may see two tiles of one row group (8 blocks apart), so the index is
     // (candidate row since g0, rank of the tile inside its row group = blk / 8, column).
-    const uint32_t tile_local = (S == 8) ? ((uint32_t)((g - g0) * 4) << (2 + bd.rank_bits)) | ((uint32_t)(blk >> 3) << 2)
+    const uint32_t rowunit = 1u << (2 + bd.rank_bits);                  // S == 8: index step of one candidate row
+    const uint32_t tile_local = (S == 8) ? (uint32_t)((g - g0) * 4) * rowunit + ((uint32_t)(blk >> 3) << 2)
                                          : (uint32_t)(item - first_item) << LK;
+    const uint32_t c16 = one << 16;                                     // x >> 16 as umulhi(x, 2^16): IMAD.HI, not SHF
     if (g < bd.n_rowgroups) {
     const int cyi0 = g * T::KY;
     const int cx0 = blk * 16 + sub - bd.xal;                            // window column of candidate k = 0 (may be < 0)
-    const uint8_t* refp = s_copy + bd.win_off - bd.xal + cyi0 * un.ref_pitch + blk * 16;     // 16-byte aligned
-    const uint8_t* orgp = s_org + bd.org_off;
-    const int rpitch = un.ref_pitch, opitch = un.org_pitch;
-    uint32_t px[4];
+    const uint32_t rpitch = (uint32_t)un.ref_pitch, opitch = (uint32_t)un.org_pitch;
+    const uint32_t refp = s_copy + (uint32_t)(bd.win_off - bd.xal + cyi0 * un.ref_pitch + blk * 16);     // 16-byte aligned
+    const uint32_t orgp = smem_u32(s_org) + (uint32_t)bd.org_off;
+    // key base of candidate (jy, k) = MV cost * mk[k] + jy * ru[k] + idx0[k]: IMADs on the FMA pipe.  Block columns outside
+    // the window take no part: their mk and ru are 0 and idx0 is KEY_NONE (MASK_BY_KEY), so the base is exactly KEY_NONE.
+    uint32_t px[4], mk[4], idx0[4], ru[4];
     bool valid[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       px[k] = bd.lambda * eg_bits(((bd.lt_x + cx0 + 4 * k) << 2) - bd.pred_x);
-      valid[k] = (unsigned)(cx0 + 4 * k) < (unsigned)bd.nx;             // block columns outside the window take no part
+      valid[k] = (unsigned)(cx0 + 4 * k) < (unsigned)bd.nx;
+      const bool on = valid[k] || !MASK_BY_KEY;
+      mk[k] = on ? (1u << CU_LOCAL_BITS) : 0u;
+      idx0[k] = on ? (tile_local | (uint32_t)k) : KEY_NONE;
+      ru[k] = on ? rowunit : 0u;
     }
 
     if constexpr (S == 8) {
@@ -353,7 +389,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
       // column half c, Q[1][c] = rows 0..7 (the lower half continues the upper half's accumulators)
       uint32_t o[8][2];
 #pragma unroll
-      for (int r = 0; r < 8; r++) cu_load_org<2>(cu_row_ptr(orgp, r, opitch), o[r]);
+      for (int r = 0; r < 8; r++) cu_load_org<2>(cu_row_addr(orgp, r, opitch), o[r]);
       uint32_t Q[T::KY][2][2][4];
 #pragma unroll
       for (int a = 0; a < T::KY; a++)
@@ -364,7 +400,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
 #pragma unroll
       for (int r = 0; r < 8 + T::KY - 1; r++) {
         uint32_t w[5];
-        cu_load_ref<2>(cu_row_ptr(refp, r, rpitch), w);
+        cu_load_ref<2>(cu_row_addr(refp, r, rpitch), w);
 #pragma unroll
         for (int jy = 0; jy < T::KY; jy++) {
           const int orow = r - jy;
@@ -391,10 +427,9 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
           uint32_t key[4][5];
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            uint32_t base = ((((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)k) + ((uint32_t)jy << (2 + bd.rank_bits));
-            base = valid[k] ? base : KEY_NONE;
-            const uint32_t t = Q[jy][0][0][k] + Q[jy][0][1][k], l = Q[jy][1][0][k];
-            const uint32_t k0 = (l + Q[jy][1][1][k]) * M1 + base;
+            const uint32_t base = __umulhi(px[k] + py, c16) * mk[k] + ((uint32_t)jy * ru[k] + idx0[k]);
+            const uint32_t t = Q[jy][0][0][k] * one + Q[jy][0][1][k], l = Q[jy][1][0][k];
+            const uint32_t k0 = Q[jy][1][1][k] * M1 + (l * M1 + base);
             key[k][0] = k0;                       // 8x8  (no PU of an 8x8 CU has more than 8 rows: iSubShift = 0)
             key[k][1] = t * M1 + base;            // 8x4 top
             key[k][2] = k0 - t * M1;              // 8x4 bottom = whole - top
@@ -422,12 +457,12 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
           for (int rr = 0; rr < T::G; rr += 2) {
             const int row = r * T::G + rr;
             uint32_t o[T::WW];
-            cu_load_org<T::WW>(cu_row_ptr(orgp, row, opitch), o);
-            cu_row<T::WW, 4>(cu_row_ptr(refp, row, rpitch), o, P[r]);
+            cu_load_org<T::WW>(cu_row_addr(orgp, row, opitch), o);
+            cu_row<T::WW, 4>(cu_row_addr(refp, row, rpitch), o, P[r]);
             if (odd_here) {
               uint32_t o1[T::WW];
-              cu_load_org<T::WW>(cu_row_ptr(orgp, row + 1, opitch), o1);
-              cu_row1<T::WW>(cu_row_ptr(refp, row + 1, rpitch), o1, OP[r]);
+              cu_load_org<T::WW>(cu_row_addr(orgp, row + 1, opitch), o1);
+              cu_row1<T::WW>(cu_row_addr(refp, row + 1, rpitch), o1, OP[r]);
             }
           }
         } else {
@@ -435,8 +470,8 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
           for (int rr = 0; rr < T::G; rr++) {
             const int row = r * T::G + rr;
             uint32_t o[T::WW];
-            cu_load_org<T::WW>(cu_row_ptr(orgp, row, opitch), o);
-            cu_row<T::WW, 4>(cu_row_ptr(refp, row, rpitch), o, P[r]);
+            cu_load_org<T::WW>(cu_row_addr(orgp, row, opitch), o);
+            cu_row<T::WW, 4>(cu_row_addr(refp, row, rpitch), o, P[r]);
           }
         }
       }
@@ -444,11 +479,11 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
         const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + bd.cy_first + cyi0) << 2) - bd.pred_y);
         uint32_t base[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) base[k] = (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)k;
+        for (int k = 0; k < 4; k++) base[k] = __umulhi(px[k] + py, c16) * mk[k] + idx0[k];
         if constexpr (MASK_BY_KEY) {
 #pragma unroll
           for (int kk = 0; kk < 4; kk += 2) {
-            const CuKeys<S, FEN> a(P, OP, kk, valid[kk] ? base[kk] : KEY_NONE), b(P, OP, kk + 1, valid[kk + 1] ? base[kk + 1] : KEY_NONE);
+            const CuKeys<S, FEN> a(P, OP, kk, base[kk], one), b(P, OP, kk + 1, base[kk + 1], one);
 #pragma unroll
             for (int s = 0; s < CU_SLOTS; s++) cu_min2(best[s], a.v[s], b.v[s]);
           }
@@ -456,7 +491,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
 #pragma unroll
           for (int k = 0; k < 4; k++)
             if (valid[k]) {
-              const CuKeys<S, FEN> a(P, OP, k, base[k]);
+              const CuKeys<S, FEN> a(P, OP, k, base[k], one);
 #pragma unroll
               for (int s = 0; s < CU_SLOTS; s++) best[s] = min(best[s], a.v[s]);
             }
