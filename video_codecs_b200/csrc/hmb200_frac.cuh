@@ -235,6 +235,148 @@ k_frac_tiles(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_re
   atomicAdd(&dist[(size_t)pu * 9 + ci], s);
 }
 
+// ---- 8-bit planes, stages 0 / 1: reference patches staged in shared memory ------------------------------------------
+// All candidates of a stage read the same 16 x 16 (8x8 tiles) or 12 x 16 (4x4 tiles) block of integer samples around
+// the tile at the integer MV: columns -4..11, rows -4..N+3 (the candidates' integer parts are -1 or 0, the filter
+// reaches 3 samples left / up and 4 right / down).  k_frac_tiles fetched those rows per (candidate, strip) with four
+// unaligned global loads each and was bound by their latency (ncu: long_scoreboard the top stall, issue 0.55).  Here a
+// CTA stages the patches of its 14 (half stage, 9 candidates) or 16 (quarter stage, 8 candidates) tiles once - one
+// 16-byte row per thread and step, written with the patch's own alignment - and every (tile, candidate) thread reads
+// whole rows with one LDS.128.  Arithmetic is frac_tile_diff_u8's, bit for bit.
+__device__ __forceinline__ uint32_t frac_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 frac_lds128(uint32_t a) {
+  uint4 v;
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t frac_lds32(uint32_t a) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
+// prow: shared address of the patch row that holds reference row (-3 + dy) of the tile (dy = integer part of the
+// candidate's y offset); sh: 8 * (1 + dx), the byte phase of column (-3 + dx) inside the patch row; orgp: the tile's
+// original samples, N bytes per row.
+template <int N>
+__device__ __forceinline__ void frac_tile_diff_patch(uint32_t prow, uint32_t sh, uint32_t orgp, int fx, int fy, int (&d)[N * N]) {
+  constexpr int vshift = 12;                                             // bit depth 8: headroom 14 - 8
+  constexpr int voff = (1 << (vshift - 1)) + (8192 << 6);
+  int t0, t1, tv[8];
+  frac_packed_taps(fx, t0, t1);
+  frac_load_taps(fy, tv);
+  int dA[N][4], dB[N][4];
+#pragma unroll 1
+  for (int cs = 0; cs < N; cs += 4) {
+    int hh[N + 7][4];
+#pragma unroll
+    for (int r = 0; r < N + 7; r++) {
+      const uint4 v = frac_lds128(prow + 16 * r);                        // patch columns 0..15 = tile columns -4..11
+      const uint32_t a0 = cs ? v.y : v.x, a1 = cs ? v.z : v.y, a2 = cs ? v.w : v.z, a3 = 0u;   // the 11th sample ends in a2
+      const uint32_t s0 = __funnelshift_r(a0, a1, sh), s1 = __funnelshift_r(a1, a2, sh), s2 = __funnelshift_r(a2, a3, sh);
+      const uint32_t W0 = s0, W1 = __funnelshift_r(s0, s1, 8), W2 = __funnelshift_r(s0, s1, 16), W3 = __funnelshift_r(s0, s1, 24);
+      const uint32_t W4 = s1, W5 = __funnelshift_r(s1, s2, 8), W6 = __funnelshift_r(s1, s2, 16), W7 = __funnelshift_r(s1, s2, 24);
+      hh[r][0] = dp4a_us(W4, t1, dp4a_us(W0, t0, -8192));                  // filter<> isFirst at bit depth 8: shift 0, offset -8192
+      hh[r][1] = dp4a_us(W5, t1, dp4a_us(W1, t0, -8192));
+      hh[r][2] = dp4a_us(W6, t1, dp4a_us(W2, t0, -8192));
+      hh[r][3] = dp4a_us(W7, t1, dp4a_us(W3, t0, -8192));
+      if (r >= 7) {
+        const int y = r - 7;
+        const uint32_t ow = frac_lds32(orgp + y * N + cs);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          int sum = voff;
+#pragma unroll
+          for (int t = 0; t < 8; t++) sum += hh[y + t][c] * tv[t];
+          const int val = min(max(sum >> vshift, 0), 255);               // filter<> isLast + clip
+          const int dv = (int)((ow >> (8 * c)) & 0xffu) - val;
+          if (cs == 0) dA[y][c] = dv; else dB[y][c] = dv;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int y = 0; y < N; y++)
+#pragma unroll
+    for (int c = 0; c < N; c++) d[y * N + c] = (c < 4) ? dA[y][c] : dB[y][c & 3];
+}
+
+template <int N> struct FracPatch {
+  static constexpr int ROWS = N + 8;                                     // reference rows -4 .. N+3
+  static constexpr int STRIDE = ROWS * 16 + 16;                          // 272 / 208 bytes: tiles of one warp fall on disjoint banks
+  static constexpr int ORG = N * N;
+  static constexpr int MAX_TILES = 16;
+};
+
+template <int N, bool HAD>
+__global__ void __launch_bounds__(FRAC_TILE_THREADS, N == 8 ? 4 : 8)
+k_frac_patch(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_result* __restrict__ results,
+             const uint32_t* __restrict__ tiles, int n_tiles, uint32_t* __restrict__ dist, DevPlane cur_plane, DevPlane ref_plane) {
+  typedef FracPatch<N> P;
+  __shared__ __align__(16) uint8_t s_patch[P::MAX_TILES * P::STRIDE];
+  __shared__ __align__(16) uint8_t s_org[P::MAX_TILES * P::ORG];
+  __shared__ int s_pu[P::MAX_TILES], s_rx[P::MAX_TILES], s_ry[P::MAX_TILES], s_ox[P::MAX_TILES], s_oy[P::MAX_TILES];
+  __shared__ int s_hx[P::MAX_TILES], s_hy[P::MAX_TILES];
+  const int nc = stage == 0 ? 9 : 8;
+  const int tpc = FRAC_TILE_THREADS / nc;                                // tiles per CTA: 14 / 16
+  const int slot0 = blockIdx.x * tpc;
+  const int nt = min(tpc, n_tiles - slot0);
+  if ((int)threadIdx.x < nt) {
+    const uint32_t tile = tiles[slot0 + threadIdx.x];
+    const int pu = (int)(tile & 0xffffffu), tx = (tile >> 24) & 15, ty = tile >> 28;
+    const SearchTask tk = tasks[pu];
+    const hmb200_pu_result rs = results[pu];
+    s_pu[threadIdx.x] = pu;
+    s_rx[threadIdx.x] = tk.ref_x + rs.mv_x + tx * N - 4; s_ry[threadIdx.x] = tk.ref_y + rs.mv_y + ty * N - 4;
+    s_ox[threadIdx.x] = tk.org_x + tx * N;               s_oy[threadIdx.x] = tk.org_y + ty * N;
+    s_hx[threadIdx.x] = rs.half_x;                       s_hy[threadIdx.x] = rs.half_y;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nt * P::ROWS; i += FRAC_TILE_THREADS) {   // one 16-byte patch row per step
+    const int tl = i / P::ROWS, row = i - tl * P::ROWS;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(plane_at<uint8_t>(ref_plane, s_rx[tl], s_ry[tl] + row));
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8u;
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
+    uint4 o;
+    o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh); o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+    *reinterpret_cast<uint4*>(s_patch + tl * P::STRIDE + row * 16) = o;
+  }
+  for (int i = threadIdx.x; i < nt * N; i += FRAC_TILE_THREADS) {          // original rows
+    const int tl = i / N, row = i - tl * N;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(plane_at<uint8_t>(cur_plane, s_ox[tl], s_oy[tl] + row));   // any alignment
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8u;
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+    if constexpr (N == 8) {
+      const uint32_t w2 = __ldg(w + 2);
+      *reinterpret_cast<uint2*>(s_org + tl * P::ORG + row * 8) = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+    } else {
+      *reinterpret_cast<uint32_t*>(s_org + tl * P::ORG + row * 4) = __funnelshift_r(w0, w1, sh);
+    }
+  }
+  __syncthreads();
+  const int tl = threadIdx.x / nc, cand = threadIdx.x - tl * nc;
+  if (tl >= nt) return;
+  int ci, qx, qy;
+  if (stage == 0) { ci = cand; qx = 2 * k_refine_h[ci][0]; qy = 2 * k_refine_h[ci][1]; }
+  else            { ci = cand + 1; qx = 2 * s_hx[tl] + k_refine_q[ci][0]; qy = 2 * s_hy[tl] + k_refine_q[ci][1]; }
+  const int dx = qx >> 2, dy = qy >> 2;                                  // -1 or 0
+  const uint32_t prow = frac_smem_addr(s_patch) + (uint32_t)(tl * P::STRIDE + (1 + dy) * 16);
+  int d[N * N];
+  frac_tile_diff_patch<N>(prow, (uint32_t)(1 + dx) * 8u, frac_smem_addr(s_org) + (uint32_t)(tl * P::ORG), qx & 3, qy & 3, d);
+  uint32_t sv;
+  if (HAD) {
+    if constexpr (N == 8) sv = (had8x8_abs(d) + 2) >> 2;                 // TComRdCost.cpp:1520
+    else                  sv = (had4x4_abs(d) + 1) >> 1;                 // TComRdCost.cpp:1423
+  } else {
+    sv = 0;
+#pragma unroll
+    for (int i = 0; i < N * N; i++) sv += (uint32_t)abs(d[i]);
+  }
+  atomicAdd(&dist[(size_t)s_pu[tl] * 9 + ci], sv);
+}
+
 // xPatternRefinement's argmin (TEncSearch.cpp:808-861).  STAGE 0 writes rcMvHalf and seeds the quarter stage's
 // centre distortion; STAGE 1 writes rcMvQter and ruiCost.
 template <int STAGE>
@@ -328,14 +470,26 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
     uint32_t* dist = stage == 0 ? dist0 : dist1;
     const int nc = stage == 0 ? 9 : 8;
     auto blocks = [&](int n_tiles) { return (int)((((long long)(n_tiles + 31) / 32) * 32 * nc + FRAC_TILE_THREADS - 1) / FRAC_TILE_THREADS); };
+    constexpr bool PATCH = sizeof(RefT) == 1 && sizeof(OrgT) == 1;        // 8-bit planes: shared-memory patches (k_frac_patch)
+    const int tpc = FRAC_TILE_THREADS / nc;
     if (fs.n_tiles8 > 0) {
-      if (use_had) k_frac_tiles<RefT, OrgT, 8, true><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
-      else         k_frac_tiles<RefT, OrgT, 8, false><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
+      if constexpr (PATCH) {
+        if (use_had) k_frac_patch<8, true><<<(fs.n_tiles8 + tpc - 1) / tpc, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
+        else         k_frac_patch<8, false><<<(fs.n_tiles8 + tpc - 1) / tpc, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
+      } else {
+        if (use_had) k_frac_tiles<RefT, OrgT, 8, true><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
+        else         k_frac_tiles<RefT, OrgT, 8, false><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
+      }
       launches++;
     }
     if (fs.n_tiles4 > 0) {
-      if (use_had) k_frac_tiles<RefT, OrgT, 4, true><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
-      else         k_frac_tiles<RefT, OrgT, 4, false><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
+      if constexpr (PATCH) {
+        if (use_had) k_frac_patch<4, true><<<(fs.n_tiles4 + tpc - 1) / tpc, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
+        else         k_frac_patch<4, false><<<(fs.n_tiles4 + tpc - 1) / tpc, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
+      } else {
+        if (use_had) k_frac_tiles<RefT, OrgT, 4, true><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
+        else         k_frac_tiles<RefT, OrgT, 4, false><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
+      }
       launches++;
     }
     const int nb = (fs.n_pu + 255) / 256;
