@@ -391,7 +391,7 @@ def run_ours(args):
             "cand_sad_per_s": world * work["cand_sads"] / (ms_per_step / 1e3),
             "sharding": "tile columns of one picture" if tiles else "independent frame pairs",
             "search_ms": srch / K, "frac_ms": frac / K, "wall_ms_per_step_incl_flush": wall_ms / K,
-            "roofline": {"bound": "int_alu", "kernel": "k_search8<*> (VABSDIFF4.U8.ACC)", "achieved": achieved / 1e12,
+            "roofline": {"bound": "int_alu", "kernel": ("k_search8_cu<S,FEN> (VABSDIFF4.U8.ACC)" if BIT_DEPTH == 8 else "k_search16_cu<S,FEN> (VIADD.16x2 / VIADDMNMX.S16x2 / IDP.2A)"), "achieved": achieved / 1e12,
                          "peak": peak_abs / 1e12, "unit": "Tabsdiff/s", "frac": achieved / peak_abs, "traffic": traffic,
                          "traffic_kernel": traffic_kernel,
                          "peak_source": peak_src,
@@ -402,7 +402,7 @@ def run_ours(args):
                                  "H>8) per second; executed = abs-diffs the kernels really issue (CU-fused kernels compute each "
                                  "CU sample once for all 13 partitions, so achieved/peak may exceed 1; executed_frac is the pipe "
                                  "utilisation); per-rank search time incl. key memset + finalize"},
-            "roofline_refine": {"bound": "int_alu", "kernel": "k_frac_tiles<u8,u8,8|4,HAD>", "achieved": frac_ops / (frac / K / 1e3) / 1e12,
+            "roofline_refine": {"bound": "int_alu", "kernel": ("k_frac_patch<8|4,HAD>" if BIT_DEPTH == 8 else "k_frac_tiles<i16,i16,8|4,HAD>"), "achieved": frac_ops / (frac / K / 1e3) / 1e12,
                                 "peak": imad_peak / 1e12, "unit": "Tintop/s", "frac": frac_ops / (frac / K / 1e3) / imad_peak,
                                 "traffic": None, "peak_source": "measured IMAD issue rate, profiles/r01_microbench_int.json",
                                 "note": "400 integer ops per PU pixel (model, DESIGN.md 3.2)"},

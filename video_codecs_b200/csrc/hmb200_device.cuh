@@ -32,9 +32,7 @@ __device__ __forceinline__ const T* plane_at(const DevPlane& p, int x, int y) {
 // 1 + 2*floor(log2(v <= 0 ? -2v+1 : 2v))
 __device__ __forceinline__ uint32_t eg_bits(int v) {
   uint32_t t = (v <= 0) ? (((uint32_t)(-v)) << 1) + 1u : ((uint32_t)v << 1);
-  uint32_t msb;                                      // t >= 1: position of its most significant bit (FLO), no clz round trip
-  asm("bfind.u32 %0, %1;" : "=r"(msb) : "r"(t));
-  return 2u * msb + 1u;
+  return 2u * (31u - (uint32_t)__clz(t)) + 1u;
 }
 __device__ __forceinline__ uint32_t mv_bits(int x, int y, int pred_x, int pred_y, int scale) {
   return eg_bits(x * (1 << scale) - pred_x) + eg_bits(y * (1 << scale) - pred_y);

@@ -377,6 +377,185 @@ k_frac_patch(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_re
   atomicAdd(&dist[(size_t)s_pu[tl] * 9 + ci], sv);
 }
 
+// ---- 8-bit planes, stages 0 / 1: horizontal pass shared by the candidates, vertical pass as 16-bit dot products ------
+// The nine (eight) candidates of a stage use only three horizontal positions (stage 0: -1/2, 0, +1/2 around the integer
+// MV; stage 1: -1/4, 0, +1/4 around the best half-pel), so the first filter pass (TComInterpolationFilter.cpp:172-257,
+// isFirst) is computed once per (tile, horizontal position) for the rows -4..N+3 that the two integer row offsets need,
+// by the whole CTA, from the staged patches (k_frac_patch's layout).  The 14-bit intermediates are stored as PAIRS of
+// vertically adjacent rows in one 32-bit word - pairs (0,1),(2,3).. and pairs (1,2),(3,4).. - which is the operand
+// layout of IDP.2A.S16.S8: the second pass (isLast) of an output is four dot products of two rows x two taps instead of
+// eight IMADs.  Same integers as k_frac_tiles: the products and the 32-bit sum are exact either way.
+template <int N> struct FracHV {
+  typedef FracPatch<N> P;
+  static constexpr int NPE = P::ROWS / 2;                 // pair rows (2i, 2i+1): 8 / 6
+  static constexpr int NPO = P::ROWS / 2 - 1;             // pair rows (2i+1, 2i+2): 7 / 5
+  static constexpr int PRB = N * 4;                       // bytes of one pair row (N columns)
+  static constexpr int OOFF = NPE * PRB + 48;             // odd pairs behind the even ones, shifted by 12 banks
+  static constexpr int VSTR = OOFF + NPO * PRB;           // one horizontal position: 528 / 224 bytes
+  static constexpr int TSTR = 3 * VSTR + 64;              // one tile
+};
+
+__device__ __forceinline__ int dp2a_lo_ss(uint32_t a, int b, int c) {
+  int d;
+  asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_hi_ss(uint32_t a, int b, int c) {
+  int d;
+  asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// first-pass intermediates of patch row `prow` (shared address) for N columns at horizontal position (dx, fx)
+template <int N>
+__device__ __forceinline__ void frac_hrow(uint32_t prow, uint32_t sh, int t0, int t1, int (&h)[N]) {
+  const uint4 v = frac_lds128(prow);
+#pragma unroll
+  for (int cs = 0; cs < N; cs += 4) {
+    const uint32_t a0 = cs ? v.y : v.x, a1 = cs ? v.z : v.y, a2 = cs ? v.w : v.z;
+    const uint32_t s0 = __funnelshift_r(a0, a1, sh), s1 = __funnelshift_r(a1, a2, sh), s2 = __funnelshift_r(a2, 0u, sh);
+    const uint32_t W1 = __funnelshift_r(s0, s1, 8), W2 = __funnelshift_r(s0, s1, 16), W3 = __funnelshift_r(s0, s1, 24);
+    const uint32_t W5 = __funnelshift_r(s1, s2, 8), W6 = __funnelshift_r(s1, s2, 16), W7 = __funnelshift_r(s1, s2, 24);
+    h[cs + 0] = dp4a_us(s1, t1, dp4a_us(s0, t0, -8192));                 // filter<> isFirst at bit depth 8: shift 0, offset -8192
+    h[cs + 1] = dp4a_us(W5, t1, dp4a_us(W1, t0, -8192));
+    h[cs + 2] = dp4a_us(W6, t1, dp4a_us(W2, t0, -8192));
+    h[cs + 3] = dp4a_us(W7, t1, dp4a_us(W3, t0, -8192));
+  }
+}
+
+template <int N, bool HAD>
+__global__ void __launch_bounds__(FRAC_TILE_THREADS, N == 8 ? 4 : 8)
+k_frac_hv(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_result* __restrict__ results,
+          const uint32_t* __restrict__ tiles, int n_tiles, uint32_t* __restrict__ dist, DevPlane cur_plane, DevPlane ref_plane) {
+  typedef FracPatch<N> P;
+  typedef FracHV<N> H;
+  __shared__ __align__(16) uint8_t s_patch[P::MAX_TILES * P::STRIDE];
+  __shared__ __align__(16) uint8_t s_org[P::MAX_TILES * P::ORG];
+  __shared__ __align__(16) uint8_t s_h[P::MAX_TILES * H::TSTR];
+  __shared__ int s_pu[P::MAX_TILES], s_rx[P::MAX_TILES], s_ry[P::MAX_TILES], s_ox[P::MAX_TILES], s_oy[P::MAX_TILES];
+  __shared__ int s_hx[P::MAX_TILES], s_hy[P::MAX_TILES];
+  const int nc = stage == 0 ? 9 : 8;
+  const int tpc = FRAC_TILE_THREADS / nc;                                // tiles per CTA: 14 / 16
+  const int slot0 = blockIdx.x * tpc;
+  const int nt = min(tpc, n_tiles - slot0);
+  if ((int)threadIdx.x < nt) {
+    const uint32_t tile = tiles[slot0 + threadIdx.x];
+    const int pu = (int)(tile & 0xffffffu), tx = (tile >> 24) & 15, ty = tile >> 28;
+    const SearchTask tk = tasks[pu];
+    const hmb200_pu_result rs = results[pu];
+    s_pu[threadIdx.x] = pu;
+    s_rx[threadIdx.x] = tk.ref_x + rs.mv_x + tx * N - 4; s_ry[threadIdx.x] = tk.ref_y + rs.mv_y + ty * N - 4;
+    s_ox[threadIdx.x] = tk.org_x + tx * N;               s_oy[threadIdx.x] = tk.org_y + ty * N;
+    s_hx[threadIdx.x] = rs.half_x;                       s_hy[threadIdx.x] = rs.half_y;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nt * P::ROWS; i += FRAC_TILE_THREADS) {   // one 16-byte patch row per step
+    const int tl = i / P::ROWS, row = i - tl * P::ROWS;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(plane_at<uint8_t>(ref_plane, s_rx[tl], s_ry[tl] + row));
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8u;
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
+    uint4 o;
+    o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh); o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+    *reinterpret_cast<uint4*>(s_patch + tl * P::STRIDE + row * 16) = o;
+  }
+  for (int i = threadIdx.x; i < nt * N; i += FRAC_TILE_THREADS) {          // original rows
+    const int tl = i / N, row = i - tl * N;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(plane_at<uint8_t>(cur_plane, s_ox[tl], s_oy[tl] + row));   // any alignment
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8u;
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+    if constexpr (N == 8) {
+      const uint32_t w2 = __ldg(w + 2);
+      *reinterpret_cast<uint2*>(s_org + tl * P::ORG + row * 8) = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+    } else {
+      *reinterpret_cast<uint32_t*>(s_org + tl * P::ORG + row * 4) = __funnelshift_r(w0, w1, sh);
+    }
+  }
+  __syncthreads();
+  // first pass: unit = (tile, horizontal position j, pair index m) -> rows 2m, 2m+1, 2m+2 -> pair rows E[m], O[m]
+  for (int u = threadIdx.x; u < nt * 3 * H::NPE; u += FRAC_TILE_THREADS) {
+    const int tl = u / (3 * H::NPE), rem = u - tl * (3 * H::NPE), j = rem / H::NPE, m = rem - j * H::NPE;
+    const int qx = stage == 0 ? 2 * (j - 1) : 2 * s_hx[tl] + (j - 1);
+    int t0, t1;
+    frac_packed_taps(qx & 3, t0, t1);
+    const uint32_t sh = (uint32_t)(1 + (qx >> 2)) * 8u;
+    const uint32_t prow = frac_smem_addr(s_patch) + (uint32_t)(tl * P::STRIDE + 2 * m * 16);
+    int h0[N], h1[N], h2[N];
+    frac_hrow<N>(prow, sh, t0, t1, h0);
+    frac_hrow<N>(prow + 16, sh, t0, t1, h1);
+    uint8_t* dst = s_h + tl * H::TSTR + j * H::VSTR + m * H::PRB;
+    uint32_t e[N], o[N];
+#pragma unroll
+    for (int c = 0; c < N; c++) e[c] = __byte_perm((uint32_t)h0[c], (uint32_t)h1[c], 0x5410);
+#pragma unroll
+    for (int c = 0; c < N; c += 4) *reinterpret_cast<uint4*>(dst + 4 * c) = make_uint4(e[c], e[c + 1], e[c + 2], e[c + 3]);
+    if (m < H::NPO) {
+      frac_hrow<N>(prow + 32, sh, t0, t1, h2);
+#pragma unroll
+      for (int c = 0; c < N; c++) o[c] = __byte_perm((uint32_t)h1[c], (uint32_t)h2[c], 0x5410);
+#pragma unroll
+      for (int c = 0; c < N; c += 4) *reinterpret_cast<uint4*>(dst + H::OOFF + 4 * c) = make_uint4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+    }
+  }
+  __syncthreads();
+  const int tl = threadIdx.x / nc, cand = threadIdx.x - tl * nc;
+  if (tl >= nt) return;
+  int ci, j, qy;
+  if (stage == 0) { ci = cand; j = k_refine_h[ci][0] + 1; qy = 2 * k_refine_h[ci][1]; }
+  else            { ci = cand + 1; j = k_refine_q[ci][0] + 1; qy = 2 * s_hy[tl] + k_refine_q[ci][1]; }
+  const int dy = qy >> 2;                                                // -1 or 0
+  int tl4, th4;
+  frac_packed_taps(qy & 3, tl4, th4);
+  // output row y needs intermediate rows y+dy+1 .. y+dy+8 (patch row numbering): even y -> E (dy = -1) or O (dy = 0)
+  // from pair y/2; odd y -> O from pair (y-1)/2 (dy = -1) or E from pair (y+1)/2 (dy = 0)
+  const uint32_t hb = frac_smem_addr(s_h) + (uint32_t)(tl * H::TSTR + j * H::VSTR);
+  const uint32_t pe = hb + (dy ? 0u : (uint32_t)H::OOFF), po = hb + (dy ? (uint32_t)H::OOFF : (uint32_t)H::PRB);
+  const uint32_t orgp = frac_smem_addr(s_org) + (uint32_t)(tl * P::ORG);
+  constexpr int vshift = 12, voff = (1 << (vshift - 1)) + (8192 << 6);   // bit depth 8: headroom 14 - 8
+  constexpr int NPR = N / 2 + 3;                                         // pair rows per parity that a tile touches
+  int dA[N][4], dB[N][4];
+#pragma unroll 1
+  for (int cs = 0; cs < N; cs += 4) {
+    uint4 PE[NPR], PO[NPR];
+#pragma unroll
+    for (int i = 0; i < NPR; i++) { PE[i] = frac_lds128(pe + i * H::PRB + cs * 4); PO[i] = frac_lds128(po + i * H::PRB + cs * 4); }
+#pragma unroll
+    for (int y = 0; y < N; y++) {
+      const uint32_t ow = frac_lds32(orgp + y * N + cs);
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        int sum = voff;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const uint4 q = (y & 1) ? PO[(y >> 1) + t] : PE[(y >> 1) + t];
+          const uint32_t w = c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w;
+          const int taps = t < 2 ? tl4 : th4;
+          sum = (t & 1) ? dp2a_hi_ss(w, taps, sum) : dp2a_lo_ss(w, taps, sum);
+        }
+        const int val = min(max(sum >> vshift, 0), 255);                 // filter<> isLast + clip
+        const int dv = (int)((ow >> (8 * c)) & 0xffu) - val;
+        if (cs == 0) dA[y][c] = dv; else dB[y][c] = dv;
+      }
+    }
+  }
+  int d[N * N];
+#pragma unroll
+  for (int y = 0; y < N; y++)
+#pragma unroll
+    for (int c = 0; c < N; c++) d[y * N + c] = (c < 4) ? dA[y][c] : dB[y][c & 3];
+  uint32_t sv;
+  if (HAD) {
+    if constexpr (N == 8) sv = (had8x8_abs(d) + 2) >> 2;                 // TComRdCost.cpp:1520
+    else                  sv = (had4x4_abs(d) + 1) >> 1;                 // TComRdCost.cpp:1423
+  } else {
+    sv = 0;
+#pragma unroll
+    for (int i = 0; i < N * N; i++) sv += (uint32_t)abs(d[i]);
+  }
+  atomicAdd(&dist[(size_t)s_pu[tl] * 9 + ci], sv);
+}
+
 // xPatternRefinement's argmin (TEncSearch.cpp:808-861).  STAGE 0 writes rcMvHalf and seeds the quarter stage's
 // centre distortion; STAGE 1 writes rcMvQter and ruiCost.
 template <int STAGE>
@@ -470,12 +649,15 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
     uint32_t* dist = stage == 0 ? dist0 : dist1;
     const int nc = stage == 0 ? 9 : 8;
     auto blocks = [&](int n_tiles) { return (int)((((long long)(n_tiles + 31) / 32) * 32 * nc + FRAC_TILE_THREADS - 1) / FRAC_TILE_THREADS); };
-    constexpr bool PATCH = sizeof(RefT) == 1 && sizeof(OrgT) == 1;        // 8-bit planes: shared-memory patches (k_frac_patch)
+    constexpr bool PATCH = sizeof(RefT) == 1 && sizeof(OrgT) == 1;        // 8-bit planes: shared-memory patches (k_frac_hv / k_frac_patch)
+    static const bool old_path = getenv("HMB200_FRAC_PATCH") != nullptr;  // A/B knob: per-candidate first pass
     const int tpc = FRAC_TILE_THREADS / nc;
     if (fs.n_tiles8 > 0) {
       if constexpr (PATCH) {
-        if (use_had) k_frac_patch<8, true><<<(fs.n_tiles8 + tpc - 1) / tpc, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
-        else         k_frac_patch<8, false><<<(fs.n_tiles8 + tpc - 1) / tpc, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
+        const int nb8 = (fs.n_tiles8 + tpc - 1) / tpc;
+        if (!use_had)      k_frac_patch<8, false><<<nb8, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
+        else if (old_path) k_frac_patch<8, true><<<nb8, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
+        else               k_frac_hv<8, true><<<nb8, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
       } else {
         if (use_had) k_frac_tiles<RefT, OrgT, 8, true><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
         else         k_frac_tiles<RefT, OrgT, 8, false><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
@@ -484,8 +666,10 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
     }
     if (fs.n_tiles4 > 0) {
       if constexpr (PATCH) {
-        if (use_had) k_frac_patch<4, true><<<(fs.n_tiles4 + tpc - 1) / tpc, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
-        else         k_frac_patch<4, false><<<(fs.n_tiles4 + tpc - 1) / tpc, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
+        const int nb4 = (fs.n_tiles4 + tpc - 1) / tpc;
+        if (!use_had)      k_frac_patch<4, false><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
+        else if (old_path) k_frac_patch<4, true><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
+        else               k_frac_hv<4, true><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
       } else {
         if (use_had) k_frac_tiles<RefT, OrgT, 4, true><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
         else         k_frac_tiles<RefT, OrgT, 4, false><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
