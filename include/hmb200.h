@@ -190,6 +190,29 @@ typedef struct { int32_t pu_x, pu_y, w, h, mv_x, mv_y; } hmb200_mc_desc;
  * the MV-index bit cost and calcRdCost stay on the host. */
 int  hmb200_mc_dist_batch(int cur_plane, int ref_plane, int func, int n, const hmb200_mc_desc* descs, uint32_t* out);
 
+/* ------------------------------------------------------------------ intra first pass -------------------------- */
+
+/* One block of the intra mode pre-selection.  (x, y): position in the registered ORIGINAL plane; n = 4, 8, 16, 32 or 64;
+ * ref_off: index (in samples) of the block's reference lines in `refs`: top_unf[2n+1], left_unf[2n+1], top_flt[2n+1],
+ * left_flt[2n+1], each with the corner sample at index 0 - row 0 and column 0 of the reference's unfiltered / smoothed
+ * (2n+1)-strided buffers (m_piYuvExt[COMPONENT_Y][PRED_BUF_UNFILTERED / _FILTERED] after
+ * TComPrediction::initIntraPatternChType, TLibCommon/TComPattern.cpp:115-320, which stays on the host: availability and
+ * reconstruction state are the encoder's).  flags: bit 0 bAbove, bit 1 bLeft as passed to predIntraAng (both set by
+ * initIntraPatternChType, :155-156).  24 bytes. */
+typedef struct { int32_t x, y, n, ref_off, flags, reserved; } hmb200_intra_block;
+#define HMB200_INTRA_MODES 35
+/* The mode loop of TEncSearch::estIntraPredQT (TLibEncoder/TEncSearch.cpp:2270-2296) for nblocks blocks in one launch
+ * set: for every mode 0..34 filteringIntraReferenceSamples (TComPattern.cpp:544-568) + predIntraAng (TComPrediction.cpp:
+ * 412-494: planar :756-816, DC :183-222 + :819-848, angular :250-410 with the edge filters) + distParam.DistFunc =
+ * xGetHADs (TComRdCost.cpp:380-392, 1526-1593).  out[i * 35 + mode] = uiSad of block i; the mode bits
+ * (xModeBitsIntra), the cost and the candidate list (:2282-2294) stay on the host. */
+int  hmb200_intra_modes_had_batch(int org_plane, int nblocks, const hmb200_intra_block* blocks, const int16_t* refs,
+                                  int n_ref_samples, uint32_t* out);
+/* 1:1 form with the reference's own buffers: org = piOrg (stride org_stride), ref_unf / ref_flt = the two (2n+1)-strided
+ * predictor buffers (getPredictorPtr(COMPONENT_Y, false / true), TComPrediction.h:121), above / left = bAbove / bLeft. */
+int  hmb200_intra_modes_had(const int16_t* org, int org_stride, const int16_t* ref_unf, const int16_t* ref_flt, int n,
+                            int bit_depth, int above, int left, uint32_t out[HMB200_INTRA_MODES]);
+
 /* ------------------------------------------------------------------ searches, 1:1 ----------------------------- */
 
 /* TEncSearch::xPatternSearch(TComPattern*, Pel* piRefY, Int iRefStride, TComMv* LT, TComMv* RB, TComMv& rcMv,

@@ -559,3 +559,105 @@ double hmo_run_jobs(const int16_t* cur0, int cur_stride, const int16_t* ref0, in
   }
   return (double)(clock() - t0) / CLOCKS_PER_SEC;
 }
+
+/* ---------------------------------------------------------------- intra first pass ----------------------------- */
+/* The 35 luma intra predictions of one block and their Hadamard distortions: the loop of TEncSearch::estIntraPredQT
+ * (TLibEncoder/TEncSearch.cpp:2270-2296: predIntraAng + distParam.DistFunc per mode).  Reference samples arrive the way
+ * the encoder has them after initIntraPatternChType: two (2N+1) x (2N+1)-strided buffers (unfiltered / smoothed), of
+ * which only row 0 (corner, above, above-right) and column 0 (left, below-left) are defined
+ * (TLibCommon/TComPattern.cpp:115-175; TComPrediction.cpp:412-494 reads them at ptrSrc + sw + 1).  Here they are two
+ * lines instead: top[0..2N] = corner, above, above-right and left[0..2N] = corner, left, below-left. */
+
+static int clip_pel(int v, int bit_depth) { int m = (1 << bit_depth) - 1; return v < 0 ? 0 : (v > m ? m : v); }
+static int log2i(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
+
+/* TLibCommon/TComPattern.cpp:544-568 filteringIntraReferenceSamples (luma; thresholds TComPrediction.cpp:50-57) */
+int hmo_intra_use_filtered(int mode, int n)
+{
+  static const int thr[5] = {10, 7, 1, 0, 10};               /* 4, 8, 16, 32, 64 */
+  if (mode == 1) return 0;                                    /* DC: never */
+  int d1 = abs(mode - 10), d2 = abs(mode - 26);               /* HOR_IDX, VER_IDX; planar (0): min(10, 26) = 10 */
+  return (d1 < d2 ? d1 : d2) > thr[log2i(n) - 2];
+}
+
+/* one prediction: TComPrediction.cpp:412-494 (predIntraAng, luma, no lossless DPCM), :756-816 (planar), :183-222 + :819-848
+ * (DC and its edge filter), :250-410 (angular, edge filter of the pure vertical / horizontal modes).
+ * above_ok / left_ok: bAbove / bLeft of predIntraAng (always true after initIntraPatternChType, :155-156). */
+void hmo_intra_predict(int mode, const int16_t* top, const int16_t* left, int n, int bit_depth, int above_ok, int left_ok,
+                       int edge_filters, int16_t* dst, int sd)
+{
+  if (mode == 0)                                              /* planar */
+  {
+    int sh = log2i(n);
+    for (int y = 0; y < n; y++)
+      for (int x = 0; x < n; x++)
+      {
+        int hor = (n - 1 - x) * left[1 + y] + (x + 1) * top[1 + n];
+        int ver = (n - 1 - y) * top[1 + x] + (y + 1) * left[1 + n];
+        dst[y * sd + x] = (int16_t)((hor + ver + n) >> (sh + 1));
+      }
+    return;
+  }
+  if (mode == 1)                                              /* DC */
+  {
+    int sum = 0, dc;
+    if (above_ok) for (int i = 0; i < n; i++) sum += top[1 + i];
+    if (left_ok)  for (int i = 0; i < n; i++) sum += left[1 + i];
+    if (above_ok && left_ok) dc = (sum + n) / (2 * n);
+    else if (above_ok || left_ok) dc = (sum + n / 2) / n;
+    else dc = left[1];                                        /* pSrc[-1] (:218) */
+    for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) dst[y * sd + x] = (int16_t)dc;
+    if (above_ok && left_ok && n <= 16)                       /* xDCPredFiltering, luma, blocks up to 16x16 */
+    {
+      dst[0] = (int16_t)((top[1] + left[1] + 2 * dc + 2) >> 2);
+      for (int x = 1; x < n; x++) dst[x] = (int16_t)((top[1 + x] + 3 * dc + 2) >> 2);
+      for (int y = 1; y < n; y++) dst[y * sd] = (int16_t)((left[1 + y] + 3 * dc + 2) >> 2);
+    }
+    return;
+  }
+  static const int ang_tab[9] = {0, 2, 5, 9, 13, 17, 21, 26, 32};
+  static const int inv_tab[9] = {0, 4096, 1638, 910, 630, 482, 390, 315, 256};
+  const int ver = mode >= 18;
+  const int am = ver ? mode - 26 : -(mode - 10);
+  const int aabs = am < 0 ? -am : am;
+  const int angle = (am < 0 ? -1 : 1) * ang_tab[aabs];
+  const int16_t* mainl = ver ? top : left;                    /* index 0 = corner */
+  const int16_t* side = ver ? left : top;
+  int16_t buf[3 * 64 + 2];
+  int16_t* ref = buf + 64;                                    /* ref[-n .. 2n], ref[0] = corner */
+  if (angle < 0)
+  {
+    for (int i = 0; i <= n; i++) ref[i] = mainl[i];
+    int last = (n * angle) >> 5, acc = 128;
+    for (int k = -1; k > last; k--) { acc += inv_tab[aabs]; ref[k] = side[acc >> 8]; }
+  }
+  else
+    for (int i = 0; i <= 2 * n; i++) ref[i] = mainl[i];
+  for (int j = 0; j < n; j++)                                 /* j runs along the prediction direction's minor axis */
+  {
+    int pos = (j + 1) * angle, ip = pos >> 5, fr = pos & 31;
+    for (int i = 0; i < n; i++)
+    {
+      int v;
+      if (angle == 0) v = ref[i + 1];
+      else if (fr)    v = ((32 - fr) * ref[i + ip + 1] + fr * ref[i + ip + 2] + 16) >> 5;
+      else            v = ref[i + ip + 1];
+      if (angle == 0 && i == 0 && edge_filters && n <= 16) v = clip_pel(v + ((side[j + 1] - side[0]) >> 1), bit_depth);
+      if (ver) dst[j * sd + i] = (int16_t)v; else dst[i * sd + j] = (int16_t)v;
+    }
+  }
+}
+
+/* out[35]: Hadamard distortion of every mode, the uiSad of TEncSearch.cpp:2280 (setDistParam ..., bUseHadamard at :2268;
+ * TComRdCost.cpp:380-392 selects DF_HADS*, i.e. xGetHADs). */
+void hmo_intra_modes_had(const int16_t* org, int so, const int16_t* top_unf, const int16_t* left_unf, const int16_t* top_flt,
+                         const int16_t* left_flt, int n, int bit_depth, int above_ok, int left_ok, uint32_t* out)
+{
+  int16_t pred[64 * 64];
+  for (int mode = 0; mode < 35; mode++)
+  {
+    int f = hmo_intra_use_filtered(mode, n);
+    hmo_intra_predict(mode, f ? top_flt : top_unf, f ? left_flt : left_unf, n, bit_depth, above_ok, left_ok, 1, pred, n);
+    out[mode] = hmo_had(org, so, pred, n, n, n, bit_depth);
+  }
+}

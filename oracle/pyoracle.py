@@ -32,7 +32,42 @@ def _ptr(a, off=0):
     return C.cast(a.ctypes.data + 2 * int(off), _p16)
 
 
-class _Base:
+
+
+def _intra_bind(lib, prefix, with_handle):
+    h = [C.c_void_p] if with_handle else []
+    f = getattr(lib, prefix + "intra_use_filtered"); f.restype = C.c_int; f.argtypes = [C.c_int, C.c_int]
+    f = getattr(lib, prefix + "intra_predict"); f.restype = None
+    f.argtypes = h + [C.c_int, _p16, _p16, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p16, C.c_int]
+    f = getattr(lib, prefix + "intra_modes_had"); f.restype = None
+    f.argtypes = h + [_p16, C.c_int, _p16, _p16, _p16, _p16, C.c_int, C.c_int] + ([] if with_handle else [C.c_int, C.c_int]) + [_pu]
+
+
+class _IntraMixin:
+    """35 luma intra predictions + Hadamard distortions (TEncSearch::estIntraPredQT first pass).  top / left: int16 lines
+    of 2n+1 reference samples with the corner at index 0."""
+
+    def intra_use_filtered(self, mode, n):
+        return int(getattr(self.lib, self._pfx + "intra_use_filtered")(int(mode), int(n)))
+
+    def intra_predict(self, mode, top, left, n, bit_depth=8, above_ok=1, left_ok=1, edge_filters=1):
+        top = np.ascontiguousarray(top, dtype=np.int16); left = np.ascontiguousarray(left, dtype=np.int16)
+        out = np.zeros((n, n), dtype=np.int16)
+        args = [int(mode), _ptr(top), _ptr(left), int(n), int(bit_depth), int(above_ok), int(left_ok), int(edge_filters), _ptr(out), int(n)]
+        getattr(self.lib, self._pfx + "intra_predict")(*(self._h() + args))
+        return out
+
+    def intra_modes_had(self, org, top_unf, left_unf, top_flt, left_flt, n, bit_depth=8):
+        (oa, oo, os_) = org
+        arrs = [np.ascontiguousarray(a, dtype=np.int16) for a in (top_unf, left_unf, top_flt, left_flt)]
+        out = np.zeros(35, dtype=np.uint32)
+        args = [_ptr(oa, oo), int(os_)] + [_ptr(a) for a in arrs] + [int(n), int(bit_depth)] + ([] if self._h() else [1, 1]) + \
+               [out.ctypes.data_as(_pu)]
+        getattr(self.lib, self._pfx + "intra_modes_had")(*(self._h() + args))
+        return out
+
+
+class _Base(_IntraMixin):
     """Shared Python surface.  `org`/`cur`/`ref` arguments are (array, element offset, stride) triples."""
 
     def dist(self, kind, org, cur, w, h, bit_depth=8, sub_shift=0):
@@ -52,6 +87,8 @@ class Oracle(_Base):
     def __init__(self, fen=1, hadme=1):
         self.fen, self.hadme = int(fen), int(hadme)
         L = self.lib = C.CDLL(_b.build_oracle())
+        self._pfx = "hmo_"; self._h = lambda: []
+        _intra_bind(L, "hmo_", False)
         L.hmo_eg_bits.restype = C.c_uint32
         L.hmo_eg_bits.argtypes = [C.c_int32]
         L.hmo_mv_bits.restype = C.c_uint32
@@ -165,6 +202,8 @@ class Reference(_Base):
             raise FileNotFoundError("oracle/_ref/libhmref.so not built (needs /root/reference)")
         self.fen, self.hadme = int(fen), int(hadme)
         L = self.lib = C.CDLL(so)
+        self._pfx = "hmref_"; self._h = lambda: [self.h]
+        _intra_bind(L, "hmref_", True)
         L.hmref_create.restype = C.c_void_p
         L.hmref_create.argtypes = [C.c_int, C.c_int]
         L.hmref_destroy.argtypes = [C.c_void_p]

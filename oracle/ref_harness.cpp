@@ -174,6 +174,21 @@ struct Harness : public TEncSearch
     xTZSearch(&cu, &pat, refAtPu, refStride, &lt, &rb, mv, d, hasImv ? &imv : NULL);
     *mvx = mv.getHor(); *mvy = mv.getVer(); *sad = d;
   }
+
+  // one luma intra prediction the way TComPrediction::predIntraAng (TComPrediction.cpp:412-494) produces it, from a
+  // (2n+1)-strided reference-sample buffer laid out like m_piYuvExt (row 0 = corner / above / above-right, column 0 =
+  // left / below-left).  predIntraAng itself needs a TComTU; its body for the non-DPCM case is these three protected calls.
+  void intraPredict(int mode, const Pel* buf, int n, int bitDepth, bool above, bool left, bool edgeFilters, Pel* dst, int dstStride)
+  {
+    const Int sw = 2 * n + 1;
+    const Pel* src = buf + sw + 1;
+    if (mode == PLANAR_IDX) xPredIntraPlanar(src, sw, dst, dstStride, n, n);
+    else
+    {
+      xPredIntraAng(bitDepth, src, sw, dst, dstStride, n, n, CHANNEL_TYPE_LUMA, mode, above, left, edgeFilters);
+      if (mode == DC_IDX && above && left) xDCPredFiltering(src, sw, dst, dstStride, n, n, CHANNEL_TYPE_LUMA);
+    }
+  }
 };
 
 bool g_rom = false;
@@ -320,6 +335,39 @@ int hmref_read_luma(const char* path, int width, int height, int pad_x, int pad_
   pic.destroy();
   io.close();
   return ok ? 0 : -1;
+}
+
+
+// 35 luma intra predictions + Hadamard distortions of one block (TEncSearch::estIntraPredQT first pass, TEncSearch.cpp:
+// 2270-2296).  top / left: reference lines with the corner at index 0 (2n+1 samples each), unfiltered and smoothed.
+int hmref_intra_use_filtered(int mode, int n)
+{
+  return TComPrediction::filteringIntraReferenceSamples(COMPONENT_Y, mode, n, n, CHROMA_420, false) ? 1 : 0;
+}
+void hmref_intra_predict(void* hv, int mode, const int16_t* top, const int16_t* left, int n, int bit_depth, int above_ok, int left_ok,
+                         int edge_filters, int16_t* dst, int dst_stride)
+{
+  Harness* H = static_cast<Harness*>(hv);
+  const int sw = 2 * n + 1;
+  std::vector<Pel> buf((size_t)sw * sw, 0);
+  for (int i = 0; i < sw; i++) buf[i] = top[i];
+  for (int i = 1; i < sw; i++) buf[(size_t)i * sw] = left[i];
+  H->intraPredict(mode, buf.data(), n, bit_depth, above_ok != 0, left_ok != 0, edge_filters != 0, dst, dst_stride);
+}
+void hmref_intra_modes_had(void* hv, const int16_t* org, int org_stride, const int16_t* top_unf, const int16_t* left_unf,
+                           const int16_t* top_flt, const int16_t* left_flt, int n, int bit_depth, uint32_t* out)
+{
+  Harness* H = static_cast<Harness*>(hv);
+  std::vector<Pel> pred((size_t)n * n);
+  DistParam dp;
+  H->rd.setDistParam(dp, bit_depth, const_cast<Pel*>(org), org_stride, pred.data(), n, n, n, true);      // TEncSearch.cpp:2268
+  dp.bApplyWeight = false;
+  for (int mode = 0; mode < 35; mode++)
+  {
+    const bool f = hmref_intra_use_filtered(mode, n) != 0;
+    hmref_intra_predict(hv, mode, f ? top_flt : top_unf, f ? left_flt : left_unf, n, bit_depth, 1, 1, 1, pred.data(), n);
+    out[mode] = dp.DistFunc(&dp);
+  }
 }
 
 } // extern "C"

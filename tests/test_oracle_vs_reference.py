@@ -100,3 +100,39 @@ def test_tie_break_is_raster_first(oracle, reference):
         b = reference.pattern_search((cur, off, 200), 8, 8, (ref, off, 200), (-5, -4), (6, 7), lam, pred)
         assert a == b
     assert oracle.pattern_search((cur, off, 200), 8, 8, (ref, off, 200), (-5, -4), (6, 7), 0, (0, 0))[0] == (-5, -4)
+
+
+def _intra_lines(rng, n, bd, kind):
+    hi = (1 << bd) - 1
+    if kind == 0:
+        top, left = rng.integers(0, hi + 1, 2 * n + 1), rng.integers(0, hi + 1, 2 * n + 1)
+    elif kind == 1:      # smooth ramp + small noise (what smoothed reference samples look like)
+        top = np.clip(np.linspace(rng.integers(0, hi), rng.integers(0, hi), 2 * n + 1) + rng.integers(-3, 4, 2 * n + 1), 0, hi)
+        left = np.clip(np.linspace(top[0], rng.integers(0, hi), 2 * n + 1) + rng.integers(-3, 4, 2 * n + 1), 0, hi)
+    else:                # extremes
+        top, left = rng.choice([0, hi], 2 * n + 1), rng.choice([0, hi], 2 * n + 1)
+    top = np.asarray(top, dtype=np.int16); left = np.asarray(left, dtype=np.int16)
+    left[0] = top[0]
+    return top, left
+
+
+def test_intra_predictions_and_mode_distortions(oracle, reference):
+    """All 35 luma intra predictions (planar, DC + edge filter, 33 angles incl. the filtered pure vertical / horizontal),
+    the smoothed-reference decision and the per-mode Hadamard distortion of the first pass, restatement vs reference."""
+    O, R = oracle, reference
+    rng = np.random.default_rng(77)
+    for n in (4, 8, 16, 32, 64):
+        for mode in range(35):
+            assert O.intra_use_filtered(mode, n) == R.intra_use_filtered(mode, n), (mode, n)
+        for bd in (8, 10):
+            for kind in range(3):
+                top, left = _intra_lines(rng, n, bd, kind)
+                for mode in range(35):
+                    for above_ok, left_ok, ef in ((1, 1, 1), (1, 1, 0)) + (((1, 0, 1), (0, 1, 1), (0, 0, 1)) if mode == 1 else ()):
+                        a = O.intra_predict(mode, top, left, n, bd, above_ok, left_ok, ef)
+                        b = R.intra_predict(mode, top, left, n, bd, above_ok, left_ok, ef)
+                        assert np.array_equal(a, b), (n, bd, kind, mode, above_ok, left_ok, ef)
+                top2, left2 = _intra_lines(rng, n, bd, 1)
+                org = rng.integers(0, 1 << bd, (n, n)).astype(np.int16)
+                assert np.array_equal(O.intra_modes_had((org, 0, n), top, left, top2, left2, n, bd),
+                                      R.intra_modes_had((org, 0, n), top, left, top2, left2, n, bd)), (n, bd, kind)

@@ -20,6 +20,7 @@ DIST_DESC_DTYPE = np.dtype([("org_plane", "<i4"), ("org_x", "<i4"), ("org_y", "<
                             ("cur_plane", "<i4"), ("cur_x", "<i4"), ("cur_y", "<i4"),
                             ("w", "<i4"), ("h", "<i4"), ("sub_shift", "<i4"), ("reserved", "<i4")])
 MC_DESC_DTYPE = np.dtype([("pu_x", "<i4"), ("pu_y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("mv_x", "<i4"), ("mv_y", "<i4")])
+INTRA_BLOCK_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("n", "<i4"), ("ref_off", "<i4"), ("flags", "<i4"), ("reserved", "<i4")])
 TZ_EXTRA_DTYPE = np.dtype([("cu_x", "<i4"), ("cu_y", "<i4"), ("has_imv", "<i4"), ("imv_x", "<i4"), ("imv_y", "<i4"),
                            ("reserved", "<i4", (3,))])
 assert TZ_EXTRA_DTYPE.itemsize == 32
@@ -76,6 +77,8 @@ def _load():
         "hmb200_dist": (u32, [C.POINTER(_DistParam)]),
         "hmb200_dist_batch": (i32, [i32, i32, i32, vp, vp]),
         "hmb200_mc_dist_batch": (i32, [i32, i32, i32, i32, vp, vp]),
+        "hmb200_intra_modes_had_batch": (i32, [i32, i32, vp, vp, i32, vp]),
+        "hmb200_intra_modes_had": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp]),
         "hmb200_pattern_search": (i32, [C.POINTER(_Pattern), vp, i32, _Mv, _Mv, C.POINTER(_CostState), i32,
                                         C.POINTER(_Mv), C.POINTER(u32)]),
         "hmb200_pattern_search_tz": (i32, [C.POINTER(_Pattern), vp, i32, _Mv, _Mv, C.POINTER(_CostState), i32, vp, i32, i32, i32, i32,
@@ -225,6 +228,26 @@ class HMB200:
         descs = np.ascontiguousarray(descs, dtype=MC_DESC_DTYPE)
         out = np.zeros(len(descs), dtype=np.uint32)
         self._check(self.lib.hmb200_mc_dist_batch(cur_plane, ref_plane, func, len(descs), descs.ctypes.data, out.ctypes.data))
+        return out
+
+    # -- intra first pass ------------------------------------------------------------------------------------------
+    def intra_modes_had_batch(self, org_plane, blocks, refs):
+        """blocks: INTRA_BLOCK_DTYPE records; refs: int16 array holding every block's four reference lines (see the
+        header).  Returns a (len(blocks), 35) uint32 array: the first-pass Hadamard distortion of every mode."""
+        blocks = np.ascontiguousarray(blocks, dtype=INTRA_BLOCK_DTYPE)
+        refs = np.ascontiguousarray(refs, dtype=np.int16)
+        out = np.zeros((len(blocks), 35), dtype=np.uint32)
+        self._check(self.lib.hmb200_intra_modes_had_batch(org_plane, len(blocks), blocks.ctypes.data, refs.ctypes.data, refs.size,
+                                                          out.ctypes.data))
+        return out
+
+    def intra_modes_had(self, org, ref_unf, ref_flt, n, bit_depth=8, above=1, left=1):
+        """1:1 form: org = (array, offset, stride); ref_unf / ref_flt: (2n+1) x (2n+1) int16 predictor buffers."""
+        (oa, oo, os_) = org
+        ref_unf = np.ascontiguousarray(ref_unf, dtype=np.int16); ref_flt = np.ascontiguousarray(ref_flt, dtype=np.int16)
+        out = np.zeros(35, dtype=np.uint32)
+        self._check(self.lib.hmb200_intra_modes_had(_addr(oa, oo), os_, ref_unf.ctypes.data, ref_flt.ctypes.data, n, bit_depth,
+                                                    above, left, out.ctypes.data))
         return out
 
     # -- 1:1 searches ----------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@
 #include "hmb200_search8.cuh"
 #include "hmb200_search8_cu.cuh"
 #include "hmb200_search16_cu.cuh"
+#include "hmb200_intra.cuh"
 #include "hmb200_frac.cuh"
 #include "hmb200_tz.cuh"
 
@@ -574,6 +575,89 @@ int hmb200_mc_dist_batch(int cur_plane, int ref_plane, int func, int n, const hm
   frac_free_schedule(&fs);
   if (nl < 0 || e != cudaSuccess) return fail(HMB200_ERR_CUDA, std::string("hmb200_mc_dist_batch: ") + cudaGetErrorString(cudaGetLastError()));
   return HMB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// intra first pass
+// ------------------------------------------------------------------------------------------------------------------
+static int intra_run(const DevPlane& org, int nblocks, const hmb200_intra_block* blocks, const int16_t* refs, int n_ref_samples,
+                     const void* org_upload, size_t org_upload_bytes, uint32_t* out) {
+  std::vector<IntraBlockDev> hb((size_t)nblocks);
+  std::vector<int32_t> ord4, ord8;
+  for (int i = 0; i < nblocks; i++) {
+    const hmb200_intra_block& b = blocks[i];
+    if (!(b.n == 4 || b.n == 8 || b.n == 16 || b.n == 32 || b.n == 64) || b.ref_off < 0 || (int64_t)b.ref_off + 4 * (2 * b.n + 1) > n_ref_samples)
+      return fail(HMB200_ERR_ARG, "hmb200_intra_modes_had: bad block size or reference-line offset in block " + std::to_string(i));
+    if (!org_upload && (b.x < -org.margin_x || b.y < -org.margin_y || b.x + b.n > org.width + org.margin_x || b.y + b.n > org.height + org.margin_y))
+      return fail(HMB200_ERR_ARG, "hmb200_intra_modes_had: block " + std::to_string(i) + " leaves the padded plane");
+    hb[(size_t)i] = IntraBlockDev{b.x, b.y, b.n, b.ref_off, b.flags, 0};
+    (b.n == 4 ? ord4 : ord8).push_back(i);
+  }
+  auto up64 = [](size_t v) { return (v + 63) & ~(size_t)63; };
+  const size_t bb = up64(hb.size() * sizeof(IntraBlockDev)), ob = up64((size_t)nblocks * sizeof(int32_t)), rb = up64((size_t)n_ref_samples * 2),
+               ub = up64(org_upload_bytes), outb = (size_t)nblocks * INTRA_MODES * sizeof(uint32_t);
+  int rc = ensure_dstage(bb + ob + rb + ub + outb + 256);
+  if (rc != HMB200_OK) return rc;
+  char* base = reinterpret_cast<char*>(g.dstage);
+  IntraBlockDev* d_blocks = reinterpret_cast<IntraBlockDev*>(base);
+  int32_t* d_ord = reinterpret_cast<int32_t*>(base + bb);
+  int16_t* d_refs = reinterpret_cast<int16_t*>(base + bb + ob);
+  void* d_org = base + bb + ob + rb;
+  uint32_t* d_out = reinterpret_cast<uint32_t*>(base + bb + ob + rb + ub);
+  std::vector<int32_t> ord(ord8);
+  ord.insert(ord.end(), ord4.begin(), ord4.end());
+  CUDA_TRY(cudaMemcpyAsync(d_blocks, hb.data(), hb.size() * sizeof(IntraBlockDev), cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(d_ord, ord.data(), ord.size() * sizeof(int32_t), cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(d_refs, refs, (size_t)n_ref_samples * 2, cudaMemcpyHostToDevice, g.stream));
+  DevPlane pl = org;
+  if (org_upload) {
+    CUDA_TRY(cudaMemcpyAsync(d_org, org_upload, org_upload_bytes, cudaMemcpyHostToDevice, g.stream));
+    pl.base = d_org;
+  }
+  const int bd = pl.bit_depth;
+  if (!ord8.empty()) {
+    if (pl.bytes_per_sample == 1) k_intra_modes_had<8, uint8_t><<<(int)ord8.size(), INTRA_THREADS, 0, g.stream>>>(d_blocks, d_ord, d_refs, d_out, pl, bd);
+    else                          k_intra_modes_had<8, int16_t><<<(int)ord8.size(), INTRA_THREADS, 0, g.stream>>>(d_blocks, d_ord, d_refs, d_out, pl, bd);
+    g.launches++;
+  }
+  if (!ord4.empty()) {
+    if (pl.bytes_per_sample == 1) k_intra_modes_had<4, uint8_t><<<(int)ord4.size(), INTRA_THREADS, 0, g.stream>>>(d_blocks, d_ord + ord8.size(), d_refs, d_out, pl, bd);
+    else                          k_intra_modes_had<4, int16_t><<<(int)ord4.size(), INTRA_THREADS, 0, g.stream>>>(d_blocks, d_ord + ord8.size(), d_refs, d_out, pl, bd);
+    g.launches++;
+  }
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, outb, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaGetLastError());
+  return HMB200_OK;
+}
+
+int hmb200_intra_modes_had_batch(int org_plane, int nblocks, const hmb200_intra_block* blocks, const int16_t* refs, int n_ref_samples,
+                                 uint32_t* out) {
+  NEED_READY();
+  if (nblocks <= 0) return HMB200_OK;
+  Plane* po = get_plane(org_plane);
+  if (!po) return fail(HMB200_ERR_ARG, "hmb200_intra_modes_had_batch: unknown plane");
+  if (!blocks || !refs || !out || n_ref_samples <= 0) return fail(HMB200_ERR_ARG, "hmb200_intra_modes_had_batch: bad arguments");
+  return intra_run(po->d, nblocks, blocks, refs, n_ref_samples, nullptr, 0, out);
+}
+
+int hmb200_intra_modes_had(const int16_t* org, int org_stride, const int16_t* ref_unf, const int16_t* ref_flt, int n, int bit_depth,
+                           int above, int left, uint32_t* out) {
+  NEED_READY();
+  if (!org || !ref_unf || !ref_flt || !out || org_stride < n || bit_depth < 8 || bit_depth > 14 ||
+      !(n == 4 || n == 8 || n == 16 || n == 32 || n == 64))
+    return fail(HMB200_ERR_ARG, "hmb200_intra_modes_had: bad arguments");
+  const int L = 2 * n + 1;
+  std::vector<int16_t> lines((size_t)4 * L), blk((size_t)n * n);
+  for (int i = 0; i < L; i++) {                               // row 0 and column 0 of the (2n+1)-strided predictor buffers
+    lines[i] = ref_unf[i];             lines[L + i] = ref_unf[(size_t)i * L];
+    lines[2 * L + i] = ref_flt[i];     lines[3 * L + i] = ref_flt[(size_t)i * L];
+  }
+  for (int y = 0; y < n; y++) memcpy(&blk[(size_t)y * n], org + (size_t)y * org_stride, (size_t)n * 2);
+  DevPlane pl{};
+  pl.base = nullptr; pl.pitch = n; pl.width = n; pl.height = n; pl.margin_x = 0; pl.margin_y = 0; pl.bytes_per_sample = 2; pl.bit_depth = bit_depth;
+  hmb200_intra_block b{0, 0, n, 0, (above ? 1 : 0) | (left ? 2 : 0), 0};
+  return intra_run(pl, 1, &b, lines.data(), 4 * L, blk.data(), blk.size() * 2, out);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -650,7 +650,9 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
     const int nc = stage == 0 ? 9 : 8;
     auto blocks = [&](int n_tiles) { return (int)((((long long)(n_tiles + 31) / 32) * 32 * nc + FRAC_TILE_THREADS - 1) / FRAC_TILE_THREADS); };
     constexpr bool PATCH = sizeof(RefT) == 1 && sizeof(OrgT) == 1;        // 8-bit planes: shared-memory patches (k_frac_hv / k_frac_patch)
-    static const bool old_path = getenv("HMB200_FRAC_PATCH") != nullptr;  // A/B knob: per-candidate first pass
+    static const bool old_path = getenv("HMB200_FRAC_PATCH") != nullptr;  // A/B knob: per-candidate first pass for 8x8 tiles too
+    static const bool hv4 = getenv("HMB200_FRAC_HV4") != nullptr;         // 4x4 tiles: the shared first pass costs more in barriers than
+                                                                          // it saves (ncu: 263 vs 225 us per stage), so it is opt-in
     const int tpc = FRAC_TILE_THREADS / nc;
     if (fs.n_tiles8 > 0) {
       if constexpr (PATCH) {
@@ -668,7 +670,7 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
       if constexpr (PATCH) {
         const int nb4 = (fs.n_tiles4 + tpc - 1) / tpc;
         if (!use_had)      k_frac_patch<4, false><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
-        else if (old_path) k_frac_patch<4, true><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
+        else if (!hv4)     k_frac_patch<4, true><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
         else               k_frac_hv<4, true><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
       } else {
         if (use_had) k_frac_tiles<RefT, OrgT, 4, true><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
