@@ -402,7 +402,7 @@ def run_ours(args):
                                  "H>8) per second; executed = abs-diffs the kernels really issue (CU-fused kernels compute each "
                                  "CU sample once for all 13 partitions, so achieved/peak may exceed 1; executed_frac is the pipe "
                                  "utilisation); per-rank search time incl. key memset + finalize"},
-            "roofline_refine": {"bound": "int_alu", "kernel": ("k_frac_patch<8|4,HAD>" if BIT_DEPTH == 8 else "k_frac_tiles<i16,i16,8|4,HAD>"), "achieved": frac_ops / (frac / K / 1e3) / 1e12,
+            "roofline_refine": {"bound": "int_alu", "kernel": ("k_frac_hv<8,HAD> + k_frac_patch<4,HAD>" if BIT_DEPTH == 8 else "k_frac_tiles<i16,i16,8|4,HAD>"), "achieved": frac_ops / (frac / K / 1e3) / 1e12,
                                 "peak": imad_peak / 1e12, "unit": "Tintop/s", "frac": frac_ops / (frac / K / 1e3) / imad_peak,
                                 "traffic": None, "peak_source": "measured IMAD issue rate, profiles/r01_microbench_int.json",
                                 "note": "400 integer ops per PU pixel (model, DESIGN.md 3.2)"},
