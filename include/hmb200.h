@@ -256,6 +256,12 @@ hmb200_prepared* hmb200_prepare_jobs(const hmb200_pu_job* jobs, int njobs, int f
 void hmb200_free_prepared(hmb200_prepared* p);
 int  hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane);
 int  hmb200_fetch_results(hmb200_prepared* p, hmb200_pu_result* results);   /* D2H + sync */
+/* Transport only (no reference counterpart): the D2H copy of the last run's results on a second stream, so that it runs
+ * behind the next frame pair's upload and kernels (alternate two prepared handles).  results must be page-locked
+ * (hmb200_host_alloc).  hmb200_fetch_wait blocks until they have arrived; a new hmb200_run_prepared on the same handle
+ * is ordered after a pending fetch on the device. */
+int  hmb200_fetch_results_async(hmb200_prepared* p, hmb200_pu_result* results);
+int  hmb200_fetch_wait(hmb200_prepared* p);
 int  hmb200_sync(void);
 /* CUDA-event timing of the last hmb200_run_prepared: total and per-kernel milliseconds. */
 int  hmb200_last_timing(float* total_ms, float* search_ms, float* frac_ms);

@@ -265,6 +265,49 @@ def _run_full(hm, cur, ref, jobs, flags):
         hm.release_plane(idr)
 
 
+def test_pipelined_fetch_equals_blocking_fetch(hm):
+    """hmb200_fetch_results_async / hmb200_fetch_wait with two alternating prepared handles (what bench.py's end-to-end
+    leg does): every frame pair's MV field equals the one a blocking run + fetch gives; a handle that is run again while
+    its fetch is pending is ordered after the copy."""
+    from video_codecs_b200 import RESULT_DTYPE
+    W, H = 256, 192
+    frames = [synth.luma_frame(W, H, t, seed=31) for t in range(4)]
+    lam = int(np.floor(65536.0 * np.sqrt(0.4624 * 2 ** ((35 - 12) / 3.0))))
+    jobs = hm.build_canonical_jobs(W, H, 64, lam)[::5]
+    flags = flags_of(1, 1)
+    preps = [hm.prepare_jobs(jobs, flags, 8), hm.prepare_jobs(jobs, flags, 8)]
+    outs = [hm.host_array(len(jobs), RESULT_DTYPE), hm.host_array(len(jobs), RESULT_DTYPE)]
+    pinned = []
+    for f in frames:
+        a = hm.host_array(f.size, np.uint8).reshape(f.shape)
+        a[...] = f
+        pinned.append(a)
+    got = []
+    try:
+        for k in range(6):
+            p, o = preps[k % 2], outs[k % 2]
+            p.fetch_wait()
+            if k >= 2:
+                got.append(o.copy())
+            idc = hm.register_plane_u8(pinned[(k + 1) % 4], MARGIN, MARGIN, kind=0)
+            idr = hm.register_plane_u8(pinned[k % 4], MARGIN, MARGIN, kind=1)
+            p.run(idc, idr)
+            p.fetch_async(o)
+            hm.release_plane(idc)
+            hm.release_plane(idr)
+        for k in (4, 5):
+            preps[k % 2].fetch_wait()
+            got.append(outs[k % 2].copy())
+        for k in range(6):
+            exp, _ = _run_full(hm, frames[(k + 1) % 4], frames[k % 4], jobs, flags)
+            assert results_equal(got[k], exp) == [], k
+        with pytest.raises(Exception):
+            preps[0].fetch_async(np.zeros(len(jobs), dtype=RESULT_DTYPE))      # pageable memory is refused
+    finally:
+        for p in preps:
+            p.free()
+
+
 def test_1080p_fused_path_equals_per_pu_path_and_oracle_samples(hm, monkeypatch):
     """The CU-fused kernels (one pass per CU for all 13 partitions) and the per-PU kernels must give the same MV field,
     SADs and refinement for the whole 1080p canonical list; 400 sampled PUs are also checked against the oracle."""

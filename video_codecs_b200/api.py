@@ -89,6 +89,7 @@ def _load():
         "hmb200_me_ctu_row": (i32, [i32, i32, i32, i32, vp, i32, i32, vp]),
         "hmb200_prepare_jobs": (vp, [vp, i32, i32, i32]), "hmb200_free_prepared": (None, [vp]),
         "hmb200_run_prepared": (i32, [vp, i32, i32]), "hmb200_fetch_results": (i32, [vp, vp]),
+        "hmb200_fetch_results_async": (i32, [vp, vp]), "hmb200_fetch_wait": (i32, [vp]),
         "hmb200_sync": (i32, []),
         "hmb200_last_timing": (i32, [C.POINTER(C.c_float)] * 3),
         "hmb200_prepared_work": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -339,6 +340,13 @@ class Prepared:
             out = np.zeros(self.n, dtype=RESULT_DTYPE)
         self.o._check(self.o.lib.hmb200_fetch_results(self.h, out.ctypes.data))
         return out
+
+    def fetch_async(self, out):
+        """D2H of the last run's results on the copy stream; `out` must be a HMB200.host_array."""
+        self.o._check(self.o.lib.hmb200_fetch_results_async(self.h, out.ctypes.data))
+
+    def fetch_wait(self):
+        self.o._check(self.o.lib.hmb200_fetch_wait(self.h))
 
     def timing(self):
         t = [C.c_float() for _ in range(3)]

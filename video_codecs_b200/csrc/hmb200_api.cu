@@ -42,6 +42,7 @@ struct State {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};     // side streams for concurrent variant kernels
+  cudaStream_t copy = nullptr;                                     // D2H of results behind the next frame pair's kernels (hmb200_fetch_results_async)
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<Plane> planes;
   void* pinned = nullptr; size_t pinned_bytes = 0;
@@ -167,6 +168,8 @@ struct hmb200_prepared {
   FracSchedule frac;              // tile tables of the batched quarter-pel refinement
   hmb200_tz_extra* d_tz = nullptr;    // HMB200_FLAG_TZ: per-PU CU geometry / 2Nx2N integer MV
   TzParams tz{0, 0, 0, 0, 0};
+  cudaEvent_t ev_done = nullptr, ev_fetched = nullptr;   // end of the last run on the compute stream / of the last asynchronous fetch
+  bool fetch_pending = false;
 };
 
 extern "C" {
@@ -190,6 +193,7 @@ int hmb200_init(int device) {
   CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   for (auto& ev : g.ev) CUDA_TRY(cudaEventCreate(&ev));
   for (auto& st : g.side) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
   for (auto& ev : g.ev_join) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   int rc = search8_configure(&g_err);
@@ -220,6 +224,7 @@ void hmb200_shutdown(void) {
   g.pinned = nullptr; g.pinned_bytes = 0; g.dstage = nullptr; g.dstage_bytes = 0;
   for (auto& ev : g.ev) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
   for (auto& st : g.side) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; }
+  if (g.copy) { cudaStreamSynchronize(g.copy); cudaStreamDestroy(g.copy); g.copy = nullptr; }
   if (g.ev_fork) { cudaEventDestroy(g.ev_fork); g.ev_fork = nullptr; }
   for (auto& ev : g.ev_join) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
   cudaStreamDestroy(g.stream); g.stream = nullptr;
@@ -396,7 +401,9 @@ int hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width,
   k_pad_plane_u8<<<grid, 256, 0, g.stream>>>(reinterpret_cast<const uint8_t*>(g.dstage), width,
                                              reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, width, height, margin_x, margin_y);
   g.launches++;
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  // a page-locked source stays the caller's until the copy has run (hmb200_sync / any fetch orders it); the library's own
+  // staging buffer is reused by the next call, so that path waits here
+  if (!user_pinned) CUDA_TRY(cudaStreamSynchronize(g.stream));
   p.kind = kind; p.poc = poc;
   return id;
 }
@@ -712,7 +719,9 @@ hmb200_prepared* hmb200_prepare_jobs(const hmb200_pu_job* jobs, int njobs, int f
 
 void hmb200_free_prepared(hmb200_prepared* p) {
   if (!p) return;
-  if (g.ready) cudaStreamSynchronize(g.stream);
+  if (g.ready) { cudaStreamSynchronize(g.stream); if (g.copy) cudaStreamSynchronize(g.copy); }
+  if (p->ev_done) cudaEventDestroy(p->ev_done);
+  if (p->ev_fetched) cudaEventDestroy(p->ev_fetched);
   if (p->d_tasks) cudaFree(p->d_tasks);
   if (p->d_results) cudaFree(p->d_results);
   search8_free_schedule(&p->sched);
@@ -782,6 +791,7 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
   if (!pc || !pr) return fail(HMB200_ERR_ARG, "hmb200_run_prepared: unknown plane");
   if (pr->d.bit_depth != p->bit_depth) return fail(HMB200_ERR_ARG, "hmb200_run_prepared: bit depth differs from prepare_jobs");
   if (p->n == 0) return HMB200_OK;
+  if (p->fetch_pending) CUDA_TRY(cudaStreamWaitEvent(g.stream, p->ev_fetched, 0));     // the results of the previous run are still being copied out
   CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
   const Search8Schedule& sc = p->sched;
   const CuSchedule& cu = p->cu;
@@ -853,6 +863,8 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
     g.launches += (uint64_t)nl;
   }
   CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  if (!p->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(p->ev_done, g.stream));
   CUDA_TRY(cudaGetLastError());
   return HMB200_OK;
 }
@@ -869,10 +881,35 @@ int hmb200_last_timing(float* total_ms, float* search_ms, float* frac_ms) {
   return HMB200_OK;
 }
 
+int hmb200_fetch_results_async(hmb200_prepared* p, hmb200_pu_result* results) {
+  NEED_READY();
+  if (!p || (p->n > 0 && !results)) return fail(HMB200_ERR_ARG, "hmb200_fetch_results_async: bad arguments");
+  if (p->n == 0) return HMB200_OK;
+  if (!p->ev_done) return fail(HMB200_ERR_STATE, "hmb200_fetch_results_async: nothing has run on this handle");
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, results) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (!pinned) return fail(HMB200_ERR_ARG, "hmb200_fetch_results_async: results must come from hmb200_host_alloc (page-locked)");
+  if (!p->ev_fetched) CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fetched, cudaEventDisableTiming));
+  CUDA_TRY(cudaStreamWaitEvent(g.copy, p->ev_done, 0));
+  CUDA_TRY(cudaMemcpyAsync(results, p->d_results, (size_t)p->n * sizeof(hmb200_pu_result), cudaMemcpyDeviceToHost, g.copy));
+  CUDA_TRY(cudaEventRecord(p->ev_fetched, g.copy));
+  p->fetch_pending = true;
+  return HMB200_OK;
+}
+
+int hmb200_fetch_wait(hmb200_prepared* p) {
+  NEED_READY();
+  if (!p) return fail(HMB200_ERR_ARG, "null handle");
+  if (p->fetch_pending) { CUDA_TRY(cudaEventSynchronize(p->ev_fetched)); p->fetch_pending = false; }
+  return HMB200_OK;
+}
+
 int hmb200_fetch_results(hmb200_prepared* p, hmb200_pu_result* results) {
   NEED_READY();
   if (!p || (p->n > 0 && !results)) return fail(HMB200_ERR_ARG, "hmb200_fetch_results: bad arguments");
   if (p->n == 0) return HMB200_OK;
+  if (p->fetch_pending) { CUDA_TRY(cudaEventSynchronize(p->ev_fetched)); p->fetch_pending = false; }
   const size_t bytes = (size_t)p->n * sizeof(hmb200_pu_result);
   cudaPointerAttributes attr;
   const bool user_pinned = cudaPointerGetAttributes(&attr, results) == cudaSuccess && attr.type == cudaMemoryTypeHost;
