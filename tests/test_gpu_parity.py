@@ -416,6 +416,31 @@ def test_fused_windows_at_every_alignment(hm, fen):
         hm.release_plane(idr)
 
 
+def test_fused_small_cus_wide_windows_index_flush(hm):
+    """+-128 windows for every 8x8 and 16x16 CU of a CTU: a warp's run of 8x8-CU tiles covers more candidate rows than the
+    local index of the argmin key can number, so the kernel has to flush mid-CU (and a lane sees up to three tiles per
+    row group); half of the runs use flat content so that only the raster order decides."""
+    W, H = 320, 256
+    lam = 77777
+    for flat in (False, True):
+        f0 = np.full((H, W), 90, dtype=np.uint8) if flat else synth.luma_frame(W, H, 0, seed=17)
+        f1 = f0 if flat else synth.luma_frame(W, H, 2, seed=17)
+        jobs = hm.build_canonical_jobs(W, H, 128, 0 if flat else lam, pred=(0, 0) if flat else (-9, 14), ctu_first=6, ctu_count=1)
+        jobs = jobs[np.maximum(jobs["w"], jobs["h"]) <= 16]
+        jobs = jobs[: 13 * 4 + 5 * 24] if flat else jobs[::2]
+        cur, o0, stride = padded(f1, 144)
+        ref, _, _ = padded(f0, 144)
+        idc = hm.register_plane_u8(f1, 144, 144, kind=0)
+        idr = hm.register_plane_u8(f0, 144, 144, kind=1)
+        try:
+            got = hm.me_jobs(idc, idr, jobs, flags_of(1, 1, frac=False))
+        finally:
+            hm.release_plane(idc)
+            hm.release_plane(idr)
+        exp, _ = Oracle(fen=1, hadme=1).run_jobs((cur, o0, stride), (ref, o0, stride), jobs, 8, False)
+        assert results_equal(got, exp, ("mv_x", "mv_y", "sad")) == [], flat
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # 10-bit content: CU-fused 16-bit kernels (packed 16x2 arithmetic, distortion precision shift)
 # ---------------------------------------------------------------------------------------------------------------------
