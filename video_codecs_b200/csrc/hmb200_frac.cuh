@@ -423,8 +423,11 @@ __device__ __forceinline__ void frac_hrow(uint32_t prow, uint32_t sh, int t0, in
   }
 }
 
+#ifndef HV8_MIN_CTAS
+#define HV8_MIN_CTAS 5            // 96 registers, 5 CTAs per SM: 1.358 ms per 1080p frame pair vs 1.378 at 4 (112 registers) and 1.478 at 6 (80, spills)
+#endif
 template <int N, bool HAD>
-__global__ void __launch_bounds__(FRAC_TILE_THREADS, N == 8 ? 4 : 8)
+__global__ void __launch_bounds__(FRAC_TILE_THREADS, N == 8 ? HV8_MIN_CTAS : 8)
 k_frac_hv(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_result* __restrict__ results,
           const uint32_t* __restrict__ tiles, int n_tiles, uint32_t* __restrict__ dist, DevPlane cur_plane, DevPlane ref_plane) {
   typedef FracPatch<N> P;
