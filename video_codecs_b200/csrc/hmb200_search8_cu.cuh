@@ -28,6 +28,7 @@ constexpr int CU_SLOTS = 13;
 // cu_load_ref): 4 x 37 KB for a CTU at +-64.  The 16-bit kernels keep two CTAs of 8 warps.
 constexpr int CU8_THREADS = 512;
 constexpr int CU8_WARPS = CU8_THREADS / 32;
+constexpr int CU_PX_BLOCKS = 16;             // windows up to 256 columns keep their per-column MV-cost terms in shared memory
 
 struct S8Bundle {             // 128 bytes
   int32_t org_off, win_off;   // byte offsets of the CU's top-left sample / of candidate (lt_x, lt_y) in the staged tiles
@@ -240,6 +241,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   extern __shared__ __align__(128) uint8_t s8_smem[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ S8Bundle s_bd[CU8_WARPS];
+  __shared__ __align__(16) uint32_t s_px[CU8_WARPS][CU_PX_BLOCKS * 16];   // per warp: lambda * bits of the x component of its CU's columns
 
   const S8Unit un = units[blockIdx.x];
   uint8_t* s_ref = s8_smem;
@@ -287,6 +289,15 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
     __syncwarp();
     reinterpret_cast<int32_t*>(&bd)[lane] = reinterpret_cast<const int32_t*>(&bundles[bslot])[lane];   // 32 ints
     __syncwarp();
+    // x part of the MV cost of every column of the CU's window, once per CU and warp instead of four times per tile;
+    // stored in the order the lanes read it: [block][lane & 3][k] = column block * 16 + (lane & 3) + 4 k
+    if (bd.n_blk <= CU_PX_BLOCKS) {
+      for (int i = lane; i < bd.n_blk * 16; i += 32) {
+        const int col = (i & ~15) + ((i >> 2) & 3) + 4 * (i & 3) - bd.xal;
+        s_px[warp][i] = bd.lambda * eg_bits(((bd.lt_x + col) << 2) - bd.pred_x);
+      }
+      __syncwarp();
+    }
   };
   constexpr int LK = (S == 8) ? 4 : 2;                // bits of the within-tile candidate index
   constexpr int TILE_LIMIT = 1 << (CU_LOCAL_BITS - LK);   // tiles a lane may see between two flushes
@@ -374,9 +385,15 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
     // the window take no part: their mk and ru are 0 and idx0 is KEY_NONE (MASK_BY_KEY), so the base is exactly KEY_NONE.
     uint32_t px[4], mk[4], idx0[4], ru[4];
     bool valid[4];
+    if (bd.n_blk <= CU_PX_BLOCKS) {
+      const uint4 v = *reinterpret_cast<const uint4*>(&s_px[warp][blk * 16 + sub * 4]);
+      px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) px[k] = bd.lambda * eg_bits(((bd.lt_x + cx0 + 4 * k) << 2) - bd.pred_x);
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      px[k] = bd.lambda * eg_bits(((bd.lt_x + cx0 + 4 * k) << 2) - bd.pred_x);
       valid[k] = (unsigned)(cx0 + 4 * k) < (unsigned)bd.nx;
       const bool on = valid[k] || !MASK_BY_KEY;
       mk[k] = on ? (1u << CU_LOCAL_BITS) : 0u;
