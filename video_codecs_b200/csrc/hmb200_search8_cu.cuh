@@ -470,7 +470,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
           OP[r][k] = r ? OP[OPREV[r]][k] : 0u;
         }
         if constexpr (T::PARITY) {
-#pragma unroll 2
+#pragma unroll 4
           for (int rr = 0; rr < T::G; rr += 2) {
             const int row = r * T::G + rr;
             uint32_t o[T::WW];
@@ -483,7 +483,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
             }
           }
         } else {
-#pragma unroll 2
+#pragma unroll 4
           for (int rr = 0; rr < T::G; rr++) {
             const int row = r * T::G + rr;
             uint32_t o[T::WW];
