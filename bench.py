@@ -47,6 +47,18 @@ METRIC = "Mpixel/s, full-search +-64 ME with quarter-pel SATD refinement, 1080p"
 INT_PEAK_FILE = os.path.join(ROOT, "profiles", "r01_microbench_int.json")
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line on the real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -244,7 +256,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -439,7 +451,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline and args.workload == "1080p":
             line["cpu_baseline"] = cpu_sample_single(args.cpu_ctus)
-        print(json.dumps(line), flush=True)
+        emit(line)
     prep.free()
     prep2.free()
     hm.shutdown()
@@ -463,6 +475,12 @@ def main():
     ap.add_argument("--search", default="full", choices=["full", "tz"], help="tz: xTZSearch (FastSearch=1) instead of the full search")
     args = ap.parse_args()
     select_workload(args.workload)
+    # stdout carries exactly ONE line, the JSON result: libraries that write banners to fd 1 (NCCL's version line, worker
+    # processes) are sent to stderr for the duration of the run; emit() writes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)
