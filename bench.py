@@ -369,7 +369,7 @@ def run_ours(args):
         for p in preps:
             p.fetch_wait()
 
-    e2e_steps = max(4, min(args.steps, 10))
+    e2e_steps = max(4, min(args.steps, 30))
     for k in range(2):
         e2e_step(k)
     e2e_drain()

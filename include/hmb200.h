@@ -155,7 +155,11 @@ int  hmb200_tile_column_range(int pic_w, int max_cu, int n_columns, int column, 
 int  hmb200_register_plane(const int16_t* host_origin, int stride, int width, int height,
                            int margin_x, int margin_y, int bit_depth, int kind, int poc);
 /* Same, from 8-bit samples without margins (planar YUV luma as read by TVideoIOYuv); the margins are synthesised on
- * the device exactly like extendPicBorder. */
+ * the device exactly like extendPicBorder.  A tightly packed frame in page-locked memory (hmb200_host_alloc) is uploaded
+ * on a separate stream and the call returns at once - the copy then runs behind the kernels of the frame pair before it;
+ * every consumer of the plane is ordered after it on the device, the source must stay untouched until hmb200_sync (or a
+ * blocking call that uses the plane) returns.  hmb200_release_plane is stream-ordered as well: the buffer is recycled
+ * behind its last reader, without a host synchronisation. */
 int  hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width, int height,
                               int margin_x, int margin_y, int kind, int poc);
 /* Direct ingest of one frame's luma from a planar YUV file image: TVideoIOYuv::read for COMPONENT_Y

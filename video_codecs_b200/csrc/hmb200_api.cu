@@ -31,7 +31,11 @@ struct Plane {
   int host_stride = 0;
   int kind = 0, poc = 0;
   size_t bytes = 0;
+  cudaEvent_t ev_ready = nullptr;     // uploaded on the upload stream: recorded behind the border extension, consumed by get_plane
+  cudaEvent_t ev_reuse = nullptr;     // the recycled buffer's last reader on the compute stream (taken from the pool entry)
 };
+
+struct PoolBuf { size_t bytes; void* base; cudaEvent_t ev_free; };   // ev_free: behind the last kernel that may read the buffer
 
 constexpr int N_SIDE = 4;
 
@@ -43,12 +47,15 @@ struct State {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};     // side streams for concurrent variant kernels
   cudaStream_t copy = nullptr;                                     // D2H of results behind the next frame pair's kernels (hmb200_fetch_results_async)
+  cudaStream_t up = nullptr;                                       // H2D + border extension of page-locked frames behind the current pair's kernels
+  void* upstage = nullptr; size_t upstage_bytes = 0;               // device staging of the upload stream (g.dstage belongs to the compute stream)
+  std::vector<cudaEvent_t> free_events;
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<Plane> planes;
   void* pinned = nullptr; size_t pinned_bytes = 0;
   void* dstage = nullptr; size_t dstage_bytes = 0;     // device staging for plane uploads / per-call blocks
   Plane pattern;                                       // 64x64 int16 pattern buffer for the 1:1 entries
-  std::vector<std::pair<size_t, void*> > pool;         // released plane buffers, recycled by size (no malloc/free per frame)
+  std::vector<PoolBuf> pool;                           // released plane buffers, recycled by size (no malloc/free per frame)
   uint64_t launches = 0;
   float last_total_ms = 0, last_search_ms = 0, last_frac_ms = 0;
 };
@@ -83,6 +90,14 @@ int ensure_dstage(size_t bytes) {
   return HMB200_OK;
 }
 
+cudaEvent_t take_event() {
+  if (!g.free_events.empty()) { cudaEvent_t e = g.free_events.back(); g.free_events.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  return e;
+}
+void give_event(cudaEvent_t e) { if (e) g.free_events.push_back(e); }
+
 int alloc_plane_slot() {
   for (size_t i = 0; i < g.planes.size(); i++) if (!g.planes[i].used) return (int)i;
   g.planes.emplace_back();
@@ -99,15 +114,19 @@ int make_plane(Plane& p, int width, int height, int mx, int my, int bit_depth) {
   p.bytes = (size_t)pitch_bytes * total_h;
   p.d.base = nullptr;
   for (size_t i = 0; i < g.pool.size(); i++)
-    if (g.pool[i].first == p.bytes) { p.d.base = g.pool[i].second; g.pool.erase(g.pool.begin() + i); break; }
+    if (g.pool[i].bytes == p.bytes) { p.d.base = g.pool[i].base; p.ev_reuse = g.pool[i].ev_free; g.pool.erase(g.pool.begin() + i); break; }
   if (!p.d.base) CUDA_TRY(cudaMalloc(&p.d.base, p.bytes));
   p.used = true;
   return HMB200_OK;
 }
 
+// Every consumer of a plane on the compute stream goes through here: a plane that was uploaded on the upload stream
+// becomes visible to the compute stream (and the side streams forked from it) by one event wait.
 Plane* get_plane(int id) {
   if (id < 0 || id >= (int)g.planes.size() || !g.planes[id].used) return nullptr;
-  return &g.planes[id];
+  Plane& p = g.planes[id];
+  if (p.ev_ready) { cudaStreamWaitEvent(g.stream, p.ev_ready, 0); give_event(p.ev_ready); p.ev_ready = nullptr; }
+  return &p;
 }
 
 // which registered plane does a host Pel* fall into?  (1:1 entries hand us raw pointers into TComPicYuv buffers)
@@ -194,6 +213,7 @@ int hmb200_init(int device) {
   for (auto& ev : g.ev) CUDA_TRY(cudaEventCreate(&ev));
   for (auto& st : g.side) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.up, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
   for (auto& ev : g.ev_join) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   int rc = search8_configure(&g_err);
@@ -215,8 +235,12 @@ void hmb200_shutdown(void) {
   cudaStreamSynchronize(g.stream);
   for (auto& p : g.planes) if (p.used && p.d.base) cudaFree(p.d.base);
   g.planes.clear();
-  for (auto& b : g.pool) cudaFree(b.second);
+  for (auto& b : g.pool) { cudaFree(b.base); if (b.ev_free) cudaEventDestroy(b.ev_free); }
   g.pool.clear();
+  for (auto& pl : g.planes) { if (pl.ev_ready) cudaEventDestroy(pl.ev_ready); if (pl.ev_reuse) cudaEventDestroy(pl.ev_reuse); pl.ev_ready = pl.ev_reuse = nullptr; }
+  for (auto e : g.free_events) cudaEventDestroy(e);
+  g.free_events.clear();
+  if (g.upstage) { cudaFree(g.upstage); g.upstage = nullptr; g.upstage_bytes = 0; }
   if (g.pattern.d.base) cudaFree(g.pattern.d.base);
   g.pattern = Plane();
   if (g.pinned) cudaFreeHost(g.pinned);
@@ -225,6 +249,7 @@ void hmb200_shutdown(void) {
   for (auto& ev : g.ev) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
   for (auto& st : g.side) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; }
   if (g.copy) { cudaStreamSynchronize(g.copy); cudaStreamDestroy(g.copy); g.copy = nullptr; }
+  if (g.up) { cudaStreamSynchronize(g.up); cudaStreamDestroy(g.up); g.up = nullptr; }
   if (g.ev_fork) { cudaEventDestroy(g.ev_fork); g.ev_fork = nullptr; }
   for (auto& ev : g.ev_join) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
   cudaStreamDestroy(g.stream); g.stream = nullptr;
@@ -239,7 +264,13 @@ void* hmb200_host_alloc(size_t bytes) {
 }
 void hmb200_host_free(void* p) { if (p) cudaFreeHost(p); }
 
-int hmb200_sync(void) { NEED_READY(); CUDA_TRY(cudaStreamSynchronize(g.stream)); return HMB200_OK; }
+int hmb200_sync(void) {
+  NEED_READY();
+  CUDA_TRY(cudaStreamSynchronize(g.up));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.copy));
+  return HMB200_OK;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // host-side window / job-list logic (no GPU)
@@ -385,10 +416,31 @@ int hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width,
   int rc = make_plane(p, width, height, margin_x, margin_y, 8);
   if (rc != HMB200_OK) return rc;
   size_t bytes = (size_t)width * height;
-  if ((rc = ensure_dstage(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
   cudaPointerAttributes attr;
   const bool user_pinned = stride == width && cudaPointerGetAttributes(&attr, host_samples) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
+  if (user_pinned) {
+    // page-locked, tightly packed frame: H2D + border extension on the upload stream, behind whatever the compute stream is
+    // doing; the source stays the caller's until the copy has run (hmb200_sync or any later fetch / blocking call orders it)
+    if (bytes > g.upstage_bytes) {
+      CUDA_TRY(cudaStreamSynchronize(g.up));
+      if (g.upstage) cudaFree(g.upstage);
+      g.upstage = nullptr; g.upstage_bytes = 0;
+      CUDA_TRY(cudaMalloc(&g.upstage, bytes));
+      g.upstage_bytes = bytes;
+    }
+    if (p.ev_reuse) { CUDA_TRY(cudaStreamWaitEvent(g.up, p.ev_reuse, 0)); give_event(p.ev_reuse); p.ev_reuse = nullptr; }
+    CUDA_TRY(cudaMemcpyAsync(g.upstage, host_samples, bytes, cudaMemcpyHostToDevice, g.up));
+    dim3 ugrid((width + 2 * margin_x + 255) / 256, height + 2 * margin_y);
+    k_pad_plane_u8<<<ugrid, 256, 0, g.up>>>(reinterpret_cast<const uint8_t*>(g.upstage), width,
+                                            reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, width, height, margin_x, margin_y);
+    g.launches++;
+    p.ev_ready = take_event();
+    CUDA_TRY(cudaEventRecord(p.ev_ready, g.up));
+    p.kind = kind; p.poc = poc;
+    return id;
+  }
+  if ((rc = ensure_dstage(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
   const uint8_t* src = host_samples;                      // page-locked, tightly packed frames go to the device without a staging copy
   if (!user_pinned) {
     if ((rc = ensure_pinned(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
@@ -465,13 +517,23 @@ int hmb200_read_plane(int plane_id, int16_t* dst_origin, int dst_stride) {
 }
 
 void hmb200_release_plane(int plane_id) {
-  Plane* p = get_plane(plane_id);
+  Plane* p = get_plane(plane_id);            // also orders a still pending upload of this plane before the compute stream's tail
   if (!p) return;
-  cudaStreamSynchronize(g.stream);
   if (p->d.base) {
-    if (g.pool.size() < 16) g.pool.push_back(std::make_pair(p->bytes, p->d.base));
-    else cudaFree(p->d.base);
+    if (g.pool.size() < 16) {
+      // no host synchronisation: the buffer goes back to the pool with an event behind the last kernel that may read it
+      // (side streams are joined into the compute stream before a run ends); whoever reuses it on the upload stream waits on it
+      cudaEvent_t ev = p->ev_reuse ? p->ev_reuse : take_event();
+      p->ev_reuse = nullptr;
+      cudaEventRecord(ev, g.stream);
+      g.pool.push_back(PoolBuf{p->bytes, p->d.base, ev});
+    } else {
+      cudaStreamSynchronize(g.up);
+      cudaStreamSynchronize(g.stream);
+      cudaFree(p->d.base);
+    }
   }
+  give_event(p->ev_reuse);
   *p = Plane();
 }
 
