@@ -2,7 +2,7 @@
 (64x64 .. 8x8 CUs as 2Nx2N, 8x8 CUs also as four 4x4: 341 blocks per CTU, 173 910 blocks), reference lines taken from
 the original picture's own neighbours, and the oracle (CPU, one core) on a sample.  Prints one JSON object.
 
-    python tools/measure_intra.py            (needs a B200; the oracle leg is test infrastructure, used as the checker)
+    python tests/measure_intra.py            (needs a B200; the oracle leg is test infrastructure, used as the checker)
 """
 import json
 import os
@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repo root
 sys.path.insert(0, ROOT)
 
 from video_codecs_b200 import HMB200, INTRA_BLOCK_DTYPE, synth  # noqa: E402
