@@ -45,6 +45,7 @@ N_FRAMES = 5                      # distinct synthetic frames per rank -> 4 fram
 WORKLOAD = "1080p_8bit_lowdelayP_fullsearch64_canonical593_fen1_hadme1_qpel"
 METRIC = "Mpixel/s, full-search +-64 ME with quarter-pel SATD refinement, 1080p"
 INT_PEAK_FILE = os.path.join(ROOT, "profiles", "r01_microbench_int.json")
+INT16_PEAK_FILE = os.path.join(ROOT, "profiles", "r01_microbench_int16.json")
 
 
 _REAL_STDOUT = None
@@ -112,8 +113,19 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def int_simd_peak():
-    """Measured VABSDIFF4.U8.ACC issue peak of this pool's B200 (tools/microbench_int.cu, profiles/): abs-diffs / s."""
+def int_simd_peak(bit_depth=8):
+    """Measured integer-SIMD SAD peak of this pool's B200, abs-diffs / s: the VABSDIFF4.U8.ACC issue rate for 8-bit
+    content (tools/microbench_int.cu), and for deeper content the register-only rate of the instruction sequence
+    k_search16_cu uses (VIADD.16x2 + VIADDMNMX.S16x2 + IDP.2A.LO per two samples; tools/microbench_int16.cu) --
+    SURVEY.md 8d asks for a separately calibrated peak there."""
+    if bit_depth > 8:
+        try:
+            d = json.load(open(INT16_PEAK_FILE))
+            seqs = max(v for k, v in d.items() if k.startswith("sad16x2_seq3"))
+            return seqs * 1e9 * 2.0, ("measured: profiles/r01_microbench_int16.json (register-only VIADD.16x2 + VIADDMNMX.S16x2 + "
+                                      "IDP.2A.LO loop, two abs-diffs per sequence)")
+        except Exception:
+            return 148 * 64 * (2.0 / 3.0) * 1.965e9, "fallback: 3 ALU-pipe instructions per 2 samples at 64 lanes/clk/SM x 148 SMs x 1.965 GHz"
     try:
         d = json.load(open(INT_PEAK_FILE))
         lane_ops = max(v for k, v in d.items() if k.startswith("alu_vabsdiff4_acc"))
@@ -403,7 +415,7 @@ def run_ours(args):
         units = 1 if tiles else world                       # tile columns: all ranks together process ONE picture per step
         value = units * mpix_step / (ms_per_step / 1e3)
         e2e_value = units * mpix_step / (e2e_ms / 1e3)
-        peak_abs, peak_src = int_simd_peak()
+        peak_abs, peak_src = int_simd_peak(BIT_DEPTH)
         search_s = srch / K / 1e3
         achieved = work["abs_diffs"] / search_s
         executed = work["abs_diffs_executed"] / search_s

@@ -83,14 +83,16 @@ def build(force=False):
     subprocess.check_call(["g++", "-o", BIN, os.path.join(OUT, "TEncSearch_shim.o"), os.path.join(OUT, "hm_shim.o")] + objs +
                           ["-L" + os.path.dirname(lib), "-lhmb200", "-Wl,-rpath,$ORIGIN/../../video_codecs_b200"])
     write_settings(os.path.join(OUT, "lowdelay_P_settings.cfg"))
+    write_settings(os.path.join(OUT, "randomaccess_main10_settings.cfg"), "encoder_randomaccess_main10.cfg")
     return BIN
 
 
-def write_settings(path):
-    """The encoder settings of BASELINE.json configs[0] (the values of the stock lowdelay-P main configuration), reduced
-    to bare `Key : value` lines so that the test can run where /root/reference does not exist."""
+def write_settings(path, cfg="encoder_lowdelay_P_main.cfg"):
+    """The encoder settings of BASELINE.json configs[0] (the values of the stock lowdelay-P main configuration) or
+    configs[3] (random-access Main10), reduced to bare `Key : value` lines so that the test can run where
+    /root/reference does not exist."""
     keep = []
-    for line in open(os.path.join(REF, "cfg", "encoder_lowdelay_P_main.cfg")):
+    for line in open(os.path.join(REF, "cfg", cfg)):
         line = line.split("#", 1)[0].strip()
         if ":" in line:
             k, v = line.split(":", 1)

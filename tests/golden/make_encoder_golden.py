@@ -78,9 +78,39 @@ def args_tz(cfg, yuv, w, h, frames, out_bin):
             "--SearchRange=64", "--SEIDecodedPictureHash=1", "-b", out_bin, "-o", ""]
 
 
+CFG_RA10 = "/root/reference/hm-16.5rc1/cfg/encoder_randomaccess_main10.cfg"
+RA10_FRAMES = 5
+
+
+def args_ra10(cfg, yuv, frames, out_bin):
+    """BASELINE.json configs[3]'s coding structure on a CPU-runnable picture: encoder_randomaccess_main10.cfg (B slices,
+    GOP 8, two lists, bi-prediction refinement at +-4 on a signed 16-bit pattern), 10-bit input and internal depth,
+    full search +-128."""
+    return ["-c", cfg, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", str(frames), "--InputBitDepth=10",
+            "--FastSearch=0", "--SearchRange=128", "--SEIDecodedPictureHash=1", "-b", out_bin, "-o", ""]
+
+
+def write_clip_ra10(path, frames):
+    synth.write_yuv420(path, [synth.luma_frame(W, H, t, seed=77, bit_depth=10) for t in range(frames)], 10)
+
+
+def golden_ra10():
+    yuv, binf = "/tmp/hmgold_ra10.yuv", "/tmp/hmgold_ra10.bin"
+    write_clip_ra10(yuv, RA10_FRAMES)
+    t0 = time.time()
+    p = subprocess.run([ENC] + args_ra10(CFG_RA10, yuv, RA10_FRAMES, binf), capture_output=True, text=True, check=True)
+    out = {"bitstream_md5": hashlib.md5(open(binf, "rb").read()).hexdigest(), "bitstream_bytes": os.path.getsize(binf),
+           "picture_md5": parse_md5_lines(p.stdout), "cpu_seconds": round(time.time() - t0, 1), "frames": RA10_FRAMES,
+           "yuv_md5": hashlib.md5(open(yuv, "rb").read()).hexdigest()}
+    json.dump(out, open(os.path.join(ROOT, "tests", "golden", "encoder_md5_ra10.json"), "w"), indent=1)
+    print(out)
+
+
 def main():
     if "--1080p" in sys.argv:
         return golden_1080p()
+    if "--ra10" in sys.argv:
+        return golden_ra10()
     if "--tz" in sys.argv:
         return golden_tz()
     out = {}

@@ -80,3 +80,29 @@ def test_encoder_bitstream_md5_tz_search(tmp_path, tag, mode):
     assert "integer searches" in p.stderr and " 0 integer searches" not in p.stderr
     assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
     assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]
+
+
+CFG_RA10 = os.path.join(ROOT, "integration", "_build", "randomaccess_main10_settings.cfg")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["verify", "gpu"])
+def test_encoder_bitstream_md5_randomaccess_main10(tmp_path, mode):
+    """BASELINE.json configs[3]'s coding structure (encoder_randomaccess_main10.cfg: B slices, GOP 8, two lists, 10-bit,
+    full search +-128) on a CPU-runnable picture: besides the uni-directional searches every bi-prediction refinement
+    (xPatternSearch at +-BipredSearchRange on the signed `2*org - other prediction` pattern, TEncSearch.cpp:3690-3706)
+    and the 10-bit quarter-pel SATD refinement go through libhmb200; bitstream and picture MD5s must equal the stock
+    encoder's (tests/golden/encoder_md5_ra10.json)."""
+    _need_binary()
+    if not os.path.exists(CFG_RA10):
+        pytest.skip("integration/_build/randomaccess_main10_settings.cfg not written (python integration/build_shim.py)")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "encoder_md5_ra10.json")))
+    yuv, binf = str(tmp_path / "clip.yuv"), str(tmp_path / "out.bin")
+    meg.write_clip_ra10(yuv, gold["frames"])
+    assert hashlib.md5(open(yuv, "rb").read()).hexdigest() == gold["yuv_md5"], "synthetic clip differs from the golden run's"
+    p = subprocess.run([BIN] + meg.args_ra10(CFG_RA10, yuv, gold["frames"], binf), capture_output=True, text=True,
+                       env=dict(os.environ, HMB200_SHIM=mode), timeout=3000)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "integer searches" in p.stderr and " 0 integer searches" not in p.stderr, "the GPU path was not exercised"
+    assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
+    assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]

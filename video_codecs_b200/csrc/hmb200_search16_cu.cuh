@@ -1,5 +1,6 @@
 // CU-fused integer full search for 16-bit planes (bit depths 9..14): the hmb200_search8_cu.cuh scheme with packed
-// 16x2 arithmetic.  There is no 16-bit SIMD SAD instruction on sm_100a; per 32-bit word (two samples) and candidate:
+// 16x2 arithmetic.  CUs of 16x16 and larger use the sum-of-minima form described further down; 8x8 CUs use the direct
+// form.  There is no 16-bit SIMD SAD instruction on sm_100a; per 32-bit word (two samples) and candidate:
 //     t = o + (-r)                VIADD.16x2          (o - r)
 //     m = max(r + (-o), t)        VIADDMNMX.S16x2     (|r - o| per half-word)
 //     acc += m.lo + m.hi          IDP.2A.LO.S16.S8    (32-bit accumulator, taps 1,1)
@@ -38,6 +39,93 @@ __device__ __forceinline__ void cu16_row(const uint8_t* rp8, const uint32_t (&o)
       const int i = j - k;
       if (i >= 0 && i < WW) acc[i / (WW / NC)][k] = absdiff16x2_acc(sw, nsw, o[i], no[i], acc[i / (WW / NC)][k]);
     }
+  }
+}
+
+// ---- sum-of-minima form (CUs of 16x16 and larger) ----------------------------------------------------------------
+//     |o - r| = o + r - 2 min(o, r)   =>   SAD(cell, candidate) = A(cell) + B(cell, candidate) - 2 M(cell, candidate)
+// M = sum of min(o, r): VIMNMX.U16x2 (ALU pipe) + IDP.2A.LO (FMA pipe) per two samples, no negated operands -- the
+// register-only rate of this pair is 2.1x that of the three-instruction |o - r| sequence (profiles/r01_microbench_int16.json).
+// B = box sum of the reference under the cell: one IDP.2A per shifted reference word and row into per-word column
+// accumulators W[j] (shared by the lane's four candidates and all cells of the chunk), folded once per strip.
+// A = sum of the original cell: once per CU and warp, kept in shared memory.
+// Samples are < 2^15 (bit depth <= 14), so unsigned minima and the signed 16-bit dot product agree.
+template <int WW>
+__device__ __forceinline__ void cu16_load_org_raw(const uint8_t* p, uint32_t (&o)[WW]) {
+#pragma unroll
+  for (int i = 0; i < WW / 4; i++) {
+    const uint4 v = reinterpret_cast<const uint4*>(p)[i];
+    o[4 * i] = v.x; o[4 * i + 1] = v.y; o[4 * i + 2] = v.z; o[4 * i + 3] = v.w;
+  }
+}
+
+// one reference row against WW original words: M[c][k] += sum of minima, W[j] += sum of the j-th shifted reference word
+template <int WW, int NC>
+__device__ __forceinline__ void cu16_row_min(const uint8_t* rp8, const uint32_t (&o)[WW], uint32_t sh, uint32_t (*M)[4],
+                                             uint32_t (&W)[WW + 3]) {
+  const uint32_t* rp = reinterpret_cast<const uint32_t*>(rp8);
+  uint32_t lo = rp[0];
+#pragma unroll
+  for (int j = 0; j < WW + 3; j++) {
+    const uint32_t hi = rp[j + 1];
+    const uint32_t sw = __funnelshift_r(lo, hi, sh);
+    lo = hi;
+    W[j] = (uint32_t)__dp2a_lo((int)sw, 0x0101, (int)W[j]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int i = j - k;
+      if (i >= 0 && i < WW) M[i / (WW / NC)][k] = (uint32_t)__dp2a_lo((int)__vminu2(sw, o[i]), 0x0101, (int)M[i / (WW / NC)][k]);
+    }
+  }
+}
+
+// M[c][k] <- B(c, k) - 2 M[c][k] with B(c, k) = W[c*cw + k] + ... + W[c*cw + k + cw - 1]
+template <int WW, int NC>
+__device__ __forceinline__ void cu16_fold(uint32_t (*M)[4], const uint32_t (&W)[WW + 3]) {
+  constexpr int CWD = WW / NC;
+  uint32_t P[WW + 4];
+  P[0] = 0;
+#pragma unroll
+  for (int j = 0; j < WW + 3; j++) P[j + 1] = P[j] + W[j];
+#pragma unroll
+  for (int c = 0; c < NC; c++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) M[c][k] = (P[c * CWD + k + CWD] - P[c * CWD + k]) - 2u * M[c][k];
+}
+
+// rows row0, row0 + rstep, ... (nrows of them) of one chunk of WW words: acc[c][k] <- (B - 2M) of those rows
+template <int WW, int NC>
+__device__ __forceinline__ void cu16_strip_min(const uint8_t* refp, int ref_pitch, const uint8_t* orgp, int org_pitch, int row0,
+                                               int rstep, int nrows, uint32_t sh, uint32_t (*acc)[4]) {
+  uint32_t W[WW + 3];
+#pragma unroll
+  for (int j = 0; j < WW + 3; j++) W[j] = 0;
+#pragma unroll 1
+  for (int i = 0, row = row0; i < nrows; i++, row += rstep) {
+    uint32_t o[WW];
+    cu16_load_org_raw<WW>(orgp + row * org_pitch, o);
+    cu16_row_min<WW, NC>(refp + row * ref_pitch, o, sh, acc, W);
+  }
+  cu16_fold<WW, NC>(acc, W);
+}
+
+// A sums of one CU for one warp: dst[r*4 + c] = cell (r, c) over the rows the search visits, dst[16 + r] = the odd rows
+// of strip r over the whole CU width (FEN partitions of height <= 8 read them, TComRdCost.cpp:566-571)
+template <int S, bool PARITY>
+__device__ __forceinline__ void cu16_org_sums(const uint8_t* orgp, int org_pitch, int lane, uint32_t* dst) {
+  constexpr int WW = S / 2, G = S / 4, CWD = WW / 4, RSTEP = PARITY ? 2 : 1;
+  if (lane < 20) {
+    const bool odd = lane >= 16;
+    const int r = odd ? lane - 16 : lane >> 2, c = odd ? 0 : lane & 3;
+    const int nw = odd ? WW : CWD;
+    uint32_t a = 0;
+    if (!odd || PARITY) {
+      for (int rr = 0; rr < G; rr += RSTEP) {
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(orgp + (r * G + rr + (odd ? 1 : 0)) * org_pitch) + c * CWD;
+        for (int j = 0; j < nw; j++) a = (uint32_t)__dp2a_lo((int)row[j], 0x0101, (int)a);
+      }
+    }
+    dst[lane] = a;
   }
 }
 
@@ -97,6 +185,7 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
   extern __shared__ __align__(128) uint8_t s8_smem[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ S8Bundle s_bd[S8_WARPS];
+  __shared__ uint32_t s_asum[S8_WARPS][20];
 
   const S8Unit un = units[blockIdx.x];
   uint8_t* s_ref = s8_smem;
@@ -125,6 +214,10 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
     __syncwarp();
     reinterpret_cast<int32_t*>(&bd)[lane] = reinterpret_cast<const int32_t*>(&bundles[bslot])[lane];
     __syncwarp();
+    if constexpr (S >= 16) {
+      cu16_org_sums<S, PARITY>(s_org + bd.org_off, un.org_pitch, lane, s_asum[warp]);
+      __syncwarp();
+    }
   };
   load_bundle();
   constexpr int LK = (S == 8) ? 4 : 2;
@@ -243,27 +336,32 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
           }
         constexpr int NCH = WW / CH;                // chunks per row
         constexpr int CPC = 4 / NCH;                // cell columns per chunk
+        constexpr int RSTEP = PARITY ? 2 : 1;
+        const uint32_t* asum = s_asum[warp];
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           const bool odd_here = ODD_ALL || (ODD_EDGE && (r == 0 || r == 3));
-          constexpr int RSTEP = PARITY ? 2 : 1;
-#pragma unroll 1
-          for (int rr = 0; rr < G; rr += RSTEP) {
-            const int row = r * G + rr;
+#pragma unroll
+          for (int ch = 0; ch < NCH; ch++)
+            cu16_strip_min<CH, CPC>(refp + ch * CH * 4, un.ref_pitch, orgp + ch * CH * 4, un.org_pitch, r * G, RSTEP, G / RSTEP, sh,
+                                    &E[r][ch * CPC]);
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const uint32_t a = asum[r * 4 + c];
+#pragma unroll
+            for (int k = 0; k < 4; k++) E[r][c][k] += a;
+          }
+          if (PARITY && odd_here) {
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) {
-              uint32_t o[CH], no[CH];
-              cu16_load_org<CH>(orgp + row * un.org_pitch + ch * CH * 4, o, no);
-              cu16_row<CH, CPC>(refp + row * un.ref_pitch + ch * CH * 4, o, no, sh, &E[r][ch * CPC]);
-            }
-            if (PARITY && odd_here) {
+              uint32_t part[1][4] = {{0, 0, 0, 0}};
+              cu16_strip_min<CH, 1>(refp + ch * CH * 4, un.ref_pitch, orgp + ch * CH * 4, un.org_pitch, r * G + 1, 2, G / 2, sh, part);
 #pragma unroll
-              for (int ch = 0; ch < NCH; ch++) {
-                uint32_t o[CH], no[CH];
-                cu16_load_org<CH>(orgp + (row + 1) * un.org_pitch + ch * CH * 4, o, no);
-                cu16_row<CH, 1>(refp + (row + 1) * un.ref_pitch + ch * CH * 4, o, no, sh, &O[r]);
-              }
+              for (int k = 0; k < 4; k++) O[r][k] += part[0][k];
             }
+            const uint32_t a = asum[16 + r];
+#pragma unroll
+            for (int k = 0; k < 4; k++) O[r][k] += a;
           }
         }
         if (cyl0 < bd.ny) {
