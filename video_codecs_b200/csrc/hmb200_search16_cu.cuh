@@ -1,11 +1,9 @@
 // CU-fused integer full search for 16-bit planes (bit depths 9..14): the hmb200_search8_cu.cuh scheme with packed
-// 16x2 arithmetic.  CUs of 16x16 and larger use the sum-of-minima form described further down; 8x8 CUs use the direct
-// form.  There is no 16-bit SIMD SAD instruction on sm_100a; per 32-bit word (two samples) and candidate:
-//     t = o + (-r)                VIADD.16x2          (o - r)
-//     m = max(r + (-o), t)        VIADDMNMX.S16x2     (|r - o| per half-word)
-//     acc += m.lo + m.hi          IDP.2A.LO.S16.S8    (32-bit accumulator, taps 1,1)
-// with the half-word negations of the original words (once per row) and of the byte-shifted reference words (once per
-// word, shared by the lane's four candidates) hoisted.  ~1.6 instructions per sample against 0.25 for 8-bit content.
+// 16x2 arithmetic.  There is no 16-bit SIMD SAD instruction on sm_100a; the direct form costs three instructions per
+// 32-bit word (two samples) and candidate -- VIADD.16x2 (o - r), VIADDMNMX.S16x2 (max(r - o, o - r)), IDP.2A.LO (sum of
+// the half-words) -- plus hoisted negations, two of the three on the ALU pipe (measured 15.9 T abs-diff/s register-only).
+// The kernels use the sum-of-minima form below instead: one ALU-pipe and one FMA-pipe instruction per word and
+// candidate (33.3 T abs-diff/s register-only, profiles/r01_microbench_int16.json).
 // Distortion precision: (sum << iSubShift) >> (bitDepth - 8)  (TComRdCost.cpp:505-517, DISTORTION_PRECISION_ADJUSTMENT).
 // Lane layout: a PAIR of lanes owns 8 candidate columns (lane parity = sample alignment inside the word, four candidates
 // two samples apart per lane), 16 pairs per warp-item.
@@ -16,33 +14,7 @@ namespace hmb200 {
 
 __host__ __device__ constexpr int cu16_ky(int S) { return S == 8 ? 2 : 1; }
 
-__device__ __forceinline__ uint32_t absdiff16x2_acc(uint32_t r, uint32_t nr, uint32_t o, uint32_t no, uint32_t acc) {
-  const uint32_t t = __vadd2(o, nr);
-  const uint32_t m = __viaddmax_s16x2(r, no, t);
-  return (uint32_t)__dp2a_lo((int)m, 0x0101, (int)acc);
-}
-
-// one reference row against WW original words (a chunk of the CU row); words of cell column c feed acc[c][k]
-template <int WW, int NC>
-__device__ __forceinline__ void cu16_row(const uint8_t* rp8, const uint32_t (&o)[WW], const uint32_t (&no)[WW], uint32_t sh,
-                                         uint32_t (*acc)[4]) {
-  const uint32_t* rp = reinterpret_cast<const uint32_t*>(rp8);
-  uint32_t lo = rp[0];
-#pragma unroll
-  for (int j = 0; j < WW + 3; j++) {
-    const uint32_t hi = rp[j + 1];
-    const uint32_t sw = __funnelshift_r(lo, hi, sh);
-    lo = hi;
-    const uint32_t nsw = __vneg2(sw);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int i = j - k;
-      if (i >= 0 && i < WW) acc[i / (WW / NC)][k] = absdiff16x2_acc(sw, nsw, o[i], no[i], acc[i / (WW / NC)][k]);
-    }
-  }
-}
-
-// ---- sum-of-minima form (CUs of 16x16 and larger) ----------------------------------------------------------------
+// ---- sum-of-minima form --------------------------------------------------------------------------------------------
 //     |o - r| = o + r - 2 min(o, r)   =>   SAD(cell, candidate) = A(cell) + B(cell, candidate) - 2 M(cell, candidate)
 // M = sum of min(o, r): VIMNMX.U16x2 (ALU pipe) + IDP.2A.LO (FMA pipe) per two samples, no negated operands -- the
 // register-only rate of this pair is 2.1x that of the three-instruction |o - r| sequence (profiles/r01_microbench_int16.json).
@@ -129,17 +101,6 @@ __device__ __forceinline__ void cu16_org_sums(const uint8_t* orgp, int org_pitch
   }
 }
 
-template <int WW>
-__device__ __forceinline__ void cu16_load_org(const uint8_t* p, uint32_t (&o)[WW], uint32_t (&no)[WW]) {
-#pragma unroll
-  for (int i = 0; i < WW / 4; i++) {
-    const uint4 v = reinterpret_cast<const uint4*>(p)[i];
-    o[4 * i] = v.x; o[4 * i + 1] = v.y; o[4 * i + 2] = v.z; o[4 * i + 3] = v.w;
-  }
-#pragma unroll
-  for (int i = 0; i < WW; i++) no[i] = __vneg2(o[i]);
-}
-
 // key of one PU: ((sum << ss) >> shr) scaled into the cost field
 __device__ __forceinline__ void cu16_min(uint32_t& best, uint32_t sum, int ss, int shr, uint32_t base) {
   best = min(best, (((sum << ss) >> shr) << CU_LOCAL_BITS) + base);
@@ -216,8 +177,17 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
     __syncwarp();
     if constexpr (S >= 16) {
       cu16_org_sums<S, PARITY>(s_org + bd.org_off, un.org_pitch, lane, s_asum[warp]);
-      __syncwarp();
+    } else if (lane < 4) {                              // 8x8 CU: four 4x4 quadrants
+      uint32_t a = 0;
+#pragma unroll
+      for (int rr = 0; rr < 4; rr++) {
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(s_org + bd.org_off + ((lane >> 1) * 4 + rr) * un.org_pitch) + (lane & 1) * 2;
+        a = (uint32_t)__dp2a_lo((int)row[0], 0x0101, (int)a);
+        a = (uint32_t)__dp2a_lo((int)row[1], 0x0101, (int)a);
+      }
+      s_asum[warp][lane] = a;
     }
+    __syncwarp();
   };
   load_bundle();
   constexpr int LK = (S == 8) ? 4 : 2;
@@ -271,18 +241,22 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
       for (int k = 0; k < 4; k++) px[k] = bd.lambda * eg_bits(((bd.lt_x + cxi0 + 2 * k) << 2) - bd.pred_x);
 
       if constexpr (S == 8) {
-        uint32_t o[8][4], no[8][4];
+        // sum-of-minima form with two candidate rows per lane: reference row r meets original row r - jy
+        uint32_t o[8][4];
 #pragma unroll
-        for (int r = 0; r < 8; r++) cu16_load_org<4>(orgp + r * un.org_pitch, o[r], no[r]);
-        uint32_t Q[KY][2][2][4];
+        for (int r = 0; r < 8; r++) cu16_load_org_raw<4>(orgp + r * un.org_pitch, o[r]);
+        uint32_t Q[KY][2][2][4], W[KY][2][7];
 #pragma unroll
         for (int a = 0; a < KY; a++)
 #pragma unroll
-          for (int b = 0; b < 2; b++)
+          for (int b = 0; b < 2; b++) {
+#pragma unroll
+            for (int j = 0; j < 7; j++) W[a][b][j] = 0;
 #pragma unroll
             for (int c = 0; c < 2; c++)
 #pragma unroll
               for (int k = 0; k < 4; k++) Q[a][b][c][k] = 0;
+          }
 #pragma unroll
         for (int r = 0; r < 8 + KY - 1; r++) {
           const uint32_t* rp = reinterpret_cast<const uint32_t*>(refp + r * un.ref_pitch);
@@ -292,19 +266,34 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
             const uint32_t hi = rp[j + 1];
             const uint32_t sw = __funnelshift_r(lo, hi, sh);
             lo = hi;
-            const uint32_t nsw = __vneg2(sw);
 #pragma unroll
             for (int jy = 0; jy < KY; jy++) {
               if (r - jy >= 0 && r - jy < 8) {
+                W[jy][(r - jy) >> 2][j] = (uint32_t)__dp2a_lo((int)sw, 0x0101, (int)W[jy][(r - jy) >> 2][j]);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                   const int i = j - k;
                   if (i >= 0 && i < 4)
-                    Q[jy][(r - jy) >> 2][i >> 1][k] = absdiff16x2_acc(sw, nsw, o[r - jy][i], no[r - jy][i], Q[jy][(r - jy) >> 2][i >> 1][k]);
+                    Q[jy][(r - jy) >> 2][i >> 1][k] =
+                        (uint32_t)__dp2a_lo((int)__vminu2(sw, o[r - jy][i]), 0x0101, (int)Q[jy][(r - jy) >> 2][i >> 1][k]);
                 }
               }
             }
           }
+        }
+        {
+          const uint32_t* asum = s_asum[warp];
+#pragma unroll
+          for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+              const uint32_t a = asum[b * 2 + c];
+#pragma unroll
+              for (int jy = 0; jy < KY; jy++)
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                  Q[jy][b][c][k] = a + W[jy][b][2 * c + k] + W[jy][b][2 * c + k + 1] - 2u * Q[jy][b][c][k];
+            }
         }
 #pragma unroll
         for (int jy = 0; jy < KY; jy++) {
