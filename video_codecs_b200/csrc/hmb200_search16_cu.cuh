@@ -66,17 +66,26 @@ __device__ __forceinline__ void cu16_fold(uint32_t (*M)[4], const uint32_t (&W)[
 }
 
 // rows row0, row0 + rstep, ... (nrows of them) of one chunk of WW words: acc[c][k] <- (B - 2M) of those rows
-template <int WW, int NC>
+template <int WW, int NC, int NROWS>
 __device__ __forceinline__ void cu16_strip_min(const uint8_t* refp, int ref_pitch, const uint8_t* orgp, int org_pitch, int row0,
-                                               int rstep, int nrows, uint32_t sh, uint32_t (*acc)[4]) {
+                                               int rstep, uint32_t sh, uint32_t (*acc)[4]) {
   uint32_t W[WW + 3];
 #pragma unroll
   for (int j = 0; j < WW + 3; j++) W[j] = 0;
+  if constexpr (NROWS <= 2) {                       // 16x16 CUs: two rows per strip and parity, straight-line code
+#pragma unroll
+    for (int i = 0; i < NROWS; i++) {
+      uint32_t o[WW];
+      cu16_load_org_raw<WW>(orgp + (row0 + i * rstep) * org_pitch, o);
+      cu16_row_min<WW, NC>(refp + (row0 + i * rstep) * ref_pitch, o, sh, acc, W);
+    }
+  } else {
 #pragma unroll 1
-  for (int i = 0, row = row0; i < nrows; i++, row += rstep) {
-    uint32_t o[WW];
-    cu16_load_org_raw<WW>(orgp + row * org_pitch, o);
-    cu16_row_min<WW, NC>(refp + row * ref_pitch, o, sh, acc, W);
+    for (int i = 0, row = row0; i < NROWS; i++, row += rstep) {
+      uint32_t o[WW];
+      cu16_load_org_raw<WW>(orgp + row * org_pitch, o);
+      cu16_row_min<WW, NC>(refp + row * ref_pitch, o, sh, acc, W);
+    }
   }
   cu16_fold<WW, NC>(acc, W);
 }
@@ -102,8 +111,9 @@ __device__ __forceinline__ void cu16_org_sums(const uint8_t* orgp, int org_pitch
 }
 
 // key of one PU: ((sum << ss) >> shr) scaled into the cost field
+// (16-bit planes have bit depth >= 9, so shr >= 1 >= ss and the two shifts are one: sums are below 2^31)
 __device__ __forceinline__ void cu16_min(uint32_t& best, uint32_t sum, int ss, int shr, uint32_t base) {
-  best = min(best, (((sum << ss) >> shr) << CU_LOCAL_BITS) + base);
+  best = min(best, ((sum >> (shr - ss)) << CU_LOCAL_BITS) + base);
 }
 
 template <int S, bool FEN>
@@ -332,8 +342,8 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
           const bool odd_here = ODD_ALL || (ODD_EDGE && (r == 0 || r == 3));
 #pragma unroll
           for (int ch = 0; ch < NCH; ch++)
-            cu16_strip_min<CH, CPC>(refp + ch * CH * 4, un.ref_pitch, orgp + ch * CH * 4, un.org_pitch, r * G, RSTEP, G / RSTEP, sh,
-                                    &E[r][ch * CPC]);
+            cu16_strip_min<CH, CPC, G / RSTEP>(refp + ch * CH * 4, un.ref_pitch, orgp + ch * CH * 4, un.org_pitch, r * G, RSTEP, sh,
+                                               &E[r][ch * CPC]);
 #pragma unroll
           for (int c = 0; c < 4; c++) {
             const uint32_t a = asum[r * 4 + c];
@@ -344,7 +354,7 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) {
               uint32_t part[1][4] = {{0, 0, 0, 0}};
-              cu16_strip_min<CH, 1>(refp + ch * CH * 4, un.ref_pitch, orgp + ch * CH * 4, un.org_pitch, r * G + 1, 2, G / 2, sh, part);
+              cu16_strip_min<CH, 1, G / 2>(refp + ch * CH * 4, un.ref_pitch, orgp + ch * CH * 4, un.org_pitch, r * G + 1, 2, sh, part);
 #pragma unroll
               for (int k = 0; k < 4; k++) O[r][k] += part[0][k];
             }
