@@ -115,17 +115,18 @@ class ClockSampler(threading.Thread):
 
 def int_simd_peak(bit_depth=8):
     """Measured integer-SIMD SAD peak of this pool's B200, abs-diffs / s: the VABSDIFF4.U8.ACC issue rate for 8-bit
-    content (tools/microbench_int.cu), and for deeper content the register-only rate of the instruction sequence
-    k_search16_cu uses (VIADD.16x2 + VIADDMNMX.S16x2 + IDP.2A.LO per two samples; tools/microbench_int16.cu) --
-    SURVEY.md 8d asks for a separately calibrated peak there."""
+    content (tools/microbench_int.cu), and for deeper content the register-only rate of the instruction pair
+    k_search16_cu uses (VIMNMX.U16x2 + IDP.2A.LO per two samples, the sum-of-minima form; tools/microbench_int16.cu) --
+    SURVEY.md 8d asks for a separately calibrated peak there.  (The direct three-instruction |o - r| sequence the
+    kernel used before peaks at 15.9 T abs-diff/s in the same file.)"""
     if bit_depth > 8:
         try:
             d = json.load(open(INT16_PEAK_FILE))
-            seqs = max(v for k, v in d.items() if k.startswith("sad16x2_seq3"))
-            return seqs * 1e9 * 2.0, ("measured: profiles/r01_microbench_int16.json (register-only VIADD.16x2 + VIADDMNMX.S16x2 + "
-                                      "IDP.2A.LO loop, two abs-diffs per sequence)")
+            seqs = max(v for k, v in d.items() if k.startswith("vimnmx16x2_plus_idp2a"))
+            return seqs * 1e9 * 2.0, ("measured: profiles/r01_microbench_int16.json (register-only VIMNMX.U16x2 + IDP.2A.LO loop, "
+                                      "two abs-diffs per pair)")
         except Exception:
-            return 148 * 64 * (2.0 / 3.0) * 1.965e9, "fallback: 3 ALU-pipe instructions per 2 samples at 64 lanes/clk/SM x 148 SMs x 1.965 GHz"
+            return 148 * 64 * 2.0 * 1.965e9, "fallback: one ALU-pipe + one FMA-pipe instruction per 2 samples at 64 lanes/clk/SM and pipe x 148 SMs x 1.965 GHz"
     try:
         d = json.load(open(INT_PEAK_FILE))
         lane_ops = max(v for k, v in d.items() if k.startswith("alu_vabsdiff4_acc"))
@@ -438,7 +439,7 @@ def run_ours(args):
             "cand_sad_per_s": world * work["cand_sads"] / (ms_per_step / 1e3),
             "sharding": "tile columns of one picture" if tiles else "independent frame pairs",
             "search_ms": srch / K, "frac_ms": frac / K, "wall_ms_per_step_incl_flush": wall_ms / K,
-            "roofline": {"bound": "int_alu", "kernel": ("k_search8_cu<S,FEN> (VABSDIFF4.U8.ACC)" if BIT_DEPTH == 8 else "k_search16_cu<S,FEN> (VIADD.16x2 / VIADDMNMX.S16x2 / IDP.2A)"), "achieved": achieved / 1e12,
+            "roofline": {"bound": "int_alu", "kernel": ("k_search8_cu<S,FEN> (VABSDIFF4.U8.ACC)" if BIT_DEPTH == 8 else "k_search16_cu<S,FEN> (sum of minima: VIMNMX.U16x2 + IDP.2A)"), "achieved": achieved / 1e12,
                          "peak": peak_abs / 1e12, "unit": "Tabsdiff/s", "frac": achieved / peak_abs, "traffic": traffic,
                          "traffic_kernel": traffic_kernel,
                          "peak_source": peak_src,

@@ -473,6 +473,44 @@ def test_me_canonical_ctus_10bit_vs_oracle(hm, fen, sr):
     assert results_equal(got, exp) == []
 
 
+@pytest.mark.parametrize("bd,fen", [(12, 1), (14, 1), (14, 0), (9, 1)])
+def test_me_deep_bit_depths_extreme_samples_vs_oracle(hm, bd, fen):
+    """The 16-bit kernels compute SAD = sum(org) + sum(ref) - 2 sum(min(org, ref)) with packed 16x2 minima and signed
+    16-bit dot products: exercise every bit depth class with samples at both ends of the range (0 and 2^bd - 1 in
+    large flat patches next to noise), where a sign or overflow slip in that form would show."""
+    W, H = 192, 128
+    rng = np.random.default_rng(1000 + bd)
+    top = (1 << bd) - 1
+    def frame():
+        f = rng.integers(0, top + 1, size=(H, W)).astype(np.uint16)
+        f[16:48, 20:90] = top
+        f[60:100, 100:170] = 0
+        f[70:90, 10:60] = top
+        return f
+    f0 = frame()
+    f1 = np.roll(f0, (3, -5), axis=(0, 1))
+    f1[::7, ::5] = rng.integers(0, top + 1, size=f1[::7, ::5].shape).astype(np.uint16)
+    cur, o0, stride = padded(f1, MARGIN)
+    ref, _, _ = padded(f0, MARGIN)
+    lam = int(np.floor(65536.0 * np.sqrt(0.4624 * 2 ** ((35 - 12) / 3.0))))
+    jobs = hm.build_canonical_jobs(W, H, 64, lam, pred=(-6, 9))
+    jobs = jobs[::3]
+    idc = hm.register_plane(cur, W, H, MARGIN, MARGIN, bd, kind=0)
+    idr = hm.register_plane(ref, W, H, MARGIN, MARGIN, bd, kind=1)
+    try:
+        prep = hm.prepare_jobs(jobs, flags_of(fen, 1, frac=False), bd)
+        prep.run(idc, idr)
+        got = prep.fetch()
+        work = prep.work()
+        prep.free()
+    finally:
+        hm.release_plane(idc)
+        hm.release_plane(idr)
+    assert work["pus_fused"] > 0.3 * len(jobs)          # the fused 16-bit kernels did run
+    exp, _ = Oracle(fen=fen, hadme=1).run_jobs((cur, o0, stride), (ref, o0, stride), jobs, bd, False)
+    assert results_equal(got, exp, ("mv_x", "mv_y", "sad")) == []
+
+
 def test_me_ctu_row_entry(hm):
     """hmb200_me_ctu_row: the per-CTU-row launch granularity of the in-encoder frontend; rows must agree with one
     whole-picture call, and a job outside the row is rejected."""

@@ -51,24 +51,35 @@ __device__ __forceinline__ void cu16_row_min(const uint8_t* rp8, const uint32_t 
   }
 }
 
-// M[c][k] <- B(c, k) - 2 M[c][k] with B(c, k) = W[c*cw + k] + ... + W[c*cw + k + cw - 1]
+// M[c][k] <- A[c] + B(c, k) - 2 M[c][k]  (= the SAD) with B(c, k) = W[c*cw + k] + ... + W[c*cw + k + cw - 1]
 template <int WW, int NC>
-__device__ __forceinline__ void cu16_fold(uint32_t (*M)[4], const uint32_t (&W)[WW + 3]) {
+__device__ __forceinline__ void cu16_fold(uint32_t (*M)[4], const uint32_t (&W)[WW + 3], const uint32_t* asum) {
   constexpr int CWD = WW / NC;
-  uint32_t P[WW + 4];
-  P[0] = 0;
+  if constexpr (CWD == 2) {                          // 16x16 CUs: one three-input add per cell and candidate
 #pragma unroll
-  for (int j = 0; j < WW + 3; j++) P[j + 1] = P[j] + W[j];
+    for (int c = 0; c < NC; c++) {
+      const uint32_t a = asum[c];
 #pragma unroll
-  for (int c = 0; c < NC; c++)
+      for (int k = 0; k < 4; k++) M[c][k] = (W[c * 2 + k] + W[c * 2 + k + 1] + a) - 2u * M[c][k];
+    }
+  } else {
+    uint32_t P[WW + 4];
+    P[0] = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) M[c][k] = (P[c * CWD + k + CWD] - P[c * CWD + k]) - 2u * M[c][k];
+    for (int j = 0; j < WW + 3; j++) P[j + 1] = P[j] + W[j];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const uint32_t a = asum[c];
+#pragma unroll
+      for (int k = 0; k < 4; k++) M[c][k] = (P[c * CWD + k + CWD] - P[c * CWD + k] + a) - 2u * M[c][k];
+    }
+  }
 }
 
-// rows row0, row0 + rstep, ... (nrows of them) of one chunk of WW words: acc[c][k] <- (B - 2M) of those rows
+// rows row0, row0 + rstep, ... (NROWS of them) of one chunk of WW words: acc[c][k] (zero on entry) <- SAD over those rows
 template <int WW, int NC, int NROWS>
 __device__ __forceinline__ void cu16_strip_min(const uint8_t* refp, int ref_pitch, const uint8_t* orgp, int org_pitch, int row0,
-                                               int rstep, uint32_t sh, uint32_t (*acc)[4]) {
+                                               int rstep, uint32_t sh, uint32_t (*acc)[4], const uint32_t* asum) {
   uint32_t W[WW + 3];
 #pragma unroll
   for (int j = 0; j < WW + 3; j++) W[j] = 0;
@@ -87,7 +98,7 @@ __device__ __forceinline__ void cu16_strip_min(const uint8_t* refp, int ref_pitc
       cu16_row_min<WW, NC>(refp + row * ref_pitch, o, sh, acc, W);
     }
   }
-  cu16_fold<WW, NC>(acc, W);
+  cu16_fold<WW, NC>(acc, W, asum);
 }
 
 // A sums of one CU for one warp: dst[r*4 + c] = cell (r, c) over the rows the search visits, dst[16 + r] = the odd rows
@@ -343,24 +354,10 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
 #pragma unroll
           for (int ch = 0; ch < NCH; ch++)
             cu16_strip_min<CH, CPC, G / RSTEP>(refp + ch * CH * 4, un.ref_pitch, orgp + ch * CH * 4, un.org_pitch, r * G, RSTEP, sh,
-                                               &E[r][ch * CPC]);
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            const uint32_t a = asum[r * 4 + c];
-#pragma unroll
-            for (int k = 0; k < 4; k++) E[r][c][k] += a;
-          }
+                                               &E[r][ch * CPC], asum + r * 4 + ch * CPC);
           if (PARITY && odd_here) {
-#pragma unroll
-            for (int ch = 0; ch < NCH; ch++) {
-              uint32_t part[1][4] = {{0, 0, 0, 0}};
-              cu16_strip_min<CH, 1, G / 2>(refp + ch * CH * 4, un.ref_pitch, orgp + ch * CH * 4, un.org_pitch, r * G + 1, 2, sh, part);
-#pragma unroll
-              for (int k = 0; k < 4; k++) O[r][k] += part[0][k];
-            }
-            const uint32_t a = asum[16 + r];
-#pragma unroll
-            for (int k = 0; k < 4; k++) O[r][k] += a;
+            static_assert(!PARITY || S == 64 || NCH == 1, "odd rows: one chunk per row");
+            cu16_strip_min<CH, 1, G / 2>(refp, un.ref_pitch, orgp, un.org_pitch, r * G + 1, 2, sh, &O[r], asum + 16 + r);
           }
         }
         if (cyl0 < bd.ny) {
