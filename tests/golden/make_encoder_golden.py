@@ -82,27 +82,32 @@ CFG_RA10 = "/root/reference/hm-16.5rc1/cfg/encoder_randomaccess_main10.cfg"
 RA10_FRAMES = 5
 
 
-def args_ra10(cfg, yuv, frames, out_bin):
+def args_ra10(cfg, yuv, frames, out_bin, fast_search=0):
     """BASELINE.json configs[3]'s coding structure on a CPU-runnable picture: encoder_randomaccess_main10.cfg (B slices,
     GOP 8, two lists, bi-prediction refinement at +-4 on a signed 16-bit pattern), 10-bit input and internal depth,
-    full search +-128."""
+    full search +-128 (fast_search=1: the configuration's own TZ search instead)."""
     return ["-c", cfg, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", str(frames), "--InputBitDepth=10",
-            "--FastSearch=0", "--SearchRange=128", "--SEIDecodedPictureHash=1", "-b", out_bin, "-o", ""]
+            f"--FastSearch={fast_search}", "--SearchRange=128", "--SEIDecodedPictureHash=1", "-b", out_bin, "-o", ""]
 
 
 def write_clip_ra10(path, frames):
     synth.write_yuv420(path, [synth.luma_frame(W, H, t, seed=77, bit_depth=10) for t in range(frames)], 10)
 
 
-def golden_ra10():
+RA10_TZ_FRAMES = 9          # one whole GOP of 8 behind the I picture
+
+
+def golden_ra10(fast_search=0):
+    frames = RA10_TZ_FRAMES if fast_search else RA10_FRAMES
     yuv, binf = "/tmp/hmgold_ra10.yuv", "/tmp/hmgold_ra10.bin"
-    write_clip_ra10(yuv, RA10_FRAMES)
+    write_clip_ra10(yuv, frames)
     t0 = time.time()
-    p = subprocess.run([ENC] + args_ra10(CFG_RA10, yuv, RA10_FRAMES, binf), capture_output=True, text=True, check=True)
+    p = subprocess.run([ENC] + args_ra10(CFG_RA10, yuv, frames, binf, fast_search), capture_output=True, text=True, check=True)
     out = {"bitstream_md5": hashlib.md5(open(binf, "rb").read()).hexdigest(), "bitstream_bytes": os.path.getsize(binf),
-           "picture_md5": parse_md5_lines(p.stdout), "cpu_seconds": round(time.time() - t0, 1), "frames": RA10_FRAMES,
+           "picture_md5": parse_md5_lines(p.stdout), "cpu_seconds": round(time.time() - t0, 1), "frames": frames,
            "yuv_md5": hashlib.md5(open(yuv, "rb").read()).hexdigest()}
-    json.dump(out, open(os.path.join(ROOT, "tests", "golden", "encoder_md5_ra10.json"), "w"), indent=1)
+    name = "encoder_md5_ra10_tz.json" if fast_search else "encoder_md5_ra10.json"
+    json.dump(out, open(os.path.join(ROOT, "tests", "golden", name), "w"), indent=1)
     print(out)
 
 
@@ -111,6 +116,8 @@ def main():
         return golden_1080p()
     if "--ra10" in sys.argv:
         return golden_ra10()
+    if "--ra10-tz" in sys.argv:
+        return golden_ra10(fast_search=1)
     if "--tz" in sys.argv:
         return golden_tz()
     out = {}

@@ -122,3 +122,24 @@ def test_encoder_randomaccess_main10_verify_mode_prefix(tmp_path):
     assert p.returncode == 0, p.stderr[-2000:]
     assert "integer searches" in p.stderr and " 0 integer searches" not in p.stderr, "the GPU path was not exercised"
     assert len(meg.parse_md5_lines(p.stdout)) == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["verify", "gpu"])
+def test_encoder_bitstream_md5_randomaccess_main10_tz(tmp_path, mode):
+    """encoder_randomaccess_main10.cfg with its own FastSearch = 1 over one whole GOP (I + 8 B pictures, 10-bit): the TZ
+    search on 16-bit planes, every bi-prediction refinement search and the 10-bit quarter-pel refinement run through
+    libhmb200 (verify: each call also checked against the reference body); md5s from the stock encoder."""
+    _need_binary()
+    if not os.path.exists(CFG_RA10):
+        pytest.skip("integration/_build/randomaccess_main10_settings.cfg not written (python integration/build_shim.py)")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "encoder_md5_ra10_tz.json")))
+    yuv, binf = str(tmp_path / "clip.yuv"), str(tmp_path / "out.bin")
+    meg.write_clip_ra10(yuv, gold["frames"])
+    assert hashlib.md5(open(yuv, "rb").read()).hexdigest() == gold["yuv_md5"], "synthetic clip differs from the golden run's"
+    p = subprocess.run([BIN] + meg.args_ra10(CFG_RA10, yuv, gold["frames"], binf, fast_search=1), capture_output=True, text=True,
+                       env=dict(os.environ, HMB200_SHIM=mode), timeout=3000)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "integer searches" in p.stderr and " 0 integer searches" not in p.stderr, "the GPU path was not exercised"
+    assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
+    assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]
