@@ -135,17 +135,23 @@ def int_simd_peak(bit_depth=8):
         return 148 * 64 * 4 * 1.965e9, "fallback: 64 lanes/clk/SM x 4 bytes x 148 SMs x 1.965 GHz"
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant search kernel, from the committed ncu
-    --set full capture of this round (profiles/r01_ncu_full_final.csv); None when the file is absent."""
+def ncu_traffic(workload="1080p"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant (longest) search kernel, from the committed
+    ncu --set full capture of this round (profiles/r01_ncu_full_final.csv for the 8-bit kernels, r01_ncu_full_2160p10.csv
+    for the 16-bit ones); None when the file is absent or the workload has no capture."""
     import csv
+    import math
+    src = {"1080p": ("r01_ncu_full_final.csv", "k_search8_cu"), "2160p10": ("r01_ncu_full_2160p10.csv", "k_search16_cu")}.get(workload)
+    if src is None:
+        return None, None
     try:
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01_ncu_full_final.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", src[0]))))
         hdr, units = rows[0], rows[1]
         ki, ti = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
         ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        best = max((r for r in rows[2:] if "k_search8_cu" in r[ki]), key=lambda r: float(r[ti]))
+        ok = [r for r in rows[2:] if src[1] in r[ki] and not math.isnan(float(r[ri])) and not math.isnan(float(r[wi]))]
+        best = max(ok, key=lambda r: float(r[ti]))
         return int(float(best[ri]) * scale.get(units[ri], 1.0) + float(best[wi]) * scale.get(units[wi], 1.0)), best[ki].split("(")[0]
     except Exception:
         return None, None
@@ -421,7 +427,7 @@ def run_ours(args):
         achieved = work["abs_diffs"] / search_s
         executed = work["abs_diffs_executed"] / search_s
         hbm, hbm_src = hbm_peak()
-        traffic, traffic_kernel = ncu_traffic() if args.workload == "1080p" else (None, None)
+        traffic, traffic_kernel = ncu_traffic(args.workload)
         # refinement: integer multiply-add model per PU pixel: 17 SATD candidates x (separable 8-tap
         # interpolation 16 MAC + Hadamard ~8 add/sub/abs) ~ 400 integer ops per pixel of every PU
         pu_pixels = float(np.sum(jobs["w"].astype(np.int64) * jobs["h"].astype(np.int64)))
