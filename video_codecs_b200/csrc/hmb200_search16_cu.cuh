@@ -6,7 +6,10 @@
 // candidate (33.3 T abs-diff/s register-only, profiles/r01_microbench_int16.json).
 // Distortion precision: (sum << iSubShift) >> (bitDepth - 8)  (TComRdCost.cpp:505-517, DISTORTION_PRECISION_ADJUSTMENT).
 // Lane layout: a PAIR of lanes owns 8 candidate columns (lane parity = sample alignment inside the word, four candidates
-// two samples apart per lane), 16 pairs per warp-item.
+// two samples apart per lane), 16 pairs per warp-item.  The window is kept twice in shared memory, as staged and shifted
+// by one sample (built by the CTA after the bulk copies land), in the kernels for CUs up to 16x16, so that both lanes of a
+// pair read aligned words; the windows of 32x32 and 64x64 CUs at +-128 would leave too few candidate rows per unit
+// that way and keep one copy and a funnel shift per word.
 #pragma once
 #include "hmb200_search8_cu.cuh"
 
@@ -31,17 +34,24 @@ __device__ __forceinline__ void cu16_load_org_raw(const uint8_t* p, uint32_t (&o
   }
 }
 
-// one reference row against WW original words: M[c][k] += sum of minima, W[j] += sum of the j-th shifted reference word
-template <int WW, int NC>
+// one reference row against WW original words: M[c][k] += sum of minima, W[j] += sum of the j-th reference word.
+// SHIFT: rp8 is word-aligned and the lane's words start `sh` bits in (one funnel shift per word); otherwise rp8 points
+// into the window copy of the lane's sample phase and the words are read as they are.
+template <int WW, int NC, bool SHIFT>
 __device__ __forceinline__ void cu16_row_min(const uint8_t* rp8, const uint32_t (&o)[WW], uint32_t sh, uint32_t (*M)[4],
                                              uint32_t (&W)[WW + 3]) {
   const uint32_t* rp = reinterpret_cast<const uint32_t*>(rp8);
-  uint32_t lo = rp[0];
+  uint32_t lo = SHIFT ? rp[0] : 0u;
 #pragma unroll
   for (int j = 0; j < WW + 3; j++) {
-    const uint32_t hi = rp[j + 1];
-    const uint32_t sw = __funnelshift_r(lo, hi, sh);
-    lo = hi;
+    uint32_t sw;
+    if constexpr (SHIFT) {
+      const uint32_t hi = rp[j + 1];
+      sw = __funnelshift_r(lo, hi, sh);
+      lo = hi;
+    } else {
+      sw = rp[j];
+    }
     W[j] = (uint32_t)__dp2a_lo((int)sw, 0x0101, (int)W[j]);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -77,7 +87,7 @@ __device__ __forceinline__ void cu16_fold(uint32_t (*M)[4], const uint32_t (&W)[
 }
 
 // rows row0, row0 + rstep, ... (NROWS of them) of one chunk of WW words: acc[c][k] (zero on entry) <- SAD over those rows
-template <int WW, int NC, int NROWS>
+template <int WW, int NC, int NROWS, bool SHIFT>
 __device__ __forceinline__ void cu16_strip_min(const uint8_t* refp, int ref_pitch, const uint8_t* orgp, int org_pitch, int row0,
                                                int rstep, uint32_t sh, uint32_t (*acc)[4], const uint32_t* asum) {
   uint32_t W[WW + 3];
@@ -88,14 +98,14 @@ __device__ __forceinline__ void cu16_strip_min(const uint8_t* refp, int ref_pitc
     for (int i = 0; i < NROWS; i++) {
       uint32_t o[WW];
       cu16_load_org_raw<WW>(orgp + (row0 + i * rstep) * org_pitch, o);
-      cu16_row_min<WW, NC>(refp + (row0 + i * rstep) * ref_pitch, o, sh, acc, W);
+      cu16_row_min<WW, NC, SHIFT>(refp + (row0 + i * rstep) * ref_pitch, o, sh, acc, W);
     }
   } else {
 #pragma unroll 1
     for (int i = 0, row = row0; i < NROWS; i++, row += rstep) {
       uint32_t o[WW];
       cu16_load_org_raw<WW>(orgp + row * org_pitch, o);
-      cu16_row_min<WW, NC>(refp + row * ref_pitch, o, sh, acc, W);
+      cu16_row_min<WW, NC, SHIFT>(refp + row * ref_pitch, o, sh, acc, W);
     }
   }
   cu16_fold<WW, NC>(acc, W, asum);
@@ -164,6 +174,7 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
   constexpr int G = S / 4;                             // rows per strip (S >= 16)
   constexpr int CH = WW > 16 ? 16 : WW;                // words per row chunk (keeps the original row in <= 32 registers)
   constexpr bool PARITY = FEN && S >= 16, ODD_ALL = PARITY && S == 16, ODD_EDGE = PARITY && S == 32;
+  constexpr bool TWO = S <= 16;                        // two window copies (host: cu16_two_phase)
   extern __shared__ __align__(128) uint8_t s8_smem[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ S8Bundle s_bd[S8_WARPS];
@@ -189,6 +200,14 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
       if (r >= 0) bulk_g2s(s_org + r * un.org_pitch, gorg + (size_t)r * cur_plane.pitch * 2, (uint32_t)un.org_pitch, &s_bar);
   }
   mbar_wait(&s_bar, 0);
+  if constexpr (TWO) {
+    // second copy of the window, one sample to the left: word w = samples (2w + 1, 2w + 2)
+    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(s_ref);
+    uint32_t* p1 = reinterpret_cast<uint32_t*>(s_ref + un.copy_stride);
+    const int nw = (un.ref_pitch * un.ref_rows) >> 2;
+    for (int w = threadIdx.x; w < nw; w += S8_THREADS) p1[w] = __funnelshift_r(p0[w], p0[w + 1], 16);
+    __syncthreads();
+  }
 
   int bslot = un.job_first;
   S8Bundle& bd = s_bd[warp];
@@ -253,8 +272,8 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
       const int cyl0 = g * KY;                                            // candidate row inside this (row-split) bundle
       const int cxi0 = min(blk * 8, bd.nx - 8) + (lane & 1);              // the last block overlaps its neighbour
       const int off = bd.win_off + cyl0 * un.ref_pitch + cxi0 * 2;        // bytes
-      const uint8_t* refp = s_ref + (off & ~3);
-      const uint32_t sh = (uint32_t)(off & 3) * 8u;
+      const uint8_t* refp = s_ref + ((TWO && (off & 2)) ? un.copy_stride : 0) + (off & ~3);
+      const uint32_t sh = (uint32_t)(off & 3) * 8u;      // used by the single-copy kernels only
       const uint8_t* orgp = s_org + bd.org_off;
       const int shr = bd.shr;
       uint32_t px[4];
@@ -281,12 +300,9 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
 #pragma unroll
         for (int r = 0; r < 8 + KY - 1; r++) {
           const uint32_t* rp = reinterpret_cast<const uint32_t*>(refp + r * un.ref_pitch);
-          uint32_t lo = rp[0];
 #pragma unroll
           for (int j = 0; j < 4 + 3; j++) {
-            const uint32_t hi = rp[j + 1];
-            const uint32_t sw = __funnelshift_r(lo, hi, sh);
-            lo = hi;
+            const uint32_t sw = rp[j];
 #pragma unroll
             for (int jy = 0; jy < KY; jy++) {
               if (r - jy >= 0 && r - jy < 8) {
@@ -353,11 +369,11 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
           const bool odd_here = ODD_ALL || (ODD_EDGE && (r == 0 || r == 3));
 #pragma unroll
           for (int ch = 0; ch < NCH; ch++)
-            cu16_strip_min<CH, CPC, G / RSTEP>(refp + ch * CH * 4, un.ref_pitch, orgp + ch * CH * 4, un.org_pitch, r * G, RSTEP, sh,
-                                               &E[r][ch * CPC], asum + r * 4 + ch * CPC);
+            cu16_strip_min<CH, CPC, G / RSTEP, !TWO>(refp + ch * CH * 4, un.ref_pitch, orgp + ch * CH * 4, un.org_pitch, r * G, RSTEP, sh,
+                                                     &E[r][ch * CPC], asum + r * 4 + ch * CPC);
           if (PARITY && odd_here) {
             static_assert(!PARITY || S == 64 || NCH == 1, "odd rows: one chunk per row");
-            cu16_strip_min<CH, 1, G / 2>(refp, un.ref_pitch, orgp, un.org_pitch, r * G + 1, 2, sh, &O[r], asum + 16 + r);
+            cu16_strip_min<CH, 1, G / 2, !TWO>(refp, un.ref_pitch, orgp, un.org_pitch, r * G + 1, 2, sh, &O[r], asum + 16 + r);
           }
         }
         if (cyl0 < bd.ny) {

@@ -574,8 +574,21 @@ inline CuGeom cu_geom(int bps) { return bps == 1 ? CuGeom{1, 16, 8, CU8_WARPS, S
 // copy_stride = 32 mod 128 so that the four lanes of a quad (one copy each) and the next quad (16 bytes further) hit
 // disjoint banks; a few slack rows behind the window for masked candidates; then the original tile.
 constexpr int CU8_SLACK_ROWS = 4;
-inline int cu_smem_need(const S8Box& rb, const S8Box& ob, int* org_off, int* copy_stride, int bps) {
-  if (bps != 1) { if (copy_stride) *copy_stride = 0; return s8_smem_need(rb, ob, org_off, bps); }
+// 16-bit planes, CUs up to 16x16 (cu16_two_phase): the staged window plus a second copy shifted by one sample.
+inline bool cu16_two_phase(int S) { return S <= 16; }
+inline int cu_smem_need(const S8Box& rb, const S8Box& ob, int* org_off, int* copy_stride, int bps, bool two_phase = false) {
+  if (bps != 1 && !two_phase) { if (copy_stride) *copy_stride = 0; return s8_smem_need(rb, ob, org_off, bps); }
+  if (bps != 1) {
+    // hmb200_search16_cu.cuh: lanes whose candidates start at an odd sample read aligned words from the second copy.
+    // Its offset is 8 bytes past a multiple of 128 so that the two lanes of a pair land in different shared-memory banks.
+    const int rp = (s8_ce(rb.x1) - s8_fl(rb.x0)) * bps, rr = rb.y1 - rb.y0 + S8_SLACK_ROWS;
+    const int op = (s8_ce(ob.x1) - s8_fl(ob.x0)) * bps, orr = ob.y1 - ob.y0;
+    const int cs = (((rp * rr + 16) + 127) & ~127) + 8;
+    const int ro = (2 * cs + 127) & ~127;
+    if (copy_stride) *copy_stride = cs;
+    if (org_off) *org_off = ro;
+    return ro + op * orr + 16;
+  }
   const int rp = s8_ce(rb.x1) - s8_fl(rb.x0), rr = rb.y1 - rb.y0 + CU8_SLACK_ROWS;
   const int op = s8_ce(ob.x1) - s8_fl(ob.x0), orr = ob.y1 - ob.y0;
   const int cs = ((rp * rr + 16 + 127) & ~127) + 32;
@@ -604,7 +617,8 @@ inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, int bps, st
     const int cx = t.org_x - t.org_x % S, cy = t.org_y - t.org_y % S;
     // even a one-row-group slice of the window must fit in shared memory, and the per-lane local candidate index of
     // a slice that fills it must fit CU_LOCAL_BITS (see cu_min)
-    if (cu_smem_need(S8Box{cx + t.lt_x, cy + t.lt_y, cx + t.rb_x + S, cy + t.lt_y + G.ky(S) - 1 + S}, S8Box{cx, cy, cx + S, cy + S}, nullptr, nullptr, bps) > S8_SMEM_MAX) continue;
+    if (cu_smem_need(S8Box{cx + t.lt_x, cy + t.lt_y, cx + t.rb_x + S, cy + t.lt_y + G.ky(S) - 1 + S}, S8Box{cx, cy, cx + S, cy + S}, nullptr, nullptr, bps,
+                     bps != 1 && cu16_two_phase(S)) > S8_SMEM_MAX) continue;
     {
       const int n_blk = (nx + (bps == 1 ? 15 : 0) + G.blkw - 1) / G.blkw, nrg = (ny + G.ky(S) - 1) / G.ky(S);   // worst alignment
       const int n_items = (n_blk * nrg + G.groups - 1) / G.groups;
@@ -649,7 +663,7 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
   const CuGeom GM = cu_geom(bps);
   out->bps = bps;
   // entity = a bundle, or a horizontal slice of its window when the whole window does not let two CTAs share an SM
-  struct Ent { int b, cy_first, ny; S8Box rb, ob; };
+  struct Ent { int b, cy_first, ny; S8Box rb, ob; bool two; };
   std::vector<Ent> ents;
   auto any_task = [&](const CuBundleHost& b) -> const SearchTask& {
     for (int s = 0; s < CU_SLOTS; s++) if (b.slot_task[s] >= 0) return tasks[b.slot_task[s]];
@@ -661,34 +675,37 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     const int ny = t.rb_y - t.lt_y + 1, ky = GM.ky(b.S);
     const S8Box ob{b.cu_x, b.cu_y, b.cu_x + b.S, b.cu_y + b.S};
     auto rbox_of = [&](int r0, int n) { return S8Box{b.cu_x + t.lt_x, b.cu_y + t.lt_y + r0, b.cu_x + t.rb_x + b.S, b.cu_y + t.lt_y + r0 + n - 1 + b.S}; };
+    const bool two = bps != 1 && cu16_two_phase(b.S);
     int parts = 1, rows = ny;
-    while (cu_smem_need(rbox_of(0, rows), ob, nullptr, nullptr, bps) > GM.smem_group && rows > ky) {
+    while (cu_smem_need(rbox_of(0, rows), ob, nullptr, nullptr, bps, two) > GM.smem_group && rows > ky) {
       parts++;
       rows = (((ny + parts - 1) / parts + ky - 1) / ky) * ky;
     }
     for (int r0 = 0; r0 < ny; r0 += rows) {
       const int n = std::min(rows, ny - r0);
-      ents.push_back(Ent{(int)i, r0, n, rbox_of(r0, n), ob});
+      ents.push_back(Ent{(int)i, r0, n, rbox_of(r0, n), ob, two});
     }
   }
   std::stable_sort(ents.begin(), ents.end(), [&](const Ent& a, const Ent& b) {
     const int ka = a.ob.y0 >> 6, kb = b.ob.y0 >> 6;
     if (ka != kb) return ka < kb;
-    return (a.ob.x0 >> 6) < (b.ob.x0 >> 6);
+    if ((a.ob.x0 >> 6) != (b.ob.x0 >> 6)) return (a.ob.x0 >> 6) < (b.ob.x0 >> 6);
+    return a.two < b.two;                                  // groups hold one shared-memory layout
   });
-  struct Group { int first, count; S8Box rb, ob; };
+  struct Group { int first, count; S8Box rb, ob; bool two; };
   std::vector<Group> groups;
   for (size_t p = 0; p < ents.size(); p++) {
     if (!groups.empty()) {
       Group& g = groups.back();
       const S8Box nr = s8_union(g.rb, ents[p].rb), no = s8_union(g.ob, ents[p].ob);
-      if (g.count < 4096 && no.x1 - no.x0 <= 128 && no.y1 - no.y0 <= 128 && cu_smem_need(nr, no, nullptr, nullptr, bps) <= GM.smem_group) {
+      if (g.count < 4096 && g.two == ents[p].two && no.x1 - no.x0 <= 128 && no.y1 - no.y0 <= 128 &&
+          cu_smem_need(nr, no, nullptr, nullptr, bps, g.two) <= GM.smem_group) {
         g.rb = nr; g.ob = no; g.count++;
         continue;
       }
     }
-    if (cu_smem_need(ents[p].rb, ents[p].ob, nullptr, nullptr, bps) > S8_SMEM_MAX) { if (err) *err = "cu_build_schedule: window too large"; return false; }
-    groups.push_back(Group{(int)p, 1, ents[p].rb, ents[p].ob});
+    if (cu_smem_need(ents[p].rb, ents[p].ob, nullptr, nullptr, bps, ents[p].two) > S8_SMEM_MAX) { if (err) *err = "cu_build_schedule: window too large"; return false; }
+    groups.push_back(Group{(int)p, 1, ents[p].rb, ents[p].ob, ents[p].two});
   }
   auto rows_visited = [](int S, bool fen) { return (fen && S >= 16) ? (S == 16 ? 16 : S == 32 ? 24 : 32) : S; };
   auto item_cost = [&](int S, bool fen) -> long long {
@@ -751,7 +768,7 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     u.ref_bx = rx0; u.ref_by = g.rb.y0; u.ref_pitch = (s8_ce(g.rb.x1) - rx0) * bps; u.ref_rows = g.rb.y1 - g.rb.y0;
     u.org_bx = ox0; u.org_by = g.ob.y0; u.org_pitch = (s8_ce(g.ob.x1) - ox0) * bps; u.org_rows = g.ob.y1 - g.ob.y0;
     int org_off = 0, copy_stride = 0;
-    u.smem_need = cu_smem_need(g.rb, g.ob, &org_off, &copy_stride, bps);
+    u.smem_need = cu_smem_need(g.rb, g.ob, &org_off, &copy_stride, bps, g.two);
     u.org_smem_off = org_off; u.copy_stride = copy_stride;
     const int bfirst = group_range[gi].first, bcount = group_range[gi].second;
     long long acc = 0;
