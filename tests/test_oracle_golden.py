@@ -47,3 +47,32 @@ def test_golden_covers_all_fractional_outcomes(gold):
             halves |= set(zip(r["half_x"].tolist(), r["half_y"].tolist()))
             qters |= set(zip(r["qter_x"].tolist(), r["qter_y"].tolist()))
     assert len(halves) == 9 and len(qters) == 9
+
+
+@pytest.mark.parametrize("bd", [9, 10, 12, 14])
+def test_sad_sum_of_minima_identity_matches_oracle(bd):
+    """The arithmetic the 16-bit CUDA search relies on (hmb200_search16_cu.cuh): SAD = sum(org) + sum(ref) - 2 sum(min),
+    accumulated from packed half-word pairs by a signed 16-bit dot product, and one shift instead of
+    (sum << iSubShift) >> (bitDepth - 8) -- checked here against the oracle's xGetSAD restatement, FEN row sub-sampling
+    included, with samples at both ends of the range."""
+    from oracle.pyoracle import Oracle
+    o = Oracle()
+    rng = np.random.default_rng(bd)
+    top = (1 << bd) - 1
+    for (w, h, ss) in [(8, 8, 0), (16, 16, 1), (16, 4, 0), (32, 24, 1), (64, 64, 1), (64, 16, 1)]:
+        org = rng.integers(0, top + 1, size=(h, 80)).astype(np.int16)
+        ref = rng.integers(0, top + 1, size=(h, 80)).astype(np.int16)
+        org[: h // 2, :5] = top
+        ref[: h // 2, :5] = 0
+        ref[h // 2:, 3:9] = top
+        rows = np.arange(0, h, 1 << ss)
+        a = org[rows, :w].astype(np.int64)
+        b = ref[rows, :w].astype(np.int64)
+        # packed pairs as the kernel sees them: signed 16-bit halves times taps (1, 1)
+        halves = np.minimum(a, b).astype(np.uint16).view(np.int16).astype(np.int64)
+        m = int(halves.sum())
+        total = int(a.sum() + b.sum() - 2 * m)
+        shr = bd - 8
+        assert shr >= ss
+        assert total >> (shr - ss) == (total << ss) >> shr
+        assert total >> (shr - ss) == o.sad((org, 0, 80), (ref, 0, 80), w, h, bd, ss)
