@@ -89,7 +89,7 @@ CFG_RA10 = os.path.join(ROOT, "integration", "_build", "randomaccess_main10_sett
 def test_encoder_bitstream_md5_randomaccess_main10(tmp_path):
     """BASELINE.json configs[3]'s coding structure (encoder_randomaccess_main10.cfg: B slices, GOP 8, two lists, 10-bit,
     full search +-128) on a CPU-runnable picture: besides the uni-directional searches every bi-prediction refinement
-    (xPatternSearch at +-BipredSearchRange on the signed `2*org - other prediction` pattern, TEncSearch.cpp:3690-3706)
+    (xPatternSearch at +-BipredSearchRange on the signed `2*org - other prediction` pattern, TEncSearch.cpp:3686-3697, 3710-3728)
     and the 10-bit quarter-pel SATD refinement go through libhmb200; bitstream and picture MD5s must equal the stock
     encoder's (tests/golden/encoder_md5_ra10.json)."""
     _need_binary()
