@@ -105,10 +105,25 @@ typedef struct {
 /* ------------------------------------------------------------------ lifetime ---------------------------------- */
 
 /* Replaces nothing in the reference; called from TEncSearch::init (TEncSearch.cpp:201) where picture and CTU size
- * are known.  Selects the device, creates streams and pinned staging.  Idempotent per device. */
+ * are known.  Selects the device, creates streams and pinned staging.  Idempotent per device.  This is the process-wide
+ * DEFAULT context: the single-GPU encoder needs nothing else. */
 int  hmb200_init(int device);
-void hmb200_shutdown(void);
-const char* hmb200_last_error(void);
+void hmb200_shutdown(void);                 /* tears down the calling thread's current context's device state */
+const char* hmb200_last_error(void);        /* last error of the calling thread */
+
+/* Multi-GPU inside one process (lookahead frame pairs / tile columns, "one host thread and stream set per
+ * GPU"; the reference's frame loop is TAppEncTop::encode, App/TAppEncoder/TAppEncTop.cpp:478-520).  A context owns one
+ * device's streams, planes and staging; every entry point of this header works on the CALLING THREAD'S CURRENT context.
+ * hmb200_ctx_create makes the new context current on the calling thread; hmb200_ctx_set_current(ctx) binds one to another
+ * thread (NULL = the default context of hmb200_init) and selects its device.  A context is used by one thread at a time;
+ * different contexts run concurrently on their own threads.  Plane ids and prepared handles belong to the context they
+ * were made in (a handle used under another context fails with HMB200_ERR_STATE). */
+typedef struct hmb200_ctx hmb200_ctx;
+hmb200_ctx* hmb200_ctx_create(int device);
+void hmb200_ctx_destroy(hmb200_ctx* ctx);
+int  hmb200_ctx_set_current(hmb200_ctx* ctx);
+hmb200_ctx* hmb200_ctx_get_current(void);
+int  hmb200_ctx_device(const hmb200_ctx* ctx);
 /* Page-locked host memory for result arrays (hmb200_fetch_results copies straight into it, without the staging copy it
  * needs for pageable memory) and for planes handed to hmb200_register_plane*. */
 void* hmb200_host_alloc(size_t bytes);
@@ -266,6 +281,16 @@ int  hmb200_fetch_results(hmb200_prepared* p, hmb200_pu_result* results);   /* D
  * is ordered after a pending fetch on the device. */
 int  hmb200_fetch_results_async(hmb200_prepared* p, hmb200_pu_result* results);
 int  hmb200_fetch_wait(hmb200_prepared* p);
+/* The same record in 16 bytes for the D2H link (the MV field is two thirds of a frame pair's host traffic): TComMv
+ * components are Shorts (TLibCommon/TComMv.h:53-54), the half / quarter offsets lie in -1..1 (s_acMvRefineH/Q,
+ * TLibEncoder/TEncSearch.cpp:51-75).  Packed on the device behind the run, then copied like hmb200_fetch_results_async. */
+typedef struct {
+  int16_t mv_x, mv_y;
+  uint32_t sad;
+  int8_t half_x, half_y, qter_x, qter_y;
+  uint32_t frac_cost;
+} hmb200_pu_result16;
+int  hmb200_fetch_results16_async(hmb200_prepared* p, hmb200_pu_result16* results);
 int  hmb200_sync(void);
 /* CUDA-event timing of the last hmb200_run_prepared: total and per-kernel milliseconds. */
 int  hmb200_last_timing(float* total_ms, float* search_ms, float* frac_ms);
@@ -298,6 +323,9 @@ int  hmb200_tz_jobs(int cur_plane, int ref_plane, const hmb200_pu_job* jobs, con
  * of a CU shared by all its partitions): executed < algorithmic when fusion applies.  Reported next to the roofline
  * so that algorithmic throughput and pipe utilisation are not conflated. */
 int  hmb200_prepared_executed_work(const hmb200_prepared* p, uint64_t* abs_diffs_executed, uint64_t* pus_fused);
+/* The roofline numerator: byte abs-diffs the shipped algorithm cannot avoid - every visited sample of every CU once per
+ * candidate of its window for the CU-fused kernels (no masked lanes, no padding), W*H per candidate for PUs searched alone. */
+int  hmb200_prepared_unique_work(const hmb200_prepared* p, uint64_t* abs_diffs_unique);
 
 #ifdef __cplusplus
 }

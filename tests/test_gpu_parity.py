@@ -441,6 +441,47 @@ def test_fused_small_cus_wide_windows_index_flush(hm):
         assert results_equal(got, exp, ("mv_x", "mv_y", "sad")) == [], flat
 
 
+@pytest.mark.parametrize("fen", [1, 0])
+def test_child_fold_and_edge_items_equal_separate_kernels(hm, monkeypatch, fen):
+    """A 16x16 CU's pass also yields the PUs of its four 8x8 child CUs (CHILD kernels), and a window whose last column
+    starts a 16-column block runs that column as edge items (a lane per candidate row).  Both are scheduling choices: the MV
+    field must equal the one of the separate 8x8-CU kernel with masked last blocks (knobs off), for the whole 416x240 list,
+    for a thinned list (CUs with missing partitions / missing children) and for flat content (raster order alone decides,
+    and the last column precedes the next rows); sampled PUs are checked against the oracle."""
+    W, H = 416, 240
+    lam = int(np.floor(65536.0 * np.sqrt(0.4624 * 2 ** ((35 - 12) / 3.0))))
+    full = hm.build_canonical_jobs(W, H, 64, lam)
+    rng = np.random.default_rng(77)
+    thin = full[np.sort(rng.choice(len(full), len(full) // 2, replace=False))]
+    flat = np.full((H, W), 55, dtype=np.uint8)
+    cases = [("full", synth.luma_frame(W, H, 1, seed=9), synth.luma_frame(W, H, 0, seed=9), full),
+             ("thin", synth.luma_frame(W, H, 2, seed=9), synth.luma_frame(W, H, 0, seed=9), thin),
+             ("flat", flat, flat, hm.build_canonical_jobs(W, H, 64, 0, ctu_first=8, ctu_count=2))]
+    # flat content, windows kept but the predictor moved next to the last column: every PU's winner is the edge candidate
+    # (64, 0), which ties with (64, 1) - decoded from an edge item's local index
+    ew = hm.build_canonical_jobs(W, H, 64, 65536 * 4, ctu_first=8, ctu_count=1).copy()
+    ew["pred_x"], ew["pred_y"] = 258, 2
+    cases.append(("edgewin", flat, flat, ew))
+    for name, f1, f0, jobs in cases:
+        fused, work = _run_full(hm, f1, f0, jobs, flags_of(fen, 1, frac=False))
+        monkeypatch.setenv("HMB200_NO_CHILD_FOLD", "1")
+        monkeypatch.setenv("HMB200_NO_EDGE_ITEMS", "1")
+        plain, work2 = _run_full(hm, f1, f0, jobs, flags_of(fen, 1, frac=False))
+        monkeypatch.delenv("HMB200_NO_CHILD_FOLD")
+        monkeypatch.delenv("HMB200_NO_EDGE_ITEMS")
+        assert work["abs_diffs_executed"] < work2["abs_diffs_executed"], name
+        assert results_equal(fused, plain, ("mv_x", "mv_y", "sad")) == [], name
+        pick = np.sort(rng.choice(len(jobs), 150, replace=False))
+        cur, o0, stride = padded(f1)
+        ref, _, _ = padded(f0)
+        exp, _ = Oracle(fen=fen, hadme=1).run_jobs((cur, o0, stride), (ref, o0, stride), jobs[pick], 8, False)
+        assert results_equal(fused[pick], exp, ("mv_x", "mv_y", "sad")) == [], name
+        if name == "flat":
+            assert np.array_equal(fused["mv_x"], jobs["lt_x"]) and np.array_equal(fused["mv_y"], jobs["lt_y"])
+        if name == "edgewin":
+            assert np.all(fused["mv_x"] == 64) and np.all(fused["mv_y"] == 0)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # 10-bit content: CU-fused 16-bit kernels (packed 16x2 arithmetic, distortion precision shift)
 # ---------------------------------------------------------------------------------------------------------------------

@@ -5,4 +5,5 @@ is a thin ctypes mirror of that ABI for tests and benchmarks; it never computes 
 back to a CPU implementation: if the shared library is missing, importing `video_codecs_b200.api` raises.
 """
 from .api import (HMB200, HMB200Error, JOB_DTYPE, RESULT_DTYPE, DIST_DESC_DTYPE,  # noqa: F401
-                  FLAG_FEN, FLAG_HADME, FLAG_FRAC, FLAG_TZ, FLAG_TZ_STOP, TZ_EXTRA_DTYPE, MC_DESC_DTYPE, INTRA_BLOCK_DTYPE, DF_SAD, DF_SSE, DF_HADS, DF_SADS, lib_path)
+                  FLAG_FEN, FLAG_HADME, FLAG_FRAC, FLAG_TZ, FLAG_TZ_STOP, TZ_EXTRA_DTYPE, MC_DESC_DTYPE, INTRA_BLOCK_DTYPE, DF_SAD, DF_SSE, DF_HADS, DF_SADS, lib_path,
+                  RESULT16_DTYPE, widen_results16)

@@ -23,7 +23,9 @@ MC_DESC_DTYPE = np.dtype([("pu_x", "<i4"), ("pu_y", "<i4"), ("w", "<i4"), ("h", 
 INTRA_BLOCK_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("n", "<i4"), ("ref_off", "<i4"), ("flags", "<i4"), ("reserved", "<i4")])
 TZ_EXTRA_DTYPE = np.dtype([("cu_x", "<i4"), ("cu_y", "<i4"), ("has_imv", "<i4"), ("imv_x", "<i4"), ("imv_y", "<i4"),
                            ("reserved", "<i4", (3,))])
-assert TZ_EXTRA_DTYPE.itemsize == 32
+RESULT16_DTYPE = np.dtype([("mv_x", "<i2"), ("mv_y", "<i2"), ("sad", "<u4"), ("half_x", "i1"), ("half_y", "i1"), ("qter_x", "i1"),
+                           ("qter_y", "i1"), ("frac_cost", "<u4")])
+assert TZ_EXTRA_DTYPE.itemsize == 32 and RESULT16_DTYPE.itemsize == 16
 assert JOB_DTYPE.itemsize == 48 and RESULT_DTYPE.itemsize == 32 and DIST_DESC_DTYPE.itemsize == 40
 
 
@@ -97,6 +99,10 @@ def _load():
         "hmb200_prepared_set_tz": (i32, [vp, vp, i32, i32, i32, i32]),
         "hmb200_tz_jobs": (i32, [i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
         "hmb200_prepared_executed_work": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "hmb200_prepared_unique_work": (i32, [vp, C.POINTER(C.c_uint64)]),
+        "hmb200_fetch_results16_async": (i32, [vp, vp]),
+        "hmb200_ctx_create": (vp, [i32]), "hmb200_ctx_destroy": (None, [vp]), "hmb200_ctx_set_current": (i32, [vp]),
+        "hmb200_ctx_get_current": (vp, []), "hmb200_ctx_device": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)          # AttributeError here == the library does not export what the header declares
@@ -108,8 +114,16 @@ def _addr(a, off=0):
     return a.ctypes.data + a.dtype.itemsize * int(off)
 
 
+def widen_results16(r16):
+    """RESULT16_DTYPE -> RESULT_DTYPE (same values)."""
+    out = np.zeros(len(r16), dtype=RESULT_DTYPE)
+    for f in RESULT_DTYPE.names:
+        out[f] = r16[f]
+    return out
+
+
 class HMB200:
-    """One instance per process (the C library keeps process-global state, like the encoder it serves)."""
+    """Thin wrapper; all state lives in the C library's contexts (default context: init(); more: ctx_create())."""
 
     def __init__(self):
         self.lib, self.exported = _load()
@@ -125,6 +139,19 @@ class HMB200:
 
     def shutdown(self):
         self.lib.hmb200_shutdown()
+
+    # -- contexts: one per GPU, each bound to the host thread that drives it (hmb200_ctx_*) ------------------------------
+    def ctx_create(self, device):
+        h = self.lib.hmb200_ctx_create(int(device))
+        if not h:
+            raise HMB200Error(self.lib.hmb200_last_error().decode())
+        return h
+
+    def ctx_set_current(self, ctx):
+        self._check(self.lib.hmb200_ctx_set_current(ctx))
+
+    def ctx_destroy(self, ctx):
+        self.lib.hmb200_ctx_destroy(ctx)
 
     def host_array(self, n, dtype):
         """numpy array of n records in page-locked memory (hmb200_host_alloc); keep the returned array alive, free with host_free."""
@@ -345,6 +372,11 @@ class Prepared:
         """D2H of the last run's results on the copy stream; `out` must be a HMB200.host_array."""
         self.o._check(self.o.lib.hmb200_fetch_results_async(self.h, out.ctypes.data))
 
+    def fetch16_async(self, out):
+        """Same with 16-byte records (RESULT16_DTYPE), packed on the device behind the run."""
+        assert out.dtype == RESULT16_DTYPE
+        self.o._check(self.o.lib.hmb200_fetch_results16_async(self.h, out.ctypes.data))
+
     def fetch_wait(self):
         self.o._check(self.o.lib.hmb200_fetch_wait(self.h))
 
@@ -358,7 +390,10 @@ class Prepared:
         self.o._check(self.o.lib.hmb200_prepared_work(self.h, C.byref(a), C.byref(b)))
         c, d = C.c_uint64(), C.c_uint64()
         self.o._check(self.o.lib.hmb200_prepared_executed_work(self.h, C.byref(c), C.byref(d)))
-        return {"cand_sads": a.value, "abs_diffs": b.value, "abs_diffs_executed": c.value, "pus_fused": d.value}
+        e = C.c_uint64()
+        self.o._check(self.o.lib.hmb200_prepared_unique_work(self.h, C.byref(e)))
+        return {"cand_sads": a.value, "abs_diffs": b.value, "abs_diffs_executed": c.value, "pus_fused": d.value,
+                "abs_diffs_unique": e.value}
 
     def free(self):
         if self.h:

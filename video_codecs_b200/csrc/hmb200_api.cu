@@ -1,6 +1,7 @@
 // C-ABI frontend of libhmb200.so (include/hmb200.h): plane registry, job scheduling, kernel launches.
-// One caller thread per process (the reference path is non-reentrant too: shared m_cDistParam / m_filteredBlock,
-// TLibEncoder/TEncSearch.h:113).  No CPU fallback anywhere: without a usable sm_100 device every compute entry
+// One caller thread per CONTEXT (the reference path is non-reentrant too: shared m_cDistParam / m_filteredBlock,
+// TLibEncoder/TEncSearch.h:113); several contexts - one per GPU - may run concurrently on their own threads.
+// No CPU fallback anywhere: without a usable sm_100 device every compute entry
 // fails with HMB200_ERR_CUDA.
 #include <cmath>
 #include <cstdio>
@@ -9,6 +10,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 #include <cuda_runtime.h>
 #include "hmb200_device.cuh"
 #include "hmb200_generic.cuh"
@@ -48,7 +50,7 @@ struct State {
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};     // side streams for concurrent variant kernels
   cudaStream_t copy = nullptr;                                     // D2H of results behind the next frame pair's kernels (hmb200_fetch_results_async)
   cudaStream_t up = nullptr;                                       // H2D + border extension of page-locked frames behind the current pair's kernels
-  void* upstage = nullptr; size_t upstage_bytes = 0;               // device staging of the upload stream (g.dstage belongs to the compute stream)
+  void* upstage = nullptr; size_t upstage_bytes = 0;               // device staging of the upload stream (G.dstage belongs to the compute stream)
   std::vector<cudaEvent_t> free_events;
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<Plane> planes;
@@ -60,10 +62,18 @@ struct State {
   float last_total_ms = 0, last_search_ms = 0, last_frac_ms = 0;
 };
 
-State g;
-std::string g_err;
+// One State per context.  The process-wide default context is what hmb200_init creates (the single-GPU encoder: one
+// caller thread, nothing to bind); hmb200_ctx_create makes further ones - one per GPU, each driven by its own host thread
+// ("one host thread and stream set per GPU").  Every entry point works on the calling thread's current
+// context; a context must not be used by two threads at the same time.
+State g_default;
+thread_local State* tl_ctx = nullptr;            // nullptr: the default context
+inline State& cur_state() { return tl_ctx ? *tl_ctx : g_default; }
+#define G cur_state()
+thread_local std::string g_err;                  // last error of the calling thread
+std::mutex g_init_mutex;                         // context creation / destruction is serialised (kernel attribute tables, device selection)
 
-int g_err_code = HMB200_OK;
+thread_local int g_err_code = HMB200_OK;
 int fail(int code, const std::string& msg) { g_err = msg; g_err_code = code; return code; }
 #define CUDA_TRY(expr)                                                                                   \
   do {                                                                                                   \
@@ -71,37 +81,37 @@ int fail(int code, const std::string& msg) { g_err = msg; g_err_code = code; ret
     if (e__ != cudaSuccess)                                                                              \
       return fail(HMB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
   } while (0)
-#define NEED_READY() do { if (!g.ready) return fail(HMB200_ERR_STATE, "hmb200_init has not succeeded"); } while (0)
+#define NEED_READY() do { if (!G.ready) return fail(HMB200_ERR_STATE, "hmb200_init has not succeeded"); } while (0)
 
 int ensure_pinned(size_t bytes) {
-  if (bytes <= g.pinned_bytes) return HMB200_OK;
-  if (g.pinned) cudaFreeHost(g.pinned);
-  g.pinned = nullptr; g.pinned_bytes = 0;
-  CUDA_TRY(cudaMallocHost(&g.pinned, bytes));
-  g.pinned_bytes = bytes;
+  if (bytes <= G.pinned_bytes) return HMB200_OK;
+  if (G.pinned) cudaFreeHost(G.pinned);
+  G.pinned = nullptr; G.pinned_bytes = 0;
+  CUDA_TRY(cudaMallocHost(&G.pinned, bytes));
+  G.pinned_bytes = bytes;
   return HMB200_OK;
 }
 int ensure_dstage(size_t bytes) {
-  if (bytes <= g.dstage_bytes) return HMB200_OK;
-  if (g.dstage) cudaFree(g.dstage);
-  g.dstage = nullptr; g.dstage_bytes = 0;
-  CUDA_TRY(cudaMalloc(&g.dstage, bytes));
-  g.dstage_bytes = bytes;
+  if (bytes <= G.dstage_bytes) return HMB200_OK;
+  if (G.dstage) cudaFree(G.dstage);
+  G.dstage = nullptr; G.dstage_bytes = 0;
+  CUDA_TRY(cudaMalloc(&G.dstage, bytes));
+  G.dstage_bytes = bytes;
   return HMB200_OK;
 }
 
 cudaEvent_t take_event() {
-  if (!g.free_events.empty()) { cudaEvent_t e = g.free_events.back(); g.free_events.pop_back(); return e; }
+  if (!G.free_events.empty()) { cudaEvent_t e = G.free_events.back(); G.free_events.pop_back(); return e; }
   cudaEvent_t e = nullptr;
   cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   return e;
 }
-void give_event(cudaEvent_t e) { if (e) g.free_events.push_back(e); }
+void give_event(cudaEvent_t e) { if (e) G.free_events.push_back(e); }
 
 int alloc_plane_slot() {
-  for (size_t i = 0; i < g.planes.size(); i++) if (!g.planes[i].used) return (int)i;
-  g.planes.emplace_back();
-  return (int)g.planes.size() - 1;
+  for (size_t i = 0; i < G.planes.size(); i++) if (!G.planes[i].used) return (int)i;
+  G.planes.emplace_back();
+  return (int)G.planes.size() - 1;
 }
 
 int make_plane(Plane& p, int width, int height, int mx, int my, int bit_depth) {
@@ -113,8 +123,8 @@ int make_plane(Plane& p, int width, int height, int mx, int my, int bit_depth) {
   p.d.bytes_per_sample = bps; p.d.bit_depth = bit_depth;
   p.bytes = (size_t)pitch_bytes * total_h;
   p.d.base = nullptr;
-  for (size_t i = 0; i < g.pool.size(); i++)
-    if (g.pool[i].bytes == p.bytes) { p.d.base = g.pool[i].base; p.ev_reuse = g.pool[i].ev_free; g.pool.erase(g.pool.begin() + i); break; }
+  for (size_t i = 0; i < G.pool.size(); i++)
+    if (G.pool[i].bytes == p.bytes) { p.d.base = G.pool[i].base; p.ev_reuse = G.pool[i].ev_free; G.pool.erase(G.pool.begin() + i); break; }
   if (!p.d.base) CUDA_TRY(cudaMalloc(&p.d.base, p.bytes));
   p.used = true;
   return HMB200_OK;
@@ -123,15 +133,15 @@ int make_plane(Plane& p, int width, int height, int mx, int my, int bit_depth) {
 // Every consumer of a plane on the compute stream goes through here: a plane that was uploaded on the upload stream
 // becomes visible to the compute stream (and the side streams forked from it) by one event wait.
 Plane* get_plane(int id) {
-  if (id < 0 || id >= (int)g.planes.size() || !g.planes[id].used) return nullptr;
-  Plane& p = g.planes[id];
-  if (p.ev_ready) { cudaStreamWaitEvent(g.stream, p.ev_ready, 0); give_event(p.ev_ready); p.ev_ready = nullptr; }
+  if (id < 0 || id >= (int)G.planes.size() || !G.planes[id].used) return nullptr;
+  Plane& p = G.planes[id];
+  if (p.ev_ready) { cudaStreamWaitEvent(G.stream, p.ev_ready, 0); give_event(p.ev_ready); p.ev_ready = nullptr; }
   return &p;
 }
 
 // which registered plane does a host Pel* fall into?  (1:1 entries hand us raw pointers into TComPicYuv buffers)
 Plane* find_plane_by_host(const int16_t* ptr, int* x, int* y) {
-  for (auto& p : g.planes) {
+  for (auto& p : G.planes) {
     if (!p.used || !p.host_lo) continue;
     if (ptr >= p.host_lo && ptr < p.host_hi) {
       ptrdiff_t off = ptr - p.host_lo;
@@ -143,7 +153,25 @@ Plane* find_plane_by_host(const int16_t* ptr, int* x, int* y) {
   return nullptr;
 }
 
-bool supported_pu(int w, int h) { return w >= 4 && h >= 4 && w <= 64 && h <= 64 && (w % 4) == 0 && (h % 2) == 0; }
+// The PU shapes HM produces (TLibCommon/TComDataCU.cpp:1893-1931: 2Nx2N .. nRx2N of 8..64 CUs, plus 4x4): widths and heights
+// of 4, 8, 12, 16, 24, 32, 48, 64.  Other shapes would need the 2x2 Hadamard tiles / generic-width SAD of the distortion
+// table (hmb200_dist / hmb200_dist_batch cover those); the search and refinement kernels reject them instead of guessing.
+bool pu_dim_ok(int v) { return v == 4 || v == 8 || v == 12 || v == 16 || v == 24 || v == 32 || v == 48 || v == 64; }
+bool supported_pu(int w, int h) { return pu_dim_ok(w) && pu_dim_ok(h); }
+
+// Footprints in picture coordinates, [x0, x1) x [y0, y1).  Every launch is preceded by a host-side check that the samples it
+// may read lie inside the padded plane: an out-of-plane window would be an out-of-bounds global read (the reference would
+// read outside its picture buffer in the same situation; we reject with HMB200_ERR_ARG instead).
+struct Box { int x0, y0, x1, y1; };
+inline Box box_empty() { return Box{1 << 30, 1 << 30, -(1 << 30), -(1 << 30)}; }
+inline void box_add(Box& b, int x0, int y0, int x1, int y1) {
+  b.x0 = std::min(b.x0, x0); b.y0 = std::min(b.y0, y0); b.x1 = std::max(b.x1, x1); b.y1 = std::max(b.y1, y1);
+}
+inline bool box_inside(const DevPlane& d, const Box& b) {
+  if (b.x0 > b.x1) return true;                       // empty
+  return b.x0 >= -d.margin_x && b.x1 <= d.width + d.margin_x && b.y0 >= -d.margin_y && b.y1 <= d.height + d.margin_y;
+}
+constexpr int FRAC_REACH = 4;                         // 8-tap filter: 3 samples before, 4 after (TComInterpolationFilter.cpp:57-63)
 
 template <typename RefT, typename OrgT>
 void launch_generic(const SearchTask* d_tasks, hmb200_pu_result* d_res, int n, const DevPlane& cur, const DevPlane& ref,
@@ -151,21 +179,21 @@ void launch_generic(const SearchTask* d_tasks, hmb200_pu_result* d_res, int n, c
   if (do_search) {
     const int blocks = d_index ? n_index : n;
     if (blocks > 0) {
-      k_search_generic<RefT, OrgT><<<blocks, 256, 0, g.stream>>>(d_tasks, d_res, cur, ref, d_index);
-      g.launches++;
+      k_search_generic<RefT, OrgT><<<blocks, 256, 0, G.stream>>>(d_tasks, d_res, cur, ref, d_index);
+      G.launches++;
     }
   }
-  if (mid) cudaEventRecord(mid, g.stream);
+  if (mid) cudaEventRecord(mid, G.stream);
   if (flags & HMB200_FLAG_FRAC) {
-    k_frac_generic<RefT, OrgT><<<n, FRAC_THREADS, FRAC_SMEM_BYTES, g.stream>>>(d_tasks, d_res, cur, ref,
+    k_frac_generic<RefT, OrgT><<<n, FRAC_THREADS, FRAC_SMEM_BYTES, G.stream>>>(d_tasks, d_res, cur, ref,
                                                                                (flags & HMB200_FLAG_HADME) ? 1 : 0);
-    g.launches++;
+    G.launches++;
   }
 }
 
 void dispatch_generic(const SearchTask* d_tasks, hmb200_pu_result* d_res, int n, const DevPlane& cur, const DevPlane& ref,
                       int flags, bool do_search, cudaEvent_t mid) {
-  if (n <= 0) { if (mid) cudaEventRecord(mid, g.stream); return; }
+  if (n <= 0) { if (mid) cudaEventRecord(mid, G.stream); return; }
   bool r8 = ref.bytes_per_sample == 1, o8 = cur.bytes_per_sample == 1;
   if (r8 && o8)        launch_generic<uint8_t, uint8_t>(d_tasks, d_res, n, cur, ref, flags, do_search, mid);
   else if (r8 && !o8)  launch_generic<uint8_t, int16_t>(d_tasks, d_res, n, cur, ref, flags, do_search, mid);
@@ -174,6 +202,17 @@ void dispatch_generic(const SearchTask* d_tasks, hmb200_pu_result* d_res, int n,
 }
 
 } // namespace
+
+__global__ void k_pack_results16(const hmb200_pu_result* __restrict__ in, hmb200_pu_result16* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const hmb200_pu_result r = in[i];
+  hmb200_pu_result16 o;
+  o.mv_x = (int16_t)r.mv_x; o.mv_y = (int16_t)r.mv_y; o.sad = r.sad;
+  o.half_x = (int8_t)r.half_x; o.half_y = (int8_t)r.half_y; o.qter_x = (int8_t)r.qter_x; o.qter_y = (int8_t)r.qter_y;
+  o.frac_cost = r.frac_cost;
+  out[i] = o;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 struct hmb200_prepared {
@@ -189,16 +228,52 @@ struct hmb200_prepared {
   TzParams tz{0, 0, 0, 0, 0};
   cudaEvent_t ev_done = nullptr, ev_fetched = nullptr;   // end of the last run on the compute stream / of the last asynchronous fetch
   bool fetch_pending = false;
+  hmb200_pu_result16* d_packed = nullptr;   // hmb200_fetch_results16_async: the 16-byte records
+  State* owner = nullptr;         // the context the handle was prepared in (its streams, its device)
+  Box foot_ref = box_empty(), foot_org = box_empty();    // samples any kernel of this list may read (validated against the planes per run)
 };
+#define NEED_OWNER(p) do { if ((p)->owner != &G) return fail(HMB200_ERR_STATE, "the prepared handle belongs to another context"); } while (0)
 
 extern "C" {
 
 const char* hmb200_last_error(void) { return g_err.c_str(); }
-uint64_t hmb200_launch_count(void) { return g.launches; }
+uint64_t hmb200_launch_count(void) { return G.launches; }
 
-int hmb200_init(int device) {
-  if (g.ready && g.device == device) return HMB200_OK;
-  if (g.ready) hmb200_shutdown();
+// ---- context lifetime ------------------------------------------------------------------------------------------
+static void teardown_state(State& st) {
+  // called with the state's device current; safe on a partially initialised state (init failure paths come here too)
+  if (st.stream) cudaStreamSynchronize(st.stream);
+  if (st.up) cudaStreamSynchronize(st.up);
+  if (st.copy) cudaStreamSynchronize(st.copy);
+  for (auto& p : st.planes) {
+    if (p.used && p.d.base) cudaFree(p.d.base);
+    if (p.ev_ready) cudaEventDestroy(p.ev_ready);
+    if (p.ev_reuse) cudaEventDestroy(p.ev_reuse);
+  }
+  st.planes.clear();
+  for (auto& b : st.pool) { cudaFree(b.base); if (b.ev_free) cudaEventDestroy(b.ev_free); }
+  st.pool.clear();
+  for (auto e : st.free_events) cudaEventDestroy(e);
+  st.free_events.clear();
+  if (st.upstage) { cudaFree(st.upstage); st.upstage = nullptr; st.upstage_bytes = 0; }
+  if (st.pattern.d.base) cudaFree(st.pattern.d.base);
+  st.pattern = Plane();
+  if (st.pinned) cudaFreeHost(st.pinned);
+  if (st.dstage) cudaFree(st.dstage);
+  st.pinned = nullptr; st.pinned_bytes = 0; st.dstage = nullptr; st.dstage_bytes = 0;
+  for (auto& ev : st.ev) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+  for (auto& s : st.side) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); s = nullptr; }
+  if (st.copy) { cudaStreamDestroy(st.copy); st.copy = nullptr; }
+  if (st.up) { cudaStreamDestroy(st.up); st.up = nullptr; }
+  if (st.ev_fork) { cudaEventDestroy(st.ev_fork); st.ev_fork = nullptr; }
+  for (auto& ev : st.ev_join) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+  if (st.stream) { cudaStreamDestroy(st.stream); st.stream = nullptr; }
+  st.ready = false; st.device = -1;
+}
+
+// Brings `st` up on `device`.  The caller holds g_init_mutex and has made `st` the calling thread's current context (the
+// helpers below allocate through G).
+static int init_state_body(State& st, int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
@@ -208,56 +283,87 @@ int hmb200_init(int device) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(HMB200_ERR_CUDA, "libhmb200 is built for sm_100a only; found " + std::string(prop.name));
-  g.sm_count = prop.multiProcessorCount;
-  CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-  for (auto& ev : g.ev) CUDA_TRY(cudaEventCreate(&ev));
-  for (auto& st : g.side) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  CUDA_TRY(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
-  CUDA_TRY(cudaStreamCreateWithFlags(&g.up, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
-  for (auto& ev : g.ev_join) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  int rc = search8_configure(&g_err);
+  st.sm_count = prop.multiProcessorCount;
+  st.device = device;
+  CUDA_TRY(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  for (auto& ev : st.ev) CUDA_TRY(cudaEventCreate(&ev));
+  for (auto& s : st.side) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&st.copy, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&st.up, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&st.ev_fork, cudaEventDisableTiming));
+  for (auto& ev : st.ev_join) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  int rc = search8_configure(&g_err);               // kernel attributes are per device: set for every context
   if (rc != HMB200_OK) return rc;
   if ((rc = cu_configure(&g_err)) != HMB200_OK) return rc;
   if ((rc = cu16_configure(&g_err)) != HMB200_OK) return rc;
-  g.device = device;
-  g.ready = true;
+  st.ready = true;
   // pattern buffer for the 1:1 entries: 64x64 int16, no margins
-  g.pattern = Plane();
-  rc = make_plane(g.pattern, 64, 64, 0, 0, 16);
-  if (rc != HMB200_OK) { g.ready = false; return rc; }
-  g.launches = 0;
+  st.pattern = Plane();
+  if ((rc = make_plane(st.pattern, 64, 64, 0, 0, 16)) != HMB200_OK) return rc;
+  st.launches = 0;
   return HMB200_OK;
+}
+static int init_state(State& st, int device) {
+  const int rc = init_state_body(st, device);
+  if (rc != HMB200_OK) { const std::string why = g_err; teardown_state(st); g_err = why; }   // no half-built context, nothing leaked
+  return rc;
+}
+
+int hmb200_init(int device) {
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  tl_ctx = nullptr;                                  // the default context becomes the calling thread's current one
+  if (g_default.ready && g_default.device == device) { cudaSetDevice(device); return HMB200_OK; }
+  if (g_default.ready) { cudaSetDevice(g_default.device); teardown_state(g_default); }
+  return init_state(g_default, device);
 }
 
 void hmb200_shutdown(void) {
-  if (!g.ready) return;
-  cudaStreamSynchronize(g.stream);
-  for (auto& p : g.planes) if (p.used && p.d.base) cudaFree(p.d.base);
-  g.planes.clear();
-  for (auto& b : g.pool) { cudaFree(b.base); if (b.ev_free) cudaEventDestroy(b.ev_free); }
-  g.pool.clear();
-  for (auto& pl : g.planes) { if (pl.ev_ready) cudaEventDestroy(pl.ev_ready); if (pl.ev_reuse) cudaEventDestroy(pl.ev_reuse); pl.ev_ready = pl.ev_reuse = nullptr; }
-  for (auto e : g.free_events) cudaEventDestroy(e);
-  g.free_events.clear();
-  if (g.upstage) { cudaFree(g.upstage); g.upstage = nullptr; g.upstage_bytes = 0; }
-  if (g.pattern.d.base) cudaFree(g.pattern.d.base);
-  g.pattern = Plane();
-  if (g.pinned) cudaFreeHost(g.pinned);
-  if (g.dstage) cudaFree(g.dstage);
-  g.pinned = nullptr; g.pinned_bytes = 0; g.dstage = nullptr; g.dstage_bytes = 0;
-  for (auto& ev : g.ev) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
-  for (auto& st : g.side) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; }
-  if (g.copy) { cudaStreamSynchronize(g.copy); cudaStreamDestroy(g.copy); g.copy = nullptr; }
-  if (g.up) { cudaStreamSynchronize(g.up); cudaStreamDestroy(g.up); g.up = nullptr; }
-  if (g.ev_fork) { cudaEventDestroy(g.ev_fork); g.ev_fork = nullptr; }
-  for (auto& ev : g.ev_join) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
-  cudaStreamDestroy(g.stream); g.stream = nullptr;
-  g.ready = false; g.device = -1;
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  State& st = G;
+  if (!st.ready) return;
+  cudaSetDevice(st.device);
+  teardown_state(st);
+}
+
+struct hmb200_ctx { State st; };
+
+hmb200_ctx* hmb200_ctx_create(int device) {
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  hmb200_ctx* c = new hmb200_ctx();
+  State* prev = tl_ctx;
+  tl_ctx = &c->st;
+  if (init_state(c->st, device) != HMB200_OK) { tl_ctx = prev; delete c; return nullptr; }
+  return c;                                          // current on the calling thread
+}
+
+int hmb200_ctx_set_current(hmb200_ctx* ctx) {
+  State& st = ctx ? ctx->st : g_default;
+  if (!st.ready) return fail(HMB200_ERR_STATE, "hmb200_ctx_set_current: the context is not initialised");
+  CUDA_TRY(cudaSetDevice(st.device));
+  tl_ctx = ctx ? &ctx->st : nullptr;
+  return HMB200_OK;
+}
+
+hmb200_ctx* hmb200_ctx_get_current(void) { return tl_ctx ? reinterpret_cast<hmb200_ctx*>(tl_ctx) : nullptr; }
+
+int hmb200_ctx_device(const hmb200_ctx* ctx) { return ctx ? ctx->st.device : g_default.device; }
+
+void hmb200_ctx_destroy(hmb200_ctx* ctx) {
+  if (!ctx) return;
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  if (ctx->st.ready) {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->st.device);
+    teardown_state(ctx->st);
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  if (tl_ctx == &ctx->st) tl_ctx = nullptr;
+  delete ctx;
 }
 
 void* hmb200_host_alloc(size_t bytes) {
-  if (!g.ready) { fail(HMB200_ERR_STATE, "hmb200_init has not succeeded"); return nullptr; }
+  if (!G.ready) { fail(HMB200_ERR_STATE, "hmb200_init has not succeeded"); return nullptr; }
   void* p = nullptr;
   if (cudaMallocHost(&p, bytes) != cudaSuccess) { fail(HMB200_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(cudaGetLastError())); return nullptr; }
   return p;
@@ -266,9 +372,9 @@ void hmb200_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int hmb200_sync(void) {
   NEED_READY();
-  CUDA_TRY(cudaStreamSynchronize(g.up));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.copy));
+  CUDA_TRY(cudaStreamSynchronize(G.up));
+  CUDA_TRY(cudaStreamSynchronize(G.stream));
+  CUDA_TRY(cudaStreamSynchronize(G.copy));
   return HMB200_OK;
 }
 
@@ -380,7 +486,7 @@ int hmb200_register_plane(const int16_t* host_origin, int stride, int width, int
       bit_depth < 8 || bit_depth > 16)
     return fail(HMB200_ERR_ARG, "hmb200_register_plane: bad geometry");
   int id = alloc_plane_slot();
-  Plane& p = g.planes[id];
+  Plane& p = G.planes[id];
   p = Plane();
   int rc = make_plane(p, width, height, margin_x, margin_y, bit_depth);
   if (rc != HMB200_OK) return rc;
@@ -388,18 +494,18 @@ int hmb200_register_plane(const int16_t* host_origin, int stride, int width, int
   const int16_t* src = host_origin - (ptrdiff_t)margin_y * stride - margin_x;
   size_t bytes = (size_t)total_w * total_h * sizeof(int16_t);
   if ((rc = ensure_pinned(bytes)) != HMB200_OK || (rc = ensure_dstage(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
-  int16_t* pin = reinterpret_cast<int16_t*>(g.pinned);
+  int16_t* pin = reinterpret_cast<int16_t*>(G.pinned);
   for (int y = 0; y < total_h; y++) memcpy(pin + (size_t)y * total_w, src + (size_t)y * stride, (size_t)total_w * sizeof(int16_t));
-  CUDA_TRY(cudaMemcpyAsync(g.dstage, pin, bytes, cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(G.dstage, pin, bytes, cudaMemcpyHostToDevice, G.stream));
   dim3 grid((total_w + 255) / 256, total_h);
   if (p.d.bytes_per_sample == 1)
-    k_narrow_plane<uint8_t><<<grid, 256, 0, g.stream>>>(reinterpret_cast<const int16_t*>(g.dstage), total_w,
+    k_narrow_plane<uint8_t><<<grid, 256, 0, G.stream>>>(reinterpret_cast<const int16_t*>(G.dstage), total_w,
                                                         reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, total_w, total_h);
   else
-    k_narrow_plane<uint16_t><<<grid, 256, 0, g.stream>>>(reinterpret_cast<const int16_t*>(g.dstage), total_w,
+    k_narrow_plane<uint16_t><<<grid, 256, 0, G.stream>>>(reinterpret_cast<const int16_t*>(G.dstage), total_w,
                                                          reinterpret_cast<uint16_t*>(p.d.base), p.d.pitch, total_w, total_h);
-  g.launches++;
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  G.launches++;
+  CUDA_TRY(cudaStreamSynchronize(G.stream));
   p.host_lo = src; p.host_hi = src + (size_t)(total_h - 1) * stride + total_w; p.host_stride = stride;
   p.kind = kind; p.poc = poc;
   return id;
@@ -411,7 +517,7 @@ int hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width,
   if (!host_samples || width <= 0 || height <= 0 || stride < width || margin_x < 0 || margin_y < 0)
     return fail(HMB200_ERR_ARG, "hmb200_register_plane_u8: bad geometry");
   int id = alloc_plane_slot();
-  Plane& p = g.planes[id];
+  Plane& p = G.planes[id];
   p = Plane();
   int rc = make_plane(p, width, height, margin_x, margin_y, 8);
   if (rc != HMB200_OK) return rc;
@@ -422,40 +528,42 @@ int hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width,
   if (user_pinned) {
     // page-locked, tightly packed frame: H2D + border extension on the upload stream, behind whatever the compute stream is
     // doing; the source stays the caller's until the copy has run (hmb200_sync or any later fetch / blocking call orders it)
-    if (bytes > g.upstage_bytes) {
-      CUDA_TRY(cudaStreamSynchronize(g.up));
-      if (g.upstage) cudaFree(g.upstage);
-      g.upstage = nullptr; g.upstage_bytes = 0;
-      CUDA_TRY(cudaMalloc(&g.upstage, bytes));
-      g.upstage_bytes = bytes;
-    }
-    if (p.ev_reuse) { CUDA_TRY(cudaStreamWaitEvent(g.up, p.ev_reuse, 0)); give_event(p.ev_reuse); p.ev_reuse = nullptr; }
-    CUDA_TRY(cudaMemcpyAsync(g.upstage, host_samples, bytes, cudaMemcpyHostToDevice, g.up));
-    dim3 ugrid((width + 2 * margin_x + 255) / 256, height + 2 * margin_y);
-    k_pad_plane_u8<<<ugrid, 256, 0, g.up>>>(reinterpret_cast<const uint8_t*>(g.upstage), width,
-                                            reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, width, height, margin_x, margin_y);
-    g.launches++;
-    p.ev_ready = take_event();
-    CUDA_TRY(cudaEventRecord(p.ev_ready, g.up));
+    auto upload = [&]() -> int {
+      if (bytes > G.upstage_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(G.up));
+        if (G.upstage) cudaFree(G.upstage);
+        G.upstage = nullptr; G.upstage_bytes = 0;
+        CUDA_TRY(cudaMalloc(&G.upstage, bytes));
+        G.upstage_bytes = bytes;
+      }
+      if (p.ev_reuse) { CUDA_TRY(cudaStreamWaitEvent(G.up, p.ev_reuse, 0)); give_event(p.ev_reuse); p.ev_reuse = nullptr; }
+      CUDA_TRY(cudaMemcpyAsync(G.upstage, host_samples, bytes, cudaMemcpyHostToDevice, G.up));
+      dim3 ugrid((width + 2 * margin_x + 255) / 256, height + 2 * margin_y);
+      k_pad_plane_u8<<<ugrid, 256, 0, G.up>>>(reinterpret_cast<const uint8_t*>(G.upstage), width,
+                                              reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, width, height, margin_x, margin_y);
+      G.launches++;
+      p.ev_ready = take_event();
+      CUDA_TRY(cudaEventRecord(p.ev_ready, G.up));
+      return HMB200_OK;
+    };
+    if ((rc = upload()) != HMB200_OK) { const std::string why = g_err; hmb200_release_plane(id); g_err = why; return rc; }
     p.kind = kind; p.poc = poc;
     return id;
   }
-  if ((rc = ensure_dstage(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
-  const uint8_t* src = host_samples;                      // page-locked, tightly packed frames go to the device without a staging copy
-  if (!user_pinned) {
-    if ((rc = ensure_pinned(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
-    uint8_t* pin = reinterpret_cast<uint8_t*>(g.pinned);
-    for (int y = 0; y < height; y++) memcpy(pin + (size_t)y * width, host_samples + (size_t)y * stride, (size_t)width);
-    src = pin;
-  }
-  CUDA_TRY(cudaMemcpyAsync(g.dstage, src, bytes, cudaMemcpyHostToDevice, g.stream));
-  dim3 grid((width + 2 * margin_x + 255) / 256, height + 2 * margin_y);
-  k_pad_plane_u8<<<grid, 256, 0, g.stream>>>(reinterpret_cast<const uint8_t*>(g.dstage), width,
-                                             reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, width, height, margin_x, margin_y);
-  g.launches++;
-  // a page-locked source stays the caller's until the copy has run (hmb200_sync / any fetch orders it); the library's own
-  // staging buffer is reused by the next call, so that path waits here
-  if (!user_pinned) CUDA_TRY(cudaStreamSynchronize(g.stream));
+  // pageable (or strided) source: through the library's page-locked staging buffer, which the next call reuses - so this path waits
+  if ((rc = ensure_dstage(bytes)) != HMB200_OK || (rc = ensure_pinned(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
+  uint8_t* pin = reinterpret_cast<uint8_t*>(G.pinned);
+  for (int y = 0; y < height; y++) memcpy(pin + (size_t)y * width, host_samples + (size_t)y * stride, (size_t)width);
+  auto upload = [&]() -> int {
+    CUDA_TRY(cudaMemcpyAsync(G.dstage, pin, bytes, cudaMemcpyHostToDevice, G.stream));
+    dim3 grid((width + 2 * margin_x + 255) / 256, height + 2 * margin_y);
+    k_pad_plane_u8<<<grid, 256, 0, G.stream>>>(reinterpret_cast<const uint8_t*>(G.dstage), width,
+                                               reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, width, height, margin_x, margin_y);
+    G.launches++;
+    CUDA_TRY(cudaStreamSynchronize(G.stream));
+    return HMB200_OK;
+  };
+  if ((rc = upload()) != HMB200_OK) { const std::string why = g_err; hmb200_release_plane(id); g_err = why; return rc; }
   p.kind = kind; p.poc = poc;
   return id;
 }
@@ -467,25 +575,25 @@ int hmb200_register_plane_yuv(const void* file_luma, int file_is16, int width, i
       file_bit_depth > 16 || internal_bit_depth < 8 || internal_bit_depth > 14 || (!file_is16 && file_bit_depth > 8))
     return fail(HMB200_ERR_ARG, "hmb200_register_plane_yuv: bad geometry or bit depths");
   int id = alloc_plane_slot();
-  Plane& p = g.planes[id];
+  Plane& p = G.planes[id];
   p = Plane();
   const int cw = width + pad_x, ch = height + pad_y;
   int rc = make_plane(p, cw, ch, margin_x, margin_y, internal_bit_depth);
   if (rc != HMB200_OK) return rc;
   const size_t bytes = (size_t)width * height * (file_is16 ? 2 : 1);
   if ((rc = ensure_pinned(bytes)) != HMB200_OK || (rc = ensure_dstage(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
-  memcpy(g.pinned, file_luma, bytes);
-  CUDA_TRY(cudaMemcpyAsync(g.dstage, g.pinned, bytes, cudaMemcpyHostToDevice, g.stream));
+  memcpy(G.pinned, file_luma, bytes);
+  CUDA_TRY(cudaMemcpyAsync(G.dstage, G.pinned, bytes, cudaMemcpyHostToDevice, G.stream));
   const int shift = internal_bit_depth - file_bit_depth, maxval = (1 << internal_bit_depth) - 1;
   dim3 grid((cw + 2 * margin_x + 255) / 256, ch + 2 * margin_y);
   if (p.d.bytes_per_sample == 1)
-    k_ingest_luma<uint8_t><<<grid, 256, 0, g.stream>>>(reinterpret_cast<const uint8_t*>(g.dstage), file_is16, width, height, pad_x, pad_y,
+    k_ingest_luma<uint8_t><<<grid, 256, 0, G.stream>>>(reinterpret_cast<const uint8_t*>(G.dstage), file_is16, width, height, pad_x, pad_y,
                                                        shift, maxval, reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, margin_x, margin_y);
   else
-    k_ingest_luma<uint16_t><<<grid, 256, 0, g.stream>>>(reinterpret_cast<const uint8_t*>(g.dstage), file_is16, width, height, pad_x, pad_y,
+    k_ingest_luma<uint16_t><<<grid, 256, 0, G.stream>>>(reinterpret_cast<const uint8_t*>(G.dstage), file_is16, width, height, pad_x, pad_y,
                                                         shift, maxval, reinterpret_cast<uint16_t*>(p.d.base), p.d.pitch, margin_x, margin_y);
-  g.launches++;
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  G.launches++;
+  CUDA_TRY(cudaStreamSynchronize(G.stream));
   CUDA_TRY(cudaGetLastError());
   p.kind = kind; p.poc = poc;
   return id;
@@ -502,15 +610,15 @@ int hmb200_read_plane(int plane_id, int16_t* dst_origin, int dst_stride) {
   if ((rc = ensure_pinned(bytes)) != HMB200_OK || (rc = ensure_dstage(bytes)) != HMB200_OK) return rc;
   dim3 grid((total_w + 255) / 256, total_h);
   if (p->d.bytes_per_sample == 1)
-    k_widen_plane<uint8_t><<<grid, 256, 0, g.stream>>>(reinterpret_cast<const uint8_t*>(p->d.base), p->d.pitch,
-                                                       reinterpret_cast<int16_t*>(g.dstage), total_w, total_w, total_h);
+    k_widen_plane<uint8_t><<<grid, 256, 0, G.stream>>>(reinterpret_cast<const uint8_t*>(p->d.base), p->d.pitch,
+                                                       reinterpret_cast<int16_t*>(G.dstage), total_w, total_w, total_h);
   else
-    k_widen_plane<uint16_t><<<grid, 256, 0, g.stream>>>(reinterpret_cast<const uint16_t*>(p->d.base), p->d.pitch,
-                                                        reinterpret_cast<int16_t*>(g.dstage), total_w, total_w, total_h);
-  g.launches++;
-  CUDA_TRY(cudaMemcpyAsync(g.pinned, g.dstage, bytes, cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
-  const int16_t* pin = reinterpret_cast<const int16_t*>(g.pinned);
+    k_widen_plane<uint16_t><<<grid, 256, 0, G.stream>>>(reinterpret_cast<const uint16_t*>(p->d.base), p->d.pitch,
+                                                        reinterpret_cast<int16_t*>(G.dstage), total_w, total_w, total_h);
+  G.launches++;
+  CUDA_TRY(cudaMemcpyAsync(G.pinned, G.dstage, bytes, cudaMemcpyDeviceToHost, G.stream));
+  CUDA_TRY(cudaStreamSynchronize(G.stream));
+  const int16_t* pin = reinterpret_cast<const int16_t*>(G.pinned);
   int16_t* dst = dst_origin - (ptrdiff_t)p->d.margin_y * dst_stride - p->d.margin_x;
   for (int y = 0; y < total_h; y++) memcpy(dst + (size_t)y * dst_stride, pin + (size_t)y * total_w, (size_t)total_w * sizeof(int16_t));
   return HMB200_OK;
@@ -520,16 +628,16 @@ void hmb200_release_plane(int plane_id) {
   Plane* p = get_plane(plane_id);            // also orders a still pending upload of this plane before the compute stream's tail
   if (!p) return;
   if (p->d.base) {
-    if (g.pool.size() < 16) {
+    if (G.pool.size() < 16) {
       // no host synchronisation: the buffer goes back to the pool with an event behind the last kernel that may read it
       // (side streams are joined into the compute stream before a run ends); whoever reuses it on the upload stream waits on it
       cudaEvent_t ev = p->ev_reuse ? p->ev_reuse : take_event();
       p->ev_reuse = nullptr;
-      cudaEventRecord(ev, g.stream);
-      g.pool.push_back(PoolBuf{p->bytes, p->d.base, ev});
+      cudaEventRecord(ev, G.stream);
+      G.pool.push_back(PoolBuf{p->bytes, p->d.base, ev});
     } else {
-      cudaStreamSynchronize(g.up);
-      cudaStreamSynchronize(g.stream);
+      cudaStreamSynchronize(G.up);
+      cudaStreamSynchronize(G.stream);
       cudaFree(p->d.base);
     }
   }
@@ -542,7 +650,7 @@ void hmb200_release_plane(int plane_id) {
 // ------------------------------------------------------------------------------------------------------------------
 uint32_t hmb200_dist(const hmb200_dist_param* dp) {
   auto die = [](const char* m) { fprintf(stderr, "hmb200_dist: %s (%s)\n", m, g_err.c_str()); abort(); };
-  if (!g.ready) die("library not initialised");
+  if (!G.ready) die("library not initialised");
   if (!dp || !dp->pOrg || !dp->pCur) die("null DistParam");
   if (dp->bApplyWeight) die("weighted prediction is out of scope (bApplyWeight must be false)");
   if (dp->iStep != 1) die("iStep must be 1");
@@ -551,23 +659,23 @@ uint32_t hmb200_dist(const hmb200_dist_param* dp) {
   size_t n = (size_t)w * h;
   if (ensure_pinned(2 * n * sizeof(int16_t) + 64) != HMB200_OK || ensure_dstage(2 * n * sizeof(int16_t) + sizeof(DistTask) + 64) != HMB200_OK)
     die("allocation failed");
-  int16_t* pin = reinterpret_cast<int16_t*>(g.pinned);
+  int16_t* pin = reinterpret_cast<int16_t*>(G.pinned);
   for (int y = 0; y < h; y++) {
     memcpy(pin + (size_t)y * w, dp->pOrg + (ptrdiff_t)y * dp->iStrideOrg, (size_t)w * sizeof(int16_t));
     memcpy(pin + n + (size_t)y * w, dp->pCur + (ptrdiff_t)y * dp->iStrideCur, (size_t)w * sizeof(int16_t));
   }
-  int16_t* d = reinterpret_cast<int16_t*>(g.dstage);
+  int16_t* d = reinterpret_cast<int16_t*>(G.dstage);
   size_t task_off = ((2 * n * sizeof(int16_t) + 15) / 16) * 16;
   DistTask t{d, d + n, w, w, w, h, dp->iSubShift, 0};
-  memcpy(reinterpret_cast<char*>(g.pinned) + task_off, &t, sizeof(t));
-  uint32_t* d_out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(g.dstage) + task_off + sizeof(DistTask));
-  if (cudaMemcpyAsync(g.dstage, g.pinned, task_off + sizeof(DistTask), cudaMemcpyHostToDevice, g.stream) != cudaSuccess) die("H2D failed");
-  k_dist_generic<int16_t><<<1, 128, 0, g.stream>>>(reinterpret_cast<const DistTask*>(reinterpret_cast<char*>(g.dstage) + task_off),
+  memcpy(reinterpret_cast<char*>(G.pinned) + task_off, &t, sizeof(t));
+  uint32_t* d_out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(G.dstage) + task_off + sizeof(DistTask));
+  if (cudaMemcpyAsync(G.dstage, G.pinned, task_off + sizeof(DistTask), cudaMemcpyHostToDevice, G.stream) != cudaSuccess) die("H2D failed");
+  k_dist_generic<int16_t><<<1, 128, 0, G.stream>>>(reinterpret_cast<const DistTask*>(reinterpret_cast<char*>(G.dstage) + task_off),
                                                    d_out, 1, dp->func, dp->bitDepth);
-  g.launches++;
+  G.launches++;
   uint32_t out = 0;
-  if (cudaMemcpyAsync(&out, d_out, sizeof(out), cudaMemcpyDeviceToHost, g.stream) != cudaSuccess ||
-      cudaStreamSynchronize(g.stream) != cudaSuccess) { g_err = cudaGetErrorString(cudaGetLastError()); die("kernel failed"); }
+  if (cudaMemcpyAsync(&out, d_out, sizeof(out), cudaMemcpyDeviceToHost, G.stream) != cudaSuccess ||
+      cudaStreamSynchronize(G.stream) != cudaSuccess) { g_err = cudaGetErrorString(cudaGetLastError()); die("kernel failed"); }
   return out;
 }
 
@@ -585,6 +693,8 @@ int hmb200_dist_batch(int func, int bit_depth, int n, const hmb200_dist_desc* de
     if (bps && bps != po->d.bytes_per_sample) return fail(HMB200_ERR_ARG, "hmb200_dist_batch: mixed sample sizes in one batch");
     bps = po->d.bytes_per_sample;
     if (d.w <= 0 || d.h <= 0 || d.w > 64 || d.h > 64) return fail(HMB200_ERR_ARG, "hmb200_dist_batch: block size out of range");
+    if (!box_inside(po->d, Box{d.org_x, d.org_y, d.org_x + d.w, d.org_y + d.h}) || !box_inside(pc->d, Box{d.cur_x, d.cur_y, d.cur_x + d.w, d.cur_y + d.h}))
+      return fail(HMB200_ERR_ARG, "hmb200_dist_batch: block " + std::to_string(i) + " leaves its padded plane");
     auto addr = [&](Plane* p, int x, int y) {
       return reinterpret_cast<char*>(p->d.base) + ((size_t)(y + p->d.margin_y) * p->d.pitch + (x + p->d.margin_x)) * bps;
     };
@@ -593,14 +703,14 @@ int hmb200_dist_batch(int func, int bit_depth, int n, const hmb200_dist_desc* de
   size_t tb = tasks.size() * sizeof(DistTask), ob = (size_t)n * sizeof(uint32_t);
   int rc;
   if ((rc = ensure_dstage(tb + ob)) != HMB200_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(g.dstage, tasks.data(), tb, cudaMemcpyHostToDevice, g.stream));
-  uint32_t* d_out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(g.dstage) + tb);
+  CUDA_TRY(cudaMemcpyAsync(G.dstage, tasks.data(), tb, cudaMemcpyHostToDevice, G.stream));
+  uint32_t* d_out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(G.dstage) + tb);
   int blocks = (n + 3) / 4;
-  if (bps == 1) k_dist_generic<uint8_t><<<blocks, 128, 0, g.stream>>>(reinterpret_cast<const DistTask*>(g.dstage), d_out, n, func, bit_depth);
-  else          k_dist_generic<int16_t><<<blocks, 128, 0, g.stream>>>(reinterpret_cast<const DistTask*>(g.dstage), d_out, n, func, bit_depth);
-  g.launches++;
-  CUDA_TRY(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  if (bps == 1) k_dist_generic<uint8_t><<<blocks, 128, 0, G.stream>>>(reinterpret_cast<const DistTask*>(G.dstage), d_out, n, func, bit_depth);
+  else          k_dist_generic<int16_t><<<blocks, 128, 0, G.stream>>>(reinterpret_cast<const DistTask*>(G.dstage), d_out, n, func, bit_depth);
+  G.launches++;
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, G.stream));
+  CUDA_TRY(cudaStreamSynchronize(G.stream));
   CUDA_TRY(cudaGetLastError());
   return HMB200_OK;
 }
@@ -618,29 +728,35 @@ int hmb200_mc_dist_batch(int cur_plane, int ref_plane, int func, int n, const hm
   for (int i = 0; i < n; i++) {
     const hmb200_mc_desc& d = descs[i];
     if (!supported_pu(d.w, d.h)) return fail(HMB200_ERR_ARG, "hmb200_mc_dist_batch: unsupported PU size in descriptor " + std::to_string(i));
+    {
+      const int ix = d.pu_x + (d.mv_x >> 2), iy = d.pu_y + (d.mv_y >> 2);
+      if (!box_inside(pc->d, Box{d.pu_x, d.pu_y, d.pu_x + d.w, d.pu_y + d.h}) ||
+          !box_inside(pr->d, Box{ix - FRAC_REACH, iy - FRAC_REACH, ix + d.w + FRAC_REACH, iy + d.h + FRAC_REACH}))
+        return fail(HMB200_ERR_ARG, "hmb200_mc_dist_batch: descriptor " + std::to_string(i) + " (PU or its motion-compensated block with the 8-tap reach) leaves the padded plane");
+    }
     tasks[i] = SearchTask{d.pu_x, d.pu_y, d.pu_x, d.pu_y, d.w, d.h, 0, 0, 0, 0, 0, 0, 0u, 0};
     mv[i] = hmb200_pu_result{0, 0, 0u, 0, 0, d.mv_x, d.mv_y, 0u};          // k_frac_tiles stage 2 reads the MV from qter_x / qter_y
   }
   FracSchedule fs;
   std::string why;
-  if (!frac_build_schedule(tasks, g.stream, &fs, &why)) return fail(HMB200_ERR_CUDA, why);
+  if (!frac_build_schedule(tasks, G.stream, &fs, &why)) return fail(HMB200_ERR_CUDA, why);
   const size_t tb = (size_t)n * sizeof(SearchTask), rb = (size_t)n * sizeof(hmb200_pu_result), ob = (size_t)n * sizeof(uint32_t);
   int rc = ensure_dstage(tb + rb + ob + 256);
   if (rc != HMB200_OK) { frac_free_schedule(&fs); return rc; }
-  char* base = reinterpret_cast<char*>(g.dstage);
+  char* base = reinterpret_cast<char*>(G.dstage);
   SearchTask* d_tasks = reinterpret_cast<SearchTask*>(base);
   hmb200_pu_result* d_mv = reinterpret_cast<hmb200_pu_result*>(base + ((tb + 63) & ~(size_t)63));
   uint32_t* d_out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d_mv) + ((rb + 63) & ~(size_t)63));
-  cudaError_t e = cudaMemcpyAsync(d_tasks, tasks.data(), tb, cudaMemcpyHostToDevice, g.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_mv, mv.data(), rb, cudaMemcpyHostToDevice, g.stream);
+  cudaError_t e = cudaMemcpyAsync(d_tasks, tasks.data(), tb, cudaMemcpyHostToDevice, G.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_mv, mv.data(), rb, cudaMemcpyHostToDevice, G.stream);
   int nl = -1;
   if (e == cudaSuccess) {
     const bool had = func == HMB200_DF_HADS;
-    nl = pr->d.bytes_per_sample == 1 ? mc_launch<uint8_t, uint8_t>(fs, d_tasks, d_mv, d_out, pc->d, pr->d, had, g.stream)
-                                     : mc_launch<int16_t, int16_t>(fs, d_tasks, d_mv, d_out, pc->d, pr->d, had, g.stream);
+    nl = pr->d.bytes_per_sample == 1 ? mc_launch<uint8_t, uint8_t>(fs, d_tasks, d_mv, d_out, pc->d, pr->d, had, G.stream)
+                                     : mc_launch<int16_t, int16_t>(fs, d_tasks, d_mv, d_out, pc->d, pr->d, had, G.stream);
   }
-  if (nl >= 0) { g.launches += (uint64_t)nl; e = cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, g.stream); }
-  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  if (nl >= 0) { G.launches += (uint64_t)nl; e = cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, G.stream); }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(G.stream);
   frac_free_schedule(&fs);
   if (nl < 0 || e != cudaSuccess) return fail(HMB200_ERR_CUDA, std::string("hmb200_mc_dist_batch: ") + cudaGetErrorString(cudaGetLastError()));
   return HMB200_OK;
@@ -667,7 +783,7 @@ static int intra_run(const DevPlane& org, int nblocks, const hmb200_intra_block*
                ub = up64(org_upload_bytes), outb = (size_t)nblocks * INTRA_MODES * sizeof(uint32_t);
   int rc = ensure_dstage(bb + ob + rb + ub + outb + 256);
   if (rc != HMB200_OK) return rc;
-  char* base = reinterpret_cast<char*>(g.dstage);
+  char* base = reinterpret_cast<char*>(G.dstage);
   IntraBlockDev* d_blocks = reinterpret_cast<IntraBlockDev*>(base);
   int32_t* d_ord = reinterpret_cast<int32_t*>(base + bb);
   int16_t* d_refs = reinterpret_cast<int16_t*>(base + bb + ob);
@@ -675,27 +791,27 @@ static int intra_run(const DevPlane& org, int nblocks, const hmb200_intra_block*
   uint32_t* d_out = reinterpret_cast<uint32_t*>(base + bb + ob + rb + ub);
   std::vector<int32_t> ord(ord8);
   ord.insert(ord.end(), ord4.begin(), ord4.end());
-  CUDA_TRY(cudaMemcpyAsync(d_blocks, hb.data(), hb.size() * sizeof(IntraBlockDev), cudaMemcpyHostToDevice, g.stream));
-  CUDA_TRY(cudaMemcpyAsync(d_ord, ord.data(), ord.size() * sizeof(int32_t), cudaMemcpyHostToDevice, g.stream));
-  CUDA_TRY(cudaMemcpyAsync(d_refs, refs, (size_t)n_ref_samples * 2, cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(d_blocks, hb.data(), hb.size() * sizeof(IntraBlockDev), cudaMemcpyHostToDevice, G.stream));
+  CUDA_TRY(cudaMemcpyAsync(d_ord, ord.data(), ord.size() * sizeof(int32_t), cudaMemcpyHostToDevice, G.stream));
+  CUDA_TRY(cudaMemcpyAsync(d_refs, refs, (size_t)n_ref_samples * 2, cudaMemcpyHostToDevice, G.stream));
   DevPlane pl = org;
   if (org_upload) {
-    CUDA_TRY(cudaMemcpyAsync(d_org, org_upload, org_upload_bytes, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(d_org, org_upload, org_upload_bytes, cudaMemcpyHostToDevice, G.stream));
     pl.base = d_org;
   }
   const int bd = pl.bit_depth;
   if (!ord8.empty()) {
-    if (pl.bytes_per_sample == 1) k_intra_modes_had<8, uint8_t><<<(int)ord8.size(), INTRA_THREADS, 0, g.stream>>>(d_blocks, d_ord, d_refs, d_out, pl, bd);
-    else                          k_intra_modes_had<8, int16_t><<<(int)ord8.size(), INTRA_THREADS, 0, g.stream>>>(d_blocks, d_ord, d_refs, d_out, pl, bd);
-    g.launches++;
+    if (pl.bytes_per_sample == 1) k_intra_modes_had<8, uint8_t><<<(int)ord8.size(), INTRA_THREADS, 0, G.stream>>>(d_blocks, d_ord, d_refs, d_out, pl, bd);
+    else                          k_intra_modes_had<8, int16_t><<<(int)ord8.size(), INTRA_THREADS, 0, G.stream>>>(d_blocks, d_ord, d_refs, d_out, pl, bd);
+    G.launches++;
   }
   if (!ord4.empty()) {
-    if (pl.bytes_per_sample == 1) k_intra_modes_had<4, uint8_t><<<(int)ord4.size(), INTRA_THREADS, 0, g.stream>>>(d_blocks, d_ord + ord8.size(), d_refs, d_out, pl, bd);
-    else                          k_intra_modes_had<4, int16_t><<<(int)ord4.size(), INTRA_THREADS, 0, g.stream>>>(d_blocks, d_ord + ord8.size(), d_refs, d_out, pl, bd);
-    g.launches++;
+    if (pl.bytes_per_sample == 1) k_intra_modes_had<4, uint8_t><<<(int)ord4.size(), INTRA_THREADS, 0, G.stream>>>(d_blocks, d_ord + ord8.size(), d_refs, d_out, pl, bd);
+    else                          k_intra_modes_had<4, int16_t><<<(int)ord4.size(), INTRA_THREADS, 0, G.stream>>>(d_blocks, d_ord + ord8.size(), d_refs, d_out, pl, bd);
+    G.launches++;
   }
-  CUDA_TRY(cudaMemcpyAsync(out, d_out, outb, cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, outb, cudaMemcpyDeviceToHost, G.stream));
+  CUDA_TRY(cudaStreamSynchronize(G.stream));
   CUDA_TRY(cudaGetLastError());
   return HMB200_OK;
 }
@@ -733,10 +849,11 @@ int hmb200_intra_modes_had(const int16_t* org, int org_stride, const int16_t* re
 // batched searches
 // ------------------------------------------------------------------------------------------------------------------
 hmb200_prepared* hmb200_prepare_jobs(const hmb200_pu_job* jobs, int njobs, int flags, int bit_depth) {
-  if (!g.ready) { fail(HMB200_ERR_STATE, "hmb200_init has not succeeded"); return nullptr; }
+  if (!G.ready) { fail(HMB200_ERR_STATE, "hmb200_init has not succeeded"); return nullptr; }
   if (njobs < 0 || (njobs > 0 && !jobs)) { fail(HMB200_ERR_ARG, "hmb200_prepare_jobs: bad arguments"); return nullptr; }
   auto* p = new hmb200_prepared();
-  p->n = njobs; p->flags = flags; p->bit_depth = bit_depth;
+  p->n = njobs; p->flags = flags; p->bit_depth = bit_depth; p->owner = &G;
+  const int reach = (flags & HMB200_FLAG_FRAC) ? FRAC_REACH : 0;
   p->tasks.resize((size_t)njobs);
   for (int i = 0; i < njobs; i++) {
     const hmb200_pu_job& j = jobs[i];
@@ -750,13 +867,15 @@ hmb200_prepared* hmb200_prepare_jobs(const hmb200_pu_job* jobs, int njobs, int f
     uint64_t nc = (uint64_t)(j.rb_x - j.lt_x + 1) * (uint64_t)(j.rb_y - j.lt_y + 1);
     p->cand_sads += nc;
     p->abs_diffs += nc * (uint64_t)j.w * (uint64_t)(j.h >> ss);
+    box_add(p->foot_org, j.pu_x, j.pu_y, j.pu_x + j.w, j.pu_y + j.h);
+    box_add(p->foot_ref, j.pu_x + j.lt_x - reach, j.pu_y + j.lt_y - reach, j.pu_x + j.rb_x + j.w + reach, j.pu_y + j.rb_y + j.h + reach);
   }
   if (njobs > 0) {
     if (cudaMalloc(&p->d_tasks, (size_t)njobs * sizeof(SearchTask)) != cudaSuccess ||
         cudaMalloc(&p->d_results, (size_t)njobs * sizeof(hmb200_pu_result)) != cudaSuccess ||
-        cudaMemcpyAsync(p->d_tasks, p->tasks.data(), (size_t)njobs * sizeof(SearchTask), cudaMemcpyHostToDevice, g.stream) != cudaSuccess ||
-        cudaMemsetAsync(p->d_results, 0, (size_t)njobs * sizeof(hmb200_pu_result), g.stream) != cudaSuccess ||
-        cudaStreamSynchronize(g.stream) != cudaSuccess) {
+        cudaMemcpyAsync(p->d_tasks, p->tasks.data(), (size_t)njobs * sizeof(SearchTask), cudaMemcpyHostToDevice, G.stream) != cudaSuccess ||
+        cudaMemsetAsync(p->d_results, 0, (size_t)njobs * sizeof(hmb200_pu_result), G.stream) != cudaSuccess ||
+        cudaStreamSynchronize(G.stream) != cudaSuccess) {
       fail(HMB200_ERR_CUDA, std::string("hmb200_prepare_jobs: ") + cudaGetErrorString(cudaGetLastError()));
       hmb200_free_prepared(p); return nullptr;
     }
@@ -767,12 +886,12 @@ hmb200_prepared* hmb200_prepare_jobs(const hmb200_pu_job* jobs, int njobs, int f
       std::vector<char> bundled;
       std::vector<CuBundleHost> hb;
       if (!getenv("HMB200_NO_CU_FUSION")) cu_extract_bundles(p->tasks, bps, bundled, hb);
-      if (!search8_build_schedule(p->tasks, bundled, g.sm_count, g.stream, &p->sched, &why, /*tiled=*/bps == 1) ||
-          !cu_build_schedule(p->tasks, hb, bps, bit_depth, g.sm_count, g.stream, &p->cu, &why)) {
+      if (!search8_build_schedule(p->tasks, bundled, G.sm_count, G.stream, &p->sched, &why, /*tiled=*/bps == 1) ||
+          !cu_build_schedule(p->tasks, hb, bps, bit_depth, G.sm_count, G.stream, &p->cu, &why)) {
         fail(HMB200_ERR_CUDA, why); hmb200_free_prepared(p); return nullptr;
       }
     }
-    if ((flags & HMB200_FLAG_FRAC) && !frac_build_schedule(p->tasks, g.stream, &p->frac, &why)) {
+    if ((flags & HMB200_FLAG_FRAC) && !frac_build_schedule(p->tasks, G.stream, &p->frac, &why)) {
       fail(HMB200_ERR_CUDA, why); hmb200_free_prepared(p); return nullptr;
     }
   }
@@ -781,7 +900,9 @@ hmb200_prepared* hmb200_prepare_jobs(const hmb200_pu_job* jobs, int njobs, int f
 
 void hmb200_free_prepared(hmb200_prepared* p) {
   if (!p) return;
-  if (g.ready) { cudaStreamSynchronize(g.stream); if (g.copy) cudaStreamSynchronize(g.copy); }
+  State& st = p->owner ? *p->owner : G;           // stream waits and frees work from any thread / current device
+  if (st.ready) { cudaStreamSynchronize(st.stream); if (st.copy) cudaStreamSynchronize(st.copy); }
+  if (p->d_packed) cudaFree(p->d_packed);
   if (p->ev_done) cudaEventDestroy(p->ev_done);
   if (p->ev_fetched) cudaEventDestroy(p->ev_fetched);
   if (p->d_tasks) cudaFree(p->d_tasks);
@@ -815,10 +936,20 @@ int hmb200_prepared_set_tz(hmb200_prepared* p, const hmb200_tz_extra* extra, int
   if (!p || !(p->flags & HMB200_FLAG_TZ)) return fail(HMB200_ERR_ARG, "hmb200_prepared_set_tz: the list was not prepared with HMB200_FLAG_TZ");
   if ((p->n > 0 && !extra) || pic_w <= 0 || pic_h <= 0 || max_cu <= 0 || search_range < 1 || search_range > 4096)
     return fail(HMB200_ERR_ARG, "hmb200_prepared_set_tz: bad arguments");
+  NEED_OWNER(p);
+  // xTZSearch also visits the zero vector, the clipped predictor / 2Nx2N integer MV and a raster range re-centred on them:
+  // all inside TComDataCU::clipMv's range for the owning CU
+  const int reach = (p->flags & HMB200_FLAG_FRAC) ? FRAC_REACH : 0;
+  for (int i = 0; i < p->n; i++) {
+    const SearchTask& t = p->tasks[(size_t)i];
+    const int xmin = std::min(0, -max_cu - 8 - extra[i].cu_x + 1), xmax = std::max(0, pic_w + 8 - extra[i].cu_x - 1);
+    const int ymin = std::min(0, -max_cu - 8 - extra[i].cu_y + 1), ymax = std::max(0, pic_h + 8 - extra[i].cu_y - 1);
+    box_add(p->foot_ref, t.ref_x + xmin - reach, t.ref_y + ymin - reach, t.ref_x + xmax + t.w + reach, t.ref_y + ymax + t.h + reach);
+  }
   if (p->n > 0) {
     if (!p->d_tz) CUDA_TRY(cudaMalloc((void**)&p->d_tz, (size_t)p->n * sizeof(hmb200_tz_extra)));
-    CUDA_TRY(cudaMemcpyAsync(p->d_tz, extra, (size_t)p->n * sizeof(hmb200_tz_extra), cudaMemcpyHostToDevice, g.stream));
-    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_tz, extra, (size_t)p->n * sizeof(hmb200_tz_extra), cudaMemcpyHostToDevice, G.stream));
+    CUDA_TRY(cudaStreamSynchronize(G.stream));
   }
   p->tz = TzParams{pic_w, pic_h, max_cu, search_range, (p->flags & HMB200_FLAG_TZ_STOP) ? 1 : 0};
   return HMB200_OK;
@@ -846,15 +977,24 @@ int hmb200_prepared_executed_work(const hmb200_prepared* p, uint64_t* abs_diffs_
   return HMB200_OK;
 }
 
+int hmb200_prepared_unique_work(const hmb200_prepared* p, uint64_t* abs_diffs_unique) {
+  if (!p) return fail(HMB200_ERR_ARG, "null handle");
+  if (abs_diffs_unique) *abs_diffs_unique = p->sched.unique_abs_diffs + p->cu.unique_abs_diffs;
+  return HMB200_OK;
+}
+
 int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
   NEED_READY();
   if (!p) return fail(HMB200_ERR_ARG, "null handle");
   Plane* pc = get_plane(cur_plane); Plane* pr = get_plane(ref_plane);
   if (!pc || !pr) return fail(HMB200_ERR_ARG, "hmb200_run_prepared: unknown plane");
   if (pr->d.bit_depth != p->bit_depth) return fail(HMB200_ERR_ARG, "hmb200_run_prepared: bit depth differs from prepare_jobs");
+  NEED_OWNER(p);
   if (p->n == 0) return HMB200_OK;
-  if (p->fetch_pending) CUDA_TRY(cudaStreamWaitEvent(g.stream, p->ev_fetched, 0));     // the results of the previous run are still being copied out
-  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  if (!box_inside(pr->d, p->foot_ref)) return fail(HMB200_ERR_ARG, "hmb200_run_prepared: a search window (plus the interpolation reach) leaves the padded reference plane");
+  if (!box_inside(pc->d, p->foot_org)) return fail(HMB200_ERR_ARG, "hmb200_run_prepared: a PU leaves the padded current plane");
+  if (p->fetch_pending) CUDA_TRY(cudaStreamWaitEvent(G.stream, p->ev_fetched, 0));     // the results of the previous run are still being copied out
+  CUDA_TRY(cudaEventRecord(G.ev[0], G.stream));
   const Search8Schedule& sc = p->sched;
   const CuSchedule& cu = p->cu;
   const int bps = pr->d.bytes_per_sample;
@@ -862,14 +1002,14 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
     if (!p->d_tz) return fail(HMB200_ERR_STATE, "hmb200_run_prepared: HMB200_FLAG_TZ list without hmb200_prepared_set_tz");
     if (pc->d.bytes_per_sample != bps) return fail(HMB200_ERR_ARG, "hmb200_run_prepared: TZ search needs planes of one sample size");
     const int blocks = (p->n + TZ_WARPS - 1) / TZ_WARPS;
-    if (bps == 1) k_tz_search<uint8_t, uint8_t><<<blocks, TZ_WARPS * 32, 0, g.stream>>>(p->d_tasks, p->d_tz, p->d_results, p->n, pc->d, pr->d, p->tz);
-    else          k_tz_search<int16_t, int16_t><<<blocks, TZ_WARPS * 32, 0, g.stream>>>(p->d_tasks, p->d_tz, p->d_results, p->n, pc->d, pr->d, p->tz);
-    g.launches++;
+    if (bps == 1) k_tz_search<uint8_t, uint8_t><<<blocks, TZ_WARPS * 32, 0, G.stream>>>(p->d_tasks, p->d_tz, p->d_results, p->n, pc->d, pr->d, p->tz);
+    else          k_tz_search<int16_t, int16_t><<<blocks, TZ_WARPS * 32, 0, G.stream>>>(p->d_tasks, p->d_tz, p->d_results, p->n, pc->d, pr->d, p->tz);
+    G.launches++;
   }
   bool fast = !(p->flags & HMB200_FLAG_TZ) && pc->d.bytes_per_sample == bps && ((bps == 1 && (sc.n_jobs > 0 || cu.n_bundles > 0)) || (bps == 2 && cu.n_bundles > 0)) &&
               cu.bps == bps && pc->d.margin_x % 16 == 0 && pr->d.margin_x % 16 == 0 && sc.d_keys != nullptr;
   if (fast) {
-    // every staged byte must lie inside the padded buffers (the reference would read outside its planes too)
+    // the staged boxes are the footprints rounded out to 16 bytes: the round-up may reach into the row padding (pitch), never past it
     auto inside = [](const DevPlane& d, int x0, int y0, int x1, int y1) {
       return x0 + d.margin_x >= 0 && x1 + d.margin_x <= d.pitch && y0 + d.margin_y >= 0 && y1 + d.margin_y <= d.height + 2 * d.margin_y;
     };
@@ -879,73 +1019,76 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
     if ((sc.n_jobs > 0 && !inside(pc->d, sc.omin_x, sc.omin_y, sc.omax_x, sc.omax_y)) ||
         (cu.n_bundles > 0 && !inside(pc->d, cu.obox.x0, cu.obox.y0, cu.obox.x1, cu.obox.y1)))
       return fail(HMB200_ERR_ARG, "hmb200_run_prepared: a PU leaves the padded current plane");
-    CUDA_TRY(cudaMemsetAsync(sc.d_keys, 0xff, (size_t)sc.n_tasks * sizeof(unsigned long long), g.stream));
+    CUDA_TRY(cudaMemsetAsync(sc.d_keys, 0xff, (size_t)sc.n_tasks * sizeof(unsigned long long), G.stream));
     // one launch per tile variant present, spread over side streams so that their tails overlap
     const S8Kernel* kern = search8_kernels();
     const S8CuKernel* cukern = bps == 1 ? search8_cu_kernels() : search16_cu_kernels();
-    CUDA_TRY(cudaEventRecord(g.ev_fork, g.stream));
+    CUDA_TRY(cudaEventRecord(G.ev_fork, G.stream));
     int order[S8V_COUNT + CUV_COUNT], used = 0;       // >= 0: per-PU variant, < 0: CU-fused variant ~v
-    if (bps == 1) { for (int v = 0; v < CUV_COUNT; v++) if (cu.unit_count[v] > 0) order[used++] = ~v; }       // longest CTAs first: 8x8 CUs
-    else for (int v = CUV_COUNT - 1; v >= 0; v--) if (cu.unit_count[v] > 0) order[used++] = ~v;
+    if (bps == 1) {                                   // longest CTAs first: 16x16 CUs with their children, then 8x8 CUs
+      for (int v = CUV_BASE_COUNT; v < CUV_COUNT; v++) if (cu.unit_count[v] > 0) order[used++] = ~v;
+      for (int v = 0; v < CUV_BASE_COUNT; v++) if (cu.unit_count[v] > 0) order[used++] = ~v;
+    } else for (int v = CUV_BASE_COUNT - 1; v >= 0; v--) if (cu.unit_count[v] > 0) order[used++] = ~v;
     for (int v = S8V_COUNT - 1; v >= 0; v--) if (sc.unit_count[v] > 0) order[used++] = v;     // wide tiles first
     for (int k = 0; k < used; k++) {
       const int v = order[k];
-      cudaStream_t st = (k == 0) ? g.stream : g.side[(k - 1) % N_SIDE];
-      if (k >= 1 && k <= N_SIDE) CUDA_TRY(cudaStreamWaitEvent(st, g.ev_fork, 0));
+      cudaStream_t st = (k == 0) ? G.stream : G.side[(k - 1) % N_SIDE];
+      if (k >= 1 && k <= N_SIDE) CUDA_TRY(cudaStreamWaitEvent(st, G.ev_fork, 0));
       if (v >= 0)
         kern[v]<<<sc.unit_count[v], S8_THREADS, sc.smem_of[v], st>>>(sc.d_units + sc.unit_first[v], sc.d_jobs, sc.d_keys, pc->d, pr->d);
       else
         cukern[~v]<<<cu.unit_count[~v], bps == 1 ? CU8_THREADS : S8_THREADS, cu.smem_of[~v], st>>>(cu.d_units + cu.unit_first[~v], cu.d_bundles, sc.d_keys, pc->d, pr->d);
-      g.launches++;
+      G.launches++;
     }
     for (int k = 0; k < N_SIDE && k + 1 < used; k++) {
-      CUDA_TRY(cudaEventRecord(g.ev_join[k], g.side[k]));
-      CUDA_TRY(cudaStreamWaitEvent(g.stream, g.ev_join[k], 0));
+      CUDA_TRY(cudaEventRecord(G.ev_join[k], G.side[k]));
+      CUDA_TRY(cudaStreamWaitEvent(G.stream, G.ev_join[k], 0));
     }
     if (sc.n_leftover > 0) {    // shapes / windows the tiled kernels do not cover
-      if (bps == 1) k_search_generic<uint8_t, uint8_t><<<sc.n_leftover, 256, 0, g.stream>>>(p->d_tasks, p->d_results, pc->d, pr->d, sc.d_leftover);
-      else          k_search_generic<int16_t, int16_t><<<sc.n_leftover, 256, 0, g.stream>>>(p->d_tasks, p->d_results, pc->d, pr->d, sc.d_leftover);
-      g.launches++;
+      if (bps == 1) k_search_generic<uint8_t, uint8_t><<<sc.n_leftover, 256, 0, G.stream>>>(p->d_tasks, p->d_results, pc->d, pr->d, sc.d_leftover);
+      else          k_search_generic<int16_t, int16_t><<<sc.n_leftover, 256, 0, G.stream>>>(p->d_tasks, p->d_results, pc->d, pr->d, sc.d_leftover);
+      G.launches++;
     }
-    k_search8_finalize<<<(sc.n_tasks + 255) / 256, 256, 0, g.stream>>>(p->d_tasks, sc.d_keys, p->d_results, sc.n_tasks);
-    g.launches++;
+    k_search8_finalize<<<(sc.n_tasks + 255) / 256, 256, 0, G.stream>>>(p->d_tasks, sc.d_keys, p->d_results, sc.n_tasks);
+    G.launches++;
   } else if (!(p->flags & HMB200_FLAG_TZ)) {
     dispatch_generic(p->d_tasks, p->d_results, p->n, pc->d, pr->d, p->flags & ~HMB200_FLAG_FRAC, /*do_search=*/true, nullptr);
   }
-  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  CUDA_TRY(cudaEventRecord(G.ev[1], G.stream));
   if (p->flags & HMB200_FLAG_FRAC) {
     const bool had = (p->flags & HMB200_FLAG_HADME) != 0;
     int nl;
     if (pc->d.bytes_per_sample == 1 && pr->d.bytes_per_sample == 1)
-      nl = frac_launch<uint8_t, uint8_t>(p->frac, p->d_tasks, p->d_results, pc->d, pr->d, had, g.stream);
+      nl = frac_launch<uint8_t, uint8_t>(p->frac, p->d_tasks, p->d_results, pc->d, pr->d, had, G.stream);
     else if (pc->d.bytes_per_sample == 2 && pr->d.bytes_per_sample == 2)
-      nl = frac_launch<int16_t, int16_t>(p->frac, p->d_tasks, p->d_results, pc->d, pr->d, had, g.stream);
+      nl = frac_launch<int16_t, int16_t>(p->frac, p->d_tasks, p->d_results, pc->d, pr->d, had, G.stream);
     else { dispatch_generic(p->d_tasks, p->d_results, p->n, pc->d, pr->d, p->flags, /*do_search=*/false, nullptr); nl = 0; }
     if (nl < 0) return fail(HMB200_ERR_CUDA, std::string("frac_launch: ") + cudaGetErrorString(cudaGetLastError()));
-    g.launches += (uint64_t)nl;
+    G.launches += (uint64_t)nl;
   }
-  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaEventRecord(G.ev[2], G.stream));
   if (!p->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventRecord(p->ev_done, g.stream));
+  CUDA_TRY(cudaEventRecord(p->ev_done, G.stream));
   CUDA_TRY(cudaGetLastError());
   return HMB200_OK;
 }
 
 int hmb200_last_timing(float* total_ms, float* search_ms, float* frac_ms) {
   NEED_READY();
-  CUDA_TRY(cudaEventSynchronize(g.ev[2]));
-  CUDA_TRY(cudaEventElapsedTime(&g.last_total_ms, g.ev[0], g.ev[2]));
-  CUDA_TRY(cudaEventElapsedTime(&g.last_search_ms, g.ev[0], g.ev[1]));
-  CUDA_TRY(cudaEventElapsedTime(&g.last_frac_ms, g.ev[1], g.ev[2]));
-  if (total_ms) *total_ms = g.last_total_ms;
-  if (search_ms) *search_ms = g.last_search_ms;
-  if (frac_ms) *frac_ms = g.last_frac_ms;
+  CUDA_TRY(cudaEventSynchronize(G.ev[2]));
+  CUDA_TRY(cudaEventElapsedTime(&G.last_total_ms, G.ev[0], G.ev[2]));
+  CUDA_TRY(cudaEventElapsedTime(&G.last_search_ms, G.ev[0], G.ev[1]));
+  CUDA_TRY(cudaEventElapsedTime(&G.last_frac_ms, G.ev[1], G.ev[2]));
+  if (total_ms) *total_ms = G.last_total_ms;
+  if (search_ms) *search_ms = G.last_search_ms;
+  if (frac_ms) *frac_ms = G.last_frac_ms;
   return HMB200_OK;
 }
 
 int hmb200_fetch_results_async(hmb200_prepared* p, hmb200_pu_result* results) {
   NEED_READY();
   if (!p || (p->n > 0 && !results)) return fail(HMB200_ERR_ARG, "hmb200_fetch_results_async: bad arguments");
+  NEED_OWNER(p);
   if (p->n == 0) return HMB200_OK;
   if (!p->ev_done) return fail(HMB200_ERR_STATE, "hmb200_fetch_results_async: nothing has run on this handle");
   cudaPointerAttributes attr;
@@ -953,9 +1096,31 @@ int hmb200_fetch_results_async(hmb200_prepared* p, hmb200_pu_result* results) {
   cudaGetLastError();
   if (!pinned) return fail(HMB200_ERR_ARG, "hmb200_fetch_results_async: results must come from hmb200_host_alloc (page-locked)");
   if (!p->ev_fetched) CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fetched, cudaEventDisableTiming));
-  CUDA_TRY(cudaStreamWaitEvent(g.copy, p->ev_done, 0));
-  CUDA_TRY(cudaMemcpyAsync(results, p->d_results, (size_t)p->n * sizeof(hmb200_pu_result), cudaMemcpyDeviceToHost, g.copy));
-  CUDA_TRY(cudaEventRecord(p->ev_fetched, g.copy));
+  CUDA_TRY(cudaStreamWaitEvent(G.copy, p->ev_done, 0));
+  CUDA_TRY(cudaMemcpyAsync(results, p->d_results, (size_t)p->n * sizeof(hmb200_pu_result), cudaMemcpyDeviceToHost, G.copy));
+  CUDA_TRY(cudaEventRecord(p->ev_fetched, G.copy));
+  p->fetch_pending = true;
+  return HMB200_OK;
+}
+
+int hmb200_fetch_results16_async(hmb200_prepared* p, hmb200_pu_result16* results) {
+  NEED_READY();
+  if (!p || (p->n > 0 && !results)) return fail(HMB200_ERR_ARG, "hmb200_fetch_results16_async: bad arguments");
+  NEED_OWNER(p);
+  if (p->n == 0) return HMB200_OK;
+  if (!p->ev_done) return fail(HMB200_ERR_STATE, "hmb200_fetch_results16_async: nothing has run on this handle");
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, results) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (!pinned) return fail(HMB200_ERR_ARG, "hmb200_fetch_results16_async: results must come from hmb200_host_alloc (page-locked)");
+  if (!p->d_packed) CUDA_TRY(cudaMalloc((void**)&p->d_packed, (size_t)p->n * sizeof(hmb200_pu_result16)));
+  if (!p->ev_fetched) CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fetched, cudaEventDisableTiming));
+  // pack on the copy stream behind the run: the compute stream goes on with the next frame pair
+  CUDA_TRY(cudaStreamWaitEvent(G.copy, p->ev_done, 0));
+  k_pack_results16<<<(p->n + 255) / 256, 256, 0, G.copy>>>(p->d_results, p->d_packed, p->n);
+  G.launches++;
+  CUDA_TRY(cudaMemcpyAsync(results, p->d_packed, (size_t)p->n * sizeof(hmb200_pu_result16), cudaMemcpyDeviceToHost, G.copy));
+  CUDA_TRY(cudaEventRecord(p->ev_fetched, G.copy));
   p->fetch_pending = true;
   return HMB200_OK;
 }
@@ -970,6 +1135,7 @@ int hmb200_fetch_wait(hmb200_prepared* p) {
 int hmb200_fetch_results(hmb200_prepared* p, hmb200_pu_result* results) {
   NEED_READY();
   if (!p || (p->n > 0 && !results)) return fail(HMB200_ERR_ARG, "hmb200_fetch_results: bad arguments");
+  NEED_OWNER(p);
   if (p->n == 0) return HMB200_OK;
   if (p->fetch_pending) { CUDA_TRY(cudaEventSynchronize(p->ev_fetched)); p->fetch_pending = false; }
   const size_t bytes = (size_t)p->n * sizeof(hmb200_pu_result);
@@ -977,17 +1143,17 @@ int hmb200_fetch_results(hmb200_prepared* p, hmb200_pu_result* results) {
   const bool user_pinned = cudaPointerGetAttributes(&attr, results) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();                                                                              // clear the "not registered" status
   if (user_pinned) {                                                                               // hmb200_host_alloc'ed: straight D2H
-    CUDA_TRY(cudaMemcpyAsync(results, p->d_results, bytes, cudaMemcpyDeviceToHost, g.stream));
-    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    CUDA_TRY(cudaMemcpyAsync(results, p->d_results, bytes, cudaMemcpyDeviceToHost, G.stream));
+    CUDA_TRY(cudaStreamSynchronize(G.stream));
     CUDA_TRY(cudaGetLastError());
     return HMB200_OK;
   }
   int rc = ensure_pinned(bytes);
   if (rc != HMB200_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(g.pinned, p->d_results, bytes, cudaMemcpyDeviceToHost, g.stream));    // pinned staging: full PCIe rate
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaMemcpyAsync(G.pinned, p->d_results, bytes, cudaMemcpyDeviceToHost, G.stream));    // pinned staging: full PCIe rate
+  CUDA_TRY(cudaStreamSynchronize(G.stream));
   CUDA_TRY(cudaGetLastError());
-  memcpy(results, g.pinned, bytes);
+  memcpy(results, G.pinned, bytes);
   return HMB200_OK;
 }
 
@@ -1019,11 +1185,11 @@ static int upload_pattern(const hmb200_pattern* key) {
   if (!key || !key->roi || !supported_pu(key->width, key->height)) return fail(HMB200_ERR_ARG, "unsupported pattern");
   int rc = ensure_pinned(64 * 64 * sizeof(int16_t));
   if (rc != HMB200_OK) return rc;
-  int16_t* pin = reinterpret_cast<int16_t*>(g.pinned);
+  int16_t* pin = reinterpret_cast<int16_t*>(G.pinned);
   for (int y = 0; y < key->height; y++)
     memcpy(pin + (size_t)y * key->width, key->roi + (ptrdiff_t)y * key->stride, (size_t)key->width * sizeof(int16_t));
-  CUDA_TRY(cudaMemcpy2DAsync(g.pattern.d.base, (size_t)g.pattern.d.pitch * sizeof(int16_t), pin, (size_t)key->width * sizeof(int16_t),
-                             (size_t)key->width * sizeof(int16_t), key->height, cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaMemcpy2DAsync(G.pattern.d.base, (size_t)G.pattern.d.pitch * sizeof(int16_t), pin, (size_t)key->width * sizeof(int16_t),
+                             (size_t)key->width * sizeof(int16_t), key->height, cudaMemcpyHostToDevice, G.stream));
   return HMB200_OK;
 }
 
@@ -1037,27 +1203,33 @@ static int run_single(const hmb200_pattern* key, const int16_t* ref_at_pu, const
   if (rc != HMB200_OK) return rc;
   SearchTask t = proto;
   t.org_x = 0; t.org_y = 0; t.ref_x = rx; t.ref_y = ry; t.w = key->width; t.h = key->height;
+  {
+    const int reach = (flags & HMB200_FLAG_FRAC) ? FRAC_REACH : 0;
+    const Box b = do_search ? Box{rx + t.lt_x - reach, ry + t.lt_y - reach, rx + t.rb_x + t.w + reach, ry + t.rb_y + t.h + reach}
+                            : Box{rx + io->mv_x - reach, ry + io->mv_y - reach, rx + io->mv_x + t.w + reach, ry + io->mv_y + t.h + reach};
+    if (!box_inside(pr->d, b)) return fail(HMB200_ERR_ARG, "the search window / refinement block leaves the padded reference plane");
+  }
   size_t need = sizeof(SearchTask) + sizeof(hmb200_pu_result) + 128;
   if ((rc = ensure_dstage(need)) != HMB200_OK) return rc;
-  SearchTask* d_t = reinterpret_cast<SearchTask*>(g.dstage);
-  hmb200_pu_result* d_r = reinterpret_cast<hmb200_pu_result*>(reinterpret_cast<char*>(g.dstage) + 64);
-  unsigned long long* d_key = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(g.dstage) + 64 + sizeof(hmb200_pu_result));
-  CUDA_TRY(cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, g.stream));
-  CUDA_TRY(cudaMemcpyAsync(d_r, io, sizeof(*io), cudaMemcpyHostToDevice, g.stream));
+  SearchTask* d_t = reinterpret_cast<SearchTask*>(G.dstage);
+  hmb200_pu_result* d_r = reinterpret_cast<hmb200_pu_result*>(reinterpret_cast<char*>(G.dstage) + 64);
+  unsigned long long* d_key = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(G.dstage) + 64 + sizeof(hmb200_pu_result));
+  CUDA_TRY(cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, G.stream));
+  CUDA_TRY(cudaMemcpyAsync(d_r, io, sizeof(*io), cudaMemcpyHostToDevice, G.stream));
   if (do_search) {
     // one PU: spread its candidates over the whole GPU (one CTA per ~256 candidates), fold with atomicMin, decode
     const long long total = (long long)(t.rb_x - t.lt_x + 1) * (t.rb_y - t.lt_y + 1);
-    const int splits = (int)std::max<long long>(1, std::min<long long>(4 * g.sm_count, (total + 255) / 256));
-    CUDA_TRY(cudaMemsetAsync(d_key, 0xff, sizeof(unsigned long long), g.stream));
+    const int splits = (int)std::max<long long>(1, std::min<long long>(4 * G.sm_count, (total + 255) / 256));
+    CUDA_TRY(cudaMemsetAsync(d_key, 0xff, sizeof(unsigned long long), G.stream));
     const dim3 grid(1, splits);
-    if (pr->d.bytes_per_sample == 1) k_search_split<uint8_t, int16_t><<<grid, 256, 0, g.stream>>>(d_t, d_key, g.pattern.d, pr->d);
-    else                             k_search_split<int16_t, int16_t><<<grid, 256, 0, g.stream>>>(d_t, d_key, g.pattern.d, pr->d);
-    k_search8_finalize<<<1, 32, 0, g.stream>>>(d_t, d_key, d_r, 1);
-    g.launches += 2;
+    if (pr->d.bytes_per_sample == 1) k_search_split<uint8_t, int16_t><<<grid, 256, 0, G.stream>>>(d_t, d_key, G.pattern.d, pr->d);
+    else                             k_search_split<int16_t, int16_t><<<grid, 256, 0, G.stream>>>(d_t, d_key, G.pattern.d, pr->d);
+    k_search8_finalize<<<1, 32, 0, G.stream>>>(d_t, d_key, d_r, 1);
+    G.launches += 2;
   }
-  dispatch_generic(d_t, d_r, 1, g.pattern.d, pr->d, flags, /*do_search=*/false, nullptr);
-  CUDA_TRY(cudaMemcpyAsync(io, d_r, sizeof(*io), cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  dispatch_generic(d_t, d_r, 1, G.pattern.d, pr->d, flags, /*do_search=*/false, nullptr);
+  CUDA_TRY(cudaMemcpyAsync(io, d_r, sizeof(*io), cudaMemcpyDeviceToHost, G.stream));
+  CUDA_TRY(cudaStreamSynchronize(G.stream));
   CUDA_TRY(cudaGetLastError());
   return HMB200_OK;
 }
@@ -1094,20 +1266,26 @@ int hmb200_pattern_search_tz(const hmb200_pattern* key, const int16_t* ref_at_pu
   SearchTask t{};
   t.org_x = 0; t.org_y = 0; t.ref_x = rx; t.ref_y = ry; t.w = key->width; t.h = key->height;
   t.lt_x = lt.x; t.lt_y = lt.y; t.rb_x = rb.x; t.rb_y = rb.y; t.pred_x = cs->pred.x; t.pred_y = cs->pred.y;
+  {
+    const int xmin = std::min(std::min(0, lt.x), -max_cu - 8 - extra->cu_x + 1), xmax = std::max(std::max(0, rb.x), pic_w + 8 - extra->cu_x - 1);
+    const int ymin = std::min(std::min(0, lt.y), -max_cu - 8 - extra->cu_y + 1), ymax = std::max(std::max(0, rb.y), pic_h + 8 - extra->cu_y - 1);
+    if (!box_inside(pr->d, Box{rx + xmin, ry + ymin, rx + xmax + t.w, ry + ymax + t.h}))
+      return fail(HMB200_ERR_ARG, "hmb200_pattern_search_tz: the clipped search range leaves the padded reference plane");
+  }
   t.lambda_cost = cs->lambda_cost;
   t.sub_shift = ((flags & HMB200_FLAG_FEN) && key->height > 8) ? 1 : 0;
   // one staging record: [SearchTask | tz_extra | result]
   struct Rec { SearchTask t; hmb200_tz_extra e; hmb200_pu_result r; } rec{t, *extra, hmb200_pu_result{}};
   if ((rc = ensure_dstage(sizeof(Rec) + 64)) != HMB200_OK) return rc;
-  Rec* d = reinterpret_cast<Rec*>(g.dstage);
-  CUDA_TRY(cudaMemcpyAsync(d, &rec, sizeof(rec), cudaMemcpyHostToDevice, g.stream));
+  Rec* d = reinterpret_cast<Rec*>(G.dstage);
+  CUDA_TRY(cudaMemcpyAsync(d, &rec, sizeof(rec), cudaMemcpyHostToDevice, G.stream));
   const TzParams P{pic_w, pic_h, max_cu, search_range, (flags & HMB200_FLAG_TZ_STOP) ? 1 : 0};
-  if (pr->d.bytes_per_sample == 1) k_tz_search<uint8_t, int16_t><<<1, TZ_WARPS * 32, 0, g.stream>>>(&d->t, &d->e, &d->r, 1, g.pattern.d, pr->d, P);
-  else                             k_tz_search<int16_t, int16_t><<<1, TZ_WARPS * 32, 0, g.stream>>>(&d->t, &d->e, &d->r, 1, g.pattern.d, pr->d, P);
-  g.launches++;
+  if (pr->d.bytes_per_sample == 1) k_tz_search<uint8_t, int16_t><<<1, TZ_WARPS * 32, 0, G.stream>>>(&d->t, &d->e, &d->r, 1, G.pattern.d, pr->d, P);
+  else                             k_tz_search<int16_t, int16_t><<<1, TZ_WARPS * 32, 0, G.stream>>>(&d->t, &d->e, &d->r, 1, G.pattern.d, pr->d, P);
+  G.launches++;
   hmb200_pu_result r{};
-  CUDA_TRY(cudaMemcpyAsync(&r, &d->r, sizeof(r), cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaMemcpyAsync(&r, &d->r, sizeof(r), cudaMemcpyDeviceToHost, G.stream));
+  CUDA_TRY(cudaStreamSynchronize(G.stream));
   CUDA_TRY(cudaGetLastError());
   mv_out->x = r.mv_x; mv_out->y = r.mv_y; *sad_out = r.sad;
   return HMB200_OK;

@@ -391,14 +391,14 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
 
 typedef void (*S16CuKernel)(const S8Unit*, const S8Bundle*, unsigned long long*, DevPlane, DevPlane);
 inline const S16CuKernel* search16_cu_kernels() {
-  static const S16CuKernel table[CUV_COUNT] = { k_search16_cu<8, false>, k_search16_cu<16, false>, k_search16_cu<16, true>,
+  static const S16CuKernel table[CUV_BASE_COUNT] = { k_search16_cu<8, false>, k_search16_cu<16, false>, k_search16_cu<16, true>,
                                                 k_search16_cu<32, false>, k_search16_cu<32, true>, k_search16_cu<64, false>,
                                                 k_search16_cu<64, true> };
   return table;
 }
 inline int cu16_configure(std::string* err) {
   const S16CuKernel* k = search16_cu_kernels();
-  for (int v = 0; v < CUV_COUNT; v++) {
+  for (int v = 0; v < CUV_BASE_COUNT; v++) {
     cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k[v]), cudaFuncAttributeMaxDynamicSharedMemorySize, S8_SMEM_MAX);
     if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(k_search16_cu): ") + cudaGetErrorString(e); return HMB200_ERR_CUDA; }
   }

@@ -420,6 +420,7 @@ struct Search8Schedule {
   unsigned long long* d_keys = nullptr;
   int n_tasks = 0;
   unsigned long long executed_abs_diffs = 0;     // byte abs-diffs the per-PU tiles execute (== algorithmic for these)
+  unsigned long long unique_abs_diffs = 0;       // same thing: a PU searched alone shares nothing
   int unit_first[S8V_COUNT] = {0}, unit_count[S8V_COUNT] = {0};   // units are bucketed by tile variant
   int smem_of[S8V_COUNT] = {0};
   // footprint of the scheduled jobs in picture coordinates (validated against the planes at run time)
@@ -558,6 +559,7 @@ inline bool search8_build_schedule(const std::vector<SearchTask>& tasks, const s
       j.item_start = item;
       item += j.n_items;
       out->executed_abs_diffs += (unsigned long long)j.nx * j.ny * (unsigned long long)(4 * j.ww * j.hn);
+      out->unique_abs_diffs += (unsigned long long)j.nx * j.ny * (unsigned long long)(4 * j.ww * j.hn);
       const long long c = (long long)(j.ww * j.hn + 6) * j.ky;
       job_item_cost.push_back(c);
       gi[gidx].cost += c * j.n_items;

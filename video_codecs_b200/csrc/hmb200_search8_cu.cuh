@@ -24,18 +24,23 @@
 namespace hmb200 {
 
 constexpr int CU_SLOTS = 13;
+// A 16x16 CU whose four 8x8 child CUs share its window, predictor and lambda carries their PUs along (CHILD kernels):
+// 4 children x (8x8, 8x4 top, 8x4 bottom, 4x8 left, 4x8 right)
+constexpr int CU_CHILD_SLOTS = 20;
+constexpr int CU_SLOTS_ALL = CU_SLOTS + CU_CHILD_SLOTS;
 // 8-bit CU-fused kernels: ONE CTA of 16 warps per SM, because the window is staged four times (byte phases 0..3, see
 // cu_load_ref): 4 x 37 KB for a CTU at +-64.  The 16-bit kernels keep two CTAs of 8 warps.
 constexpr int CU8_THREADS = 512;
 constexpr int CU8_WARPS = CU8_THREADS / 32;
 constexpr int CU_PX_BLOCKS = 16;             // windows up to 256 columns keep their per-column MV-cost terms in shared memory
 
-struct S8Bundle {             // 128 bytes
+struct S8Bundle {             // 256 bytes; the 16-bit kernels read the first 128 only
   int32_t org_off, win_off;   // byte offsets of the CU's top-left sample / of candidate (lt_x, lt_y) in the staged tiles
   int32_t nx, ny;
   int32_t lt_x, lt_y, pred_x, pred_y;
   uint32_t lambda;
-  int32_t n_blk;              // 16-column blocks per candidate row: ceil((xal + nx) / 16) for 8-bit planes, ceil(nx / 8) for 16-bit
+  int32_t n_blk;              // blocks per candidate row that run as block items: ceil((xal + nx) / 16) for 8-bit planes (one less when
+                              // the last column runs as edge items), ceil(nx / 8) for 16-bit
   int32_t item_start, n_items;
   int32_t out_idx[CU_SLOTS];  // task index per partition slot (-1: that PU is not in the job list)
   int32_t n_rowgroups;        // ceil(ny / KY)
@@ -45,7 +50,14 @@ struct S8Bundle {             // 128 bytes
                               // aligned in shared memory; columns of the first / last block outside the window are masked)
   int32_t step_g, step_blk;   // (quads per item step) / n_blk and % n_blk: how far a quad moves per item step
   int32_t rank_bits;          // 8x8 CUs (four candidate rows per tile): bits that number a lane's tiles inside one row group
+  // ---- 8-bit kernels only ----
+  int32_t child_idx[CU_CHILD_SLOTS];   // CHILD kernels: task index per PU of the four 8x8 child CUs (-1: not in the job list)
+  int32_t n_main;             // block items; the items behind them (n_items - n_main) are edge items
+  int32_t edge;               // 1: (xal + nx) % 16 == 1, i.e. the window's last column would be a block of its own with 15 of 16
+                              // columns masked (129 = 8 * 16 + 1): it runs as edge items instead, a lane per candidate row
+  int32_t pad_[10];
 };
+static_assert(sizeof(S8Bundle) == 256, "S8Bundle is loaded as 64 ints per warp");
 
 // partition slots: 0 2Nx2N | 1,2 2NxN top,bottom | 3,4 Nx2N left,right | 5,6 2NxnU | 7,8 2NxnD | 9,10 nLx2N | 11,12 nRx2N
 __host__ __device__ constexpr int cu_slot_h(int S, int slot) {
@@ -111,32 +123,34 @@ __device__ __forceinline__ void cu_load_org(uint32_t p, uint32_t (&o)[WW]) {
 // The staged window exists four times in shared memory: copy s holds the rows shifted left by s bytes (built once per
 // CTA after the bulk copies land).  A lane whose candidates start s bytes past a 16-byte boundary reads copy s with
 // aligned LDS.128 and gets its reference words ready to use: no per-word funnel shift in the inner loop (the ALU pipe
-// that executes VABSDIFF4 also executes SHF, and it was the bound).  WW + 3 words serve the lane's four candidates.
-template <int WW>
-__device__ __forceinline__ void cu_load_ref(uint32_t p, uint32_t (&w)[WW + 3]) {
-  constexpr int NW = WW + 3;
+// that executes VABSDIFF4 also executes SHF, and it was the bound).  NW = WW + KC - 1 words serve the lane's KC candidates.
+template <int NW>
+__device__ __forceinline__ void cu_load_ref(uint32_t p, uint32_t (&w)[NW]) {
 #pragma unroll
   for (int i = 0; i < NW / 4; i++) {
     const uint4 v = cu_lds128(p + 16 * i);
     w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
   }
-  if constexpr (NW % 4 == 3) {                           // WW = 4, 8, 16: 7, 11, 19 words -> the last LDS.128 carries one spare word
+  if constexpr (NW % 4 == 3) {                           // WW = 4, 8, 16 with four candidates: 7, 11, 19 words -> the last LDS.128 carries one spare word
     const uint4 v = cu_lds128(p + 16 * (NW / 4));
     w[NW - 3] = v.x; w[NW - 2] = v.y; w[NW - 1] = v.z;
+  } else if constexpr (NW % 4 == 2) {
+    const uint2 v = cu_lds64(p + 16 * (NW / 4));
+    w[NW - 2] = v.x; w[NW - 1] = v.y;
   } else if constexpr (NW % 4 == 1) {                    // WW = 2: five words
     w[NW - 1] = cu_lds32(p + 16 * (NW / 4));
   }
 }
 
-// one reference row against one original row: the words of cell column c feed acc[c][k] (k = candidate column)
-template <int WW, int NC>
-__device__ __forceinline__ void cu_row(uint32_t rp8, const uint32_t (&o)[WW], uint32_t (&acc)[NC][4]) {
-  uint32_t w[WW + 3];
-  cu_load_ref<WW>(rp8, w);
+// one reference row against one original row: the words of cell column c feed acc[c][k] (k = candidate column, 4 bytes apart)
+template <int WW, int NC, int KC>
+__device__ __forceinline__ void cu_row(uint32_t rp8, const uint32_t (&o)[WW], uint32_t (&acc)[NC][KC]) {
+  uint32_t w[WW + KC - 1];
+  cu_load_ref<WW + KC - 1>(rp8, w);
 #pragma unroll
-  for (int j = 0; j < WW + 3; j++) {
+  for (int j = 0; j < WW + KC - 1; j++) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < KC; k++) {
       const int i = j - k;
       if (i >= 0 && i < WW) acc[i / (WW / NC)][k] = sad4_acc(w[j], o[i], acc[i / (WW / NC)][k]);
     }
@@ -144,14 +158,14 @@ __device__ __forceinline__ void cu_row(uint32_t rp8, const uint32_t (&o)[WW], ui
 }
 
 // same, every word into one accumulator per candidate column (odd-row strips)
-template <int WW>
-__device__ __forceinline__ void cu_row1(uint32_t rp8, const uint32_t (&o)[WW], uint32_t (&acc)[4]) {
-  uint32_t w[WW + 3];
-  cu_load_ref<WW>(rp8, w);
+template <int WW, int KC>
+__device__ __forceinline__ void cu_row1(uint32_t rp8, const uint32_t (&o)[WW], uint32_t (&acc)[KC]) {
+  uint32_t w[WW + KC - 1];
+  cu_load_ref<WW + KC - 1>(rp8, w);
 #pragma unroll
-  for (int j = 0; j < WW + 3; j++) {
+  for (int j = 0; j < WW + KC - 1; j++) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < KC; k++) {
       const int i = j - k;
       if (i >= 0 && i < WW) acc[k] = sad4_acc(w[j], o[i], acc[k]);
     }
@@ -179,7 +193,7 @@ __device__ __forceinline__ void cu_min2(uint32_t& best, uint32_t a, uint32_t b) 
 #ifndef CU_ADD_ON_FMA
 #define CU_ADD_ON_FMA 0
 #endif
-template <int S, bool FEN>
+template <int S, bool FEN, int KC>
 struct CuKeys {
   uint32_t v[CU_SLOTS];
   // a + b as a * one + b with a run-time 1: IMAD on the FMA pipe instead of IADD3 on the ALU pipe
@@ -187,7 +201,7 @@ struct CuKeys {
   static __device__ __forceinline__ uint32_t add4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t one) {
     return CU_ADD_ON_FMA ? add(add(a, b, one), add(c, d, one), one) : a + b + c + d;
   }
-  __device__ __forceinline__ CuKeys(const uint32_t (&P)[4][4][4], const uint32_t (&OP)[4][4], int k, uint32_t base, uint32_t one) {
+  __device__ __forceinline__ CuKeys(const uint32_t (&P)[4][4][KC], const uint32_t (&OP)[4][KC], int k, uint32_t base, uint32_t one) {
     // a PU with <= 8 rows under FEN visits every row: add the odd rows of its strips; all others shift by iSubShift
     constexpr bool f1 = FEN && cu_slot_h(S, 1) <= 8;      // 2NxN halves (S == 16)
     constexpr bool f5 = FEN && cu_slot_h(S, 5) <= 8;      // AMP quarter strips (S == 16, 32)
@@ -230,12 +244,165 @@ struct CuKeys {
   }
 };
 
-template <int S, bool FEN>
+// One tile of a 16x16 / 32x32 / 64x64 CU: KC candidate columns (4 bytes apart) of one candidate row against the whole CU,
+// all 13 partitions.  base[k]: MV cost and local index of column k, pre-shifted (KEY_NONE for a column that takes no part
+// when the mask is part of the key, else valid[k] says so).
+template <int S, bool FEN, int KC, bool MASK_BY_KEY, int NS>
+__device__ __forceinline__ void cu_tile(uint32_t refp, uint32_t orgp, uint32_t rpitch, uint32_t opitch, const uint32_t (&base)[KC],
+                                        const bool (&valid)[KC], uint32_t one, uint32_t (&best)[NS]) {
+  typedef CuTraits<S, FEN> T;
+  uint32_t P[4][4][KC], OP[4][KC];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {                                      // strips: static, so the grid row index is too
+    const bool odd_here = T::ODD_ALL || (T::ODD_EDGE && (r == 0 || r == 3));
+    constexpr int OPREV[4] = {0, 0, 1, T::ODD_ALL ? 2 : 0};          // the strip whose odd-row sums strip r continues
+#pragma unroll
+    for (int k = 0; k < KC; k++) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) P[r][c][k] = r ? P[r - 1][c][k] : 0u;
+      OP[r][k] = r ? OP[OPREV[r]][k] : 0u;
+    }
+    if constexpr (T::PARITY) {
+#pragma unroll 4
+      for (int rr = 0; rr < T::G; rr += 2) {
+        const int row = r * T::G + rr;
+        uint32_t o[T::WW];
+        cu_load_org<T::WW>(cu_row_addr(orgp, row, opitch), o);
+        cu_row<T::WW, 4, KC>(cu_row_addr(refp, row, rpitch), o, P[r]);
+        if (odd_here) {
+          uint32_t o1[T::WW];
+          cu_load_org<T::WW>(cu_row_addr(orgp, row + 1, opitch), o1);
+          cu_row1<T::WW, KC>(cu_row_addr(refp, row + 1, rpitch), o1, OP[r]);
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int rr = 0; rr < T::G; rr++) {
+        const int row = r * T::G + rr;
+        uint32_t o[T::WW];
+        cu_load_org<T::WW>(cu_row_addr(orgp, row, opitch), o);
+        cu_row<T::WW, 4, KC>(cu_row_addr(refp, row, rpitch), o, P[r]);
+      }
+    }
+  }
+  if constexpr (MASK_BY_KEY && KC >= 2) {
+#pragma unroll
+    for (int kk = 0; kk < KC; kk += 2) {
+      const CuKeys<S, FEN, KC> a(P, OP, kk, base[kk], one), b(P, OP, kk + 1, base[kk + 1], one);
+#pragma unroll
+      for (int s = 0; s < CU_SLOTS; s++) cu_min2(best[s], a.v[s], b.v[s]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < KC; k++)
+      if (MASK_BY_KEY || valid[k]) {
+        const CuKeys<S, FEN, KC> a(P, OP, k, base[k], one);
+#pragma unroll
+        for (int s = 0; s < CU_SLOTS; s++) best[s] = min(best[s], a.v[s]);
+      }
+  }
+}
+
+// One tile of a 16x16 CU that carries its four 8x8 child CUs: every row is visited once (the children's PUs have at most 8
+// rows, so none of them is sub-sampled: TEncSearch.cpp:3804-3810) and the CU is walked in two halves of two 4-row strips.
+// Per half and candidate column: E[q][c] = even rows (all rows without FEN) of cell column c over the half's strips 0..q,
+// O[q][c] = odd rows (FEN).  A child (half h, column pair j) is the sum of four cells; the 16x16 CU's own partitions need
+// from the upper half only R0, R1 (strip / half sums of the even rows) and the column sums C0, C0+C1, C3.
+// best[13 + 5 * (2 h + j) + {0: 8x8, 1: 8x4 top, 2: 8x4 bottom, 3: 4x8 left, 4: 4x8 right}] are the children's argmins.
+template <bool FEN, int KC, int NS>
+__device__ __forceinline__ void cu16_child_tile(uint32_t refp, uint32_t orgp, uint32_t rpitch, uint32_t opitch,
+                                                const uint32_t (&base)[KC], uint32_t (&best)[NS]) {
+  static_assert(NS == CU_SLOTS_ALL, "child tiles keep 33 argmins");
+  constexpr uint32_t M1 = 1u << CU_LOCAL_BITS;          // key scale of a PU that visits every row (<= 8 rows)
+  constexpr uint32_t MS = M1 << (FEN ? 1 : 0);          // ... of a PU with iSubShift = FEN (> 8 rows)
+  constexpr int KP = KC >= 2 ? 2 : 1;                   // candidate columns whose keys are formed together (one VIMNMX3 per pair)
+  uint32_t R0[KC], R1[KC], C0[KC], C01[KC], C3[KC];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    uint32_t E[2][4][KC], O[2][4][KC];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < KC; k++) { E[q][c][k] = q ? E[0][c][k] : 0u; O[q][c][k] = q ? O[0][c][k] : 0u; }
+#pragma unroll
+      for (int rr = 0; rr < 4; rr++) {
+        const int row = 8 * h + 4 * q + rr;
+        uint32_t o[4];
+        cu_load_org<4>(cu_row_addr(orgp, row, opitch), o);
+        if (FEN && (rr & 1)) cu_row<4, 4, KC>(cu_row_addr(refp, row, rpitch), o, O[q]);
+        else                 cu_row<4, 4, KC>(cu_row_addr(refp, row, rpitch), o, E[q]);
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KC; kk += KP) {
+      uint32_t kc[KP][10], kh[KP][2], kf[KP][9];
+#pragma unroll
+      for (int u = 0; u < KP; u++) {
+        const int k = kk + u;
+        const uint32_t b = base[k];
+        uint32_t T0[4], T1[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) { T0[c] = FEN ? E[0][c][k] + O[0][c][k] : E[0][c][k]; T1[c] = FEN ? E[1][c][k] + O[1][c][k] : E[1][c][k]; }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const uint32_t s88 = T1[2 * j] + T1[2 * j + 1], top = T0[2 * j] + T0[2 * j + 1], left = T1[2 * j];
+          const uint32_t k88 = s88 * M1 + b;
+          kc[u][5 * j + 0] = k88;
+          kc[u][5 * j + 1] = top * M1 + b;
+          kc[u][5 * j + 2] = k88 - top * M1;
+          kc[u][5 * j + 3] = left * M1 + b;
+          kc[u][5 * j + 4] = k88 - left * M1;
+        }
+        const uint32_t all1 = (T1[0] + T1[1]) + (T1[2] + T1[3]);      // every row of the half: a 16x8 PU (2NxN), never sub-sampled
+        const uint32_t all0 = (T0[0] + T0[1]) + (T0[2] + T0[3]);      // every row of the half's first strip
+        const uint32_t e0 = (E[0][0][k] + E[0][1][k]) + (E[0][2][k] + E[0][3][k]);   // even rows of the first strip
+        const uint32_t e1 = (E[1][0][k] + E[1][1][k]) + (E[1][2][k] + E[1][3][k]);   // even rows of the half
+        if (h == 0) {
+          kh[u][0] = all1 * M1 + b;                     // slot 1: 2NxN top
+          kh[u][1] = all0 * M1 + b;                     // slot 5: 2NxnU top (16x4)
+          R0[k] = e0; R1[k] = e1; C0[k] = E[1][0][k]; C01[k] = E[1][0][k] + E[1][1][k]; C3[k] = E[1][3][k];
+        } else {
+          kh[u][0] = all1 * M1 + b;                     // slot 2: 2NxN bottom
+          kh[u][1] = (all1 - all0) * M1 + b;            // slot 8: 2NxnD bottom (16x4)
+          const uint32_t tot = R1[k] + e1, k0 = tot * MS + b;
+          const uint32_t left = C01[k] + E[1][0][k] + E[1][1][k], c0 = C0[k] + E[1][0][k], c3 = C3[k] + E[1][3][k];
+          kf[u][0] = k0;                                // slot 0: 2Nx2N
+          kf[u][1] = left * MS + b;                     // slot 3: Nx2N left
+          kf[u][2] = k0 - left * MS;                    // slot 4: Nx2N right
+          kf[u][3] = k0 - R0[k] * MS;                   // slot 6: 2NxnU bottom (16x12)
+          kf[u][4] = (R1[k] + e0) * MS + b;             // slot 7: 2NxnD top (16x12)
+          kf[u][5] = c0 * MS + b;                       // slot 9: nLx2N left
+          kf[u][6] = k0 - c0 * MS;                      // slot 10
+          kf[u][7] = k0 - c3 * MS;                      // slot 11: nRx2N left
+          kf[u][8] = c3 * MS + b;                       // slot 12
+        }
+      }
+      auto upd = [&](uint32_t& bst, const uint32_t a0, const uint32_t a1) { if constexpr (KP == 2) cu_min2(bst, a0, a1); else bst = min(bst, a0); };
+#pragma unroll
+      for (int i = 0; i < 10; i++) upd(best[CU_SLOTS + 10 * h + i], kc[0][i], kc[KP - 1][i]);
+      if (h == 0) {
+        upd(best[1], kh[0][0], kh[KP - 1][0]);
+        upd(best[5], kh[0][1], kh[KP - 1][1]);
+      } else {
+        constexpr int FSLOT[9] = {0, 3, 4, 6, 7, 9, 10, 11, 12};
+        upd(best[2], kh[0][0], kh[KP - 1][0]);
+        upd(best[8], kh[0][1], kh[KP - 1][1]);
+#pragma unroll
+        for (int i = 0; i < 9; i++) upd(best[FSLOT[i]], kf[0][i], kf[KP - 1][i]);
+      }
+    }
+  }
+}
+
+template <int S, bool FEN, bool CHILD>
 __global__ void __launch_bounds__(CU8_THREADS, 1)
 k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bundles, unsigned long long* __restrict__ keys,
              DevPlane cur_plane, DevPlane ref_plane) {
   typedef CuTraits<S, FEN> T;
-  constexpr int NSLOT = (S == 8) ? 5 : CU_SLOTS;
+  static_assert(!CHILD || S == 16, "only 16x16 CUs carry child CUs");
+  constexpr int NSLOT = (S == 8) ? 5 : CHILD ? CU_SLOTS_ALL : CU_SLOTS;
   constexpr bool MASK_BY_KEY = S <= 32;                 // see cu_key_masked
   constexpr uint32_t KEY_NONE = MASK_BY_KEY ? cu_key_masked(S) : 0xffffffffu;   // best >= KEY_NONE: no candidate yet
   extern __shared__ __align__(128) uint8_t s8_smem[];
@@ -287,7 +454,8 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   S8Bundle& bd = s_bd[warp];
   auto load_bundle = [&]() {
     __syncwarp();
-    reinterpret_cast<int32_t*>(&bd)[lane] = reinterpret_cast<const int32_t*>(&bundles[bslot])[lane];   // 32 ints
+    reinterpret_cast<int32_t*>(&bd)[lane] = reinterpret_cast<const int32_t*>(&bundles[bslot])[lane];            // 64 ints
+    reinterpret_cast<int32_t*>(&bd)[lane + 32] = reinterpret_cast<const int32_t*>(&bundles[bslot])[lane + 32];
     __syncwarp();
     // x part of the MV cost of every column of the CU's window, once per CU and warp instead of four times per tile;
     // stored in the order the lanes read it: [block][lane & 3][k] = column block * 16 + (lane & 3) + 4 k
@@ -304,14 +472,15 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   const int quad = lane >> 2, sub = lane & 3;
   const uint32_t s_copy = smem_u32(s_ref) + (uint32_t)(sub * un.copy_stride);   // this lane's byte phase (shared address)
   const uint32_t one = blockDim.x >> 9;               // 1, but not to the compiler: see CuKeys::add
-  uint32_t best[CU_SLOTS];
+  uint32_t best[NSLOT];
 #pragma unroll
-  for (int s = 0; s < CU_SLOTS; s++) best[s] = 0xffffffffu;
+  for (int s = 0; s < NSLOT; s++) best[s] = 0xffffffffu;
   // every warp takes a contiguous run of the unit's items (round-robin dealing made every warp visit, and flush, every CU)
   const int per_warp = (un.item_last - un.item_first + CU8_WARPS - 1) / CU8_WARPS;
   const int w_first = un.item_first + warp * per_warp, w_last = min(w_first + per_warp, un.item_last);
   int first_item = w_first;                           // first item since the last flush (decodes local indices)
   int g = 0, blk = 0, g0 = 0;                         // row group / block of the lane's quad; g0: row group at the last flush (8x8 CUs)
+  bool edge_mode = false;                             // the candidates since the last flush came from edge items (S >= 16)
   auto flush = [&]() {
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) {
@@ -327,6 +496,8 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
           const int rb = bd.rank_bits, rowrel = (int)(local >> (2 + rb)), rank = (int)(local >> 2) & ((1 << rb) - 1);
           const int gg = g0 + (rowrel >> 2), bb = ((quad - gg * bd.n_blk) & 7) + 8 * rank;
           cyi = bd.cy_first + gg * T::KY + (rowrel & 3); cxi = bb * 16 + sub + 4 * (int)(local & 3u) - bd.xal;
+        } else if (edge_mode) {      // edge item number since the last flush; the lane is the candidate row, the column is the last one
+          cyi = bd.cy_first + (first_item + (int)(local >> LK) - bd.item_start - bd.n_main) * 32 + lane; cxi = bd.nx - 1;
         } else {                     // tile number since the last flush, column
           const int q = (first_item + (int)(local >> LK) - bd.item_start) * 8 + quad;
           const int gg = q / bd.n_blk, bb = q - gg * bd.n_blk;
@@ -335,7 +506,8 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
         idx = (uint32_t)(cyi * bd.nx + cxi);
       }
       const uint32_t imin = __reduce_min_sync(0xffffffffu, idx);
-      if (lane == 0 && cmin != 0xffffffffu && bd.out_idx[s] >= 0) atomicMin(&keys[bd.out_idx[s]], make_key(cmin, imin));
+      const int out = (s < CU_SLOTS) ? bd.out_idx[s < CU_SLOTS ? s : 0] : bd.child_idx[s < CU_SLOTS ? 0 : s - CU_SLOTS];
+      if (lane == 0 && cmin != 0xffffffffu && out >= 0) atomicMin(&keys[out], make_key(cmin, imin));
       best[s] = 0xffffffffu;
     }
   };
@@ -354,18 +526,50 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
     }
     load_bundle();
     locate(w_first);
+    edge_mode = S >= 16 && w_first - bd.item_start >= bd.n_main;
   }
 
   for (int item = w_first; item < w_last; item++) {
-    if (item >= bd.item_start + bd.n_items) {
+    const bool next_cu = item >= bd.item_start + bd.n_items;
+    if (next_cu) {
       flush();
       do { bslot++; } while (item >= bundles[bslot].item_start + bundles[bslot].n_items);
       load_bundle();
       first_item = item;
       locate(item);
-    } else if (S == 8 ? __any_sync(0xffffffffu, (g - g0) >= (1 << (CU_LOCAL_BITS - 4 - bd.rank_bits))) : (item - first_item >= TILE_LIMIT)) {
-      flush();                                        // the local index would run out of bits
-      first_item = item; g0 = g;
+    }
+    const bool is_edge = S >= 16 && item - bd.item_start >= bd.n_main;        // warp-uniform
+    if (!next_cu) {
+      if (is_edge != edge_mode) {                       // the last column's candidates precede later rows' in raster order: a lane's
+        flush();                                        // local order holds only inside one kind of item
+        first_item = item;
+      } else if (S == 8 ? __any_sync(0xffffffffu, (g - g0) >= (1 << (CU_LOCAL_BITS - 4 - bd.rank_bits))) : (item - first_item >= TILE_LIMIT)) {
+        flush();                                        // the local index would run out of bits
+        first_item = item; g0 = g;
+      }
+    }
+    edge_mode = is_edge;
+    const uint32_t c16 = one << 16;                                     // x >> 16 as umulhi(x, 2^16): IMAD.HI, not SHF
+    const uint32_t rpitch = (uint32_t)un.ref_pitch, opitch = (uint32_t)un.org_pitch;
+    const uint32_t orgp = smem_u32(s_org) + (uint32_t)bd.org_off;
+    if constexpr (S >= 16) {
+      if (is_edge) {
+        // Edge item: the window's last column, one candidate row per lane (32 rows per item).  (xal + nx - 1) % 16 == 0, so the
+        // column starts a 16-byte block of copy 0 and every lane reads aligned words of its own row.
+        const int row = (item - bd.item_start - bd.n_main) * 32 + lane;
+        const bool ok = row < bd.ny;
+        const int rowc = min(row, bd.ny - 1);
+        const uint32_t refp = smem_u32(s_ref) + (uint32_t)(bd.win_off + rowc * un.ref_pitch + bd.nx - 1);
+        const uint32_t px = bd.lambda * eg_bits(((bd.lt_x + bd.nx - 1) << 2) - bd.pred_x);
+        const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + bd.cy_first + rowc) << 2) - bd.pred_y);
+        const uint32_t tile_local = (uint32_t)(item - first_item) << LK;
+        uint32_t base[1];
+        bool valid[1] = {ok};
+        base[0] = (ok || !MASK_BY_KEY) ? (__umulhi(px + py, c16) << CU_LOCAL_BITS) + tile_local : KEY_NONE;
+        if constexpr (CHILD) cu16_child_tile<FEN, 1, NSLOT>(refp, orgp, rpitch, opitch, base, best);
+        else                 cu_tile<S, FEN, 1, MASK_BY_KEY, NSLOT>(refp, orgp, rpitch, opitch, base, valid, one, best);
+        continue;
+      }
     }
     // Local index of a candidate inside the key: must grow in raster order along the candidates ONE LANE sees between
     // two flushes.  S >= 16 (one candidate row per tile): the lane's tiles come in raster order, so the tile number does.
@@ -374,13 +578,10 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
     const uint32_t rowunit = 1u << (2 + bd.rank_bits);                  // S == 8: index step of one candidate row
     const uint32_t tile_local = (S == 8) ? (uint32_t)((g - g0) * 4) * rowunit + ((uint32_t)(blk >> 3) << 2)
                                          : (uint32_t)(item - first_item) << LK;
-    const uint32_t c16 = one << 16;                                     // x >> 16 as umulhi(x, 2^16): IMAD.HI, not SHF
     if (g < bd.n_rowgroups) {
     const int cyi0 = g * T::KY;
     const int cx0 = blk * 16 + sub - bd.xal;                            // window column of candidate k = 0 (may be < 0)
-    const uint32_t rpitch = (uint32_t)un.ref_pitch, opitch = (uint32_t)un.org_pitch;
     const uint32_t refp = s_copy + (uint32_t)(bd.win_off - bd.xal + cyi0 * un.ref_pitch + blk * 16);     // 16-byte aligned
-    const uint32_t orgp = smem_u32(s_org) + (uint32_t)bd.org_off;
     // key base of candidate (jy, k) = MV cost * mk[k] + jy * ru[k] + idx0[k]: IMADs on the FMA pipe.  Block columns outside
     // the window take no part: their mk and ru are 0 and idx0 is KEY_NONE (MASK_BY_KEY), so the base is exactly KEY_NONE.
     uint32_t px[4], mk[4], idx0[4], ru[4];
@@ -417,7 +618,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
 #pragma unroll
       for (int r = 0; r < 8 + T::KY - 1; r++) {
         uint32_t w[5];
-        cu_load_ref<2>(cu_row_addr(refp, r, rpitch), w);
+        cu_load_ref<5>(cu_row_addr(refp, r, rpitch), w);
 #pragma unroll
         for (int jy = 0; jy < T::KY; jy++) {
           const int orow = r - jy;
@@ -458,62 +659,12 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
         }
       }
     } else {
-      uint32_t P[4][4][4], OP[4][4];
+      const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + bd.cy_first + cyi0) << 2) - bd.pred_y);
+      uint32_t base[4];
 #pragma unroll
-      for (int r = 0; r < 4; r++) {                                      // strips: static, so the grid row index is too
-        const bool odd_here = T::ODD_ALL || (T::ODD_EDGE && (r == 0 || r == 3));
-        constexpr int OPREV[4] = {0, 0, 1, T::ODD_ALL ? 2 : 0};          // the strip whose odd-row sums strip r continues
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-#pragma unroll
-          for (int c = 0; c < 4; c++) P[r][c][k] = r ? P[r - 1][c][k] : 0u;
-          OP[r][k] = r ? OP[OPREV[r]][k] : 0u;
-        }
-        if constexpr (T::PARITY) {
-#pragma unroll 4
-          for (int rr = 0; rr < T::G; rr += 2) {
-            const int row = r * T::G + rr;
-            uint32_t o[T::WW];
-            cu_load_org<T::WW>(cu_row_addr(orgp, row, opitch), o);
-            cu_row<T::WW, 4>(cu_row_addr(refp, row, rpitch), o, P[r]);
-            if (odd_here) {
-              uint32_t o1[T::WW];
-              cu_load_org<T::WW>(cu_row_addr(orgp, row + 1, opitch), o1);
-              cu_row1<T::WW>(cu_row_addr(refp, row + 1, rpitch), o1, OP[r]);
-            }
-          }
-        } else {
-#pragma unroll 4
-          for (int rr = 0; rr < T::G; rr++) {
-            const int row = r * T::G + rr;
-            uint32_t o[T::WW];
-            cu_load_org<T::WW>(cu_row_addr(orgp, row, opitch), o);
-            cu_row<T::WW, 4>(cu_row_addr(refp, row, rpitch), o, P[r]);
-          }
-        }
-      }
-      if (cyi0 < bd.ny) {
-        const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + bd.cy_first + cyi0) << 2) - bd.pred_y);
-        uint32_t base[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) base[k] = __umulhi(px[k] + py, c16) * mk[k] + idx0[k];
-        if constexpr (MASK_BY_KEY) {
-#pragma unroll
-          for (int kk = 0; kk < 4; kk += 2) {
-            const CuKeys<S, FEN> a(P, OP, kk, base[kk], one), b(P, OP, kk + 1, base[kk + 1], one);
-#pragma unroll
-            for (int s = 0; s < CU_SLOTS; s++) cu_min2(best[s], a.v[s], b.v[s]);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            if (valid[k]) {
-              const CuKeys<S, FEN> a(P, OP, k, base[k], one);
-#pragma unroll
-              for (int s = 0; s < CU_SLOTS; s++) best[s] = min(best[s], a.v[s]);
-            }
-        }
-      }
+      for (int k = 0; k < 4; k++) base[k] = __umulhi(px[k] + py, c16) * mk[k] + idx0[k];
+      if constexpr (CHILD) cu16_child_tile<FEN, 4, NSLOT>(refp, orgp, rpitch, opitch, base, best);
+      else                 cu_tile<S, FEN, 4, MASK_BY_KEY, NSLOT>(refp, orgp, rpitch, opitch, base, valid, one, best);
     }
     }   // row group in range
     blk += bd.step_blk; g += bd.step_g;                                  // 8 quads further
@@ -525,19 +676,24 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-enum : int { CUV_8 = 0, CUV_16_F0, CUV_16_F1, CUV_32_F0, CUV_32_F1, CUV_64_F0, CUV_64_F1, CUV_COUNT };
+// CUV_16C_*: 16x16 CUs that carry their four 8x8 child CUs (8-bit planes only; the 16-bit tables end at CUV_BASE_COUNT)
+enum : int { CUV_8 = 0, CUV_16_F0, CUV_16_F1, CUV_32_F0, CUV_32_F1, CUV_64_F0, CUV_64_F1, CUV_BASE_COUNT, CUV_16C_F0 = CUV_BASE_COUNT, CUV_16C_F1, CUV_COUNT };
 typedef void (*S8CuKernel)(const S8Unit*, const S8Bundle*, unsigned long long*, DevPlane, DevPlane);
 inline const S8CuKernel* search8_cu_kernels() {
-  static const S8CuKernel table[CUV_COUNT] = { k_search8_cu<8, false>, k_search8_cu<16, false>, k_search8_cu<16, true>,
-                                               k_search8_cu<32, false>, k_search8_cu<32, true>, k_search8_cu<64, false>,
-                                               k_search8_cu<64, true> };
+  static const S8CuKernel table[CUV_COUNT] = { k_search8_cu<8, false, false>, k_search8_cu<16, false, false>, k_search8_cu<16, true, false>,
+                                               k_search8_cu<32, false, false>, k_search8_cu<32, true, false>, k_search8_cu<64, false, false>,
+                                               k_search8_cu<64, true, false>, k_search8_cu<16, false, true>, k_search8_cu<16, true, true> };
   return table;
 }
-inline int cu_variant(int S, bool fen) { return S == 8 ? CUV_8 : S == 16 ? (fen ? CUV_16_F1 : CUV_16_F0) : S == 32 ? (fen ? CUV_32_F1 : CUV_32_F0) : (fen ? CUV_64_F1 : CUV_64_F0); }
+inline int cu_variant(int S, bool fen, bool child = false) {
+  if (child) return fen ? CUV_16C_F1 : CUV_16C_F0;
+  return S == 8 ? CUV_8 : S == 16 ? (fen ? CUV_16_F1 : CUV_16_F0) : S == 32 ? (fen ? CUV_32_F1 : CUV_32_F0) : (fen ? CUV_64_F1 : CUV_64_F0);
+}
 
 struct CuSchedule {
   int n_units = 0, n_bundles = 0;
   unsigned long long executed_abs_diffs = 0;     // byte abs-diffs the fused kernels execute (incl. overlapped last blocks)
+  unsigned long long unique_abs_diffs = 0;       // ... they cannot avoid: every visited sample of every CU once per candidate (no masked lanes)
   unsigned long long fused_tasks = 0;
   int bps = 1;                                   // bytes per sample of the planes this schedule was built for
   S8Unit* d_units = nullptr;
@@ -600,7 +756,11 @@ inline int cu_smem_need(const S8Box& rb, const S8Box& ob, int* org_off, int* cop
 
 // Finds CU bundles: PUs that are partitions of the same aligned S x S CU and share window, predictor and lambda.
 // taken[i] = 1 for every bundled task (the per-PU schedule skips those).
-struct CuBundleHost { int S; bool fen; int cu_x, cu_y; int slot_task[CU_SLOTS]; int first_task; };
+struct CuBundleHost {
+  int S; bool fen; int cu_x, cu_y; int slot_task[CU_SLOTS]; int first_task;
+  bool child = false;                       // 16x16 CU that carries its 8x8 child CUs (8-bit planes)
+  int child_task[CU_CHILD_SLOTS];           // task per child PU: 5 * (2 * row + column) + {8x8, 8x4 top, 8x4 bottom, 4x8 left, 4x8 right}
+};
 inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, int bps, std::vector<char>& taken, std::vector<CuBundleHost>& out) {
   const CuGeom G = cu_geom(bps);
   struct Key {
@@ -639,6 +799,8 @@ inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, int bps, st
     it->second.slot_task[slot] = i;
   }
   taken.assign(tasks.size(), 0);
+  std::map<Key, int> where;                 // bundle key -> index in out (to find a 16x16 CU's children)
+  std::vector<Key> key_of;
   for (auto& kv : found) {
     CuBundleHost& b = kv.second;
     int n = 0, fen_seen = -1; bool consistent = true;
@@ -651,8 +813,32 @@ inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, int bps, st
     }
     if (n < 2 || !consistent) continue;
     b.fen = fen_seen == 1;
+    for (int s = 0; s < CU_CHILD_SLOTS; s++) b.child_task[s] = -1;
     for (int s = 0; s < CU_SLOTS; s++) if (b.slot_task[s] >= 0) taken[b.slot_task[s]] = 1;
+    where[kv.first] = (int)out.size();
+    key_of.push_back(kv.first);
     out.push_back(b);
+  }
+  // 8-bit planes: a 16x16 CU takes the PUs of its four 8x8 child CUs along when they share its window (as displacements),
+  // predictor and lambda - the child SADs are sums of the 4x4 cells the 16x16 pass computes anyway (hmb200 CHILD kernels).
+  std::vector<char> absorbed(out.size(), 0);
+  if (bps == 1 && !getenv("HMB200_NO_CHILD_FOLD")) {
+    for (size_t i = 0; i < out.size(); i++) {
+      if (out[i].S != 16) continue;
+      for (int c = 0; c < 4; c++) {
+        Key k = key_of[i];
+        k.v[0] = out[i].cu_x + 8 * (c & 1); k.v[1] = out[i].cu_y + 8 * (c >> 1); k.v[2] = 8;
+        auto it = where.find(k);
+        if (it == where.end() || absorbed[it->second]) continue;
+        const CuBundleHost& ch = out[it->second];
+        for (int s = 0; s < 5; s++) out[i].child_task[5 * c + s] = ch.slot_task[s];
+        out[i].child = true;
+        absorbed[it->second] = 1;
+      }
+    }
+    std::vector<CuBundleHost> kept;
+    for (size_t i = 0; i < out.size(); i++) if (!absorbed[i]) kept.push_back(out[i]);
+    out.swap(kept);
   }
   std::sort(out.begin(), out.end(), [](const CuBundleHost& a, const CuBundleHost& b) { return a.first_task < b.first_task; });
 }
@@ -707,10 +893,14 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     if (cu_smem_need(ents[p].rb, ents[p].ob, nullptr, nullptr, bps, ents[p].two) > S8_SMEM_MAX) { if (err) *err = "cu_build_schedule: window too large"; return false; }
     groups.push_back(Group{(int)p, 1, ents[p].rb, ents[p].ob, ents[p].two});
   }
+  const int S_of_variant[CUV_COUNT] = {8, 16, 16, 32, 32, 64, 64, 16, 16};
+  const bool F_of_variant[CUV_COUNT] = {false, false, true, false, true, false, true, false, true};
   auto rows_visited = [](int S, bool fen) { return (fen && S >= 16) ? (S == 16 ? 16 : S == 32 ? 24 : 32) : S; };
-  auto item_cost = [&](int S, bool fen) -> long long {
-    return (long long)GM.ky(S) * (rows_visited(S, fen) * (S / 4) * (bps == 1 ? 1 : 6) + 40);
+  auto item_cost = [&](int S, bool fen, bool child = false) -> long long {
+    return (long long)GM.ky(S) * (rows_visited(S, fen) * (S / 4) * (bps == 1 ? 1 : 6) + (child ? 100 : 40));
   };
+  auto vcost = [&](int v) { return item_cost(S_of_variant[v], F_of_variant[v], v >= CUV_BASE_COUNT); };
+  const bool use_edge = bps == 1 && !getenv("HMB200_NO_EDGE_ITEMS");
   std::vector<S8Bundle> bundles; bundles.reserve(ents.size());
   std::vector<int> bvar; bvar.reserve(ents.size());
   std::vector<std::pair<int, int> > group_range(groups.size());
@@ -721,7 +911,7 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     std::vector<int> ids;
     for (int k = 0; k < g.count; k++) ids.push_back(g.first + k);
     std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) {
-      return cu_variant(hb[ents[a].b].S, hb[ents[a].b].fen) > cu_variant(hb[ents[b].b].S, hb[ents[b].b].fen);
+      return cu_variant(hb[ents[a].b].S, hb[ents[a].b].fen, hb[ents[a].b].child) > cu_variant(hb[ents[b].b].S, hb[ents[b].b].fen, hb[ents[b].b].child);
     });
     const int rx0 = s8_fl(g.rb.x0), ox0 = s8_fl(g.ob.x0);
     const int rpitch = (s8_ce(g.rb.x1) - rx0) * bps, opitch = (s8_ce(g.ob.x1) - ox0) * bps;      // bytes
@@ -738,18 +928,29 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
       d.lt_x = t.lt_x; d.lt_y = t.lt_y; d.pred_x = t.pred_x; d.pred_y = t.pred_y; d.lambda = t.lambda_cost;
       d.xal = (bps == 1) ? (d.win_off & 15) : 0;           // window pitch and origin are multiples of 16 bytes
       d.n_blk = (d.xal + d.nx + GM.blkw - 1) / GM.blkw;
+      // 129 = 8 * 16 + 1: a last block with a single column in it runs as edge items (a lane per candidate row) instead
+      d.edge = (use_edge && b.S >= 16 && d.n_blk >= 2 && ((d.xal + d.nx) & 15) == 1) ? 1 : 0;
+      if (d.edge) d.n_blk--;
       d.step_g = GM.groups / d.n_blk; d.step_blk = GM.groups % d.n_blk;      // 8-bit kernels: consecutive items per warp
       d.rank_bits = 0;
       while ((8 << d.rank_bits) < d.n_blk) d.rank_bits++;
       d.n_rowgroups = (d.ny + GM.ky(b.S) - 1) / GM.ky(b.S);
-      d.n_items = (d.n_blk * d.n_rowgroups + GM.groups - 1) / GM.groups;
+      d.n_main = (d.n_blk * d.n_rowgroups + GM.groups - 1) / GM.groups;
+      const int n_edge = d.edge ? (d.ny + 31) / 32 : 0;
+      d.n_items = d.n_main + n_edge;
       d.item_start = item; item += d.n_items;
       for (int s = 0; s < CU_SLOTS; s++) d.out_idx[s] = b.slot_task[s];
-      const int v = cu_variant(b.S, b.fen);
-      variant_cost[v] += item_cost(b.S, b.fen) * d.n_items;
-      out->executed_abs_diffs += (unsigned long long)d.n_blk * GM.blkw * (unsigned long long)(d.n_rowgroups * GM.ky(b.S)) *
-                                 rows_visited(b.S, b.fen) * b.S;
-      if (e.cy_first == 0) for (int s2 = 0; s2 < CU_SLOTS; s2++) if (b.slot_task[s2] >= 0) out->fused_tasks++;
+      for (int s = 0; s < CU_CHILD_SLOTS; s++) d.child_idx[s] = b.child ? b.child_task[s] : -1;
+      const int v = cu_variant(b.S, b.fen, b.child);
+      const int rows_v = b.child ? 16 : rows_visited(b.S, b.fen);         // child tiles visit every row
+      variant_cost[v] += vcost(v) * d.n_main + (vcost(v) / 3) * n_edge;
+      out->executed_abs_diffs += ((unsigned long long)d.n_blk * GM.blkw * (unsigned long long)(d.n_rowgroups * GM.ky(b.S)) + (unsigned long long)n_edge * 32) *
+                                 rows_v * b.S;
+      out->unique_abs_diffs += (unsigned long long)d.nx * d.ny * rows_v * b.S;
+      if (e.cy_first == 0) {
+        for (int s2 = 0; s2 < CU_SLOTS; s2++) if (b.slot_task[s2] >= 0) out->fused_tasks++;
+        if (b.child) for (int s2 = 0; s2 < CU_CHILD_SLOTS; s2++) if (b.child_task[s2] >= 0) out->fused_tasks++;
+      }
       bundles.push_back(d); bvar.push_back(v);
     }
     all_r = s8_union(all_r, g.rb); all_o = s8_union(all_o, g.ob);
@@ -758,8 +959,6 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
   int per_slot = bps == 1 ? 3 : 6;                     // units per resident CTA slot and variant (knob: HMB200_UNITS_PER_SLOT); 8-bit: one CTA per SM
   if (const char* e = getenv("HMB200_UNITS_PER_SLOT")) per_slot = std::max(1, atoi(e));
   for (int v = 0; v < CUV_COUNT; v++) target[v] = std::max<long long>(variant_cost[v] / std::max(1, sm_count * (bps == 1 ? 1 : 2) * per_slot), 4000);
-  const int S_of_variant[CUV_COUNT] = {8, 16, 16, 32, 32, 64, 64};
-  const bool F_of_variant[CUV_COUNT] = {false, false, true, false, true, false, true};
   std::vector<S8Unit> units;
   for (size_t gi = 0; gi < groups.size(); gi++) {
     const Group& g = groups[gi];
@@ -781,7 +980,7 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     for (int bl = 0; bl < bcount; bl++) {
       const S8Bundle& b = bundles[bfirst + bl];
       const int v = bvar[bfirst + bl];
-      const long long per_item = item_cost(S_of_variant[v], F_of_variant[v]);
+      const long long per_item = vcost(v);
       if (acc > 0 && v != bvar[bfirst + bl - 1]) { emit(bl - 1, b.item_start); acc = 0; ufirst_item = b.item_start; ufirst_b = bl; }
       int done = 0;
       while (done < b.n_items) {
