@@ -177,6 +177,10 @@ int  hmb200_register_plane(const int16_t* host_origin, int stride, int width, in
  * behind its last reader, without a host synchronisation. */
 int  hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width, int height,
                               int margin_x, int margin_y, int kind, int poc);
+/* Same for 9..14-bit content held as 16-bit samples (planar 16-bit YUV luma as TVideoIOYuv reads it for Main10,
+ * TLibVideoIO/TVideoIOYuv.cpp:247-377); stride in samples. */
+int  hmb200_register_plane_u16(const uint16_t* host_samples, int stride, int width, int height,
+                               int margin_x, int margin_y, int bit_depth, int kind, int poc);
 /* Direct ingest of one frame's luma from a planar YUV file image: TVideoIOYuv::read for COMPONENT_Y
  * (TLibVideoIO/TVideoIOYuv.cpp:680-741 -> readPlane :247-377 -> scalePlane :70-99) fused with extendPicBorder.
  * file_luma: width x height samples, bytes or (file_is16) 16-bit little endian; pad_x / pad_y: conformance padding

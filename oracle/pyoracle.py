@@ -295,3 +295,55 @@ class Reference(_Base):
         t = self.lib.hmref_run_jobs(self.h, _ptr(ca, co), cs, _ptr(ra, ro), rs, bit_depth, jobs.ctypes.data, len(jobs),
                                     int(bool(do_frac)), out.ctypes.data)
         return out, t
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Canonical all-PU job list in plain Python - so that the reference arm of bench.py and the CPU tests can
+# build job lists without loading the product library.  Restates TComDataCU::clipMv (TLibCommon/TComDataCU.cpp:2788-2801),
+# TEncSearch::xSetSearchRange (TLibEncoder/TEncSearch.cpp:3765-3781) and the partition geometry of
+# TComDataCU::getPartIndexAndSize (TLibCommon/TComDataCU.cpp:1893-1931).
+# ---------------------------------------------------------------------------------------------------------------------
+def _clip_mv(x, y, cu_x, cu_y, pic_w, pic_h, max_cu):
+    off = 8
+    hmax, hmin = (pic_w + off - cu_x - 1) * 4, (-max_cu - off - cu_x + 1) * 4
+    vmax, vmin = (pic_h + off - cu_y - 1) * 4, (-max_cu - off - cu_y + 1) * 4
+    return min(hmax, max(hmin, x)), min(vmax, max(vmin, y))
+
+
+def _s16(v):
+    return ((v + 0x8000) & 0xFFFF) - 0x8000          # TComMv components are Shorts
+
+
+def py_search_range(pred, search_range, cu_xy, pic_wh, max_cu=64):
+    px, py = _clip_mv(pred[0], pred[1], cu_xy[0], cu_xy[1], pic_wh[0], pic_wh[1], max_cu)
+    lx, ly = _s16(px - (search_range << 2)), _s16(py - (search_range << 2))
+    rx, ry = _s16(px + (search_range << 2)), _s16(py + (search_range << 2))
+    lx, ly = _clip_mv(lx, ly, cu_xy[0], cu_xy[1], pic_wh[0], pic_wh[1], max_cu)
+    rx, ry = _clip_mv(rx, ry, cu_xy[0], cu_xy[1], pic_wh[0], pic_wh[1], max_cu)
+    return lx >> 2, ly >> 2, rx >> 2, ry >> 2
+
+
+def py_canonical_jobs(pic_w, pic_h, search_range=64, lambda_cost=0, pred=(0, 0), max_cu=64, ctu_first=0, ctu_count=-1):
+    """Every CU of depth 0..3 inside the picture; 2Nx2N, 2NxN, Nx2N at every depth plus the four AMP modes at depths 0..2:
+    593 PUs per 64x64 CTU, in the order hmb200_build_canonical_jobs emits them."""
+    ctus_x, ctus_y = (pic_w + max_cu - 1) // max_cu, (pic_h + max_cu - 1) // max_cu
+    n_ctus = ctus_x * ctus_y
+    ctu_end = n_ctus if ctu_count < 0 else min(n_ctus, ctu_first + ctu_count)
+    rows = []
+    for ctu in range(max(0, ctu_first), ctu_end):
+        ox, oy = (ctu % ctus_x) * max_cu, (ctu // ctus_x) * max_cu
+        s = max_cu
+        while s >= 8:
+            for cy in range(oy, oy + max_cu, s):
+                for cx in range(ox, ox + max_cu, s):
+                    if cx + s > pic_w or cy + s > pic_h:
+                        continue
+                    q = s >> 2
+                    pus = [(cx, cy, s, s), (cx, cy, s, s // 2), (cx, cy + s // 2, s, s // 2), (cx, cy, s // 2, s), (cx + s // 2, cy, s // 2, s)]
+                    if s > 8:
+                        pus += [(cx, cy, s, q), (cx, cy + q, s, s - q), (cx, cy, s, s - q), (cx, cy + s - q, s, q),
+                                (cx, cy, q, s), (cx + q, cy, s - q, s), (cx, cy, s - q, s), (cx + s - q, cy, q, s)]
+                    lt_x, lt_y, rb_x, rb_y = py_search_range(pred, search_range, (cx, cy), (pic_w, pic_h), max_cu)
+                    rows += [(x, y, w, h, lt_x, lt_y, rb_x, rb_y, pred[0], pred[1], int(lambda_cost), 0) for (x, y, w, h) in pus]
+            s >>= 1
+    return np.array(rows, dtype=JOB_DTYPE) if rows else np.zeros(0, dtype=JOB_DTYPE)

@@ -572,3 +572,42 @@ def test_me_ctu_row_entry(hm):
     finally:
         hm.release_plane(idc)
         hm.release_plane(idr)
+
+
+@pytest.mark.parametrize("bd,sr,n_cols", [(8, 64, 3), (10, 128, 2)])
+def test_tile_column_shards_with_halo_crops_equal_unsharded(hm, bd, sr, n_cols):
+    """BASELINE.json configs[3]: every tile-column shard uploads only its crop of both planes (column +- search range +
+    interpolation reach) and searches its own jobs in crop coordinates; the shards merged in job order must equal the MV
+    field of the whole picture searched at once (integer MV, SAD, half / quarter MV and cost)."""
+    from video_codecs_b200 import shard
+    W, H = 704, 192
+    margin = 80 if sr <= 64 else 144
+    f0, f1 = synth.luma_frame(W, H, 0, seed=41, bit_depth=bd), synth.luma_frame(W, H, 1, seed=41, bit_depth=bd)
+    lam = 51234
+
+    def reg(f, kind):
+        return hm.register_plane_u8(f, margin, margin, kind=kind) if bd == 8 else hm.register_plane_u16(f, bd, margin, margin, kind=kind)
+
+    def run(fc, fr, jobs):
+        idc, idr = reg(np.ascontiguousarray(fc), 0), reg(np.ascontiguousarray(fr), 1)
+        try:
+            return hm.me_jobs(idc, idr, jobs, flags_of(1, 1))
+        finally:
+            hm.release_plane(idc)
+            hm.release_plane(idr)
+
+    full = hm.build_canonical_jobs(W, H, sr, lam)
+    whole = run(f1, f0, full)
+    parts, results, uploaded = [], [], 0
+    for c in range(n_cols):
+        x0, x1 = hm.tile_column_range(W, n_cols, c)
+        jobs = shard.tile_column_jobs(hm, W, H, n_cols, c, sr, lam)
+        c0, c1 = shard.tile_column_crop(W, x0, x1, sr)
+        assert c0 % 16 == 0 and 0 <= c0 < c1 <= W
+        uploaded += c1 - c0
+        results.append(run(f1[:, c0:c1], f0[:, c0:c1], shard.shift_jobs(jobs, c0)))
+        parts.append(jobs)
+    merged = shard.merge_shards(parts, results, full)
+    assert results_equal(merged, whole) == []
+    assert uploaded < n_cols * W                       # the crops are smaller than whole planes per rank
+    assert len(set(zip(whole["mv_x"].tolist(), whole["mv_y"].tolist()))) >= 2

@@ -100,3 +100,14 @@ def test_motion_lambda_cost_matches_reference(lib, reference):
             lam = scale * 2 ** ((qp - 12) / 3.0)
             assert lib.motion_lambda_cost(lam) == f(lam, 8)
     assert lib.motion_lambda_cost(0.4624 * 2 ** ((35 - 12) / 3.0)) == 635239
+
+
+def test_python_canonical_job_list_equals_the_library_builder():
+    """oracle.pyoracle.py_canonical_jobs (what the reference arm of bench.py uses, so that it never loads libhmb200) against
+    hmb200_build_canonical_jobs: same PUs, windows and order, incl. clipped windows and a non-zero predictor."""
+    from oracle.pyoracle import py_canonical_jobs
+    from video_codecs_b200 import HMB200
+    hm = HMB200()
+    for (w, h, sr, pred) in [(416, 240, 64, (0, 0)), (320, 256, 128, (6, -3)), (200, 136, 16, (-300, 500))]:
+        assert np.array_equal(hm.build_canonical_jobs(w, h, sr, 777, pred=pred), py_canonical_jobs(w, h, sr, 777, pred))
+    assert np.array_equal(hm.build_canonical_jobs(416, 240, 64, 5, ctu_first=9, ctu_count=2), py_canonical_jobs(416, 240, 64, 5, ctu_first=9, ctu_count=2))

@@ -74,6 +74,7 @@ def _load():
         "hmb200_tile_column_range": (i32, [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]),
         "hmb200_register_plane": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32]),
         "hmb200_register_plane_u8": (i32, [vp, i32, i32, i32, i32, i32, i32, i32]),
+        "hmb200_register_plane_u16": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32]),
         "hmb200_register_plane_yuv": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32]),
         "hmb200_read_plane": (i32, [i32, vp, i32]), "hmb200_release_plane": (None, [i32]),
         "hmb200_dist": (u32, [C.POINTER(_DistParam)]),
@@ -220,6 +221,12 @@ class HMB200:
         assert samples.dtype == np.uint8 and samples.ndim == 2 and samples.strides[1] == 1
         h, w = samples.shape
         return self._check(self.lib.hmb200_register_plane_u8(samples.ctypes.data, samples.strides[0], w, h, margin_x, margin_y, kind, poc))
+
+    def register_plane_u16(self, samples, bit_depth, margin_x=80, margin_y=80, kind=PLANE_REC, poc=0):
+        assert samples.dtype == np.uint16 and samples.ndim == 2 and samples.strides[1] == 2
+        h, w = samples.shape
+        return self._check(self.lib.hmb200_register_plane_u16(samples.ctypes.data, samples.strides[0] // 2, w, h, margin_x, margin_y,
+                                                              bit_depth, kind, poc))
 
     def register_plane_yuv(self, file_luma, width, height, pad_x=0, pad_y=0, file_bit_depth=8, internal_bit_depth=8,
                            margin_x=80, margin_y=80, kind=PLANE_ORG, poc=0):

@@ -511,20 +511,31 @@ int hmb200_register_plane(const int16_t* host_origin, int stride, int width, int
   return id;
 }
 
-int hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width, int height, int margin_x, int margin_y,
-                             int kind, int poc) {
+// Tightly packed samples without margins (bytes for 8-bit content, 16-bit words for deeper content); the margins are
+// synthesised on the device exactly like extendPicBorder.  stride in samples.
+static int register_packed(const void* host_samples, int stride, int width, int height, int margin_x, int margin_y, int bit_depth,
+                           int kind, int poc, const char* who) {
   NEED_READY();
-  if (!host_samples || width <= 0 || height <= 0 || stride < width || margin_x < 0 || margin_y < 0)
-    return fail(HMB200_ERR_ARG, "hmb200_register_plane_u8: bad geometry");
+  if (!host_samples || width <= 0 || height <= 0 || stride < width || margin_x < 0 || margin_y < 0 || bit_depth < 8 || bit_depth > 14)
+    return fail(HMB200_ERR_ARG, std::string(who) + ": bad geometry");
   int id = alloc_plane_slot();
   Plane& p = G.planes[id];
   p = Plane();
-  int rc = make_plane(p, width, height, margin_x, margin_y, 8);
+  int rc = make_plane(p, width, height, margin_x, margin_y, bit_depth);
   if (rc != HMB200_OK) return rc;
-  size_t bytes = (size_t)width * height;
+  const int bps = p.d.bytes_per_sample;
+  const size_t bytes = (size_t)width * height * bps;
   cudaPointerAttributes attr;
   const bool user_pinned = stride == width && cudaPointerGetAttributes(&attr, host_samples) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
+  auto pad_launch = [&](const void* d_src, cudaStream_t st) {
+    dim3 grid((width + 2 * margin_x + 255) / 256, height + 2 * margin_y);
+    if (bps == 1) k_pad_plane<uint8_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(d_src), width, reinterpret_cast<uint8_t*>(p.d.base),
+                                                             p.d.pitch, width, height, margin_x, margin_y);
+    else          k_pad_plane<uint16_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(d_src), width, reinterpret_cast<uint16_t*>(p.d.base),
+                                                              p.d.pitch, width, height, margin_x, margin_y);
+    G.launches++;
+  };
   if (user_pinned) {
     // page-locked, tightly packed frame: H2D + border extension on the upload stream, behind whatever the compute stream is
     // doing; the source stays the caller's until the copy has run (hmb200_sync or any later fetch / blocking call orders it)
@@ -538,10 +549,7 @@ int hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width,
       }
       if (p.ev_reuse) { CUDA_TRY(cudaStreamWaitEvent(G.up, p.ev_reuse, 0)); give_event(p.ev_reuse); p.ev_reuse = nullptr; }
       CUDA_TRY(cudaMemcpyAsync(G.upstage, host_samples, bytes, cudaMemcpyHostToDevice, G.up));
-      dim3 ugrid((width + 2 * margin_x + 255) / 256, height + 2 * margin_y);
-      k_pad_plane_u8<<<ugrid, 256, 0, G.up>>>(reinterpret_cast<const uint8_t*>(G.upstage), width,
-                                              reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, width, height, margin_x, margin_y);
-      G.launches++;
+      pad_launch(G.upstage, G.up);
       p.ev_ready = take_event();
       CUDA_TRY(cudaEventRecord(p.ev_ready, G.up));
       return HMB200_OK;
@@ -553,19 +561,28 @@ int hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width,
   // pageable (or strided) source: through the library's page-locked staging buffer, which the next call reuses - so this path waits
   if ((rc = ensure_dstage(bytes)) != HMB200_OK || (rc = ensure_pinned(bytes)) != HMB200_OK) { hmb200_release_plane(id); return rc; }
   uint8_t* pin = reinterpret_cast<uint8_t*>(G.pinned);
-  for (int y = 0; y < height; y++) memcpy(pin + (size_t)y * width, host_samples + (size_t)y * stride, (size_t)width);
+  for (int y = 0; y < height; y++)
+    memcpy(pin + (size_t)y * width * bps, reinterpret_cast<const uint8_t*>(host_samples) + (size_t)y * stride * bps, (size_t)width * bps);
   auto upload = [&]() -> int {
     CUDA_TRY(cudaMemcpyAsync(G.dstage, pin, bytes, cudaMemcpyHostToDevice, G.stream));
-    dim3 grid((width + 2 * margin_x + 255) / 256, height + 2 * margin_y);
-    k_pad_plane_u8<<<grid, 256, 0, G.stream>>>(reinterpret_cast<const uint8_t*>(G.dstage), width,
-                                               reinterpret_cast<uint8_t*>(p.d.base), p.d.pitch, width, height, margin_x, margin_y);
-    G.launches++;
+    pad_launch(G.dstage, G.stream);
     CUDA_TRY(cudaStreamSynchronize(G.stream));
     return HMB200_OK;
   };
   if ((rc = upload()) != HMB200_OK) { const std::string why = g_err; hmb200_release_plane(id); g_err = why; return rc; }
   p.kind = kind; p.poc = poc;
   return id;
+}
+
+int hmb200_register_plane_u8(const uint8_t* host_samples, int stride, int width, int height, int margin_x, int margin_y,
+                             int kind, int poc) {
+  return register_packed(host_samples, stride, width, height, margin_x, margin_y, 8, kind, poc, "hmb200_register_plane_u8");
+}
+
+int hmb200_register_plane_u16(const uint16_t* host_samples, int stride, int width, int height, int margin_x, int margin_y,
+                              int bit_depth, int kind, int poc) {
+  if (bit_depth <= 8) return fail(HMB200_ERR_ARG, "hmb200_register_plane_u16: bit_depth must be 9..14 (8-bit content uses hmb200_register_plane_u8)");
+  return register_packed(host_samples, stride, width, height, margin_x, margin_y, bit_depth, kind, poc, "hmb200_register_plane_u16");
 }
 
 int hmb200_register_plane_yuv(const void* file_luma, int file_is16, int width, int height, int pad_x, int pad_y,

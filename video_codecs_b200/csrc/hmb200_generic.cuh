@@ -338,10 +338,11 @@ __global__ void k_widen_plane(const T* __restrict__ src, int src_pitch, int16_t*
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x < total_w && y < total_h) dst[(size_t)y * dst_stride + x] = (int16_t)src[(size_t)y * src_pitch + x];
 }
-// src: tightly packed w x h samples (u8); dst: padded plane; every destination sample (margins included) is the
+// src: tightly packed w x h samples (u8 or u16); dst: padded plane; every destination sample (margins included) is the
 // clamped-coordinate source sample — identical to replicating edges.
-__global__ void k_pad_plane_u8(const uint8_t* __restrict__ src, int src_stride, uint8_t* __restrict__ dst, int dst_pitch,
-                               int w, int h, int mx, int my) {
+template <typename T>
+__global__ void k_pad_plane(const T* __restrict__ src, int src_stride, T* __restrict__ dst, int dst_pitch,
+                            int w, int h, int mx, int my) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x < w + 2 * mx && y < h + 2 * my) {
     int sx = min(max(x - mx, 0), w - 1), sy = min(max(y - my, 0), h - 1);
