@@ -127,6 +127,18 @@ uint32_t hmo_dist(int kind, const int16_t* org, int so, const int16_t* cur, int 
   return hmo_sad(org, so, cur, sc, w, h, bit_depth, sub_shift);
 }
 
+/* n evaluations between two padded planes (test convenience: what hmb200_dist_batch computes on the device).
+ * descs: n x {org_x, org_y, cur_x, cur_y, w, h, sub_shift}; org0 / cur0 point at sample (0, 0). */
+void hmo_dist_batch(int kind, const int16_t* org0, int so, const int16_t* cur0, int sc, int bit_depth, int n,
+                    const int32_t* descs, uint32_t* out)
+{
+  for (int i = 0; i < n; i++)
+  {
+    const int32_t* d = descs + 7 * i;
+    out[i] = hmo_dist(kind, org0 + d[1] * so + d[0], so, cur0 + d[3] * sc + d[2], sc, d[4], d[5], bit_depth, d[6]);
+  }
+}
+
 /* ---------------------------------------------------------------- search window -------------------------------- */
 
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }

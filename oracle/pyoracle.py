@@ -125,6 +125,17 @@ class Oracle(_Base):
         (oa, oo, os_), (ca, co, cs) = org, cur
         return self.lib.hmo_dist(kind, _ptr(oa, oo), os_, _ptr(ca, co), cs, w, h, bit_depth, sub_shift)
 
+    def dist_batch(self, kind, org, cur, blocks, bit_depth=8):
+        """org / cur: (padded int16 array, offset of sample (0,0), stride); blocks: int32 array (n, 7) of
+        org_x, org_y, cur_x, cur_y, w, h, sub_shift."""
+        (oa, oo, os_), (ca, co, cs) = org, cur
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32)
+        out = np.zeros(len(blocks), dtype=np.uint32)
+        self.lib.hmo_dist_batch.restype = None
+        self.lib.hmo_dist_batch.argtypes = [C.c_int, _p16, C.c_int, _p16, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.hmo_dist_batch(kind, _ptr(oa, oo), os_, _ptr(ca, co), cs, bit_depth, len(blocks), blocks.ctypes.data, out.ctypes.data)
+        return out
+
     def search_range(self, pred, rng, cu_xy, pic_wh, max_cu=64):
         o = [C.c_int() for _ in range(4)]
         self.lib.hmo_search_range(pred[0], pred[1], rng, cu_xy[0], cu_xy[1], pic_wh[0], pic_wh[1], max_cu, max_cu,

@@ -59,6 +59,81 @@ def test_dist_batch_every_pu_size(hm, oracle, bd):
         hm.release_plane(idb)
 
 
+@pytest.mark.parametrize("bd", [8, 10])
+def test_dist_table_ten_thousand_blocks_per_size(hm, oracle, bd):
+    """BASELINE.json configs[1] at the size SURVEY.md 8d asks for: 10^4 random block pairs for each of the 24 PU sizes, every
+    family (SAD with random iSubShift, SSE, HADs), 8- and 10-bit, random offsets incl. the margins - bit-exact."""
+    rng = np.random.default_rng(140 + bd)
+    W, H, N = 640, 384, 10000
+    hi = 1 << bd
+    a = rng.integers(0, hi, size=(H, W)).astype(np.int16)
+    b = np.clip(a.astype(np.int32) + rng.integers(-40, 41, size=a.shape), 0, hi - 1).astype(np.int16)
+    pa, o0, stride = padded(a.astype(np.uint16))
+    pb, _, _ = padded(b.astype(np.uint16))
+    ida = hm.register_plane(pa, W, H, MARGIN, MARGIN, bd)
+    idb = hm.register_plane(pb, W, H, MARGIN, MARGIN, bd)
+    try:
+        blocks = np.zeros((len(PU_SIZES) * N, 7), dtype=np.int32)
+        for i, (w, h) in enumerate(PU_SIZES):
+            v = blocks[i * N:(i + 1) * N]
+            v[:, 0], v[:, 1] = rng.integers(-8, W - w + 8, N), rng.integers(-8, H - h + 8, N)
+            v[:, 2], v[:, 3] = rng.integers(-8, W - w + 8, N), rng.integers(-8, H - h + 8, N)
+            v[:, 4], v[:, 5], v[:, 6] = w, h, rng.integers(0, 2, N)
+        descs = np.zeros(len(blocks), dtype=DIST_DESC_DTYPE)
+        descs["org_plane"], descs["cur_plane"] = ida, idb
+        for f, c in (("org_x", 0), ("org_y", 1), ("cur_x", 2), ("cur_y", 3), ("w", 4), ("h", 5)):
+            descs[f] = blocks[:, c]
+        for func in (DF_SAD, DF_SSE, DF_HADS):
+            blk = blocks.copy()
+            if func != DF_SAD:
+                blk[:, 6] = 0
+            descs["sub_shift"] = blk[:, 6]
+            got = hm.dist_batch(func, bd, descs)
+            exp = oracle.dist_batch(func, (pa, o0, stride), (pb, o0, stride), blk, bd)
+            assert np.array_equal(got, exp), func
+    finally:
+        hm.release_plane(ida)
+        hm.release_plane(idb)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_dist_generic_shapes_2x2_hadamard_and_unsized_sad(hm, oracle, bd):
+    """Shapes outside the 24 PU sizes: xGetHADs falls back to 2x2 tiles when a dimension is not a multiple of 4
+    (xCalcHADs2x2, TComRdCost.cpp:1310-1330, 1573-1586) and the generic xGetSAD (:461-487) ignores iSubShift for widths
+    without an unrolled variant; both through the batched entry (registered planes) and the 1:1 FpDistFunc-style call."""
+    rng = np.random.default_rng(11 + bd)
+    W, H = 128, 96
+    hi = 1 << bd
+    a = rng.integers(0, hi, size=(H, W)).astype(np.int16)
+    b = rng.integers(0, hi, size=(H, W)).astype(np.int16)
+    pa, o0, stride = padded(a.astype(np.uint16))
+    pb, _, _ = padded(b.astype(np.uint16))
+    shapes = [(2, 2), (6, 2), (2, 6), (6, 6), (10, 4), (4, 10), (20, 10), (2, 8), (36, 18), (64, 2), (6, 64), (20, 16), (40, 8), (36, 36)]
+    ida = hm.register_plane(pa, W, H, MARGIN, MARGIN, bd)
+    idb = hm.register_plane(pb, W, H, MARGIN, MARGIN, bd)
+    try:
+        for func in (DF_HADS, DF_SAD, DF_SSE):
+            blocks = []
+            for (w, h) in shapes:
+                for rep in range(25):
+                    blocks.append((int(rng.integers(0, W - w)), int(rng.integers(0, H - h)), int(rng.integers(0, W - w)), int(rng.integers(0, H - h)),
+                                   w, h, int(rng.integers(0, 2)) if func == DF_SAD else 0))
+            blocks = np.array(blocks, dtype=np.int32)
+            descs = np.zeros(len(blocks), dtype=DIST_DESC_DTYPE)
+            descs["org_plane"], descs["cur_plane"] = ida, idb
+            for f, c in (("org_x", 0), ("org_y", 1), ("cur_x", 2), ("cur_y", 3), ("w", 4), ("h", 5), ("sub_shift", 6)):
+                descs[f] = blocks[:, c]
+            exp = oracle.dist_batch(func, (pa, o0, stride), (pb, o0, stride), blocks, bd)
+            assert np.array_equal(hm.dist_batch(func, bd, descs), exp), func
+            for k in range(0, len(blocks), 9):         # the same evaluations through hmb200_dist (host Pel* in, one call each)
+                ox, oy, cx, cy, w, h, ss = [int(v) for v in blocks[k]]
+                got = hm.dist(func, (pa, o0 + oy * stride + ox, stride), (pb, o0 + cy * stride + cx, stride), w, h, bd, ss)
+                assert got == int(exp[k]), (func, w, h)
+    finally:
+        hm.release_plane(ida)
+        hm.release_plane(idb)
+
+
 def test_dist_signed_pattern(hm, oracle):
     rng = np.random.default_rng(6)
     org = rng.integers(-255, 511, size=64 * 64).astype(np.int16)
