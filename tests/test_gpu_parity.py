@@ -557,6 +557,31 @@ def test_child_fold_and_edge_items_equal_separate_kernels(hm, monkeypatch, fen):
             assert np.all(fused["mv_x"] == 64) and np.all(fused["mv_y"] == 0)
 
 
+def test_refinement_on_unique_tiles_equals_per_instance_refinement(hm, monkeypatch):
+    """The quarter-pel refinement computes each (original tile, reference tile at the integer MV, half offset) once for all
+    PUs that share it (hash pass + gather).  Same MV field, half / quarter vectors and costs as one SATD per tile instance
+    (knob off), for coherent motion (most tiles shared), for content whose MVs differ from PU to PU, and with SAD instead of
+    the Hadamard distortion; sampled PUs against the oracle."""
+    W, H = 416, 240
+    lam = int(np.floor(65536.0 * np.sqrt(0.4624 * 2 ** ((35 - 12) / 3.0))))
+    jobs = hm.build_canonical_jobs(W, H, 64, lam)
+    rng = np.random.default_rng(5)
+    noise0, noise1 = rng.integers(0, 256, size=(H, W)).astype(np.uint8), rng.integers(0, 256, size=(H, W)).astype(np.uint8)
+    cases = [("coherent", synth.luma_frame(W, H, 1, seed=3), synth.luma_frame(W, H, 0, seed=3), 1),
+             ("noise", noise1, noise0, 1), ("sad", synth.luma_frame(W, H, 2, seed=3), synth.luma_frame(W, H, 0, seed=3), 0)]
+    for name, f1, f0, had in cases:
+        got, _ = _run_full(hm, f1, f0, jobs, flags_of(1, had))
+        monkeypatch.setenv("HMB200_NO_FRAC_DEDUPE", "1")
+        plain, _ = _run_full(hm, f1, f0, jobs, flags_of(1, had))
+        monkeypatch.delenv("HMB200_NO_FRAC_DEDUPE")
+        assert results_equal(got, plain) == [], name
+        pick = np.sort(rng.choice(len(jobs), 120, replace=False))
+        cur, o0, stride = padded(f1)
+        ref, _, _ = padded(f0)
+        exp, _ = Oracle(fen=1, hadme=had).run_jobs((cur, o0, stride), (ref, o0, stride), jobs[pick], 8, True)
+        assert results_equal(got[pick], exp) == [], name
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # 10-bit content: CU-fused 16-bit kernels (packed 16x2 arithmetic, distortion precision shift)
 # ---------------------------------------------------------------------------------------------------------------------

@@ -235,6 +235,72 @@ k_frac_tiles(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_re
   atomicAdd(&dist[(size_t)pu * 9 + ci], s);
 }
 
+// ---- unique tiles -------------------------------------------------------------------------------------------------------
+// The PUs of a job list overlap: every sample of a CTU lies in 18 PUs whose Hadamard tiles are 8x8 (all partitions of the
+// 64x64 and 32x32 CUs, three of the 16x16 CU's, the 8x8 PU) and in 6 whose tiles are 4x4, and those tiles sit on one 8 / 4
+// sample grid because CU origins do.  Two PUs that found the same integer MV (and, for the quarter stage, the same half-pel
+// offset) therefore ask for the SATD of exactly the same (original tile, interpolated tile) pairs.  The refinement works on
+// UNIQUE tiles: a hash pass keys every tile instance by (original position, reference position incl. the integer MV, half
+// offset), the SATD kernels run once per unique tile and candidate and store plain words, and a gather pass adds each
+// instance's nine (eight) values to its PU.  Same integers, added in a different order - sums of uint32 are exact.
+struct FracUTile { int16_t rx, ry, ox, oy; int16_t hx, hy; int16_t pad[2]; };      // 16 bytes: patch origin (tile - 4), original tile, half offset
+constexpr unsigned long long FRAC_KEY_EMPTY = ~0ull;
+
+__device__ __forceinline__ uint32_t frac_hash64(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+// One thread per tile instance: inserts its key, the first inserter of a key allocates the dense unique id and writes the
+// descriptor.  inst_slot[i] = hash slot of instance i (k_frac_gather turns it into the id after this kernel has finished).
+template <int N>
+__global__ void k_frac_unique(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_result* __restrict__ results,
+                              const uint32_t* __restrict__ tiles, int n_tiles, unsigned long long* __restrict__ hkeys, uint32_t mask,
+                              uint32_t* __restrict__ hval, uint32_t* __restrict__ count, FracUTile* __restrict__ utiles,
+                              uint32_t* __restrict__ inst_slot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_tiles) return;
+  const uint32_t tile = tiles[i];
+  const int pu = (int)(tile & 0xffffffu), tx = (tile >> 24) & 15, ty = tile >> 28;
+  const SearchTask tk = tasks[pu];
+  const hmb200_pu_result rs = results[pu];
+  FracUTile u;
+  u.rx = (int16_t)(tk.ref_x + rs.mv_x + tx * N - 4); u.ry = (int16_t)(tk.ref_y + rs.mv_y + ty * N - 4);
+  u.ox = (int16_t)(tk.org_x + tx * N);               u.oy = (int16_t)(tk.org_y + ty * N);
+  u.hx = (int16_t)(stage ? rs.half_x : 0);           u.hy = (int16_t)(stage ? rs.half_y : 0);
+  u.pad[0] = u.pad[1] = 0;
+  // 14 bits per coordinate (planes up to 8192 + margins around zero), 2 bits per half offset: 60 bits, never FRAC_KEY_EMPTY
+  const unsigned long long key = ((unsigned long long)((uint32_t)(u.rx + 4096) & 0x3fffu)) | ((unsigned long long)((uint32_t)(u.ry + 4096) & 0x3fffu) << 14) |
+                                 ((unsigned long long)((uint32_t)(u.ox + 4096) & 0x3fffu) << 28) | ((unsigned long long)((uint32_t)(u.oy + 4096) & 0x3fffu) << 42) |
+                                 ((unsigned long long)((uint32_t)(u.hx + 1) & 3u) << 56) | ((unsigned long long)((uint32_t)(u.hy + 1) & 3u) << 58);
+  uint32_t slot = frac_hash64(key) & mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(&hkeys[slot], FRAC_KEY_EMPTY, key);
+    if (prev == FRAC_KEY_EMPTY) {                        // first instance of this tile
+      const uint32_t id = atomicAdd(count, 1u);
+      hval[slot] = id;
+      utiles[id] = u;
+      break;
+    }
+    if (prev == key) break;
+    slot = (slot + 1) & mask;
+  }
+  inst_slot[i] = slot;
+}
+
+// dist[pu][c] += udist[unique id of instance i][c]; one thread per (instance, candidate)
+__global__ void k_frac_gather(int stage, const uint32_t* __restrict__ tiles, int n_tiles, const uint32_t* __restrict__ inst_slot,
+                              const uint32_t* __restrict__ hval, const uint32_t* __restrict__ udist, uint32_t* __restrict__ dist) {
+  const int nc = stage == 0 ? 9 : 8;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(t / nc), cand = (int)(t - (long long)i * nc);
+  if (i >= n_tiles) return;
+  const int ci = stage == 0 ? cand : cand + 1;
+  const uint32_t pu = tiles[i] & 0xffffffu;
+  const uint32_t id = hval[inst_slot[i]];
+  atomicAdd(&dist[(size_t)pu * 9 + ci], udist[(size_t)id * 9 + ci]);
+}
+
 // ---- 8-bit planes, stages 0 / 1: reference patches staged in shared memory ------------------------------------------
 // All candidates of a stage read the same 16 x 16 (8x8 tiles) or 12 x 16 (4x4 tiles) block of integer samples around
 // the tile at the integer MV: columns -4..11, rows -4..N+3 (the candidates' integer parts are -1 or 0, the filter
@@ -311,7 +377,8 @@ template <int N> struct FracPatch {
 template <int N, bool HAD>
 __global__ void __launch_bounds__(FRAC_TILE_THREADS, N == 8 ? 4 : 8)
 k_frac_patch(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_result* __restrict__ results,
-             const uint32_t* __restrict__ tiles, int n_tiles, uint32_t* __restrict__ dist, DevPlane cur_plane, DevPlane ref_plane) {
+             const uint32_t* __restrict__ tiles, int n_tiles, uint32_t* __restrict__ dist, DevPlane cur_plane, DevPlane ref_plane,
+             const FracUTile* __restrict__ utiles, const uint32_t* __restrict__ n_unique) {
   typedef FracPatch<N> P;
   __shared__ __align__(16) uint8_t s_patch[P::MAX_TILES * P::STRIDE];
   __shared__ __align__(16) uint8_t s_org[P::MAX_TILES * P::ORG];
@@ -320,16 +387,25 @@ k_frac_patch(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_re
   const int nc = stage == 0 ? 9 : 8;
   const int tpc = FRAC_TILE_THREADS / nc;                                // tiles per CTA: 14 / 16
   const int slot0 = blockIdx.x * tpc;
+  if (utiles) n_tiles = (int)*n_unique;                                  // unique tiles: the grid covers the worst case, the count is the device's
   const int nt = min(tpc, n_tiles - slot0);
+  if (nt <= 0) return;
   if ((int)threadIdx.x < nt) {
-    const uint32_t tile = tiles[slot0 + threadIdx.x];
-    const int pu = (int)(tile & 0xffffffu), tx = (tile >> 24) & 15, ty = tile >> 28;
-    const SearchTask tk = tasks[pu];
-    const hmb200_pu_result rs = results[pu];
-    s_pu[threadIdx.x] = pu;
-    s_rx[threadIdx.x] = tk.ref_x + rs.mv_x + tx * N - 4; s_ry[threadIdx.x] = tk.ref_y + rs.mv_y + ty * N - 4;
-    s_ox[threadIdx.x] = tk.org_x + tx * N;               s_oy[threadIdx.x] = tk.org_y + ty * N;
-    s_hx[threadIdx.x] = rs.half_x;                       s_hy[threadIdx.x] = rs.half_y;
+    if (utiles) {
+      const FracUTile u = utiles[slot0 + threadIdx.x];
+      s_pu[threadIdx.x] = slot0 + (int)threadIdx.x;                      // row of the unique-tile distortion table
+      s_rx[threadIdx.x] = u.rx; s_ry[threadIdx.x] = u.ry; s_ox[threadIdx.x] = u.ox; s_oy[threadIdx.x] = u.oy;
+      s_hx[threadIdx.x] = u.hx; s_hy[threadIdx.x] = u.hy;
+    } else {
+      const uint32_t tile = tiles[slot0 + threadIdx.x];
+      const int pu = (int)(tile & 0xffffffu), tx = (tile >> 24) & 15, ty = tile >> 28;
+      const SearchTask tk = tasks[pu];
+      const hmb200_pu_result rs = results[pu];
+      s_pu[threadIdx.x] = pu;
+      s_rx[threadIdx.x] = tk.ref_x + rs.mv_x + tx * N - 4; s_ry[threadIdx.x] = tk.ref_y + rs.mv_y + ty * N - 4;
+      s_ox[threadIdx.x] = tk.org_x + tx * N;               s_oy[threadIdx.x] = tk.org_y + ty * N;
+      s_hx[threadIdx.x] = rs.half_x;                       s_hy[threadIdx.x] = rs.half_y;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nt * P::ROWS; i += FRAC_TILE_THREADS) {   // one 16-byte patch row per step
@@ -374,7 +450,8 @@ k_frac_patch(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_re
 #pragma unroll
     for (int i = 0; i < N * N; i++) sv += (uint32_t)abs(d[i]);
   }
-  atomicAdd(&dist[(size_t)s_pu[tl] * 9 + ci], sv);
+  if (utiles) dist[(size_t)s_pu[tl] * 9 + ci] = sv;                     // one thread per (unique tile, candidate): plain store
+  else        atomicAdd(&dist[(size_t)s_pu[tl] * 9 + ci], sv);
 }
 
 // ---- 8-bit planes, stages 0 / 1: horizontal pass shared by the candidates, vertical pass as 16-bit dot products ------
@@ -429,7 +506,8 @@ __device__ __forceinline__ void frac_hrow(uint32_t prow, uint32_t sh, int t0, in
 template <int N, bool HAD>
 __global__ void __launch_bounds__(FRAC_TILE_THREADS, N == 8 ? HV8_MIN_CTAS : 8)
 k_frac_hv(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_result* __restrict__ results,
-          const uint32_t* __restrict__ tiles, int n_tiles, uint32_t* __restrict__ dist, DevPlane cur_plane, DevPlane ref_plane) {
+          const uint32_t* __restrict__ tiles, int n_tiles, uint32_t* __restrict__ dist, DevPlane cur_plane, DevPlane ref_plane,
+          const FracUTile* __restrict__ utiles, const uint32_t* __restrict__ n_unique) {
   typedef FracPatch<N> P;
   typedef FracHV<N> H;
   __shared__ __align__(16) uint8_t s_patch[P::MAX_TILES * P::STRIDE];
@@ -440,16 +518,25 @@ k_frac_hv(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_resul
   const int nc = stage == 0 ? 9 : 8;
   const int tpc = FRAC_TILE_THREADS / nc;                                // tiles per CTA: 14 / 16
   const int slot0 = blockIdx.x * tpc;
+  if (utiles) n_tiles = (int)*n_unique;                                  // unique tiles: the grid covers the worst case, the count is the device's
   const int nt = min(tpc, n_tiles - slot0);
+  if (nt <= 0) return;
   if ((int)threadIdx.x < nt) {
-    const uint32_t tile = tiles[slot0 + threadIdx.x];
-    const int pu = (int)(tile & 0xffffffu), tx = (tile >> 24) & 15, ty = tile >> 28;
-    const SearchTask tk = tasks[pu];
-    const hmb200_pu_result rs = results[pu];
-    s_pu[threadIdx.x] = pu;
-    s_rx[threadIdx.x] = tk.ref_x + rs.mv_x + tx * N - 4; s_ry[threadIdx.x] = tk.ref_y + rs.mv_y + ty * N - 4;
-    s_ox[threadIdx.x] = tk.org_x + tx * N;               s_oy[threadIdx.x] = tk.org_y + ty * N;
-    s_hx[threadIdx.x] = rs.half_x;                       s_hy[threadIdx.x] = rs.half_y;
+    if (utiles) {
+      const FracUTile u = utiles[slot0 + threadIdx.x];
+      s_pu[threadIdx.x] = slot0 + (int)threadIdx.x;                      // row of the unique-tile distortion table
+      s_rx[threadIdx.x] = u.rx; s_ry[threadIdx.x] = u.ry; s_ox[threadIdx.x] = u.ox; s_oy[threadIdx.x] = u.oy;
+      s_hx[threadIdx.x] = u.hx; s_hy[threadIdx.x] = u.hy;
+    } else {
+      const uint32_t tile = tiles[slot0 + threadIdx.x];
+      const int pu = (int)(tile & 0xffffffu), tx = (tile >> 24) & 15, ty = tile >> 28;
+      const SearchTask tk = tasks[pu];
+      const hmb200_pu_result rs = results[pu];
+      s_pu[threadIdx.x] = pu;
+      s_rx[threadIdx.x] = tk.ref_x + rs.mv_x + tx * N - 4; s_ry[threadIdx.x] = tk.ref_y + rs.mv_y + ty * N - 4;
+      s_ox[threadIdx.x] = tk.org_x + tx * N;               s_oy[threadIdx.x] = tk.org_y + ty * N;
+      s_hx[threadIdx.x] = rs.half_x;                       s_hy[threadIdx.x] = rs.half_y;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nt * P::ROWS; i += FRAC_TILE_THREADS) {   // one 16-byte patch row per step
@@ -556,7 +643,8 @@ k_frac_hv(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_resul
 #pragma unroll
     for (int i = 0; i < N * N; i++) sv += (uint32_t)abs(d[i]);
   }
-  atomicAdd(&dist[(size_t)s_pu[tl] * 9 + ci], sv);
+  if (utiles) dist[(size_t)s_pu[tl] * 9 + ci] = sv;                     // one thread per (unique tile, candidate): plain store
+  else        atomicAdd(&dist[(size_t)s_pu[tl] * 9 + ci], sv);
 }
 
 // xPatternRefinement's argmin (TEncSearch.cpp:808-861).  STAGE 0 writes rcMvHalf and seeds the quarter stage's
@@ -603,13 +691,49 @@ struct FracSchedule {
   uint32_t* d_tiles8 = nullptr;
   uint32_t* d_tiles4 = nullptr;
   uint32_t* d_dist = nullptr;        // [2][n_pu][9]
+  // unique-tile pass (8-bit planes): per tile size a hash table (keys, dense ids), the unique descriptors, per-instance slots
+  // and the unique tiles' distortions; d_count[2 * stage + (N == 4)]
+  unsigned long long* d_hkeys[2] = {nullptr, nullptr};
+  uint32_t* d_hval[2] = {nullptr, nullptr};
+  uint32_t* d_inst[2] = {nullptr, nullptr};
+  FracUTile* d_utiles[2] = {nullptr, nullptr};
+  uint32_t* d_udist[2] = {nullptr, nullptr};
+  uint32_t* d_count = nullptr;
+  uint32_t hmask[2] = {0, 0};
 };
 
 inline void frac_free_schedule(FracSchedule* s) {
   if (s->d_tiles8) cudaFree(s->d_tiles8);
   if (s->d_tiles4) cudaFree(s->d_tiles4);
   if (s->d_dist) cudaFree(s->d_dist);
+  for (int k = 0; k < 2; k++) {
+    if (s->d_hkeys[k]) cudaFree(s->d_hkeys[k]);
+    if (s->d_hval[k]) cudaFree(s->d_hval[k]);
+    if (s->d_inst[k]) cudaFree(s->d_inst[k]);
+    if (s->d_utiles[k]) cudaFree(s->d_utiles[k]);
+    if (s->d_udist[k]) cudaFree(s->d_udist[k]);
+  }
+  if (s->d_count) cudaFree(s->d_count);
   *s = FracSchedule();
+}
+
+// Buffers of the unique-tile pass, allocated on first use (8-bit planes with more than a handful of tiles).
+inline bool frac_alloc_unique(FracSchedule* fs) {
+  if (fs->d_count) return true;
+  const int n[2] = {fs->n_tiles8, fs->n_tiles4};
+  bool ok = cudaMalloc((void**)&fs->d_count, 4 * sizeof(uint32_t)) == cudaSuccess;
+  for (int k = 0; k < 2 && ok; k++) {
+    if (n[k] == 0) continue;
+    uint32_t cap = 1024;
+    while (cap < 2u * (uint32_t)n[k]) cap <<= 1;
+    fs->hmask[k] = cap - 1;
+    ok = cudaMalloc((void**)&fs->d_hkeys[k], (size_t)cap * sizeof(unsigned long long)) == cudaSuccess &&
+         cudaMalloc((void**)&fs->d_hval[k], (size_t)cap * sizeof(uint32_t)) == cudaSuccess &&
+         cudaMalloc((void**)&fs->d_inst[k], (size_t)n[k] * sizeof(uint32_t)) == cudaSuccess &&
+         cudaMalloc((void**)&fs->d_utiles[k], (size_t)n[k] * sizeof(FracUTile)) == cudaSuccess &&
+         cudaMalloc((void**)&fs->d_udist[k], (size_t)n[k] * 9 * sizeof(uint32_t)) == cudaSuccess;
+  }
+  return ok;
 }
 
 inline bool frac_build_schedule(const std::vector<SearchTask>& tasks, cudaStream_t stream, FracSchedule* out, std::string* err) {
@@ -645,6 +769,9 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
                        const DevPlane& ref, bool use_had, cudaStream_t stream) {
   if (fs.n_pu == 0) return 0;
   int launches = 0;
+  // unique-tile keys hold 14-bit coordinates (-4096 .. 12287): larger planes keep one SATD per tile instance
+  const bool plane_fits_i16 = std::max(cur.width, ref.width) + 2 * std::max(cur.margin_x, ref.margin_x) < 12000 &&
+                              std::max(cur.height, ref.height) + 2 * std::max(cur.margin_y, ref.margin_y) < 12000;
   uint32_t* dist0 = fs.d_dist;
   uint32_t* dist1 = fs.d_dist + (size_t)fs.n_pu * 9;
   if (cudaMemsetAsync(fs.d_dist, 0, (size_t)fs.n_pu * 18 * sizeof(uint32_t), stream) != cudaSuccess) return -1;
@@ -653,16 +780,34 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
     const int nc = stage == 0 ? 9 : 8;
     auto blocks = [&](int n_tiles) { return (int)((((long long)(n_tiles + 31) / 32) * 32 * nc + FRAC_TILE_THREADS - 1) / FRAC_TILE_THREADS); };
     constexpr bool PATCH = sizeof(RefT) == 1 && sizeof(OrgT) == 1;        // 8-bit planes: shared-memory patches (k_frac_hv / k_frac_patch)
-    static const bool old_path = getenv("HMB200_FRAC_PATCH") != nullptr;  // A/B knob: per-candidate first pass for 8x8 tiles too
-    static const bool hv4 = getenv("HMB200_FRAC_HV4") != nullptr;         // 4x4 tiles: the shared first pass costs more in barriers than
+    const bool old_path = getenv("HMB200_FRAC_PATCH") != nullptr;         // A/B knob: per-candidate first pass for 8x8 tiles too
+    const bool hv4 = getenv("HMB200_FRAC_HV4") != nullptr;                // 4x4 tiles: the shared first pass costs more in barriers than
                                                                           // it saves (ncu: 263 vs 225 us per stage), so it is opt-in
     const int tpc = FRAC_TILE_THREADS / nc;
+    bool unique = false;
+    if constexpr (PATCH) {
+      const bool no_unique = getenv("HMB200_NO_FRAC_DEDUPE") != nullptr;   // A/B knob: every tile instance on its own
+      unique = !no_unique && plane_fits_i16 && frac_alloc_unique(const_cast<FracSchedule*>(&fs));
+      if (unique && stage == 0 && cudaMemsetAsync(fs.d_count, 0, 4 * sizeof(uint32_t), stream) != cudaSuccess) return -1;
+    }
     if (fs.n_tiles8 > 0) {
       if constexpr (PATCH) {
         const int nb8 = (fs.n_tiles8 + tpc - 1) / tpc;
-        if (!use_had)      k_frac_patch<8, false><<<nb8, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
-        else if (old_path) k_frac_patch<8, true><<<nb8, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
-        else               k_frac_hv<8, true><<<nb8, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
+        const FracUTile* ut = nullptr; const uint32_t* cnt = nullptr; uint32_t* out8 = dist;
+        if (unique) {
+          if (cudaMemsetAsync(fs.d_hkeys[0], 0xff, ((size_t)fs.hmask[0] + 1) * sizeof(unsigned long long), stream) != cudaSuccess) return -1;
+          k_frac_unique<8><<<(fs.n_tiles8 + 255) / 256, 256, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, fs.d_hkeys[0], fs.hmask[0],
+                                                                         fs.d_hval[0], fs.d_count + 2 * stage, fs.d_utiles[0], fs.d_inst[0]);
+          launches++;
+          ut = fs.d_utiles[0]; cnt = fs.d_count + 2 * stage; out8 = fs.d_udist[0];
+        }
+        if (!use_had)      k_frac_patch<8, false><<<nb8, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, out8, cur, ref, ut, cnt);
+        else if (old_path) k_frac_patch<8, true><<<nb8, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, out8, cur, ref, ut, cnt);
+        else               k_frac_hv<8, true><<<nb8, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, out8, cur, ref, ut, cnt);
+        if (unique) {
+          k_frac_gather<<<(int)(((long long)fs.n_tiles8 * nc + 255) / 256), 256, 0, stream>>>(stage, fs.d_tiles8, fs.n_tiles8, fs.d_inst[0], fs.d_hval[0], fs.d_udist[0], dist);
+          launches++;
+        }
       } else {
         if (use_had) k_frac_tiles<RefT, OrgT, 8, true><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
         else         k_frac_tiles<RefT, OrgT, 8, false><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
@@ -672,9 +817,21 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
     if (fs.n_tiles4 > 0) {
       if constexpr (PATCH) {
         const int nb4 = (fs.n_tiles4 + tpc - 1) / tpc;
-        if (!use_had)      k_frac_patch<4, false><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
-        else if (!hv4)     k_frac_patch<4, true><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
-        else               k_frac_hv<4, true><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
+        const FracUTile* ut = nullptr; const uint32_t* cnt = nullptr; uint32_t* out4 = dist;
+        if (unique) {
+          if (cudaMemsetAsync(fs.d_hkeys[1], 0xff, ((size_t)fs.hmask[1] + 1) * sizeof(unsigned long long), stream) != cudaSuccess) return -1;
+          k_frac_unique<4><<<(fs.n_tiles4 + 255) / 256, 256, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, fs.d_hkeys[1], fs.hmask[1],
+                                                                         fs.d_hval[1], fs.d_count + 2 * stage + 1, fs.d_utiles[1], fs.d_inst[1]);
+          launches++;
+          ut = fs.d_utiles[1]; cnt = fs.d_count + 2 * stage + 1; out4 = fs.d_udist[1];
+        }
+        if (!use_had)      k_frac_patch<4, false><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, out4, cur, ref, ut, cnt);
+        else if (!hv4)     k_frac_patch<4, true><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, out4, cur, ref, ut, cnt);
+        else               k_frac_hv<4, true><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, out4, cur, ref, ut, cnt);
+        if (unique) {
+          k_frac_gather<<<(int)(((long long)fs.n_tiles4 * nc + 255) / 256), 256, 0, stream>>>(stage, fs.d_tiles4, fs.n_tiles4, fs.d_inst[1], fs.d_hval[1], fs.d_udist[1], dist);
+          launches++;
+        }
       } else {
         if (use_had) k_frac_tiles<RefT, OrgT, 4, true><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
         else         k_frac_tiles<RefT, OrgT, 4, false><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);

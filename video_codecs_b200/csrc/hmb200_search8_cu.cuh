@@ -553,7 +553,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
     const uint32_t rpitch = (uint32_t)un.ref_pitch, opitch = (uint32_t)un.org_pitch;
     const uint32_t orgp = smem_u32(s_org) + (uint32_t)bd.org_off;
     if constexpr (S >= 16) {
-      if (is_edge) {
+      if (__builtin_expect(is_edge, 0)) {              // rare (5 of 134 items): keep its code out of the block loop's straight line
         // Edge item: the window's last column, one candidate row per lane (32 rows per item).  (xal + nx - 1) % 16 == 0, so the
         // column starts a 16-byte block of copy 0 and every lane reads aligned words of its own row.
         const int row = (item - bd.item_start - bd.n_main) * 32 + lane;
