@@ -5,6 +5,7 @@
 What it does, without copying any reference source into the repository:
   1. reads /root/reference/hm-16.5rc1/source/Lib/TLibEncoder/TEncSearch.cpp and injects three one-line forwarders
      (the same ones INTEGRATION.md shows a maintainer) into a scratch copy under integration/_build/ (git-ignored);
+     likewise TLibCommon/TComRdCost.cpp with one call appended to TComRdCost::init() (the distortion-table hook);
   2. compiles that copy and integration/hm_shim.cpp (our binding code) against the reference headers;
   3. links them with the UNMODIFIED reference objects already built by oracle/Makefile.ref (oracle/_ref/obj, minus the
      stock TEncSearch.o) and video_codecs_b200/libhmb200.so into integration/_build/TAppEncoderB200.
@@ -57,6 +58,18 @@ def patched_source():
     return src
 
 
+def patched_rdcost():
+    """TComRdCost.cpp with one call appended to TComRdCost::init(): the distortion-table hook (INTEGRATION.md, row a2)."""
+    src = open(os.path.join(REF, "source/Lib/TLibCommon/TComRdCost.cpp")).read()
+    marker = '#include "TComRdCost.h"'
+    assert src.count(marker) == 1
+    src = src.replace(marker, marker + "\nvoid hmb200_shim_dist_table(FpDistFunc* table, int n);\n")
+    start = src.index("Void TComRdCost::init()")
+    tail = "  m_iCostScale                 = 0;\n}"
+    end = src.index(tail, start)
+    return src[:end] + "  m_iCostScale                 = 0;\n  hmb200_shim_dist_table(m_afpDistortFunc, DF_TOTAL_FUNCTIONS);\n}" + src[end + len(tail):]
+
+
 def build(force=False):
     if not os.path.isdir(REF):
         return BIN if os.path.exists(BIN) else None
@@ -75,12 +88,17 @@ def build(force=False):
     flags = ["-O3", "-fPIC", "-w", "-DMSYS_LINUX", "-D_LARGEFILE64_SOURCE", "-D_FILE_OFFSET_BITS=64", "-DMSYS_UNIX_LARGEFILE"]
     subprocess.check_call(["g++"] + flags + inc + ["-c", patched, "-o", os.path.join(OUT, "TEncSearch_shim.o")])
     os.remove(patched)                      # the scratch copy of the reference source does not stay in the tree
+    patched_rd = os.path.join(OUT, "TComRdCost_shim.cpp")
+    open(patched_rd, "w").write(patched_rdcost())
+    subprocess.check_call(["g++"] + flags + inc + ["-c", patched_rd, "-o", os.path.join(OUT, "TComRdCost_shim.o")])
+    os.remove(patched_rd)
     subprocess.check_call(["g++"] + flags + inc + ["-c", os.path.join(HERE, "hm_shim.cpp"), "-o", os.path.join(OUT, "hm_shim.o")])
     objs = []
     for sub in ("Lib/TLibCommon", "Lib/TLibEncoder", "Lib/TLibVideoIO", "Lib/TAppCommon", "Lib/libmd5", "App/TAppEncoder"):
         d = os.path.join(OBJ, sub)
-        objs += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(".o") and f != "TEncSearch.o"]
-    subprocess.check_call(["g++", "-o", BIN, os.path.join(OUT, "TEncSearch_shim.o"), os.path.join(OUT, "hm_shim.o")] + objs +
+        objs += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(".o") and f not in ("TEncSearch.o", "TComRdCost.o")]
+    subprocess.check_call(["g++", "-o", BIN, os.path.join(OUT, "TEncSearch_shim.o"), os.path.join(OUT, "TComRdCost_shim.o"),
+                           os.path.join(OUT, "hm_shim.o")] + objs +
                           ["-L" + os.path.dirname(lib), "-lhmb200", "-Wl,-rpath,$ORIGIN/../../video_codecs_b200"])
     write_settings(os.path.join(OUT, "lowdelay_P_settings.cfg"))
     write_settings(os.path.join(OUT, "randomaccess_main10_settings.cfg"), "encoder_randomaccess_main10.cfg")

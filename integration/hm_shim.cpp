@@ -7,6 +7,10 @@
 // HMB200_SHIM=verify         the GPU result is checked call by call against the reference body (abort on mismatch)
 // HMB200_SHIM=off            the reference bodies run (the stock encoder)
 // HMB200_SHIM_LOG=<file>     appends one record per call (PU, window, predictor, MV, SAD / half, quarter, cost)
+// HMB200_SHIM_TABLE=<n>|all  installs forwarders in TComRdCost::m_afpDistortFunc (the FpDistFunc table, TComRdCost.cpp:224-276):
+//                            every n-th call of each family (SAD / SADS / SSE / HADS) is also evaluated by hmb200_dist and compared
+//                            (abort on mismatch), the reference value is returned; `all` returns the GPU value of every call
+//                            (per-call host copies: tiny clips only).  Unset: the table is left alone.
 //
 // The private cost state of TComRdCost (m_uiCost, m_mvPredictor; TLibCommon/TComRdCost.h:118-130) is read with the
 // access-specifier trick below; a maintainer would add three public getters instead.
@@ -58,6 +62,10 @@ struct Shim {
   FILE* log = nullptr;
   std::map<const Pel*, std::pair<int, int> > planes;   // buffer origin -> (plane id, POC)
   unsigned long long n_search = 0, n_frac = 0, n_upload = 0;
+  // distortion-table hook
+  FpDistFunc orig[DF_TOTAL_FUNCTIONS];
+  unsigned long long table_period = 0;               // 0: not installed; 1: every call goes to the GPU
+  unsigned long long table_calls[4] = {0, 0, 0, 0}, table_checked[4] = {0, 0, 0, 0};
 };
 Shim g_shim;
 
@@ -69,6 +77,10 @@ void die(const char* what) {
 void at_exit() {
   fprintf(stderr, "hmb200 shim: %llu integer searches, %llu fractional refinements, %llu plane uploads, %llu kernel launches\n",
           g_shim.n_search, g_shim.n_frac, g_shim.n_upload, (unsigned long long)hmb200_launch_count());
+  if (g_shim.table_period)
+    fprintf(stderr, "hmb200 shim: distortion-table hook: SAD %llu/%llu SADS %llu/%llu SSE %llu/%llu HADS %llu/%llu calls evaluated on the GPU (all equal)\n",
+            g_shim.table_checked[0], g_shim.table_calls[0], g_shim.table_checked[3], g_shim.table_calls[3], g_shim.table_checked[1],
+            g_shim.table_calls[1], g_shim.table_checked[2], g_shim.table_calls[2]);
   if (g_shim.log) fclose(g_shim.log);
 }
 
@@ -233,4 +245,57 @@ bool hmb200_shim_pattern_search_frac(TEncSearch* self, Bool lossless, TComPatter
   rcMvQter.set((Short)qter.x, (Short)qter.y);
   ruiCost = cost;
   return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The distortion function-pointer table (row a2 of the scope table): TComRdCost::init() fills m_afpDistortFunc with the
+// xGetSAD* / xGetSSE* / xGetHADs members (TLibCommon/TComRdCost.cpp:224-276); build_shim.py appends one call to the function
+// below at the end of init().  A forwarder has the FpDistFunc signature (TComRdCost.h:60) and knows its table index.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+int family_of(int idx) {          // HMB200_DF_* of a DFunc index (TLibCommon/TypeDef.h:334-378)
+  if (idx >= DF_SSE && idx <= DF_SSE16N) return HMB200_DF_SSE;
+  if ((idx >= DF_SAD && idx <= DF_SAD16N) || (idx >= DF_SAD12 && idx <= DF_SAD48)) return HMB200_DF_SAD;
+  if ((idx >= DF_SADS && idx <= DF_SADS16N) || (idx >= DF_SADS12 && idx <= DF_SADS48)) return HMB200_DF_SADS;
+  if (idx >= DF_HADS && idx <= DF_HADS16N) return HMB200_DF_HADS;
+  return -1;
+}
+
+Distortion table_forward(int idx, DistParam* p) {
+  const int fam = family_of(idx);
+  const Distortion ref = g_shim.orig[idx](p);
+  if (fam < 0 || p->bApplyWeight || p->iStep != 1 || p->iCols > 64 || p->iRows > 64) return ref;    // outside the path: reference body only
+  const unsigned long long n = ++g_shim.table_calls[fam];
+  if (n % g_shim.table_period != 0) return ref;
+  if (!active()) return ref;
+  hmb200_dist_param dp;
+  dp.pOrg = p->pOrg; dp.pCur = p->pCur; dp.iStrideOrg = p->iStrideOrg; dp.iStrideCur = p->iStrideCur;
+  dp.iRows = p->iRows; dp.iCols = p->iCols; dp.iStep = p->iStep; dp.func = fam; dp.bitDepth = p->bitDepth;
+  dp.bApplyWeight = 0; dp.iSubShift = p->iSubShift;
+  const uint32_t gpu = hmb200_dist(&dp);
+  g_shim.table_checked[fam]++;
+  if ((Distortion)gpu != ref) {
+    fprintf(stderr, "hmb200 shim: m_afpDistortFunc[%d] mismatch %dx%d subShift %d bitDepth %d: gpu %u, reference %u\n", idx, p->iCols, p->iRows,
+            p->iSubShift, p->bitDepth, gpu, (unsigned)ref);
+    abort();
+  }
+  return (Distortion)gpu;
+}
+
+template <int I> Distortion table_entry(DistParam* p) { return table_forward(I, p); }
+template <int I> struct TableFill {
+  static void run(FpDistFunc* t) { if (t[I]) t[I] = table_entry<I>; TableFill<I + 1>::run(t); }
+};
+template <> struct TableFill<DF_TOTAL_FUNCTIONS> { static void run(FpDistFunc*) {} };
+
+}  // namespace
+
+void hmb200_shim_dist_table(FpDistFunc* table, int n) {
+  const char* m = getenv("HMB200_SHIM_TABLE");
+  if (!m || !*m || n != DF_TOTAL_FUNCTIONS) return;
+  g_shim.table_period = !strcmp(m, "all") ? 1ull : (unsigned long long)atoll(m);
+  if (g_shim.table_period == 0) return;
+  for (int i = 0; i < DF_TOTAL_FUNCTIONS; i++) g_shim.orig[i] = table[i];
+  TableFill<0>::run(table);
 }

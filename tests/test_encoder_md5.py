@@ -143,3 +143,37 @@ def test_encoder_bitstream_md5_randomaccess_main10_tz(tmp_path, mode):
     assert "integer searches" in p.stderr and " 0 integer searches" not in p.stderr, "the GPU path was not exercised"
     assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
     assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg_kind", ["lowdelay8", "ra10"])
+def test_distortion_table_hook_in_encoder(tmp_path, cfg_kind):
+    """Row a2 of the scope table: forwarders installed in TComRdCost::m_afpDistortFunc at the end of TComRdCost::init()
+    (TLibCommon/TComRdCost.cpp:224-276).  Every 499th call of each family - whatever the encoder asks the table for: RD-stage
+    SSE of luma and chroma blocks, intra HADs, sub-pel SADs, bi-pred patterns - is also evaluated by hmb200_dist and must
+    equal the reference member function (the shim aborts otherwise); the bitstream stays the stock encoder's."""
+    _need_binary()
+    if cfg_kind == "lowdelay8":
+        gold = json.load(open(GOLD))["3"]
+        frames, cfg = 3, CFG
+        yuv, binf = str(tmp_path / "clip.yuv"), str(tmp_path / "out.bin")
+        meg.write_clip(yuv, frames)
+        args = meg.encoder_args(cfg, yuv, frames, binf)
+    else:
+        if not os.path.exists(CFG_RA10):
+            pytest.skip("integration/_build/randomaccess_main10_settings.cfg not written")
+        gold = None
+        frames = 2
+        yuv, binf = str(tmp_path / "clip.yuv"), str(tmp_path / "out.bin")
+        meg.write_clip_ra10(yuv, frames)
+        args = meg.args_ra10(CFG_RA10, yuv, frames, binf, fast_search=1)
+    p = subprocess.run([BIN] + args, capture_output=True, text=True, env=dict(os.environ, HMB200_SHIM="gpu", HMB200_SHIM_TABLE="499"), timeout=3000)
+    assert p.returncode == 0, p.stderr[-2000:]
+    import re
+    m = re.search(r"distortion-table hook: SAD (\d+)/(\d+) SADS (\d+)/(\d+) SSE (\d+)/(\d+) HADS (\d+)/(\d+)", p.stderr)
+    assert m, p.stderr[-1500:]
+    checked = [int(m.group(i)) for i in (1, 3, 5, 7)]
+    assert checked[2] > 100 and checked[3] > 100 and sum(checked) > 1000, checked      # SSE and HADS are the table's big users
+    if gold is not None:
+        assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
+        assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]

@@ -691,23 +691,30 @@ def test_tile_column_shards_with_halo_crops_equal_unsharded(hm, bd, sr, n_cols):
     def run(fc, fr, jobs):
         idc, idr = reg(np.ascontiguousarray(fc), 0), reg(np.ascontiguousarray(fr), 1)
         try:
-            return hm.me_jobs(idc, idr, jobs, flags_of(1, 1))
+            prep = hm.prepare_jobs(jobs, flags_of(1, 1), bd)
+            prep.run(idc, idr)
+            out, work = prep.fetch(), prep.work()
+            prep.free()
+            return out, work
         finally:
             hm.release_plane(idc)
             hm.release_plane(idr)
 
     full = hm.build_canonical_jobs(W, H, sr, lam)
-    whole = run(f1, f0, full)
-    parts, results, uploaded = [], [], 0
+    whole, work_whole = run(f1, f0, full)
+    parts, results, uploaded, fused = [], [], 0, 0
     for c in range(n_cols):
         x0, x1 = hm.tile_column_range(W, n_cols, c)
         jobs = shard.tile_column_jobs(hm, W, H, n_cols, c, sr, lam)
         c0, c1 = shard.tile_column_crop(W, x0, x1, sr)
-        assert c0 % 16 == 0 and 0 <= c0 < c1 <= W
+        assert c0 % 64 == 0 and 0 <= c0 < c1 <= W
         uploaded += c1 - c0
-        results.append(run(f1[:, c0:c1], f0[:, c0:c1], shard.shift_jobs(jobs, c0)))
+        res, work = run(f1[:, c0:c1], f0[:, c0:c1], shard.shift_jobs(jobs, c0))
+        fused += work["pus_fused"]
+        results.append(res)
         parts.append(jobs)
     merged = shard.merge_shards(parts, results, full)
     assert results_equal(merged, whole) == []
     assert uploaded < n_cols * W                       # the crops are smaller than whole planes per rank
+    assert fused == work_whole["pus_fused"] > 0.9 * len(full)      # a crop keeps every CU on the CU-fused kernels
     assert len(set(zip(whole["mv_x"].tolist(), whole["mv_y"].tolist()))) >= 2

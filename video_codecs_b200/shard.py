@@ -23,16 +23,18 @@ def tile_column_jobs(hm, pic_w, pic_h, n_columns, column, search_range=64, lambd
     return hm.build_canonical_jobs_rect(pic_w, pic_h, (x0, x1), (0, ctus_y), search_range, lambda_cost, pred, max_cu)
 
 
-def tile_column_crop(pic_w, ctu_x0, ctu_x1, search_range, max_cu=64, reach=4, align=16):
+def tile_column_crop(pic_w, ctu_x0, ctu_x1, search_range, max_cu=64, reach=4):
     """Picture columns [c0, c1) that the searches of the tile column's CTUs [ctu_x0, ctu_x1) can read: the column itself
-    +- (search range + the 8-tap interpolation reach), rounded out to `align` samples (the kernels stage 16-byte aligned
-    windows) and clipped to the picture - SURVEY.md 8e's "column +- (R + 80) halo" without the part no window reaches.
+    +- (search range + the 8-tap interpolation reach), clipped to the picture - SURVEY.md 8e's "column +- (R + 80) halo"
+    without the part no window reaches.  Both ends are rounded out to whole CTUs: the kernels recognise the partitions of a
+    CU by its alignment in plane coordinates, so a crop must start on a CTU boundary to keep every CU on the CU-fused path
+    (any other start is still correct, but falls back to the per-PU / generic kernels).
     A rank uploads only this crop of both planes; beyond a crop edge that is not a picture edge the replicated margin holds
     wrong samples, which no candidate of the shard's jobs touches."""
     lo = ctu_x0 * max_cu - search_range - reach
     hi = min(pic_w, ctu_x1 * max_cu) + search_range + reach
-    c0 = max(0, (lo // align) * align)
-    c1 = min(pic_w, -(-hi // align) * align)
+    c0 = max(0, (lo // max_cu) * max_cu)
+    c1 = min(pic_w, -(-hi // max_cu) * max_cu)
     return c0, c1
 
 
