@@ -213,6 +213,38 @@ typedef struct { int32_t pu_x, pu_y, w, h, mv_x, mv_y; } hmb200_mc_desc;
  * the MV-index bit cost and calcRdCost stay on the host. */
 int  hmb200_mc_dist_batch(int cur_plane, int ref_plane, int func, int n, const hmb200_mc_desc* descs, uint32_t* out);
 
+/* One merge / AMVP candidate of a PU.  inter_dir: 1 = list 0, 2 = list 1, 3 = bi-prediction (the interDir of
+ * TComDataCU::getInterMergeCandidates); mv*: quarter pel, clipped by the caller (TComDataCU::clipMv, as xPredInterUni does);
+ * ref*_plane: registered planes of the two reference pictures (ignored for an unused list); bits: the candidate's rate term
+ * (uiBitsCand of xMergeEstimation / m_auiMVPIdxCost[idx][AMVP_MAX_NUM_CANDS] of xGetTemplateCost).  48 bytes. */
+typedef struct {
+  int32_t pu_x, pu_y, w, h;
+  int32_t inter_dir;
+  int32_t mv0_x, mv0_y, ref0_plane;
+  int32_t mv1_x, mv1_y, ref1_plane;
+  int32_t bits;
+} hmb200_mc_cand;
+/* Prediction error of n candidates in one launch set: TComPrediction::motionCompensation (TLibCommon/TComPrediction.cpp:
+ * 539-586) - uni-directional xPredInterBlk, or xPredInterBi: xPredInterBlk(bi = true) per list + TComYuv::addAvg
+ * (TComPrediction.cpp:609-652, 708-724; TComYuv.cpp:352-407) - followed by the distortion: func = HMB200_DF_HADS as
+ * TEncSearch::xGetInterPredictionError (TLibEncoder/TEncSearch.cpp:2805-2826), HMB200_DF_SAD as xGetTemplateCost (:3619-3658).
+ * A bi-directional candidate whose lists name the same plane with the same MV is predicted from list 0 alone
+ * (xCheckIdenticalMotion, TComPrediction.cpp:496-517).  Weighted prediction is out of scope. */
+int  hmb200_mc_cand_dist_batch(int cur_plane, int func, int n, const hmb200_mc_cand* cands, uint32_t* dist);
+/* The candidate loop of TEncSearch::xMergeEstimation (TLibEncoder/TEncSearch.cpp:2868-2892) for n_pu PUs at once: the candidates
+ * of PU i are cands[cand_first[i] .. cand_first[i+1]) in merge-index order (cand_first has n_pu + 1 entries);
+ * cost = error + getCost(bits) = error + ((lambda_cost * bits) >> 16) in UInt arithmetic, strict '<'.  use_hadme = getUseHADME().
+ * best_cand[i] = merge index inside the PU's list, best_cost[i] = ruiCost.  cand_dist (optional, may be NULL) receives every
+ * candidate's error.  getInterMergeCandidates / xRestrictBipredMergeCand stay on the host (they read the CU's neighbours). */
+int  hmb200_merge_estimation_batch(int cur_plane, int n_pu, const int32_t* cand_first, const hmb200_mc_cand* cands, int use_hadme,
+                                   uint32_t lambda_cost, uint32_t* best_cand, uint32_t* best_cost, uint32_t* cand_dist);
+/* The candidate loop of TEncSearch::xEstimateMvPredAMVP (:3457-3469) over xGetTemplateCost: uni-directional prediction from
+ * the candidate MV (list 0 fields of hmb200_mc_cand, inter_dir = 1), SAD, cost = (UInt) calcRdCost(bits, SAD, false, DF_SAD)
+ * = SAD + ((bits * lambda_motion_sad) >> 16) (TLibCommon/TComRdCost.cpp:67-73, 99-108; lambda_motion_sad = m_uiLambdaMotionSAD[0]),
+ * `uiBestCost > uiTmpCost` keeps the first minimum.  best_cand[i] = iBestIdx, best_cost[i] = uiBestCost (= *puiDistBiP). */
+int  hmb200_amvp_estimation_batch(int cur_plane, int n_pu, const int32_t* cand_first, const hmb200_mc_cand* cands,
+                                  uint32_t lambda_motion_sad, uint32_t* best_cand, uint32_t* best_cost, uint32_t* cand_dist);
+
 /* ------------------------------------------------------------------ intra first pass -------------------------- */
 
 /* One block of the intra mode pre-selection.  (x, y): position in the registered ORIGINAL plane; n = 4, 8, 16, 32 or 64;

@@ -541,6 +541,114 @@ uint32_t hmo_mc_dist(int kind, const int16_t* org, int so, const int16_t* ref_at
   return hmo_dist(kind, org, so, pred, 64, w, h, bit_depth, 0);
 }
 
+/* xPredInterBlk with bi == true (TLibCommon/TComPrediction.cpp:668-706: every filter call gets isLast = !bi = false): the
+ * block stays in the 14-bit intermediate domain.  yFrac == 0: one horizontal pass, isFirst (shift 6 - headroom, offset
+ * -8192 << shift; xFrac == 0 is filterCopy's (s << headroom) - 8192, TComInterpolationFilter.cpp:113-124); xFrac == 0: one
+ * vertical pass with the same shift and offset; else horizontal isFirst, then vertical with isFirst = isLast = false:
+ * shift 6, no offset, no clip (:196-251). */
+void hmo_mc_block_bi(const int16_t* ref_at_pu, int sr, int w, int h, int mv_x, int mv_y, int bit_depth, int16_t* dst, int sd)
+{
+  const int16_t* ref = ref_at_pu + asr2(mv_x) + asr2(mv_y) * sr;
+  const int fx = mv_x & 3, fy = mv_y & 3;
+  int head = 14 - bit_depth; if (head < 2) head = 2;
+  const int sh1 = 6 - head;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+    {
+      const int16_t* p = ref + y * sr + x;
+      if (fy == 0)
+      {
+        if (fx == 0) { dst[y * sd + x] = (int16_t)((p[0] << head) - 8192); continue; }
+        int sum = 0;
+        for (int t = 0; t < 8; t++) sum += k_luma_taps[fx][t] * p[t - 3];
+        dst[y * sd + x] = (int16_t)((sum - (8192 << sh1)) >> sh1);
+      }
+      else if (fx == 0)
+      {
+        int sum = 0;
+        for (int t = 0; t < 8; t++) sum += k_luma_taps[fy][t] * p[(t - 3) * sr];
+        dst[y * sd + x] = (int16_t)((sum - (8192 << sh1)) >> sh1);
+      }
+      else
+      {
+        int col[8];
+        for (int r = 0; r < 8; r++)
+        {
+          int sum = 0;
+          for (int t = 0; t < 8; t++) sum += k_luma_taps[fx][t] * p[(r - 3) * sr + t - 3];
+          col[r] = (int16_t)((sum - (8192 << sh1)) >> sh1);
+        }
+        int sum = 0;
+        for (int t = 0; t < 8; t++) sum += k_luma_taps[fy][t] * col[t];
+        dst[y * sd + x] = (int16_t)(sum >> 6);
+      }
+    }
+}
+
+/* TComYuv::addAvg (TLibCommon/TComYuv.cpp:352-407) through TComPrediction::xWeightedAverage (TComPrediction.cpp:708-724):
+ * clip((a + b + offset) >> shift), shift = max(2, 14 - bitDepth) + 1, offset = (1 << (shift - 1)) + 2 * 8192. */
+void hmo_add_avg(const int16_t* a, int sa, const int16_t* b, int sb, int w, int h, int bit_depth, int16_t* dst, int sd)
+{
+  int head = 14 - bit_depth; if (head < 2) head = 2;
+  const int shift = head + 1, offset = (1 << (shift - 1)) + 2 * 8192, maxv = (1 << bit_depth) - 1;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+      dst[y * sd + x] = mc_clip((a[y * sa + x] + b[y * sb + x] + offset) >> shift, maxv);
+}
+
+/* Prediction error of one merge / AMVP candidate (TEncSearch::xGetInterPredictionError, TLibEncoder/TEncSearch.cpp:2805-2826,
+ * after TComPrediction::motionCompensation, TComPrediction.cpp:539-586): inter_dir 1 / 2 = uni-directional from list 0 / 1,
+ * 3 = bi-prediction average - unless both lists point at the same picture with the same MV (xCheckIdenticalMotion, :496-517),
+ * which the caller signals with same_picture and which predicts from list 0 alone. */
+uint32_t hmo_mc_cand_dist(int kind, const int16_t* org, int so, int w, int h, int bit_depth, int inter_dir,
+                          const int16_t* ref0_at_pu, int sr0, int mv0_x, int mv0_y,
+                          const int16_t* ref1_at_pu, int sr1, int mv1_x, int mv1_y, int same_picture)
+{
+  int16_t pred[64 * 64];
+  if (inter_dir == 3 && same_picture && mv0_x == mv1_x && mv0_y == mv1_y) inter_dir = 1;
+  if (inter_dir == 3)
+  {
+    int16_t a[64 * 64], b[64 * 64];
+    hmo_mc_block_bi(ref0_at_pu, sr0, w, h, mv0_x, mv0_y, bit_depth, a, 64);
+    hmo_mc_block_bi(ref1_at_pu, sr1, w, h, mv1_x, mv1_y, bit_depth, b, 64);
+    hmo_add_avg(a, 64, b, 64, w, h, bit_depth, pred, 64);
+  }
+  else if (inter_dir == 1) hmo_mc_block(ref0_at_pu, sr0, w, h, mv0_x, mv0_y, bit_depth, pred, 64);
+  else                     hmo_mc_block(ref1_at_pu, sr1, w, h, mv1_x, mv1_y, bit_depth, pred, 64);
+  return hmo_dist(kind, org, so, pred, 64, w, h, bit_depth, 0);
+}
+
+/* The candidate loop of TEncSearch::xMergeEstimation (TLibEncoder/TEncSearch.cpp:2868-2892): cost = error + getCost(bits)
+ * = error + ((m_uiCost * bits) >> 16) in UInt arithmetic (TLibCommon/TComRdCost.h:177), strict '<' in candidate order.
+ * dist / bits: n candidates of one PU.  Returns the merge index, *cost = its cost. */
+int hmo_merge_pick(const uint32_t* dist, const uint32_t* bits, int n, uint32_t lambda_cost, uint32_t* cost)
+{
+  uint32_t best = 0xffffffffu; int bi = 0;
+  for (int i = 0; i < n; i++)
+  {
+    const uint32_t c = dist[i] + ((uint32_t)(lambda_cost * bits[i]) >> 16);
+    if (c < best) { best = c; bi = i; }
+  }
+  *cost = best;
+  return bi;
+}
+
+/* The candidate loop of TEncSearch::xEstimateMvPredAMVP (TLibEncoder/TEncSearch.cpp:3457-3469) over xGetTemplateCost
+ * (:3619-3658): cost = (UInt) calcRdCost(bits, SAD, false, DF_SAD) = floor(SAD + floor(bits * lambda + 0.5) / 65536) with
+ * lambda = m_uiLambdaMotionSAD[0] as a double (TLibCommon/TComRdCost.cpp:67-73, 99-108) - an integer product, so
+ * SAD + ((bits * lambda) >> 16) in 64 bits; `uiBestCost > uiTmpCost` keeps the first minimum. */
+int hmo_amvp_pick(const uint32_t* sad, const uint32_t* bits, int n, uint32_t lambda_motion_sad, uint32_t* cost)
+{
+  uint32_t best = 0xffffffffu; int bi = 0;
+  for (int i = 0; i < n; i++)
+  {
+    const uint32_t c = (uint32_t)((uint64_t)sad[i] + (((uint64_t)bits[i] * (uint64_t)lambda_motion_sad) >> 16));
+    if (best > c) { best = c; bi = i; }
+  }
+  *cost = best;
+  return bi;
+}
+
 /* ---------------------------------------------------------------- job lists ------------------------------------ */
 
 /* Executes a job list the way TEncSearch::xMotionEstimation (TLibEncoder/TEncSearch.cpp:3663-3760) drives the two

@@ -170,6 +170,31 @@ class Oracle(_Base):
         f.argtypes = [C.c_int, _p16, C.c_int, _p16, C.c_int] + [C.c_int] * 5
         return f(kind, _ptr(oa, oo), os_, _ptr(ra, ro), rs, w, h, mv[0], mv[1], bit_depth)
 
+    def mc_cand_dist(self, kind, org, w, h, inter_dir, ref0, mv0, ref1, mv1, bit_depth=8, same_picture=0):
+        """Prediction error of one merge / AMVP candidate: inter_dir 1 / 2 uni-directional, 3 bi-prediction (addAvg).
+        org / ref0 / ref1: (array, offset of the PU's top-left / co-located sample, stride)."""
+        (oa, oo, os_), (ra, ro, rs), (rb, rbo, rbs) = org, ref0, ref1
+        f = self.lib.hmo_mc_cand_dist
+        f.restype = C.c_uint32
+        f.argtypes = [C.c_int, _p16, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p16, C.c_int, C.c_int, C.c_int, _p16, C.c_int, C.c_int, C.c_int, C.c_int]
+        return f(kind, _ptr(oa, oo), os_, w, h, bit_depth, inter_dir, _ptr(ra, ro), rs, mv0[0], mv0[1], _ptr(rb, rbo), rbs, mv1[0], mv1[1], same_picture)
+
+    def merge_pick(self, dist, bits, lambda_cost):
+        d, b = np.ascontiguousarray(dist, dtype=np.uint32), np.ascontiguousarray(bits, dtype=np.uint32)
+        cost = C.c_uint32()
+        self.lib.hmo_merge_pick.restype = C.c_int
+        self.lib.hmo_merge_pick.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_uint32)]
+        i = self.lib.hmo_merge_pick(d.ctypes.data, b.ctypes.data, len(d), int(lambda_cost), C.byref(cost))
+        return i, cost.value
+
+    def amvp_pick(self, sad, bits, lambda_motion_sad):
+        d, b = np.ascontiguousarray(sad, dtype=np.uint32), np.ascontiguousarray(bits, dtype=np.uint32)
+        cost = C.c_uint32()
+        self.lib.hmo_amvp_pick.restype = C.c_int
+        self.lib.hmo_amvp_pick.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_uint32)]
+        i = self.lib.hmo_amvp_pick(d.ctypes.data, b.ctypes.data, len(d), int(lambda_motion_sad), C.byref(cost))
+        return i, cost.value
+
     def tz_search(self, org, w, h, ref, lt, rb, lambda_cost, pred, cu_xy, pic_wh, search_range=64, imv=None, bit_depth=8, max_cu=64,
                   first_search_stop=1):
         """xTZSearch (FastSearch=1).  imv: pIntegerMv2Nx2NPred (integer pel) or None; first_search_stop:
@@ -276,6 +301,22 @@ class Reference(_Base):
         f.restype = C.c_uint32
         f.argtypes = [C.c_void_p, C.c_int, _p16, C.c_int, C.c_int, C.c_int, C.c_int, _p16, C.c_int] + [C.c_int] * 7
         return f(self.h, kind, _ptr(oa, oo), os_, w, h, bit_depth, _ptr(ra, ro), rs, pic_wh[0], pic_wh[1], margin, pu_xy[0], pu_xy[1], mv[0], mv[1])
+
+    def mc_bi_dist(self, kind, org, w, h, ref_a0, ref_b0, pic_wh, margin, pu_xy, mv0, mv1, bit_depth=8):
+        """The reference's own xPredInterBlk(bi = true) x 2 + xWeightedAverage (TComYuv::addAvg) + distortion.  ref_a0 / ref_b0:
+        (padded array, offset of sample (0,0), stride) of the list-0 / list-1 pictures (same stride)."""
+        (oa, oo, os_), (ra, ro, rs), (rb, rbo, _) = org, ref_a0, ref_b0
+        f = self.lib.hmref_mc_bi_dist
+        f.restype = C.c_uint32
+        f.argtypes = [C.c_void_p, C.c_int, _p16, C.c_int, C.c_int, C.c_int, C.c_int, _p16, _p16, C.c_int] + [C.c_int] * 9
+        return f(self.h, kind, _ptr(oa, oo), os_, w, h, bit_depth, _ptr(ra, ro), _ptr(rb, rbo), rs, pic_wh[0], pic_wh[1], margin, pu_xy[0], pu_xy[1],
+                 mv0[0], mv0[1], mv1[0], mv1[1])
+
+    def template_rd_cost(self, bits, dist, lam, bit_depth=8):
+        f = self.lib.hmref_template_rd_cost
+        f.restype = C.c_uint32
+        f.argtypes = [C.c_uint32, C.c_uint32, C.c_double, C.c_int]
+        return f(int(bits), int(dist), float(lam), bit_depth)
 
     def tz_search(self, org, w, h, ref, lt, rb, lambda_cost, pred, cu_xy, pic_wh, search_range=64, imv=None, bit_depth=8, max_cu=64,
                   first_search_stop=1):

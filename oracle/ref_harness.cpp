@@ -148,6 +148,56 @@ struct Harness : public TEncSearch
     return d;
   }
 
+  // Bi-prediction the way TComPrediction::xPredInterBi builds it (TComPrediction.cpp:609-652): xPredInterBlk with bi = true from
+  // each list into its own TComYuv, then TComYuv::addAvg through xWeightedAverage (:708-724); distortion as in mcDist.
+  void fillRef(TComPicYuv& refPic, const Pel* ref0, int refStride, int picW, int picH, int margin)
+  {
+    refPic.create(picW, picH, CHROMA_400, 64, 64, 4, true);
+    const int m = refPic.getMarginX(COMPONENT_Y);
+    for (int y = -m; y < picH + m; y++)
+      for (int x = -m; x < picW + m; x++)
+      {
+        const int sy = y < -margin ? -margin : (y >= picH + margin ? picH + margin - 1 : y);
+        const int sx = x < -margin ? -margin : (x >= picW + margin ? picW + margin - 1 : x);
+        refPic.getAddr(COMPONENT_Y)[y * refPic.getStride(COMPONENT_Y) + x] = ref0[sy * refStride + sx];
+      }
+  }
+  uint32_t mcBiDist(int kind, Pel* org, int orgStride, int w, int h, int bitDepth, const Pel* refA, const Pel* refB, int refStride,
+                    int picW, int picH, int margin, int pux, int puy, int mv0x, int mv0y, int mv1x, int mv1y)
+  {
+    TComPicYuv picA, picB;
+    fillRef(picA, refA, refStride, picW, picH, margin);
+    fillRef(picB, refB, refStride, picW, picH, margin);
+    TComPic pic;
+    cu.m_pcPic = &pic; cu.m_ctuRsAddr = 0; cu.m_absZIdxInCtu = 0;
+    TComYuv a, b, dst;
+    a.create(64, 64, CHROMA_400); b.create(64, 64, CHROMA_400); dst.create(64, 64, CHROMA_400);
+    TComMv m0((Short)(mv0x + 4 * pux), (Short)(mv0y + 4 * puy)), m1((Short)(mv1x + 4 * pux), (Short)(mv1y + 4 * puy));
+    pic.m_apcPicYuv[TComPic::PIC_YUV_REC] = &picA;
+    xPredInterBlk(COMPONENT_Y, &cu, &picA, 0, &m0, w, h, &a, true, bitDepth);
+    pic.m_apcPicYuv[TComPic::PIC_YUV_REC] = &picB;
+    xPredInterBlk(COMPONENT_Y, &cu, &picB, 0, &m1, w, h, &b, true, bitDepth);
+    BitDepths bds; bds.recon[0] = bds.recon[1] = bitDepth;
+#if O0043_BEST_EFFORT_DECODING
+    bds.stream[0] = bds.stream[1] = bitDepth;
+#endif
+    xWeightedAverage(&a, &b, 0, 0, 0, w, h, &dst, bds);
+    uint32_t d;
+    if (kind == 0)
+      d = rd.getDistPart(bitDepth, dst.getAddr(COMPONENT_Y, 0), dst.getStride(COMPONENT_Y), org, orgStride, w, h, COMPONENT_Y, DF_SAD);
+    else
+    {
+      DistParam dp; dp.bApplyWeight = false;
+      rd.setDistParam(dp, bitDepth, org, orgStride, dst.getAddr(COMPONENT_Y, 0), dst.getStride(COMPONENT_Y), w, h, true);
+      d = dp.DistFunc(&dp);
+    }
+    a.destroy(); b.destroy(); dst.destroy();
+    pic.m_apcPicYuv[TComPic::PIC_YUV_REC] = NULL;
+    cu.m_pcPic = NULL;
+    picA.destroy(); picB.destroy();
+    return d;
+  }
+
   // TEncSearch::xTZSearch (TEncSearch.cpp:3881) as xMotionEstimation / xPatternSearchFast reach it with FastSearch = 1.
   // The CU only has to answer clipMv(): picture size and max CU size through its slice's SPS, and its own position.
   TComSPS    sps;
@@ -303,6 +353,27 @@ uint32_t hmref_mc_dist(void* hv, int kind, const int16_t* org, int org_stride, i
 {
   return static_cast<Harness*>(hv)->mcDist(kind, const_cast<Pel*>(org), org_stride, w, h, bit_depth, ref0, ref_stride, pic_w, pic_h,
                                            margin, pu_x, pu_y, mv_x, mv_y);
+}
+
+uint32_t hmref_mc_bi_dist(void* hv, int kind, const int16_t* org, int org_stride, int w, int h, int bit_depth, const int16_t* ref_a,
+                          const int16_t* ref_b, int ref_stride, int pic_w, int pic_h, int margin, int pu_x, int pu_y, int mv0_x, int mv0_y,
+                          int mv1_x, int mv1_y)
+{
+  return static_cast<Harness*>(hv)->mcBiDist(kind, const_cast<Pel*>(org), org_stride, w, h, bit_depth, ref_a, ref_b, ref_stride, pic_w, pic_h,
+                                             margin, pu_x, pu_y, mv0_x, mv0_y, mv1_x, mv1_y);
+}
+
+// (UInt) calcRdCost(bits, dist, false, DF_SAD) with m_uiLambdaMotionSAD[0] = lambda_motion_sad: what xGetTemplateCost adds to the SAD
+uint32_t hmref_template_rd_cost(uint32_t bits, uint32_t dist, double lambda, int bit_depth)
+{
+  TComRdCost rd;
+  rd.init();
+  BitDepths bd; bd.recon[0] = bd.recon[1] = bit_depth;
+#if O0043_BEST_EFFORT_DECODING
+  bd.stream[0] = bd.stream[1] = bit_depth;
+#endif
+  rd.setLambda(lambda, bd);
+  return (uint32_t)rd.calcRdCost(bits, dist, false, DF_SAD);
 }
 
 void hmref_tz_search(void* hv, const int16_t* org, int org_stride, int w, int h, int bit_depth,

@@ -184,7 +184,30 @@ def make_mc_golden():
     print("wrote mc_golden.npz")
 
 
+def make_mc_cand_golden():
+    """tests/golden/mc_cand_golden.npz: bi-prediction (xPredInterBlk bi = true x 2 + xWeightedAverage) + SAD / HADs of the unmodified
+    reference for tests/test_mc_cand.py::bi_cases."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_mc_cand as T
+    ref_impl = Reference(fen=1, hadme=1)
+    out = {}
+    for bd in (8, 10):
+        f, pads, o0, stride = T.frames(bd)
+        cur, ra, rb = pads[1], pads[0], pads[2]
+        cs = T.bi_cases(np.random.default_rng(17 + bd), 200)
+        out[f"frame2_{bd}"] = f[2]
+        out[f"cases_{bd}"] = np.array(cs, dtype=np.int64)
+        out[f"expected_{bd}"] = np.array([ref_impl.mc_bi_dist(kind, (cur, o0 + py * stride + px, stride), w, h, (ra, o0, stride), (rb, o0, stride),
+                                                              (T.W, T.H), T.MARGIN, (px, py), (ax, ay), (bx, by), bd)
+                                          for (px, py, w, h, ax, ay, bx, by, kind) in cs], dtype=np.int64)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "mc_cand_golden.npz"), **out)
+    print("wrote mc_cand_golden.npz")
+
+
 if __name__ == "__main__":
+    if "--mc-cand" in sys.argv:
+        make_mc_cand_golden()
+        sys.exit(0)
     if "--mc" in sys.argv:
         make_mc_golden()
         sys.exit(0)

@@ -6,4 +6,4 @@ back to a CPU implementation: if the shared library is missing, importing `video
 """
 from .api import (HMB200, HMB200Error, JOB_DTYPE, RESULT_DTYPE, DIST_DESC_DTYPE,  # noqa: F401
                   FLAG_FEN, FLAG_HADME, FLAG_FRAC, FLAG_TZ, FLAG_TZ_STOP, TZ_EXTRA_DTYPE, MC_DESC_DTYPE, INTRA_BLOCK_DTYPE, DF_SAD, DF_SSE, DF_HADS, DF_SADS, lib_path,
-                  RESULT16_DTYPE, widen_results16)
+                  RESULT16_DTYPE, widen_results16, MC_CAND_DTYPE)

@@ -20,6 +20,9 @@ DIST_DESC_DTYPE = np.dtype([("org_plane", "<i4"), ("org_x", "<i4"), ("org_y", "<
                             ("cur_plane", "<i4"), ("cur_x", "<i4"), ("cur_y", "<i4"),
                             ("w", "<i4"), ("h", "<i4"), ("sub_shift", "<i4"), ("reserved", "<i4")])
 MC_DESC_DTYPE = np.dtype([("pu_x", "<i4"), ("pu_y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("mv_x", "<i4"), ("mv_y", "<i4")])
+MC_CAND_DTYPE = np.dtype([("pu_x", "<i4"), ("pu_y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("inter_dir", "<i4"), ("mv0_x", "<i4"), ("mv0_y", "<i4"),
+                          ("ref0_plane", "<i4"), ("mv1_x", "<i4"), ("mv1_y", "<i4"), ("ref1_plane", "<i4"), ("bits", "<i4")])
+assert MC_CAND_DTYPE.itemsize == 48
 INTRA_BLOCK_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("n", "<i4"), ("ref_off", "<i4"), ("flags", "<i4"), ("reserved", "<i4")])
 TZ_EXTRA_DTYPE = np.dtype([("cu_x", "<i4"), ("cu_y", "<i4"), ("has_imv", "<i4"), ("imv_x", "<i4"), ("imv_y", "<i4"),
                            ("reserved", "<i4", (3,))])
@@ -80,6 +83,9 @@ def _load():
         "hmb200_dist": (u32, [C.POINTER(_DistParam)]),
         "hmb200_dist_batch": (i32, [i32, i32, i32, vp, vp]),
         "hmb200_mc_dist_batch": (i32, [i32, i32, i32, i32, vp, vp]),
+        "hmb200_mc_cand_dist_batch": (i32, [i32, i32, i32, vp, vp]),
+        "hmb200_merge_estimation_batch": (i32, [i32, i32, vp, vp, i32, u32, vp, vp, vp]),
+        "hmb200_amvp_estimation_batch": (i32, [i32, i32, vp, vp, u32, vp, vp, vp]),
         "hmb200_intra_modes_had_batch": (i32, [i32, i32, vp, vp, i32, vp]),
         "hmb200_intra_modes_had": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp]),
         "hmb200_pattern_search": (i32, [C.POINTER(_Pattern), vp, i32, _Mv, _Mv, C.POINTER(_CostState), i32,
@@ -264,6 +270,28 @@ class HMB200:
         out = np.zeros(len(descs), dtype=np.uint32)
         self._check(self.lib.hmb200_mc_dist_batch(cur_plane, ref_plane, func, len(descs), descs.ctypes.data, out.ctypes.data))
         return out
+
+    def mc_cand_dist_batch(self, cur_plane, func, cands):
+        cands = np.ascontiguousarray(cands, dtype=MC_CAND_DTYPE)
+        out = np.zeros(len(cands), dtype=np.uint32)
+        self._check(self.lib.hmb200_mc_cand_dist_batch(cur_plane, func, len(cands), cands.ctypes.data, out.ctypes.data))
+        return out
+
+    def _estimation(self, fn, cur_plane, cand_first, cands, *mid):
+        cands = np.ascontiguousarray(cands, dtype=MC_CAND_DTYPE)
+        first = np.ascontiguousarray(cand_first, dtype=np.int32)
+        n_pu = len(first) - 1
+        best, cost, dist = np.zeros(n_pu, dtype=np.uint32), np.zeros(n_pu, dtype=np.uint32), np.zeros(len(cands), dtype=np.uint32)
+        self._check(fn(cur_plane, n_pu, first.ctypes.data, cands.ctypes.data, *mid, best.ctypes.data, cost.ctypes.data, dist.ctypes.data))
+        return best, cost, dist
+
+    def merge_estimation_batch(self, cur_plane, cand_first, cands, use_hadme, lambda_cost):
+        """xMergeEstimation's candidate loop for many PUs: returns (merge index, cost, per-candidate error)."""
+        return self._estimation(self.lib.hmb200_merge_estimation_batch, cur_plane, cand_first, cands, int(use_hadme), int(lambda_cost))
+
+    def amvp_estimation_batch(self, cur_plane, cand_first, cands, lambda_motion_sad):
+        """xEstimateMvPredAMVP's candidate loop (xGetTemplateCost) for many PUs: returns (MVP index, cost, per-candidate SAD)."""
+        return self._estimation(self.lib.hmb200_amvp_estimation_batch, cur_plane, cand_first, cands, int(lambda_motion_sad))
 
     # -- intra first pass ------------------------------------------------------------------------------------------
     def intra_modes_had_batch(self, org_plane, blocks, refs):

@@ -20,6 +20,7 @@
 #include "hmb200_intra.cuh"
 #include "hmb200_frac.cuh"
 #include "hmb200_tz.cuh"
+#include "hmb200_mc_cand.cuh"
 
 using namespace hmb200;
 
@@ -776,6 +777,139 @@ int hmb200_mc_dist_batch(int cur_plane, int ref_plane, int func, int n, const hm
   if (e == cudaSuccess) e = cudaStreamSynchronize(G.stream);
   frac_free_schedule(&fs);
   if (nl < 0 || e != cudaSuccess) return fail(HMB200_ERR_CUDA, std::string("hmb200_mc_dist_batch: ") + cudaGetErrorString(cudaGetLastError()));
+  return HMB200_OK;
+}
+
+// merge / AMVP candidates: uni- or bi-directional prediction + distortion per candidate, candidate loops on the host
+static int mc_cand_run(int cur_plane, int func, int n, const hmb200_mc_cand* cands, uint32_t* dist, const char* who) {
+  Plane* pc = get_plane(cur_plane);
+  if (!pc) return fail(HMB200_ERR_ARG, std::string(who) + ": unknown current plane");
+  if (!cands || !dist || (func != HMB200_DF_SAD && func != HMB200_DF_SADS && func != HMB200_DF_HADS))
+    return fail(HMB200_ERR_ARG, std::string(who) + ": bad arguments (func must be SAD or HADS)");
+  const int bps = pc->d.bytes_per_sample, bd = pc->d.bit_depth;
+  std::vector<McCandDev> dev((size_t)n);
+  std::vector<uint32_t> t8, t4;
+  if (n >= (1 << 24)) return fail(HMB200_ERR_ARG, std::string(who) + ": more than 2^24 candidates in one batch");
+  for (int i = 0; i < n; i++) {
+    const hmb200_mc_cand& c = cands[i];
+    if (!supported_pu(c.w, c.h) || c.inter_dir < 1 || c.inter_dir > 3)
+      return fail(HMB200_ERR_ARG, std::string(who) + ": unsupported PU size or inter_dir in candidate " + std::to_string(i));
+    if (!box_inside(pc->d, Box{c.pu_x, c.pu_y, c.pu_x + c.w, c.pu_y + c.h}))
+      return fail(HMB200_ERR_ARG, std::string(who) + ": PU of candidate " + std::to_string(i) + " leaves the padded current plane");
+    McCandDev d{};
+    d.org = reinterpret_cast<const char*>(pc->d.base) + ((size_t)(c.pu_y + pc->d.margin_y) * pc->d.pitch + (c.pu_x + pc->d.margin_x)) * bps;
+    d.org_pitch = pc->d.pitch; d.w = c.w; d.h = c.h;
+    int dir = c.inter_dir;
+    if (dir == 3 && c.ref0_plane == c.ref1_plane && c.mv0_x == c.mv1_x && c.mv0_y == c.mv1_y) dir = 1;     // xCheckIdenticalMotion
+    for (int l = 0; l < 2; l++) {
+      if (!(dir & (1 << l))) continue;
+      Plane* pr = get_plane(l ? c.ref1_plane : c.ref0_plane);
+      const int mvx = l ? c.mv1_x : c.mv0_x, mvy = l ? c.mv1_y : c.mv0_y;
+      if (!pr) return fail(HMB200_ERR_ARG, std::string(who) + ": unknown reference plane in candidate " + std::to_string(i));
+      if (pr->d.bytes_per_sample != bps || pr->d.bit_depth != bd)
+        return fail(HMB200_ERR_ARG, std::string(who) + ": reference and current planes differ in bit depth");
+      const int ix = c.pu_x + (mvx >> 2), iy = c.pu_y + (mvy >> 2);
+      if (!box_inside(pr->d, Box{ix - FRAC_REACH, iy - FRAC_REACH, ix + c.w + FRAC_REACH, iy + c.h + FRAC_REACH}))
+        return fail(HMB200_ERR_ARG, std::string(who) + ": the motion-compensated block of candidate " + std::to_string(i) +
+                                        " (with the 8-tap reach) leaves the padded reference plane");
+      const void* at = reinterpret_cast<const char*>(pr->d.base) + ((size_t)(c.pu_y + pr->d.margin_y) * pr->d.pitch + (c.pu_x + pr->d.margin_x)) * bps;
+      if (l == 0) { d.ref0 = at; d.ref0_pitch = pr->d.pitch; d.mv0_x = mvx; d.mv0_y = mvy; }
+      else        { d.ref1 = at; d.ref1_pitch = pr->d.pitch; d.mv1_x = mvx; d.mv1_y = mvy; }
+    }
+    dev[(size_t)i] = d;
+    const int e = (c.w % 8 == 0 && c.h % 8 == 0) ? 8 : 4;                 // xGetHADs tile choice (TComRdCost.cpp:1544-1572); SAD: any tiling
+    std::vector<uint32_t>& dst = (e == 8) ? t8 : t4;
+    for (int ty = 0; ty < c.h / e; ty++)
+      for (int tx = 0; tx < c.w / e; tx++) dst.push_back(frac_pack_tile((uint32_t)i, (uint32_t)tx, (uint32_t)ty));
+  }
+  auto up64 = [](size_t v) { return (v + 63) & ~(size_t)63; };
+  const size_t cb = up64(dev.size() * sizeof(McCandDev)), b8 = up64(t8.size() * 4), b4 = up64(t4.size() * 4), ob = (size_t)n * sizeof(uint32_t);
+  int rc = ensure_dstage(cb + b8 + b4 + ob + 256);
+  if (rc != HMB200_OK) return rc;
+  char* base = reinterpret_cast<char*>(G.dstage);
+  McCandDev* d_c = reinterpret_cast<McCandDev*>(base);
+  uint32_t* d_t8 = reinterpret_cast<uint32_t*>(base + cb);
+  uint32_t* d_t4 = reinterpret_cast<uint32_t*>(base + cb + b8);
+  uint32_t* d_out = reinterpret_cast<uint32_t*>(base + cb + b8 + b4);
+  CUDA_TRY(cudaMemcpyAsync(d_c, dev.data(), dev.size() * sizeof(McCandDev), cudaMemcpyHostToDevice, G.stream));
+  if (!t8.empty()) CUDA_TRY(cudaMemcpyAsync(d_t8, t8.data(), t8.size() * 4, cudaMemcpyHostToDevice, G.stream));
+  if (!t4.empty()) CUDA_TRY(cudaMemcpyAsync(d_t4, t4.data(), t4.size() * 4, cudaMemcpyHostToDevice, G.stream));
+  CUDA_TRY(cudaMemsetAsync(d_out, 0, ob, G.stream));
+  const bool had = func == HMB200_DF_HADS;
+  auto launch = [&](auto tag, int N_, const uint32_t* d_t, int nt) {
+    typedef decltype(tag) T;
+    if (nt == 0) return;
+    const int blocks = (nt + 127) / 128;
+    if (N_ == 8) { if (had) k_mc_cand_tiles<T, 8, true><<<blocks, 128, 0, G.stream>>>(d_c, d_t, nt, d_out, bd); else k_mc_cand_tiles<T, 8, false><<<blocks, 128, 0, G.stream>>>(d_c, d_t, nt, d_out, bd); }
+    else         { if (had) k_mc_cand_tiles<T, 4, true><<<blocks, 128, 0, G.stream>>>(d_c, d_t, nt, d_out, bd); else k_mc_cand_tiles<T, 4, false><<<blocks, 128, 0, G.stream>>>(d_c, d_t, nt, d_out, bd); }
+    G.launches++;
+  };
+  if (bps == 1) { launch(uint8_t(), 8, d_t8, (int)t8.size()); launch(uint8_t(), 4, d_t4, (int)t4.size()); }
+  else          { launch(int16_t(), 8, d_t8, (int)t8.size()); launch(int16_t(), 4, d_t4, (int)t4.size()); }
+  if (bd > 8) { k_mc_cand_finish<<<(n + 255) / 256, 256, 0, G.stream>>>(d_out, n, bd); G.launches++; }
+  CUDA_TRY(cudaMemcpyAsync(dist, d_out, ob, cudaMemcpyDeviceToHost, G.stream));
+  CUDA_TRY(cudaStreamSynchronize(G.stream));
+  CUDA_TRY(cudaGetLastError());
+  return HMB200_OK;
+}
+
+int hmb200_mc_cand_dist_batch(int cur_plane, int func, int n, const hmb200_mc_cand* cands, uint32_t* dist) {
+  NEED_READY();
+  if (n <= 0) return HMB200_OK;
+  return mc_cand_run(cur_plane, func, n, cands, dist, "hmb200_mc_cand_dist_batch");
+}
+
+static int cand_ranges_ok(int n_pu, const int32_t* cand_first) {
+  if (n_pu < 0 || !cand_first || cand_first[0] != 0) return 0;
+  for (int i = 0; i < n_pu; i++) if (cand_first[i + 1] < cand_first[i]) return 0;
+  return 1;
+}
+
+int hmb200_merge_estimation_batch(int cur_plane, int n_pu, const int32_t* cand_first, const hmb200_mc_cand* cands, int use_hadme,
+                                  uint32_t lambda_cost, uint32_t* best_cand, uint32_t* best_cost, uint32_t* cand_dist) {
+  NEED_READY();
+  if (n_pu == 0) return HMB200_OK;
+  if (!cand_ranges_ok(n_pu, cand_first) || !best_cand || !best_cost) return fail(HMB200_ERR_ARG, "hmb200_merge_estimation_batch: bad arguments");
+  const int n = cand_first[n_pu];
+  std::vector<uint32_t> dist((size_t)std::max(n, 1));
+  if (n > 0) {
+    const int rc = mc_cand_run(cur_plane, use_hadme ? HMB200_DF_HADS : HMB200_DF_SAD, n, cands, dist.data(), "hmb200_merge_estimation_batch");
+    if (rc != HMB200_OK) return rc;
+  }
+  for (int i = 0; i < n_pu; i++) {                     // TEncSearch.cpp:2868-2892
+    uint32_t best = 0xffffffffu, bi = 0;
+    for (int k = cand_first[i]; k < cand_first[i + 1]; k++) {
+      const uint32_t cost = dist[(size_t)k] + ((lambda_cost * (uint32_t)cands[k].bits) >> 16);
+      if (cost < best) { best = cost; bi = (uint32_t)(k - cand_first[i]); }
+    }
+    best_cand[i] = bi; best_cost[i] = best;
+  }
+  if (cand_dist && n > 0) memcpy(cand_dist, dist.data(), (size_t)n * sizeof(uint32_t));
+  return HMB200_OK;
+}
+
+int hmb200_amvp_estimation_batch(int cur_plane, int n_pu, const int32_t* cand_first, const hmb200_mc_cand* cands, uint32_t lambda_motion_sad,
+                                 uint32_t* best_cand, uint32_t* best_cost, uint32_t* cand_dist) {
+  NEED_READY();
+  if (n_pu == 0) return HMB200_OK;
+  if (!cand_ranges_ok(n_pu, cand_first) || !best_cand || !best_cost) return fail(HMB200_ERR_ARG, "hmb200_amvp_estimation_batch: bad arguments");
+  const int n = cand_first[n_pu];
+  for (int k = 0; k < n; k++)
+    if (cands[k].inter_dir != 1) return fail(HMB200_ERR_ARG, "hmb200_amvp_estimation_batch: AMVP candidates are uni-directional (inter_dir = 1, list-0 fields)");
+  std::vector<uint32_t> dist((size_t)std::max(n, 1));
+  if (n > 0) {
+    const int rc = mc_cand_run(cur_plane, HMB200_DF_SAD, n, cands, dist.data(), "hmb200_amvp_estimation_batch");
+    if (rc != HMB200_OK) return rc;
+  }
+  for (int i = 0; i < n_pu; i++) {                     // TEncSearch.cpp:3457-3469 over xGetTemplateCost
+    uint32_t best = 0xffffffffu, bi = 0;
+    for (int k = cand_first[i]; k < cand_first[i + 1]; k++) {
+      const uint32_t cost = (uint32_t)((uint64_t)dist[(size_t)k] + (((uint64_t)(uint32_t)cands[k].bits * (uint64_t)lambda_motion_sad) >> 16));
+      if (best > cost) { best = cost; bi = (uint32_t)(k - cand_first[i]); }
+    }
+    best_cand[i] = bi; best_cost[i] = best;
+  }
+  if (cand_dist && n > 0) memcpy(cand_dist, dist.data(), (size_t)n * sizeof(uint32_t));
   return HMB200_OK;
 }
 
