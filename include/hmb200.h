@@ -291,6 +291,20 @@ int  hmb200_pattern_search_frac(int lossless, const hmb200_pattern* key, const i
                                 hmb200_mv mv_int, const hmb200_cost_state* cs, int flags,
                                 hmb200_mv* half_out, hmb200_mv* qter_out, uint32_t* cost_out);
 
+/* Both calls of TEncSearch::xMotionEstimation for one PU in ONE device round trip (TLibEncoder/TEncSearch.cpp:3728 and :3749:
+ * xPatternSearch, then xPatternSearchFracDIF on the integer MV it found, same pattern, reference, predictor and m_uiCost).
+ * The in-encoder frontend calls this from the xPatternSearch forwarder and hands the refinement's outputs to the
+ * xPatternSearchFracDIF forwarder that follows (integration/hm_shim.cpp); flags: HMB200_FLAG_FEN | HMB200_FLAG_HADME. */
+int  hmb200_pattern_search_and_refine(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride,
+                                      hmb200_mv lt, hmb200_mv rb, const hmb200_cost_state* cs, int flags,
+                                      hmb200_mv* mv_out, uint32_t* sad_out, hmb200_mv* half_out, hmb200_mv* qter_out, uint32_t* frac_cost_out);
+
+/* The same for FastSearch = 1: xTZSearch, then xPatternSearchFracDIF on its MV.  flags: FEN | TZ_STOP | HADME. */
+int  hmb200_pattern_search_tz_and_refine(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride, hmb200_mv lt, hmb200_mv rb,
+                                         const hmb200_cost_state* cs, int flags, const struct hmb200_tz_extra_s* extra, int pic_w, int pic_h,
+                                         int max_cu, int search_range, hmb200_mv* mv_out, uint32_t* sad_out, hmb200_mv* half_out,
+                                         hmb200_mv* qter_out, uint32_t* frac_cost_out);
+
 /* ------------------------------------------------------------------ searches, batched ------------------------- */
 
 /* Many PUs of one (current, reference) plane pair.  Jobs are grouped by CTU and search window on the host side; each

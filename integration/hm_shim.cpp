@@ -14,6 +14,7 @@
 //
 // The private cost state of TComRdCost (m_uiCost, m_mvPredictor; TLibCommon/TComRdCost.h:118-130) is read with the
 // access-specifier trick below; a maintainer would add three public getters instead.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -61,7 +62,18 @@ struct Shim {
   bool in_reference = false;          // re-entrancy guard of verify mode
   FILE* log = nullptr;
   std::map<const Pel*, std::pair<int, int> > planes;   // buffer origin -> (plane id, POC)
-  unsigned long long n_search = 0, n_frac = 0, n_upload = 0;
+  unsigned long long n_search = 0, n_frac = 0, n_upload = 0, n_frac_fused = 0;
+  double seconds = 0.0;                              // wall time spent inside the forwarders (host copies, launches, waits)
+  // xMotionEstimation calls xPatternSearch and then xPatternSearchFracDIF on the MV it found (TEncSearch.cpp:3728, 3749): the
+  // search forwarder runs both in one device round trip and keeps the refinement for the forwarder that follows
+  struct Fused {
+    bool valid = false;
+    const Pel* roi = nullptr; const Pel* ref = nullptr;
+    int w = 0, h = 0, flags_hadme = 0;
+    hmb200_mv mv{0, 0}, half{0, 0}, qter{0, 0};
+    hmb200_cost_state cs{0, {0, 0}};
+    uint32_t cost = 0;
+  } fused;
   // distortion-table hook
   FpDistFunc orig[DF_TOTAL_FUNCTIONS];
   unsigned long long table_period = 0;               // 0: not installed; 1: every call goes to the GPU
@@ -69,14 +81,21 @@ struct Shim {
 };
 Shim g_shim;
 
+struct Stopwatch {                                   // adds a forwarder's wall time to g_shim.seconds
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  ~Stopwatch();
+};
+
+Stopwatch::~Stopwatch() { g_shim.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+
 void die(const char* what) {
   fprintf(stderr, "hmb200 shim: %s: %s\n", what, hmb200_last_error());
   abort();                            // like the reference: assert/exit, no CPU fallback
 }
 
 void at_exit() {
-  fprintf(stderr, "hmb200 shim: %llu integer searches, %llu fractional refinements, %llu plane uploads, %llu kernel launches\n",
-          g_shim.n_search, g_shim.n_frac, g_shim.n_upload, (unsigned long long)hmb200_launch_count());
+  fprintf(stderr, "hmb200 shim: %llu integer searches, %llu fractional refinements (%llu of them served by the search's round trip), %llu plane uploads, %llu kernel launches, %.2f s inside the forwarders\n",
+          g_shim.n_search, g_shim.n_frac, g_shim.n_frac_fused, g_shim.n_upload, (unsigned long long)hmb200_launch_count(), g_shim.seconds);
   if (g_shim.table_period)
     fprintf(stderr, "hmb200 shim: distortion-table hook: SAD %llu/%llu SADS %llu/%llu SSE %llu/%llu HADS %llu/%llu calls evaluated on the GPU (all equal)\n",
             g_shim.table_checked[0], g_shim.table_calls[0], g_shim.table_checked[3], g_shim.table_calls[3], g_shim.table_checked[1],
@@ -124,6 +143,7 @@ hmb200_pattern pattern_of(TComPattern* key) {
 // (TLibCommon/TComSlice.cpp:351-377); a picture buffer is re-used for later pictures, hence the POC check.
 void hmb200_shim_ref_plane(TComPic* pic) {
   if (!active()) return;
+  Stopwatch sw;
   TComPicYuv* rec = pic->getPicYuvRec();
   const Pel* origin = rec->getAddr(COMPONENT_Y);
   const int poc = pic->getPOC();
@@ -145,13 +165,22 @@ void hmb200_shim_ref_plane(TComPic* pic) {
 bool hmb200_shim_pattern_search(TEncSearch* self, TComPattern* key, Pel* piRefY, Int iRefStride, TComMv* lt, TComMv* rb,
                                 TComMv& rcMv, Distortion& ruiSAD) {
   if (!active()) return false;
+  Stopwatch sw;
   if (self->m_cDistParam.bApplyWeight) { fprintf(stderr, "hmb200 shim: weighted prediction is out of scope\n"); abort(); }
   const hmb200_pattern p = pattern_of(key);
   const hmb200_cost_state cs = cost_state(self->m_pcRdCost);
   hmb200_mv l = {lt->getHor(), lt->getVer()}, r = {rb->getHor(), rb->getVer()}, mv;
   uint32_t sad = 0;
   const int flags = self->m_pcEncCfg->getUseFastEnc() ? HMB200_FLAG_FEN : 0;
-  if (hmb200_pattern_search(&p, piRefY, iRefStride, l, r, &cs, flags, &mv, &sad) != HMB200_OK) die("hmb200_pattern_search");
+  static const bool fuse = getenv("HMB200_SHIM_NO_FUSE") == nullptr;
+  g_shim.fused.valid = false;
+  if (fuse) {
+    const int hadme = self->m_pcEncCfg->getUseHADME() ? HMB200_FLAG_HADME : 0;
+    Shim::Fused& f = g_shim.fused;
+    if (hmb200_pattern_search_and_refine(&p, piRefY, iRefStride, l, r, &cs, flags | hadme, &mv, &sad, &f.half, &f.qter, &f.cost) != HMB200_OK)
+      die("hmb200_pattern_search_and_refine");
+    f.valid = true; f.roi = p.roi; f.ref = piRefY; f.w = p.width; f.h = p.height; f.flags_hadme = hadme; f.mv = mv; f.cs = cs;
+  } else if (hmb200_pattern_search(&p, piRefY, iRefStride, l, r, &cs, flags, &mv, &sad) != HMB200_OK) die("hmb200_pattern_search");
   g_shim.n_search++;
   if (g_shim.mode == VERIFY) {
     TComMv ref_mv; Distortion ref_sad = 0;
@@ -177,6 +206,8 @@ bool hmb200_shim_pattern_search(TEncSearch* self, TComPattern* key, Pel* piRefY,
 bool hmb200_shim_pattern_search_fast(TEncSearch* self, TComDataCU* pcCU, TComPattern* key, Pel* piRefY, Int iRefStride, TComMv* lt,
                                      TComMv* rb, TComMv& rcMv, Distortion& ruiSAD, const TComMv* pIntegerMv2Nx2NPred) {
   if (!active()) return false;
+  Stopwatch sw;
+  g_shim.fused.valid = false;
   if (self->m_iFastSearch != 1) return false;
   if (self->m_cDistParam.bApplyWeight) { fprintf(stderr, "hmb200 shim: weighted prediction is out of scope\n"); abort(); }
   const hmb200_pattern p = pattern_of(key);
@@ -191,7 +222,16 @@ bool hmb200_shim_pattern_search_fast(TEncSearch* self, TComDataCU* pcCU, TComPat
   uint32_t sad = 0;
   const int flags = (self->m_pcEncCfg->getUseFastEnc() ? HMB200_FLAG_FEN : 0) |
                     (self->m_pcEncCfg->getFastMEAssumingSmootherMVEnabled() ? HMB200_FLAG_TZ_STOP : 0);
-  if (hmb200_pattern_search_tz(&p, piRefY, iRefStride, l, r, &cs, flags, &ex, (int)sps.getPicWidthInLumaSamples(),
+  static const bool fuse = getenv("HMB200_SHIM_NO_FUSE") == nullptr;
+  if (fuse) {
+    const int hadme = self->m_pcEncCfg->getUseHADME() ? HMB200_FLAG_HADME : 0;
+    Shim::Fused& f = g_shim.fused;
+    if (hmb200_pattern_search_tz_and_refine(&p, piRefY, iRefStride, l, r, &cs, flags | hadme, &ex, (int)sps.getPicWidthInLumaSamples(),
+                                            (int)sps.getPicHeightInLumaSamples(), (int)sps.getMaxCUWidth(), self->m_iSearchRange, &mv, &sad,
+                                            &f.half, &f.qter, &f.cost) != HMB200_OK)
+      die("hmb200_pattern_search_tz_and_refine");
+    f.valid = true; f.roi = p.roi; f.ref = piRefY; f.w = p.width; f.h = p.height; f.flags_hadme = hadme; f.mv = mv; f.cs = cs;
+  } else if (hmb200_pattern_search_tz(&p, piRefY, iRefStride, l, r, &cs, flags, &ex, (int)sps.getPicWidthInLumaSamples(),
                                (int)sps.getPicHeightInLumaSamples(), (int)sps.getMaxCUWidth(), self->m_iSearchRange, &mv, &sad) != HMB200_OK)
     die("hmb200_pattern_search_tz");
   g_shim.n_search++;
@@ -218,13 +258,21 @@ bool hmb200_shim_pattern_search_fast(TEncSearch* self, TComDataCU* pcCU, TComPat
 bool hmb200_shim_pattern_search_frac(TEncSearch* self, Bool lossless, TComPattern* key, Pel* piRefY, Int iRefStride, TComMv* mvInt,
                                      TComMv& rcMvHalf, TComMv& rcMvQter, Distortion& ruiCost) {
   if (!active()) return false;
+  Stopwatch sw;
   const hmb200_pattern p = pattern_of(key);
   const hmb200_cost_state cs = cost_state(self->m_pcRdCost);
   hmb200_mv mi = {mvInt->getHor(), mvInt->getVer()}, half, qter;
   uint32_t cost = 0;
   const int flags = self->m_pcEncCfg->getUseHADME() ? HMB200_FLAG_HADME : 0;
-  if (hmb200_pattern_search_frac(lossless ? 1 : 0, &p, piRefY, iRefStride, mi, &cs, flags, &half, &qter, &cost) != HMB200_OK)
-    die("hmb200_pattern_search_frac");
+  {
+    Shim::Fused& f = g_shim.fused;
+    const bool hit = f.valid && !lossless && f.roi == p.roi && f.ref == piRefY && f.w == p.width && f.h == p.height && f.flags_hadme == flags &&
+                     f.mv.x == mi.x && f.mv.y == mi.y && f.cs.lambda_cost == cs.lambda_cost && f.cs.pred.x == cs.pred.x && f.cs.pred.y == cs.pred.y;
+    f.valid = false;                                   // one use: only the call that directly follows the search
+    if (hit) { half = f.half; qter = f.qter; cost = f.cost; g_shim.n_frac_fused++; }
+    else if (hmb200_pattern_search_frac(lossless ? 1 : 0, &p, piRefY, iRefStride, mi, &cs, flags, &half, &qter, &cost) != HMB200_OK)
+      die("hmb200_pattern_search_frac");
+  }
   g_shim.n_frac++;
   if (g_shim.mode == VERIFY) {
     TComMv rh, rq; Distortion rc = 0;

@@ -55,9 +55,12 @@ def test_encoder_bitstream_md5_1080p_prefix(tmp_path):
     yuv, binf = str(tmp_path / "clip.yuv"), str(tmp_path / "out.bin")
     synth.write_yuv420(yuv, [synth.luma_frame(1920, 1080, t, seed=77) for t in range(2)], 8)
     assert hashlib.md5(open(yuv, "rb").read()).hexdigest() == gold["yuv_md5"]
+    import time
+    t0 = time.time()
     p = subprocess.run([BIN] + meg.args_1080p(CFG, yuv, 2, binf), capture_output=True, text=True,
                        env=dict(os.environ, HMB200_SHIM="gpu"), timeout=3000)
     assert p.returncode == 0, p.stderr[-2000:]
+    print(f"\n1080p I+P through libhmb200: {time.time() - t0:.1f} s wall; " + "; ".join(l for l in p.stderr.splitlines() if l.startswith("hmb200 shim:")))
     assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
     assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]
 

@@ -90,8 +90,12 @@ def _load():
         "hmb200_intra_modes_had": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp]),
         "hmb200_pattern_search": (i32, [C.POINTER(_Pattern), vp, i32, _Mv, _Mv, C.POINTER(_CostState), i32,
                                         C.POINTER(_Mv), C.POINTER(u32)]),
+        "hmb200_pattern_search_and_refine": (i32, [C.POINTER(_Pattern), vp, i32, _Mv, _Mv, C.POINTER(_CostState), i32,
+                                                   C.POINTER(_Mv), C.POINTER(u32), C.POINTER(_Mv), C.POINTER(_Mv), C.POINTER(u32)]),
         "hmb200_pattern_search_tz": (i32, [C.POINTER(_Pattern), vp, i32, _Mv, _Mv, C.POINTER(_CostState), i32, vp, i32, i32, i32, i32,
                                            C.POINTER(_Mv), C.POINTER(u32)]),
+        "hmb200_pattern_search_tz_and_refine": (i32, [C.POINTER(_Pattern), vp, i32, _Mv, _Mv, C.POINTER(_CostState), i32, vp, i32, i32, i32, i32,
+                                                      C.POINTER(_Mv), C.POINTER(u32), C.POINTER(_Mv), C.POINTER(_Mv), C.POINTER(u32)]),
         "hmb200_pattern_search_frac": (i32, [i32, C.POINTER(_Pattern), vp, i32, _Mv, C.POINTER(_CostState), i32,
                                              C.POINTER(_Mv), C.POINTER(_Mv), C.POINTER(u32)]),
         "hmb200_me_jobs": (i32, [i32, i32, vp, i32, i32, vp]),
@@ -323,6 +327,16 @@ class HMB200:
         self._check(self.lib.hmb200_pattern_search(C.byref(key), _addr(ra, ro), rs, _Mv(*lt), _Mv(*rb), C.byref(cs), flags,
                                                    C.byref(mv), C.byref(sad)))
         return (mv.x, mv.y), sad.value
+
+    def pattern_search_and_refine(self, org, w, h, ref, lt, rb, lambda_cost, pred, bit_depth=8, flags=FLAG_FEN | FLAG_HADME):
+        """xPatternSearch + xPatternSearchFracDIF of one PU in one device round trip: ((mv), sad, (half), (qter), frac_cost)."""
+        (oa, oo, os_), (ra, ro, rs) = org, ref
+        key = _Pattern(_addr(oa, oo), w, h, os_, bit_depth)
+        cs = _CostState(int(lambda_cost), _Mv(*pred))
+        mv, sad, half, qter, cost = _Mv(), C.c_uint32(), _Mv(), _Mv(), C.c_uint32()
+        self._check(self.lib.hmb200_pattern_search_and_refine(C.byref(key), _addr(ra, ro), rs, _Mv(*lt), _Mv(*rb), C.byref(cs), flags,
+                                                              C.byref(mv), C.byref(sad), C.byref(half), C.byref(qter), C.byref(cost)))
+        return (mv.x, mv.y), sad.value, (half.x, half.y), (qter.x, qter.y), cost.value
 
     def pattern_search_tz(self, org, w, h, ref, lt, rb, lambda_cost, pred, cu_xy, pic_wh, search_range=64, imv=None, bit_depth=8,
                           flags=FLAG_FEN, max_cu=64):

@@ -41,6 +41,8 @@ struct Plane {
 struct PoolBuf { size_t bytes; void* base; cudaEvent_t ev_free; };   // ev_free: behind the last kernel that may read the buffer
 
 constexpr int N_SIDE = 4;
+// layout of the per-call record of the 1:1 entries (host page-locked copy and device copy): offsets in bytes
+constexpr size_t ONE_KEY = 0, ONE_RESULT = 16, ONE_TASK = 64, ONE_TZ = 128, ONE_HEAD = 256;
 
 struct State {
   bool ready = false;
@@ -57,7 +59,9 @@ struct State {
   std::vector<Plane> planes;
   void* pinned = nullptr; size_t pinned_bytes = 0;
   void* dstage = nullptr; size_t dstage_bytes = 0;     // device staging for plane uploads / per-call blocks
-  Plane pattern;                                       // 64x64 int16 pattern buffer for the 1:1 entries
+  Plane pattern;                                       // 64x64 int16 pattern buffer for the 1:1 entries (inside one_dev)
+  // 1:1 entries: ONE page-locked record up (argmin key | result | task | TZ extra | pattern rows) and one result down per call
+  char* one_host = nullptr; char* one_dev = nullptr;
   std::vector<PoolBuf> pool;                           // released plane buffers, recycled by size (no malloc/free per frame)
   uint64_t launches = 0;
   float last_total_ms = 0, last_search_ms = 0, last_frac_ms = 0;
@@ -257,7 +261,9 @@ static void teardown_state(State& st) {
   for (auto e : st.free_events) cudaEventDestroy(e);
   st.free_events.clear();
   if (st.upstage) { cudaFree(st.upstage); st.upstage = nullptr; st.upstage_bytes = 0; }
-  if (st.pattern.d.base) cudaFree(st.pattern.d.base);
+  if (st.one_dev) cudaFree(st.one_dev);
+  if (st.one_host) cudaFreeHost(st.one_host);
+  st.one_dev = st.one_host = nullptr;
   st.pattern = Plane();
   if (st.pinned) cudaFreeHost(st.pinned);
   if (st.dstage) cudaFree(st.dstage);
@@ -300,7 +306,11 @@ static int init_state_body(State& st, int device) {
   st.ready = true;
   // pattern buffer for the 1:1 entries: 64x64 int16, no margins
   st.pattern = Plane();
-  if ((rc = make_plane(st.pattern, 64, 64, 0, 0, 16)) != HMB200_OK) return rc;
+  CUDA_TRY(cudaMalloc((void**)&st.one_dev, ONE_HEAD + 64 * 64 * sizeof(int16_t)));
+  CUDA_TRY(cudaMallocHost((void**)&st.one_host, ONE_HEAD + 64 * 64 * sizeof(int16_t)));
+  st.pattern.used = true;
+  st.pattern.d.base = st.one_dev + ONE_HEAD; st.pattern.d.pitch = 64; st.pattern.d.width = 64; st.pattern.d.height = 64;
+  st.pattern.d.margin_x = 0; st.pattern.d.margin_y = 0; st.pattern.d.bytes_per_sample = 2; st.pattern.d.bit_depth = 16;
   st.launches = 0;
   return HMB200_OK;
 }
@@ -1332,15 +1342,25 @@ int hmb200_me_ctu_row(int cur_plane, int ref_plane, int ctu_row, int max_cu, con
 // ------------------------------------------------------------------------------------------------------------------
 // 1:1 entries (per call, synchronous): exact inside the real encoder where predictors arrive one PU at a time
 // ------------------------------------------------------------------------------------------------------------------
-static int upload_pattern(const hmb200_pattern* key) {
+// Fills the host record: pattern rows (pitch 64 samples), task, result seed, argmin key; one H2D copy brings it to the device.
+static int stage_one_call(const hmb200_pattern* key, const SearchTask& t, const hmb200_pu_result& io, const hmb200_tz_extra* tz) {
   if (!key || !key->roi || !supported_pu(key->width, key->height)) return fail(HMB200_ERR_ARG, "unsupported pattern");
-  int rc = ensure_pinned(64 * 64 * sizeof(int16_t));
-  if (rc != HMB200_OK) return rc;
-  int16_t* pin = reinterpret_cast<int16_t*>(G.pinned);
+  char* h = G.one_host;
+  *reinterpret_cast<unsigned long long*>(h + ONE_KEY) = ~0ull;
+  memcpy(h + ONE_RESULT, &io, sizeof(io));
+  memcpy(h + ONE_TASK, &t, sizeof(t));
+  if (tz) memcpy(h + ONE_TZ, tz, sizeof(*tz));
+  int16_t* rows = reinterpret_cast<int16_t*>(h + ONE_HEAD);
   for (int y = 0; y < key->height; y++)
-    memcpy(pin + (size_t)y * key->width, key->roi + (ptrdiff_t)y * key->stride, (size_t)key->width * sizeof(int16_t));
-  CUDA_TRY(cudaMemcpy2DAsync(G.pattern.d.base, (size_t)G.pattern.d.pitch * sizeof(int16_t), pin, (size_t)key->width * sizeof(int16_t),
-                             (size_t)key->width * sizeof(int16_t), key->height, cudaMemcpyHostToDevice, G.stream));
+    memcpy(rows + (size_t)y * 64, key->roi + (ptrdiff_t)y * key->stride, (size_t)key->width * sizeof(int16_t));
+  CUDA_TRY(cudaMemcpyAsync(G.one_dev, h, ONE_HEAD + (size_t)key->height * 64 * sizeof(int16_t), cudaMemcpyHostToDevice, G.stream));
+  return HMB200_OK;
+}
+static int finish_one_call(hmb200_pu_result* io) {
+  CUDA_TRY(cudaMemcpyAsync(G.one_host + ONE_RESULT, G.one_dev + ONE_RESULT, sizeof(*io), cudaMemcpyDeviceToHost, G.stream));
+  CUDA_TRY(cudaStreamSynchronize(G.stream));
+  CUDA_TRY(cudaGetLastError());
+  memcpy(io, G.one_host + ONE_RESULT, sizeof(*io));
   return HMB200_OK;
 }
 
@@ -1349,9 +1369,8 @@ static int run_single(const hmb200_pattern* key, const int16_t* ref_at_pu, const
   int rx, ry;
   Plane* pr = find_plane_by_host(ref_at_pu, &rx, &ry);
   if (!pr) return fail(HMB200_ERR_ARG, "reference pointer does not fall into a registered plane");
-  if (pr->d.bit_depth != key->bit_depth) return fail(HMB200_ERR_ARG, "pattern bit depth differs from the reference plane");
-  int rc = upload_pattern(key);
-  if (rc != HMB200_OK) return rc;
+  if (!key || pr->d.bit_depth != key->bit_depth) return fail(HMB200_ERR_ARG, "pattern bit depth differs from the reference plane");
+  get_plane((int)(pr - &G.planes[0]));                // orders a pending upload of the plane before this call's kernels
   SearchTask t = proto;
   t.org_x = 0; t.org_y = 0; t.ref_x = rx; t.ref_y = ry; t.w = key->width; t.h = key->height;
   {
@@ -1360,18 +1379,15 @@ static int run_single(const hmb200_pattern* key, const int16_t* ref_at_pu, const
                             : Box{rx + io->mv_x - reach, ry + io->mv_y - reach, rx + io->mv_x + t.w + reach, ry + io->mv_y + t.h + reach};
     if (!box_inside(pr->d, b)) return fail(HMB200_ERR_ARG, "the search window / refinement block leaves the padded reference plane");
   }
-  size_t need = sizeof(SearchTask) + sizeof(hmb200_pu_result) + 128;
-  if ((rc = ensure_dstage(need)) != HMB200_OK) return rc;
-  SearchTask* d_t = reinterpret_cast<SearchTask*>(G.dstage);
-  hmb200_pu_result* d_r = reinterpret_cast<hmb200_pu_result*>(reinterpret_cast<char*>(G.dstage) + 64);
-  unsigned long long* d_key = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(G.dstage) + 64 + sizeof(hmb200_pu_result));
-  CUDA_TRY(cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, G.stream));
-  CUDA_TRY(cudaMemcpyAsync(d_r, io, sizeof(*io), cudaMemcpyHostToDevice, G.stream));
+  int rc = stage_one_call(key, t, *io, nullptr);
+  if (rc != HMB200_OK) return rc;
+  SearchTask* d_t = reinterpret_cast<SearchTask*>(G.one_dev + ONE_TASK);
+  hmb200_pu_result* d_r = reinterpret_cast<hmb200_pu_result*>(G.one_dev + ONE_RESULT);
+  unsigned long long* d_key = reinterpret_cast<unsigned long long*>(G.one_dev + ONE_KEY);
   if (do_search) {
     // one PU: spread its candidates over the whole GPU (one CTA per ~256 candidates), fold with atomicMin, decode
     const long long total = (long long)(t.rb_x - t.lt_x + 1) * (t.rb_y - t.lt_y + 1);
     const int splits = (int)std::max<long long>(1, std::min<long long>(4 * G.sm_count, (total + 255) / 256));
-    CUDA_TRY(cudaMemsetAsync(d_key, 0xff, sizeof(unsigned long long), G.stream));
     const dim3 grid(1, splits);
     if (pr->d.bytes_per_sample == 1) k_search_split<uint8_t, int16_t><<<grid, 256, 0, G.stream>>>(d_t, d_key, G.pattern.d, pr->d);
     else                             k_search_split<int16_t, int16_t><<<grid, 256, 0, G.stream>>>(d_t, d_key, G.pattern.d, pr->d);
@@ -1379,10 +1395,7 @@ static int run_single(const hmb200_pattern* key, const int16_t* ref_at_pu, const
     G.launches += 2;
   }
   dispatch_generic(d_t, d_r, 1, G.pattern.d, pr->d, flags, /*do_search=*/false, nullptr);
-  CUDA_TRY(cudaMemcpyAsync(io, d_r, sizeof(*io), cudaMemcpyDeviceToHost, G.stream));
-  CUDA_TRY(cudaStreamSynchronize(G.stream));
-  CUDA_TRY(cudaGetLastError());
-  return HMB200_OK;
+  return finish_one_call(io);
 }
 
 int hmb200_pattern_search(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride, hmb200_mv lt, hmb200_mv rb,
@@ -1401,44 +1414,87 @@ int hmb200_pattern_search(const hmb200_pattern* key, const int16_t* ref_at_pu, i
   return HMB200_OK;
 }
 
-int hmb200_pattern_search_tz(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride, hmb200_mv lt, hmb200_mv rb,
-                             const hmb200_cost_state* cs, int flags, const hmb200_tz_extra* extra, int pic_w, int pic_h, int max_cu,
-                             int search_range, hmb200_mv* mv_out, uint32_t* sad_out) {
+int hmb200_pattern_search_and_refine(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride, hmb200_mv lt, hmb200_mv rb,
+                                     const hmb200_cost_state* cs, int flags, hmb200_mv* mv_out, uint32_t* sad_out, hmb200_mv* half_out,
+                                     hmb200_mv* qter_out, uint32_t* frac_cost_out) {
   NEED_READY();
   (void)ref_stride;
-  if (!key || !cs || !extra || !mv_out || !sad_out || rb.x < lt.x || rb.y < lt.y || search_range < 1)
+  if (!key || !cs || !mv_out || !sad_out || !half_out || !qter_out || !frac_cost_out || rb.x < lt.x || rb.y < lt.y)
+    return fail(HMB200_ERR_ARG, "hmb200_pattern_search_and_refine: bad arguments");
+  SearchTask t{};
+  t.lt_x = lt.x; t.lt_y = lt.y; t.rb_x = rb.x; t.rb_y = rb.y; t.pred_x = cs->pred.x; t.pred_y = cs->pred.y;
+  t.lambda_cost = cs->lambda_cost;
+  t.sub_shift = ((flags & HMB200_FLAG_FEN) && key->height > 8) ? 1 : 0;
+  hmb200_pu_result r{};
+  int rc = run_single(key, ref_at_pu, t, (flags & (HMB200_FLAG_FEN | HMB200_FLAG_HADME)) | HMB200_FLAG_FRAC, true, &r);
+  if (rc != HMB200_OK) return rc;
+  mv_out->x = r.mv_x; mv_out->y = r.mv_y; *sad_out = r.sad;
+  half_out->x = r.half_x; half_out->y = r.half_y; qter_out->x = r.qter_x; qter_out->y = r.qter_y; *frac_cost_out = r.frac_cost;
+  return HMB200_OK;
+}
+
+static int tz_single(const hmb200_pattern* key, const int16_t* ref_at_pu, hmb200_mv lt, hmb200_mv rb, const hmb200_cost_state* cs, int flags,
+                     const hmb200_tz_extra* extra, int pic_w, int pic_h, int max_cu, int search_range, hmb200_pu_result* out) {
+  NEED_READY();
+  if (!key || !cs || !extra || !out || rb.x < lt.x || rb.y < lt.y || search_range < 1)
     return fail(HMB200_ERR_ARG, "hmb200_pattern_search_tz: bad arguments");
   int rx, ry;
   Plane* pr = find_plane_by_host(ref_at_pu, &rx, &ry);
   if (!pr) return fail(HMB200_ERR_ARG, "reference pointer does not fall into a registered plane");
   if (pr->d.bit_depth != key->bit_depth) return fail(HMB200_ERR_ARG, "pattern bit depth differs from the reference plane");
-  int rc = upload_pattern(key);
-  if (rc != HMB200_OK) return rc;
   SearchTask t{};
   t.org_x = 0; t.org_y = 0; t.ref_x = rx; t.ref_y = ry; t.w = key->width; t.h = key->height;
   t.lt_x = lt.x; t.lt_y = lt.y; t.rb_x = rb.x; t.rb_y = rb.y; t.pred_x = cs->pred.x; t.pred_y = cs->pred.y;
   {
     const int xmin = std::min(std::min(0, lt.x), -max_cu - 8 - extra->cu_x + 1), xmax = std::max(std::max(0, rb.x), pic_w + 8 - extra->cu_x - 1);
     const int ymin = std::min(std::min(0, lt.y), -max_cu - 8 - extra->cu_y + 1), ymax = std::max(std::max(0, rb.y), pic_h + 8 - extra->cu_y - 1);
-    if (!box_inside(pr->d, Box{rx + xmin, ry + ymin, rx + xmax + t.w, ry + ymax + t.h}))
+    const int reach = (flags & HMB200_FLAG_FRAC) ? FRAC_REACH : 0;
+    if (!box_inside(pr->d, Box{rx + xmin - reach, ry + ymin - reach, rx + xmax + t.w + reach, ry + ymax + t.h + reach}))
       return fail(HMB200_ERR_ARG, "hmb200_pattern_search_tz: the clipped search range leaves the padded reference plane");
   }
   t.lambda_cost = cs->lambda_cost;
   t.sub_shift = ((flags & HMB200_FLAG_FEN) && key->height > 8) ? 1 : 0;
-  // one staging record: [SearchTask | tz_extra | result]
-  struct Rec { SearchTask t; hmb200_tz_extra e; hmb200_pu_result r; } rec{t, *extra, hmb200_pu_result{}};
-  if ((rc = ensure_dstage(sizeof(Rec) + 64)) != HMB200_OK) return rc;
-  Rec* d = reinterpret_cast<Rec*>(G.dstage);
-  CUDA_TRY(cudaMemcpyAsync(d, &rec, sizeof(rec), cudaMemcpyHostToDevice, G.stream));
-  const TzParams P{pic_w, pic_h, max_cu, search_range, (flags & HMB200_FLAG_TZ_STOP) ? 1 : 0};
-  if (pr->d.bytes_per_sample == 1) k_tz_search<uint8_t, int16_t><<<1, TZ_WARPS * 32, 0, G.stream>>>(&d->t, &d->e, &d->r, 1, G.pattern.d, pr->d, P);
-  else                             k_tz_search<int16_t, int16_t><<<1, TZ_WARPS * 32, 0, G.stream>>>(&d->t, &d->e, &d->r, 1, G.pattern.d, pr->d, P);
-  G.launches++;
+  get_plane((int)(pr - &G.planes[0]));
   hmb200_pu_result r{};
-  CUDA_TRY(cudaMemcpyAsync(&r, &d->r, sizeof(r), cudaMemcpyDeviceToHost, G.stream));
-  CUDA_TRY(cudaStreamSynchronize(G.stream));
-  CUDA_TRY(cudaGetLastError());
+  int rc = stage_one_call(key, t, r, extra);
+  if (rc != HMB200_OK) return rc;
+  const TzParams P{pic_w, pic_h, max_cu, search_range, (flags & HMB200_FLAG_TZ_STOP) ? 1 : 0};
+  const SearchTask* d_t = reinterpret_cast<const SearchTask*>(G.one_dev + ONE_TASK);
+  const hmb200_tz_extra* d_e = reinterpret_cast<const hmb200_tz_extra*>(G.one_dev + ONE_TZ);
+  hmb200_pu_result* d_r = reinterpret_cast<hmb200_pu_result*>(G.one_dev + ONE_RESULT);
+  if (pr->d.bytes_per_sample == 1) k_tz_search<uint8_t, int16_t><<<1, TZ_WARPS * 32, 0, G.stream>>>(d_t, d_e, d_r, 1, G.pattern.d, pr->d, P);
+  else                             k_tz_search<int16_t, int16_t><<<1, TZ_WARPS * 32, 0, G.stream>>>(d_t, d_e, d_r, 1, G.pattern.d, pr->d, P);
+  G.launches++;
+  if (flags & HMB200_FLAG_FRAC)                       // xPatternSearchFracDIF on the MV just found, same round trip
+    dispatch_generic(reinterpret_cast<const SearchTask*>(G.one_dev + ONE_TASK), d_r, 1, G.pattern.d, pr->d, flags, /*do_search=*/false, nullptr);
+  if ((rc = finish_one_call(&r)) != HMB200_OK) return rc;
+  *out = r;
+  return HMB200_OK;
+}
+
+int hmb200_pattern_search_tz(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride, hmb200_mv lt, hmb200_mv rb,
+                             const hmb200_cost_state* cs, int flags, const hmb200_tz_extra* extra, int pic_w, int pic_h, int max_cu,
+                             int search_range, hmb200_mv* mv_out, uint32_t* sad_out) {
+  (void)ref_stride;
+  if (!mv_out || !sad_out) return fail(HMB200_ERR_ARG, "hmb200_pattern_search_tz: bad arguments");
+  hmb200_pu_result r{};
+  const int rc = tz_single(key, ref_at_pu, lt, rb, cs, flags & ~(HMB200_FLAG_FRAC | HMB200_FLAG_HADME), extra, pic_w, pic_h, max_cu, search_range, &r);
+  if (rc != HMB200_OK) return rc;
   mv_out->x = r.mv_x; mv_out->y = r.mv_y; *sad_out = r.sad;
+  return HMB200_OK;
+}
+
+int hmb200_pattern_search_tz_and_refine(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride, hmb200_mv lt, hmb200_mv rb,
+                                        const hmb200_cost_state* cs, int flags, const hmb200_tz_extra* extra, int pic_w, int pic_h, int max_cu,
+                                        int search_range, hmb200_mv* mv_out, uint32_t* sad_out, hmb200_mv* half_out, hmb200_mv* qter_out,
+                                        uint32_t* frac_cost_out) {
+  (void)ref_stride;
+  if (!mv_out || !sad_out || !half_out || !qter_out || !frac_cost_out) return fail(HMB200_ERR_ARG, "hmb200_pattern_search_tz_and_refine: bad arguments");
+  hmb200_pu_result r{};
+  const int rc = tz_single(key, ref_at_pu, lt, rb, cs, flags | HMB200_FLAG_FRAC, extra, pic_w, pic_h, max_cu, search_range, &r);
+  if (rc != HMB200_OK) return rc;
+  mv_out->x = r.mv_x; mv_out->y = r.mv_y; *sad_out = r.sad;
+  half_out->x = r.half_x; half_out->y = r.half_y; qter_out->x = r.qter_x; qter_out->y = r.qter_y; *frac_cost_out = r.frac_cost;
   return HMB200_OK;
 }
 

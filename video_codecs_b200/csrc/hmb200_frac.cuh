@@ -178,25 +178,39 @@ __device__ __forceinline__ void frac_tile_diff_u8(const uint8_t* ref, int ref_pi
   (void)head;
 }
 
+// one unique tile of the refinement (see "unique tiles" below): patch origin (tile - 4), original tile, half offset; 16 bytes
+struct FracUTile { int16_t rx, ry, ox, oy; int16_t hx, hy; int16_t pad[2]; };
+
 // stage 0: half-pel candidates around the integer MV; stage 1: quarter-pel candidates 1..8 around the best half.
 // dist: [n_pu][9] accumulators (zeroed by the host; dist[.][0] of stage 1 is written by k_frac_argmin<0>).
 template <typename RefT, typename OrgT, int N, bool HAD>
 __global__ void __launch_bounds__(FRAC_TILE_THREADS, N == 8 ? 4 : 8)
 k_frac_tiles(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_result* __restrict__ results,
-             const uint32_t* __restrict__ tiles, int n_tiles, uint32_t* __restrict__ dist, DevPlane cur_plane, DevPlane ref_plane) {
+             const uint32_t* __restrict__ tiles, int n_tiles, uint32_t* __restrict__ dist, DevPlane cur_plane, DevPlane ref_plane,
+             const FracUTile* __restrict__ utiles = nullptr, const uint32_t* __restrict__ n_unique = nullptr) {
   const int nc = stage == 0 ? 9 : (stage == 1 ? 8 : 1);     // stage 2: one explicit quarter-pel MV per PU (motion compensation)
   const long long t = (long long)blockIdx.x * FRAC_TILE_THREADS + threadIdx.x;
   const int chunk = (int)(t / (32 * nc));
   const int within = (int)(t - (long long)chunk * 32 * nc);
   const int cand = within >> 5;                                          // warp-uniform
   const int slot = chunk * 32 + (within & 31);
+  if (utiles) n_tiles = (int)*n_unique;                                  // unique tiles: the grid covers the worst case
   const bool active = slot < n_tiles;
   int fx = 0, fy = 0;
   uint32_t pu = 0;
   const RefT* ref = nullptr;
   const OrgT* org = nullptr;
   int ci = 0;
-  if (active) {
+  if (active && utiles) {
+    const FracUTile u = utiles[slot];
+    pu = (uint32_t)slot;                                                 // row of the unique-tile distortion table
+    int qx, qy;
+    if (stage == 0) { ci = cand; qx = 2 * k_refine_h[ci][0]; qy = 2 * k_refine_h[ci][1]; }
+    else            { ci = cand + 1; qx = 2 * u.hx + k_refine_q[ci][0]; qy = 2 * u.hy + k_refine_q[ci][1]; }
+    fx = qx & 3; fy = qy & 3;
+    ref = plane_at<RefT>(ref_plane, u.rx + 4 + (qx >> 2), u.ry + 4 + (qy >> 2));
+    org = plane_at<OrgT>(cur_plane, u.ox, u.oy);
+  } else if (active) {
     const uint32_t tile = tiles[slot];
     pu = tile & 0xffffffu;
     const int tx = (tile >> 24) & 15, ty = tile >> 28;
@@ -232,7 +246,8 @@ k_frac_tiles(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_re
 #pragma unroll
     for (int i = 0; i < N * N; i++) s += (uint32_t)abs(d[i]);
   }
-  atomicAdd(&dist[(size_t)pu * 9 + ci], s);
+  if (utiles) dist[(size_t)pu * 9 + ci] = s;                              // one thread per (unique tile, candidate)
+  else        atomicAdd(&dist[(size_t)pu * 9 + ci], s);
 }
 
 // ---- unique tiles -------------------------------------------------------------------------------------------------------
@@ -243,7 +258,6 @@ k_frac_tiles(int stage, const SearchTask* __restrict__ tasks, const hmb200_pu_re
 // UNIQUE tiles: a hash pass keys every tile instance by (original position, reference position incl. the integer MV, half
 // offset), the SATD kernels run once per unique tile and candidate and store plain words, and a gather pass adds each
 // instance's nine (eight) values to its PU.  Same integers, added in a different order - sums of uint32 are exact.
-struct FracUTile { int16_t rx, ry, ox, oy; int16_t hx, hy; int16_t pad[2]; };      // 16 bytes: patch origin (tile - 4), original tile, half offset
 constexpr unsigned long long FRAC_KEY_EMPTY = ~0ull;
 
 __device__ __forceinline__ uint32_t frac_hash64(unsigned long long k) {
@@ -784,59 +798,57 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
     const bool hv4 = getenv("HMB200_FRAC_HV4") != nullptr;                // 4x4 tiles: the shared first pass costs more in barriers than
                                                                           // it saves (ncu: 263 vs 225 us per stage), so it is opt-in
     const int tpc = FRAC_TILE_THREADS / nc;
-    bool unique = false;
-    if constexpr (PATCH) {
-      const bool no_unique = getenv("HMB200_NO_FRAC_DEDUPE") != nullptr;   // A/B knob: every tile instance on its own
-      unique = !no_unique && plane_fits_i16 && frac_alloc_unique(const_cast<FracSchedule*>(&fs));
-      if (unique && stage == 0 && cudaMemsetAsync(fs.d_count, 0, 4 * sizeof(uint32_t), stream) != cudaSuccess) return -1;
-    }
-    if (fs.n_tiles8 > 0) {
+    const bool no_unique = getenv("HMB200_NO_FRAC_DEDUPE") != nullptr;     // A/B knob: every tile instance on its own
+    const bool unique = !no_unique && plane_fits_i16 && frac_alloc_unique(const_cast<FracSchedule*>(&fs));
+    if (unique && stage == 0 && cudaMemsetAsync(fs.d_count, 0, 4 * sizeof(uint32_t), stream) != cudaSuccess) return -1;
+    // unique-tile pass of one tile size (k = 0: 8x8 tiles, 1: 4x4): keys + descriptors before the SATD kernel, gather after it
+    auto unique_begin = [&](int k) -> bool {
+      const int n = k ? fs.n_tiles4 : fs.n_tiles8;
+      if (cudaMemsetAsync(fs.d_hkeys[k], 0xff, ((size_t)fs.hmask[k] + 1) * sizeof(unsigned long long), stream) != cudaSuccess) return false;
+      if (k == 0) k_frac_unique<8><<<(n + 255) / 256, 256, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, n, fs.d_hkeys[0], fs.hmask[0], fs.d_hval[0],
+                                                                       fs.d_count + 2 * stage, fs.d_utiles[0], fs.d_inst[0]);
+      else        k_frac_unique<4><<<(n + 255) / 256, 256, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, n, fs.d_hkeys[1], fs.hmask[1], fs.d_hval[1],
+                                                                       fs.d_count + 2 * stage + 1, fs.d_utiles[1], fs.d_inst[1]);
+      launches++;
+      return true;
+    };
+    auto unique_end = [&](int k) {
+      const int n = k ? fs.n_tiles4 : fs.n_tiles8;
+      k_frac_gather<<<(int)(((long long)n * nc + 255) / 256), 256, 0, stream>>>(stage, k ? fs.d_tiles4 : fs.d_tiles8, n, fs.d_inst[k], fs.d_hval[k], fs.d_udist[k], dist);
+      launches++;
+    };
+    for (int k = 0; k < 2; k++) {
+      const int n = k ? fs.n_tiles4 : fs.n_tiles8;
+      if (n == 0) continue;
+      const uint32_t* d_tl = k ? fs.d_tiles4 : fs.d_tiles8;
+      const FracUTile* ut = nullptr; const uint32_t* cnt = nullptr; uint32_t* out = dist;
+      if (unique) {
+        if (!unique_begin(k)) return -1;
+        ut = fs.d_utiles[k]; cnt = fs.d_count + 2 * stage + k; out = fs.d_udist[k];
+      }
       if constexpr (PATCH) {
-        const int nb8 = (fs.n_tiles8 + tpc - 1) / tpc;
-        const FracUTile* ut = nullptr; const uint32_t* cnt = nullptr; uint32_t* out8 = dist;
-        if (unique) {
-          if (cudaMemsetAsync(fs.d_hkeys[0], 0xff, ((size_t)fs.hmask[0] + 1) * sizeof(unsigned long long), stream) != cudaSuccess) return -1;
-          k_frac_unique<8><<<(fs.n_tiles8 + 255) / 256, 256, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, fs.d_hkeys[0], fs.hmask[0],
-                                                                         fs.d_hval[0], fs.d_count + 2 * stage, fs.d_utiles[0], fs.d_inst[0]);
-          launches++;
-          ut = fs.d_utiles[0]; cnt = fs.d_count + 2 * stage; out8 = fs.d_udist[0];
-        }
-        if (!use_had)      k_frac_patch<8, false><<<nb8, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, out8, cur, ref, ut, cnt);
-        else if (old_path) k_frac_patch<8, true><<<nb8, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, out8, cur, ref, ut, cnt);
-        else               k_frac_hv<8, true><<<nb8, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, out8, cur, ref, ut, cnt);
-        if (unique) {
-          k_frac_gather<<<(int)(((long long)fs.n_tiles8 * nc + 255) / 256), 256, 0, stream>>>(stage, fs.d_tiles8, fs.n_tiles8, fs.d_inst[0], fs.d_hval[0], fs.d_udist[0], dist);
-          launches++;
+        const int nb = (n + tpc - 1) / tpc;
+        if (k == 0) {
+          if (!use_had)      k_frac_patch<8, false><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          else if (old_path) k_frac_patch<8, true><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          else               k_frac_hv<8, true><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+        } else {
+          if (!use_had)      k_frac_patch<4, false><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          else if (!hv4)     k_frac_patch<4, true><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          else               k_frac_hv<4, true><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
         }
       } else {
-        if (use_had) k_frac_tiles<RefT, OrgT, 8, true><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
-        else         k_frac_tiles<RefT, OrgT, 8, false><<<blocks(fs.n_tiles8), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, fs.n_tiles8, dist, cur, ref);
+        const int nb = blocks(n);
+        if (k == 0) {
+          if (use_had) k_frac_tiles<RefT, OrgT, 8, true><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          else         k_frac_tiles<RefT, OrgT, 8, false><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+        } else {
+          if (use_had) k_frac_tiles<RefT, OrgT, 4, true><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          else         k_frac_tiles<RefT, OrgT, 4, false><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+        }
       }
       launches++;
-    }
-    if (fs.n_tiles4 > 0) {
-      if constexpr (PATCH) {
-        const int nb4 = (fs.n_tiles4 + tpc - 1) / tpc;
-        const FracUTile* ut = nullptr; const uint32_t* cnt = nullptr; uint32_t* out4 = dist;
-        if (unique) {
-          if (cudaMemsetAsync(fs.d_hkeys[1], 0xff, ((size_t)fs.hmask[1] + 1) * sizeof(unsigned long long), stream) != cudaSuccess) return -1;
-          k_frac_unique<4><<<(fs.n_tiles4 + 255) / 256, 256, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, fs.d_hkeys[1], fs.hmask[1],
-                                                                         fs.d_hval[1], fs.d_count + 2 * stage + 1, fs.d_utiles[1], fs.d_inst[1]);
-          launches++;
-          ut = fs.d_utiles[1]; cnt = fs.d_count + 2 * stage + 1; out4 = fs.d_udist[1];
-        }
-        if (!use_had)      k_frac_patch<4, false><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, out4, cur, ref, ut, cnt);
-        else if (!hv4)     k_frac_patch<4, true><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, out4, cur, ref, ut, cnt);
-        else               k_frac_hv<4, true><<<nb4, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, out4, cur, ref, ut, cnt);
-        if (unique) {
-          k_frac_gather<<<(int)(((long long)fs.n_tiles4 * nc + 255) / 256), 256, 0, stream>>>(stage, fs.d_tiles4, fs.n_tiles4, fs.d_inst[1], fs.d_hval[1], fs.d_udist[1], dist);
-          launches++;
-        }
-      } else {
-        if (use_had) k_frac_tiles<RefT, OrgT, 4, true><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
-        else         k_frac_tiles<RefT, OrgT, 4, false><<<blocks(fs.n_tiles4), FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, fs.n_tiles4, dist, cur, ref);
-      }
-      launches++;
+      if (unique) unique_end(k);
     }
     const int nb = (fs.n_pu + 255) / 256;
     if (stage == 0) k_frac_argmin<0><<<nb, 256, 0, stream>>>(d_tasks, d_results, dist0, dist1, fs.n_pu, ref.bit_depth);
