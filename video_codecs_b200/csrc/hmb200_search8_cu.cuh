@@ -480,8 +480,12 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   const int w_first = un.item_first + warp * per_warp, w_last = min(w_first + per_warp, un.item_last);
   int first_item = w_first;                           // first item since the last flush (decodes local indices)
   int g = 0, blk = 0, g0 = 0;                         // row group / block of the lane's quad; g0: row group at the last flush (8x8 CUs)
-  bool edge_mode = false;                             // the candidates since the last flush came from edge items (S >= 16)
+  bool edge_mode = false;                             // the candidates since the last flush came from edge items (S >= 16, tile-numbered keys)
+  // S >= 16, bd.edge == 2: ROW-INDEXED local keys, (candidate row << 3) | (4 for the last column, else k).  With eight blocks per
+  // candidate row a lane keeps its block (blk = quad), so this orders every candidate a lane can see - block items and edge items
+  // alike - in raster order, whatever order they are visited in: one running minimum, no flush between the two kinds of item.
   auto flush = [&]() {
+    const bool rowkeys = S >= 16 && bd.edge == 2;
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) {
       // lanes number their candidates locally: reduce the cost first, then the raster index among the lanes that hold it
@@ -496,6 +500,9 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
           const int rb = bd.rank_bits, rowrel = (int)(local >> (2 + rb)), rank = (int)(local >> 2) & ((1 << rb) - 1);
           const int gg = g0 + (rowrel >> 2), bb = ((quad - gg * bd.n_blk) & 7) + 8 * rank;
           cyi = bd.cy_first + gg * T::KY + (rowrel & 3); cxi = bb * 16 + sub + 4 * (int)(local & 3u) - bd.xal;
+        } else if (rowkeys) {
+          cyi = bd.cy_first + (int)(local >> 3);
+          cxi = (local & 4u) ? bd.nx - 1 : quad * 16 + sub + 4 * (int)(local & 3u) - bd.xal;
         } else if (edge_mode) {      // edge item number since the last flush; the lane is the candidate row, the column is the last one
           cyi = bd.cy_first + (first_item + (int)(local >> LK) - bd.item_start - bd.n_main) * 32 + lane; cxi = bd.nx - 1;
         } else {                     // tile number since the last flush, column
@@ -516,68 +523,19 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
     const int q = (item - bd.item_start) * 8 + quad;
     g = q / bd.n_blk; blk = q - g * bd.n_blk; g0 = g;
   };
-  if (w_first < w_last) {
-    // the CU that holds this warp's first item: 32 descriptors per probe instead of a walk of dependent loads
-    for (;; bslot += 32) {
-      const int j = bslot + lane;
-      const bool past = j >= un.job_first + un.job_count || w_first < bundles[j].item_start + bundles[j].n_items;
-      const unsigned m = __ballot_sync(0xffffffffu, past);
-      if (m) { bslot += __ffs(m) - 1; break; }
-    }
-    load_bundle();
-    locate(w_first);
-    edge_mode = S >= 16 && w_first - bd.item_start >= bd.n_main;
-  }
+  const uint32_t c16 = one << 16;                                       // x >> 16 as umulhi(x, 2^16): IMAD.HI, not SHF
+  const uint32_t rpitch = (uint32_t)un.ref_pitch, opitch = (uint32_t)un.org_pitch;
 
-  for (int item = w_first; item < w_last; item++) {
-    const bool next_cu = item >= bd.item_start + bd.n_items;
-    if (next_cu) {
-      flush();
-      do { bslot++; } while (item >= bundles[bslot].item_start + bundles[bslot].n_items);
-      load_bundle();
-      first_item = item;
-      locate(item);
-    }
-    const bool is_edge = S >= 16 && item - bd.item_start >= bd.n_main;        // warp-uniform
-    if (!next_cu) {
-      if (is_edge != edge_mode) {                       // the last column's candidates precede later rows' in raster order: a lane's
-        flush();                                        // local order holds only inside one kind of item
-        first_item = item;
-      } else if (S == 8 ? __any_sync(0xffffffffu, (g - g0) >= (1 << (CU_LOCAL_BITS - 4 - bd.rank_bits))) : (item - first_item >= TILE_LIMIT)) {
-        flush();                                        // the local index would run out of bits
-        first_item = item; g0 = g;
-      }
-    }
-    edge_mode = is_edge;
-    const uint32_t c16 = one << 16;                                     // x >> 16 as umulhi(x, 2^16): IMAD.HI, not SHF
-    const uint32_t rpitch = (uint32_t)un.ref_pitch, opitch = (uint32_t)un.org_pitch;
-    const uint32_t orgp = smem_u32(s_org) + (uint32_t)bd.org_off;
-    if constexpr (S >= 16) {
-      if (__builtin_expect(is_edge, 0)) {              // rare (5 of 134 items): keep its code out of the block loop's straight line
-        // Edge item: the window's last column, one candidate row per lane (32 rows per item).  (xal + nx - 1) % 16 == 0, so the
-        // column starts a 16-byte block of copy 0 and every lane reads aligned words of its own row.
-        const int row = (item - bd.item_start - bd.n_main) * 32 + lane;
-        const bool ok = row < bd.ny;
-        const int rowc = min(row, bd.ny - 1);
-        const uint32_t refp = smem_u32(s_ref) + (uint32_t)(bd.win_off + rowc * un.ref_pitch + bd.nx - 1);
-        const uint32_t px = bd.lambda * eg_bits(((bd.lt_x + bd.nx - 1) << 2) - bd.pred_x);
-        const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + bd.cy_first + rowc) << 2) - bd.pred_y);
-        const uint32_t tile_local = (uint32_t)(item - first_item) << LK;
-        uint32_t base[1];
-        bool valid[1] = {ok};
-        base[0] = (ok || !MASK_BY_KEY) ? (__umulhi(px + py, c16) << CU_LOCAL_BITS) + tile_local : KEY_NONE;
-        if constexpr (CHILD) cu16_child_tile<FEN, 1, NSLOT>(refp, orgp, rpitch, opitch, base, best);
-        else                 cu_tile<S, FEN, 1, MASK_BY_KEY, NSLOT>(refp, orgp, rpitch, opitch, base, valid, one, best);
-        continue;
-      }
-    }
+  // ---- one block item: 8 quads x 16 candidate columns x KY candidate rows -------------------------------------------------
+  auto block_item = [&](int item, bool rowkeys) {
     // Local index of a candidate inside the key: must grow in raster order along the candidates ONE LANE sees between
-    // two flushes.  S >= 16 (one candidate row per tile): the lane's tiles come in raster order, so the tile number does.
-    // S == 8 (four rows per tile): the lane may see two tiles of one row group (8 blocks apart), so the index is
-    // (candidate row since g0, rank of the tile inside its row group = blk / 8, column).
+    // two flushes.  S >= 16 (one candidate row per tile): the lane's tiles come in raster order, so the tile number does
+    // (or the row itself, see rowkeys).  S == 8 (four rows per tile): the lane may see two tiles of one row group (8 blocks
+    // apart), so the index is (candidate row since g0, rank of the tile inside its row group = blk / 8, column).
     const uint32_t rowunit = 1u << (2 + bd.rank_bits);                  // S == 8: index step of one candidate row
     const uint32_t tile_local = (S == 8) ? (uint32_t)((g - g0) * 4) * rowunit + ((uint32_t)(blk >> 3) << 2)
-                                         : (uint32_t)(item - first_item) << LK;
+                                         : rowkeys ? (uint32_t)g << 3 : (uint32_t)(item - first_item) << LK;
+    const uint32_t orgp = smem_u32(s_org) + (uint32_t)bd.org_off;
     if (g < bd.n_rowgroups) {
     const int cyi0 = g * T::KY;
     const int cx0 = blk * 16 + sub - bd.xal;                            // window column of candidate k = 0 (may be < 0)
@@ -669,8 +627,70 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
     }   // row group in range
     blk += bd.step_blk; g += bd.step_g;                                  // 8 quads further
     if (blk >= bd.n_blk) { blk -= bd.n_blk; g++; }
+  };
+
+  // ---- one edge item: the window's last column, one candidate row per lane (32 rows per item) ---------------------------------
+  // (xal + nx - 1) % 16 == 0, so the column starts a 16-byte block of copy 0 and every lane reads aligned words of its own row.
+  auto edge_item = [&](int item, bool rowkeys) {
+    if constexpr (S >= 16) {
+      const int row = (item - bd.item_start - bd.n_main) * 32 + lane;
+      const bool ok = row < bd.ny;
+      const int rowc = min(row, bd.ny - 1);
+      const uint32_t orgp = smem_u32(s_org) + (uint32_t)bd.org_off;
+      const uint32_t refp = smem_u32(s_ref) + (uint32_t)(bd.win_off + rowc * un.ref_pitch + bd.nx - 1);
+      const uint32_t px = bd.lambda * eg_bits(((bd.lt_x + bd.nx - 1) << 2) - bd.pred_x);
+      const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + bd.cy_first + rowc) << 2) - bd.pred_y);
+      const uint32_t tile_local = rowkeys ? ((uint32_t)rowc << 3) | 4u : (uint32_t)(item - first_item) << LK;
+      uint32_t base[1];
+      bool valid[1] = {ok};
+      base[0] = (ok || !MASK_BY_KEY) ? (__umulhi(px + py, c16) << CU_LOCAL_BITS) + tile_local : KEY_NONE;
+      if constexpr (CHILD) cu16_child_tile<FEN, 1, NSLOT>(refp, orgp, rpitch, opitch, base, best);
+      else                 cu_tile<S, FEN, 1, MASK_BY_KEY, NSLOT>(refp, orgp, rpitch, opitch, base, valid, one, best);
+    }
+  };
+
+  if (w_first < w_last) {
+    // the CU that holds this warp's first item: 32 descriptors per probe instead of a walk of dependent loads
+    for (;; bslot += 32) {
+      const int j = bslot + lane;
+      const bool past = j >= un.job_first + un.job_count || w_first < bundles[j].item_start + bundles[j].n_items;
+      const unsigned m = __ballot_sync(0xffffffffu, past);
+      if (m) { bslot += __ffs(m) - 1; break; }
+    }
+    load_bundle();
+    int item = w_first;
+    for (;;) {                                          // one pass per CU of this warp's run: its block items, then its edge items
+      const bool rowkeys = S >= 16 && bd.edge == 2;
+      const int main_end = min(w_last, bd.item_start + bd.n_main), cu_end = min(w_last, bd.item_start + bd.n_items);
+      bool dirty = false;                               // candidates of this CU are waiting in `best` (tile-numbered keys)
+      if (item < main_end) {
+        first_item = item;
+        locate(item);
+        edge_mode = false;
+        dirty = true;
+        for (; item < main_end; item++) {
+          if (!rowkeys && (S == 8 ? __any_sync(0xffffffffu, (g - g0) >= (1 << (CU_LOCAL_BITS - 4 - bd.rank_bits))) : (item - first_item >= TILE_LIMIT))) {
+            flush();                                    // the local index would run out of bits
+            first_item = item; g0 = g;
+          }
+          block_item(item, rowkeys);
+        }
+      }
+      if (S >= 16 && item < cu_end) {
+        if (!rowkeys && dirty) flush();                 // tile-numbered keys: the last column's candidates precede later rows' in raster
+        first_item = item;                              // order, so a lane's local order holds only inside one kind of item
+        edge_mode = true;
+        for (; item < cu_end; item++) {
+          if (!rowkeys && item - first_item >= TILE_LIMIT) { flush(); first_item = item; }
+          edge_item(item, rowkeys);
+        }
+      }
+      flush();                                          // this warp's candidates of the CU: one atomicMin per PU
+      if (item >= w_last) break;
+      do { bslot++; } while (item >= bundles[bslot].item_start + bundles[bslot].n_items);
+      load_bundle();
+    }
   }
-  if (w_first < w_last) flush();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -931,6 +951,9 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
       // 129 = 8 * 16 + 1: a last block with a single column in it runs as edge items (a lane per candidate row) instead
       d.edge = (use_edge && b.S >= 16 && d.n_blk >= 2 && ((d.xal + d.nx) & 15) == 1) ? 1 : 0;
       if (d.edge) d.n_blk--;
+      // eight blocks per candidate row and at most 256 rows: row-indexed argmin keys (see k_search8_cu), no flush between the
+      // block items and the edge items of a CU
+      if (d.edge && d.n_blk == 8 && d.ny <= 256 && !getenv("HMB200_NO_ROW_KEYS")) d.edge = 2;
       d.step_g = GM.groups / d.n_blk; d.step_blk = GM.groups % d.n_blk;      // 8-bit kernels: consecutive items per warp
       d.rank_bits = 0;
       while ((8 << d.rank_bits) < d.n_blk) d.rank_bits++;
