@@ -217,6 +217,8 @@ int  hmb200_mc_dist_batch(int cur_plane, int ref_plane, int func, int n, const h
  * TComDataCU::getInterMergeCandidates); mv*: quarter pel, clipped by the caller (TComDataCU::clipMv, as xPredInterUni does);
  * ref*_plane: registered planes of the two reference pictures (ignored for an unused list); bits: the candidate's rate term
  * (uiBitsCand of xMergeEstimation / m_auiMVPIdxCost[idx][AMVP_MAX_NUM_CANDS] of xGetTemplateCost).  48 bytes. */
+#define HMB200_INTER_DIR_NO_IDENTICAL_CHECK 4   /* or'ed into inter_dir = 3: the caller has already applied xCheckIdenticalMotion (on the
+                                                 * unclipped MVs and the POCs, as the reference does); always average the two lists */
 typedef struct {
   int32_t pu_x, pu_y, w, h;
   int32_t inter_dir;

@@ -30,11 +30,16 @@ void hmb200_shim_ref_plane(TComPic* pic);
 bool hmb200_shim_pattern_search(TEncSearch* self, TComPattern* key, Pel* piRefY, Int iRefStride, TComMv* lt, TComMv* rb, TComMv& rcMv, Distortion& ruiSAD);
 class TComDataCU;
 bool hmb200_shim_pattern_search_fast(TEncSearch* self, TComDataCU* pcCU, TComPattern* key, Pel* piRefY, Int iRefStride, TComMv* lt, TComMv* rb, TComMv& rcMv, Distortion& ruiSAD, const TComMv* pIntegerMv2Nx2NPred);
+class TComYuv;
+class TComMvField;
+bool hmb200_shim_merge_estimation(TEncSearch* self, TComDataCU* pcCU, TComYuv* pcYuvOrg, Int iPUIdx, UInt uiAbsPartIdx, Int iWidth, Int iHeight, TComMvField* nb, UChar* dirs, Int numValid, UInt& uiInterDir, TComMvField* pacMvField, UInt& uiMergeIndex, Distortion& ruiCost);
 bool hmb200_shim_pattern_search_frac(TEncSearch* self, Bool lossless, TComPattern* key, Pel* piRefY, Int iRefStride, TComMv* mvInt, TComMv& rcMvHalf, TComMv& rcMvQter, Distortion& ruiCost);
 '''
 FWD_SEARCH = "  if (hmb200_shim_pattern_search(this, pcPatternKey, piRefY, iRefStride, pcMvSrchRngLT, pcMvSrchRngRB, rcMv, ruiSAD)) return;\n"
 FWD_FRAC = "  if (hmb200_shim_pattern_search_frac(this, bIsLosslessCoded, pcPatternKey, piRefY, iRefStride, pcMvInt, rcMvHalf, rcMvQter, ruiCost)) return;\n"
 FWD_FAST = "  if (hmb200_shim_pattern_search_fast(this, pcCU, pcPatternKey, piRefY, iRefStride, pcMvSrchRngLT, pcMvSrchRngRB, rcMv, ruiSAD, pIntegerMv2Nx2NPred)) return;\n"
+FWD_MERGE = "  if (hmb200_shim_merge_estimation(this, pcCU, pcYuvOrg, iPUIdx, uiAbsPartIdx, iWidth, iHeight, cMvFieldNeighbours, uhInterDirNeighbours, numValidMergeCand, uiInterDir, pacMvField, uiMergeIndex, ruiCost)) return;\n"
+MERGE_ANCHOR = "  xRestrictBipredMergeCand( pcCU, iPUIdx, cMvFieldNeighbours, uhInterDirNeighbours, numValidMergeCand );\n"
 FWD_PLANE = "  hmb200_shim_ref_plane(pcCU->getSlice()->getRefPic( eRefPicList, iRefIdxPred ));\n"
 
 
@@ -55,6 +60,8 @@ def patched_source():
     src = inject_after_open_brace(src, "Void TEncSearch::xPatternSearchFracDIF(", FWD_FRAC)
     src = inject_after_open_brace(src, "Void TEncSearch::xPatternSearchFast( TComDataCU*   pcCU,", FWD_FAST)
     src = inject_after_open_brace(src, "Void TEncSearch::xMotionEstimation( TComDataCU* pcCU,", FWD_PLANE)
+    assert src.count(MERGE_ANCHOR) == 1
+    src = src.replace(MERGE_ANCHOR, MERGE_ANCHOR + FWD_MERGE)          # xMergeEstimation: ahead of the candidate loop (:2868)
     return src
 
 

@@ -62,7 +62,7 @@ struct Shim {
   bool in_reference = false;          // re-entrancy guard of verify mode
   FILE* log = nullptr;
   std::map<const Pel*, std::pair<int, int> > planes;   // buffer origin -> (plane id, POC)
-  unsigned long long n_search = 0, n_frac = 0, n_upload = 0, n_frac_fused = 0;
+  unsigned long long n_search = 0, n_frac = 0, n_upload = 0, n_frac_fused = 0, n_merge = 0, n_merge_cands = 0;
   double seconds = 0.0;                              // wall time spent inside the forwarders (host copies, launches, waits)
   // xMotionEstimation calls xPatternSearch and then xPatternSearchFracDIF on the MV it found (TEncSearch.cpp:3728, 3749): the
   // search forwarder runs both in one device round trip and keeps the refinement for the forwarder that follows
@@ -96,6 +96,8 @@ void die(const char* what) {
 void at_exit() {
   fprintf(stderr, "hmb200 shim: %llu integer searches, %llu fractional refinements (%llu of them served by the search's round trip), %llu plane uploads, %llu kernel launches, %.2f s inside the forwarders\n",
           g_shim.n_search, g_shim.n_frac, g_shim.n_frac_fused, g_shim.n_upload, (unsigned long long)hmb200_launch_count(), g_shim.seconds);
+  if (g_shim.n_merge)
+    fprintf(stderr, "hmb200 shim: %llu merge estimations (%llu candidates) through hmb200_merge_estimation_batch\n", g_shim.n_merge, g_shim.n_merge_cands);
   if (g_shim.table_period)
     fprintf(stderr, "hmb200 shim: distortion-table hook: SAD %llu/%llu SADS %llu/%llu SSE %llu/%llu HADS %llu/%llu calls evaluated on the GPU (all equal)\n",
             g_shim.table_checked[0], g_shim.table_calls[0], g_shim.table_checked[3], g_shim.table_calls[3], g_shim.table_checked[1],
@@ -141,24 +143,27 @@ hmb200_pattern pattern_of(TComPattern* key) {
 // Injected at the top of xMotionEstimation: makes sure the reconstructed reference picture is resident on the GPU.
 // Reconstructed planes are final and border-extended when a picture enters a reference list
 // (TLibCommon/TComSlice.cpp:351-377); a picture buffer is re-used for later pictures, hence the POC check.
-void hmb200_shim_ref_plane(TComPic* pic) {
-  if (!active()) return;
-  Stopwatch sw;
-  TComPicYuv* rec = pic->getPicYuvRec();
-  const Pel* origin = rec->getAddr(COMPONENT_Y);
-  const int poc = pic->getPOC();
+static int plane_of(TComPicYuv* yuv, int poc, int bit_depth, int kind) {
+  const Pel* origin = yuv->getAddr(COMPONENT_Y);
   std::map<const Pel*, std::pair<int, int> >::iterator it = g_shim.planes.find(origin);
   if (it != g_shim.planes.end()) {
-    if (it->second.second == poc) return;
+    if (it->second.second == poc) return it->second.first;
     hmb200_release_plane(it->second.first);
     g_shim.planes.erase(it);
   }
-  const int mx = rec->getMarginX(COMPONENT_Y), my = rec->getMarginY(COMPONENT_Y);
-  const int id = hmb200_register_plane(origin, rec->getStride(COMPONENT_Y), rec->getWidth(COMPONENT_Y), rec->getHeight(COMPONENT_Y),
-                                       mx, my, pic->getPicSym()->getSPS().getBitDepth(CHANNEL_TYPE_LUMA), HMB200_PLANE_REC, poc);
+  const int mx = yuv->getMarginX(COMPONENT_Y), my = yuv->getMarginY(COMPONENT_Y);
+  const int id = hmb200_register_plane(origin, yuv->getStride(COMPONENT_Y), yuv->getWidth(COMPONENT_Y), yuv->getHeight(COMPONENT_Y), mx, my,
+                                       bit_depth, kind, poc);
   if (id < 0) die("hmb200_register_plane");
   g_shim.planes[origin] = std::make_pair(id, poc);
   g_shim.n_upload++;
+  return id;
+}
+
+void hmb200_shim_ref_plane(TComPic* pic) {
+  if (!active()) return;
+  Stopwatch sw;
+  plane_of(pic->getPicYuvRec(), pic->getPOC(), pic->getPicSym()->getSPS().getBitDepth(CHANNEL_TYPE_LUMA), HMB200_PLANE_REC);
 }
 
 // TEncSearch::xPatternSearch (TLibEncoder/TEncSearch.cpp:3786-3843).  Returns true when the call was served.
@@ -346,4 +351,94 @@ void hmb200_shim_dist_table(FpDistFunc* table, int n) {
   if (g_shim.table_period == 0) return;
   for (int i = 0; i < DF_TOTAL_FUNCTIONS; i++) g_shim.orig[i] = table[i];
   TableFill<0>::run(table);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// TEncSearch::xMergeEstimation's candidate loop (TLibEncoder/TEncSearch.cpp:2868-2892): build_shim.py injects a call to this
+// function right after xRestrictBipredMergeCand.  All candidates of the PU go to the device in one hmb200_merge_estimation_batch
+// call: motion compensation (uni- or bi-directional) + HADs / SAD of every candidate, the argmin with getCost(bits) on the way back.
+// Opt-in: HMB200_SHIM_MERGE=1 (default: the reference loop).  Returns true when the call was served.
+// ---------------------------------------------------------------------------------------------------------------------
+bool hmb200_shim_merge_estimation(TEncSearch* self, TComDataCU* pcCU, TComYuv* pcYuvOrg, Int iPUIdx, UInt uiAbsPartIdx, Int iWidth, Int iHeight,
+                                  TComMvField* nb, UChar* dirs, Int numValid, UInt& uiInterDir, TComMvField* pacMvField, UInt& uiMergeIndex,
+                                  Distortion& ruiCost) {
+  if (!active() || numValid <= 0) return false;
+  // opt-in (HMB200_SHIM_MERGE=1): exact, but one more device round trip per PU where the host needs ~5 small motion compensations -
+  // measured on 1080p I+P it adds 5.7 s (191 164 calls x 30 us) to a 28.9 s encode; the batched entry pays off from a frontend that
+  // hands over the candidates of many PUs at once
+  static const bool enabled = getenv("HMB200_SHIM_MERGE") && strcmp(getenv("HMB200_SHIM_MERGE"), "0") != 0;
+  if (!enabled) return false;
+  TComSlice* slice = pcCU->getSlice();
+  if (slice->getPPS()->getUseWP() || slice->getPPS()->getWPBiPred()) return false;       // weighted prediction is out of scope
+  Stopwatch sw;
+  g_shim.fused.valid = false;
+  const int bd = slice->getSPS()->getBitDepth(CHANNEL_TYPE_LUMA);
+  TComPic* pic = pcCU->getPic();
+  TComPicYuv* org = pic->getPicYuvOrg();
+  const int org_plane = plane_of(org, pic->getPOC(), bd, HMB200_PLANE_ORG);
+  const ptrdiff_t off = org->getAddr(COMPONENT_Y, pcCU->getCtuRsAddr(), pcCU->getZorderIdxInCtu() + uiAbsPartIdx) - org->getAddr(COMPONENT_Y);
+  const int stride = org->getStride(COMPONENT_Y);
+  const int pu_y = (int)(off / stride), pu_x = (int)(off - (ptrdiff_t)pu_y * stride);     // positions inside the picture: 0 <= x < width <= stride
+  hmb200_mc_cand c[MRG_MAX_NUM_CANDS];
+  const int maxc = (int)self->m_pcEncCfg->getMaxNumMergeCand();
+  for (int i = 0; i < numValid; i++) {
+    const TComMvField &f0 = nb[2 * i], &f1 = nb[2 * i + 1];
+    hmb200_mc_cand& k = c[i];
+    memset(&k, 0, sizeof(k));
+    k.pu_x = pu_x; k.pu_y = pu_y; k.w = iWidth; k.h = iHeight;
+    int dir = 0;
+    if (f0.getRefIdx() >= 0) {
+      TComMv m = f0.getMv(); pcCU->clipMv(m);
+      TComPic* rp = slice->getRefPic(REF_PIC_LIST_0, f0.getRefIdx());
+      k.mv0_x = m.getHor(); k.mv0_y = m.getVer(); k.ref0_plane = plane_of(rp->getPicYuvRec(), rp->getPOC(), bd, HMB200_PLANE_REC);
+      dir |= 1;
+    }
+    if (f1.getRefIdx() >= 0) {
+      TComMv m = f1.getMv(); pcCU->clipMv(m);
+      TComPic* rp = slice->getRefPic(REF_PIC_LIST_1, f1.getRefIdx());
+      k.mv1_x = m.getHor(); k.mv1_y = m.getVer(); k.ref1_plane = plane_of(rp->getPicYuvRec(), rp->getPOC(), bd, HMB200_PLANE_REC);
+      dir |= 2;
+    }
+    if (dir == 0) return false;                                                            // not a usable candidate: leave it to the reference
+    if (dir == 3) {
+      // xCheckIdenticalMotion (TLibCommon/TComPrediction.cpp:496-517) looks at the UNCLIPPED vectors and the POCs
+      const bool same = slice->isInterB() && slice->getRefPic(REF_PIC_LIST_0, f0.getRefIdx())->getPOC() == slice->getRefPic(REF_PIC_LIST_1, f1.getRefIdx())->getPOC() &&
+                        f0.getMv() == f1.getMv();
+      dir = same ? 1 : (3 | HMB200_INTER_DIR_NO_IDENTICAL_CHECK);
+    }
+    k.inter_dir = dir;
+    k.bits = i + 1 - (i == maxc - 1 ? 1 : 0);
+  }
+  const int32_t first[2] = {0, (int32_t)numValid};
+  uint32_t best = 0, cost = 0, dist[MRG_MAX_NUM_CANDS];
+  const int use_had = self->m_pcEncCfg->getUseHADME() && (pcCU->getCUTransquantBypass(iPUIdx) == 0);
+  if (hmb200_merge_estimation_batch(org_plane, 1, first, c, use_had, self->m_pcRdCost->m_uiCost, &best, &cost, dist) != HMB200_OK)
+    die("hmb200_merge_estimation_batch");
+  g_shim.n_merge++; g_shim.n_merge_cands += (unsigned long long)numValid;
+  const PartSize ePartSize = pcCU->getPartitionSize(0);
+  if (g_shim.mode == VERIFY) {
+    // the reference loop, candidate by candidate
+    for (int i = 0; i < numValid; i++) {
+      Distortion e = 0;
+      pcCU->getCUMvField(REF_PIC_LIST_0)->setAllMvField(nb[2 * i], ePartSize, uiAbsPartIdx, 0, iPUIdx);
+      pcCU->getCUMvField(REF_PIC_LIST_1)->setAllMvField(nb[2 * i + 1], ePartSize, uiAbsPartIdx, 0, iPUIdx);
+      g_shim.in_reference = true;
+      self->xGetInterPredictionError(pcCU, pcYuvOrg, iPUIdx, e, self->m_pcEncCfg->getUseHADME());
+      g_shim.in_reference = false;
+      if ((uint32_t)e != dist[i]) {
+        fprintf(stderr, "hmb200 shim: merge candidate %d of a %dx%d PU at (%d,%d): gpu %u, reference %u (dir %d)\n", i, iWidth, iHeight, pu_x, pu_y,
+                dist[i], (unsigned)e, c[i].inter_dir);
+        abort();
+      }
+    }
+  }
+  // what the reference loop leaves behind: the CU's MV fields hold the last candidate
+  pcCU->getCUMvField(REF_PIC_LIST_0)->setAllMvField(nb[2 * (numValid - 1)], ePartSize, uiAbsPartIdx, 0, iPUIdx);
+  pcCU->getCUMvField(REF_PIC_LIST_1)->setAllMvField(nb[2 * (numValid - 1) + 1], ePartSize, uiAbsPartIdx, 0, iPUIdx);
+  ruiCost = cost;
+  uiMergeIndex = best;
+  uiInterDir = dirs[best];
+  pacMvField[0] = nb[2 * best];
+  pacMvField[1] = nb[2 * best + 1];
+  return true;
 }

@@ -31,17 +31,20 @@ def test_golden_file_is_consistent():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("frames,mode", [(3, "verify"), (8, "gpu")])
-def test_encoder_bitstream_md5_matches_reference(tmp_path, frames, mode):
+@pytest.mark.parametrize("frames,mode,merge", [(3, "verify", "1"), (8, "gpu", "0"), (8, "gpu", "1")])
+def test_encoder_bitstream_md5_matches_reference(tmp_path, frames, mode, merge):
+    """merge = "1": xMergeEstimation's candidate loop goes through hmb200_merge_estimation_batch as well (verify mode compares
+    every candidate's prediction error with xGetInterPredictionError)."""
     _need_binary()
     gold = json.load(open(GOLD))[str(frames)]
     yuv, binf = str(tmp_path / "clip.yuv"), str(tmp_path / "out.bin")
     meg.write_clip(yuv, frames)
     assert hashlib.md5(open(yuv, "rb").read()).hexdigest() == gold["yuv_md5"], "synthetic clip differs from the golden run's"
-    env = dict(os.environ, HMB200_SHIM=mode)
+    env = dict(os.environ, HMB200_SHIM=mode, HMB200_SHIM_MERGE=merge)
     p = subprocess.run([BIN] + meg.encoder_args(CFG, yuv, frames, binf), capture_output=True, text=True, env=env, timeout=1500)
     assert p.returncode == 0, p.stderr[-2000:]
     assert "integer searches" in p.stderr and " 0 integer searches" not in p.stderr, "the GPU path was not exercised"
+    assert ("merge estimations" in p.stderr) == (merge == "1")
     assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
     assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]
 
@@ -103,7 +106,7 @@ def test_encoder_bitstream_md5_randomaccess_main10(tmp_path):
     meg.write_clip_ra10(yuv, gold["frames"])
     assert hashlib.md5(open(yuv, "rb").read()).hexdigest() == gold["yuv_md5"], "synthetic clip differs from the golden run's"
     p = subprocess.run([BIN] + meg.args_ra10(CFG_RA10, yuv, gold["frames"], binf), capture_output=True, text=True,
-                       env=dict(os.environ, HMB200_SHIM="gpu"), timeout=3000)
+                       env=dict(os.environ, HMB200_SHIM="gpu", HMB200_SHIM_MERGE="1"), timeout=3000)     # bi-directional merge candidates on the GPU
     assert p.returncode == 0, p.stderr[-2000:]
     assert "integer searches" in p.stderr and " 0 integer searches" not in p.stderr, "the GPU path was not exercised"
     assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
@@ -121,7 +124,7 @@ def test_encoder_randomaccess_main10_verify_mode_prefix(tmp_path):
     yuv, binf = str(tmp_path / "clip.yuv"), str(tmp_path / "out.bin")
     meg.write_clip_ra10(yuv, 2)
     p = subprocess.run([BIN] + meg.args_ra10(CFG_RA10, yuv, 2, binf), capture_output=True, text=True,
-                       env=dict(os.environ, HMB200_SHIM="verify"), timeout=3000)
+                       env=dict(os.environ, HMB200_SHIM="verify", HMB200_SHIM_MERGE="1"), timeout=3000)
     assert p.returncode == 0, p.stderr[-2000:]
     assert "integer searches" in p.stderr and " 0 integer searches" not in p.stderr, "the GPU path was not exercised"
     assert len(meg.parse_md5_lines(p.stdout)) == 2

@@ -398,6 +398,12 @@ class HMB200:
     def sync(self):
         self._check(self.lib.hmb200_sync())
 
+    def last_timing(self):
+        """CUDA-event times of the last hmb200_run_prepared (total / search / refinement) or hmb200_dist_batch (total = its kernel)."""
+        t = [C.c_float() for _ in range(3)]
+        self._check(self.lib.hmb200_last_timing(*[C.byref(x) for x in t]))
+        return {"total_ms": t[0].value, "search_ms": t[1].value, "frac_ms": t[2].value}
+
 
 class Prepared:
     def __init__(self, owner, handle, n):

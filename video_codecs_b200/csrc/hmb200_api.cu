@@ -734,8 +734,11 @@ int hmb200_dist_batch(int func, int bit_depth, int n, const hmb200_dist_desc* de
   CUDA_TRY(cudaMemcpyAsync(G.dstage, tasks.data(), tb, cudaMemcpyHostToDevice, G.stream));
   uint32_t* d_out = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(G.dstage) + tb);
   int blocks = (n + 3) / 4;
+  CUDA_TRY(cudaEventRecord(G.ev[0], G.stream));       // hmb200_last_timing: total = the kernel alone (descriptor / result copies outside)
+  CUDA_TRY(cudaEventRecord(G.ev[1], G.stream));
   if (bps == 1) k_dist_generic<uint8_t><<<blocks, 128, 0, G.stream>>>(reinterpret_cast<const DistTask*>(G.dstage), d_out, n, func, bit_depth);
   else          k_dist_generic<int16_t><<<blocks, 128, 0, G.stream>>>(reinterpret_cast<const DistTask*>(G.dstage), d_out, n, func, bit_depth);
+  CUDA_TRY(cudaEventRecord(G.ev[2], G.stream));
   G.launches++;
   CUDA_TRY(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, G.stream));
   CUDA_TRY(cudaStreamSynchronize(G.stream));
@@ -802,15 +805,17 @@ static int mc_cand_run(int cur_plane, int func, int n, const hmb200_mc_cand* can
   if (n >= (1 << 24)) return fail(HMB200_ERR_ARG, std::string(who) + ": more than 2^24 candidates in one batch");
   for (int i = 0; i < n; i++) {
     const hmb200_mc_cand& c = cands[i];
-    if (!supported_pu(c.w, c.h) || c.inter_dir < 1 || c.inter_dir > 3)
+    const bool no_check = (c.inter_dir & HMB200_INTER_DIR_NO_IDENTICAL_CHECK) != 0;
+    const int dir_in = c.inter_dir & 3;
+    if (!supported_pu(c.w, c.h) || dir_in < 1 || (c.inter_dir & ~7) || (no_check && dir_in != 3))
       return fail(HMB200_ERR_ARG, std::string(who) + ": unsupported PU size or inter_dir in candidate " + std::to_string(i));
     if (!box_inside(pc->d, Box{c.pu_x, c.pu_y, c.pu_x + c.w, c.pu_y + c.h}))
       return fail(HMB200_ERR_ARG, std::string(who) + ": PU of candidate " + std::to_string(i) + " leaves the padded current plane");
     McCandDev d{};
     d.org = reinterpret_cast<const char*>(pc->d.base) + ((size_t)(c.pu_y + pc->d.margin_y) * pc->d.pitch + (c.pu_x + pc->d.margin_x)) * bps;
     d.org_pitch = pc->d.pitch; d.w = c.w; d.h = c.h;
-    int dir = c.inter_dir;
-    if (dir == 3 && c.ref0_plane == c.ref1_plane && c.mv0_x == c.mv1_x && c.mv0_y == c.mv1_y) dir = 1;     // xCheckIdenticalMotion
+    int dir = dir_in;
+    if (dir == 3 && !no_check && c.ref0_plane == c.ref1_plane && c.mv0_x == c.mv1_x && c.mv0_y == c.mv1_y) dir = 1;     // xCheckIdenticalMotion
     for (int l = 0; l < 2; l++) {
       if (!(dir & (1 << l))) continue;
       Plane* pr = get_plane(l ? c.ref1_plane : c.ref0_plane);
@@ -1185,11 +1190,11 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
     const S8Kernel* kern = search8_kernels();
     const S8CuKernel* cukern = bps == 1 ? search8_cu_kernels() : search16_cu_kernels();
     CUDA_TRY(cudaEventRecord(G.ev_fork, G.stream));
-    int order[S8V_COUNT + CUV_COUNT], used = 0;       // >= 0: per-PU variant, < 0: CU-fused variant ~v
+    int order[S8V_COUNT + CUV_MAX], used = 0;       // >= 0: per-PU variant, < 0: CU-fused variant ~v
     if (bps == 1) {                                   // longest CTAs first: 16x16 CUs with their children, then 8x8 CUs
       for (int v = CUV_BASE_COUNT; v < CUV_COUNT; v++) if (cu.unit_count[v] > 0) order[used++] = ~v;
       for (int v = 0; v < CUV_BASE_COUNT; v++) if (cu.unit_count[v] > 0) order[used++] = ~v;
-    } else for (int v = CUV_BASE_COUNT - 1; v >= 0; v--) if (cu.unit_count[v] > 0) order[used++] = ~v;
+    } else for (int v = CUV16_COUNT - 1; v >= 0; v--) if (cu.unit_count[v] > 0) order[used++] = ~v;
     for (int v = S8V_COUNT - 1; v >= 0; v--) if (sc.unit_count[v] > 0) order[used++] = v;     // wide tiles first
     for (int k = 0; k < used; k++) {
       const int v = order[k];

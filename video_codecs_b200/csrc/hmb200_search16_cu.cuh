@@ -37,20 +37,35 @@ __device__ __forceinline__ void cu16_load_org_raw(const uint8_t* p, uint32_t (&o
 // one reference row against WW original words: M[c][k] += sum of minima, W[j] += sum of the j-th reference word.
 // SHIFT: rp8 is word-aligned and the lane's words start `sh` bits in (one funnel shift per word); otherwise rp8 points
 // into the window copy of the lane's sample phase and the words are read as they are.
-template <int WW, int NC, bool SHIFT>
+// A8: rp8 is 8-byte aligned (host: every bundle of the unit has win_off % 8 == 0 and blocks start on multiples of 8 samples):
+// the row is read with 64-bit loads.  A pair of lanes is 16 bytes apart from the next pair, so a 32-bit load puts pairs q and
+// q + 8 on the same bank (two wavefronts per load: 42 % of the shared-memory wavefronts were conflicts in round 1); a 64-bit
+// load is served per half-warp, whose eight pairs (and the two window copies, 8 bytes apart modulo 128) fall on 32 distinct banks.
+template <int WW, int NC, bool SHIFT, bool A8>
 __device__ __forceinline__ void cu16_row_min(const uint8_t* rp8, const uint32_t (&o)[WW], uint32_t sh, uint32_t (*M)[4],
                                              uint32_t (&W)[WW + 3]) {
-  const uint32_t* rp = reinterpret_cast<const uint32_t*>(rp8);
-  uint32_t lo = SHIFT ? rp[0] : 0u;
+  constexpr int NW = SHIFT ? WW + 4 : WW + 3;
+  uint32_t rw[(NW + 1) & ~1];
+  if constexpr (A8) {
+#pragma unroll
+    for (int i = 0; i < (NW + 1) / 2; i++) {
+      const uint2 v = reinterpret_cast<const uint2*>(rp8)[i];
+      rw[2 * i] = v.x; rw[2 * i + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NW; i++) rw[i] = reinterpret_cast<const uint32_t*>(rp8)[i];
+  }
+  uint32_t lo = SHIFT ? rw[0] : 0u;
 #pragma unroll
   for (int j = 0; j < WW + 3; j++) {
     uint32_t sw;
     if constexpr (SHIFT) {
-      const uint32_t hi = rp[j + 1];
+      const uint32_t hi = rw[j + 1];
       sw = __funnelshift_r(lo, hi, sh);
       lo = hi;
     } else {
-      sw = rp[j];
+      sw = rw[j];
     }
     W[j] = (uint32_t)__dp2a_lo((int)sw, 0x0101, (int)W[j]);
 #pragma unroll
@@ -87,7 +102,7 @@ __device__ __forceinline__ void cu16_fold(uint32_t (*M)[4], const uint32_t (&W)[
 }
 
 // rows row0, row0 + rstep, ... (NROWS of them) of one chunk of WW words: acc[c][k] (zero on entry) <- SAD over those rows
-template <int WW, int NC, int NROWS, bool SHIFT>
+template <int WW, int NC, int NROWS, bool SHIFT, bool A8>
 __device__ __forceinline__ void cu16_strip_min(const uint8_t* refp, int ref_pitch, const uint8_t* orgp, int org_pitch, int row0,
                                                int rstep, uint32_t sh, uint32_t (*acc)[4], const uint32_t* asum) {
   uint32_t W[WW + 3];
@@ -98,14 +113,14 @@ __device__ __forceinline__ void cu16_strip_min(const uint8_t* refp, int ref_pitc
     for (int i = 0; i < NROWS; i++) {
       uint32_t o[WW];
       cu16_load_org_raw<WW>(orgp + (row0 + i * rstep) * org_pitch, o);
-      cu16_row_min<WW, NC, SHIFT>(refp + (row0 + i * rstep) * ref_pitch, o, sh, acc, W);
+      cu16_row_min<WW, NC, SHIFT, A8>(refp + (row0 + i * rstep) * ref_pitch, o, sh, acc, W);
     }
   } else {
 #pragma unroll 1
     for (int i = 0, row = row0; i < NROWS; i++, row += rstep) {
       uint32_t o[WW];
       cu16_load_org_raw<WW>(orgp + row * org_pitch, o);
-      cu16_row_min<WW, NC, SHIFT>(refp + row * ref_pitch, o, sh, acc, W);
+      cu16_row_min<WW, NC, SHIFT, A8>(refp + row * ref_pitch, o, sh, acc, W);
     }
   }
   cu16_fold<WW, NC>(acc, W, asum);
@@ -164,7 +179,7 @@ __device__ __forceinline__ void cu16_epilogue(const uint32_t (&E)[4][4][4], cons
   cu16_min(best[12], ec[3], ss, shr, base);
 }
 
-template <int S, bool FEN>
+template <int S, bool FEN, bool A8>
 __global__ void __launch_bounds__(S8_THREADS, 2)
 k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bundles, unsigned long long* __restrict__ keys,
               DevPlane cur_plane, DevPlane ref_plane) {
@@ -245,7 +260,7 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
         const int q = (it - bd.item_start) * 16 + (lane >> 1);
         const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
         const int w = (int)(local & ((1u << LK) - 1u));
-        const int cyi = bd.cy_first + g * KY + (w >> 2), cxi = min(blk * 8, bd.nx - 8) + (lane & 1) + 2 * (w & 3);
+        const int cyi = bd.cy_first + g * KY + (w >> 2), cxi = (A8 ? blk * 8 : min(blk * 8, bd.nx - 8)) + (lane & 1) + 2 * (w & 3);
         b = make_key(best[s] >> CU_LOCAL_BITS, (uint32_t)(cyi * bd.nx + cxi));
       }
 #pragma unroll
@@ -270,7 +285,8 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
     if (q < bd.n_blk * bd.n_rowgroups) {
       const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
       const int cyl0 = g * KY;                                            // candidate row inside this (row-split) bundle
-      const int cxi0 = min(blk * 8, bd.nx - 8) + (lane & 1);              // the last block overlaps its neighbour
+      // the last block overlaps its neighbour - or (A8: blocks stay on multiples of 8 samples) runs past the window and is masked
+      const int cxi0 = (A8 ? blk * 8 : min(blk * 8, bd.nx - 8)) + (lane & 1);
       const int off = bd.win_off + cyl0 * un.ref_pitch + cxi0 * 2;        // bytes
       const uint8_t* refp = s_ref + ((TWO && (off & 2)) ? un.copy_stride : 0) + (off & ~3);
       const uint32_t sh = (uint32_t)(off & 3) * 8u;      // used by the single-copy kernels only
@@ -299,10 +315,17 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
           }
 #pragma unroll
         for (int r = 0; r < 8 + KY - 1; r++) {
-          const uint32_t* rp = reinterpret_cast<const uint32_t*>(refp + r * un.ref_pitch);
+          uint32_t rw[8];
+          if constexpr (A8) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const uint2 v = reinterpret_cast<const uint2*>(refp + r * un.ref_pitch)[i]; rw[2 * i] = v.x; rw[2 * i + 1] = v.y; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 7; i++) rw[i] = reinterpret_cast<const uint32_t*>(refp + r * un.ref_pitch)[i];
+          }
 #pragma unroll
           for (int j = 0; j < 4 + 3; j++) {
-            const uint32_t sw = rp[j];
+            const uint32_t sw = rw[j];
 #pragma unroll
             for (int jy = 0; jy < KY; jy++) {
               if (r - jy >= 0 && r - jy < 8) {
@@ -339,6 +362,7 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
             const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + cyi) << 2) - bd.pred_y);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
+              if (A8 && cxi0 + 2 * k >= bd.nx) continue;                  // masked column of the last block
               const uint32_t base = (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)(jy * 4 + k);
               const uint32_t t = Q[jy][0][0][k] + Q[jy][0][1][k], b = Q[jy][1][0][k] + Q[jy][1][1][k];
               const uint32_t l = Q[jy][0][0][k] + Q[jy][1][0][k], r = Q[jy][0][1][k] + Q[jy][1][1][k];
@@ -369,11 +393,11 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
           const bool odd_here = ODD_ALL || (ODD_EDGE && (r == 0 || r == 3));
 #pragma unroll
           for (int ch = 0; ch < NCH; ch++)
-            cu16_strip_min<CH, CPC, G / RSTEP, !TWO>(refp + ch * CH * 4, un.ref_pitch, orgp + ch * CH * 4, un.org_pitch, r * G, RSTEP, sh,
+            cu16_strip_min<CH, CPC, G / RSTEP, !TWO, A8>(refp + ch * CH * 4, un.ref_pitch, orgp + ch * CH * 4, un.org_pitch, r * G, RSTEP, sh,
                                                      &E[r][ch * CPC], asum + r * 4 + ch * CPC);
           if (PARITY && odd_here) {
             static_assert(!PARITY || S == 64 || NCH == 1, "odd rows: one chunk per row");
-            cu16_strip_min<CH, 1, G / 2, !TWO>(refp, un.ref_pitch, orgp, un.org_pitch, r * G + 1, 2, sh, &O[r], asum + 16 + r);
+            cu16_strip_min<CH, 1, G / 2, !TWO, A8>(refp, un.ref_pitch, orgp, un.org_pitch, r * G + 1, 2, sh, &O[r], asum + 16 + r);
           }
         }
         if (cyl0 < bd.ny) {
@@ -381,7 +405,8 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
           const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + cyi) << 2) - bd.pred_y);
 #pragma unroll
           for (int k = 0; k < 4; k++)
-            cu16_epilogue<S, FEN>(E, O, k, shr, (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)k, best);
+            if (!A8 || cxi0 + 2 * k < bd.nx)
+              cu16_epilogue<S, FEN>(E, O, k, shr, (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)k, best);
         }
       }
     }
@@ -389,16 +414,20 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
   flush();
 }
 
+// variants 0..6 as cu_variant(); 7..13 = the same with A8 (64-bit loads, masked last block) for units whose windows are 8-byte aligned
+constexpr int CUV16_COUNT = 2 * CUV_BASE_COUNT;
 typedef void (*S16CuKernel)(const S8Unit*, const S8Bundle*, unsigned long long*, DevPlane, DevPlane);
 inline const S16CuKernel* search16_cu_kernels() {
-  static const S16CuKernel table[CUV_BASE_COUNT] = { k_search16_cu<8, false>, k_search16_cu<16, false>, k_search16_cu<16, true>,
-                                                k_search16_cu<32, false>, k_search16_cu<32, true>, k_search16_cu<64, false>,
-                                                k_search16_cu<64, true> };
+  static const S16CuKernel table[CUV16_COUNT] = {
+      k_search16_cu<8, false, false>, k_search16_cu<16, false, false>, k_search16_cu<16, true, false>, k_search16_cu<32, false, false>,
+      k_search16_cu<32, true, false>, k_search16_cu<64, false, false>, k_search16_cu<64, true, false>,
+      k_search16_cu<8, false, true>, k_search16_cu<16, false, true>, k_search16_cu<16, true, true>, k_search16_cu<32, false, true>,
+      k_search16_cu<32, true, true>, k_search16_cu<64, false, true>, k_search16_cu<64, true, true> };
   return table;
 }
 inline int cu16_configure(std::string* err) {
   const S16CuKernel* k = search16_cu_kernels();
-  for (int v = 0; v < CUV_BASE_COUNT; v++) {
+  for (int v = 0; v < CUV16_COUNT; v++) {
     cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k[v]), cudaFuncAttributeMaxDynamicSharedMemorySize, S8_SMEM_MAX);
     if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(k_search16_cu): ") + cudaGetErrorString(e); return HMB200_ERR_CUDA; }
   }

@@ -698,6 +698,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
 // ---------------------------------------------------------------------------------------------------------------
 // CUV_16C_*: 16x16 CUs that carry their four 8x8 child CUs (8-bit planes only; the 16-bit tables end at CUV_BASE_COUNT)
 enum : int { CUV_8 = 0, CUV_16_F0, CUV_16_F1, CUV_32_F0, CUV_32_F1, CUV_64_F0, CUV_64_F1, CUV_BASE_COUNT, CUV_16C_F0 = CUV_BASE_COUNT, CUV_16C_F1, CUV_COUNT };
+constexpr int CUV_MAX = 2 * CUV_BASE_COUNT;      // schedule tables: 16-bit planes number their aligned variants 7..13 (hmb200_search16_cu.cuh)
 typedef void (*S8CuKernel)(const S8Unit*, const S8Bundle*, unsigned long long*, DevPlane, DevPlane);
 inline const S8CuKernel* search8_cu_kernels() {
   static const S8CuKernel table[CUV_COUNT] = { k_search8_cu<8, false, false>, k_search8_cu<16, false, false>, k_search8_cu<16, true, false>,
@@ -718,7 +719,7 @@ struct CuSchedule {
   int bps = 1;                                   // bytes per sample of the planes this schedule was built for
   S8Unit* d_units = nullptr;
   S8Bundle* d_bundles = nullptr;
-  int unit_first[CUV_COUNT] = {0}, unit_count[CUV_COUNT] = {0}, smem_of[CUV_COUNT] = {0};
+  int unit_first[CUV_MAX] = {0}, unit_count[CUV_MAX] = {0}, smem_of[CUV_MAX] = {0};
   S8Box rbox{0, 0, 0, 0}, obox{0, 0, 0, 0};
 };
 
@@ -913,25 +914,34 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     if (cu_smem_need(ents[p].rb, ents[p].ob, nullptr, nullptr, bps, ents[p].two) > S8_SMEM_MAX) { if (err) *err = "cu_build_schedule: window too large"; return false; }
     groups.push_back(Group{(int)p, 1, ents[p].rb, ents[p].ob, ents[p].two});
   }
-  const int S_of_variant[CUV_COUNT] = {8, 16, 16, 32, 32, 64, 64, 16, 16};
-  const bool F_of_variant[CUV_COUNT] = {false, false, true, false, true, false, true, false, true};
+  // 8-bit planes: variants 0..8 (7, 8 = 16x16 CUs with children); 16-bit planes: 0..6 and 7..13 = the same with aligned 64-bit loads
+  const int S_of_variant[CUV_MAX] = {8, 16, 16, 32, 32, 64, 64, bps == 1 ? 16 : 8, 16, 16, 32, 32, 64, 64};
+  const bool F_of_variant[CUV_MAX] = {false, false, true, false, true, false, true, bps == 1 ? false : false, bps == 1 ? true : false, true, false, true, false, true};
+  const bool use_a8 = bps == 2 && !getenv("HMB200_NO_LDS64");
+  // 16-bit planes: the unit can read its window rows with 64-bit loads when candidate column 0 sits on an 8-byte boundary of the
+  // staged window (whose origin is 16-sample aligned): (cu_x + lt_x) % 4 == 0
+  auto variant_of = [&](const CuBundleHost& b, const SearchTask& t) {
+    int v = cu_variant(b.S, b.fen, b.child);
+    if (use_a8 && ((b.cu_x + t.lt_x) & 3) == 0) v += CUV_BASE_COUNT;
+    return v;
+  };
   auto rows_visited = [](int S, bool fen) { return (fen && S >= 16) ? (S == 16 ? 16 : S == 32 ? 24 : 32) : S; };
   auto item_cost = [&](int S, bool fen, bool child = false) -> long long {
     return (long long)GM.ky(S) * (rows_visited(S, fen) * (S / 4) * (bps == 1 ? 1 : 6) + (child ? 100 : 40));
   };
-  auto vcost = [&](int v) { return item_cost(S_of_variant[v], F_of_variant[v], v >= CUV_BASE_COUNT); };
+  auto vcost = [&](int v) { return item_cost(S_of_variant[v], F_of_variant[v], bps == 1 && v >= CUV_BASE_COUNT); };
   const bool use_edge = bps == 1 && !getenv("HMB200_NO_EDGE_ITEMS");
   std::vector<S8Bundle> bundles; bundles.reserve(ents.size());
   std::vector<int> bvar; bvar.reserve(ents.size());
   std::vector<std::pair<int, int> > group_range(groups.size());
-  long long variant_cost[CUV_COUNT] = {0};
+  long long variant_cost[CUV_MAX] = {0};
   S8Box all_r{1 << 30, 1 << 30, -(1 << 30), -(1 << 30)}, all_o = all_r;
   for (size_t gi = 0; gi < groups.size(); gi++) {
     Group& g = groups[gi];
     std::vector<int> ids;
     for (int k = 0; k < g.count; k++) ids.push_back(g.first + k);
     std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) {
-      return cu_variant(hb[ents[a].b].S, hb[ents[a].b].fen, hb[ents[a].b].child) > cu_variant(hb[ents[b].b].S, hb[ents[b].b].fen, hb[ents[b].b].child);
+      return variant_of(hb[ents[a].b], any_task(hb[ents[a].b])) > variant_of(hb[ents[b].b], any_task(hb[ents[b].b]));
     });
     const int rx0 = s8_fl(g.rb.x0), ox0 = s8_fl(g.ob.x0);
     const int rpitch = (s8_ce(g.rb.x1) - rx0) * bps, opitch = (s8_ce(g.ob.x1) - ox0) * bps;      // bytes
@@ -964,7 +974,7 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
       d.item_start = item; item += d.n_items;
       for (int s = 0; s < CU_SLOTS; s++) d.out_idx[s] = b.slot_task[s];
       for (int s = 0; s < CU_CHILD_SLOTS; s++) d.child_idx[s] = b.child ? b.child_task[s] : -1;
-      const int v = cu_variant(b.S, b.fen, b.child);
+      const int v = variant_of(b, t);
       const int rows_v = b.child ? 16 : rows_visited(b.S, b.fen);         // child tiles visit every row
       variant_cost[v] += vcost(v) * d.n_main + (vcost(v) / 3) * n_edge;
       out->executed_abs_diffs += ((unsigned long long)d.n_blk * GM.blkw * (unsigned long long)(d.n_rowgroups * GM.ky(b.S)) + (unsigned long long)n_edge * 32) *
@@ -978,10 +988,10 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     }
     all_r = s8_union(all_r, g.rb); all_o = s8_union(all_o, g.ob);
   }
-  long long target[CUV_COUNT];
+  long long target[CUV_MAX];
   int per_slot = bps == 1 ? 3 : 6;                     // units per resident CTA slot and variant (knob: HMB200_UNITS_PER_SLOT); 8-bit: one CTA per SM
   if (const char* e = getenv("HMB200_UNITS_PER_SLOT")) per_slot = std::max(1, atoi(e));
-  for (int v = 0; v < CUV_COUNT; v++) target[v] = std::max<long long>(variant_cost[v] / std::max(1, sm_count * (bps == 1 ? 1 : 2) * per_slot), 4000);
+  for (int v = 0; v < CUV_MAX; v++) target[v] = std::max<long long>(variant_cost[v] / std::max(1, sm_count * (bps == 1 ? 1 : 2) * per_slot), 4000);
   std::vector<S8Unit> units;
   for (size_t gi = 0; gi < groups.size(); gi++) {
     const Group& g = groups[gi];
