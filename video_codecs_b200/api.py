@@ -56,7 +56,8 @@ class _CostState(C.Structure):
 
 
 def lib_path():
-    return os.path.join(HERE, "libhmb200.so")
+    """video_codecs_b200/libhmb200.so; HMB200_LIB names another build of the same sources (A/B experiments with compile-time knobs)."""
+    return os.environ.get("HMB200_LIB") or os.path.join(HERE, "libhmb200.so")
 
 
 def _load():

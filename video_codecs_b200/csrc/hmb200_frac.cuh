@@ -289,7 +289,10 @@ __global__ void k_frac_unique(int stage, const SearchTask* __restrict__ tasks, c
                                  ((unsigned long long)((uint32_t)(u.hx + 1) & 3u) << 56) | ((unsigned long long)((uint32_t)(u.hy + 1) & 3u) << 58);
   uint32_t slot = frac_hash64(key) & mask;
   for (;;) {
-    const unsigned long long prev = atomicCAS(&hkeys[slot], FRAC_KEY_EMPTY, key);
+    // most instances find their tile already there (4-8 instances per unique tile on coherent content): a plain load first,
+    // the compare-and-swap only for slots that still look empty
+    unsigned long long prev = *reinterpret_cast<volatile unsigned long long*>(&hkeys[slot]);
+    if (prev == FRAC_KEY_EMPTY) prev = atomicCAS(&hkeys[slot], FRAC_KEY_EMPTY, key);
     if (prev == FRAC_KEY_EMPTY) {                        // first instance of this tile
       const uint32_t id = atomicAdd(count, 1u);
       hval[slot] = id;
@@ -302,17 +305,21 @@ __global__ void k_frac_unique(int stage, const SearchTask* __restrict__ tasks, c
   inst_slot[i] = slot;
 }
 
-// dist[pu][c] += udist[unique id of instance i][c]; one thread per (instance, candidate)
-__global__ void k_frac_gather(int stage, const uint32_t* __restrict__ tiles, int n_tiles, const uint32_t* __restrict__ inst_slot,
+// dist[pu][c] = sum over the PU's tile instances of udist[unique id][c]: one thread per (PU, candidate), plain stores.  The tile
+// instances of a PU are contiguous in its tile table (frac_build_schedule emits them PU by PU): pu_first[pu] .. pu_first[pu + 1];
+// a PU has tiles of one size only, so every (PU, candidate) is written by exactly one of the two launches.
+__global__ void k_frac_gather(int stage, const uint32_t* __restrict__ pu_first, int n_pu, const uint32_t* __restrict__ inst_slot,
                               const uint32_t* __restrict__ hval, const uint32_t* __restrict__ udist, uint32_t* __restrict__ dist) {
   const int nc = stage == 0 ? 9 : 8;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = (int)(t / nc), cand = (int)(t - (long long)i * nc);
-  if (i >= n_tiles) return;
+  const int pu = (int)(t / nc), cand = (int)(t - (long long)pu * nc);
+  if (pu >= n_pu) return;
+  const uint32_t a = pu_first[pu], b = pu_first[pu + 1];
+  if (a == b) return;                                  // this PU's tiles are of the other size
   const int ci = stage == 0 ? cand : cand + 1;
-  const uint32_t pu = tiles[i] & 0xffffffu;
-  const uint32_t id = hval[inst_slot[i]];
-  atomicAdd(&dist[(size_t)pu * 9 + ci], udist[(size_t)id * 9 + ci]);
+  uint32_t sum = 0;
+  for (uint32_t i = a; i < b; i++) sum += udist[(size_t)hval[inst_slot[i]] * 9 + ci];
+  dist[(size_t)pu * 9 + ci] = sum;
 }
 
 // ---- 8-bit planes, stages 0 / 1: reference patches staged in shared memory ------------------------------------------
@@ -713,6 +720,7 @@ struct FracSchedule {
   FracUTile* d_utiles[2] = {nullptr, nullptr};
   uint32_t* d_udist[2] = {nullptr, nullptr};
   uint32_t* d_count = nullptr;
+  uint32_t* d_pu_first[2] = {nullptr, nullptr};   // [n_pu + 1] first tile instance of every PU in d_tiles8 / d_tiles4
   uint32_t hmask[2] = {0, 0};
 };
 
@@ -726,6 +734,7 @@ inline void frac_free_schedule(FracSchedule* s) {
     if (s->d_inst[k]) cudaFree(s->d_inst[k]);
     if (s->d_utiles[k]) cudaFree(s->d_utiles[k]);
     if (s->d_udist[k]) cudaFree(s->d_udist[k]);
+    if (s->d_pu_first[k]) cudaFree(s->d_pu_first[k]);
   }
   if (s->d_count) cudaFree(s->d_count);
   *s = FracSchedule();
@@ -753,21 +762,23 @@ inline bool frac_alloc_unique(FracSchedule* fs) {
 inline bool frac_build_schedule(const std::vector<SearchTask>& tasks, cudaStream_t stream, FracSchedule* out, std::string* err) {
   const int n = (int)tasks.size();
   if (n >= (1 << 24)) { if (err) *err = "frac_build_schedule: more than 2^24 PUs in one batch"; return false; }
-  std::vector<uint32_t> t8, t4;
+  std::vector<uint32_t> t8, t4, f8((size_t)n + 1), f4((size_t)n + 1);
   for (int i = 0; i < n; i++) {
     const SearchTask& t = tasks[i];
     const int e = (t.w % 8 == 0 && t.h % 8 == 0) ? 8 : 4;               // xGetHADs tile choice (TComRdCost.cpp:1544-1572)
     std::vector<uint32_t>& dst = (e == 8) ? t8 : t4;
+    f8[(size_t)i] = (uint32_t)t8.size(); f4[(size_t)i] = (uint32_t)t4.size();
     for (int ty = 0; ty < t.h / e; ty++)
       for (int tx = 0; tx < t.w / e; tx++) dst.push_back(frac_pack_tile((uint32_t)i, (uint32_t)tx, (uint32_t)ty));
   }
+  f8[(size_t)n] = (uint32_t)t8.size(); f4[(size_t)n] = (uint32_t)t4.size();
   out->n_pu = n; out->n_tiles8 = (int)t8.size(); out->n_tiles4 = (int)t4.size();
   auto up = [&](uint32_t** d, const std::vector<uint32_t>& h) {
     if (h.empty()) return true;
     if (cudaMalloc((void**)d, h.size() * sizeof(uint32_t)) != cudaSuccess) return false;
     return cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream) == cudaSuccess;
   };
-  bool ok = up(&out->d_tiles8, t8) && up(&out->d_tiles4, t4) &&
+  bool ok = up(&out->d_tiles8, t8) && up(&out->d_tiles4, t4) && (n == 0 || (up(&out->d_pu_first[0], f8) && up(&out->d_pu_first[1], f4))) &&
             (n == 0 || cudaMalloc((void**)&out->d_dist, (size_t)n * 18 * sizeof(uint32_t)) == cudaSuccess) &&
             cudaStreamSynchronize(stream) == cudaSuccess;
   if (!ok) {
@@ -814,7 +825,8 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
     };
     auto unique_end = [&](int k) {
       const int n = k ? fs.n_tiles4 : fs.n_tiles8;
-      k_frac_gather<<<(int)(((long long)n * nc + 255) / 256), 256, 0, stream>>>(stage, k ? fs.d_tiles4 : fs.d_tiles8, n, fs.d_inst[k], fs.d_hval[k], fs.d_udist[k], dist);
+      (void)n;
+      k_frac_gather<<<(int)(((long long)fs.n_pu * nc + 255) / 256), 256, 0, stream>>>(stage, fs.d_pu_first[k], fs.n_pu, fs.d_inst[k], fs.d_hval[k], fs.d_udist[k], dist);
       launches++;
     };
     for (int k = 0; k < 2; k++) {
