@@ -128,8 +128,25 @@ int make_plane(Plane& p, int width, int height, int mx, int my, int bit_depth) {
   p.d.bytes_per_sample = bps; p.d.bit_depth = bit_depth;
   p.bytes = (size_t)pitch_bytes * total_h;
   p.d.base = nullptr;
-  for (size_t i = 0; i < G.pool.size(); i++)
-    if (G.pool[i].bytes == p.bytes) { p.d.base = G.pool[i].base; p.ev_reuse = G.pool[i].ev_free; G.pool.erase(G.pool.begin() + i); break; }
+  // Recycle a released buffer of this size.  A buffer whose last reader has finished is taken at once; one that is still being
+  // read (its event has not fired) would make this plane's upload wait for that kernel - with two planes per frame pair in
+  // circulation every upload would queue behind the previous pair's kernels instead of running next to them - so up to
+  // POOL_KEEP busy buffers of a size are left alone and a new one is allocated instead.
+  static const int POOL_KEEP = getenv("HMB200_POOL_KEEP") ? std::max(1, atoi(getenv("HMB200_POOL_KEEP"))) : 4;
+  int busy = 0, oldest = -1;
+  for (size_t i = 0; i < G.pool.size() && !p.d.base; i++) {
+    if (G.pool[i].bytes != p.bytes) continue;
+    if (!G.pool[i].ev_free || cudaEventQuery(G.pool[i].ev_free) == cudaSuccess) {
+      p.d.base = G.pool[i].base; p.ev_reuse = G.pool[i].ev_free; G.pool.erase(G.pool.begin() + i);
+    } else {
+      if (oldest < 0) oldest = (int)i;
+      busy++;
+    }
+  }
+  cudaGetLastError();                                  // cudaErrorNotReady from the queries is not an error
+  if (!p.d.base && busy >= POOL_KEEP) {
+    p.d.base = G.pool[oldest].base; p.ev_reuse = G.pool[oldest].ev_free; G.pool.erase(G.pool.begin() + oldest);
+  }
   if (!p.d.base) CUDA_TRY(cudaMalloc(&p.d.base, p.bytes));
   p.used = true;
   return HMB200_OK;
@@ -656,6 +673,17 @@ void hmb200_release_plane(int plane_id) {
   Plane* p = get_plane(plane_id);            // also orders a still pending upload of this plane before the compute stream's tail
   if (!p) return;
   if (p->d.base) {
+    if (G.pool.size() >= 16) {
+      // the pool is full: drop the oldest buffer of ANOTHER size (a geometry that is no longer in use would otherwise occupy the
+      // pool for good and turn every release into a synchronise + free, every registration into a malloc)
+      for (size_t i = 0; i < G.pool.size(); i++)
+        if (G.pool[i].bytes != p->bytes) {
+          if (G.pool[i].ev_free) { cudaEventSynchronize(G.pool[i].ev_free); give_event(G.pool[i].ev_free); }
+          cudaFree(G.pool[i].base);
+          G.pool.erase(G.pool.begin() + i);
+          break;
+        }
+    }
     if (G.pool.size() < 16) {
       // no host synchronisation: the buffer goes back to the pool with an event behind the last kernel that may read it
       // (side streams are joined into the compute stream before a run ends); whoever reuses it on the upload stream waits on it
