@@ -1253,9 +1253,9 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
     const bool had = (p->flags & HMB200_FLAG_HADME) != 0;
     int nl;
     if (pc->d.bytes_per_sample == 1 && pr->d.bytes_per_sample == 1)
-      nl = frac_launch<uint8_t, uint8_t>(p->frac, p->d_tasks, p->d_results, pc->d, pr->d, had, G.stream);
+      nl = frac_launch<uint8_t, uint8_t>(p->frac, p->d_tasks, p->d_results, pc->d, pr->d, had, G.stream, G.side[0], G.ev_fork, G.ev_join[0]);
     else if (pc->d.bytes_per_sample == 2 && pr->d.bytes_per_sample == 2)
-      nl = frac_launch<int16_t, int16_t>(p->frac, p->d_tasks, p->d_results, pc->d, pr->d, had, G.stream);
+      nl = frac_launch<int16_t, int16_t>(p->frac, p->d_tasks, p->d_results, pc->d, pr->d, had, G.stream, G.side[0], G.ev_fork, G.ev_join[0]);
     else { dispatch_generic(p->d_tasks, p->d_results, p->n, pc->d, pr->d, p->flags, /*do_search=*/false, nullptr); nl = 0; }
     if (nl < 0) return fail(HMB200_ERR_CUDA, std::string("frac_launch: ") + cudaGetErrorString(cudaGetLastError()));
     G.launches += (uint64_t)nl;

@@ -791,7 +791,8 @@ inline bool frac_build_schedule(const std::vector<SearchTask>& tasks, cudaStream
 // Enqueues the whole refinement on `stream`; returns the number of kernel launches, or -1 on a launch error.
 template <typename RefT, typename OrgT>
 inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200_pu_result* d_results, const DevPlane& cur,
-                       const DevPlane& ref, bool use_had, cudaStream_t stream) {
+                       const DevPlane& ref, bool use_had, cudaStream_t stream, cudaStream_t side = nullptr, cudaEvent_t ev_fork = nullptr,
+                       cudaEvent_t ev_join = nullptr) {
   if (fs.n_pu == 0) return 0;
   int launches = 0;
   // unique-tile keys hold 14-bit coordinates (-4096 .. 12287): larger planes keep one SATD per tile instance
@@ -813,12 +814,17 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
     const bool unique = !no_unique && plane_fits_i16 && frac_alloc_unique(const_cast<FracSchedule*>(&fs));
     if (unique && stage == 0 && cudaMemsetAsync(fs.d_count, 0, 4 * sizeof(uint32_t), stream) != cudaSuccess) return -1;
     // unique-tile pass of one tile size (k = 0: 8x8 tiles, 1: 4x4): keys + descriptors before the SATD kernel, gather after it
+    // The 8x8-tile and the 4x4-tile pipelines of a stage are independent (disjoint PUs, own hash tables) and each is a chain of
+    // small kernels: with a side stream they run next to each other and meet again in front of the argmin.
+    const bool two = side && ev_fork && ev_join && fs.n_tiles8 > 0 && fs.n_tiles4 > 0 && !getenv("HMB200_FRAC_ONE_STREAM");
+    if (two && (cudaEventRecord(ev_fork, stream) != cudaSuccess || cudaStreamWaitEvent(side, ev_fork, 0) != cudaSuccess)) return -1;
+    cudaStream_t st_k = stream;
     auto unique_begin = [&](int k) -> bool {
       const int n = k ? fs.n_tiles4 : fs.n_tiles8;
-      if (cudaMemsetAsync(fs.d_hkeys[k], 0xff, ((size_t)fs.hmask[k] + 1) * sizeof(unsigned long long), stream) != cudaSuccess) return false;
-      if (k == 0) k_frac_unique<8><<<(n + 255) / 256, 256, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles8, n, fs.d_hkeys[0], fs.hmask[0], fs.d_hval[0],
+      if (cudaMemsetAsync(fs.d_hkeys[k], 0xff, ((size_t)fs.hmask[k] + 1) * sizeof(unsigned long long), st_k) != cudaSuccess) return false;
+      if (k == 0) k_frac_unique<8><<<(n + 255) / 256, 256, 0, st_k>>>(stage, d_tasks, d_results, fs.d_tiles8, n, fs.d_hkeys[0], fs.hmask[0], fs.d_hval[0],
                                                                        fs.d_count + 2 * stage, fs.d_utiles[0], fs.d_inst[0]);
-      else        k_frac_unique<4><<<(n + 255) / 256, 256, 0, stream>>>(stage, d_tasks, d_results, fs.d_tiles4, n, fs.d_hkeys[1], fs.hmask[1], fs.d_hval[1],
+      else        k_frac_unique<4><<<(n + 255) / 256, 256, 0, st_k>>>(stage, d_tasks, d_results, fs.d_tiles4, n, fs.d_hkeys[1], fs.hmask[1], fs.d_hval[1],
                                                                        fs.d_count + 2 * stage + 1, fs.d_utiles[1], fs.d_inst[1]);
       launches++;
       return true;
@@ -826,12 +832,13 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
     auto unique_end = [&](int k) {
       const int n = k ? fs.n_tiles4 : fs.n_tiles8;
       (void)n;
-      k_frac_gather<<<(int)(((long long)fs.n_pu * nc + 255) / 256), 256, 0, stream>>>(stage, fs.d_pu_first[k], fs.n_pu, fs.d_inst[k], fs.d_hval[k], fs.d_udist[k], dist);
+      k_frac_gather<<<(int)(((long long)fs.n_pu * nc + 255) / 256), 256, 0, st_k>>>(stage, fs.d_pu_first[k], fs.n_pu, fs.d_inst[k], fs.d_hval[k], fs.d_udist[k], dist);
       launches++;
     };
     for (int k = 0; k < 2; k++) {
       const int n = k ? fs.n_tiles4 : fs.n_tiles8;
       if (n == 0) continue;
+      st_k = (k == 1 && two) ? side : stream;
       const uint32_t* d_tl = k ? fs.d_tiles4 : fs.d_tiles8;
       const FracUTile* ut = nullptr; const uint32_t* cnt = nullptr; uint32_t* out = dist;
       if (unique) {
@@ -841,27 +848,28 @@ inline int frac_launch(const FracSchedule& fs, const SearchTask* d_tasks, hmb200
       if constexpr (PATCH) {
         const int nb = (n + tpc - 1) / tpc;
         if (k == 0) {
-          if (!use_had)      k_frac_patch<8, false><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
-          else if (old_path) k_frac_patch<8, true><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
-          else               k_frac_hv<8, true><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          if (!use_had)      k_frac_patch<8, false><<<nb, FRAC_TILE_THREADS, 0, st_k>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          else if (old_path) k_frac_patch<8, true><<<nb, FRAC_TILE_THREADS, 0, st_k>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          else               k_frac_hv<8, true><<<nb, FRAC_TILE_THREADS, 0, st_k>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
         } else {
-          if (!use_had)      k_frac_patch<4, false><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
-          else if (!hv4)     k_frac_patch<4, true><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
-          else               k_frac_hv<4, true><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          if (!use_had)      k_frac_patch<4, false><<<nb, FRAC_TILE_THREADS, 0, st_k>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          else if (!hv4)     k_frac_patch<4, true><<<nb, FRAC_TILE_THREADS, 0, st_k>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          else               k_frac_hv<4, true><<<nb, FRAC_TILE_THREADS, 0, st_k>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
         }
       } else {
         const int nb = blocks(n);
         if (k == 0) {
-          if (use_had) k_frac_tiles<RefT, OrgT, 8, true><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
-          else         k_frac_tiles<RefT, OrgT, 8, false><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          if (use_had) k_frac_tiles<RefT, OrgT, 8, true><<<nb, FRAC_TILE_THREADS, 0, st_k>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          else         k_frac_tiles<RefT, OrgT, 8, false><<<nb, FRAC_TILE_THREADS, 0, st_k>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
         } else {
-          if (use_had) k_frac_tiles<RefT, OrgT, 4, true><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
-          else         k_frac_tiles<RefT, OrgT, 4, false><<<nb, FRAC_TILE_THREADS, 0, stream>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          if (use_had) k_frac_tiles<RefT, OrgT, 4, true><<<nb, FRAC_TILE_THREADS, 0, st_k>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
+          else         k_frac_tiles<RefT, OrgT, 4, false><<<nb, FRAC_TILE_THREADS, 0, st_k>>>(stage, d_tasks, d_results, d_tl, n, out, cur, ref, ut, cnt);
         }
       }
       launches++;
       if (unique) unique_end(k);
     }
+    if (two && (cudaEventRecord(ev_join, side) != cudaSuccess || cudaStreamWaitEvent(stream, ev_join, 0) != cudaSuccess)) return -1;
     const int nb = (fs.n_pu + 255) / 256;
     if (stage == 0) k_frac_argmin<0><<<nb, 256, 0, stream>>>(d_tasks, d_results, dist0, dist1, fs.n_pu, ref.bit_depth);
     else            k_frac_argmin<1><<<nb, 256, 0, stream>>>(d_tasks, d_results, dist1, nullptr, fs.n_pu, ref.bit_depth);
