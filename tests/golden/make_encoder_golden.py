@@ -111,7 +111,48 @@ def golden_ra10(fast_search=0):
     print(out)
 
 
+TILE_ARGS = ["--TileUniformSpacing=1", "--NumTileColumnsMinus1=1"]      # two uniformly spaced tile columns (TAppEncCfg.cpp:905-906)
+
+
+TILE_W, TILE_H = 576, 240           # 9 CTUs wide: two uniform tile columns of 4 and 5 CTUs (a tile must be at least 256 luma samples wide)
+
+
+def tile_args(args):
+    """The untiled command line at 576x240 with two tile columns."""
+    args = list(args)
+    args[args.index("-wdt") + 1] = str(TILE_W)
+    args[args.index("-hgt") + 1] = str(TILE_H)
+    return args + TILE_ARGS
+
+
+def write_clip_tiles(path, frames, bit_depth=8):
+    synth.write_yuv420(path, [synth.luma_frame(TILE_W, TILE_H, t, seed=77, bit_depth=bit_depth) for t in range(frames)], bit_depth)
+
+
+def golden_tiles():
+    """Tiles enabled (BASELINE.json configs[3]'s sharding unit, in-encoder): two uniform tile columns.  Tiles restrict MV prediction
+    and merge candidates across the column boundary, not the search window, so the routed calls see other predictors and windows
+    than the untiled runs.  lowdelay-P 8-bit full search (3 frames) and random-access Main10 with the file's TZ search (one GOP)."""
+    out = {}
+    yuv, binf = "/tmp/hmgold_tiles.yuv", "/tmp/hmgold_tiles.bin"
+    write_clip_tiles(yuv, 3)
+    t0 = time.time()
+    p = subprocess.run([ENC] + tile_args(encoder_args(CFG, yuv, 3, binf)), capture_output=True, text=True, check=True)
+    out["lowdelay8"] = {"bitstream_md5": hashlib.md5(open(binf, "rb").read()).hexdigest(), "picture_md5": parse_md5_lines(p.stdout),
+                        "cpu_seconds": round(time.time() - t0, 1), "frames": 3, "yuv_md5": hashlib.md5(open(yuv, "rb").read()).hexdigest()}
+    print(out["lowdelay8"], flush=True)
+    write_clip_tiles(yuv, RA10_TZ_FRAMES, 10)
+    t0 = time.time()
+    p = subprocess.run([ENC] + tile_args(args_ra10(CFG_RA10, yuv, RA10_TZ_FRAMES, binf, 1)), capture_output=True, text=True, check=True)
+    out["ra10_tz"] = {"bitstream_md5": hashlib.md5(open(binf, "rb").read()).hexdigest(), "picture_md5": parse_md5_lines(p.stdout),
+                      "cpu_seconds": round(time.time() - t0, 1), "frames": RA10_TZ_FRAMES, "yuv_md5": hashlib.md5(open(yuv, "rb").read()).hexdigest()}
+    print(out["ra10_tz"], flush=True)
+    json.dump(out, open(os.path.join(ROOT, "tests", "golden", "encoder_md5_tiles.json"), "w"), indent=1)
+
+
 def main():
+    if "--tiles" in sys.argv:
+        return golden_tiles()
     if "--1080p" in sys.argv:
         return golden_1080p()
     if "--ra10" in sys.argv:

@@ -183,3 +183,30 @@ def test_distortion_table_hook_in_encoder(tmp_path, cfg_kind):
     if gold is not None:
         assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
         assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg_kind", ["lowdelay8", "ra10_tz"])
+def test_encoder_bitstream_md5_with_tile_columns(tmp_path, cfg_kind):
+    """Two uniformly spaced tile columns (TileUniformSpacing / NumTileColumnsMinus1, App/TAppEncoder/TAppEncCfg.cpp:905-906 - the
+    sharding unit of BASELINE.json configs[3]) in the routed encoder: predictors, merge candidates and therefore windows differ
+    from the untiled runs along the column boundary; searches, refinements and merge estimation go through libhmb200 and the
+    bitstream equals the stock encoder's with the same options (tests/golden/encoder_md5_tiles.json)."""
+    _need_binary()
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "encoder_md5_tiles.json")))[cfg_kind]
+    yuv, binf = str(tmp_path / "clip.yuv"), str(tmp_path / "out.bin")
+    if cfg_kind == "lowdelay8":
+        meg.write_clip_tiles(yuv, gold["frames"])
+        args = meg.encoder_args(CFG, yuv, gold["frames"], binf)
+    else:
+        if not os.path.exists(CFG_RA10):
+            pytest.skip("integration/_build/randomaccess_main10_settings.cfg not written")
+        meg.write_clip_tiles(yuv, gold["frames"], 10)
+        args = meg.args_ra10(CFG_RA10, yuv, gold["frames"], binf, fast_search=1)
+    assert hashlib.md5(open(yuv, "rb").read()).hexdigest() == gold["yuv_md5"]
+    p = subprocess.run([BIN] + meg.tile_args(args), capture_output=True, text=True,
+                       env=dict(os.environ, HMB200_SHIM="gpu", HMB200_SHIM_MERGE="1"), timeout=3000)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "integer searches" in p.stderr and " 0 integer searches" not in p.stderr
+    assert [list(x) for x in meg.parse_md5_lines(p.stdout)] == [list(x) for x in gold["picture_md5"]]
+    assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]
