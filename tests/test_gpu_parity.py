@@ -718,3 +718,48 @@ def test_tile_column_shards_with_halo_crops_equal_unsharded(hm, bd, sr, n_cols):
     assert uploaded < n_cols * W                       # the crops are smaller than whole planes per rank
     assert fused == work_whole["pus_fused"] > 0.9 * len(full)      # a crop keeps every CU on the CU-fused kernels
     assert len(set(zip(whole["mv_x"].tolist(), whole["mv_y"].tolist()))) >= 2
+
+
+@pytest.mark.parametrize("bd,fen,sr", [(10, 1, 64), (10, 0, 64), (12, 1, 128)])
+def test_child_fold_16bit_equals_separate_kernels(hm, monkeypatch, bd, fen, sr):
+    """16-bit planes: a 16x16 CU's pass also yields its four 8x8 children (child minima kept in shared memory).  Same MV field
+    as with the separate 8x8-CU kernel (knob HMB200_NO_CHILD_FOLD16), whole canonical list and a thinned one (missing partitions /
+    children), flat content for the raster-order tie-break; sampled PUs against the oracle."""
+    W, H = 320, 192
+    margin = 80 if sr <= 64 else 144
+    lam = 51000
+    full = hm.build_canonical_jobs(W, H, sr, lam)
+    rng = np.random.default_rng(7 + bd + fen)
+    thin = full[np.sort(rng.choice(len(full), len(full) // 2, replace=False))]
+    flat = np.full((H, W), 300, dtype=np.uint16)
+    cases = [("full", synth.luma_frame(W, H, 1, seed=19, bit_depth=bd), synth.luma_frame(W, H, 0, seed=19, bit_depth=bd), full),
+             ("thin", synth.luma_frame(W, H, 2, seed=19, bit_depth=bd), synth.luma_frame(W, H, 0, seed=19, bit_depth=bd), thin),
+             ("flat", flat, flat, hm.build_canonical_jobs(W, H, sr, 0, ctu_first=6, ctu_count=1))]
+
+    def run(f1, f0, jobs):
+        idc = hm.register_plane_u16(np.ascontiguousarray(f1), bd, margin, margin, kind=0)
+        idr = hm.register_plane_u16(np.ascontiguousarray(f0), bd, margin, margin, kind=1)
+        try:
+            prep = hm.prepare_jobs(jobs, flags_of(fen, 1, frac=False), bd)
+            prep.run(idc, idr)
+            out, work = prep.fetch(), prep.work()
+            prep.free()
+            return out, work
+        finally:
+            hm.release_plane(idc)
+            hm.release_plane(idr)
+
+    for name, f1, f0, jobs in cases:
+        fused, work = run(f1, f0, jobs)
+        monkeypatch.setenv("HMB200_NO_CHILD_FOLD16", "1")
+        plain, work2 = run(f1, f0, jobs)
+        monkeypatch.delenv("HMB200_NO_CHILD_FOLD16")
+        assert work["abs_diffs_executed"] < work2["abs_diffs_executed"], name
+        assert results_equal(fused, plain, ("mv_x", "mv_y", "sad")) == [], name
+        pick = np.sort(rng.choice(len(jobs), 100, replace=False))
+        cur, o0, stride = padded(f1, margin)
+        ref, _, _ = padded(f0, margin)
+        exp, _ = Oracle(fen=fen, hadme=1).run_jobs((cur, o0, stride), (ref, o0, stride), jobs[pick], bd, False)
+        assert results_equal(fused[pick], exp, ("mv_x", "mv_y", "sad")) == [], name
+        if name == "flat":
+            assert np.array_equal(fused["mv_x"], jobs["lt_x"]) and np.array_equal(fused["mv_y"], jobs["lt_y"])

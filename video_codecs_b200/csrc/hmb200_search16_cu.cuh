@@ -146,6 +146,23 @@ __device__ __forceinline__ void cu16_org_sums(const uint8_t* orgp, int org_pitch
   }
 }
 
+// CHILD tiles (a 16x16 CU that carries its 8x8 children): per-cell sums of the rows the even-row pass visits (every row without
+// FEN) in dst[r*4 + c], of the odd rows (FEN) in dst[16 + r*4 + c]
+template <bool PARITY>
+__device__ __forceinline__ void cu16_org_sums_child(const uint8_t* orgp, int org_pitch, int lane, uint32_t* dst) {
+  const bool odd = lane >= 16;
+  const int r = (lane & 15) >> 2, c = lane & 3;
+  uint32_t a = 0;
+  if (!odd || PARITY) {
+    for (int rr = odd ? 1 : 0; rr < 4; rr += PARITY ? 2 : 1) {
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(orgp + (r * 4 + rr) * org_pitch) + c * 2;
+      a = (uint32_t)__dp2a_lo((int)row[0], 0x0101, (int)a);
+      a = (uint32_t)__dp2a_lo((int)row[1], 0x0101, (int)a);
+    }
+  }
+  dst[lane] = a;
+}
+
 // key of one PU: ((sum << ss) >> shr) scaled into the cost field
 // (16-bit planes have bit depth >= 9, so shr >= 1 >= ss and the two shifts are one: sums are below 2^31)
 __device__ __forceinline__ void cu16_min(uint32_t& best, uint32_t sum, int ss, int shr, uint32_t base) {
@@ -179,10 +196,14 @@ __device__ __forceinline__ void cu16_epilogue(const uint32_t (&E)[4][4][4], cons
   cu16_min(best[12], ec[3], ss, shr, base);
 }
 
-template <int S, bool FEN, bool A8>
+// CHILD (S == 16): the CU's pass also yields the PUs of its four 8x8 child CUs, as in k_search8_cu.  33 running minima do not fit
+// next to the sum-of-minima accumulators, so the 20 child minima live in shared memory, one word per thread and PU: a tile folds
+// its four candidate columns first and touches each word once.
+template <int S, bool FEN, bool A8, bool CHILD = false>
 __global__ void __launch_bounds__(S8_THREADS, 2)
 k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bundles, unsigned long long* __restrict__ keys,
               DevPlane cur_plane, DevPlane ref_plane) {
+  static_assert(!CHILD || S == 16, "only 16x16 CUs carry child CUs");
   constexpr int NSLOT = (S == 8) ? 5 : CU_SLOTS;
   constexpr int KY = cu16_ky(S);
   constexpr int WW = S / 2;                            // 32-bit words per CU row
@@ -193,7 +214,8 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
   extern __shared__ __align__(128) uint8_t s8_smem[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ S8Bundle s_bd[S8_WARPS];
-  __shared__ uint32_t s_asum[S8_WARPS][20];
+  __shared__ uint32_t s_asum[S8_WARPS][CHILD ? 32 : 20];
+  __shared__ uint32_t s_cbest[CHILD ? CU_CHILD_SLOTS : 1][CHILD ? S8_THREADS : 1];
 
   const S8Unit un = units[blockIdx.x];
   uint8_t* s_ref = s8_smem;
@@ -229,8 +251,11 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
   auto load_bundle = [&]() {
     __syncwarp();
     reinterpret_cast<int32_t*>(&bd)[lane] = reinterpret_cast<const int32_t*>(&bundles[bslot])[lane];
+    if constexpr (CHILD) reinterpret_cast<int32_t*>(&bd)[lane + 32] = reinterpret_cast<const int32_t*>(&bundles[bslot])[lane + 32];
     __syncwarp();
-    if constexpr (S >= 16) {
+    if constexpr (CHILD) {
+      cu16_org_sums_child<PARITY>(s_org + bd.org_off, un.org_pitch, lane, s_asum[warp]);
+    } else if constexpr (S >= 16) {
       cu16_org_sums<S, PARITY>(s_org + bd.org_off, un.org_pitch, lane, s_asum[warp]);
     } else if (lane < 4) {                              // 8x8 CU: four 4x4 quadrants
       uint32_t a = 0;
@@ -249,27 +274,36 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
   uint32_t best[CU_SLOTS];
 #pragma unroll
   for (int s = 0; s < CU_SLOTS; s++) best[s] = 0xffffffffu;
+  volatile uint32_t* cbest = &s_cbest[0][CHILD ? threadIdx.x : 0];      // this thread's child minima: cbest[slot * S8_THREADS]
+  if constexpr (CHILD) {
+#pragma unroll
+    for (int s = 0; s < CU_CHILD_SLOTS; s++) cbest[s * S8_THREADS] = 0xffffffffu;
+  }
   int first_item = un.item_first + warp;
+  auto flush_one = [&](uint32_t v, int out) {
+    unsigned long long b = ~0ull;
+    if (v != 0xffffffffu) {
+      const uint32_t local = v & ((1u << CU_LOCAL_BITS) - 1u);
+      const int it = first_item + (int)(local >> LK) * S8_WARPS;
+      const int q = (it - bd.item_start) * 16 + (lane >> 1);
+      const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
+      const int w = (int)(local & ((1u << LK) - 1u));
+      const int cyi = bd.cy_first + g * KY + (w >> 2), cxi = (A8 ? blk * 8 : min(blk * 8, bd.nx - 8)) + (lane & 1) + 2 * (w & 3);
+      b = make_key(v >> CU_LOCAL_BITS, (uint32_t)(cyi * bd.nx + cxi));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
+      b = other < b ? other : b;
+    }
+    if (lane == 0 && b != ~0ull && out >= 0) atomicMin(&keys[out], b);
+  };
   auto flush = [&]() {
 #pragma unroll
-    for (int s = 0; s < NSLOT; s++) {
-      unsigned long long b = ~0ull;
-      if (best[s] != 0xffffffffu) {
-        const uint32_t local = best[s] & ((1u << CU_LOCAL_BITS) - 1u);
-        const int it = first_item + (int)(local >> LK) * S8_WARPS;
-        const int q = (it - bd.item_start) * 16 + (lane >> 1);
-        const int g = q / bd.n_blk, blk = q - g * bd.n_blk;
-        const int w = (int)(local & ((1u << LK) - 1u));
-        const int cyi = bd.cy_first + g * KY + (w >> 2), cxi = (A8 ? blk * 8 : min(blk * 8, bd.nx - 8)) + (lane & 1) + 2 * (w & 3);
-        b = make_key(best[s] >> CU_LOCAL_BITS, (uint32_t)(cyi * bd.nx + cxi));
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
-        b = other < b ? other : b;
-      }
-      if (lane == 0 && b != ~0ull && bd.out_idx[s] >= 0) atomicMin(&keys[bd.out_idx[s]], b);
-      best[s] = 0xffffffffu;
+    for (int s = 0; s < NSLOT; s++) { flush_one(best[s], bd.out_idx[s]); best[s] = 0xffffffffu; }
+    if constexpr (CHILD) {
+#pragma unroll 1
+      for (int s = 0; s < CU_CHILD_SLOTS; s++) { flush_one(cbest[s * S8_THREADS], bd.child_idx[s]); cbest[s * S8_THREADS] = 0xffffffffu; }
     }
   };
 
@@ -374,6 +408,119 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
             }
           }
         }
+      } else if constexpr (CHILD) {
+        // two halves of two 4-row strips; per strip the per-cell SADs of the even rows (every row without FEN) and of the odd rows
+        const uint32_t* asum = s_asum[warp];
+        const bool row_ok = cyl0 < bd.ny;
+        const uint32_t py = bd.lambda * eg_bits(((bd.lt_y + bd.cy_first + cyl0) << 2) - bd.pred_y);
+        uint32_t base[4];
+        bool valid[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          base[k] = (((px[k] + py) >> 16) << CU_LOCAL_BITS) | tile_local | (uint32_t)k;
+          valid[k] = row_ok && (!A8 || cxi0 + 2 * k < bd.nx);
+        }
+        constexpr int ss = FEN ? 1 : 0;
+        // all candidate columns of one child PU -> its minimum in shared memory
+        auto child_min = [&](int slot, const uint32_t (&sum)[4]) {
+          uint32_t m = 0xffffffffu;
+#pragma unroll
+          for (int k = 0; k < 4; k++) if (valid[k]) m = min(m, ((sum[k] >> shr) << CU_LOCAL_BITS) + base[k]);
+          cbest[slot * S8_THREADS] = min(cbest[slot * S8_THREADS], m);
+        };
+        auto own_min = [&](int slot, const uint32_t (&sum)[4], int sub) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) if (valid[k]) cu16_min(best[slot], sum[k], sub, shr, base[k]);
+        };
+        uint32_t ec[4][4], P[4], P1[4], T0[4][4], all0[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { P[k] = 0; P1[k] = 0; all0[k] = 0;
+#pragma unroll
+          for (int c = 0; c < 4; c++) { ec[c][k] = 0; T0[c][k] = 0; } }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          uint32_t Tc[4][4], er[4], alls[4];
+          {
+            uint32_t Ec[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+              for (int k = 0; k < 4; k++) Ec[c][k] = 0;
+            cu16_strip_min<8, 4, FEN ? 2 : 4, false, A8>(refp, un.ref_pitch, orgp, un.org_pitch, r * 4, FEN ? 2 : 1, sh, Ec, asum + r * 4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              er[k] = (Ec[0][k] + Ec[1][k]) + (Ec[2][k] + Ec[3][k]);
+#pragma unroll
+              for (int c = 0; c < 4; c++) { ec[c][k] += Ec[c][k]; Tc[c][k] = Ec[c][k]; }
+            }
+          }
+          if constexpr (FEN) {
+            uint32_t Oc[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+              for (int k = 0; k < 4; k++) Oc[c][k] = 0;
+            cu16_strip_min<8, 4, 2, false, A8>(refp, un.ref_pitch, orgp, un.org_pitch, r * 4 + 1, 2, sh, Oc, asum + 16 + r * 4);
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+              for (int k = 0; k < 4; k++) Tc[c][k] += Oc[c][k];
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) { alls[k] = (Tc[0][k] + Tc[1][k]) + (Tc[2][k] + Tc[3][k]); P[k] += er[k]; }
+          if (r == 0) { own_min(5, alls, 0);                                  // 2NxnU top: 16x4, every row
+#pragma unroll
+            for (int k = 0; k < 4; k++) P1[k] = P[k]; }
+          if (r == 2) {                                                       // 2NxnD top: rows 0..11 (sub-sampled under FEN)
+            own_min(7, P, ss);
+          }
+          if (r == 3) own_min(8, alls, 0);                                    // 2NxnD bottom: 16x4, every row
+          if ((r & 1) == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { all0[k] = alls[k];
+#pragma unroll
+              for (int c = 0; c < 4; c++) T0[c][k] = Tc[c][k]; }
+          } else {
+            const int h = r >> 1;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              uint32_t s88[4], top[4], bot[4], lft[4], rgt[4];
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                top[k] = T0[2 * j][k] + T0[2 * j + 1][k]; bot[k] = Tc[2 * j][k] + Tc[2 * j + 1][k];
+                lft[k] = T0[2 * j][k] + Tc[2 * j][k];     rgt[k] = T0[2 * j + 1][k] + Tc[2 * j + 1][k];
+                s88[k] = top[k] + bot[k];
+              }
+              const int cs = 5 * (2 * h + j);
+              child_min(cs + 0, s88); child_min(cs + 1, top); child_min(cs + 2, bot); child_min(cs + 3, lft); child_min(cs + 4, rgt);
+            }
+            uint32_t half[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) half[k] = all0[k] + alls[k];
+            own_min(h == 0 ? 1 : 2, half, 0);                                 // 2NxN: 16x8, every row
+          }
+        }
+        {
+          uint32_t t[4];
+          own_min(0, P, ss);
+#pragma unroll
+          for (int k = 0; k < 4; k++) t[k] = ec[0][k] + ec[1][k];
+          own_min(3, t, ss);
+#pragma unroll
+          for (int k = 0; k < 4; k++) t[k] = ec[2][k] + ec[3][k];
+          own_min(4, t, ss);
+#pragma unroll
+          for (int k = 0; k < 4; k++) t[k] = P[k] - P1[k];
+          own_min(6, t, ss);
+          own_min(9, ec[0], ss);
+#pragma unroll
+          for (int k = 0; k < 4; k++) t[k] = ec[1][k] + ec[2][k] + ec[3][k];
+          own_min(10, t, ss);
+#pragma unroll
+          for (int k = 0; k < 4; k++) t[k] = ec[0][k] + ec[1][k] + ec[2][k];
+          own_min(11, t, ss);
+          own_min(12, ec[3], ss);
+        }
       } else {
         uint32_t E[4][4][4], O[4][4];
 #pragma unroll
@@ -414,15 +561,19 @@ k_search16_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bun
   flush();
 }
 
-// variants 0..6 as cu_variant(); 7..13 = the same with A8 (64-bit loads, masked last block) for units whose windows are 8-byte aligned
-constexpr int CUV16_COUNT = 2 * CUV_BASE_COUNT;
+// variants 0..6 as cu_variant(); 7..13 = the same with A8 (64-bit loads, masked last block) for units whose windows are 8-byte aligned;
+// 14..17 = 16x16 CUs that carry their 8x8 children: 14 + FEN + 2 * A8
+constexpr int CUV16_CHILD = 2 * CUV_BASE_COUNT;
+constexpr int CUV16_COUNT = CUV16_CHILD + 4;
 typedef void (*S16CuKernel)(const S8Unit*, const S8Bundle*, unsigned long long*, DevPlane, DevPlane);
 inline const S16CuKernel* search16_cu_kernels() {
   static const S16CuKernel table[CUV16_COUNT] = {
       k_search16_cu<8, false, false>, k_search16_cu<16, false, false>, k_search16_cu<16, true, false>, k_search16_cu<32, false, false>,
       k_search16_cu<32, true, false>, k_search16_cu<64, false, false>, k_search16_cu<64, true, false>,
       k_search16_cu<8, false, true>, k_search16_cu<16, false, true>, k_search16_cu<16, true, true>, k_search16_cu<32, false, true>,
-      k_search16_cu<32, true, true>, k_search16_cu<64, false, true>, k_search16_cu<64, true, true> };
+      k_search16_cu<32, true, true>, k_search16_cu<64, false, true>, k_search16_cu<64, true, true>,
+      k_search16_cu<16, false, false, true>, k_search16_cu<16, true, false, true>, k_search16_cu<16, false, true, true>,
+      k_search16_cu<16, true, true, true> };
   return table;
 }
 inline int cu16_configure(std::string* err) {

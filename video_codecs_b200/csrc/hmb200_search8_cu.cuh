@@ -698,7 +698,8 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
 // ---------------------------------------------------------------------------------------------------------------
 // CUV_16C_*: 16x16 CUs that carry their four 8x8 child CUs (8-bit planes only; the 16-bit tables end at CUV_BASE_COUNT)
 enum : int { CUV_8 = 0, CUV_16_F0, CUV_16_F1, CUV_32_F0, CUV_32_F1, CUV_64_F0, CUV_64_F1, CUV_BASE_COUNT, CUV_16C_F0 = CUV_BASE_COUNT, CUV_16C_F1, CUV_COUNT };
-constexpr int CUV_MAX = 2 * CUV_BASE_COUNT;      // schedule tables: 16-bit planes number their aligned variants 7..13 (hmb200_search16_cu.cuh)
+constexpr int CUV_MAX = 2 * CUV_BASE_COUNT + 4;  // schedule tables: 16-bit planes number their aligned variants 7..13 and their child variants 14..17 (hmb200_search16_cu.cuh)
+constexpr int CU16_CHILD_STATIC_SMEM = 24 * 1024;  // k_search16_cu<16,.,.,CHILD>: 20 KB of per-thread child minima + descriptors (two CTAs per SM must still fit)
 typedef void (*S8CuKernel)(const S8Unit*, const S8Bundle*, unsigned long long*, DevPlane, DevPlane);
 inline const S8CuKernel* search8_cu_kernels() {
   static const S8CuKernel table[CUV_COUNT] = { k_search8_cu<8, false, false>, k_search8_cu<16, false, false>, k_search8_cu<16, true, false>,
@@ -843,7 +844,7 @@ inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, int bps, st
   // 8-bit planes: a 16x16 CU takes the PUs of its four 8x8 child CUs along when they share its window (as displacements),
   // predictor and lambda - the child SADs are sums of the 4x4 cells the 16x16 pass computes anyway (hmb200 CHILD kernels).
   std::vector<char> absorbed(out.size(), 0);
-  if (bps == 1 && !getenv("HMB200_NO_CHILD_FOLD")) {
+  if (!getenv("HMB200_NO_CHILD_FOLD") && (bps == 1 || !getenv("HMB200_NO_CHILD_FOLD16"))) {
     for (size_t i = 0; i < out.size(); i++) {
       if (out[i].S != 16) continue;
       for (int c = 0; c < 4; c++) {
@@ -867,8 +868,10 @@ inline void cu_extract_bundles(const std::vector<SearchTask>& tasks, int bps, st
 inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::vector<CuBundleHost>& hb, int bps, int bit_depth,
                               int sm_count, cudaStream_t stream, CuSchedule* out, std::string* err) {
   if (hb.empty()) return true;
-  const CuGeom GM = cu_geom(bps);
+  CuGeom GM = cu_geom(bps);
   out->bps = bps;
+  if (bps == 2)                                       // the child kernels keep 23 KB of static shared memory; two CTAs per SM must still fit
+    for (const CuBundleHost& b : hb) if (b.child) { GM.smem_group -= CU16_CHILD_STATIC_SMEM; break; }
   // entity = a bundle, or a horizontal slice of its window when the whole window does not let two CTAs share an SM
   struct Ent { int b, cy_first, ny; S8Box rb, ob; bool two; };
   std::vector<Ent> ents;
@@ -915,21 +918,24 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     groups.push_back(Group{(int)p, 1, ents[p].rb, ents[p].ob, ents[p].two});
   }
   // 8-bit planes: variants 0..8 (7, 8 = 16x16 CUs with children); 16-bit planes: 0..6 and 7..13 = the same with aligned 64-bit loads
-  const int S_of_variant[CUV_MAX] = {8, 16, 16, 32, 32, 64, 64, bps == 1 ? 16 : 8, 16, 16, 32, 32, 64, 64};
-  const bool F_of_variant[CUV_MAX] = {false, false, true, false, true, false, true, bps == 1 ? false : false, bps == 1 ? true : false, true, false, true, false, true};
+  const int S_of_variant[CUV_MAX] = {8, 16, 16, 32, 32, 64, 64, bps == 1 ? 16 : 8, 16, 16, 32, 32, 64, 64, 16, 16, 16, 16};
+  const bool F_of_variant[CUV_MAX] = {false, false, true, false, true, false, true, bps == 1 ? false : false, bps == 1 ? true : false, true, false, true, false, true,
+                                      false, true, false, true};
   const bool use_a8 = bps == 2 && !getenv("HMB200_NO_LDS64");
   // 16-bit planes: the unit can read its window rows with 64-bit loads when candidate column 0 sits on an 8-byte boundary of the
   // staged window (whose origin is 16-sample aligned): (cu_x + lt_x) % 4 == 0
   auto variant_of = [&](const CuBundleHost& b, const SearchTask& t) {
-    int v = cu_variant(b.S, b.fen, b.child);
-    if (use_a8 && ((b.cu_x + t.lt_x) & 3) == 0) v += CUV_BASE_COUNT;
-    return v;
+    if (bps == 1) return cu_variant(b.S, b.fen, b.child);
+    const bool a8 = use_a8 && ((b.cu_x + t.lt_x) & 3) == 0;
+    if (b.child) return 2 * CUV_BASE_COUNT + (b.fen ? 1 : 0) + (a8 ? 2 : 0);
+    return cu_variant(b.S, b.fen, false) + (a8 ? CUV_BASE_COUNT : 0);
   };
+  auto variant_is_child = [&](int v) { return bps == 1 ? v >= CUV_BASE_COUNT : v >= 2 * CUV_BASE_COUNT; };
   auto rows_visited = [](int S, bool fen) { return (fen && S >= 16) ? (S == 16 ? 16 : S == 32 ? 24 : 32) : S; };
   auto item_cost = [&](int S, bool fen, bool child = false) -> long long {
     return (long long)GM.ky(S) * (rows_visited(S, fen) * (S / 4) * (bps == 1 ? 1 : 6) + (child ? 100 : 40));
   };
-  auto vcost = [&](int v) { return item_cost(S_of_variant[v], F_of_variant[v], bps == 1 && v >= CUV_BASE_COUNT); };
+  auto vcost = [&](int v) { return item_cost(S_of_variant[v], F_of_variant[v], variant_is_child(v)) * (bps == 2 && variant_is_child(v) ? 2 : 1); };
   const bool use_edge = bps == 1 && !getenv("HMB200_NO_EDGE_ITEMS");
   std::vector<S8Bundle> bundles; bundles.reserve(ents.size());
   std::vector<int> bvar; bvar.reserve(ents.size());
