@@ -496,7 +496,7 @@ def measure_pairs(env, wl_key, steps, warmup, shard="frames", search="full", pre
             p.fetch_wait()
 
     e2e_steps = max(4, min(steps, 30))
-    for k in range(2):
+    for k in range(max(4, warmup)):                                  # the plane pool reaches its steady size (HMB200_POOL_KEEP + 2 buffers)
         e2e_step(k)
     e2e_drain()
     env.barrier()

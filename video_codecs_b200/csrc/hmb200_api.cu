@@ -213,6 +213,27 @@ void launch_generic(const SearchTask* d_tasks, hmb200_pu_result* d_res, int n, c
   }
 }
 
+// 2-D tensor map over a padded 8-bit plane (rows of `pitch` bytes) with a box of box_w bytes x box_h rows, no swizzle, zero fill
+// outside: what k_search8_cu's tensor-map staging loads (cp.async.bulk.tensor.2d).  cuTensorMapEncodeTiled is a driver entry
+// point; it is resolved through the runtime so that the library does not link libcuda itself.
+bool encode_plane_map(const DevPlane& d, int box_w, int box_h, CUtensorMap* out) {
+  typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Encode encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return false;
+    encode = reinterpret_cast<Encode>(fn);
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)d.pitch, (cuuint64_t)(d.height + 2 * d.margin_y)};
+  const cuuint64_t gstride[1] = {(cuuint64_t)d.pitch};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d.base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 void dispatch_generic(const SearchTask* d_tasks, hmb200_pu_result* d_res, int n, const DevPlane& cur, const DevPlane& ref,
                       int flags, bool do_search, cudaEvent_t mid) {
   if (n <= 0) { if (mid) cudaEventRecord(mid, G.stream); return; }
@@ -1216,7 +1237,6 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
     CUDA_TRY(cudaMemsetAsync(sc.d_keys, 0xff, (size_t)sc.n_tasks * sizeof(unsigned long long), G.stream));
     // one launch per tile variant present, spread over side streams so that their tails overlap
     const S8Kernel* kern = search8_kernels();
-    const S8CuKernel* cukern = bps == 1 ? search8_cu_kernels() : search16_cu_kernels();
     CUDA_TRY(cudaEventRecord(G.ev_fork, G.stream));
     int order[S8V_COUNT + CUV_MAX], used = 0;       // >= 0: per-PU variant, < 0: CU-fused variant ~v
     if (bps == 1) {                                   // longest CTAs first: 16x16 CUs with their children, then 8x8 CUs
@@ -1230,8 +1250,16 @@ int hmb200_run_prepared(hmb200_prepared* p, int cur_plane, int ref_plane) {
       if (k >= 1 && k <= N_SIDE) CUDA_TRY(cudaStreamWaitEvent(st, G.ev_fork, 0));
       if (v >= 0)
         kern[v]<<<sc.unit_count[v], S8_THREADS, sc.smem_of[v], st>>>(sc.d_units + sc.unit_first[v], sc.d_jobs, sc.d_keys, pc->d, pr->d);
-      else
-        cukern[~v]<<<cu.unit_count[~v], bps == 1 ? CU8_THREADS : S8_THREADS, cu.smem_of[~v], st>>>(cu.d_units + cu.unit_first[~v], cu.d_bundles, sc.d_keys, pc->d, pr->d);
+      else if (bps == 1) {
+        // the variant's common window geometry goes through a tensor map of the reference plane (the other units stage row by row)
+        CUtensorMap map;
+        memset(&map, 0, sizeof(map));
+        if (cu.tma_w[~v] > 0 && !encode_plane_map(pr->d, cu.tma_w[~v], cu.tma_h[~v], &map))
+          return fail(HMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the reference plane");
+        search8_cu_kernels()[~v]<<<cu.unit_count[~v], CU8_THREADS, cu.smem_of[~v], st>>>(cu.d_units + cu.unit_first[~v], cu.d_bundles, sc.d_keys,
+                                                                                      pc->d, pr->d, map);
+      } else
+        search16_cu_kernels()[~v]<<<cu.unit_count[~v], S8_THREADS, cu.smem_of[~v], st>>>(cu.d_units + cu.unit_first[~v], cu.d_bundles, sc.d_keys, pc->d, pr->d);
       G.launches++;
     }
     for (int k = 0; k < N_SIDE && k + 1 < used; k++) {

@@ -90,6 +90,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// one 2-D box of a tensor map (cuTensorMapEncodeTiled on the host) into shared memory; SASS: UTMALDG.  dst is 128-byte aligned; x
+// (the coordinate of the contiguous dimension) times the element size must be a multiple of 16 - otherwise the instruction
+// traps as illegal (tools/tma_probe.cu); elements outside the tensor read as 0.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // SAD tiles.  refp: word-aligned address at or below the lane's first candidate (row 0 of the tile); sh: bit shift
 // (8 * byte misalignment); rows advance by ref_step / org_step bytes (pitch << ss).  acc[jy][k]: candidate row jy

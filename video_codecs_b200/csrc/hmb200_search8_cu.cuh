@@ -399,7 +399,7 @@ __device__ __forceinline__ void cu16_child_tile(uint32_t refp, uint32_t orgp, ui
 template <int S, bool FEN, bool CHILD>
 __global__ void __launch_bounds__(CU8_THREADS, 1)
 k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bundles, unsigned long long* __restrict__ keys,
-             DevPlane cur_plane, DevPlane ref_plane) {
+             DevPlane cur_plane, DevPlane ref_plane, const __grid_constant__ CUtensorMap ref_map) {
   typedef CuTraits<S, FEN> T;
   static_assert(!CHILD || S == 16, "only 16x16 CUs carry child CUs");
   constexpr int NSLOT = (S == 8) ? 5 : CHILD ? CU_SLOTS_ALL : CU_SLOTS;
@@ -415,17 +415,23 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   uint8_t* s_org = s8_smem + un.org_smem_off;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  // every thread issues the bulk copies of its rows (one warp alone serialises ~250 UBLKCP issues: ncu showed a
-  // fifth of the stall samples on the mbarrier spin); thread 0 arms the transaction count first
+  const bool use_map = (un.variant & 0x100) != 0;       // host: this unit's window has the geometry the launch's tensor map was built for
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();                                      // the initialised barrier is visible before its first use
   if (threadIdx.x == 0) mbar_expect_tx(&s_bar, (uint32_t)(un.ref_pitch * un.ref_rows + un.org_pitch * un.org_rows));
   __syncthreads();                                      // ... and armed before any copy can complete on it
   {
-    const uint8_t* gref = reinterpret_cast<const uint8_t*>(ref_plane.base) +
-                          (size_t)(un.ref_by + ref_plane.margin_y) * ref_plane.pitch + (un.ref_bx + ref_plane.margin_x);
-    for (int r = threadIdx.x; r < un.ref_rows; r += CU8_THREADS)
-      bulk_g2s(s_ref + r * un.ref_pitch, gref + (size_t)r * ref_plane.pitch, (uint32_t)un.ref_pitch, &s_bar);
+    if (use_map) {
+      // tensor-map TMA (SASS UTMALDG): the whole window is one 2-D box of the reference plane
+      if (threadIdx.x == 0) tma_load_2d(s_ref, &ref_map, un.ref_bx + ref_plane.margin_x, un.ref_by + ref_plane.margin_y, &s_bar);
+    } else {
+      // every thread issues the bulk copies of its rows (one warp alone serialises ~250 UBLKCP issues: ncu showed a
+      // fifth of the stall samples on the mbarrier spin)
+      const uint8_t* gref = reinterpret_cast<const uint8_t*>(ref_plane.base) +
+                            (size_t)(un.ref_by + ref_plane.margin_y) * ref_plane.pitch + (un.ref_bx + ref_plane.margin_x);
+      for (int r = threadIdx.x; r < un.ref_rows; r += CU8_THREADS)
+        bulk_g2s(s_ref + r * un.ref_pitch, gref + (size_t)r * ref_plane.pitch, (uint32_t)un.ref_pitch, &s_bar);
+    }
     const uint8_t* gorg = reinterpret_cast<const uint8_t*>(cur_plane.base) +
                           (size_t)(un.org_by + cur_plane.margin_y) * cur_plane.pitch + (un.org_bx + cur_plane.margin_x);
     for (int r = (int)threadIdx.x - 256; r < un.org_rows; r += CU8_THREADS)
@@ -433,7 +439,8 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   }
   mbar_wait(&s_bar, 0);
   {
-    // copies 1..3: the window shifted left by 1..3 bytes (the word past the last row belongs to the slack rows)
+    // copies 1..3: the window shifted left by 1..3 bytes (the word past the last row belongs to the slack rows).  These cannot be
+    // loaded: bulk and tensor copies start on 16-byte boundaries of global memory.
     const int nvec = (un.ref_pitch * un.ref_rows) >> 4;
     const int cs = un.copy_stride;
     for (int i = threadIdx.x; i < nvec; i += CU8_THREADS) {
@@ -700,7 +707,7 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
 enum : int { CUV_8 = 0, CUV_16_F0, CUV_16_F1, CUV_32_F0, CUV_32_F1, CUV_64_F0, CUV_64_F1, CUV_BASE_COUNT, CUV_16C_F0 = CUV_BASE_COUNT, CUV_16C_F1, CUV_COUNT };
 constexpr int CUV_MAX = 2 * CUV_BASE_COUNT + 4;  // schedule tables: 16-bit planes number their aligned variants 7..13 and their child variants 14..17 (hmb200_search16_cu.cuh)
 constexpr int CU16_CHILD_STATIC_SMEM = 24 * 1024;  // k_search16_cu<16,.,.,CHILD>: 20 KB of per-thread child minima + descriptors (two CTAs per SM must still fit)
-typedef void (*S8CuKernel)(const S8Unit*, const S8Bundle*, unsigned long long*, DevPlane, DevPlane);
+typedef void (*S8CuKernel)(const S8Unit*, const S8Bundle*, unsigned long long*, DevPlane, DevPlane, const CUtensorMap);
 inline const S8CuKernel* search8_cu_kernels() {
   static const S8CuKernel table[CUV_COUNT] = { k_search8_cu<8, false, false>, k_search8_cu<16, false, false>, k_search8_cu<16, true, false>,
                                                k_search8_cu<32, false, false>, k_search8_cu<32, true, false>, k_search8_cu<64, false, false>,
@@ -721,6 +728,9 @@ struct CuSchedule {
   S8Unit* d_units = nullptr;
   S8Bundle* d_bundles = nullptr;
   int unit_first[CUV_MAX] = {0}, unit_count[CUV_MAX] = {0}, smem_of[CUV_MAX] = {0};
+  // 8-bit planes: the units of a variant whose window has the variant's most common geometry are staged through a tensor map
+  // (box tma_w bytes x tma_h rows); tma_units of the variant's units take that path (0: none)
+  int tma_w[CUV_MAX] = {0}, tma_h[CUV_MAX] = {0}, tma_units[CUV_MAX] = {0};
   S8Box rbox{0, 0, 0, 0}, obox{0, 0, 0, 0};
 };
 
@@ -1039,6 +1049,25 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     const int v = units[i].variant;
     if (out->unit_count[v]++ == 0) out->unit_first[v] = (int)i;
     out->smem_of[v] = std::max(out->smem_of[v], units[i].smem_need);
+  }
+  if (bps == 1 && !getenv("HMB200_NO_TENSOR_MAP")) {
+    // Most common window geometry per variant -> that window is staged by ONE tensor-map load (box = pitch x rows, both <= 256)
+    // instead of one bulk copy per row; flag 0x100 in the unit's variant word (read by the kernel only).  Only the unshifted copy
+    // can come from the TMA unit: a box must start on a 16-byte boundary of the global row (tools/tma_probe.cu).
+    for (int v = 0; v < CUV_COUNT; v++) {
+      std::map<std::pair<int, int>, int> freq;
+      for (int i = out->unit_first[v]; i < out->unit_first[v] + out->unit_count[v]; i++) {
+        const S8Unit& u = units[(size_t)i];
+        if (u.ref_pitch <= 256 && u.ref_rows <= 256) freq[std::make_pair(u.ref_pitch, u.ref_rows)]++;
+      }
+      std::pair<int, int> best(0, 0); int n = 0;
+      for (auto& kv : freq) if (kv.second > n) { n = kv.second; best = kv.first; }
+      if (n == 0) continue;
+      out->tma_w[v] = best.first; out->tma_h[v] = best.second; out->tma_units[v] = n;
+      if (getenv("HMB200_DEBUG_TMA")) fprintf(stderr, "[hmb200] variant %d: %d of %d units staged by a %d x %d tensor-map box\n", v, n, out->unit_count[v], best.first, best.second);
+      for (int i = out->unit_first[v]; i < out->unit_first[v] + out->unit_count[v]; i++)
+        if (units[(size_t)i].ref_pitch == best.first && units[(size_t)i].ref_rows == best.second) units[(size_t)i].variant |= 0x100;
+    }
   }
   out->n_units = (int)units.size(); out->n_bundles = (int)bundles.size();
   out->rbox = S8Box{s8_fl(all_r.x0), all_r.y0, s8_ce(all_r.x1), all_r.y1};
