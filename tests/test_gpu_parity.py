@@ -303,6 +303,56 @@ def test_pattern_search_and_frac_one_to_one(hm, bd):
         hm.release_plane(idr)
 
 
+@pytest.mark.parametrize("bd", [8, 10])
+def test_one_pu_kernels_every_size_full_window(hm, bd):
+    """The 1:1 entries' own kernels (hmb200_one.cuh: a CTA per candidate row, byte-SIMD when pattern and plane are 8-bit, the
+    last CTA decodes; refinement with a thread per tile column; result reported through mapped host memory): every PU size,
+    +-64 windows at every byte alignment, FEN on / off, Hadamard and SAD refinement, a pattern that leaves the sample range
+    (scalar path on an 8-bit plane), the fused search + refinement entry, and flat content (the first candidate in raster
+    order must win) - against the oracle."""
+    W, H = 416, 240
+    f0 = synth.luma_frame(W, H, 0, seed=52, bit_depth=bd)
+    f1 = synth.luma_frame(W, H, 1, seed=52, bit_depth=bd)
+    ref, o0, stride = padded(f0)
+    rng = np.random.default_rng(19 + bd)
+    idr = hm.register_plane(ref, W, H, MARGIN, MARGIN, bd)
+    try:
+        for i, (w, h) in enumerate(PU_SIZES):
+            fen, had = i & 1, (i >> 1) & 1
+            O = Oracle(fen=fen, hadme=had)
+            px, py = int(rng.integers(8, (W - w - 8) // 4)) * 4, int(rng.integers(4, (H - h - 8) // 4)) * 4
+            org = np.ascontiguousarray(f1[py:py + h, px:px + w].astype(np.int16))
+            if i % 5 == 4:
+                org = (2 * org - rng.integers(0, 1 << bd, size=org.shape)).astype(np.int16)
+            pred = (int(rng.integers(-40, 41)), int(rng.integers(-40, 41)))
+            lam = int(rng.integers(100000, 6000000))
+            roff = o0 + py * stride + px
+            # +-64 around the integer predictor, clipped so that window + refinement stay inside the padded plane
+            cx, cy = pred[0] >> 2, pred[1] >> 2
+            lt = (max(cx - 64, -px - MARGIN + 8 + i % 4), max(cy - 64, -py - MARGIN + 8))
+            rb = (min(cx + 64, W - px - w + MARGIN - 8), min(cy + 64, H - py - h + MARGIN - 8))
+            flags = (FLAG_FEN if fen else 0) | (FLAG_HADME if had else 0)
+            mv, sad = hm.pattern_search((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred, bd, flags)
+            assert (mv, sad) == O.pattern_search((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred, bd), (w, h)
+            exp = O.pattern_search_frac((org, 0, w), w, h, (ref, roff, stride), mv, lam, pred, bd)
+            assert hm.pattern_search_frac((org, 0, w), w, h, (ref, roff, stride), mv, lam, pred, bd, flags) == exp, (w, h)
+            both = hm.pattern_search_and_refine((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred, bd, flags)
+            assert both == (mv, sad) + exp, (w, h)
+        # flat content: every candidate has the same SAD; with lambda 0 the first one in raster order wins
+        flat = np.full((H, W), 77, dtype=np.uint16 if bd > 8 else np.uint8)
+        pf, _, _ = padded(flat)
+        idf = hm.register_plane(pf, W, H, MARGIN, MARGIN, bd)
+        try:
+            org = np.full((16, 16), 70, dtype=np.int16)
+            roff = o0 + 96 * stride + 160
+            mv, sad = hm.pattern_search((org, 0, 16), 16, 16, (pf, roff, stride), (-61, -64), (64, 63), 0, (0, 0), bd, FLAG_FEN)
+            assert (mv, sad) == ((-61, -64), (7 * 256) >> (bd - 8))
+        finally:
+            hm.release_plane(idf)
+    finally:
+        hm.release_plane(idr)
+
+
 def test_error_behaviour(hm):
     from video_codecs_b200 import HMB200Error
     with pytest.raises(HMB200Error):
@@ -555,6 +605,26 @@ def test_child_fold_and_edge_items_equal_separate_kernels(hm, monkeypatch, fen):
             assert np.array_equal(fused["mv_x"], jobs["lt_x"]) and np.array_equal(fused["mv_y"], jobs["lt_y"])
         if name == "edgewin":
             assert np.all(fused["mv_x"] == 64) and np.all(fused["mv_y"] == 0)
+
+
+def test_tensor_map_window_load_equals_row_copies(hm, monkeypatch):
+    """The 8-bit CU kernels stage the most common window geometry of a launch with one tensor-map load (UTMALDG) and every
+    other window with one bulk copy per row (knob off: all windows).  Same MV field either way - on a picture whose right /
+    bottom CTUs have clipped (smaller) windows, so that both paths run in the same launch - and equal to the oracle."""
+    W, H = 416, 240
+    lam = int(np.floor(65536.0 * np.sqrt(0.4624 * 2 ** ((35 - 12) / 3.0))))
+    jobs = hm.build_canonical_jobs(W, H, 64, lam)
+    f1, f0 = synth.luma_frame(W, H, 1, seed=21), synth.luma_frame(W, H, 0, seed=21)
+    mapped, _ = _run_full(hm, f1, f0, jobs, flags_of(1, 1, frac=False))
+    monkeypatch.setenv("HMB200_NO_TENSOR_MAP", "1")
+    rows, _ = _run_full(hm, f1, f0, jobs, flags_of(1, 1, frac=False))
+    monkeypatch.delenv("HMB200_NO_TENSOR_MAP")
+    assert results_equal(mapped, rows, ("mv_x", "mv_y", "sad")) == []
+    pick = np.sort(np.random.default_rng(3).choice(len(jobs), 150, replace=False))
+    cur, o0, stride = padded(f1)
+    ref, _, _ = padded(f0)
+    exp, _ = Oracle(fen=1, hadme=1).run_jobs((cur, o0, stride), (ref, o0, stride), jobs[pick], 8, False)
+    assert results_equal(mapped[pick], exp, ("mv_x", "mv_y", "sad")) == []
 
 
 def test_refinement_on_unique_tiles_equals_per_instance_refinement(hm, monkeypatch):

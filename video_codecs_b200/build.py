@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libhmb200.so")
 SRC = [os.path.join(HERE, "csrc", "hmb200_api.cu")]
 DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in
-              ("hmb200_device.cuh", "hmb200_generic.cuh", "hmb200_search8.cuh", "hmb200_search8_cu.cuh", "hmb200_search16_cu.cuh", "hmb200_frac.cuh", "hmb200_tz.cuh", "hmb200_intra.cuh", "hmb200_mc_cand.cuh")] + \
+              ("hmb200_device.cuh", "hmb200_generic.cuh", "hmb200_search8.cuh", "hmb200_search8_cu.cuh", "hmb200_search16_cu.cuh", "hmb200_frac.cuh", "hmb200_tz.cuh", "hmb200_intra.cuh", "hmb200_mc_cand.cuh", "hmb200_one.cuh")] + \
        [os.path.join(HERE, "..", "include", "hmb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "--expt-relaxed-constexpr"]

@@ -21,6 +21,8 @@
 #include "hmb200_frac.cuh"
 #include "hmb200_tz.cuh"
 #include "hmb200_mc_cand.cuh"
+#include "hmb200_one.cuh"
+#include <atomic>
 
 using namespace hmb200;
 
@@ -42,7 +44,9 @@ struct PoolBuf { size_t bytes; void* base; cudaEvent_t ev_free; };   // ev_free:
 
 constexpr int N_SIDE = 4;
 // layout of the per-call record of the 1:1 entries (host page-locked copy and device copy): offsets in bytes
-constexpr size_t ONE_KEY = 0, ONE_RESULT = 16, ONE_TASK = 64, ONE_TZ = 128, ONE_HEAD = 256;
+constexpr size_t ONE_KEY = 0, ONE_TICKET = 8, ONE_RESULT = 16, ONE_TASK = 64, ONE_TZ = 128, ONE_HEAD = 256;
+// the record the call's last kernel writes into mapped host memory (State::one_back): result, then the call's sequence number
+constexpr size_t BACK_RESULT = 0, BACK_FLAG = 64, BACK_BYTES = 128;
 
 struct State {
   bool ready = false;
@@ -62,6 +66,9 @@ struct State {
   Plane pattern;                                       // 64x64 int16 pattern buffer for the 1:1 entries (inside one_dev)
   // 1:1 entries: ONE page-locked record up (argmin key | result | task | TZ extra | pattern rows) and one result down per call
   char* one_host = nullptr; char* one_dev = nullptr;
+  char* one_back = nullptr;                            // mapped page-locked: the call's last kernel stores result + sequence number here
+  uint32_t one_seq = 0;
+  bool one_fast = true;                                // hmb200_one.cuh kernels + flag spin (HMB200_NO_ONE_FAST=1: round-1 path)
   std::vector<PoolBuf> pool;                           // released plane buffers, recycled by size (no malloc/free per frame)
   uint64_t launches = 0;
   float last_total_ms = 0, last_search_ms = 0, last_frac_ms = 0;
@@ -301,7 +308,8 @@ static void teardown_state(State& st) {
   if (st.upstage) { cudaFree(st.upstage); st.upstage = nullptr; st.upstage_bytes = 0; }
   if (st.one_dev) cudaFree(st.one_dev);
   if (st.one_host) cudaFreeHost(st.one_host);
-  st.one_dev = st.one_host = nullptr;
+  if (st.one_back) cudaFreeHost(st.one_back);
+  st.one_dev = st.one_host = st.one_back = nullptr;
   st.pattern = Plane();
   if (st.pinned) cudaFreeHost(st.pinned);
   if (st.dstage) cudaFree(st.dstage);
@@ -346,6 +354,13 @@ static int init_state_body(State& st, int device) {
   st.pattern = Plane();
   CUDA_TRY(cudaMalloc((void**)&st.one_dev, ONE_HEAD + 64 * 64 * sizeof(int16_t)));
   CUDA_TRY(cudaMallocHost((void**)&st.one_host, ONE_HEAD + 64 * 64 * sizeof(int16_t)));
+  CUDA_TRY(cudaHostAlloc((void**)&st.one_back, BACK_BYTES, cudaHostAllocMapped));
+  memset(st.one_back, 0, BACK_BYTES);
+  st.one_seq = 0;
+  st.one_fast = getenv("HMB200_NO_ONE_FAST") == nullptr;
+  CUDA_TRY(cudaFuncSetAttribute(k_one_search<true, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_search<false, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_search<false, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
   st.pattern.used = true;
   st.pattern.d.base = st.one_dev + ONE_HEAD; st.pattern.d.pitch = 64; st.pattern.d.width = 64; st.pattern.d.height = 64;
   st.pattern.d.margin_x = 0; st.pattern.d.margin_y = 0; st.pattern.d.bytes_per_sample = 2; st.pattern.d.bit_depth = 16;
@@ -1403,26 +1418,73 @@ int hmb200_me_ctu_row(int cur_plane, int ref_plane, int ctu_row, int max_cu, con
 // ------------------------------------------------------------------------------------------------------------------
 // 1:1 entries (per call, synchronous): exact inside the real encoder where predictors arrive one PU at a time
 // ------------------------------------------------------------------------------------------------------------------
-// Fills the host record: pattern rows (pitch 64 samples), task, result seed, argmin key; one H2D copy brings it to the device.
-static int stage_one_call(const hmb200_pattern* key, const SearchTask& t, const hmb200_pu_result& io, const hmb200_tz_extra* tz) {
+// Fills the host record: pattern rows (dense: pitch = PU width), task, result seed, argmin key, ticket; one H2D copy brings it to
+// the device.  *fits_u8: every pattern sample is in 0..255 (not the case for the 2*org - pred pattern of bi-prediction).
+static int stage_one_call(const hmb200_pattern* key, const SearchTask& t, const hmb200_pu_result& io, const hmb200_tz_extra* tz, bool* fits_u8) {
   if (!key || !key->roi || !supported_pu(key->width, key->height)) return fail(HMB200_ERR_ARG, "unsupported pattern");
   char* h = G.one_host;
   *reinterpret_cast<unsigned long long*>(h + ONE_KEY) = ~0ull;
+  *reinterpret_cast<unsigned long long*>(h + ONE_TICKET) = 0;
   memcpy(h + ONE_RESULT, &io, sizeof(io));
   memcpy(h + ONE_TASK, &t, sizeof(t));
   if (tz) memcpy(h + ONE_TZ, tz, sizeof(*tz));
   int16_t* rows = reinterpret_cast<int16_t*>(h + ONE_HEAD);
-  for (int y = 0; y < key->height; y++)
-    memcpy(rows + (size_t)y * 64, key->roi + (ptrdiff_t)y * key->stride, (size_t)key->width * sizeof(int16_t));
-  CUDA_TRY(cudaMemcpyAsync(G.one_dev, h, ONE_HEAD + (size_t)key->height * 64 * sizeof(int16_t), cudaMemcpyHostToDevice, G.stream));
+  int all = 0;
+  for (int y = 0; y < key->height; y++) {
+    const int16_t* src = key->roi + (ptrdiff_t)y * key->stride;
+    int16_t* dst = rows + (size_t)y * key->width;
+    for (int x = 0; x < key->width; x++) { dst[x] = src[x]; all |= src[x]; }
+  }
+  if (fits_u8) *fits_u8 = (all & ~0xff) == 0;
+  CUDA_TRY(cudaMemcpyAsync(G.one_dev, h, ONE_HEAD + (size_t)key->height * key->width * sizeof(int16_t), cudaMemcpyHostToDevice, G.stream));
   return HMB200_OK;
 }
+// the pattern buffer as the plane the round-1 kernels read their "original" from
+static DevPlane pattern_plane(int width) { DevPlane d = G.pattern.d; d.pitch = width; return d; }
 static int finish_one_call(hmb200_pu_result* io) {
   CUDA_TRY(cudaMemcpyAsync(G.one_host + ONE_RESULT, G.one_dev + ONE_RESULT, sizeof(*io), cudaMemcpyDeviceToHost, G.stream));
   CUDA_TRY(cudaStreamSynchronize(G.stream));
   CUDA_TRY(cudaGetLastError());
   memcpy(io, G.one_host + ONE_RESULT, sizeof(*io));
   return HMB200_OK;
+}
+// The call's last kernel stores the result and then this call's sequence number in mapped host memory (OneBack); the host spins
+// on the number instead of paying a D2H copy and a stream synchronisation (7 us of a 16 us round trip, profiles/r02_latency_1to1.txt).
+static OneBack next_one_back() {
+  G.one_seq++;
+  if (G.one_seq == 0) G.one_seq = 1;
+  return OneBack{reinterpret_cast<hmb200_pu_result*>(G.one_back + BACK_RESULT), reinterpret_cast<uint32_t*>(G.one_back + BACK_FLAG), G.one_seq};
+}
+static int wait_one_back(const OneBack& back, hmb200_pu_result* io) {
+  CUDA_TRY(cudaGetLastError());                                   // a failed launch would never report
+  volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(G.one_back + BACK_FLAG);
+  for (uint64_t spins = 1; *flag != back.seq; spins++) {
+    if ((spins & 0x3fff) == 0) {                                  // every ~16k polls: has the stream failed or finished without reporting?
+      const cudaError_t e = cudaStreamQuery(G.stream);
+      if (e == cudaSuccess) { if (*flag != back.seq) return fail(HMB200_ERR_CUDA, "1:1 call: the stream finished without reporting a result"); break; }
+      if (e != cudaErrorNotReady) return fail(HMB200_ERR_CUDA, std::string("1:1 call: ") + cudaGetErrorString(e));
+    }
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  memcpy(io, G.one_back + BACK_RESULT, sizeof(*io));
+  return HMB200_OK;
+}
+// k_one_frac launch: a thread per column of every (candidate, tile) of a stage, capped at one full CTA
+static void launch_one_frac(const hmb200_pattern* key, const SearchTask& t, const hmb200_pu_result& seed, bool mv_from_device,
+                            const DevPlane& ref, int flags, const OneBack& back) {
+  const int had = (flags & HMB200_FLAG_HADME) ? 1 : 0;
+  const int n = !had ? 4 : ((key->width % 8 == 0 && key->height % 8 == 0) ? 8 : 4);
+  const int want = 9 * (key->width / n) * (key->height / n) * n;
+  const int threads = std::min(ONE_FRAC_THREADS_MAX, std::max(128, (want + 31) & ~31));
+  const int smem = one_frac_smem(key->width, key->height);
+  hmb200_pu_result* d_r = reinterpret_cast<hmb200_pu_result*>(G.one_dev + ONE_RESULT);
+  const int16_t* d_pat = reinterpret_cast<const int16_t*>(G.one_dev + ONE_HEAD);
+  if (ref.bytes_per_sample == 1) k_one_frac<uint8_t><<<1, threads, smem, G.stream>>>(t, seed, mv_from_device ? 1 : 0, d_r, d_pat, ref, had, back);
+  else                           k_one_frac<int16_t><<<1, threads, smem, G.stream>>>(t, seed, mv_from_device ? 1 : 0, d_r, d_pat, ref, had, back);
+  G.launches++;
 }
 
 static int run_single(const hmb200_pattern* key, const int16_t* ref_at_pu, const SearchTask& proto, int flags, bool do_search,
@@ -1440,22 +1502,59 @@ static int run_single(const hmb200_pattern* key, const int16_t* ref_at_pu, const
                             : Box{rx + io->mv_x - reach, ry + io->mv_y - reach, rx + io->mv_x + t.w + reach, ry + io->mv_y + t.h + reach};
     if (!box_inside(pr->d, b)) return fail(HMB200_ERR_ARG, "the search window / refinement block leaves the padded reference plane");
   }
-  int rc = stage_one_call(key, t, *io, nullptr);
+  bool fits_u8 = false;
+  int rc = stage_one_call(key, t, *io, nullptr, &fits_u8);
   if (rc != HMB200_OK) return rc;
   SearchTask* d_t = reinterpret_cast<SearchTask*>(G.one_dev + ONE_TASK);
   hmb200_pu_result* d_r = reinterpret_cast<hmb200_pu_result*>(G.one_dev + ONE_RESULT);
   unsigned long long* d_key = reinterpret_cast<unsigned long long*>(G.one_dev + ONE_KEY);
+  const bool r8 = pr->d.bytes_per_sample == 1;
+  const bool frac = (flags & HMB200_FLAG_FRAC) != 0;
+  if (G.one_fast) {
+    // hmb200_one.cuh: a CTA per candidate row, the last one decodes; refinement with a thread per tile column; result by flag
+    const OneBack back = next_one_back(), none{nullptr, nullptr, 0};
+    const int16_t* d_pat = reinterpret_cast<const int16_t*>(G.one_dev + ONE_HEAD);
+    bool searched = !do_search, fused = false;
+    if (do_search) {
+      const int nx = t.rb_x - t.lt_x + 1, ny = t.rb_y - t.lt_y + 1, rows = t.h >> t.sub_shift;
+      const int col0 = rx + pr->d.margin_x + t.lt_x;
+      const bool bytes = r8 && fits_u8 && pr->d.bit_depth == 8;
+      fused = frac && t.w * t.h <= ONE_FUSE_MAX_SAMPLES;           // small PU: the search's last CTA refines, one launch per call
+      const int smem = std::max(one_search_smem(bytes, col0, nx, t.w, rows), fused ? one_frac_smem(t.w, t.h) : 0);
+      if (smem <= ONE_SMEM_MAX) {
+        uint32_t* d_ticket = reinterpret_cast<uint32_t*>(G.one_dev + ONE_TICKET);
+        const OneBack& b = (frac && !fused) ? none : back;
+        const int fuse = fused ? (ONE_FUSE_FRAC | ((flags & HMB200_FLAG_HADME) ? ONE_FUSE_HAD : 0)) : 0;
+        int threads = ONE_SEARCH_THREADS;
+        if (fused) {                                               // enough threads for one pass over the refinement's tile columns
+          const int n = !(flags & HMB200_FLAG_HADME) ? 4 : ((t.w % 8 == 0 && t.h % 8 == 0) ? 8 : 4);
+          threads = std::min(ONE_SEARCH_THREADS_MAX, std::max(threads, (9 * (t.w / n) * (t.h / n) * n + 31) & ~31));
+        }
+        if (bytes)    k_one_search<true, uint8_t><<<ny, threads, smem, G.stream>>>(t, *io, d_key, d_ticket, d_r, d_pat, pr->d, fuse, b);
+        else if (r8)  k_one_search<false, uint8_t><<<ny, threads, smem, G.stream>>>(t, *io, d_key, d_ticket, d_r, d_pat, pr->d, fuse, b);
+        else          k_one_search<false, int16_t><<<ny, threads, smem, G.stream>>>(t, *io, d_key, d_ticket, d_r, d_pat, pr->d, fuse, b);
+        G.launches++;
+        searched = true;
+      }
+    }
+    if (searched) {
+      if (frac && !fused) launch_one_frac(key, t, *io, do_search, pr->d, flags, back);
+      return wait_one_back(back, io);
+    }
+    // a window too large for shared memory: the round-1 kernels below
+  }
+  const DevPlane pat = pattern_plane(key->width);
   if (do_search) {
     // one PU: spread its candidates over the whole GPU (one CTA per ~256 candidates), fold with atomicMin, decode
     const long long total = (long long)(t.rb_x - t.lt_x + 1) * (t.rb_y - t.lt_y + 1);
     const int splits = (int)std::max<long long>(1, std::min<long long>(4 * G.sm_count, (total + 255) / 256));
     const dim3 grid(1, splits);
-    if (pr->d.bytes_per_sample == 1) k_search_split<uint8_t, int16_t><<<grid, 256, 0, G.stream>>>(d_t, d_key, G.pattern.d, pr->d);
-    else                             k_search_split<int16_t, int16_t><<<grid, 256, 0, G.stream>>>(d_t, d_key, G.pattern.d, pr->d);
+    if (r8) k_search_split<uint8_t, int16_t><<<grid, 256, 0, G.stream>>>(d_t, d_key, pat, pr->d);
+    else    k_search_split<int16_t, int16_t><<<grid, 256, 0, G.stream>>>(d_t, d_key, pat, pr->d);
     k_search8_finalize<<<1, 32, 0, G.stream>>>(d_t, d_key, d_r, 1);
     G.launches += 2;
   }
-  dispatch_generic(d_t, d_r, 1, G.pattern.d, pr->d, flags, /*do_search=*/false, nullptr);
+  dispatch_generic(d_t, d_r, 1, pat, pr->d, flags, /*do_search=*/false, nullptr);
   return finish_one_call(io);
 }
 
@@ -1517,17 +1616,30 @@ static int tz_single(const hmb200_pattern* key, const int16_t* ref_at_pu, hmb200
   t.sub_shift = ((flags & HMB200_FLAG_FEN) && key->height > 8) ? 1 : 0;
   get_plane((int)(pr - &G.planes[0]));
   hmb200_pu_result r{};
-  int rc = stage_one_call(key, t, r, extra);
+  int rc = stage_one_call(key, t, r, extra, nullptr);
   if (rc != HMB200_OK) return rc;
+  const DevPlane pat = pattern_plane(key->width);
   const TzParams P{pic_w, pic_h, max_cu, search_range, (flags & HMB200_FLAG_TZ_STOP) ? 1 : 0};
   const SearchTask* d_t = reinterpret_cast<const SearchTask*>(G.one_dev + ONE_TASK);
   const hmb200_tz_extra* d_e = reinterpret_cast<const hmb200_tz_extra*>(G.one_dev + ONE_TZ);
   hmb200_pu_result* d_r = reinterpret_cast<hmb200_pu_result*>(G.one_dev + ONE_RESULT);
-  if (pr->d.bytes_per_sample == 1) k_tz_search<uint8_t, int16_t><<<1, TZ_WARPS * 32, 0, G.stream>>>(d_t, d_e, d_r, 1, G.pattern.d, pr->d, P);
-  else                             k_tz_search<int16_t, int16_t><<<1, TZ_WARPS * 32, 0, G.stream>>>(d_t, d_e, d_r, 1, G.pattern.d, pr->d, P);
+  if (pr->d.bytes_per_sample == 1) k_tz_search<uint8_t, int16_t><<<1, TZ_WARPS * 32, 0, G.stream>>>(d_t, d_e, d_r, 1, pat, pr->d, P);
+  else                             k_tz_search<int16_t, int16_t><<<1, TZ_WARPS * 32, 0, G.stream>>>(d_t, d_e, d_r, 1, pat, pr->d, P);
   G.launches++;
+  if (G.one_fast) {
+    const OneBack back = next_one_back();
+    if (flags & HMB200_FLAG_FRAC) {                    // xPatternSearchFracDIF on the MV just found, same round trip
+      launch_one_frac(key, t, r, true, pr->d, flags, back);
+    } else {
+      k_one_report<<<1, 1, 0, G.stream>>>(d_r, back);
+      G.launches++;
+    }
+    if ((rc = wait_one_back(back, &r)) != HMB200_OK) return rc;
+    *out = r;
+    return HMB200_OK;
+  }
   if (flags & HMB200_FLAG_FRAC)                       // xPatternSearchFracDIF on the MV just found, same round trip
-    dispatch_generic(reinterpret_cast<const SearchTask*>(G.one_dev + ONE_TASK), d_r, 1, G.pattern.d, pr->d, flags, /*do_search=*/false, nullptr);
+    dispatch_generic(reinterpret_cast<const SearchTask*>(G.one_dev + ONE_TASK), d_r, 1, pat, pr->d, flags, /*do_search=*/false, nullptr);
   if ((rc = finish_one_call(&r)) != HMB200_OK) return rc;
   *out = r;
   return HMB200_OK;

@@ -1,0 +1,334 @@
+// One PU per call: the kernels behind the 1:1 entries (hmb200_pattern_search, hmb200_pattern_search_frac,
+// hmb200_pattern_search_and_refine, hmb200_pattern_search_tz*), which the in-encoder forwarders call once per
+// TEncSearch::xPatternSearch / xPatternSearchFracDIF (TLibEncoder/TEncSearch.cpp:3796-3841, :4240-4276).
+//
+// A call is latency: the host waits for this PU's answer before HM can form the next PU's predictor.  Measured on B200
+// (tools/latency_1to1.py, profiles/r02_latency_1to1.txt) the floor of "copy in, K kernels, copy out, stream sync" is
+// 16 us + 2.7 us per extra kernel; "copy in, K kernels, result + sequence flag written straight into mapped host memory,
+// host spins on the flag" is 9 us + 2.7 us per extra kernel.  So:
+//   * k_one_search  one CTA per candidate ROW of the window (129 CTAs at +-64, one wave); the CTA stages the reference
+//                   rows its candidates touch (aligned 16-byte loads) and the pattern in shared memory, a thread per
+//                   candidate runs byte-SIMD SADs (VABSDIFF4 on funnel-shifted words) when pattern and plane are 8-bit
+//                   (scalar 16-bit otherwise: 10-bit planes, the signed 2*org - pred pattern of bi-prediction);
+//                   the LAST CTA to finish (ticket counter) decodes the 64-bit argmin key - no finalize launch - and, for
+//                   PUs up to 16x16 (nine calls in ten inside the encoder), refines the vector itself: one launch per call;
+//   * k_one_frac    larger PUs / refinement-only calls: one CTA, up to 1024 threads, a thread per COLUMN of a (candidate,
+//                   Hadamard tile) instead of a thread per tile (an 8x8 PU has 9 tiles per stage - 9 busy threads); the row
+//                   transform runs across the 4 / 8 lanes with shuffles.  The sum of absolute coefficients does not depend
+//                   on the butterfly order, the per-tile rounding is kept;
+//   * OneBack       whichever kernel ends the call stores the result record and then the call's sequence number into
+//                   mapped page-locked host memory (__threadfence_system between the two);
+//   * the task and the caller's result record travel as kernel arguments, not through device memory.
+// Arithmetic, candidate order and tie-breaks are those of k_search_split / k_frac_generic (hmb200_generic.cuh), which stay
+// as the fallback for windows that do not fit shared memory and as the A/B reference of tests/test_gpu_parity.py.
+#pragma once
+#include "hmb200_generic.cuh"
+
+namespace hmb200 {
+
+struct OneBack {                       // where the call's last kernel reports to (mapped host memory); host_result == nullptr: nowhere
+  hmb200_pu_result* host_result;
+  uint32_t* host_flag;
+  uint32_t seq;
+};
+
+__device__ __forceinline__ void one_report(const OneBack& back, const hmb200_pu_result& r) {
+  if (!back.host_result) return;
+  volatile int32_t* dst = reinterpret_cast<volatile int32_t*>(back.host_result);
+  const int32_t* src = reinterpret_cast<const int32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(hmb200_pu_result) / 4); i++) dst[i] = src[i];
+  __threadfence_system();              // the record is visible to the host before the flag
+  *reinterpret_cast<volatile uint32_t*>(back.host_flag) = back.seq;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// quarter-pel refinement of one PU (xPatternSearchFracDIF): k_frac_generic's stages with the vertical pass + distortion
+// spread over N threads per (candidate, tile).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int ONE_FRAC_THREADS_MAX = 1024;
+
+// column c of an N x N difference tile (d[r], r = 0..N-1) -> this lane's share of the sum of absolute Hadamard coefficients
+template <int N>
+__device__ __forceinline__ uint32_t had_columns_abs(int (&d)[N], int lane_in_group) {
+  // column transform in registers
+#pragma unroll
+  for (int len = 1; len < N; len <<= 1)
+#pragma unroll
+    for (int b = 0; b < N; b += 2 * len)
+#pragma unroll
+      for (int k = 0; k < len; k++) { const int a0 = d[b + k], a1 = d[b + k + len]; d[b + k] = a0 + a1; d[b + k + len] = a0 - a1; }
+  // row transform across the N lanes that hold the tile's columns
+#pragma unroll
+  for (int m = 1; m < N; m <<= 1) {
+    const bool upper = (lane_in_group & m) != 0;
+#pragma unroll
+    for (int r = 0; r < N; r++) {
+      const int other = __shfl_xor_sync(0xffffffffu, d[r], m);
+      d[r] = upper ? other - d[r] : d[r] + other;
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int r = 0; r < N; r++) s += (uint32_t)abs(d[r]);
+  return s;
+}
+
+template <int N>
+__device__ __forceinline__ void one_frac_tiles(const int16_t* __restrict__ s_hor, const int16_t* __restrict__ s_org, uint32_t* s_dist,
+                                               int W, int H, int RH, int stage, int base_qy, int stepq, int use_had, int head, int maxv) {
+  const int tiles_x = W / N, tiles = tiles_x * (H / N), total = 9 * tiles * N;
+  for (int base = 0; base < total; base += blockDim.x) {
+    const int tt = base + (int)threadIdx.x;
+    const bool live = tt < total;                                           // total and blockDim are multiples of N: a lane group is live as a whole
+    const int g = (live ? tt : total - 1) / N, c = threadIdx.x & (N - 1);
+    const int cand = g / tiles, tile = g - cand * tiles;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int cx = (stage == 0) ? k_refine_h[cand][0] : k_refine_q[cand][0];
+    const int cy = (stage == 0) ? k_refine_h[cand][1] : k_refine_q[cand][1];
+    const int qy = base_qy + cy * stepq;
+    const int iy = floor_div4(qy), fy = qy & 3;
+    const int16_t* hp = s_hor + ((cx + 1) * RH) * W;
+    int col[N + 7];
+#pragma unroll
+    for (int r = 0; r < N + 7; r++) col[r] = hp[(ty * N + 4 + iy + r - 3) * W + tx * N + c];
+    int d[N];
+#pragma unroll
+    for (int r = 0; r < N; r++) {
+      int cc[8];
+#pragma unroll
+      for (int tp = 0; tp < 8; tp++) cc[tp] = col[r + tp];
+      d[r] = (int)s_org[(ty * N + r) * W + tx * N + c] - interp_v(cc, fy, head, maxv);
+    }
+    uint32_t s;
+    if (use_had) s = had_columns_abs<N>(d, c);
+    else {
+      s = 0;
+#pragma unroll
+      for (int r = 0; r < N; r++) s += (uint32_t)abs(d[r]);
+    }
+#pragma unroll
+    for (int m = 1; m < N; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (live && c == 0) {
+      if (use_had) s = (N == 8) ? (s + 2) >> 2 : (s + 1) >> 1;             // TComRdCost.cpp:1520, :1423
+      atomicAdd(&s_dist[cand], s);
+    }
+  }
+}
+
+// dynamic shared memory (bytes) of one_frac_body for a PU: reference block with its 4-sample apron, three horizontally filtered
+// planes, the pattern
+__host__ __device__ inline int one_frac_smem(int w, int h) { return ((w + 8) * (h + 8) + 3 * (h + 8) * w + w * h) * 2; }
+
+// xPatternSearchFracDIF of the PU at res.mv_x / mv_y, by every thread of the calling CTA (blockDim.x a multiple of 32); fills
+// res.half_*, res.qter_*, res.frac_cost in every thread.  pattern: dense int16 rows (pitch = w).
+template <typename RefT>
+__device__ __forceinline__ void one_frac_body(const SearchTask& t, hmb200_pu_result& res, const int16_t* __restrict__ pattern,
+                                              const DevPlane& ref_plane, int use_had, int16_t* smem16) {
+  const int W = t.w, H = t.h, RW = W + 8, RH = H + 8;
+  int16_t* s_ref = smem16;                                  // [H+8][W+8], origin at (-4,-4) of the MC block
+  int16_t* s_hor = s_ref + RW * RH;                         // [3][H+8][W]
+  int16_t* s_org = s_hor + 3 * RH * W;                      // [H][W]
+  __shared__ uint32_t s_dist[9];
+  __shared__ int s_sel[2];
+
+  const RefT* ref = plane_at<RefT>(ref_plane, t.ref_x, t.ref_y);
+  const int ref_stride = ref_plane.pitch, bit_depth = ref_plane.bit_depth;
+  const int mvx = res.mv_x, mvy = res.mv_y;
+  const int head = max(2, 14 - bit_depth), maxv = (1 << bit_depth) - 1;
+
+  for (int i = threadIdx.x; i < RW * RH; i += blockDim.x) {
+    const int r = i / RW, c = i - r * RW;
+    s_ref[i] = (int16_t)ref[(ptrdiff_t)(mvy + r - 4) * ref_stride + (mvx + c - 4)];
+  }
+  for (int i = threadIdx.x; i < W * H; i += blockDim.x) s_org[i] = pattern[i];
+  const int n = (!use_had) ? 4 : ((W % 8 == 0 && H % 8 == 0) ? 8 : 4);   // tile edge
+
+  int base_qx = 0, base_qy = 0;            // 2*half after stage 1
+  for (int stage = 0; stage < 2; stage++) {
+    const int stepq = (stage == 0) ? 2 : 1;
+    if (threadIdx.x < 9) s_dist[threadIdx.x] = 0;
+    __syncthreads();
+    // horizontal pass for the three distinct quarter-pel x displacements of this stage
+    for (int i = threadIdx.x; i < 3 * RH * W; i += blockDim.x) {
+      const int k = i / (RH * W), rem = i - k * RH * W, r = rem / W, c = rem - r * W;
+      const int qx = base_qx + (k - 1) * stepq;
+      const int ix = floor_div4(qx), fx = qx & 3;
+      int s[8];
+#pragma unroll
+      for (int tp = 0; tp < 8; tp++) s[tp] = s_ref[r * RW + (c + 4 + ix + tp - 3)];
+      s_hor[i] = interp_h(s, fx, head);
+    }
+    __syncthreads();
+    if (n == 8) one_frac_tiles<8>(s_hor, s_org, s_dist, W, H, RH, stage, base_qy, stepq, use_had, head, maxv);
+    else        one_frac_tiles<4>(s_hor, s_org, s_dist, W, H, RH, stage, base_qy, stepq, use_had, head, maxv);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // cost of the nine candidates, one per lane; the first minimum wins (strict '<' in the reference's candidate order)
+      const int i = min((int)threadIdx.x, 8);
+      const int cx = (stage == 0) ? k_refine_h[i][0] : k_refine_q[i][0];
+      const int cy = (stage == 0) ? k_refine_h[i][1] : k_refine_q[i][1];
+      const uint32_t bits = (stage == 0)
+          ? mv_bits(cx + 2 * mvx, cy + 2 * mvy, t.pred_x, t.pred_y, 1)                                   // :3746
+          : mv_bits(cx + 2 * (2 * mvx) + base_qx, cy + 2 * (2 * mvy) + base_qy, t.pred_x, t.pred_y, 0);  // :4267
+      const uint32_t c = (s_dist[i] >> (bit_depth - 8)) + mv_cost(t.lambda_cost, bits);
+      unsigned long long k = threadIdx.x < 9 ? make_key(c, (uint32_t)i) : ~0ull;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
+        k = other < k ? other : k;
+      }
+      if (threadIdx.x == 0) { s_sel[0] = (int)(k & 0xffffffffu); s_sel[1] = (int)(uint32_t)(k >> 32); }
+    }
+    __syncthreads();
+    const int bi = s_sel[0];
+    if (stage == 0) {
+      res.half_x = k_refine_h[bi][0]; res.half_y = k_refine_h[bi][1];
+      base_qx = 2 * res.half_x; base_qy = 2 * res.half_y;
+    } else {
+      res.qter_x = k_refine_q[bi][0]; res.qter_y = k_refine_q[bi][1];
+      res.frac_cost = (uint32_t)s_sel[1];
+    }
+    __syncthreads();
+  }
+}
+
+// seed: the caller's result record; mv_from_device: take the integer MV from out[0] (a search kernel ran before) instead
+template <typename RefT>
+__global__ void __launch_bounds__(ONE_FRAC_THREADS_MAX)
+k_one_frac(const SearchTask t, hmb200_pu_result seed, int mv_from_device, hmb200_pu_result* __restrict__ out, const int16_t* __restrict__ pattern,
+           DevPlane ref_plane, int use_had, OneBack back) {
+  extern __shared__ __align__(16) int16_t one_smem16[];
+  hmb200_pu_result res = seed;
+  if (mv_from_device) res = out[0];
+  one_frac_body<RefT>(t, res, pattern, ref_plane, use_had, one_smem16);
+  if (threadIdx.x == 0) { out[0] = res; one_report(back, res); }
+}
+
+constexpr int ONE_SEARCH_THREADS = 160;          // 129 candidates of a +-64 window row: five warps
+constexpr int ONE_SEARCH_THREADS_MAX = 512;      // ... more when the last CTA also refines (a thread per tile column of a stage)
+constexpr int ONE_SMEM_MAX = 200 * 1024;
+constexpr int ONE_FUSE_FRAC = 1, ONE_FUSE_HAD = 2;  // k_one_search's fuse argument
+constexpr int ONE_FUSE_MAX_SAMPLES = 256;           // PUs up to 16x16 are refined by the search kernel's last CTA
+
+// dynamic shared memory of k_one_search for a task (host and device agree on the layout)
+__host__ __device__ inline int one_search_row_bytes(bool bytes, int col0, int nx, int w) {
+  if (bytes) return (((col0 & 15) + nx + w - 1 + 15) / 16 + 1) * 16;      // 16-byte vectors covering the row, one more for the word past it
+  return ((nx + w - 1 + 7) & ~7) * 2;
+}
+__host__ __device__ inline int one_search_smem(bool bytes, int col0, int nx, int w, int rows) {
+  return rows * one_search_row_bytes(bytes, col0, nx, w) + rows * w * (bytes ? 1 : 2);
+}
+
+// pattern: dense int16 rows (pitch = w).  BYTES: every pattern sample is in 0..255 and the plane holds bytes.
+template <bool BYTES, typename RefT>
+__global__ void __launch_bounds__(ONE_SEARCH_THREADS_MAX)
+k_one_search(const SearchTask t, hmb200_pu_result seed, unsigned long long* __restrict__ key, uint32_t* __restrict__ ticket,
+             hmb200_pu_result* __restrict__ out, const int16_t* __restrict__ pattern, DevPlane ref_plane, int fuse, OneBack back) {
+  extern __shared__ __align__(16) uint8_t one_smem[];
+  __shared__ unsigned long long s_best[ONE_SEARCH_THREADS_MAX / 32];
+  __shared__ int s_last;
+  __shared__ unsigned long long s_key;
+  const int nx = t.rb_x - t.lt_x + 1;
+  const int step = 1 << t.sub_shift, rows = t.h >> t.sub_shift;
+  const int cy = blockIdx.x, y = t.lt_y + cy;
+  const int col0 = t.ref_x + ref_plane.margin_x + t.lt_x;                  // plane column of candidate 0's first sample
+  const int row0 = t.ref_y + ref_plane.margin_y + y;
+  const int rp = one_search_row_bytes(BYTES, col0, nx, t.w);
+  uint8_t* s_org8 = one_smem + rows * rp;
+  unsigned long long best = ~0ull;
+
+  if (BYTES) {
+    const int nvec = rp / 16 - 1, vec0 = col0 >> 4;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(ref_plane.base);
+    for (int i = threadIdx.x; i < rows * (nvec + 1); i += blockDim.x) {
+      const int r = i / (nvec + 1), v = i - r * (nvec + 1);
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (v < nvec && (vec0 + v) * 16 < ref_plane.pitch)                   // the spare vector and anything past the row: zeros, never in a result
+        q = *reinterpret_cast<const uint4*>(base + (size_t)(row0 + r * step) * ref_plane.pitch + (size_t)(vec0 + v) * 16);
+      *reinterpret_cast<uint4*>(one_smem + r * rp + v * 16) = q;
+    }
+    for (int i = threadIdx.x; i < rows * t.w; i += blockDim.x) {
+      const int r = i / t.w, c = i - r * t.w;
+      s_org8[i] = (uint8_t)pattern[(r * step) * t.w + c];
+    }
+    __syncthreads();
+    const int ww = t.w >> 2;
+    const uint32_t* org32 = reinterpret_cast<const uint32_t*>(s_org8);
+    for (int cx = threadIdx.x; cx < nx; cx += blockDim.x) {
+      const int b = (col0 & 15) + cx, sh = (b & 3) * 8;
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(one_smem) + (b >> 2);
+      uint32_t sum = 0;
+      for (int r = 0; r < rows; r++, row += rp / 4) {
+        uint32_t lo = row[0];
+        for (int g = 0; g < ww; g++) {
+          const uint32_t hi = row[g + 1];
+          sum = sad4_acc(__funnelshift_r(lo, hi, sh), org32[r * ww + g], sum);
+          lo = hi;
+        }
+      }
+      const int x = t.lt_x + cx;
+      sum <<= t.sub_shift;                                                  // bit depth 8: no precision shift
+      const unsigned long long k = make_key(sum + mv_cost(t.lambda_cost, mv_bits(x, y, t.pred_x, t.pred_y, 2)), (uint32_t)(cy * nx + cx));
+      best = k < best ? k : best;
+    }
+  } else {
+    int16_t* s_ref = reinterpret_cast<int16_t*>(one_smem);
+    int16_t* s_org = reinterpret_cast<int16_t*>(s_org8);
+    const int rp16 = rp / 2, span = nx + t.w - 1;
+    const RefT* base = reinterpret_cast<const RefT*>(ref_plane.base);
+    for (int i = threadIdx.x; i < rows * span; i += blockDim.x) {
+      const int r = i / span, c = i - r * span;
+      s_ref[r * rp16 + c] = (int16_t)base[(size_t)(row0 + r * step) * ref_plane.pitch + col0 + c];
+    }
+    for (int i = threadIdx.x; i < rows * t.w; i += blockDim.x) {
+      const int r = i / t.w, c = i - r * t.w;
+      s_org[i] = pattern[(r * step) * t.w + c];
+    }
+    __syncthreads();
+    for (int cx = threadIdx.x; cx < nx; cx += blockDim.x) {
+      uint32_t sum = 0;
+      for (int r = 0; r < rows; r++) {
+        const int16_t* q = s_ref + r * rp16 + cx;
+        const int16_t* o = s_org + r * t.w;
+        for (int c = 0; c < t.w; c++) sum += (uint32_t)abs((int)o[c] - (int)q[c]);
+      }
+      const int x = t.lt_x + cx;
+      sum = (sum << t.sub_shift) >> (ref_plane.bit_depth - 8);
+      const unsigned long long k = make_key(sum + mv_cost(t.lambda_cost, mv_bits(x, y, t.pred_x, t.pred_y, 2)), (uint32_t)(cy * nx + cx));
+      best = k < best ? k : best;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other < best ? other : best;
+  }
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) best = s_best[w] < best ? s_best[w] : best;
+    atomicMin(key, best);
+    __threadfence();                                                        // this CTA's minimum is in the key before its ticket
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // every CTA's minimum has arrived: key -> (rcMv, ruiSAD), TEncSearch.cpp:3839-3841
+  if (threadIdx.x == 0) { __threadfence(); s_key = atomicMin(key, ~0ull); }
+  __syncthreads();
+  const unsigned long long k = s_key;
+  const uint32_t idx = (uint32_t)(k & 0xffffffffu), cost = (uint32_t)(k >> 32);
+  const int by = idx / nx, bx = idx - by * nx;
+  hmb200_pu_result r = seed;
+  r.mv_x = t.lt_x + bx; r.mv_y = t.lt_y + by;
+  r.sad = cost - mv_cost(t.lambda_cost, mv_bits(r.mv_x, r.mv_y, t.pred_x, t.pred_y, 2));
+  if (fuse & ONE_FUSE_FRAC)            // small PUs: this CTA refines the vector it just decoded - no second launch
+    one_frac_body<RefT>(t, r, pattern, ref_plane, (fuse & ONE_FUSE_HAD) ? 1 : 0, reinterpret_cast<int16_t*>(one_smem));
+  if (threadIdx.x == 0) { out[0] = r; one_report(back, r); }
+}
+
+// ends a call whose last kernel is one of the older ones (TZ search without refinement): one thread reports the record
+__global__ void k_one_report(const hmb200_pu_result* __restrict__ out, OneBack back) { one_report(back, out[0]); }
+
+}  // namespace hmb200
