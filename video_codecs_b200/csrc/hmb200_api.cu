@@ -45,8 +45,8 @@ struct PoolBuf { size_t bytes; void* base; cudaEvent_t ev_free; };   // ev_free:
 constexpr int N_SIDE = 4;
 // layout of the per-call record of the 1:1 entries (host page-locked copy and device copy): offsets in bytes
 constexpr size_t ONE_KEY = 0, ONE_TICKET = 8, ONE_RESULT = 16, ONE_TASK = 64, ONE_TZ = 128, ONE_HEAD = 256;
-// the record the call's last kernel writes into mapped host memory (State::one_back): result, then the call's sequence number
-constexpr size_t BACK_RESULT = 0, BACK_FLAG = 64, BACK_BYTES = 128;
+// the two 16-byte records the call's last kernel writes into mapped host memory (State::one_back, hmb200_one.cuh OneBack)
+constexpr size_t BACK_A = 0, BACK_B = 16, BACK_BYTES = 64;
 
 struct State {
   bool ready = false;
@@ -356,11 +356,19 @@ static int init_state_body(State& st, int device) {
   CUDA_TRY(cudaMallocHost((void**)&st.one_host, ONE_HEAD + 64 * 64 * sizeof(int16_t)));
   CUDA_TRY(cudaHostAlloc((void**)&st.one_back, BACK_BYTES, cudaHostAllocMapped));
   memset(st.one_back, 0, BACK_BYTES);
+  {
+    // argmin key = ~0, ticket = 0: the state k_one_search leaves behind after every call
+    unsigned long long init[2] = {~0ull, 0ull};
+    CUDA_TRY(cudaMemcpy(st.one_dev + ONE_KEY, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
   st.one_seq = 0;
   st.one_fast = getenv("HMB200_NO_ONE_FAST") == nullptr;
   CUDA_TRY(cudaFuncSetAttribute(k_one_search<true, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_search_args<true, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
   CUDA_TRY(cudaFuncSetAttribute(k_one_search<false, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_search_args<false, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
   CUDA_TRY(cudaFuncSetAttribute(k_one_search<false, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_search_args<false, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
   st.pattern.used = true;
   st.pattern.d.base = st.one_dev + ONE_HEAD; st.pattern.d.pitch = 64; st.pattern.d.width = 64; st.pattern.d.height = 64;
   st.pattern.d.margin_x = 0; st.pattern.d.margin_y = 0; st.pattern.d.bytes_per_sample = 2; st.pattern.d.bit_depth = 16;
@@ -1448,20 +1456,25 @@ static int finish_one_call(hmb200_pu_result* io) {
   memcpy(io, G.one_host + ONE_RESULT, sizeof(*io));
   return HMB200_OK;
 }
-// The call's last kernel stores the result and then this call's sequence number in mapped host memory (OneBack); the host spins
-// on the number instead of paying a D2H copy and a stream synchronisation (7 us of a 16 us round trip, profiles/r02_latency_1to1.txt).
+// The call's last kernel stores the result in mapped host memory as two 16-byte records ending in this call's sequence number
+// (OneBack); the host spins on the numbers instead of paying a D2H copy and a stream synchronisation (7 us of a 16 us round trip,
+// profiles/r02_latency_1to1.txt).
 static OneBack next_one_back() {
   G.one_seq++;
   if (G.one_seq == 0) G.one_seq = 1;
-  return OneBack{reinterpret_cast<hmb200_pu_result*>(G.one_back + BACK_RESULT), reinterpret_cast<uint32_t*>(G.one_back + BACK_FLAG), G.one_seq};
+  return OneBack{reinterpret_cast<uint4*>(G.one_back + BACK_A), reinterpret_cast<uint4*>(G.one_back + BACK_B), G.one_seq};
 }
 static int wait_one_back(const OneBack& back, hmb200_pu_result* io) {
   CUDA_TRY(cudaGetLastError());                                   // a failed launch would never report
-  volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(G.one_back + BACK_FLAG);
-  for (uint64_t spins = 1; *flag != back.seq; spins++) {
+  volatile uint32_t* a = reinterpret_cast<volatile uint32_t*>(G.one_back + BACK_A);
+  volatile uint32_t* b = reinterpret_cast<volatile uint32_t*>(G.one_back + BACK_B);
+  for (uint64_t spins = 1; a[3] != back.seq || b[3] != back.seq; spins++) {
     if ((spins & 0x3fff) == 0) {                                  // every ~16k polls: has the stream failed or finished without reporting?
       const cudaError_t e = cudaStreamQuery(G.stream);
-      if (e == cudaSuccess) { if (*flag != back.seq) return fail(HMB200_ERR_CUDA, "1:1 call: the stream finished without reporting a result"); break; }
+      if (e == cudaSuccess) {
+        if (a[3] != back.seq || b[3] != back.seq) return fail(HMB200_ERR_CUDA, "1:1 call: the stream finished without reporting a result");
+        break;
+      }
       if (e != cudaErrorNotReady) return fail(HMB200_ERR_CUDA, std::string("1:1 call: ") + cudaGetErrorString(e));
     }
 #if defined(__x86_64__) || defined(__i386__)
@@ -1469,7 +1482,23 @@ static int wait_one_back(const OneBack& back, hmb200_pu_result* io) {
 #endif
   }
   std::atomic_thread_fence(std::memory_order_acquire);
-  memcpy(io, G.one_back + BACK_RESULT, sizeof(*io));
+  const uint32_t fr = b[0];
+  io->mv_x = (int32_t)a[0]; io->mv_y = (int32_t)a[1]; io->sad = a[2];
+  io->half_x = (int8_t)(fr & 0xff); io->half_y = (int8_t)((fr >> 8) & 0xff);
+  io->qter_x = (int8_t)((fr >> 16) & 0xff); io->qter_y = (int8_t)((fr >> 24) & 0xff);
+  io->frac_cost = b[1];
+  return HMB200_OK;
+}
+// a PU of up to 16x16 samples as a kernel argument (dense rows); *fits_u8 as in stage_one_call
+static int fill_one_pattern(const hmb200_pattern* key, OnePattern* pat, bool* fits_u8) {
+  if (!key || !key->roi || !supported_pu(key->width, key->height)) return fail(HMB200_ERR_ARG, "unsupported pattern");
+  int all = 0;
+  for (int y = 0; y < key->height; y++) {
+    const int16_t* src = key->roi + (ptrdiff_t)y * key->stride;
+    int16_t* dst = pat->px + (size_t)y * key->width;
+    for (int x = 0; x < key->width; x++) { dst[x] = src[x]; all |= src[x]; }
+  }
+  *fits_u8 = (all & ~0xff) == 0;
   return HMB200_OK;
 }
 // k_one_frac launch: a thread per column of every (candidate, tile) of a stage, capped at one full CTA
@@ -1502,18 +1531,24 @@ static int run_single(const hmb200_pattern* key, const int16_t* ref_at_pu, const
                             : Box{rx + io->mv_x - reach, ry + io->mv_y - reach, rx + io->mv_x + t.w + reach, ry + io->mv_y + t.h + reach};
     if (!box_inside(pr->d, b)) return fail(HMB200_ERR_ARG, "the search window / refinement block leaves the padded reference plane");
   }
-  bool fits_u8 = false;
-  int rc = stage_one_call(key, t, *io, nullptr, &fits_u8);
-  if (rc != HMB200_OK) return rc;
+  const bool r8 = pr->d.bytes_per_sample == 1;
+  const bool frac = (flags & HMB200_FLAG_FRAC) != 0;
   SearchTask* d_t = reinterpret_cast<SearchTask*>(G.one_dev + ONE_TASK);
   hmb200_pu_result* d_r = reinterpret_cast<hmb200_pu_result*>(G.one_dev + ONE_RESULT);
   unsigned long long* d_key = reinterpret_cast<unsigned long long*>(G.one_dev + ONE_KEY);
-  const bool r8 = pr->d.bytes_per_sample == 1;
-  const bool frac = (flags & HMB200_FLAG_FRAC) != 0;
+  uint32_t* d_ticket = reinterpret_cast<uint32_t*>(G.one_dev + ONE_TICKET);
+  const int16_t* d_pat = reinterpret_cast<const int16_t*>(G.one_dev + ONE_HEAD);
+  bool fits_u8 = false, staged = false;
+  int rc;
   if (G.one_fast) {
-    // hmb200_one.cuh: a CTA per candidate row, the last one decodes; refinement with a thread per tile column; result by flag
+    // hmb200_one.cuh: a CTA per candidate row, the last one decodes (and refines a small PU); larger PUs: refinement with a thread per
+    // tile column in a second launch; result by flag.  Small PUs travel in the kernel arguments: no copy either way.
+    const bool small = t.w * t.h <= ONE_ARG_SAMPLES;
+    OnePattern arg;
+    if (small) { if ((rc = fill_one_pattern(key, &arg, &fits_u8)) != HMB200_OK) return rc; }
+    else       { if ((rc = stage_one_call(key, t, *io, nullptr, &fits_u8)) != HMB200_OK) return rc; staged = true; }
     const OneBack back = next_one_back(), none{nullptr, nullptr, 0};
-    const int16_t* d_pat = reinterpret_cast<const int16_t*>(G.one_dev + ONE_HEAD);
+    const int had = (flags & HMB200_FLAG_HADME) ? 1 : 0;
     bool searched = !do_search, fused = false;
     if (do_search) {
       const int nx = t.rb_x - t.lt_x + 1, ny = t.rb_y - t.lt_y + 1, rows = t.h >> t.sub_shift;
@@ -1522,27 +1557,43 @@ static int run_single(const hmb200_pattern* key, const int16_t* ref_at_pu, const
       fused = frac && t.w * t.h <= ONE_FUSE_MAX_SAMPLES;           // small PU: the search's last CTA refines, one launch per call
       const int smem = std::max(one_search_smem(bytes, col0, nx, t.w, rows), fused ? one_frac_smem(t.w, t.h) : 0);
       if (smem <= ONE_SMEM_MAX) {
-        uint32_t* d_ticket = reinterpret_cast<uint32_t*>(G.one_dev + ONE_TICKET);
         const OneBack& b = (frac && !fused) ? none : back;
-        const int fuse = fused ? (ONE_FUSE_FRAC | ((flags & HMB200_FLAG_HADME) ? ONE_FUSE_HAD : 0)) : 0;
+        const int fuse = fused ? (ONE_FUSE_FRAC | (had ? ONE_FUSE_HAD : 0)) : 0;
         int threads = ONE_SEARCH_THREADS;
         if (fused) {                                               // enough threads for one pass over the refinement's tile columns
-          const int n = !(flags & HMB200_FLAG_HADME) ? 4 : ((t.w % 8 == 0 && t.h % 8 == 0) ? 8 : 4);
+          const int n = !had ? 4 : ((t.w % 8 == 0 && t.h % 8 == 0) ? 8 : 4);
           threads = std::min(ONE_SEARCH_THREADS_MAX, std::max(threads, (9 * (t.w / n) * (t.h / n) * n + 31) & ~31));
         }
-        if (bytes)    k_one_search<true, uint8_t><<<ny, threads, smem, G.stream>>>(t, *io, d_key, d_ticket, d_r, d_pat, pr->d, fuse, b);
-        else if (r8)  k_one_search<false, uint8_t><<<ny, threads, smem, G.stream>>>(t, *io, d_key, d_ticket, d_r, d_pat, pr->d, fuse, b);
-        else          k_one_search<false, int16_t><<<ny, threads, smem, G.stream>>>(t, *io, d_key, d_ticket, d_r, d_pat, pr->d, fuse, b);
+        if (small) {
+          if (bytes)    k_one_search_args<true, uint8_t><<<ny, threads, smem, G.stream>>>(t, *io, arg, d_key, d_ticket, pr->d, fuse, b);
+          else if (r8)  k_one_search_args<false, uint8_t><<<ny, threads, smem, G.stream>>>(t, *io, arg, d_key, d_ticket, pr->d, fuse, b);
+          else          k_one_search_args<false, int16_t><<<ny, threads, smem, G.stream>>>(t, *io, arg, d_key, d_ticket, pr->d, fuse, b);
+        } else {
+          if (bytes)    k_one_search<true, uint8_t><<<ny, threads, smem, G.stream>>>(t, *io, d_key, d_ticket, d_r, d_pat, pr->d, fuse, b);
+          else if (r8)  k_one_search<false, uint8_t><<<ny, threads, smem, G.stream>>>(t, *io, d_key, d_ticket, d_r, d_pat, pr->d, fuse, b);
+          else          k_one_search<false, int16_t><<<ny, threads, smem, G.stream>>>(t, *io, d_key, d_ticket, d_r, d_pat, pr->d, fuse, b);
+        }
         G.launches++;
         searched = true;
       }
     }
     if (searched) {
-      if (frac && !fused) launch_one_frac(key, t, *io, do_search, pr->d, flags, back);
+      if (frac && !fused) {
+        if (small && !do_search) {                                 // refinement-only call of a small PU: arguments only
+          const int n = !had ? 4 : ((t.w % 8 == 0 && t.h % 8 == 0) ? 8 : 4);
+          const int threads = std::min(ONE_FRAC_THREADS_MAX, std::max(128, (9 * (t.w / n) * (t.h / n) * n + 31) & ~31));
+          if (r8) k_one_frac_args<uint8_t><<<1, threads, one_frac_smem(t.w, t.h), G.stream>>>(t, *io, arg, pr->d, had, back);
+          else    k_one_frac_args<int16_t><<<1, threads, one_frac_smem(t.w, t.h), G.stream>>>(t, *io, arg, pr->d, had, back);
+          G.launches++;
+        } else {
+          launch_one_frac(key, t, *io, do_search, pr->d, flags, back);
+        }
+      }
       return wait_one_back(back, io);
     }
     // a window too large for shared memory: the round-1 kernels below
   }
+  if (!staged && (rc = stage_one_call(key, t, *io, nullptr, &fits_u8)) != HMB200_OK) return rc;
   const DevPlane pat = pattern_plane(key->width);
   if (do_search) {
     // one PU: spread its candidates over the whole GPU (one CTA per ~256 candidates), fold with atomicMin, decode

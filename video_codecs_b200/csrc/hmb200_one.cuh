@@ -16,9 +16,10 @@
 //                   Hadamard tile) instead of a thread per tile (an 8x8 PU has 9 tiles per stage - 9 busy threads); the row
 //                   transform runs across the 4 / 8 lanes with shuffles.  The sum of absolute coefficients does not depend
 //                   on the butterfly order, the per-tile rounding is kept;
-//   * OneBack       whichever kernel ends the call stores the result record and then the call's sequence number into
-//                   mapped page-locked host memory (__threadfence_system between the two);
-//   * the task and the caller's result record travel as kernel arguments, not through device memory.
+//   * OneBack       whichever kernel ends the call stores the result into mapped page-locked host memory as two 16-byte
+//                   records that carry the call's sequence number in their last word; the host spins on the number;
+//   * the task and the caller's result record travel as kernel arguments, and so does the pattern of a PU up to 16x16
+//     (OnePattern, 512 bytes): such a call is ONE launch and no copy in either direction.
 // Arithmetic, candidate order and tie-breaks are those of k_search_split / k_frac_generic (hmb200_generic.cuh), which stay
 // as the fallback for windows that do not fit shared memory and as the A/B reference of tests/test_gpu_parity.py.
 #pragma once
@@ -26,21 +27,27 @@
 
 namespace hmb200 {
 
-struct OneBack {                       // where the call's last kernel reports to (mapped host memory); host_result == nullptr: nowhere
-  hmb200_pu_result* host_result;
-  uint32_t* host_flag;
+// Where the call's last kernel reports to: two 16-byte records in mapped page-locked host memory, each written by ONE vector store
+// whose last word is the call's sequence number - {mv_x, mv_y, sad, seq} and {half | qter (4 x int8), frac_cost, 0, seq}.  A 16-byte
+// store crosses PCIe as one write in address order, so a record whose last word shows the number is complete: no system-scope fence
+// (2.3 us of a 10.9 us round trip, tools/roundtrip_probe.cu).  host_a == nullptr: report nowhere.
+struct OneBack {
+  uint4* host_a;
+  uint4* host_b;
   uint32_t seq;
 };
 
 __device__ __forceinline__ void one_report(const OneBack& back, const hmb200_pu_result& r) {
-  if (!back.host_result) return;
-  volatile int32_t* dst = reinterpret_cast<volatile int32_t*>(back.host_result);
-  const int32_t* src = reinterpret_cast<const int32_t*>(&r);
-#pragma unroll
-  for (int i = 0; i < (int)(sizeof(hmb200_pu_result) / 4); i++) dst[i] = src[i];
-  __threadfence_system();              // the record is visible to the host before the flag
-  *reinterpret_cast<volatile uint32_t*>(back.host_flag) = back.seq;
+  if (!back.host_a) return;
+  const uint32_t frac = ((uint32_t)r.half_x & 0xffu) | (((uint32_t)r.half_y & 0xffu) << 8) | (((uint32_t)r.qter_x & 0xffu) << 16) |
+                        (((uint32_t)r.qter_y & 0xffu) << 24);
+  asm volatile("st.volatile.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(back.host_a), "r"((uint32_t)r.mv_x), "r"((uint32_t)r.mv_y), "r"(r.sad), "r"(back.seq) : "memory");
+  asm volatile("st.volatile.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(back.host_b), "r"(frac), "r"(r.frac_cost), "r"(0u), "r"(back.seq) : "memory");
 }
+
+// a PU of up to 16x16 samples travels as a kernel argument (no H2D copy in the call at all)
+constexpr int ONE_ARG_SAMPLES = 256;
+struct OnePattern { int16_t px[ONE_ARG_SAMPLES]; };
 
 // ---------------------------------------------------------------------------------------------------------------
 // quarter-pel refinement of one PU (xPatternSearchFracDIF): k_frac_generic's stages with the vertical pass + distortion
@@ -204,6 +211,15 @@ k_one_frac(const SearchTask t, hmb200_pu_result seed, int mv_from_device, hmb200
   one_frac_body<RefT>(t, res, pattern, ref_plane, use_had, one_smem16);
   if (threadIdx.x == 0) { out[0] = res; one_report(back, res); }
 }
+// refinement-only call of a small PU: everything in the arguments
+template <typename RefT>
+__global__ void __launch_bounds__(ONE_FRAC_THREADS_MAX)
+k_one_frac_args(const SearchTask t, hmb200_pu_result seed, const __grid_constant__ OnePattern pat, DevPlane ref_plane, int use_had, OneBack back) {
+  extern __shared__ __align__(16) int16_t one_smem16[];
+  hmb200_pu_result res = seed;
+  one_frac_body<RefT>(t, res, pat.px, ref_plane, use_had, one_smem16);
+  if (threadIdx.x == 0) one_report(back, res);
+}
 
 constexpr int ONE_SEARCH_THREADS = 160;          // 129 candidates of a +-64 window row: five warps
 constexpr int ONE_SEARCH_THREADS_MAX = 512;      // ... more when the last CTA also refines (a thread per tile column of a stage)
@@ -221,10 +237,11 @@ __host__ __device__ inline int one_search_smem(bool bytes, int col0, int nx, int
 }
 
 // pattern: dense int16 rows (pitch = w).  BYTES: every pattern sample is in 0..255 and the plane holds bytes.
+// key / ticket: the argmin key (~0 between calls) and the count of finished CTAs (0 between calls); the last CTA restores both.
 template <bool BYTES, typename RefT>
-__global__ void __launch_bounds__(ONE_SEARCH_THREADS_MAX)
-k_one_search(const SearchTask t, hmb200_pu_result seed, unsigned long long* __restrict__ key, uint32_t* __restrict__ ticket,
-             hmb200_pu_result* __restrict__ out, const int16_t* __restrict__ pattern, DevPlane ref_plane, int fuse, OneBack back) {
+__device__ __forceinline__ void one_search_body(const SearchTask& t, const hmb200_pu_result& seed, unsigned long long* __restrict__ key,
+                                                uint32_t* __restrict__ ticket, hmb200_pu_result* __restrict__ out,
+                                                const int16_t* __restrict__ pattern, const DevPlane& ref_plane, int fuse, const OneBack& back) {
   extern __shared__ __align__(16) uint8_t one_smem[];
   __shared__ unsigned long long s_best[ONE_SEARCH_THREADS_MAX / 32];
   __shared__ int s_last;
@@ -315,7 +332,7 @@ k_one_search(const SearchTask t, hmb200_pu_result seed, unsigned long long* __re
   __syncthreads();
   if (!s_last) return;
   // every CTA's minimum has arrived: key -> (rcMv, ruiSAD), TEncSearch.cpp:3839-3841
-  if (threadIdx.x == 0) { __threadfence(); s_key = atomicMin(key, ~0ull); }
+  if (threadIdx.x == 0) { __threadfence(); s_key = atomicExch(key, ~0ull); *ticket = 0; }
   __syncthreads();
   const unsigned long long k = s_key;
   const uint32_t idx = (uint32_t)(k & 0xffffffffu), cost = (uint32_t)(k >> 32);
@@ -325,7 +342,21 @@ k_one_search(const SearchTask t, hmb200_pu_result seed, unsigned long long* __re
   r.sad = cost - mv_cost(t.lambda_cost, mv_bits(r.mv_x, r.mv_y, t.pred_x, t.pred_y, 2));
   if (fuse & ONE_FUSE_FRAC)            // small PUs: this CTA refines the vector it just decoded - no second launch
     one_frac_body<RefT>(t, r, pattern, ref_plane, (fuse & ONE_FUSE_HAD) ? 1 : 0, reinterpret_cast<int16_t*>(one_smem));
-  if (threadIdx.x == 0) { out[0] = r; one_report(back, r); }
+  if (threadIdx.x == 0) { if (out) out[0] = r; one_report(back, r); }
+}
+
+template <bool BYTES, typename RefT>
+__global__ void __launch_bounds__(ONE_SEARCH_THREADS_MAX)
+k_one_search(const SearchTask t, hmb200_pu_result seed, unsigned long long* __restrict__ key, uint32_t* __restrict__ ticket,
+             hmb200_pu_result* __restrict__ out, const int16_t* __restrict__ pattern, DevPlane ref_plane, int fuse, OneBack back) {
+  one_search_body<BYTES, RefT>(t, seed, key, ticket, out, pattern, ref_plane, fuse, back);
+}
+// small PU: the pattern is an argument; nothing of the call lives in device memory but key and ticket
+template <bool BYTES, typename RefT>
+__global__ void __launch_bounds__(ONE_SEARCH_THREADS_MAX)
+k_one_search_args(const SearchTask t, hmb200_pu_result seed, const __grid_constant__ OnePattern pat, unsigned long long* __restrict__ key,
+                  uint32_t* __restrict__ ticket, DevPlane ref_plane, int fuse, OneBack back) {
+  one_search_body<BYTES, RefT>(t, seed, key, ticket, nullptr, pat.px, ref_plane, fuse, back);
 }
 
 // ends a call whose last kernel is one of the older ones (TZ search without refinement): one thread reports the record
