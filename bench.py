@@ -772,6 +772,51 @@ def measure_dist_table(env, blocks_per_size=10000):
     return out
 
 
+def measure_one_pu_calls(env, calls=1000):
+    """The in-encoder shape of the path: ONE PU per call through the 1:1 entries (hmb200_pattern_search[_frac|_and_refine], what the
+    forwarders of integration/hm_shim.cpp call once per TEncSearch::xPatternSearch / xPatternSearchFracDIF), host pattern in,
+    vectors out, synchronous.  Microseconds per call for a few PU sizes, +-64 window at the centre of a 1080p plane; ctypes
+    adds ~4 us per call.  The fused entry must return what the two separate entries return."""
+    from video_codecs_b200 import synth
+    hm = env.hm
+    if env.rank != 0:
+        return None
+    W, H, M = 1920, 1080, 80
+    ref = np.ascontiguousarray(np.pad(synth.luma_frame(W, H, 0).astype(np.int16), M, mode="edge"))
+    cur = np.ascontiguousarray(np.pad(synth.luma_frame(W, H, 1).astype(np.int16), M, mode="edge"))
+    stride = W + 2 * M
+    idr = hm.register_plane(ref, W, H, M, M, 8, kind=1)
+    off = (512 + M) * stride + 960 + M
+    out = {"calls_per_point": calls, "unit": "us per call (synchronous, incl. ~4 us of ctypes)", "rows": []}
+
+    def timed(fn):
+        for _ in range(30):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            fn()
+        return 1e6 * (time.perf_counter() - t0) / calls
+
+    try:
+        for w, h in ((8, 8), (16, 16), (32, 32), (64, 64)):
+            org, rf = (cur, off, stride), (ref, off, stride)
+            mv, sad = hm.pattern_search(org, w, h, rf, (-64, -64), (64, 64), LAMBDA_COST, (0, 0))
+            fr = hm.pattern_search_frac(org, w, h, rf, mv, LAMBDA_COST, (0, 0))
+            if hm.pattern_search_and_refine(org, w, h, rf, (-64, -64), (64, 64), LAMBDA_COST, (0, 0)) != (mv, sad) + fr:
+                raise SystemExit("bench: the fused 1:1 entry differs from search + refinement")
+            out["rows"].append({
+                "pu": f"{w}x{h}",
+                "search": timed(lambda: hm.pattern_search(org, w, h, rf, (-64, -64), (64, 64), LAMBDA_COST, (0, 0))),
+                "refine": timed(lambda: hm.pattern_search_frac(org, w, h, rf, mv, LAMBDA_COST, (0, 0))),
+                "search_and_refine": timed(lambda: hm.pattern_search_and_refine(org, w, h, rf, (-64, -64), (64, 64), LAMBDA_COST, (0, 0)))})
+    finally:
+        hm.release_plane(idr)
+    out["note"] = ("kernels of hmb200_one.cuh: one launch per call for PUs up to 16x16 (pattern in the kernel arguments, the search's last "
+                   "CTA refines), result as two 16-byte records in mapped host memory; round-trip floor of one trivial launch: 7.2 us "
+                   "(profiles/r02_latency_1to1.txt)")
+    return out
+
+
 def run_ours(args):
     env = Env(args)
     wl_key = args.workload
@@ -797,6 +842,7 @@ def run_ours(args):
         extra("unfused_1080p", lambda: measure_pairs(env, "1080p", 5, 3, preds="random", with_hbm=False))
         if env.world == 1:
             extra("dist_table", lambda: measure_dist_table(env))
+            extra("one_pu_calls", lambda: measure_one_pu_calls(env))
     if env.rank == 0:
         if extras:
             line["extra_workloads"] = extras
