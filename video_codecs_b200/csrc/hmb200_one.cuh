@@ -30,7 +30,7 @@ namespace hmb200 {
 // Where the call's last kernel reports to: two 16-byte records in mapped page-locked host memory, each written by ONE vector store
 // whose last word is the call's sequence number - {mv_x, mv_y, sad, seq} and {half | qter (4 x int8), frac_cost, 0, seq}.  A 16-byte
 // store crosses PCIe as one write in address order, so a record whose last word shows the number is complete: no system-scope fence
-// (2.3 us of a 10.9 us round trip, tools/roundtrip_probe.cu).  host_a == nullptr: report nowhere.
+// (2.3 us of a 10.9 us round trip, tools/roundtrip_report_probe.cu).  host_a == nullptr: report nowhere.
 struct OneBack {
   uint4* host_a;
   uint4* host_b;
