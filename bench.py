@@ -821,11 +821,16 @@ def run_ours(args):
     env = Env(args)
     wl_key = args.workload
     t_start = time.perf_counter()
-    line = measure_pairs(env, wl_key, args.steps, args.warmup, shard=args.shard, search=args.search,
-                         preds=args.preds, check_merge=(args.shard == "tiles"))
+    if args.only:
+        line = {"only": args.only}                       # development aid: one extra workload, no headline (not a bench line)
+    else:
+        line = measure_pairs(env, wl_key, args.steps, args.warmup, shard=args.shard, search=args.search,
+                             preds=args.preds, check_merge=(args.shard == "tiles"))
     extras = {}
-    if args.extras and wl_key == "1080p" and args.shard == "frames" and args.search == "full" and args.preds == "zero":
+    if args.only or (args.extras and wl_key == "1080p" and args.shard == "frames" and args.search == "full" and args.preds == "zero"):
         def extra(name, fn):
+            if args.only and name != args.only:
+                return
             t0 = time.perf_counter()
             try:
                 r = fn()
@@ -846,7 +851,7 @@ def run_ours(args):
     if env.rank == 0:
         if extras:
             line["extra_workloads"] = extras
-        if env.world == 1 and not args.no_cpu_baseline and wl_key == "1080p":
+        if env.world == 1 and not args.no_cpu_baseline and wl_key == "1080p" and not args.only:
             line["cpu_baseline"] = cpu_sample_single(WORKLOADS[wl_key], args.cpu_ctus)
         line["bench_wall_s"] = time.perf_counter() - t_start
         emit(line)
@@ -872,6 +877,7 @@ def main():
     ap.add_argument("--search", default="full", choices=["full", "tz"], help="tz: xTZSearch (FastSearch=1) instead of the full search")
     ap.add_argument("--preds", default="zero", choices=["zero", "random"], help="random: a different predictor per PU (no CU fusion)")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="headline only (skip extra_workloads)")
+    ap.add_argument("--only", default=None, help="development aid: run just this extra workload (e.g. stream_2160p8) and print it")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result: libraries that write banners to fd 1 (NCCL's version line, worker
     # processes) are sent to stderr for the duration of the run; emit() writes to the saved descriptor

@@ -353,6 +353,48 @@ def test_one_pu_kernels_every_size_full_window(hm, bd):
         hm.release_plane(idr)
 
 
+def test_one_pu_kernels_equal_round1_kernels(hm, monkeypatch):
+    """The same 1:1 calls through a second context created with HMB200_NO_ONE_FAST=1 (round 1's kernels: k_search_split +
+    finalize + k_frac_generic, D2H copy + stream synchronisation): vectors, SADs and refinement costs must be identical -
+    including sizes whose pattern travels in the kernel arguments and sizes that go through the record."""
+    W, H = 416, 240
+    f0, f1 = synth.luma_frame(W, H, 0, seed=66), synth.luma_frame(W, H, 1, seed=66)
+    ref, o0, stride = padded(f0)
+    rng = np.random.default_rng(4)
+    calls = []
+    for (w, h) in PU_SIZES[::3] + [(8, 8), (16, 16)]:
+        px, py = int(rng.integers(8, (W - w - 8) // 4)) * 4, int(rng.integers(4, (H - h - 8) // 4)) * 4
+        org = np.ascontiguousarray(f1[py:py + h, px:px + w].astype(np.int16))
+        pred = (int(rng.integers(-30, 31)), int(rng.integers(-30, 31)))
+        calls.append((org, w, h, o0 + py * stride + px, pred, int(rng.integers(100000, 6000000))))
+
+    def run_all():
+        idr = hm.register_plane(ref, W, H, MARGIN, MARGIN, 8)
+        try:
+            out = []
+            for org, w, h, roff, pred, lam in calls:
+                lt, rb = (-40 + (pred[0] >> 2), -40 + (pred[1] >> 2)), (40 + (pred[0] >> 2), 40 + (pred[1] >> 2))
+                both = hm.pattern_search_and_refine((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred, 8, FLAG_FEN | FLAG_HADME)
+                mv, sad = hm.pattern_search((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred, 8, FLAG_FEN)
+                fr = hm.pattern_search_frac((org, 0, w), w, h, (ref, roff, stride), mv, lam, pred, 8, FLAG_HADME)
+                assert both == (mv, sad) + fr
+                out.append(both)
+            return out
+        finally:
+            hm.release_plane(idr)
+
+    fast = run_all()
+    monkeypatch.setenv("HMB200_NO_ONE_FAST", "1")
+    ctx = hm.ctx_create(0)                       # the knob is read when a context is created; the new context is current
+    try:
+        slow = run_all()
+    finally:
+        hm.ctx_destroy(ctx)
+        hm.ctx_set_current(None)
+        monkeypatch.delenv("HMB200_NO_ONE_FAST")
+    assert fast == slow
+
+
 def test_error_behaviour(hm):
     from video_codecs_b200 import HMB200Error
     with pytest.raises(HMB200Error):

@@ -71,6 +71,7 @@ struct State {
   bool one_fast = true;                                // hmb200_one.cuh kernels + flag spin (HMB200_NO_ONE_FAST=1: round-1 path)
   std::vector<PoolBuf> pool;                           // released plane buffers, recycled by size (no malloc/free per frame)
   uint64_t launches = 0;
+  uint64_t pool_mallocs = 0, pool_frees = 0, pool_sync_frees = 0;   // HMB200_DEBUG_POOL: printed when the context goes away
   float last_total_ms = 0, last_search_ms = 0, last_frac_ms = 0;
 };
 
@@ -154,7 +155,25 @@ int make_plane(Plane& p, int width, int height, int mx, int my, int bit_depth) {
   if (!p.d.base && busy >= POOL_KEEP) {
     p.d.base = G.pool[oldest].base; p.ev_reuse = G.pool[oldest].ev_free; G.pool.erase(G.pool.begin() + oldest);
   }
-  if (!p.d.base) CUDA_TRY(cudaMalloc(&p.d.base, p.bytes));
+  if (!p.d.base) {
+    // A geometry the pool holds no buffer of (the first plane after a change of picture size / bit depth): this registration
+    // allocates anyway, so it is also the moment to drop the idle buffers of other geometries - never on the release path of a
+    // running pipeline, where a cudaFree would wait for the kernels in flight.
+    bool same = false;
+    for (auto& b : G.pool) same = same || b.bytes == p.bytes;
+    if (!same)
+      for (size_t i = 0; i < G.pool.size();) {
+        if (!G.pool[i].ev_free || cudaEventQuery(G.pool[i].ev_free) == cudaSuccess) {
+          give_event(G.pool[i].ev_free);
+          cudaFree(G.pool[i].base);
+          G.pool.erase(G.pool.begin() + i);
+          G.pool_frees++;
+        } else i++;
+      }
+    cudaGetLastError();
+    CUDA_TRY(cudaMalloc(&p.d.base, p.bytes));
+    G.pool_mallocs++;
+  }
   p.used = true;
   return HMB200_OK;
 }
@@ -301,6 +320,9 @@ static void teardown_state(State& st) {
     if (p.ev_reuse) cudaEventDestroy(p.ev_reuse);
   }
   st.planes.clear();
+  if (getenv("HMB200_DEBUG_POOL"))
+    fprintf(stderr, "[hmb200] plane pool: %llu mallocs, %llu frees of other geometries, %llu synchronising frees, %zu buffers held\n",
+            (unsigned long long)st.pool_mallocs, (unsigned long long)st.pool_frees, (unsigned long long)st.pool_sync_frees, st.pool.size());
   for (auto& b : st.pool) { cudaFree(b.base); if (b.ev_free) cudaEventDestroy(b.ev_free); }
   st.pool.clear();
   for (auto e : st.free_events) cudaEventDestroy(e);
@@ -725,6 +747,7 @@ void hmb200_release_plane(int plane_id) {
           if (G.pool[i].ev_free) { cudaEventSynchronize(G.pool[i].ev_free); give_event(G.pool[i].ev_free); }
           cudaFree(G.pool[i].base);
           G.pool.erase(G.pool.begin() + i);
+          G.pool_frees++;
           break;
         }
     }
@@ -739,6 +762,7 @@ void hmb200_release_plane(int plane_id) {
       cudaStreamSynchronize(G.up);
       cudaStreamSynchronize(G.stream);
       cudaFree(p->d.base);
+      G.pool_sync_frees++;
     }
   }
   give_event(p->ev_reuse);

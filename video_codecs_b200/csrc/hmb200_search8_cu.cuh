@@ -415,7 +415,9 @@ k_search8_cu(const S8Unit* __restrict__ units, const S8Bundle* __restrict__ bund
   uint8_t* s_org = s8_smem + un.org_smem_off;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  const bool use_map = (un.variant & 0x100) != 0;       // host: this unit's window has the geometry the launch's tensor map was built for
+  // host: this unit's window has the geometry the launch's tensor map was built for.  The CHILD kernel keeps the row copies: with
+  // the second staging path compiled in, its 14 k-instruction body ran 3 % slower (1304 -> 1343 us, profiles/r02_launches_final.txt)
+  const bool use_map = !CHILD && (un.variant & 0x100) != 0;
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();                                      // the initialised barrier is visible before its first use
   if (threadIdx.x == 0) mbar_expect_tx(&s_bar, (uint32_t)(un.ref_pitch * un.ref_rows + un.org_pitch * un.org_rows));
@@ -1055,6 +1057,7 @@ inline bool cu_build_schedule(const std::vector<SearchTask>& tasks, const std::v
     // instead of one bulk copy per row; flag 0x100 in the unit's variant word (read by the kernel only).  Only the unshifted copy
     // can come from the TMA unit: a box must start on a 16-byte boundary of the global row (tools/tma_probe.cu).
     for (int v = 0; v < CUV_COUNT; v++) {
+      if (variant_is_child(v)) continue;                 // see k_search8_cu: the child kernel stages row by row
       std::map<std::pair<int, int>, int> freq;
       for (int i = out->unit_first[v]; i < out->unit_first[v] + out->unit_count[v]; i++) {
         const S8Unit& u = units[(size_t)i];
