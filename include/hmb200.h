@@ -130,6 +130,11 @@ void* hmb200_host_alloc(size_t bytes);
 void  hmb200_host_free(void* p);
 /* Number of kernel launches issued by this library since init (bench.py's gpu_launches). */
 uint64_t hmb200_launch_count(void);
+/* 1:1 entries of the calling thread's context: hmb200_pattern_search_and_refine calls so far, how many of them launched a whole-CU
+ * search (a 2Nx2N PU: the CU's other partitions - 2NxN, Nx2N, AMP; TLibCommon/TComDataCU.cpp:1893-1931 - are searched and refined in
+ * the same round trip with that call's window, predictor and lambda), and how many were answered from such a launch because their
+ * window, predictor, lambda, flags, position and pattern samples were exactly those (HMB200_NO_SPECULATION=1 switches this off). */
+void hmb200_one_call_stats(uint64_t* calls, uint64_t* cu_launches, uint64_t* served_from_cu);
 
 /* ------------------------------------------------------------------ host-side window / job-list logic ---------- */
 

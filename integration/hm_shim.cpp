@@ -96,6 +96,12 @@ void die(const char* what) {
 void at_exit() {
   fprintf(stderr, "hmb200 shim: %llu integer searches, %llu fractional refinements (%llu of them served by the search's round trip), %llu plane uploads, %llu kernel launches, %.2f s inside the forwarders\n",
           g_shim.n_search, g_shim.n_frac, g_shim.n_frac_fused, g_shim.n_upload, (unsigned long long)hmb200_launch_count(), g_shim.seconds);
+  {
+    uint64_t calls = 0, cu_launches = 0, cu_served = 0;
+    hmb200_one_call_stats(&calls, &cu_launches, &cu_served);
+    fprintf(stderr, "hmb200 shim: %llu search+refinement calls: %llu launched a whole-CU search, %llu were answered from one\n",
+            (unsigned long long)calls, (unsigned long long)cu_launches, (unsigned long long)cu_served);
+  }
   if (g_shim.n_merge)
     fprintf(stderr, "hmb200 shim: %llu merge estimations (%llu candidates) through hmb200_merge_estimation_batch\n", g_shim.n_merge, g_shim.n_merge_cands);
   if (g_shim.table_period)

@@ -70,6 +70,7 @@ def _load():
     sig = {
         "hmb200_init": (i32, [i32]), "hmb200_shutdown": (None, []), "hmb200_last_error": (C.c_char_p, []),
         "hmb200_launch_count": (C.c_uint64, []),
+        "hmb200_one_call_stats": (None, [C.POINTER(C.c_uint64)] * 3),
         "hmb200_host_alloc": (vp, [C.c_size_t]), "hmb200_host_free": (None, [vp]),
         "hmb200_motion_lambda_cost": (u32, [C.c_double]),
         "hmb200_set_search_range": (None, [_Mv, i32, i32, i32, i32, i32, i32, i32, C.POINTER(_Mv), C.POINTER(_Mv)]),
@@ -185,6 +186,12 @@ class HMB200:
 
     def launch_count(self):
         return int(self.lib.hmb200_launch_count())
+
+    def one_call_stats(self):
+        """(hmb200_pattern_search_and_refine calls, whole-CU launches among them, calls answered from a whole-CU launch)."""
+        v = [C.c_uint64() for _ in range(3)]
+        self.lib.hmb200_one_call_stats(*[C.byref(x) for x in v])
+        return tuple(int(x.value) for x in v)
 
     # -- host logic ------------------------------------------------------------------------------------------------
     def motion_lambda_cost(self, lam):

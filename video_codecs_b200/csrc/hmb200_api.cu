@@ -46,7 +46,23 @@ constexpr int N_SIDE = 4;
 // layout of the per-call record of the 1:1 entries (host page-locked copy and device copy): offsets in bytes
 constexpr size_t ONE_KEY = 0, ONE_TICKET = 8, ONE_RESULT = 16, ONE_TASK = 64, ONE_TZ = 128, ONE_HEAD = 256;
 // the two 16-byte records the call's last kernel writes into mapped host memory (State::one_back, hmb200_one.cuh OneBack)
-constexpr size_t BACK_A = 0, BACK_B = 16, BACK_BYTES = 64;
+constexpr size_t BACK_A = 0, BACK_B = 16, BACK_CU = 64, BACK_BYTES = 4096;
+// after the pattern rows of the per-call record: argmin keys and integer results of a speculated CU's partitions (hmb200_one.cuh)
+constexpr size_t ONE_CU_KEYS = ONE_HEAD + 64 * 64 * sizeof(int16_t), ONE_CU_OUT = ONE_CU_KEYS + 128, ONE_DEV_BYTES = ONE_CU_OUT + 13 * 32;
+constexpr int CU_CACHE_ENTRIES = 8;                    // one per reference picture a PU loop walks over (BACK_CU + 8 * 13 * 32 <= BACK_BYTES)
+
+// What a speculated CU launch computed (hmb200_one.cuh, k_one_cu_search / k_one_cu_frac): every partition of the CU searched and
+// refined with the 2Nx2N call's window, predictor and lambda.  A later 1:1 call is served from it iff plane, position, window,
+// predictor, lambda, flags and the pattern SAMPLES are the ones the launch used.
+struct CuCacheEntry {
+  bool valid = false;
+  int plane = -1, rx = 0, ry = 0, S = 0, flags = 0;
+  int lt_x = 0, lt_y = 0, rb_x = 0, rb_y = 0, pred_x = 0, pred_y = 0;
+  uint32_t lambda = 0, seq = 0;
+  bool got[13] = {false};
+  hmb200_pu_result res[13];
+  int16_t pat[64 * 64];                                // the CU's original block, dense rows of S samples
+};
 
 struct State {
   bool ready = false;
@@ -69,6 +85,10 @@ struct State {
   char* one_back = nullptr;                            // mapped page-locked: the call's last kernel stores result + sequence number here
   uint32_t one_seq = 0;
   bool one_fast = true;                                // hmb200_one.cuh kernels + flag spin (HMB200_NO_ONE_FAST=1: round-1 path)
+  bool speculate = true;                               // a 2Nx2N call searches the CU's other partitions too (HMB200_NO_SPECULATION=1: off)
+  std::vector<CuCacheEntry> cu_cache;
+  int cu_cache_next = 0;
+  uint64_t one_calls = 0, cu_launches = 0, cu_hits = 0;
   std::vector<PoolBuf> pool;                           // released plane buffers, recycled by size (no malloc/free per frame)
   uint64_t launches = 0;
   uint64_t pool_mallocs = 0, pool_frees = 0, pool_sync_frees = 0;   // HMB200_DEBUG_POOL: printed when the context goes away
@@ -128,6 +148,7 @@ int alloc_plane_slot() {
 }
 
 int make_plane(Plane& p, int width, int height, int mx, int my, int bit_depth) {
+  for (auto& e : G.cu_cache) e.valid = false;          // a plane id / host range may now mean other samples
   int bps = bit_depth > 8 ? 2 : 1;
   int total_w = width + 2 * mx, total_h = height + 2 * my;
   int pitch_bytes = ((total_w * bps + 127) / 128) * 128;
@@ -374,7 +395,7 @@ static int init_state_body(State& st, int device) {
   st.ready = true;
   // pattern buffer for the 1:1 entries: 64x64 int16, no margins
   st.pattern = Plane();
-  CUDA_TRY(cudaMalloc((void**)&st.one_dev, ONE_HEAD + 64 * 64 * sizeof(int16_t)));
+  CUDA_TRY(cudaMalloc((void**)&st.one_dev, ONE_DEV_BYTES));
   CUDA_TRY(cudaMallocHost((void**)&st.one_host, ONE_HEAD + 64 * 64 * sizeof(int16_t)));
   CUDA_TRY(cudaHostAlloc((void**)&st.one_back, BACK_BYTES, cudaHostAllocMapped));
   memset(st.one_back, 0, BACK_BYTES);
@@ -382,7 +403,16 @@ static int init_state_body(State& st, int device) {
     // argmin key = ~0, ticket = 0: the state k_one_search leaves behind after every call
     unsigned long long init[2] = {~0ull, 0ull};
     CUDA_TRY(cudaMemcpy(st.one_dev + ONE_KEY, init, sizeof(init), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(st.one_dev + ONE_CU_KEYS, 0xff, 128));
   }
+  st.speculate = st.one_fast && getenv("HMB200_NO_SPECULATION") == nullptr;
+  st.cu_cache.assign(CU_CACHE_ENTRIES, CuCacheEntry());
+  st.cu_cache_next = 0;
+  st.one_calls = st.cu_launches = st.cu_hits = 0;
+  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search_args<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search_args<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
   st.one_seq = 0;
   st.one_fast = getenv("HMB200_NO_ONE_FAST") == nullptr;
   CUDA_TRY(cudaFuncSetAttribute(k_one_search<true, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
@@ -736,6 +766,7 @@ int hmb200_read_plane(int plane_id, int16_t* dst_origin, int dst_stride) {
 }
 
 void hmb200_release_plane(int plane_id) {
+  for (auto& e : G.cu_cache) e.valid = false;
   Plane* p = get_plane(plane_id);            // also orders a still pending upload of this plane before the compute stream's tail
   if (!p) return;
   if (p->d.base) {
@@ -1488,30 +1519,10 @@ static OneBack next_one_back() {
   if (G.one_seq == 0) G.one_seq = 1;
   return OneBack{reinterpret_cast<uint4*>(G.one_back + BACK_A), reinterpret_cast<uint4*>(G.one_back + BACK_B), G.one_seq};
 }
+static int wait_records(volatile uint32_t* a, volatile uint32_t* b, uint32_t seq, hmb200_pu_result* io);
 static int wait_one_back(const OneBack& back, hmb200_pu_result* io) {
   CUDA_TRY(cudaGetLastError());                                   // a failed launch would never report
-  volatile uint32_t* a = reinterpret_cast<volatile uint32_t*>(G.one_back + BACK_A);
-  volatile uint32_t* b = reinterpret_cast<volatile uint32_t*>(G.one_back + BACK_B);
-  for (uint64_t spins = 1; a[3] != back.seq || b[3] != back.seq; spins++) {
-    if ((spins & 0x3fff) == 0) {                                  // every ~16k polls: has the stream failed or finished without reporting?
-      const cudaError_t e = cudaStreamQuery(G.stream);
-      if (e == cudaSuccess) {
-        if (a[3] != back.seq || b[3] != back.seq) return fail(HMB200_ERR_CUDA, "1:1 call: the stream finished without reporting a result");
-        break;
-      }
-      if (e != cudaErrorNotReady) return fail(HMB200_ERR_CUDA, std::string("1:1 call: ") + cudaGetErrorString(e));
-    }
-#if defined(__x86_64__) || defined(__i386__)
-    __builtin_ia32_pause();
-#endif
-  }
-  std::atomic_thread_fence(std::memory_order_acquire);
-  const uint32_t fr = b[0];
-  io->mv_x = (int32_t)a[0]; io->mv_y = (int32_t)a[1]; io->sad = a[2];
-  io->half_x = (int8_t)(fr & 0xff); io->half_y = (int8_t)((fr >> 8) & 0xff);
-  io->qter_x = (int8_t)((fr >> 16) & 0xff); io->qter_y = (int8_t)((fr >> 24) & 0xff);
-  io->frac_cost = b[1];
-  return HMB200_OK;
+  return wait_records(reinterpret_cast<volatile uint32_t*>(G.one_back + BACK_A), reinterpret_cast<volatile uint32_t*>(G.one_back + BACK_B), back.seq, io);
 }
 // a PU of up to 16x16 samples as a kernel argument (dense rows); *fits_u8 as in stage_one_call
 static int fill_one_pattern(const hmb200_pattern* key, OnePattern* pat, bool* fits_u8) {
@@ -1649,6 +1660,140 @@ int hmb200_pattern_search(const hmb200_pattern* key, const int16_t* ref_at_pu, i
   return HMB200_OK;
 }
 
+// waits for the two 16-byte records at a / b to show seq (see wait_one_back)
+static int wait_records(volatile uint32_t* a, volatile uint32_t* b, uint32_t seq, hmb200_pu_result* io) {
+  for (uint64_t spins = 1; a[3] != seq || b[3] != seq; spins++) {
+    if ((spins & 0x3fff) == 0) {
+      const cudaError_t e = cudaStreamQuery(G.stream);
+      if (e == cudaSuccess) {
+        if (a[3] != seq || b[3] != seq) return fail(HMB200_ERR_CUDA, "1:1 call: the stream finished without reporting a result");
+        break;
+      }
+      if (e != cudaErrorNotReady) return fail(HMB200_ERR_CUDA, std::string("1:1 call: ") + cudaGetErrorString(e));
+    }
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  const uint32_t fr = b[0];
+  io->mv_x = (int32_t)a[0]; io->mv_y = (int32_t)a[1]; io->sad = a[2];
+  io->half_x = (int8_t)(fr & 0xff); io->half_y = (int8_t)((fr >> 8) & 0xff);
+  io->qter_x = (int8_t)((fr >> 16) & 0xff); io->qter_y = (int8_t)((fr >> 24) & 0xff);
+  io->frac_cost = b[1];
+  return HMB200_OK;
+}
+
+// The speculative CU path of hmb200_pattern_search_and_refine (see CuCacheEntry).  *served: *io holds the call's answer.
+static int cu_speculation(const hmb200_pattern* key, const int16_t* ref_at_pu, const SearchTask& proto, int flags, hmb200_pu_result* io,
+                          bool* served) {
+  *served = false;
+  int rx, ry;
+  Plane* pr = find_plane_by_host(ref_at_pu, &rx, &ry);
+  if (!pr || !key->roi || key->bit_depth != 8 || pr->d.bytes_per_sample != 1 || pr->d.bit_depth != 8 || !supported_pu(key->width, key->height))
+    return HMB200_OK;                                   // the per-PU path handles (or rejects) it
+  const int plane = (int)(pr - &G.planes[0]);
+  const int w = key->width, h = key->height;
+  // 1. an answer computed by an earlier CU launch?
+  for (int ei = 0; ei < (int)G.cu_cache.size(); ei++) {
+    CuCacheEntry& e = G.cu_cache[ei];
+    if (!e.valid || e.plane != plane || e.flags != flags || e.lt_x != proto.lt_x || e.lt_y != proto.lt_y || e.rb_x != proto.rb_x ||
+        e.rb_y != proto.rb_y || e.pred_x != proto.pred_x || e.pred_y != proto.pred_y || e.lambda != proto.lambda_cost) continue;
+    const int dx = rx - e.rx, dy = ry - e.ry;
+    if (dx < 0 || dy < 0 || dx + w > e.S || dy + h > e.S) continue;
+    int part = -1;
+    for (int p = 0; p < one_cu_pus(e.S) && part < 0; p++) {
+      int ox, oy, pw, ph;
+      one_cu_part(e.S, p, &ox, &oy, &pw, &ph);
+      if (ox == dx && oy == dy && pw == w && ph == h) part = p;
+    }
+    if (part < 0) continue;
+    bool same = true;
+    for (int y = 0; y < h && same; y++)
+      same = memcmp(key->roi + (ptrdiff_t)y * key->stride, e.pat + (size_t)(dy + y) * e.S + dx, (size_t)w * sizeof(int16_t)) == 0;
+    if (!same) continue;
+    if (!e.got[part]) {
+      volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(G.one_back + BACK_CU + ((size_t)ei * ONE_CU_MAX_PUS + part) * 32);
+      const int rc = wait_records(slot, slot + 4, e.seq, &e.res[part]);
+      if (rc != HMB200_OK) return rc;
+      e.got[part] = true;
+    }
+    *io = e.res[part];
+    *served = true;
+    G.cu_hits++;
+    return HMB200_OK;
+  }
+  // 2. a 2Nx2N PU: search and refine the whole CU's partitions with this call's window, predictor and lambda
+  if (w != h || (w != 8 && w != 16 && w != 32 && w != 64)) return HMB200_OK;
+  const int S = w;
+  SearchTask t = proto;
+  t.org_x = 0; t.org_y = 0; t.ref_x = rx; t.ref_y = ry; t.w = S; t.h = S;
+  if (!box_inside(pr->d, Box{rx + t.lt_x - FRAC_REACH, ry + t.lt_y - FRAC_REACH, rx + t.rb_x + S + FRAC_REACH, ry + t.rb_y + S + FRAC_REACH}))
+    return HMB200_OK;                                   // run_single reports the error
+  const int fen = (flags & HMB200_FLAG_FEN) ? 1 : 0, had = (flags & HMB200_FLAG_HADME) ? 1 : 0;
+  const int nx = t.rb_x - t.lt_x + 1, ny = t.rb_y - t.lt_y + 1;
+  const int rows = (S == 64 && fen) ? S / 2 : S;
+  const int col0 = rx + pr->d.margin_x + t.lt_x;
+  const int smem = rows * one_search_row_bytes(true, col0, nx, S) + rows * S;
+  if (smem > ONE_SMEM_MAX) return HMB200_OK;
+  const int ei = G.cu_cache_next;
+  CuCacheEntry& e = G.cu_cache[ei];
+  e.valid = false;
+  int all = 0;
+  for (int y = 0; y < S; y++) {
+    const int16_t* src = key->roi + (ptrdiff_t)y * key->stride;
+    int16_t* dst = e.pat + (size_t)y * S;
+    for (int x = 0; x < S; x++) { dst[x] = src[x]; all |= src[x]; }
+  }
+  if (all & ~0xff) return HMB200_OK;                    // e.g. the signed bi-prediction pattern: per-PU path
+  get_plane(plane);                                     // orders a pending upload of the plane before this call's kernels
+  const OneBack first = next_one_back();
+  OneBack back = first;
+  back.host_a = reinterpret_cast<uint4*>(G.one_back + BACK_CU + (size_t)ei * ONE_CU_MAX_PUS * 32);
+  back.host_b = back.host_a + 1;
+  unsigned long long* d_keys = reinterpret_cast<unsigned long long*>(G.one_dev + ONE_CU_KEYS);
+  uint32_t* d_ticket = reinterpret_cast<uint32_t*>(G.one_dev + ONE_TICKET);
+  hmb200_pu_result* d_out = reinterpret_cast<hmb200_pu_result*>(G.one_dev + ONE_CU_OUT);
+  const int np = one_cu_pus(S);
+  if (S <= 16) {
+    OnePattern arg;
+    memcpy(arg.px, e.pat, (size_t)S * S * sizeof(int16_t));
+    if (S == 8) k_one_cu_search_args<8><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, arg, d_keys, d_ticket, d_out, pr->d);
+    else        k_one_cu_search_args<16><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, arg, d_keys, d_ticket, d_out, pr->d);
+    k_one_cu_frac_args<<<np, S == 8 ? 128 : 288, one_frac_smem(S, S), G.stream>>>(t, S, arg, d_out, pr->d, had, back);
+  } else {
+    char* hrec = G.one_host;
+    memcpy(hrec + ONE_HEAD, e.pat, (size_t)S * S * sizeof(int16_t));
+    CUDA_TRY(cudaMemcpyAsync(G.one_dev + ONE_HEAD, hrec + ONE_HEAD, (size_t)S * S * sizeof(int16_t), cudaMemcpyHostToDevice, G.stream));
+    const int16_t* d_pat = reinterpret_cast<const int16_t*>(G.one_dev + ONE_HEAD);
+    if (S == 32) k_one_cu_search<32><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, d_keys, d_ticket, d_out, d_pat, pr->d);
+    else         k_one_cu_search<64><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, d_keys, d_ticket, d_out, d_pat, pr->d);
+    k_one_cu_frac<<<np, ONE_FRAC_THREADS_MAX, one_frac_smem(S, S), G.stream>>>(t, S, d_pat, d_out, pr->d, had, back);
+  }
+  G.launches += 2;
+  G.cu_launches++;
+  CUDA_TRY(cudaGetLastError());
+  e.plane = plane; e.rx = rx; e.ry = ry; e.S = S; e.flags = flags;
+  e.lt_x = t.lt_x; e.lt_y = t.lt_y; e.rb_x = t.rb_x; e.rb_y = t.rb_y; e.pred_x = t.pred_x; e.pred_y = t.pred_y; e.lambda = t.lambda_cost;
+  e.seq = first.seq;
+  for (auto& g : e.got) g = false;
+  volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(back.host_a);
+  const int rc = wait_records(slot, slot + 4, e.seq, &e.res[0]);
+  if (rc != HMB200_OK) return rc;
+  e.got[0] = true;
+  e.valid = true;
+  G.cu_cache_next = (ei + 1) % (int)G.cu_cache.size();
+  *io = e.res[0];
+  *served = true;
+  return HMB200_OK;
+}
+
+void hmb200_one_call_stats(uint64_t* calls, uint64_t* cu_launches, uint64_t* served_from_cu) {
+  if (calls) *calls = G.one_calls;
+  if (cu_launches) *cu_launches = G.cu_launches;
+  if (served_from_cu) *served_from_cu = G.cu_hits;
+}
+
 int hmb200_pattern_search_and_refine(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride, hmb200_mv lt, hmb200_mv rb,
                                      const hmb200_cost_state* cs, int flags, hmb200_mv* mv_out, uint32_t* sad_out, hmb200_mv* half_out,
                                      hmb200_mv* qter_out, uint32_t* frac_cost_out) {
@@ -1661,8 +1806,12 @@ int hmb200_pattern_search_and_refine(const hmb200_pattern* key, const int16_t* r
   t.lambda_cost = cs->lambda_cost;
   t.sub_shift = ((flags & HMB200_FLAG_FEN) && key->height > 8) ? 1 : 0;
   hmb200_pu_result r{};
-  int rc = run_single(key, ref_at_pu, t, (flags & (HMB200_FLAG_FEN | HMB200_FLAG_HADME)) | HMB200_FLAG_FRAC, true, &r);
+  const int f = (flags & (HMB200_FLAG_FEN | HMB200_FLAG_HADME)) | HMB200_FLAG_FRAC;
+  G.one_calls++;
+  bool served = false;
+  int rc = G.speculate ? cu_speculation(key, ref_at_pu, t, f, &r, &served) : HMB200_OK;
   if (rc != HMB200_OK) return rc;
+  if (!served && (rc = run_single(key, ref_at_pu, t, f, true, &r)) != HMB200_OK) return rc;
   mv_out->x = r.mv_x; mv_out->y = r.mv_y; *sad_out = r.sad;
   half_out->x = r.half_x; half_out->y = r.half_y; qter_out->x = r.qter_x; qter_out->y = r.qter_y; *frac_cost_out = r.frac_cost;
   return HMB200_OK;

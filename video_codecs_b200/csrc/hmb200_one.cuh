@@ -128,10 +128,10 @@ __device__ __forceinline__ void one_frac_tiles(const int16_t* __restrict__ s_hor
 __host__ __device__ inline int one_frac_smem(int w, int h) { return ((w + 8) * (h + 8) + 3 * (h + 8) * w + w * h) * 2; }
 
 // xPatternSearchFracDIF of the PU at res.mv_x / mv_y, by every thread of the calling CTA (blockDim.x a multiple of 32); fills
-// res.half_*, res.qter_*, res.frac_cost in every thread.  pattern: dense int16 rows (pitch = w).
+// res.half_*, res.qter_*, res.frac_cost in every thread.  pattern: int16 rows, pattern_pitch samples apart (0: dense, pitch = w).
 template <typename RefT>
 __device__ __forceinline__ void one_frac_body(const SearchTask& t, hmb200_pu_result& res, const int16_t* __restrict__ pattern,
-                                              const DevPlane& ref_plane, int use_had, int16_t* smem16) {
+                                              const DevPlane& ref_plane, int use_had, int16_t* smem16, int pattern_pitch = 0) {
   const int W = t.w, H = t.h, RW = W + 8, RH = H + 8;
   int16_t* s_ref = smem16;                                  // [H+8][W+8], origin at (-4,-4) of the MC block
   int16_t* s_hor = s_ref + RW * RH;                         // [3][H+8][W]
@@ -148,7 +148,8 @@ __device__ __forceinline__ void one_frac_body(const SearchTask& t, hmb200_pu_res
     const int r = i / RW, c = i - r * RW;
     s_ref[i] = (int16_t)ref[(ptrdiff_t)(mvy + r - 4) * ref_stride + (mvx + c - 4)];
   }
-  for (int i = threadIdx.x; i < W * H; i += blockDim.x) s_org[i] = pattern[i];
+  if (pattern_pitch == 0) pattern_pitch = W;              // dense rows unless the PU is a part of a larger block (one_cu_*)
+  for (int i = threadIdx.x; i < W * H; i += blockDim.x) { const int r = i / W; s_org[i] = pattern[r * pattern_pitch + (i - r * W)]; }
   const int n = (!use_had) ? 4 : ((W % 8 == 0 && H % 8 == 0) ? 8 : 4);   // tile edge
 
   int base_qx = 0, base_qy = 0;            // 2*half after stage 1
@@ -357,6 +358,202 @@ __global__ void __launch_bounds__(ONE_SEARCH_THREADS_MAX)
 k_one_search_args(const SearchTask t, hmb200_pu_result seed, const __grid_constant__ OnePattern pat, unsigned long long* __restrict__ key,
                   uint32_t* __restrict__ ticket, DevPlane ref_plane, int fuse, OneBack back) {
   one_search_body<BYTES, RefT>(t, seed, key, ticket, nullptr, pat.px, ref_plane, fuse, back);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One CU per call: when HM asks for the 2Nx2N PU of a CU, the other partitions of that CU (2NxN, Nx2N and the four AMP
+// splits: 13 PUs, 5 for an 8x8 CU; TLibCommon/TComDataCU.cpp:1893-1931) are searched and refined in the same round trip
+// with the 2Nx2N call's window, predictor and lambda.  The host keeps the answers and serves the following calls from them
+// when - and only when - their window, predictor, lambda, flags, position and pattern samples are the ones used here
+// (hmb200_api.cu, CuCache): exact, and HM's decision order is untouched.  In the 1080p I + P test clip 161,706 of the
+// 180,580 non-2Nx2N calls qualify (profiles/r02_latency_1to1.txt).
+//
+// Every partition is a union of cells of a 4 x 4 grid over the CU (2 x 2 for an 8x8 CU), so a candidate's 13 SADs come
+// from 16 cell sums - kept apart for even and odd rows, because under FEN a PU taller than 8 rows counts its even rows
+// twice and a shorter one counts all rows (TEncSearch.cpp:3804-3810; PU offsets are multiples of 4, so PU-relative and
+// CU-relative row parity agree).  8-bit planes and patterns only (VABSDIFF4); anything else takes the per-PU path.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int ONE_CU_MAX_PUS = 13;
+__host__ __device__ inline int one_cu_pus(int S) { return S == 8 ? 5 : 13; }
+// partition p of an S x S CU: offset and size
+__host__ __device__ inline void one_cu_part(int S, int p, int* ox, int* oy, int* w, int* h) {
+  const int H2 = S / 2, Q = S / 4;
+  int x = 0, y = 0, ww = S, hh = S;
+  switch (p) {
+    case 0: break;
+    case 1: hh = H2; break;                 case 2: y = H2; hh = H2; break;              // 2NxN
+    case 3: ww = H2; break;                 case 4: x = H2; ww = H2; break;              // Nx2N
+    case 5: hh = Q; break;                  case 6: y = Q; hh = S - Q; break;            // 2NxnU
+    case 7: hh = S - Q; break;              case 8: y = S - Q; hh = Q; break;            // 2NxnD
+    case 9: ww = Q; break;                  case 10: x = Q; ww = S - Q; break;           // nLx2N
+    case 11: ww = S - Q; break;             default: x = S - Q; ww = Q; break;           // nRx2N
+  }
+  *ox = x; *oy = y; *w = ww; *h = hh;
+}
+
+// key[p] / ticket as in one_search_body; out[p]: (rcMv, ruiSAD) of partition p.  t: the 2Nx2N task (w = h = S); fen: FLAG_FEN.
+template <int S>
+__device__ __forceinline__ void one_cu_search_body(const SearchTask& t, int fen, unsigned long long* __restrict__ keys, uint32_t* __restrict__ ticket,
+                                                   hmb200_pu_result* __restrict__ out, const int16_t* __restrict__ pattern, const DevPlane& ref_plane) {
+  constexpr int NB = (S == 8) ? 2 : 4;           // cells per CU edge
+  constexpr int BS = S / NB;                     // cell edge in samples (4, 4, 8, 16)
+  constexpr int BW = BS / 4;                     // ... in 32-bit words
+  constexpr int WW = S / 4;
+  constexpr int NP = (S == 8) ? 5 : 13;
+  extern __shared__ __align__(16) uint8_t one_smem[];
+  __shared__ unsigned long long s_best[NP][ONE_SEARCH_THREADS_MAX / 32];
+  __shared__ int s_last;
+  const int nx = t.rb_x - t.lt_x + 1;
+  const bool odd_rows = !(S == 64 && fen);       // a 64x64 CU under FEN has no PU that reads odd rows
+  const int step = odd_rows ? 1 : 2, rows = S / step;
+  const int cy = blockIdx.x, y = t.lt_y + cy;
+  const int col0 = t.ref_x + ref_plane.margin_x + t.lt_x;
+  const int row0 = t.ref_y + ref_plane.margin_y + y;
+  const int rp = one_search_row_bytes(true, col0, nx, S);
+  uint8_t* s_org8 = one_smem + rows * rp;
+  {
+    const int nvec = rp / 16 - 1, vec0 = col0 >> 4;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(ref_plane.base);
+    for (int i = threadIdx.x; i < rows * (nvec + 1); i += blockDim.x) {
+      const int r = i / (nvec + 1), v = i - r * (nvec + 1);
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (v < nvec && (vec0 + v) * 16 < ref_plane.pitch)
+        q = *reinterpret_cast<const uint4*>(base + (size_t)(row0 + r * step) * ref_plane.pitch + (size_t)(vec0 + v) * 16);
+      *reinterpret_cast<uint4*>(one_smem + r * rp + v * 16) = q;
+    }
+    for (int i = threadIdx.x; i < rows * S; i += blockDim.x) {
+      const int r = i / S, c = i - r * S;
+      s_org8[i] = (uint8_t)pattern[(r * step) * S + c];
+    }
+  }
+  __syncthreads();
+  unsigned long long best[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) best[p] = ~0ull;
+  const uint32_t* org32 = reinterpret_cast<const uint32_t*>(s_org8);
+  for (int cx = threadIdx.x; cx < nx; cx += blockDim.x) {
+    const int b = (col0 & 15) + cx, sh = (b & 3) * 8;
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(one_smem) + (b >> 2);
+    uint32_t ce[NB][NB], co[NB][NB];             // cell sums over even / odd rows
+#pragma unroll
+    for (int i = 0; i < NB; i++)
+#pragma unroll
+      for (int j = 0; j < NB; j++) { ce[i][j] = 0; co[i][j] = 0; }
+#pragma unroll
+    for (int rb = 0; rb < NB; rb++) {
+#pragma unroll 1
+      for (int rr = 0; rr < BS; rr += 2) {
+#pragma unroll
+        for (int par = 0; par < 2; par++) {
+          if (par == 1 && !odd_rows) continue;
+          const int r = (rb * BS + rr + par) / step;                    // staged row index
+          const uint32_t* q = row + r * (rp / 4);
+          const uint32_t* o = org32 + r * WW;
+          uint32_t lo = q[0];
+#pragma unroll
+          for (int g = 0; g < WW; g++) {
+            const uint32_t hi = q[g + 1];
+            const uint32_t v = __funnelshift_r(lo, hi, sh);
+            if (par == 0) ce[rb][g / BW] = sad4_acc(v, o[g], ce[rb][g / BW]);
+            else          co[rb][g / BW] = sad4_acc(v, o[g], co[rb][g / BW]);
+            lo = hi;
+          }
+        }
+      }
+    }
+    const int x = t.lt_x + cx;
+    const uint32_t mvc = mv_cost(t.lambda_cost, mv_bits(x, y, t.pred_x, t.pred_y, 2));
+    const uint32_t idx = (uint32_t)(cy * nx + cx);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      int ox, oy, w, h;
+      one_cu_part(S, p, &ox, &oy, &w, &h);
+      uint32_t e = 0, od = 0;
+#pragma unroll
+      for (int i = 0; i < NB; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++)
+          if (i * BS >= oy && i * BS < oy + h && j * BS >= ox && j * BS < ox + w) { e += ce[i][j]; od += co[i][j]; }
+      const uint32_t sad = (fen && h > 8) ? (e << 1) : (e + od);
+      const unsigned long long k = make_key(sad + mvc, idx);
+      best[p] = k < best[p] ? k : best[p];
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    unsigned long long v = best[p];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+      v = other < v ? other : v;
+    }
+    if ((threadIdx.x & 31) == 0) s_best[p][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NP) {
+    unsigned long long v = s_best[threadIdx.x][0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = s_best[threadIdx.x][w] < v ? s_best[threadIdx.x][w] : v;
+    atomicMin(&keys[threadIdx.x], v);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x < NP) {
+    __threadfence();
+    const unsigned long long k = atomicExch(&keys[threadIdx.x], ~0ull);
+    const uint32_t idx = (uint32_t)(k & 0xffffffffu), cost = (uint32_t)(k >> 32);
+    const int by = idx / nx, bx = idx - by * nx;
+    hmb200_pu_result r;
+    r.mv_x = t.lt_x + bx; r.mv_y = t.lt_y + by;
+    r.sad = cost - mv_cost(t.lambda_cost, mv_bits(r.mv_x, r.mv_y, t.pred_x, t.pred_y, 2));
+    r.half_x = r.half_y = r.qter_x = r.qter_y = 0; r.frac_cost = 0;
+    out[threadIdx.x] = r;
+  }
+  if (threadIdx.x == 0) *ticket = 0;
+}
+
+template <int S>
+__global__ void __launch_bounds__(ONE_SEARCH_THREADS_MAX)
+k_one_cu_search(const SearchTask t, int fen, unsigned long long* __restrict__ keys, uint32_t* __restrict__ ticket, hmb200_pu_result* __restrict__ out,
+                const int16_t* __restrict__ pattern, DevPlane ref_plane) {
+  one_cu_search_body<S>(t, fen, keys, ticket, out, pattern, ref_plane);
+}
+template <int S>
+__global__ void __launch_bounds__(ONE_SEARCH_THREADS_MAX)
+k_one_cu_search_args(const SearchTask t, int fen, const __grid_constant__ OnePattern pat, unsigned long long* __restrict__ keys,
+                     uint32_t* __restrict__ ticket, hmb200_pu_result* __restrict__ out, DevPlane ref_plane) {
+  one_cu_search_body<S>(t, fen, keys, ticket, out, pat.px, ref_plane);
+}
+
+// refinement of every partition: CTA p refines partition p at the vector k_one_cu_search left in out[p] and reports to host slot p
+// (two 16-byte records, 32 bytes per slot)
+template <bool ARGS>
+__device__ __forceinline__ void one_cu_frac_body(const SearchTask& t, int S, const int16_t* __restrict__ pattern, hmb200_pu_result* __restrict__ out,
+                                                 const DevPlane& ref_plane, int use_had, const OneBack& back) {
+  extern __shared__ __align__(16) int16_t one_smem16[];
+  const int p = blockIdx.x;
+  int ox, oy, w, h;
+  one_cu_part(S, p, &ox, &oy, &w, &h);
+  SearchTask tp = t;
+  tp.ref_x += ox; tp.ref_y += oy; tp.w = w; tp.h = h;
+  hmb200_pu_result res = out[p];
+  one_frac_body<uint8_t>(tp, res, pattern + oy * S + ox, ref_plane, use_had, one_smem16, S);
+  if (threadIdx.x == 0) {
+    OneBack slot = back;
+    slot.host_a = back.host_a + 2 * p; slot.host_b = back.host_a + 2 * p + 1;
+    one_report(slot, res);
+  }
+}
+__global__ void __launch_bounds__(ONE_FRAC_THREADS_MAX)
+k_one_cu_frac(const SearchTask t, int S, const int16_t* __restrict__ pattern, hmb200_pu_result* __restrict__ out, DevPlane ref_plane, int use_had, OneBack back) {
+  one_cu_frac_body<false>(t, S, pattern, out, ref_plane, use_had, back);
+}
+__global__ void __launch_bounds__(ONE_FRAC_THREADS_MAX)
+k_one_cu_frac_args(const SearchTask t, int S, const __grid_constant__ OnePattern pat, hmb200_pu_result* __restrict__ out, DevPlane ref_plane, int use_had,
+                   OneBack back) {
+  one_cu_frac_body<true>(t, S, pat.px, out, ref_plane, use_had, back);
 }
 
 // ends a call whose last kernel is one of the older ones (TZ search without refinement): one thread reports the record
