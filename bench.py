@@ -789,6 +789,9 @@ def measure_one_pu_calls(env, calls=1000):
     off = (512 + M) * stride + 960 + M
     out = {"calls_per_point": calls, "unit": "us per call (synchronous, incl. ~4 us of ctypes)", "rows": []}
 
+    import itertools
+    tick = itertools.count(1)
+
     def timed(fn):
         for _ in range(30):
             fn()
@@ -808,12 +811,36 @@ def measure_one_pu_calls(env, calls=1000):
                 "pu": f"{w}x{h}",
                 "search": timed(lambda: hm.pattern_search(org, w, h, rf, (-64, -64), (64, 64), LAMBDA_COST, (0, 0))),
                 "refine": timed(lambda: hm.pattern_search_frac(org, w, h, rf, mv, LAMBDA_COST, (0, 0))),
-                "search_and_refine": timed(lambda: hm.pattern_search_and_refine(org, w, h, rf, (-64, -64), (64, 64), LAMBDA_COST, (0, 0)))})
+                # a new lambda per call: an identical repeat would be answered from the previous call's whole-CU launch
+                "search_and_refine_2Nx2N": timed(lambda: hm.pattern_search_and_refine(org, w, h, rf, (-64, -64), (64, 64),
+                                                                                      LAMBDA_COST + next(tick), (0, 0)))})
+        # HM's call order for a CU: the 2Nx2N PU, then 2NxN / Nx2N / the AMP splits with the same window, predictor and lambda (what 90 %
+        # of the non-2Nx2N calls of the 1080p test clip look like); lambda changes per repetition so that every 2Nx2N call launches
+        out["cu_sequences"] = []
+        for S in (8, 16, 32, 64):
+            q, hf = S // 4, S // 2
+            parts = [(0, 0, S, S), (0, 0, S, hf), (0, hf, S, hf), (0, 0, hf, S), (hf, 0, hf, S)]
+            if S > 8:
+                parts += [(0, 0, S, q), (0, q, S, S - q), (0, 0, S, S - q), (0, S - q, S, q), (0, 0, q, S), (q, 0, S - q, S),
+                          (0, 0, S - q, S), (S - q, 0, q, S)]
+            cu = np.ascontiguousarray(cur[512 + M:512 + M + S, 960 + M:960 + M + S])
+            reps = max(20, calls // 10)
+            c0 = hm.one_call_stats()
+            t0 = time.perf_counter()
+            for k in range(reps):
+                for (ox, oy, w, h) in parts:
+                    hm.pattern_search_and_refine((cu, oy * S + ox, S), w, h, (ref, off + oy * stride + ox, stride), (-64, -64), (64, 64),
+                                                 LAMBDA_COST + k, (0, 0))
+            dt = time.perf_counter() - t0
+            c1 = hm.one_call_stats()
+            out["cu_sequences"].append({"cu": f"{S}x{S}", "pus": len(parts), "us_per_cu": 1e6 * dt / reps, "us_per_pu": 1e6 * dt / reps / len(parts),
+                                        "calls": c1[0] - c0[0], "whole_cu_launches": c1[1] - c0[1], "answered_from_cu_launch": c1[2] - c0[2]})
     finally:
         hm.release_plane(idr)
     out["note"] = ("kernels of hmb200_one.cuh: one launch per call for PUs up to 16x16 (pattern in the kernel arguments, the search's last "
                    "CTA refines), result as two 16-byte records in mapped host memory; round-trip floor of one trivial launch: 7.2 us "
-                   "(profiles/r02_latency_1to1.txt)")
+                   "(profiles/r02_latency_1to1.txt).  rows: one square PU; search_and_refine_2Nx2N searches and refines the whole CU; cu_sequences: "
+                   "a CU's partitions in HM's order, the 2Nx2N call searches and refines all of them, the others are answered from it")
     return out
 
 

@@ -4,7 +4,8 @@
 
 Prints microseconds per call of hmb200_pattern_search / hmb200_pattern_search_frac / hmb200_pattern_search_and_refine for one
 PU at the centre of a 1080p plane, +-64 window, FEN + Hadamard, and of the cheapest possible round trip (a 4x4 SAD through
-hmb200_dist).  ctypes adds ~2 us per call.  Needs a GPU."""
+hmb200_dist).  ctypes adds ~4 us per call.  A search_and_refine call for a square PU searches the whole CU (DESIGN.md 3.3b);
+HMB200_NO_SPECULATION=1 times the per-PU path for those sizes.  Needs a GPU."""
 import argparse
 import json
 import os
@@ -33,6 +34,9 @@ def main():
     lam = int(np.floor(65536.0 * np.sqrt(0.4624 * 2 ** ((35 - 12) / 3.0))))
     out = {}
 
+    import itertools
+    tick = itertools.count(1)
+
     def timed(fn):
         for _ in range(50):
             fn()
@@ -50,7 +54,8 @@ def main():
         out[f"{w}x{h}"] = {
             "search": timed(lambda: hm.pattern_search(org, w, h, rf, (-64, -64), (64, 64), lam, (0, 0))),
             "frac": timed(lambda: hm.pattern_search_frac(org, w, h, rf, mv, lam, (0, 0))),
-            "search_and_refine": timed(lambda: hm.pattern_search_and_refine(org, w, h, rf, (-64, -64), (64, 64), lam, (0, 0))),
+            # a new lambda per call: an identical repeat would be answered from the previous call's whole-CU launch (square PUs)
+            "search_and_refine": timed(lambda: hm.pattern_search_and_refine(org, w, h, rf, (-64, -64), (64, 64), lam + next(tick), (0, 0))),
         }
     hm.release_plane(idr)
     print(json.dumps(out, indent=1))
