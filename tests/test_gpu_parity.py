@@ -404,19 +404,21 @@ def _cu_parts(S):
     return parts
 
 
+@pytest.mark.parametrize("bd", [8, 10])
 @pytest.mark.parametrize("fen,had", [(1, 1), (0, 1), (1, 0)])
-def test_whole_cu_speculation_is_exact(hm, fen, had):
+def test_whole_cu_speculation_is_exact(hm, fen, had, bd):
     """hmb200_pattern_search_and_refine in HM's call order: the 2Nx2N PU of a CU, then its 2NxN / Nx2N / AMP partitions.  The 2Nx2N
     call searches and refines the whole CU; the following calls are answered from it when window, predictor, lambda, position and
     pattern samples match - every answer must equal the oracle's for that PU.  Calls that do not match (another predictor, a changed
-    pattern) must take the per-PU path and be exact as well; the counters show which path ran."""
+    pattern) must take the per-PU path and be exact as well; the counters show which path ran.  8-bit planes run the byte-SIMD
+    kernels, 10-bit planes the scalar 16-bit ones."""
     W, H = 416, 240
-    f0, f1 = synth.luma_frame(W, H, 0, seed=91), synth.luma_frame(W, H, 1, seed=91)
+    f0, f1 = synth.luma_frame(W, H, 0, seed=91, bit_depth=bd), synth.luma_frame(W, H, 1, seed=91, bit_depth=bd)
     ref, o0, stride = padded(f0)
     O = Oracle(fen=fen, hadme=had)
     flags = (FLAG_FEN if fen else 0) | (FLAG_HADME if had else 0)
     rng = np.random.default_rng(6 + fen + 2 * had)
-    idr = hm.register_plane(ref, W, H, MARGIN, MARGIN, 8)
+    idr = hm.register_plane(ref, W, H, MARGIN, MARGIN, bd)
     try:
         for S, (cx, cy) in ((8, (72, 40)), (16, (160, 96)), (32, (224, 128)), (64, (128, 64)), (16, (400, 224)), (64, (0, 0))):
             cu = np.ascontiguousarray(f1[cy:cy + S, cx:cx + S].astype(np.int16))        # the CU's original block, stride S (TEncCu's buffer)
@@ -428,10 +430,10 @@ def test_whole_cu_speculation_is_exact(hm, fen, had):
             c0, l0, h0 = hm.one_call_stats()
             for (ox, oy, w, h) in _cu_parts(S):
                 roff = o0 + (cy + oy) * stride + cx + ox
-                got = hm.pattern_search_and_refine((cu, oy * S + ox, S), w, h, (ref, roff, stride), lt, rb, lam, pred, 8, flags)
+                got = hm.pattern_search_and_refine((cu, oy * S + ox, S), w, h, (ref, roff, stride), lt, rb, lam, pred, bd, flags)
                 org = np.ascontiguousarray(cu[oy:oy + h, ox:ox + w])
-                mv, sad = O.pattern_search((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred, 8)
-                assert got == (mv, sad) + O.pattern_search_frac((org, 0, w), w, h, (ref, roff, stride), mv, lam, pred, 8), (S, ox, oy, w, h)
+                mv, sad = O.pattern_search((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred, bd)
+                assert got == (mv, sad) + O.pattern_search_frac((org, 0, w), w, h, (ref, roff, stride), mv, lam, pred, bd), (S, ox, oy, w, h)
             c1, l1, h1 = hm.one_call_stats()
             n = len(_cu_parts(S))
             assert (c1 - c0, l1 - l0, h1 - h0) == (n, 1, n - 1), (S, c1 - c0, l1 - l0, h1 - h0)
@@ -440,14 +442,14 @@ def test_whole_cu_speculation_is_exact(hm, fen, had):
             roff = o0 + (cy + oy) * stride + cx + ox
             org = np.ascontiguousarray(cu[oy:oy + h, ox:ox + w])
             pred2 = (pred[0] + 3, pred[1] - 2)
-            got = hm.pattern_search_and_refine((cu, oy * S + ox, S), w, h, (ref, roff, stride), lt, rb, lam, pred2, 8, flags)
-            mv, sad = O.pattern_search((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred2, 8)
-            assert got == (mv, sad) + O.pattern_search_frac((org, 0, w), w, h, (ref, roff, stride), mv, lam, pred2, 8)
+            got = hm.pattern_search_and_refine((cu, oy * S + ox, S), w, h, (ref, roff, stride), lt, rb, lam, pred2, bd, flags)
+            mv, sad = O.pattern_search((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred2, bd)
+            assert got == (mv, sad) + O.pattern_search_frac((org, 0, w), w, h, (ref, roff, stride), mv, lam, pred2, bd)
             cu[oy + 1, ox + 1] ^= 0x3f
             org = np.ascontiguousarray(cu[oy:oy + h, ox:ox + w])
-            got = hm.pattern_search_and_refine((cu, oy * S + ox, S), w, h, (ref, roff, stride), lt, rb, lam, pred, 8, flags)
-            mv, sad = O.pattern_search((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred, 8)
-            assert got == (mv, sad) + O.pattern_search_frac((org, 0, w), w, h, (ref, roff, stride), mv, lam, pred, 8)
+            got = hm.pattern_search_and_refine((cu, oy * S + ox, S), w, h, (ref, roff, stride), lt, rb, lam, pred, bd, flags)
+            mv, sad = O.pattern_search((org, 0, w), w, h, (ref, roff, stride), lt, rb, lam, pred, bd)
+            assert got == (mv, sad) + O.pattern_search_frac((org, 0, w), w, h, (ref, roff, stride), mv, lam, pred, bd)
             assert hm.one_call_stats()[2] == h1                  # neither was answered from the CU launch
     finally:
         hm.release_plane(idr)

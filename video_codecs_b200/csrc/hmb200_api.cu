@@ -409,10 +409,14 @@ static int init_state_body(State& st, int device) {
   st.cu_cache.assign(CU_CACHE_ENTRIES, CuCacheEntry());
   st.cu_cache_next = 0;
   st.one_calls = st.cu_launches = st.cu_hits = 0;
-  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
-  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
-  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search_args<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
-  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search_args<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search_args<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search_args<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search_args<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
+  CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search_args<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
   st.one_seq = 0;
   st.one_fast = getenv("HMB200_NO_ONE_FAST") == nullptr;
   CUDA_TRY(cudaFuncSetAttribute(k_one_search<true, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
@@ -1690,8 +1694,9 @@ static int cu_speculation(const hmb200_pattern* key, const int16_t* ref_at_pu, c
   *served = false;
   int rx, ry;
   Plane* pr = find_plane_by_host(ref_at_pu, &rx, &ry);
-  if (!pr || !key->roi || key->bit_depth != 8 || pr->d.bytes_per_sample != 1 || pr->d.bit_depth != 8 || !supported_pu(key->width, key->height))
+  if (!pr || !key->roi || key->bit_depth != pr->d.bit_depth || !supported_pu(key->width, key->height))
     return HMB200_OK;                                   // the per-PU path handles (or rejects) it
+  const bool bytes = pr->d.bytes_per_sample == 1;       // 8-bit plane: byte-SIMD kernels; 9..14-bit: the scalar 16-bit ones
   const int plane = (int)(pr - &G.planes[0]);
   const int w = key->width, h = key->height;
   // 1. an answer computed by an earlier CU launch?
@@ -1734,7 +1739,7 @@ static int cu_speculation(const hmb200_pattern* key, const int16_t* ref_at_pu, c
   const int nx = t.rb_x - t.lt_x + 1, ny = t.rb_y - t.lt_y + 1;
   const int rows = (S == 64 && fen) ? S / 2 : S;
   const int col0 = rx + pr->d.margin_x + t.lt_x;
-  const int smem = rows * one_search_row_bytes(true, col0, nx, S) + rows * S;
+  const int smem = rows * one_search_row_bytes(bytes, col0, nx, S) + rows * S * (bytes ? 1 : 2);
   if (smem > ONE_SMEM_MAX) return HMB200_OK;
   const int ei = G.cu_cache_next;
   CuCacheEntry& e = G.cu_cache[ei];
@@ -1745,7 +1750,7 @@ static int cu_speculation(const hmb200_pattern* key, const int16_t* ref_at_pu, c
     int16_t* dst = e.pat + (size_t)y * S;
     for (int x = 0; x < S; x++) { dst[x] = src[x]; all |= src[x]; }
   }
-  if (all & ~0xff) return HMB200_OK;                    // e.g. the signed bi-prediction pattern: per-PU path
+  if (all & ~((1 << pr->d.bit_depth) - 1)) return HMB200_OK;   // outside the sample range (the signed bi-prediction pattern): per-PU path
   get_plane(plane);                                     // orders a pending upload of the plane before this call's kernels
   const OneBack first = next_one_back();
   OneBack back = first;
@@ -1758,17 +1763,23 @@ static int cu_speculation(const hmb200_pattern* key, const int16_t* ref_at_pu, c
   if (S <= 16) {
     OnePattern arg;
     memcpy(arg.px, e.pat, (size_t)S * S * sizeof(int16_t));
-    if (S == 8) k_one_cu_search_args<8><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, arg, d_keys, d_ticket, d_out, pr->d);
-    else        k_one_cu_search_args<16><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, arg, d_keys, d_ticket, d_out, pr->d);
-    k_one_cu_frac_args<<<np, S == 8 ? 128 : 288, one_frac_smem(S, S), G.stream>>>(t, S, arg, d_out, pr->d, had, back);
+    if (S == 8 && bytes)       k_one_cu_search_args<8, true><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, arg, d_keys, d_ticket, d_out, pr->d);
+    else if (S == 8)           k_one_cu_search_args<8, false><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, arg, d_keys, d_ticket, d_out, pr->d);
+    else if (bytes)            k_one_cu_search_args<16, true><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, arg, d_keys, d_ticket, d_out, pr->d);
+    else                       k_one_cu_search_args<16, false><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, arg, d_keys, d_ticket, d_out, pr->d);
+    if (bytes) k_one_cu_frac_args<uint8_t><<<np, S == 8 ? 128 : 288, one_frac_smem(S, S), G.stream>>>(t, S, arg, d_out, pr->d, had, back);
+    else       k_one_cu_frac_args<int16_t><<<np, S == 8 ? 128 : 288, one_frac_smem(S, S), G.stream>>>(t, S, arg, d_out, pr->d, had, back);
   } else {
     char* hrec = G.one_host;
     memcpy(hrec + ONE_HEAD, e.pat, (size_t)S * S * sizeof(int16_t));
     CUDA_TRY(cudaMemcpyAsync(G.one_dev + ONE_HEAD, hrec + ONE_HEAD, (size_t)S * S * sizeof(int16_t), cudaMemcpyHostToDevice, G.stream));
     const int16_t* d_pat = reinterpret_cast<const int16_t*>(G.one_dev + ONE_HEAD);
-    if (S == 32) k_one_cu_search<32><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, d_keys, d_ticket, d_out, d_pat, pr->d);
-    else         k_one_cu_search<64><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, d_keys, d_ticket, d_out, d_pat, pr->d);
-    k_one_cu_frac<<<np, ONE_FRAC_THREADS_MAX, one_frac_smem(S, S), G.stream>>>(t, S, d_pat, d_out, pr->d, had, back);
+    if (S == 32 && bytes)      k_one_cu_search<32, true><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, d_keys, d_ticket, d_out, d_pat, pr->d);
+    else if (S == 32)          k_one_cu_search<32, false><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, d_keys, d_ticket, d_out, d_pat, pr->d);
+    else if (bytes)            k_one_cu_search<64, true><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, d_keys, d_ticket, d_out, d_pat, pr->d);
+    else                       k_one_cu_search<64, false><<<ny, ONE_SEARCH_THREADS, smem, G.stream>>>(t, fen, d_keys, d_ticket, d_out, d_pat, pr->d);
+    if (bytes) k_one_cu_frac<uint8_t><<<np, ONE_FRAC_THREADS_MAX, one_frac_smem(S, S), G.stream>>>(t, S, d_pat, d_out, pr->d, had, back);
+    else       k_one_cu_frac<int16_t><<<np, ONE_FRAC_THREADS_MAX, one_frac_smem(S, S), G.stream>>>(t, S, d_pat, d_out, pr->d, had, back);
   }
   G.launches += 2;
   G.cu_launches++;

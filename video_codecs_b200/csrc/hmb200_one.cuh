@@ -371,7 +371,8 @@ k_one_search_args(const SearchTask t, hmb200_pu_result seed, const __grid_consta
 // Every partition is a union of cells of a 4 x 4 grid over the CU (2 x 2 for an 8x8 CU), so a candidate's 13 SADs come
 // from 16 cell sums - kept apart for even and odd rows, because under FEN a PU taller than 8 rows counts its even rows
 // twice and a shorter one counts all rows (TEncSearch.cpp:3804-3810; PU offsets are multiples of 4, so PU-relative and
-// CU-relative row parity agree).  8-bit planes and patterns only (VABSDIFF4); anything else takes the per-PU path.
+// CU-relative row parity agree).  BYTES: 8-bit plane, VABSDIFF4 on funnel-shifted words; otherwise (9..14-bit planes) scalar
+// 16-bit samples.  Patterns that leave the sample range (bi-prediction's 2*org - pred) take the per-PU path.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int ONE_CU_MAX_PUS = 13;
 __host__ __device__ inline int one_cu_pus(int S) { return S == 8 ? 5 : 13; }
@@ -392,7 +393,7 @@ __host__ __device__ inline void one_cu_part(int S, int p, int* ox, int* oy, int*
 }
 
 // key[p] / ticket as in one_search_body; out[p]: (rcMv, ruiSAD) of partition p.  t: the 2Nx2N task (w = h = S); fen: FLAG_FEN.
-template <int S>
+template <int S, bool BYTES>
 __device__ __forceinline__ void one_cu_search_body(const SearchTask& t, int fen, unsigned long long* __restrict__ keys, uint32_t* __restrict__ ticket,
                                                    hmb200_pu_result* __restrict__ out, const int16_t* __restrict__ pattern, const DevPlane& ref_plane) {
   constexpr int NB = (S == 8) ? 2 : 4;           // cells per CU edge
@@ -409,9 +410,9 @@ __device__ __forceinline__ void one_cu_search_body(const SearchTask& t, int fen,
   const int cy = blockIdx.x, y = t.lt_y + cy;
   const int col0 = t.ref_x + ref_plane.margin_x + t.lt_x;
   const int row0 = t.ref_y + ref_plane.margin_y + y;
-  const int rp = one_search_row_bytes(true, col0, nx, S);
+  const int rp = one_search_row_bytes(BYTES, col0, nx, S);
   uint8_t* s_org8 = one_smem + rows * rp;
-  {
+  if (BYTES) {
     const int nvec = rp / 16 - 1, vec0 = col0 >> 4;
     const uint8_t* base = reinterpret_cast<const uint8_t*>(ref_plane.base);
     for (int i = threadIdx.x; i < rows * (nvec + 1); i += blockDim.x) {
@@ -425,6 +426,19 @@ __device__ __forceinline__ void one_cu_search_body(const SearchTask& t, int fen,
       const int r = i / S, c = i - r * S;
       s_org8[i] = (uint8_t)pattern[(r * step) * S + c];
     }
+  } else {
+    int16_t* s_ref = reinterpret_cast<int16_t*>(one_smem);
+    int16_t* s_org = reinterpret_cast<int16_t*>(s_org8);
+    const int span = nx + S - 1;
+    const int16_t* base = reinterpret_cast<const int16_t*>(ref_plane.base);
+    for (int i = threadIdx.x; i < rows * span; i += blockDim.x) {
+      const int r = i / span, c = i - r * span;
+      s_ref[r * (rp / 2) + c] = base[(size_t)(row0 + r * step) * ref_plane.pitch + col0 + c];
+    }
+    for (int i = threadIdx.x; i < rows * S; i += blockDim.x) {
+      const int r = i / S, c = i - r * S;
+      s_org[i] = pattern[(r * step) * S + c];
+    }
   }
   __syncthreads();
   unsigned long long best[NP];
@@ -432,31 +446,56 @@ __device__ __forceinline__ void one_cu_search_body(const SearchTask& t, int fen,
   for (int p = 0; p < NP; p++) best[p] = ~0ull;
   const uint32_t* org32 = reinterpret_cast<const uint32_t*>(s_org8);
   for (int cx = threadIdx.x; cx < nx; cx += blockDim.x) {
-    const int b = (col0 & 15) + cx, sh = (b & 3) * 8;
-    const uint32_t* row = reinterpret_cast<const uint32_t*>(one_smem) + (b >> 2);
     uint32_t ce[NB][NB], co[NB][NB];             // cell sums over even / odd rows
 #pragma unroll
     for (int i = 0; i < NB; i++)
 #pragma unroll
       for (int j = 0; j < NB; j++) { ce[i][j] = 0; co[i][j] = 0; }
+    if (BYTES) {
+      const int b = (col0 & 15) + cx, sh = (b & 3) * 8;
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(one_smem) + (b >> 2);
 #pragma unroll
-    for (int rb = 0; rb < NB; rb++) {
+      for (int rb = 0; rb < NB; rb++) {
 #pragma unroll 1
-      for (int rr = 0; rr < BS; rr += 2) {
+        for (int rr = 0; rr < BS; rr += 2) {
 #pragma unroll
-        for (int par = 0; par < 2; par++) {
-          if (par == 1 && !odd_rows) continue;
-          const int r = (rb * BS + rr + par) / step;                    // staged row index
-          const uint32_t* q = row + r * (rp / 4);
-          const uint32_t* o = org32 + r * WW;
-          uint32_t lo = q[0];
+          for (int par = 0; par < 2; par++) {
+            if (par == 1 && !odd_rows) continue;
+            const int r = (rb * BS + rr + par) / step;                    // staged row index
+            const uint32_t* q = row + r * (rp / 4);
+            const uint32_t* o = org32 + r * WW;
+            uint32_t lo = q[0];
 #pragma unroll
-          for (int g = 0; g < WW; g++) {
-            const uint32_t hi = q[g + 1];
-            const uint32_t v = __funnelshift_r(lo, hi, sh);
-            if (par == 0) ce[rb][g / BW] = sad4_acc(v, o[g], ce[rb][g / BW]);
-            else          co[rb][g / BW] = sad4_acc(v, o[g], co[rb][g / BW]);
-            lo = hi;
+            for (int g = 0; g < WW; g++) {
+              const uint32_t hi = q[g + 1];
+              const uint32_t v = __funnelshift_r(lo, hi, sh);
+              if (par == 0) ce[rb][g / BW] = sad4_acc(v, o[g], ce[rb][g / BW]);
+              else          co[rb][g / BW] = sad4_acc(v, o[g], co[rb][g / BW]);
+              lo = hi;
+            }
+          }
+        }
+      }
+    } else {
+      const int16_t* s_ref = reinterpret_cast<const int16_t*>(one_smem) + cx;
+      const int16_t* s_org = reinterpret_cast<const int16_t*>(s_org8);
+#pragma unroll
+      for (int rb = 0; rb < NB; rb++) {
+#pragma unroll 1
+        for (int rr = 0; rr < BS; rr += 2) {
+#pragma unroll
+          for (int par = 0; par < 2; par++) {
+            if (par == 1 && !odd_rows) continue;
+            const int r = (rb * BS + rr + par) / step;
+            const int16_t* q = s_ref + r * (rp / 2);
+            const int16_t* o = s_org + r * S;
+#pragma unroll
+            for (int cb = 0; cb < NB; cb++) {
+              uint32_t a = 0;
+#pragma unroll 8
+              for (int c = 0; c < BS; c++) a += (uint32_t)abs((int)o[cb * BS + c] - (int)q[cb * BS + c]);
+              if (par == 0) ce[rb][cb] += a; else co[rb][cb] += a;
+            }
           }
         }
       }
@@ -474,7 +513,7 @@ __device__ __forceinline__ void one_cu_search_body(const SearchTask& t, int fen,
 #pragma unroll
         for (int j = 0; j < NB; j++)
           if (i * BS >= oy && i * BS < oy + h && j * BS >= ox && j * BS < ox + w) { e += ce[i][j]; od += co[i][j]; }
-      const uint32_t sad = (fen && h > 8) ? (e << 1) : (e + od);
+      const uint32_t sad = ((fen && h > 8) ? (e << 1) : (e + od)) >> (ref_plane.bit_depth - 8);
       const unsigned long long k = make_key(sad + mvc, idx);
       best[p] = k < best[p] ? k : best[p];
     }
@@ -514,22 +553,22 @@ __device__ __forceinline__ void one_cu_search_body(const SearchTask& t, int fen,
   if (threadIdx.x == 0) *ticket = 0;
 }
 
-template <int S>
+template <int S, bool BYTES>
 __global__ void __launch_bounds__(ONE_SEARCH_THREADS_MAX)
 k_one_cu_search(const SearchTask t, int fen, unsigned long long* __restrict__ keys, uint32_t* __restrict__ ticket, hmb200_pu_result* __restrict__ out,
                 const int16_t* __restrict__ pattern, DevPlane ref_plane) {
-  one_cu_search_body<S>(t, fen, keys, ticket, out, pattern, ref_plane);
+  one_cu_search_body<S, BYTES>(t, fen, keys, ticket, out, pattern, ref_plane);
 }
-template <int S>
+template <int S, bool BYTES>
 __global__ void __launch_bounds__(ONE_SEARCH_THREADS_MAX)
 k_one_cu_search_args(const SearchTask t, int fen, const __grid_constant__ OnePattern pat, unsigned long long* __restrict__ keys,
                      uint32_t* __restrict__ ticket, hmb200_pu_result* __restrict__ out, DevPlane ref_plane) {
-  one_cu_search_body<S>(t, fen, keys, ticket, out, pat.px, ref_plane);
+  one_cu_search_body<S, BYTES>(t, fen, keys, ticket, out, pat.px, ref_plane);
 }
 
 // refinement of every partition: CTA p refines partition p at the vector k_one_cu_search left in out[p] and reports to host slot p
 // (two 16-byte records, 32 bytes per slot)
-template <bool ARGS>
+template <typename RefT>
 __device__ __forceinline__ void one_cu_frac_body(const SearchTask& t, int S, const int16_t* __restrict__ pattern, hmb200_pu_result* __restrict__ out,
                                                  const DevPlane& ref_plane, int use_had, const OneBack& back) {
   extern __shared__ __align__(16) int16_t one_smem16[];
@@ -539,21 +578,23 @@ __device__ __forceinline__ void one_cu_frac_body(const SearchTask& t, int S, con
   SearchTask tp = t;
   tp.ref_x += ox; tp.ref_y += oy; tp.w = w; tp.h = h;
   hmb200_pu_result res = out[p];
-  one_frac_body<uint8_t>(tp, res, pattern + oy * S + ox, ref_plane, use_had, one_smem16, S);
+  one_frac_body<RefT>(tp, res, pattern + oy * S + ox, ref_plane, use_had, one_smem16, S);
   if (threadIdx.x == 0) {
     OneBack slot = back;
     slot.host_a = back.host_a + 2 * p; slot.host_b = back.host_a + 2 * p + 1;
     one_report(slot, res);
   }
 }
+template <typename RefT>
 __global__ void __launch_bounds__(ONE_FRAC_THREADS_MAX)
 k_one_cu_frac(const SearchTask t, int S, const int16_t* __restrict__ pattern, hmb200_pu_result* __restrict__ out, DevPlane ref_plane, int use_had, OneBack back) {
-  one_cu_frac_body<false>(t, S, pattern, out, ref_plane, use_had, back);
+  one_cu_frac_body<RefT>(t, S, pattern, out, ref_plane, use_had, back);
 }
+template <typename RefT>
 __global__ void __launch_bounds__(ONE_FRAC_THREADS_MAX)
 k_one_cu_frac_args(const SearchTask t, int S, const __grid_constant__ OnePattern pat, hmb200_pu_result* __restrict__ out, DevPlane ref_plane, int use_had,
                    OneBack back) {
-  one_cu_frac_body<true>(t, S, pat.px, out, ref_plane, use_had, back);
+  one_cu_frac_body<RefT>(t, S, pat.px, out, ref_plane, use_had, back);
 }
 
 // ends a call whose last kernel is one of the older ones (TZ search without refinement): one thread reports the record
