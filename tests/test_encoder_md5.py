@@ -50,6 +50,24 @@ def test_encoder_bitstream_md5_matches_reference(tmp_path, frames, mode, merge):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("knob", ["HMB200_NO_SPECULATION", "HMB200_NO_ONE_FAST"])
+def test_encoder_bitstream_md5_same_without_the_latency_paths(tmp_path, knob):
+    """The in-encoder 1:1 path has three forms - whole-CU speculation (default), one launch set per PU (HMB200_NO_SPECULATION=1),
+    round 1's kernels with a copy + stream synchronisation per call (HMB200_NO_ONE_FAST=1): the bitstream must not depend on it."""
+    _need_binary()
+    frames = 3
+    gold = json.load(open(GOLD))[str(frames)]
+    yuv, binf = str(tmp_path / "clip.yuv"), str(tmp_path / "out.bin")
+    meg.write_clip(yuv, frames)
+    env = dict(os.environ, HMB200_SHIM="gpu", HMB200_SHIM_MERGE="0")
+    env[knob] = "1"
+    p = subprocess.run([BIN] + meg.encoder_args(CFG, yuv, frames, binf), capture_output=True, text=True, env=env, timeout=1500)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert " 0 were answered from one" in p.stderr, "the knob did not switch the speculation off"
+    assert hashlib.md5(open(binf, "rb").read()).hexdigest() == gold["bitstream_md5"]
+
+
+@pytest.mark.gpu
 def test_encoder_bitstream_md5_1080p_prefix(tmp_path):
     """Same check at BASELINE.json configs[2]'s geometry: 1920x1080 (ConformanceWindowMode=1 -> 1088 coded rows), I + P."""
     _need_binary()

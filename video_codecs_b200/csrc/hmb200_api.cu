@@ -405,7 +405,6 @@ static int init_state_body(State& st, int device) {
     CUDA_TRY(cudaMemcpy(st.one_dev + ONE_KEY, init, sizeof(init), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemset(st.one_dev + ONE_CU_KEYS, 0xff, 128));
   }
-  st.speculate = st.one_fast && getenv("HMB200_NO_SPECULATION") == nullptr;
   st.cu_cache.assign(CU_CACHE_ENTRIES, CuCacheEntry());
   st.cu_cache_next = 0;
   st.one_calls = st.cu_launches = st.cu_hits = 0;
@@ -419,6 +418,7 @@ static int init_state_body(State& st, int device) {
   CUDA_TRY(cudaFuncSetAttribute(k_one_cu_search_args<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
   st.one_seq = 0;
   st.one_fast = getenv("HMB200_NO_ONE_FAST") == nullptr;
+  st.speculate = st.one_fast && getenv("HMB200_NO_SPECULATION") == nullptr;
   CUDA_TRY(cudaFuncSetAttribute(k_one_search<true, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
   CUDA_TRY(cudaFuncSetAttribute(k_one_search_args<true, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
   CUDA_TRY(cudaFuncSetAttribute(k_one_search<false, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONE_SMEM_MAX));
