@@ -401,6 +401,10 @@ def _cu_parts(S):
     if S > 8:
         parts += [(0, 0, S, q), (0, q, S, S - q), (0, 0, S, S - q), (0, S - q, S, q),
                   (0, 0, q, S), (q, 0, S - q, S), (0, 0, S - q, S), (S - q, 0, q, S)]
+    if S == 16:      # HM goes on with the four 8x8 child CUs; the 16x16 launch carries their PUs as well
+        for cy in (0, 8):
+            for cx in (0, 8):
+                parts += [(cx + ox, cy + oy, w, h) for (ox, oy, w, h) in _cu_parts(8)]
     return parts
 
 

@@ -46,10 +46,11 @@ constexpr int N_SIDE = 4;
 // layout of the per-call record of the 1:1 entries (host page-locked copy and device copy): offsets in bytes
 constexpr size_t ONE_KEY = 0, ONE_TICKET = 8, ONE_RESULT = 16, ONE_TASK = 64, ONE_TZ = 128, ONE_HEAD = 256;
 // the two 16-byte records the call's last kernel writes into mapped host memory (State::one_back, hmb200_one.cuh OneBack)
-constexpr size_t BACK_A = 0, BACK_B = 16, BACK_CU = 64, BACK_BYTES = 4096;
+constexpr size_t BACK_A = 0, BACK_B = 16, BACK_CU = 64, BACK_BYTES = 16384;
 // after the pattern rows of the per-call record: argmin keys and integer results of a speculated CU's partitions (hmb200_one.cuh)
-constexpr size_t ONE_CU_KEYS = ONE_HEAD + 64 * 64 * sizeof(int16_t), ONE_CU_OUT = ONE_CU_KEYS + 128, ONE_DEV_BYTES = ONE_CU_OUT + 13 * 32;
-constexpr int CU_CACHE_ENTRIES = 8;                    // one per reference picture a PU loop walks over (BACK_CU + 8 * 13 * 32 <= BACK_BYTES)
+constexpr size_t ONE_CU_KEYS = ONE_HEAD + 64 * 64 * sizeof(int16_t), ONE_CU_OUT = ONE_CU_KEYS + 512, ONE_DEV_BYTES = ONE_CU_OUT + ONE_CU_MAX_PUS * 32;
+constexpr int CU_CACHE_ENTRIES = 8;                    // one per reference picture a PU loop walks over
+static_assert(BACK_CU + CU_CACHE_ENTRIES * ONE_CU_MAX_PUS * 32 <= BACK_BYTES && ONE_CU_MAX_PUS * 8 <= 512, "1:1 report / key areas");
 
 // What a speculated CU launch computed (hmb200_one.cuh, k_one_cu_search / k_one_cu_frac): every partition of the CU searched and
 // refined with the 2Nx2N call's window, predictor and lambda.  A later 1:1 call is served from it iff plane, position, window,
@@ -59,8 +60,8 @@ struct CuCacheEntry {
   int plane = -1, rx = 0, ry = 0, S = 0, flags = 0;
   int lt_x = 0, lt_y = 0, rb_x = 0, rb_y = 0, pred_x = 0, pred_y = 0;
   uint32_t lambda = 0, seq = 0;
-  bool got[13] = {false};
-  hmb200_pu_result res[13];
+  bool got[ONE_CU_MAX_PUS] = {false};
+  hmb200_pu_result res[ONE_CU_MAX_PUS];
   int16_t pat[64 * 64];                                // the CU's original block, dense rows of S samples
 };
 
@@ -403,7 +404,7 @@ static int init_state_body(State& st, int device) {
     // argmin key = ~0, ticket = 0: the state k_one_search leaves behind after every call
     unsigned long long init[2] = {~0ull, 0ull};
     CUDA_TRY(cudaMemcpy(st.one_dev + ONE_KEY, init, sizeof(init), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemset(st.one_dev + ONE_CU_KEYS, 0xff, 128));
+    CUDA_TRY(cudaMemset(st.one_dev + ONE_CU_KEYS, 0xff, 512));
   }
   st.cu_cache.assign(CU_CACHE_ENTRIES, CuCacheEntry());
   st.cu_cache_next = 0;

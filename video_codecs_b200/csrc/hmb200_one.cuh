@@ -374,20 +374,24 @@ k_one_search_args(const SearchTask t, hmb200_pu_result seed, const __grid_consta
 // CU-relative row parity agree).  BYTES: 8-bit plane, VABSDIFF4 on funnel-shifted words; otherwise (9..14-bit planes) scalar
 // 16-bit samples.  Patterns that leave the sample range (bi-prediction's 2*org - pred) take the per-PU path.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int ONE_CU_MAX_PUS = 13;
-__host__ __device__ inline int one_cu_pus(int S) { return S == 8 ? 5 : 13; }
-// partition p of an S x S CU: offset and size
+// A 16x16 CU also carries the 5 PUs of each of its four 8x8 child CUs (its 4x4-sample cells are theirs too): in the test clip 26,743
+// of the 32,400 2Nx2N calls of 8x8 CUs arrive with their parent's window, predictor and lambda.
+constexpr int ONE_CU_MAX_PUS = 33;
+__host__ __device__ constexpr int one_cu_pus(int S) { return S == 8 ? 5 : S == 16 ? 33 : 13; }
+// partition p of an S x S CU: offset and size (p >= 13, S = 16: partition (p - 13) % 5 of child CU (p - 13) / 5)
 __host__ __device__ inline void one_cu_part(int S, int p, int* ox, int* oy, int* w, int* h) {
+  int bx = 0, by = 0;
+  if (p >= 13) { const int c = (p - 13) / 5; p = (p - 13) % 5; bx = (c & 1) * (S / 2); by = (c >> 1) * (S / 2); S = S / 2; }
   const int H2 = S / 2, Q = S / 4;
-  int x = 0, y = 0, ww = S, hh = S;
+  int x = bx, y = by, ww = S, hh = S;
   switch (p) {
     case 0: break;
-    case 1: hh = H2; break;                 case 2: y = H2; hh = H2; break;              // 2NxN
-    case 3: ww = H2; break;                 case 4: x = H2; ww = H2; break;              // Nx2N
-    case 5: hh = Q; break;                  case 6: y = Q; hh = S - Q; break;            // 2NxnU
-    case 7: hh = S - Q; break;              case 8: y = S - Q; hh = Q; break;            // 2NxnD
-    case 9: ww = Q; break;                  case 10: x = Q; ww = S - Q; break;           // nLx2N
-    case 11: ww = S - Q; break;             default: x = S - Q; ww = Q; break;           // nRx2N
+    case 1: hh = H2; break;                 case 2: y += H2; hh = H2; break;             // 2NxN
+    case 3: ww = H2; break;                 case 4: x += H2; ww = H2; break;             // Nx2N
+    case 5: hh = Q; break;                  case 6: y += Q; hh = S - Q; break;           // 2NxnU
+    case 7: hh = S - Q; break;              case 8: y += S - Q; hh = Q; break;           // 2NxnD
+    case 9: ww = Q; break;                  case 10: x += Q; ww = S - Q; break;          // nLx2N
+    case 11: ww = S - Q; break;             default: x += S - Q; ww = Q; break;          // nRx2N
   }
   *ox = x; *oy = y; *w = ww; *h = hh;
 }
@@ -400,7 +404,7 @@ __device__ __forceinline__ void one_cu_search_body(const SearchTask& t, int fen,
   constexpr int BS = S / NB;                     // cell edge in samples (4, 4, 8, 16)
   constexpr int BW = BS / 4;                     // ... in 32-bit words
   constexpr int WW = S / 4;
-  constexpr int NP = (S == 8) ? 5 : 13;
+  constexpr int NP = one_cu_pus(S);
   extern __shared__ __align__(16) uint8_t one_smem[];
   __shared__ unsigned long long s_best[NP][ONE_SEARCH_THREADS_MAX / 32];
   __shared__ int s_last;
