@@ -303,8 +303,8 @@ int  hmb200_pattern_search_frac(int lossless, const hmb200_pattern* key, const i
  * The in-encoder frontend calls this from the xPatternSearch forwarder and hands the refinement's outputs to the
  * xPatternSearchFracDIF forwarder that follows (integration/hm_shim.cpp); flags: HMB200_FLAG_FEN | HMB200_FLAG_HADME.
  * Results are those of the two separate entries, always.  Internally a call for a square PU of 8 / 16 / 32 / 64 samples
- * also searches and refines the other partitions of a CU of that size at that position (the PUs HM's partition loop
- * asks for next, TLibCommon/TComDataCU.cpp:1893-1931) and a later call is answered from that launch iff its window, predictor,
+ * also searches and refines the other partitions of a CU of that size at that position - and of the four 8x8 child CUs of a
+ * 16x16 CU - (the PUs HM's partition loop asks for next, TLibCommon/TComDataCU.cpp:1893-1931) and a later call is answered from that launch iff its window, predictor,
  * lambda, flags, position and pattern samples are identical to the launch's; hmb200_one_call_stats counts both. */
 int  hmb200_pattern_search_and_refine(const hmb200_pattern* key, const int16_t* ref_at_pu, int ref_stride,
                                       hmb200_mv lt, hmb200_mv rb, const hmb200_cost_state* cs, int flags,
