@@ -111,3 +111,18 @@ def test_python_canonical_job_list_equals_the_library_builder():
     for (w, h, sr, pred) in [(416, 240, 64, (0, 0)), (320, 256, 128, (6, -3)), (200, 136, 16, (-300, 500))]:
         assert np.array_equal(hm.build_canonical_jobs(w, h, sr, 777, pred=pred), py_canonical_jobs(w, h, sr, 777, pred))
     assert np.array_equal(hm.build_canonical_jobs(416, 240, 64, 5, ctu_first=9, ctu_count=2), py_canonical_jobs(416, 240, 64, 5, ctu_first=9, ctu_count=2))
+
+
+def test_whole_cu_partition_geometry_matches_the_reference_table(tmp_path):
+    """one_cu_part / one_cu_pus (hmb200_one.cuh), which the whole-CU kernels and the host-side answer cache share, against an
+    independent restatement of TComDataCU::getPartIndexAndSize (tests/cpp/one_cu_part_test.cu): host code only, built with nvcc."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "one_cu_part_test")
+    subprocess.check_call([nvcc, "-std=c++17", "-I", os.path.join(ROOT, "video_codecs_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
+                           "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe, os.path.join(ROOT, "tests", "cpp", "one_cu_part_test.cu")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
